@@ -1,0 +1,125 @@
+"""CPU oracle for the gated Kronecker fusion path.  TEST INFRASTRUCTURE ONLY.
+
+Functional restatement (torch-CPU fp32) of the reference's
+`MICCAI-2022/fusion.py` (`BilinearFusion` :6-63, `TrilinearFusion_A` :66-132,
+`TrilinearFusion_B` :135-201), `utils.py:239-244` (`init_max_weights`) and
+`KD_loss.py:7-17` (`DistillKL`).  The Kronecker tensor IS materialised here, on
+purpose: this is the checker for the never-materialise CUDA kernels.  Only
+`tests/`, `__graft_entry__.smoke()` and `bench.py`'s CPU legs may import it.
+
+Parity status: PINNED against the unmodified reference modules through the
+fixtures `oracle/make_golden.py` writes under `tests/golden/` (eval mode, and
+train mode with dropout p=0 so BatchNorm batch statistics are covered; torch's
+dropout mask stream is device/version specific, so masks themselves are
+"parity unpinned" -- see DESIGN.md).
+
+State dicts use the reference's key names (`linear_h1.0.weight`,
+`linear_z1.weight`, `encoder1.0.weight`, `encoder1.1.running_mean`, ...).
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+import torch.nn.functional as F
+
+
+def init_max_weights_(sd: dict, generator: torch.Generator | None = None) -> None:
+    """utils.py:239-244 applied to a state dict: every nn.Linear weight ~
+    N(0, 1/sqrt(fan_in)), bias 0.  Linear layers are the 2-D `*.weight` entries
+    (nn.Bilinear weights are 3-D, BatchNorm weights 1-D: both keep torch defaults)."""
+    for k in list(sd.keys()):
+        if k.endswith("weight") and sd[k].dim() == 2:
+            stdv = 1.0 / math.sqrt(sd[k].size(1))
+            sd[k].normal_(0, stdv, generator=generator)
+            sd[k[:-6] + "bias"].zero_()
+
+
+def _gate(sd, tag, own, a, b, gated, use_bilinear):
+    """One gated multimodal unit, fusion.py:41-46: h = ReLU(Linear(own));
+    z = Bilinear(a, b) or Linear(cat(a, b)); o = ReLU(Linear(sigmoid(z) * h)).
+    (linear_o's trailing Dropout is identity in eval / p=0.)"""
+    if gated:
+        h = torch.relu(F.linear(own, sd[f"linear_h{tag}.0.weight"], sd[f"linear_h{tag}.0.bias"]))
+        if use_bilinear:
+            z = F.bilinear(a, b, sd[f"linear_z{tag}.weight"], sd[f"linear_z{tag}.bias"])
+        else:
+            z = F.linear(torch.cat((a, b), dim=1), sd[f"linear_z{tag}.0.weight"], sd[f"linear_z{tag}.0.bias"])
+        pre = torch.sigmoid(z) * h
+    else:
+        pre = own
+    return torch.relu(F.linear(pre, sd[f"linear_o{tag}.0.weight"], sd[f"linear_o{tag}.0.bias"]))
+
+
+def _append_one(o):
+    """fusion.py:56-57 -- constant 1 in the LAST slot of each factor."""
+    return torch.cat((o, torch.ones(o.shape[0], 1, dtype=o.dtype)), 1)
+
+
+def kron_rows(*factors):
+    """fusion.py:58 / :126-127 -- batched outer product flattened row-major over
+    (i, j[, l]): out[b, (i*(d2+1)+j)*(d3+1)+l]."""
+    out = factors[0]
+    for f in factors[1:]:
+        out = torch.bmm(out.unsqueeze(2), f.unsqueeze(1)).flatten(start_dim=1)
+    return out
+
+
+def _bn(sd, name, x, training):
+    """nn.BatchNorm1d defaults (momentum 0.1, eps 1e-5); mutates running stats
+    in `sd` when training, as the module does."""
+    if training:
+        sd[f"{name}.num_batches_tracked"] += 1
+    return F.batch_norm(x, sd[f"{name}.running_mean"], sd[f"{name}.running_var"],
+                        sd[f"{name}.weight"], sd[f"{name}.bias"], training, 0.1, 1e-5)
+
+
+def bilinear_fusion_forward(sd, vec1, vec2, *, skip=1, use_bilinear=1, gate1=1, gate2=1,
+                            training=False):
+    """BilinearFusion.forward, fusion.py:36-63, with every Dropout as identity
+    (eval mode, or train mode with dropout_rate=0)."""
+    vec1 = torch.relu(vec1)                 # :38
+    vec2 = torch.relu(vec2)                 # :39
+    o1 = _gate(sd, 1, vec1, vec1, vec2, gate1, use_bilinear)
+    o2 = _gate(sd, 2, vec2, vec1, vec2, gate2, use_bilinear)
+    o1, o2 = _append_one(o1), _append_one(o2)
+    o12 = kron_rows(o1, o2)                 # :58
+    out = F.linear(o12, sd["encoder1.0.weight"], sd["encoder1.0.bias"])
+    out = torch.relu(_bn(sd, "encoder1.1", out, training))
+    if skip:
+        out = torch.cat((out, o1, o2), 1)   # :61
+    out = F.linear(out, sd["encoder2.0.weight"], sd["encoder2.0.bias"])
+    return torch.relu(_bn(sd, "encoder2.1", out, training))
+
+
+def trilinear_fusion_forward(sd, vec1, vec2, vec3, *, variant="A", skip=1, use_bilinear=1,
+                             gate1=1, gate2=1, gate3=1):
+    """TrilinearFusion_A.forward (fusion.py:99-132) / _B (:168-201), Dropout as
+    identity.  No input ReLU, no BatchNorm.  Variant B gates the graph branch
+    with (vec2, vec1) instead of (vec2, vec3) (:179 vs :110)."""
+    o1 = _gate(sd, 1, vec1, vec1, vec3, gate1, use_bilinear)
+    if variant == "A":
+        o2 = _gate(sd, 2, vec2, vec2, vec3, gate2, use_bilinear)
+    else:
+        o2 = _gate(sd, 2, vec2, vec2, vec1, gate2, use_bilinear)
+    o3 = _gate(sd, 3, vec3, vec1, vec3, gate3, use_bilinear)
+    o1, o2, o3 = _append_one(o1), _append_one(o2), _append_one(o3)
+    o123 = kron_rows(o1, o2, o3)            # :126-127
+    out = torch.relu(F.linear(o123, sd["encoder1.0.weight"], sd["encoder1.0.bias"]))
+    if skip:
+        out = torch.cat((out, o1, o2, o3), 1)
+    return torch.relu(F.linear(out, sd["encoder2.0.weight"], sd["encoder2.0.bias"]))
+
+
+def kron_linear(factors, weight, bias):
+    """The contraction the CUDA kernel replaces: (append-1 Kronecker rows) @ W^T + b,
+    computed in float64 from fp32 inputs (factors WITHOUT the appended 1)."""
+    aug = [_append_one(f).double() for f in factors]
+    return kron_rows(*aug) @ weight.double().t() + bias.double()
+
+
+def distill_kl(y_s, y_t, T):
+    """KD_loss.py:13-17 -- KL(softmax(y_t/T) || softmax(y_s/T)) * T^2 / B, sum reduction."""
+    p_s = F.log_softmax(y_s / T, dim=1)
+    p_t = F.softmax(y_t / T, dim=1)
+    return F.kl_div(p_s, p_t, reduction="sum") * (T ** 2) / y_s.shape[0]
