@@ -1,0 +1,382 @@
+"""Benchmark of the CRD distillation step (BASELINE.json metric: distill steps/s).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --steps K --warmup W    # the reference algorithm on host cores
+
+Workload (config.workload):
+  N=1  BASELINE config 2: feat_dim 128, batch 1024, n_data 1M, nce_k 16384 -- one step =
+       Embed(f_s), Embed(f_t) -> fused gather/score/NCE-loss/gradient over 2 x 1024 x 16385 bank
+       rows -> momentum row update -> loss.backward() through the Embed heads (f_t detached,
+       SURVEY.md §8d) -> Adam step on the Embed parameters.  Synthetic inputs, fresh idx/contrast_idx per step from a device-resident pool.
+  N>1  the same unit of work per GPU on the row-sharded bank (2M rows per GPU; at N=8 this is
+       exactly BASELINE config 5: 16M x 128 banks, global batch 8192): weak scaling,
+       value = N x global steps/s = "config-2 units per second".
+
+`value` times K steps with inputs already in HBM; `e2e` times the public CRDLoss call with
+pinned HOST inputs (H2D of f_s, f_t, idx, contrast_idx and a D2H read of the loss every step).
+`roofline` is the gather kernel's algorithmic bytes / its CUDA-event time inside the timed steps.
+`cpu_baseline` / `--impl reference` time the oracle port (oracle/crd_oracle.py: the reference's own
+torch-CPU op sequence) on a bounded slice of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+import types
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+METRIC = "distill steps/s (CRD fwd/bwd, config-2 units)"
+C2 = dict(B=1024, D=128, K=16384, n=1_000_000, s_dim=128, t_dim=128)
+ROWS_PER_GPU_SHARDED = 2_000_000
+
+
+def crd_algorithmic_bytes(B, K, D):
+    """row gathers (both banks) + indices + row update r/w + v reads / dv writes."""
+    gather = 2 * B * (K + 1) * D * 4
+    idx = B * (K + 1) * 8 + B * 8
+    upd = 2 * (2 * B * D * 4)
+    vio = 4 * B * D * 4
+    return gather + idx + upd + vio, gather + idx + vio
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return json.load(f), "measured"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                       "-lms", "20", "-i", str(index)], stdout=self.f, stderr=subprocess.DEVNULL)
+        except OSError:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.f.read().splitlines():
+            parts = [x.strip() for x in line.split(",")]
+            if len(parts) < 6:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, parts[2:6]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        os.unlink(self.f.name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+class EventTimer:
+    """CUDA events on the launching (current) stream around the gather kernel's launches."""
+
+    def __init__(self):
+        self.pairs = []
+        self.enabled = False
+        self._open = None
+
+    def start(self, name, dev):
+        if self.enabled:
+            e = torch.cuda.Event(enable_timing=True)
+            e.record(torch.cuda.current_stream(dev))
+            self._open = e
+
+    def stop(self, name, dev):
+        if self.enabled and self._open is not None:
+            e = torch.cuda.Event(enable_timing=True)
+            e.record(torch.cuda.current_stream(dev))
+            self.pairs.append((self._open, e))
+            self._open = None
+
+    def mean_ms(self):
+        return statistics.mean(a.elapsed_time(b) for a, b in self.pairs) if self.pairs else None
+
+
+def make_opt(cfg, n):
+    return types.SimpleNamespace(s_dim=cfg["s_dim"], t_dim=cfg["t_dim"], feat_dim=cfg["D"], n_data=n,
+                                 nce_k=cfg["K"], nce_t=0.07, nce_m=0.5)
+
+
+def gen_inputs(cfg, B, n, gen, device, pinned=False):
+    """One step's synthetic inputs: N(0,1) features, unique anchors, uniform negatives."""
+    kw = dict(device=device, generator=gen)
+    f_s = torch.randn(B, cfg["s_dim"], **kw)
+    f_t = torch.randn(B, cfg["t_dim"], **kw)
+    idx = torch.randperm(n, **kw)[:B].contiguous()
+    cidx = torch.randint(0, n, (B, cfg["K"] + 1), **kw)
+    cidx[:, 0] = idx
+    out = (f_s, f_t, idx, cidx)
+    if pinned:
+        out = tuple(t.pin_memory() for t in out)
+    return out
+
+
+# ------------------------------------------------------------------------------------------ #
+# CPU arm: the reference's algorithm (oracle port) on the host cores
+# ------------------------------------------------------------------------------------------ #
+def cpu_port_steps_per_s(cfg, steps, warmup, sample_B, seed=2019):
+    """Times `steps` oracle steps on a slice of `sample_B` anchors and scales to the full batch
+    (the work is linear in anchors).  Returns (full-workload steps/s, seconds per sample step)."""
+    from oracle import crd_oracle as co
+    torch.manual_seed(seed)
+    n, D, K = cfg["n"], cfg["D"], cfg["K"]
+    sd = {}
+    for side, dim in (("s", cfg["s_dim"]), ("t", cfg["t_dim"])):
+        l0, l2 = torch.nn.Linear(dim, D), torch.nn.Linear(D, D)
+        sd[f"embed_{side}.linear.0.weight"], sd[f"embed_{side}.linear.0.bias"] = l0.weight.detach(), l0.bias.detach()
+        sd[f"embed_{side}.linear.2.weight"], sd[f"embed_{side}.linear.2.bias"] = l2.weight.detach(), l2.bias.detach()
+    for k in list(sd):
+        sd[k].requires_grad_(True)
+    optim = torch.optim.Adam([sd[k] for k in sd], lr=2e-4, betas=(0.9, 0.999))
+    sd["contrast.memory_v1"], sd["contrast.memory_v2"] = co.memory_init(n, D)
+    sd["contrast.params"] = co.make_params(K)
+    gen = torch.Generator().manual_seed(seed)
+    times = []
+    for i in range(warmup + steps):
+        f_s, f_t, idx, cidx = gen_inputs(cfg, sample_B, n, gen, "cpu")
+        f_s.requires_grad_(True)
+        t0 = time.perf_counter()
+        loss, _, _ = co.crd_loss(sd, f_s, f_t, idx, cidx, n)
+        loss.backward()
+        optim.step()
+        dt = time.perf_counter() - t0
+        optim.zero_grad(set_to_none=True)
+        if i >= warmup:
+            times.append(dt)
+    t_sample = statistics.mean(times)
+    return 1.0 / (t_sample * cfg["B"] / sample_B), t_sample
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cfg = dict(C2)
+    cores = torch.get_num_threads()
+    sample_B = 64
+    t0 = time.perf_counter()
+    sps, t_sample = cpu_port_steps_per_s(cfg, args.steps, args.warmup, sample_B)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": sps, "unit": "steps/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 / sps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "config 2: CRD step feat_dim=128 batch=1024 n_data=1M nce_k=16384 (CPU, sliced)"},
+        "cpu_baseline": {"value": sps, "unit": "steps/s", "cores": cores, "kind": "port",
+                         "sample": f"{sample_B} of 1024 anchors per step at full K=16384/n=1M "
+                                   f"({t_sample * 1e3:.0f} ms each), scaled x{cfg['B'] // sample_B} (work is linear in anchors)"},
+        "e2e": {"value": sps, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0, "wall_s": time.perf_counter() - t0,
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------ #
+# GPU arm
+# ------------------------------------------------------------------------------------------ #
+def run_gpu_arm(args):
+    import torch.distributed as dist
+
+    import multimodal_learning_b200 as pkg
+    from multimodal_learning_b200 import crd as crd_mod
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.gpus != world:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch N>1 with torch.distributed.run (one rank per GPU)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    cfg = dict(C2)
+    B, D, K = cfg["B"], cfg["D"], cfg["K"]
+    pkg._cabi.lib()
+
+    torch.manual_seed(2019)
+    if world == 1:
+        n = cfg["n"]
+        mod = pkg.CRDLoss(make_opt(cfg, n)).to(dev)
+        B_local, B_global = B, B
+        workload = "config 2: CRD step feat_dim=128 batch=1024 n_data=1M nce_k=16384, fwd+bwd+bank update"
+    else:
+        from multimodal_learning_b200.sharded import ShardedCRDLoss
+        n = ROWS_PER_GPU_SHARDED * world
+        B_local, B_global = B, B * world
+        mod = ShardedCRDLoss(make_opt(cfg, n), device=dev)
+        workload = (f"config-2 unit per GPU on the row-sharded bank: global batch {B_global}, n_data {n} "
+                    f"({ROWS_PER_GPU_SHARDED} rows/GPU), nce_k 16384" + (" = BASELINE config 5" if world == 8 else ""))
+    opt_params = [p for p in mod.parameters()]
+    optim = torch.optim.Adam(opt_params, lr=2e-4, betas=(0.9, 0.999), fused=True)   # networks_new.py:85
+
+    gen = torch.Generator(device=dev).manual_seed(1234 + rank)
+    pool = [gen_inputs(cfg, B_local, n, gen, dev) for _ in range(4)]
+    hgen = torch.Generator().manual_seed(4321 + rank)
+    host_pool = [gen_inputs(cfg, B_local, n, hgen, "cpu", pinned=True) for _ in range(3)]
+    h2d_bytes = sum(t.numel() * t.element_size() for t in host_pool[0])
+
+    def step_device(i):
+        f_s, f_t, idx, cidx = pool[i % len(pool)]
+        f_s = f_s.detach().requires_grad_(True)
+        for p in opt_params:
+            p.grad = None
+        loss = mod(f_s, f_t, idx, cidx)
+        loss.backward()
+        optim.step()
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            fn(i)
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return ms.item()
+
+    # ---- device-resident throughput (`value`) ----
+    for i in range(max(args.warmup, 3)):
+        step_device(i)
+    timer = EventTimer()
+    crd_mod.KERNEL_TIMER = timer
+    launches0 = pkg._cabi.launch_count()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    timer.enabled = True
+    total_ms = timed(step_device, args.steps)
+    timer.enabled = False
+    clocks = sampler.stop() if sampler else None
+    launches = pkg._cabi.launch_count() - launches0
+    crd_mod.KERNEL_TIMER = None
+    ms_per_step = total_ms / args.steps
+    value = world * 1000.0 / ms_per_step
+
+    # ---- end to end through the public API with pinned HOST inputs ----
+    copy_stream = torch.cuda.Stream(dev)
+    staged = {}
+
+    def stage(i):
+        with torch.cuda.stream(copy_stream):
+            staged[i] = tuple(t.to(dev, non_blocking=True) for t in host_pool[i % len(host_pool)])
+            ev = torch.cuda.Event()
+            ev.record(copy_stream)
+            staged[i] += (ev,)
+
+    losses_host = torch.empty(2, 1, pin_memory=True)
+
+    def step_e2e(i):
+        if i not in staged:
+            stage(i)
+        f_s, f_t, idx, cidx, ev = staged.pop(i)
+        torch.cuda.current_stream(dev).wait_event(ev)
+        stage(i + 1)                                   # upload of step i+1 overlaps step i's kernels
+        f_s = f_s.requires_grad_(True)
+        for p in opt_params:
+            p.grad = None
+        loss = mod(f_s, f_t, idx, cidx)
+        loss.backward()
+        optim.step()
+        for t in (f_s, f_t, idx, cidx):
+            t.record_stream(torch.cuda.current_stream(dev))
+        return loss.item()                             # D2H read of the step's result, every step
+
+    for i in range(3):
+        step_e2e(i)
+    staged.clear()
+    e2e_ms = timed(step_e2e, args.steps) / args.steps
+    staged.clear()
+    e2e_value = world * 1000.0 / e2e_ms
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peaks, peak_kind = measured_peaks()
+    total_bytes, gather_bytes = crd_algorithmic_bytes(B_global if world == 1 else B, K, D)
+    k_ms = timer.mean_ms()
+    achieved = gather_bytes / (k_ms * 1e-3) / 1e9 if k_ms else None
+    peak = float(peaks["hbm_gbs"])
+    line = {
+        "metric": METRIC, "value": value, "unit": "steps/s", "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload, "l2": "inputs exceed L2: 1.02 GB of bank rows gathered at random per GPU, "
+                   "4 rotating 134 MB index sets; no explicit flush", "algorithmic_bytes_per_step": total_bytes},
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": (achieved / peak) if achieved else None, "traffic": args.traffic,
+                     "kernel": "crd_gather_kernel<4,2,fused> (+2 finisher launches)", "kernel_ms": k_ms,
+                     "bytes_per_launch": gather_bytes, "peak_source": f"MEASURED_PEAKS.json ({peak_kind}, burst copy)"},
+        "e2e": {"value": e2e_value, "unit": "steps/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": h2d_bytes,
+                "d2h_bytes_per_step": 4, "note": "pinned host inputs; upload of step i+1 overlaps step i on a copy stream"},
+        "gpu_launches": launches, "clocks": clocks,
+    }
+    if world == 1 and not args.no_cpu:
+        sps, t_sample = cpu_port_steps_per_s(cfg, 6, 2, 64)
+        line["cpu_baseline"] = {"value": sps, "unit": "steps/s", "cores": torch.get_num_threads(), "kind": "port",
+                                "sample": f"64 of 1024 anchors per step at full K/n ({t_sample * 1e3:.0f} ms each), "
+                                          f"scaled x16 (work is linear in anchors)"}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--traffic", type=float, default=None,
+                    help="dram bytes/launch of the gather kernel from the committed ncu capture (profiles/)")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_gpu_arm(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,141 @@
+/* mml_b200.h -- C ABI of the B200-native fusion + CRD distillation hot path.
+ *
+ * Drop-in boundary for the hot path of CityU-AIM-Group/MultiModal-learning
+ * (citations are file:line under MICCAI-2022/ of the reference).  The reference
+ * has no FFI: its boundary is Python `nn.Module`s.  The host-side mirror of
+ * those modules lives in `multimodal-learning_b200/*.py` and calls ONLY the
+ * entry points below (through ctypes).  INTEGRATION.md shows the binding.
+ *
+ * Conventions
+ *   - plain C: pointers + sizes, no torch types.  Pointers are DEVICE pointers
+ *     unless the name ends in `_host`.  The caller owns every buffer; nothing is
+ *     allocated inside (the caller passes a workspace sized by the matching
+ *     `*_workspace_bytes` query).
+ *   - `stream` is a `cudaStream_t` passed as `void*`; all work is enqueued on it
+ *     and nothing synchronises the host.
+ *   - return value: 0 = ok; <0 = error (MML_ERR_*); `mml_last_error()` returns a
+ *     thread-local description.  There is NO CPU fallback anywhere.
+ *   - floats are fp32, indices int64, row-major, as in the reference's tensors.
+ */
+#ifndef MML_B200_H_
+#define MML_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MML_OK               0
+#define MML_ERR_INVALID_ARG -1   /* bad shape / null pointer / misalignment        */
+#define MML_ERR_CUDA        -2   /* a CUDA runtime / driver call failed            */
+#define MML_ERR_UNSUPPORTED -3   /* shape outside what the kernels are built for   */
+#define MML_ERR_WORKSPACE   -4   /* workspace smaller than *_workspace_bytes()     */
+
+#define MML_ABI_VERSION 1
+
+int         mml_abi_version(void);
+const char* mml_last_error(void);
+/* Number of kernels this library has launched in this process (bench `gpu_launches`). */
+int64_t     mml_launch_count(void);
+
+/* ------------------------------------------------------------------------- *
+ * CRD contrastive memory (CL_utils/CRD_criterion.py)
+ *
+ * Segment layout shared by the three gather entry points: anchor b owns the
+ * index range idx[seg_begin(b) .. seg_begin(b)+seg_len(b)).
+ *   dense  (seg_ptr == NULL): seg_begin = b*cols, seg_len = cols  -- the
+ *          reference's idx[B, K+1] (CRD_criterion.py:41-49).
+ *   ragged (seg_ptr != NULL): seg_begin = seg_ptr[b], seg_len = seg_ptr[b+1] -
+ *          seg_ptr[b]; `cols` is then an upper bound on seg_len.  Used by the
+ *          row-sharded bank: a rank sees only the indices it owns.
+ * `pos_flag` (uint8[B], NULL = all ones) says whether the FIRST entry of
+ * anchor b's segment is its positive (column 0 of the reference's idx).
+ * Bank 1 rows are scored against v2 ("side 2", out_v2, Z_v2); bank 2 rows
+ * against v1 ("side 1", out_v1, Z_v1) -- CRD_criterion.py:41-49.
+ * ------------------------------------------------------------------------- */
+
+size_t mml_crd_workspace_bytes(int64_t B, int64_t cols, int32_t D);
+
+/* Fused replacement for ContrastMemory.forward's gather/bmm/exp/div
+ * (CRD_criterion.py:41-49,62-63) + ContrastLoss.forward (:199-216) + their
+ * autograd: one pass over the gathered rows yields the NCE loss AND dL/dv1,
+ * dL/dv2 (closed form).  Z must already be set.
+ *   Z          float[2] = {Z_v1, Z_v2}                        (params[2:4])
+ *   n_data     size of the noise distribution (ContrastLoss.n_data, :197)
+ *   nce_k      m of ContrastLoss.forward (:201) = reference cols-1
+ *   batch_norm divisor `bsz` of :214 (global batch when sharded)
+ *   loss       float[1] or NULL: -(sum of log terms)/batch_norm
+ *   sums       float[4] or NULL: {sum log-terms side1, side2, 0, 0} raw totals
+ *   grad_v1/2  float[B,D]: dL/dv1, dL/dv2 for THESE segments (partial if sharded)
+ *   out_v1/2   optional float[nnz] laid out like idx: exp(dot/T)/Z   (:62-63)   */
+int mml_crd_fused_loss_grad(
+    const float* bank1, const float* bank2, int64_t n_rows, int32_t D,
+    const float* v1, const float* v2,
+    const int64_t* idx, const int64_t* seg_ptr, const uint8_t* pos_flag,
+    int64_t B, int64_t cols,
+    float T, const float* Z, int64_t n_data, int64_t nce_k, int64_t batch_norm,
+    float* loss, float* sums, float* grad_v1, float* grad_v2,
+    float* out_v1, float* out_v2,
+    void* workspace, size_t workspace_bytes, void* stream);
+
+/* Scores only (ContrastMemory.forward :41-49 [+ :62-63 when Z != NULL]).
+ *   Z == NULL : out = exp(dot/T) (raw);  Z != NULL: out = exp(dot/T)/Z.
+ *   sums      float[4] or NULL: {0, 0, sum raw side1, sum raw side2}
+ *   set_Z     float[2] or NULL: first-call normaliser of :52-59 -- entries that
+ *             are < 0 are replaced by mean(raw)*n_rows (mean over B*cols).
+ *   out_v1/2  may be NULL (statistics-only pass).                              */
+int mml_crd_scores(
+    const float* bank1, const float* bank2, int64_t n_rows, int32_t D,
+    const float* v1, const float* v2,
+    const int64_t* idx, const int64_t* seg_ptr,
+    int64_t B, int64_t cols,
+    float T, const float* Z, float* sums, float* set_Z,
+    float* out_v1, float* out_v2,
+    void* workspace, size_t workspace_bytes, void* stream);
+
+/* Weighted gather-sum: g1[b] = sum_k coef1[b,k]*bank2[idx[b,k]],
+ * g2[b] = sum_k coef2[b,k]*bank1[idx[b,k]].  Backward of the bmm at
+ * CRD_criterion.py:43,48 for callers that use out_v1/out_v2 in their own loss. */
+int mml_crd_weighted_rows(
+    const float* bank1, const float* bank2, int64_t n_rows, int32_t D,
+    const int64_t* idx, const int64_t* seg_ptr,
+    const float* coef1, const float* coef2,
+    int64_t B, int64_t cols,
+    float* g1, float* g2,
+    void* workspace, size_t workspace_bytes, void* stream);
+
+/* Momentum update + L2 renormalisation of the anchors' rows in both banks
+ * (CRD_criterion.py:66-79):  r <- (m*r + (1-m)*v) / ||m*r + (1-m)*v||_2.
+ * `y[i]` outside [row_begin, row_end) is skipped (owner-applies rule of the
+ * sharded bank; pass 0, n_rows for the whole bank); the row written is
+ * bank[y[i]-row_begin].  Duplicate y are order-dependent, as in the reference. */
+int mml_crd_memory_update(
+    float* bank1, float* bank2, int32_t D,
+    const float* v1, const float* v2, const int64_t* y, int64_t B,
+    float momentum, int64_t row_begin, int64_t row_end, void* stream);
+
+/* ------------------------------------------------------------------------- *
+ * AliasMethod (CRD_criterion.py:84-141)
+ * ------------------------------------------------------------------------- */
+
+/* HOST function.  Vose tables with the reference's LIFO pairing (:97-123),
+ * bit-exact in fp32.  `probs_host` must already be normalised as :90-91 does. */
+int mml_alias_build_host(const float* probs_host, int64_t n,
+                         float* prob_out_host, int64_t* alias_out_host);
+
+/* draw(), split around the two torch RNG calls it keeps (:133 random_, :137
+ * bernoulli) so the same generator state yields the same indices:
+ *   mml_alias_gather_prob: p[i] = prob[kk[i]]                           (:134)
+ *   mml_alias_select:      out[i] = b[i] ? kk[i] : alias[kk[i]]         (:135-141)
+ *     and, when y != NULL, out[r*cols + 0] = y[r] (ContrastMemory.forward :39). */
+int mml_alias_gather_prob(const float* prob, const int64_t* kk, int64_t N,
+                          float* p_out, void* stream);
+int mml_alias_select(const int64_t* alias, const int64_t* kk, const float* b, int64_t N,
+                     const int64_t* y, int64_t cols, int64_t* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MML_B200_H_ */

@@ -1,0 +1,15 @@
+"""multimodal-learning_b200: B200-native (sm_100a) fusion + CRD distillation hot path.
+
+Drop-in mirrors of the reference's modules (CityU-AIM-Group/MultiModal-learning,
+`MICCAI-2022/fusion.py`, `MICCAI-2022/CL_utils/CRD_criterion.py`, `MICCAI-2022/KD_loss.py`)
+over hand-written CUDA kernels reached through the C ABI in `include/mml_b200.h`.
+The directory name has a hyphen (task-mandated); import it as `multimodal_learning_b200`
+(the repo-root shim `multimodal_learning_b200.py` registers it), or put
+`multimodal-learning_b200/dropin` on PYTHONPATH to shadow the reference's own
+`fusion`, `KD_loss` and `CL_utils.CRD_criterion` modules unchanged.
+"""
+from . import _cabi
+from .crd import (AliasMethod, ContrastLoss, ContrastMemory, CRDLoss, Embed, Normalize)
+from .kd_loss import DistillKL
+
+__all__ = ["AliasMethod", "ContrastLoss", "ContrastMemory", "CRDLoss", "Embed", "Normalize", "DistillKL", "_cabi"]

@@ -1,0 +1,94 @@
+"""ctypes binding of libmml_b200.so -- the ONLY compute backend of this package.
+
+Every entry point declared in include/mml_b200.h is bound here with explicit
+argtypes.  There is no CPU or PyTorch-eager fallback: if the library is missing
+or a call returns non-zero, a RuntimeError is raised.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import c_char_p, c_float, c_int32, c_int64, c_size_t, c_void_p
+
+import torch
+
+PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(PKG, "lib", "libmml_b200.so")
+
+_P = c_void_p
+_SIGNATURES = {
+    "mml_abi_version": (ctypes.c_int, []),
+    "mml_last_error": (c_char_p, []),
+    "mml_launch_count": (c_int64, []),
+    "mml_crd_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int32]),
+    "mml_crd_fused_loss_grad": (ctypes.c_int, [
+        _P, _P, c_int64, c_int32, _P, _P, _P, _P, _P, c_int64, c_int64,
+        c_float, _P, c_int64, c_int64, c_int64, _P, _P, _P, _P, _P, _P, _P, c_size_t, _P]),
+    "mml_crd_scores": (ctypes.c_int, [
+        _P, _P, c_int64, c_int32, _P, _P, _P, _P, c_int64, c_int64,
+        c_float, _P, _P, _P, _P, _P, _P, c_size_t, _P]),
+    "mml_crd_weighted_rows": (ctypes.c_int, [
+        _P, _P, c_int64, c_int32, _P, _P, _P, _P, c_int64, c_int64, _P, _P, _P, c_size_t, _P]),
+    "mml_crd_memory_update": (ctypes.c_int, [
+        _P, _P, c_int32, _P, _P, _P, c_int64, c_float, c_int64, c_int64, _P]),
+    "mml_alias_build_host": (ctypes.c_int, [_P, c_int64, _P, _P]),
+    "mml_alias_gather_prob": (ctypes.c_int, [_P, _P, c_int64, _P, _P]),
+    "mml_alias_select": (ctypes.c_int, [_P, _P, _P, c_int64, _P, c_int64, _P, _P]),
+}
+
+_lib = None
+
+
+def declared_symbols():
+    return sorted(_SIGNATURES)
+
+
+def lib() -> ctypes.CDLL:
+    """Load (once) and return the C-ABI library; fail loudly if it is not built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'`. "
+                "This package has no CPU / eager fallback.")
+        handle = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in _SIGNATURES.items():
+            fn = getattr(handle, name)          # AttributeError if the .so lacks a declared symbol
+            fn.restype = res
+            fn.argtypes = args
+        if handle.mml_abi_version() != 1:
+            raise RuntimeError("libmml_b200.so ABI version mismatch")
+        _lib = handle
+    return _lib
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        raise RuntimeError(f"{what} failed (code {rc}): {lib().mml_last_error().decode()}")
+
+
+def dptr(t: torch.Tensor | None, dtype=None) -> c_void_p | None:
+    """Device pointer of a contiguous CUDA tensor (None passes NULL)."""
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise RuntimeError("mml_b200 kernels take CUDA tensors only (no CPU fallback)")
+    if dtype is not None and t.dtype != dtype:
+        raise RuntimeError(f"expected {dtype}, got {t.dtype}")
+    if not t.is_contiguous():
+        raise RuntimeError("tensor must be contiguous")
+    return c_void_p(t.data_ptr())
+
+
+def hptr(t: torch.Tensor) -> c_void_p:
+    if t.is_cuda or not t.is_contiguous():
+        raise RuntimeError("expected a contiguous host tensor")
+    return c_void_p(t.data_ptr())
+
+
+def cur_stream(device) -> c_void_p:
+    return c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def launch_count() -> int:
+    return int(lib().mml_launch_count())

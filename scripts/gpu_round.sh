@@ -1,0 +1,16 @@
+#!/bin/bash
+# One GPU-box visit: parity tests, smoke, bench, ncu launch list + full capture of the gather kernel.
+# Usage (from the repo root, under gpurun):  bash scripts/gpu_round.sh <tag>
+set -u
+TAG=${1:-r1}
+OUT=gpurun_out
+mkdir -p $OUT
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > $OUT/${TAG}_smi.txt 2>&1
+echo "== pytest -m gpu" ; timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -25 | tee $OUT/${TAG}_pytest.txt
+echo "== smoke" ; timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -8 | tee $OUT/${TAG}_smoke.txt
+echo "== bench" ; timeout 600 python bench.py --steps 100 --warmup 10 2>&1 | tail -3 | tee $OUT/${TAG}_bench.json
+echo "== ncu launches" ; timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 80 --csv \
+    --log-file $OUT/${TAG}_launches.csv python bench.py --steps 2 --warmup 1 --no-cpu > $OUT/${TAG}_ncu_launch.log 2>&1
+echo "== ncu full" ; timeout 900 ncu --set full --clock-control none --import-source on -k regex:crd_gather_kernel -s 4 -c 2 \
+    -f -o $OUT/${TAG}_prof_crd python bench.py --steps 2 --warmup 1 --no-cpu > $OUT/${TAG}_ncu_full.log 2>&1
+ls -la $OUT | tail -12

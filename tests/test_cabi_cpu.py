@@ -1,0 +1,117 @@
+"""CPU checks of the C-ABI boundary: the library builds/loads, exports every symbol the
+header declares, rejects bad arguments, and its HOST function (alias tables) is bit-exact
+against the reference's golden vectors.  No GPU compute is issued here."""
+from __future__ import annotations
+
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+import multimodal_learning_b200 as pkg
+from multimodal_learning_b200 import _cabi
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_in_header():
+    text = open(os.path.join(ROOT, "include", "mml_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(mml_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    names = _declared_in_header()
+    assert len(names) >= 10
+    handle = ctypes.CDLL(_cabi.LIB_PATH)
+    for n in names:
+        assert hasattr(handle, n), f"{n} declared in include/mml_b200.h but not exported"
+    # and the ctypes binding covers exactly the header
+    assert names == _cabi.declared_symbols()
+
+
+def test_abi_version_and_error_string():
+    lib = _cabi.lib()
+    assert lib.mml_abi_version() == 1
+    rc = lib.mml_alias_build_host(None, 0, None, None)
+    assert rc == -1
+    assert b"alias_build" in lib.mml_last_error()
+    assert lib.mml_crd_workspace_bytes(1024, 16385, 128) > 1024 * 2 * 128 * 4
+
+
+def test_kernels_refuse_cpu_tensors():
+    with pytest.raises(RuntimeError):
+        _cabi.dptr(torch.zeros(4))
+    am = pkg.AliasMethod(torch.ones(16))
+    with pytest.raises(RuntimeError):
+        am.draw(8)                       # no CPU fallback
+
+
+def test_alias_build_host_bit_exact(golden):
+    g = golden("alias")
+    for c in g.cfg["cases"]:
+        raw = torch.from_numpy(g.np(f"{c}.raw").copy())
+        am = pkg.AliasMethod(raw)        # normalises in place like the reference (:90-91)
+        assert np.array_equal(raw.numpy().view(np.uint32), g.np(f"{c}.normalised").view(np.uint32)), c
+        assert np.array_equal(am.prob.numpy().view(np.uint32), g.np(f"{c}.prob").view(np.uint32)), c
+        assert np.array_equal(am.alias.numpy(), g.np(f"{c}.alias")), c
+        assert am.alias.dtype == torch.int64 and am.prob.dtype == torch.float32
+
+
+def test_alias_build_host_matches_oracle_random():
+    from oracle import crd_oracle as co
+    rng = np.random.default_rng(0)
+    for n in (1, 2, 3, 17, 256, 5000):
+        p = torch.from_numpy(rng.random(n).astype(np.float32) ** 3 + 1e-6)
+        am = pkg.AliasMethod(p)
+        prob, alias = co.alias_build(p.numpy())
+        assert np.array_equal(am.prob.numpy().view(np.uint32), prob.view(np.uint32)), n
+        assert np.array_equal(am.alias.numpy(), alias), n
+
+
+def test_alias_uniform_large_is_identity():
+    am = pkg.AliasMethod(torch.ones(1 << 20))
+    assert bool((am.prob == 1).all()) and bool((am.alias == 0).all())
+
+
+def test_module_state_dict_layout_matches_reference(golden):
+    """Same seed -> same initial state as the reference (RNG call order preserved),
+    and identical state_dict keys/shapes so checkpoints are interchangeable."""
+    import types
+    g = golden("crd_small")
+    c = g.cfg
+    torch.manual_seed(2019)
+    opt = types.SimpleNamespace(s_dim=c["s_dim"], t_dim=c["t_dim"], feat_dim=c["D"], n_data=c["n"],
+                                nce_k=c["K"], nce_t=0.07, nce_m=0.5)
+    mod = pkg.CRDLoss(opt)
+    want = g.state_dict("init.")
+    got = mod.state_dict()
+    assert list(got.keys()) == list(want.keys())
+    for k in want:
+        assert got[k].shape == want[k].shape and got[k].dtype == want[k].dtype, k
+        assert torch.equal(got[k], want[k]), k
+    assert [n for n, _ in mod.named_parameters()] == [
+        "embed_s.linear.0.weight", "embed_s.linear.0.bias", "embed_s.linear.2.weight", "embed_s.linear.2.bias",
+        "embed_t.linear.0.weight", "embed_t.linear.0.bias", "embed_t.linear.2.weight", "embed_t.linear.2.bias"]
+
+
+def test_distill_kl_matches_golden(golden):
+    g = golden("distill_kl")
+    for i in range(g.cfg["cases"]):
+        y_s = g.t(f"c{i}.y_s").requires_grad_(True)
+        loss = pkg.DistillKL(float(g.np(f"c{i}.T")))(y_s, g.t(f"c{i}.y_t"))
+        loss.backward()
+        assert abs(loss.item() - g.t(f"c{i}.loss").item()) < 1e-6 * max(1, abs(loss.item()))
+        assert torch.allclose(y_s.grad, g.t(f"c{i}.grad_y_s"), rtol=1e-5, atol=1e-7)
+
+
+def test_contrast_loss_standalone_matches_oracle():
+    from oracle import crd_oracle as co
+    torch.manual_seed(0)
+    x = torch.rand(6, 9, 1) * 1e-2
+    got = pkg.ContrastLoss(100)(x)
+    assert got.shape == (1,)
+    assert torch.allclose(got, co.nce_loss(x, 100), rtol=1e-6)
