@@ -263,14 +263,20 @@ def run_gpu_arm(args):
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    def timed(fn, steps):
+    profile_region = os.environ.get("MML_BENCH_PROFILE") == "1"   # ncu --profile-from-start off
+
+    def timed(fn, steps, profile=False):
         barrier()
+        if profile and profile_region:
+            torch.cuda.profiler.start()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for i in range(steps):
             fn(i)
         e1.record()
         barrier()
+        if profile and profile_region:
+            torch.cuda.profiler.stop()
         ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
@@ -284,7 +290,7 @@ def run_gpu_arm(args):
     launches0 = pkg._cabi.launch_count()
     sampler = ClockSampler(local_rank) if rank == 0 else None
     timer.enabled = True
-    total_ms = timed(step_device, args.steps)
+    total_ms = timed(step_device, args.steps, profile=True)
     timer.enabled = False
     clocks = sampler.stop() if sampler else None
     launches = pkg._cabi.launch_count() - launches0

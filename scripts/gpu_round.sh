@@ -9,8 +9,10 @@ nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > $O
 echo "== pytest -m gpu" ; timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -25 | tee $OUT/${TAG}_pytest.txt
 echo "== smoke" ; timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -8 | tee $OUT/${TAG}_smoke.txt
 echo "== bench" ; timeout 600 python bench.py --steps 100 --warmup 10 2>&1 | tail -3 | tee $OUT/${TAG}_bench.json
-echo "== ncu launches" ; timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 80 --csv \
-    --log-file $OUT/${TAG}_launches.csv python bench.py --steps 2 --warmup 1 --no-cpu > $OUT/${TAG}_ncu_launch.log 2>&1
-echo "== ncu full" ; timeout 900 ncu --set full --clock-control none --import-source on -k regex:crd_gather_kernel -s 4 -c 2 \
-    -f -o $OUT/${TAG}_prof_crd python bench.py --steps 2 --warmup 1 --no-cpu > $OUT/${TAG}_ncu_full.log 2>&1
+echo "== ncu launches (timed region only: cudaProfilerStart/Stop around the K steps)"
+MML_BENCH_PROFILE=1 timeout 600 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv \
+    --log-file $OUT/${TAG}_launches.csv python bench.py --steps 3 --warmup 3 --no-cpu > $OUT/${TAG}_ncu_launch.log 2>&1
+echo "== ncu full"
+MML_BENCH_PROFILE=1 timeout 900 ncu --profile-from-start off --set full --clock-control none --import-source on \
+    -k regex:crd_gather_kernel -c 2 -f -o $OUT/${TAG}_prof_crd python bench.py --steps 2 --warmup 3 --no-cpu > $OUT/${TAG}_ncu_full.log 2>&1
 ls -la $OUT | tail -12

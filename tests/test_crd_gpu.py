@@ -173,7 +173,12 @@ def test_kernels_vs_oracle_closed_form(pkg, co, B, D, K, n):
     loss, _, g1, g2, o1, o2 = crd.crd_fused_loss_grad(d(m1), d(m2), d(v1), d(v2), d(idx), T, Zt, n, K, want_out=True)
     w_loss, w_g1, w_g2, x1, x2 = co.crd_closed_form(m1, m2, v1, v2, idx, T, Z1, Z2, n)
     assert rel_err(loss, w_loss.reshape(1)) < TOL
-    assert rel_err(g1, w_g1) < TOL and rel_err(g2, w_g2) < TOL
+    # gradients are sums of +/- terms of size ~ |row| / (T*B); when they cancel (e.g. n=2 and the negative IS the
+    # positive's row) the exact result is ~0 and only an absolute comparison at that scale is meaningful
+    gscale = 1.0 / (T * B) * max(m1.abs().max().item(), m2.abs().max().item())
+    for got, want in ((g1, w_g1), (g2, w_g2)):
+        err = (got.double().cpu() - want).abs().max().item()
+        assert err < TOL * max(want.abs().max().item(), 1e-2 * gscale)
     assert rel_err(o1, x1) < TOL and rel_err(o2, x2) < TOL
     # scores-only kernel agrees with the fused kernel's optional outputs
     s1, s2, sums = crd.crd_scores(d(m1), d(m2), d(v1), d(v2), d(idx), T, Z=Zt, want_sums=True)
