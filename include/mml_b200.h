@@ -135,6 +135,53 @@ int mml_alias_gather_prob(const float* prob, const int64_t* kk, int64_t N,
 int mml_alias_select(const int64_t* alias, const int64_t* kk, const float* b, int64_t N,
                      const int64_t* y, int64_t cols, int64_t* out, void* stream);
 
+/* ------------------------------------------------------------------------- *
+ * Gated Kronecker fusion encoder (fusion.py)
+ *
+ * Replaces, for BilinearFusion (fusion.py:56-60) and TrilinearFusion_A/B
+ * (fusion.py:123-129, :192-198), the chain
+ *   cat-with-1 -> bmm outer product(s) -> flatten -> post_fusion_dropout -> encoder1[0] (nn.Linear)
+ * by   y[b,n] = sum_k A[b,k] m[b,k] W[n,k] + bias[n]
+ * where A[b, (i*(d2+1)+j)*(d3+1)+l] = g1[b,i] g2[b,j] g3[b,l], g(x) = f[b,x] for x < d and 1 for
+ * x == d, is generated on chip and NEVER written to HBM, forward or backward.
+ *   f1,f2,f3   float[B,d1|d2|d3] factors WITHOUT the appended 1 (f3 = NULL, d3 = 0: bilinear)
+ *   W          float[N, Kk] = encoder1[0].weight, Kk = (d1+1)(d2+1)(d3+1 | 1), row-major
+ *   m          dropout multiplier of `post_fusion_dropout`: 0 or 1/(1-p'), a pure function of
+ *              (seed, b, k) (counter-based hash; p' = round(p*65536)/65536); identity when
+ *              training == 0 or drop_p == 0.
+ * ------------------------------------------------------------------------- */
+
+/* Tensor-core path (tcgen05 kind::tf32, A generated into TMEM, W streamed by TMA).
+ * The weight must first be repacked into chunk order:
+ *   n = mml_kron_num_chunks(d1,d2,d3);  table: int32[n*8] built on the HOST by
+ *   mml_kron_chunk_table_host and copied to the device by the caller (16-byte aligned);
+ *   Wp: float[mml_kron_packed_floats(N,d1,d2,d3)] (128-byte aligned), filled by mml_kron_pack_weight
+ *   whenever W changes.  mml_kron_linear_fwd needs N <= 256.                               */
+int64_t mml_kron_num_chunks(int32_t d1, int32_t d2, int32_t d3);
+int     mml_kron_chunk_table_host(int32_t d1, int32_t d2, int32_t d3, int32_t* table_host);
+int64_t mml_kron_packed_floats(int32_t N, int32_t d1, int32_t d2, int32_t d3);
+int     mml_kron_pack_weight(const float* W, int32_t N, int32_t d1, int32_t d2, int32_t d3,
+                             const int32_t* table, float* Wp, void* stream);
+int     mml_kron_fwd_supported(int64_t B, int32_t N, int32_t d1, int32_t d2, int32_t d3);   /* 1 / 0 */
+size_t  mml_kron_fwd_workspace_bytes(int64_t B, int32_t N, int32_t d1, int32_t d2, int32_t d3);
+int     mml_kron_linear_fwd(const float* f1, const float* f2, const float* f3, int64_t B,
+                            int32_t d1, int32_t d2, int32_t d3, const int32_t* table, const float* Wp,
+                            const float* bias, int32_t N, float drop_p, uint64_t seed, int32_t training,
+                            float* y, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Exact-fp32 CUDA-core path on the dense weight (any N, any widths): forward, and backward
+ *   dW[n,k] = sum_b dy[b,n] A[b,k] m[b,k]            (NULL to skip)
+ *   df_x    = factor gradients through dA = m * (dy W), contracted on chip (all NULL to skip);
+ *             the appended 1 receives no gradient.                                         */
+int mml_kron_linear_fwd_simt(const float* f1, const float* f2, const float* f3, int64_t B,
+                             int32_t d1, int32_t d2, int32_t d3, const float* W, const float* bias,
+                             int32_t N, float drop_p, uint64_t seed, int32_t training, float* y,
+                             void* stream);
+int mml_kron_linear_bwd_simt(const float* f1, const float* f2, const float* f3, int64_t B,
+                             int32_t d1, int32_t d2, int32_t d3, const float* W, const float* dy,
+                             int32_t N, float drop_p, uint64_t seed, int32_t training,
+                             float* df1, float* df2, float* df3, float* dW, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -10,6 +10,7 @@ The directory name has a hyphen (task-mandated); import it as `multimodal_learni
 """
 from . import _cabi
 from .crd import (AliasMethod, ContrastLoss, ContrastMemory, CRDLoss, Embed, Normalize)
+from .fusion import BilinearFusion, TrilinearFusion_A, TrilinearFusion_B, init_max_weights, kron_linear
 from .kd_loss import DistillKL
 
-__all__ = ["AliasMethod", "ContrastLoss", "ContrastMemory", "CRDLoss", "Embed", "Normalize", "DistillKL", "_cabi"]
+__all__ = ["BilinearFusion", "TrilinearFusion_A", "TrilinearFusion_B", "init_max_weights", "kron_linear", "AliasMethod", "ContrastLoss", "ContrastMemory", "CRDLoss", "Embed", "Normalize", "DistillKL", "_cabi"]

@@ -34,6 +34,20 @@ _SIGNATURES = {
     "mml_alias_build_host": (ctypes.c_int, [_P, c_int64, _P, _P]),
     "mml_alias_gather_prob": (ctypes.c_int, [_P, _P, c_int64, _P, _P]),
     "mml_alias_select": (ctypes.c_int, [_P, _P, _P, c_int64, _P, c_int64, _P, _P]),
+    "mml_kron_num_chunks": (c_int64, [c_int32, c_int32, c_int32]),
+    "mml_kron_chunk_table_host": (ctypes.c_int, [c_int32, c_int32, c_int32, _P]),
+    "mml_kron_packed_floats": (c_int64, [c_int32, c_int32, c_int32, c_int32]),
+    "mml_kron_pack_weight": (ctypes.c_int, [_P, c_int32, c_int32, c_int32, c_int32, _P, _P, _P]),
+    "mml_kron_fwd_supported": (ctypes.c_int, [c_int64, c_int32, c_int32, c_int32, c_int32]),
+    "mml_kron_fwd_workspace_bytes": (c_size_t, [c_int64, c_int32, c_int32, c_int32, c_int32]),
+    "mml_kron_linear_fwd": (ctypes.c_int, [
+        _P, _P, _P, c_int64, c_int32, c_int32, c_int32, _P, _P, _P, c_int32, c_float, ctypes.c_uint64, c_int32,
+        _P, _P, c_size_t, _P]),
+    "mml_kron_linear_fwd_simt": (ctypes.c_int, [
+        _P, _P, _P, c_int64, c_int32, c_int32, c_int32, _P, _P, c_int32, c_float, ctypes.c_uint64, c_int32, _P, _P]),
+    "mml_kron_linear_bwd_simt": (ctypes.c_int, [
+        _P, _P, _P, c_int64, c_int32, c_int32, c_int32, _P, _P, c_int32, c_float, ctypes.c_uint64, c_int32,
+        _P, _P, _P, _P, _P]),
 }
 
 _lib = None

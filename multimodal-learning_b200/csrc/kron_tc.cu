@@ -1,0 +1,573 @@
+// K1: Kronecker-fusion encoder forward on the 5th-gen tensor cores (tcgen05 / TMEM / TMA).
+//
+//   y[b, n] = sum_k A[b,k] m[b,k] W[n,k] + bias[n]        encoder1[0] of fusion.py:29,60 / :94,129
+//
+// The (d+1)^2 / (d+1)^3 Kronecker operand A (fusion.py:58, :126-127) and its dropout copy
+// (fusion.py:59, :128) are never written to HBM: each CTA owns 128 batch rows, its 128 generator
+// threads (one per row = one per TMEM lane) compute 32-wide slices  scalar[b] * vector[b, 0..31]
+// of A in registers and store them straight into TENSOR MEMORY (tcgen05.st), where the MMA reads
+// its A operand (tcgen05.mma kind::tf32, A from TMEM, B from shared memory).  The weight is
+// repacked once per weight version into the same chunk order ([Np, 32*chunks] fp32, TF32-rounded,
+// 16-byte row pitch) so TMA can stream [Np x 32] tiles (128B-swizzled, K-major) into a ring.
+// The fp32 accumulator [128 x Np] lives in TMEM and is read back once (tcgen05.ld) for the epilogue.
+//
+// Chunk order ("K permutation"): A's columns are regrouped into chunks of <= 32 logical k that
+// share one per-row scalar:  core block  o1[i] (x o2[j]) * o_last[32-wide segment],  then the faces /
+// edges that contain an appended 1, then the corner (1*1[*1]).  A chunk is (p, q, vsrc, vcol, vlen,
+// kbase, kstride): scalar = R[p]*R[q] with R = [1, f1.., f2..] per row, vector = f_vsrc[vcol + t],
+// logical k of element t = kbase + t*kstride (used for weight packing and the dropout counter).
+//
+// Warp roles (192 threads): warps 0-3 generate A / run the epilogue, warp 4 issues TMA,
+// warp 5 allocates TMEM and issues the MMAs.  Operand precision: TF32 (10-bit mantissa, fp32 range,
+// both operands rounded to nearest) with fp32 accumulation -> rel error ~3e-4 (tolerance 2e-3).
+#include <cuda.h>
+#include <string.h>
+
+#include <mutex>
+#include <unordered_map>
+#include <vector>
+
+#include "kron_common.cuh"
+
+namespace mml {
+namespace {
+
+constexpr int kTileM = 128;
+constexpr int kChunkK = 32;                 // tf32 elements per chunk = one 128-byte swizzle row
+constexpr int kGenThreads = 128;
+constexpr int kThreadsTc = 192;
+constexpr uint32_t kSpinLimit = 1u << 28;   // mbarrier spin guard: trap instead of hanging the GPU
+
+struct Chunk {                // 32 bytes, read as two int4
+  int32_t p, q, vsrc, vcol;
+  int32_t vlen, kbase, kstride, pad;
+};
+
+// ---------------------------------------------------------------- chunk table (host)
+std::vector<Chunk> build_chunks(int d1, int d2, int d3) {
+  std::vector<Chunk> out;
+  const int e2 = d2 + 1, e3 = d3 > 0 ? d3 + 1 : 1;
+  const int P1 = 1, P2 = 1 + d1;                      // positions of f1[0], f2[0] in R = [1, f1, f2]
+  auto seg = [](int d, int s) { return d - s < kChunkK ? d - s : kChunkK; };
+  auto add = [&](int p, int q, int vsrc, int vcol, int vlen, int kbase, int kstride) {
+    out.push_back(Chunk{p, q, vsrc, vcol, vlen, kbase, kstride, 0});
+  };
+  if (d3 == 0) {
+    for (int js = 0; js < d2; js += kChunkK)          // core: o1[i] * o2[js..]
+      for (int i = 0; i < d1; ++i) add(P1 + i, 0, 2, js, seg(d2, js), i * e2 + js, 1);
+    for (int is = 0; is < d1; is += kChunkK)          // j = d2 border: o1[is..] * 1
+      add(0, 0, 1, is, seg(d1, is), is * e2 + d2, e2);
+    for (int js = 0; js < d2; js += kChunkK)          // i = d1 border: 1 * o2[js..]
+      add(0, 0, 2, js, seg(d2, js), d1 * e2 + js, 1);
+    add(0, 0, 0, 0, 1, d1 * e2 + d2, 1);              // corner 1*1
+  } else {
+    for (int ls = 0; ls < d3; ls += kChunkK)          // core: o1[i] o2[j] * o3[ls..]
+      for (int i = 0; i < d1; ++i)
+        for (int j = 0; j < d2; ++j) add(P1 + i, P2 + j, 3, ls, seg(d3, ls), (i * e2 + j) * e3 + ls, 1);
+    for (int js = 0; js < d2; js += kChunkK)          // l = d3 face: o1[i] * o2[js..]
+      for (int i = 0; i < d1; ++i) add(P1 + i, 0, 2, js, seg(d2, js), (i * e2 + js) * e3 + d3, e3);
+    for (int ls = 0; ls < d3; ls += kChunkK) {
+      for (int i = 0; i < d1; ++i)                    // j = d2 face: o1[i] * o3[ls..]
+        add(P1 + i, 0, 3, ls, seg(d3, ls), (i * e2 + d2) * e3 + ls, 1);
+      for (int j = 0; j < d2; ++j)                    // i = d1 face: o2[j] * o3[ls..]
+        add(P2 + j, 0, 3, ls, seg(d3, ls), (d1 * e2 + j) * e3 + ls, 1);
+      add(0, 0, 3, ls, seg(d3, ls), (d1 * e2 + d2) * e3 + ls, 1);     // i = d1, j = d2 edge: o3[ls..]
+    }
+    for (int is = 0; is < d1; is += kChunkK)          // j = d2, l = d3 edge: o1[is..]
+      add(0, 0, 1, is, seg(d1, is), (is * e2 + d2) * e3 + d3, e2 * e3);
+    for (int js = 0; js < d2; js += kChunkK)          // i = d1, l = d3 edge: o2[js..]
+      add(0, 0, 2, js, seg(d2, js), (d1 * e2 + js) * e3 + d3, e3);
+    add(0, 0, 0, 0, 1, (d1 * e2 + d2) * e3 + d3, 1);  // corner
+  }
+  return out;
+}
+
+int round_np(int N) { return (N + 15) / 16 * 16; }
+
+// ---------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  uint32_t done = 0, spins = 0;
+  while (true) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (done) break;
+    if (++spins > kSpinLimit) __trap();
+  }
+}
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* tmap, int32_t c0, int32_t c1, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// D[tmem] (+)= A[tmem] * B[smem desc],  kind::tf32, M = 128, K = 8
+__device__ __forceinline__ void tc_mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tc_st_32x32b_x32(uint32_t taddr, const uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+      "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]),
+      "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]),
+      "r"(r[29]), "r"(r[30]), "r"(r[31])
+      : "memory");
+}
+__device__ __forceinline__ void tc_ld_32x32b_x32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+        "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tc_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major, 128B-swizzled operand tile: rows of 128 bytes, 8-row swizzle atoms 1024 bytes apart.
+__device__ __forceinline__ uint64_t umma_desc_k_sw128(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);          // start address
+  d |= static_cast<uint64_t>(1) << 16;                               // LBO (unused for swizzled K-major) = 1
+  d |= static_cast<uint64_t>(1024 >> 4) << 32;                       // SBO = 1024 B between 8-row groups
+  d |= static_cast<uint64_t>(1) << 46;                               // descriptor version (Blackwell)
+  d |= static_cast<uint64_t>(2) << 61;                               // SWIZZLE_128B
+  return d;
+}
+
+struct TcArgs {
+  const float* f1;
+  const float* f2;
+  const float* f3;
+  const int4* table;        // [nchunks][2]
+  const float* bias;        // may be NULL
+  float* out;               // y [B,N] (ksplit == 1) or partials [ksplit, B, N]
+  int64_t B;
+  int32_t d1, d2, d3;
+  int32_t N, Np;
+  int32_t nchunks, chunks_per_split, ksplit;
+  int32_t n_scal;           // 1 + d1 (+ d2 when trilinear)
+  int32_t stages;
+  int32_t tmem_cols;
+  uint32_t idesc;
+  KronDropout dr;
+};
+
+template <bool kDropout>
+__global__ void __launch_bounds__(kThreadsTc, 1) kron_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const TcArgs a) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // carve: B stages | scalars (transposed: [n_scal][128]) | barriers | tmem base
+  const uint32_t stage_bytes = static_cast<uint32_t>(a.Np) * 128u;
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint8_t* sm_b = smem;
+  float* sm_S = reinterpret_cast<float*>(smem + static_cast<size_t>(a.stages) * stage_bytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sm_S + static_cast<size_t>(a.n_scal) * kTileM);
+  uint64_t* bar_full = bars;                    // [stages]  A stored (128 arrivals) + B landed (1 arrival + tx bytes)
+  uint64_t* bar_empty = bars + a.stages;        // [stages]  MMAs that read the stage have completed
+  uint64_t* bar_acc = bars + 2 * a.stages;      // accumulator complete
+  uint32_t* sm_tmem = reinterpret_cast<uint32_t*>(bars + 2 * a.stages + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int64_t b0 = static_cast<int64_t>(blockIdx.x) * kTileM;
+  const int c_begin = blockIdx.y * a.chunks_per_split;
+  const int c_end = min(a.nchunks, c_begin + a.chunks_per_split);
+
+  if (warp == 4 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_w)) : "memory");
+    for (int s = 0; s < a.stages; ++s) {
+      mbar_init(&bar_full[s], kGenThreads + 1);
+      mbar_init(&bar_empty[s], 1);
+    }
+    mbar_init(bar_acc, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 5) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(sm_tmem)), "r"(a.tmem_cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (warp < 4) {
+    // per-row scalars R = [1, f1, (f2)] transposed into shared memory: thread t owns row b0+t
+    const int t = threadIdx.x;
+    const int64_t b = b0 + t;
+    const bool live = b < a.B;
+    sm_S[t] = 1.0f;
+    for (int i = 0; i < a.d1; ++i) sm_S[(1 + i) * kTileM + t] = live ? __ldg(a.f1 + b * a.d1 + i) : 0.f;
+    if (a.d3 > 0)
+      for (int j = 0; j < a.d2; ++j) sm_S[(1 + a.d1 + j) * kTileM + t] = live ? __ldg(a.f2 + b * a.d2 + j) : 0.f;
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *sm_tmem;
+  const uint32_t tmem_d = tmem_base;                                  // accumulator: columns [0, Np)
+  const uint32_t tmem_a = tmem_base + static_cast<uint32_t>(a.Np);    // A ring: stages x 32 columns
+
+  if (warp == 4) {
+    // ===================== TMA producer: weight tiles [Np x 32] =====================
+    if (lane == 0) {
+      for (int c = c_begin; c < c_end; ++c) {
+        const int it = c - c_begin;
+        const int s = it % a.stages;
+        const uint32_t ph = (it / a.stages) & 1;
+        mbar_wait(&bar_empty[s], ph ^ 1);
+        mbar_arrive_expect_tx(&bar_full[s], stage_bytes);
+        tma_load_2d(sm_b + static_cast<size_t>(s) * stage_bytes, &tmap_w, c * kChunkK, 0, &bar_full[s]);
+      }
+    }
+  } else if (warp == 5) {
+    // ===================== MMA issuer (one thread) =====================
+    if (lane == 0) {
+      for (int c = c_begin; c < c_end; ++c) {
+        const int it = c - c_begin;
+        const int s = it % a.stages;
+        const uint32_t ph = (it / a.stages) & 1;
+        mbar_wait(&bar_full[s], ph);
+        tc_fence_after();
+        const uint32_t b_addr = smem_u32(sm_b + static_cast<size_t>(s) * stage_bytes);
+#pragma unroll
+        for (int j = 0; j < kChunkK / 8; ++j) {
+          const uint64_t b_desc = umma_desc_k_sw128(b_addr + j * 32);            // +8 tf32 along K inside the swizzle row
+          tc_mma_tf32_ts(tmem_d, tmem_a + s * kChunkK + j * 8, b_desc, a.idesc, (it > 0 || j > 0) ? 1u : 0u);
+        }
+        tc_commit(&bar_empty[s]);          // frees the A columns and the B tile of this stage
+      }
+      tc_commit(bar_acc);
+    }
+  } else {
+    // ===================== A generators (one thread per batch row / TMEM lane) =====================
+    const int t = threadIdx.x;
+    const int64_t b = b0 + t;
+    const bool live = b < a.B;
+    const uint32_t lane_base = static_cast<uint32_t>(warp * 32) << 16;
+    float v[kChunkK];
+#pragma unroll
+    for (int e = 0; e < kChunkK; ++e) v[e] = 0.f;
+    int cur_src = -1, cur_col = -1;
+    for (int c = c_begin; c < c_end; ++c) {
+      const int it = c - c_begin;
+      const int s = it % a.stages;
+      const uint32_t ph = (it / a.stages) & 1;
+      const int4 e0 = __ldg(a.table + 2 * c);
+      const int4 e1 = __ldg(a.table + 2 * c + 1);
+      if (e0.z != cur_src || e0.w != cur_col) {          // (re)load this row's 32-wide vector segment
+        cur_src = e0.z;
+        cur_col = e0.w;
+        const float* src = cur_src == 1 ? a.f1 : (cur_src == 2 ? a.f2 : a.f3);
+        const int d = cur_src == 1 ? a.d1 : (cur_src == 2 ? a.d2 : a.d3);
+#pragma unroll
+        for (int e = 0; e < kChunkK; ++e) {
+          float x = 0.f;
+          if (cur_src == 0) x = (e == 0) ? 1.0f : 0.f;
+          else if (live && e < e1.x) x = __ldg(src + b * d + cur_col + e);
+          v[e] = x;
+        }
+      }
+      float sc = sm_S[e0.x * kTileM + t] * sm_S[e0.y * kTileM + t];
+      if (kDropout) sc *= a.dr.scale;
+      uint32_t r[kChunkK];
+#pragma unroll
+      for (int e = 0; e < kChunkK; ++e) {
+        float x = sc * v[e];
+        if (kDropout) {
+          const int64_t cc = b * a.dr.pairs_per_row + ((e1.y + e * e1.z) >> 1);
+          const uint32_t h = kron_hash(static_cast<uint32_t>(cc), static_cast<uint32_t>(static_cast<uint64_t>(cc) >> 32),
+                                       a.dr.seed_lo, a.dr.seed_hi);
+          const uint32_t r16 = ((e1.y + e * e1.z) & 1) ? (h >> 16) : (h & 0xffffu);
+          x = (r16 >= a.dr.thresh) ? x : 0.f;
+        }
+        r[e] = __float_as_uint(x) + 0x1000u;              // round-to-nearest onto the TF32 grid (hardware truncates)
+      }
+      mbar_wait(&bar_empty[s], ph ^ 1);
+      tc_fence_after();
+      tc_st_32x32b_x32(tmem_a + lane_base + s * kChunkK, r);
+      tc_wait_st();
+      tc_fence_before();
+      mbar_arrive(&bar_full[s]);
+    }
+    // ===================== epilogue: TMEM accumulator -> registers -> y =====================
+    mbar_wait(bar_acc, 0);
+    tc_fence_after();
+    float* dst = a.out + (static_cast<int64_t>(blockIdx.y) * a.B + b) * a.N;
+    const bool add_bias = (a.ksplit == 1) && (a.bias != nullptr);
+    for (int n0 = 0; n0 < a.Np; n0 += 32) {
+      uint32_t acc[32];
+      tc_ld_32x32b_x32(tmem_d + lane_base + n0, acc);
+      tc_wait_ld();
+      if (live) {
+#pragma unroll
+        for (int e = 0; e < 32; ++e) {
+          const int n = n0 + e;
+          if (n < a.N) dst[n] = __uint_as_float(acc[e]) + (add_bias ? __ldg(a.bias + n) : 0.f);
+        }
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 5) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(a.tmem_cols) : "memory");
+  }
+}
+
+// sum split-K partials in split order and add the bias
+__global__ void kron_reduce_kernel(const float* __restrict__ part, int32_t ksplit, int64_t BN, int32_t N,
+                                   const float* __restrict__ bias, float* __restrict__ y) {
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < BN;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    float t = 0.f;
+    for (int z = 0; z < ksplit; ++z) t += part[z * BN + i];
+    y[i] = t + (bias ? bias[i % N] : 0.f);
+  }
+}
+
+// dense W[N, Kk] fp32 -> packed Wp[Np, 32*nchunks] in chunk order, TF32-rounded (RN), zero padded
+__global__ void kron_pack_kernel(const float* __restrict__ W, int32_t N, int32_t Np, int32_t Kk, const int4* __restrict__ table,
+                                 int32_t nchunks, float* __restrict__ Wp) {
+  const int64_t total = static_cast<int64_t>(Np) * nchunks * kChunkK;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t kp = i % (static_cast<int64_t>(nchunks) * kChunkK);
+    const int n = static_cast<int>(i / (static_cast<int64_t>(nchunks) * kChunkK));
+    const int c = static_cast<int>(kp / kChunkK), e = static_cast<int>(kp % kChunkK);
+    const int4 e1 = __ldg(table + 2 * c + 1);
+    float w = 0.f;
+    if (n < N && e < e1.x) w = __ldg(W + static_cast<int64_t>(n) * Kk + e1.y + e * e1.z);
+    uint32_t u = __float_as_uint(w);
+    u = (u + 0x1000u) & 0xFFFFE000u;
+    Wp[i] = __uint_as_float(u);
+  }
+}
+
+// ---------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+struct MapKey {
+  const void* ptr;
+  int32_t Np, Kp;
+  bool operator==(const MapKey& o) const { return ptr == o.ptr && Np == o.Np && Kp == o.Kp; }
+};
+struct MapKeyHash {
+  size_t operator()(const MapKey& k) const {
+    return std::hash<const void*>()(k.ptr) ^ (static_cast<size_t>(k.Np) << 40) ^ static_cast<size_t>(k.Kp);
+  }
+};
+
+// cached TMA descriptors keyed by pointer + shape (the only global state of the library)
+int get_tensor_map(const float* Wp, int32_t Np, int32_t Kp, CUtensorMap* out) {
+  static std::mutex mu;
+  static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> cache;
+  std::lock_guard<std::mutex> lock(mu);
+  const MapKey key{Wp, Np, Kp};
+  auto it = cache.find(key);
+  if (it != cache.end()) {
+    *out = it->second;
+    return MML_OK;
+  }
+  EncodeTiledFn enc = get_encode_fn();
+  MML_REQUIRE(enc != nullptr, MML_ERR_CUDA, "kron: cuTensorMapEncodeTiled entry point unavailable");
+  CUtensorMap m;
+  const cuuint64_t gdim[2] = {static_cast<cuuint64_t>(Kp), static_cast<cuuint64_t>(Np)};
+  const cuuint64_t gstride[1] = {static_cast<cuuint64_t>(Kp) * sizeof(float)};
+  const cuuint32_t box[2] = {static_cast<cuuint32_t>(kChunkK), static_cast<cuuint32_t>(Np)};
+  const cuuint32_t estride[2] = {1, 1};
+  const CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(Wp), gdim, gstride, box, estride,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  MML_REQUIRE(r == CUDA_SUCCESS, MML_ERR_CUDA, "kron: cuTensorMapEncodeTiled failed (%d)", static_cast<int>(r));
+  if (cache.size() > 256) cache.clear();
+  cache[key] = m;
+  *out = m;
+  return MML_OK;
+}
+
+struct TcPlan {
+  int32_t nchunks, Np, n_scal, stages, tmem_cols, ksplit, chunks_per_split;
+  size_t smem;
+  bool ok;
+};
+
+TcPlan make_tc_plan(int64_t B, int32_t N, int32_t d1, int32_t d2, int32_t d3) {
+  TcPlan p{};
+  p.nchunks = static_cast<int32_t>(build_chunks(d1, d2, d3).size());
+  p.Np = round_np(N);
+  p.n_scal = 1 + d1 + (d3 > 0 ? d2 : 0);
+  const size_t fixed = static_cast<size_t>(p.n_scal) * kTileM * sizeof(float) + 256 + 1024;
+  const size_t budget = 227 * 1024;
+  const size_t stage = static_cast<size_t>(p.Np) * 128;
+  int stages = fixed < budget ? static_cast<int>((budget - fixed) / stage) : 0;
+  if (stages > 4) stages = 4;
+  p.stages = stages;
+  p.ok = p.Np <= 256 && stages >= 2;
+  p.smem = fixed + static_cast<size_t>(stages > 0 ? stages : 0) * stage;
+  int cols = p.Np + stages * kChunkK;
+  int pow2 = 32;
+  while (pow2 < cols) pow2 <<= 1;
+  p.tmem_cols = pow2;
+  if (pow2 > 512) p.ok = false;
+  // split K when the batch alone cannot fill the 148 SMs
+  const int64_t tiles = (B + kTileM - 1) / kTileM;
+  int64_t ks = 1;
+  if (tiles < 148) ks = (148 + tiles - 1) / tiles;
+  const int64_t max_ks = p.nchunks / 8 > 0 ? p.nchunks / 8 : 1;      // keep >= 8 chunks per split
+  if (ks > max_ks) ks = max_ks;
+  if (ks > 32) ks = 32;
+  p.chunks_per_split = static_cast<int32_t>((p.nchunks + ks - 1) / ks);
+  p.ksplit = (p.nchunks + p.chunks_per_split - 1) / p.chunks_per_split;
+  return p;
+}
+
+uint32_t make_idesc_tf32(int M, int N) {
+  uint32_t d = 0;
+  d |= 1u << 4;                                   // D format: F32
+  d |= 2u << 7;                                   // A format: TF32
+  d |= 2u << 10;                                  // B format: TF32
+  d |= static_cast<uint32_t>(N >> 3) << 17;       // N / 8
+  d |= static_cast<uint32_t>(M >> 4) << 24;       // M / 16
+  return d;                                       // A, B K-major; no negate; dense
+}
+
+}  // namespace
+}  // namespace mml
+
+using namespace mml;
+
+extern "C" int64_t mml_kron_num_chunks(int32_t d1, int32_t d2, int32_t d3) {
+  if (d1 < 1 || d2 < 1 || d3 < 0) return -1;
+  return static_cast<int64_t>(build_chunks(d1, d2, d3).size());
+}
+
+extern "C" int mml_kron_chunk_table_host(int32_t d1, int32_t d2, int32_t d3, int32_t* table_host) {
+  MML_REQUIRE(table_host && d1 >= 1 && d2 >= 1 && d3 >= 0, MML_ERR_INVALID_ARG, "kron_chunk_table: bad arguments");
+  const std::vector<Chunk> ch = build_chunks(d1, d2, d3);
+  memcpy(table_host, ch.data(), ch.size() * sizeof(Chunk));
+  return MML_OK;
+}
+
+extern "C" int mml_kron_pack_weight(const float* W, int32_t N, int32_t d1, int32_t d2, int32_t d3, const int32_t* table,
+                                    float* Wp, void* stream) {
+  MML_REQUIRE(W && table && Wp && N >= 1, MML_ERR_INVALID_ARG, "kron_pack_weight: bad arguments");
+  MML_REQUIRE(aligned16(table) && aligned16(Wp), MML_ERR_INVALID_ARG, "kron_pack_weight: table / Wp must be 16-byte aligned");
+  const KronShape s = make_kron_shape(d1, d2, d3);
+  const int32_t nchunks = static_cast<int32_t>(build_chunks(d1, d2, d3).size());
+  const int64_t total = static_cast<int64_t>(round_np(N)) * nchunks * kChunkK;
+  int64_t grid = (total + 255) / 256;
+  if (grid > 148 * 16) grid = 148 * 16;
+  kron_pack_kernel<<<static_cast<unsigned>(grid), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      W, N, round_np(N), s.Kk, reinterpret_cast<const int4*>(table), nchunks, Wp);
+  return check_launch("kron_pack_kernel");
+}
+
+extern "C" int64_t mml_kron_packed_floats(int32_t N, int32_t d1, int32_t d2, int32_t d3) {
+  if (N < 1 || d1 < 1 || d2 < 1 || d3 < 0) return -1;
+  return static_cast<int64_t>(round_np(N)) * static_cast<int64_t>(build_chunks(d1, d2, d3).size()) * kChunkK;
+}
+
+extern "C" int mml_kron_fwd_supported(int64_t B, int32_t N, int32_t d1, int32_t d2, int32_t d3) {
+  if (B < 0 || N < 1 || d1 < 1 || d2 < 1 || d3 < 0) return 0;
+  return make_tc_plan(B, N, d1, d2, d3).ok ? 1 : 0;
+}
+
+extern "C" size_t mml_kron_fwd_workspace_bytes(int64_t B, int32_t N, int32_t d1, int32_t d2, int32_t d3) {
+  if (B < 0 || N < 1 || d1 < 1 || d2 < 1 || d3 < 0) return 0;
+  const TcPlan p = make_tc_plan(B, N, d1, d2, d3);
+  return (p.ksplit > 1 ? static_cast<size_t>(p.ksplit) * B * N * sizeof(float) : 0) + 256;
+}
+
+extern "C" int mml_kron_linear_fwd(const float* f1, const float* f2, const float* f3, int64_t B, int32_t d1, int32_t d2,
+                                   int32_t d3, const int32_t* table, const float* Wp, const float* bias, int32_t N,
+                                   float drop_p, uint64_t seed, int32_t training, float* y, void* workspace,
+                                   size_t workspace_bytes, void* stream) {
+  MML_REQUIRE(f1 && f2 && table && Wp && y, MML_ERR_INVALID_ARG, "kron_linear_fwd: null pointer");
+  MML_REQUIRE((d3 > 0) == (f3 != nullptr), MML_ERR_INVALID_ARG, "kron_linear_fwd: f3 and d3 must both be set or both be absent");
+  MML_REQUIRE(B >= 0 && d1 >= 1 && d2 >= 1 && d3 >= 0 && N >= 1, MML_ERR_INVALID_ARG, "kron_linear_fwd: bad sizes");
+  MML_REQUIRE(aligned16(table) && (reinterpret_cast<uintptr_t>(Wp) & 127u) == 0, MML_ERR_INVALID_ARG,
+              "kron_linear_fwd: table must be 16-byte and Wp 128-byte aligned");
+  if (B == 0) return MML_OK;
+  const TcPlan p = make_tc_plan(B, N, d1, d2, d3);
+  MML_REQUIRE(p.ok, MML_ERR_UNSUPPORTED, "kron_linear_fwd: N=%d (<=256) / factor widths (%d,%d,%d) exceed the tile budget", N,
+              d1, d2, d3);
+  MML_REQUIRE(workspace_bytes >= mml_kron_fwd_workspace_bytes(B, N, d1, d2, d3) && (p.ksplit == 1 || workspace != nullptr),
+              MML_ERR_WORKSPACE, "kron_linear_fwd: workspace too small");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  CUtensorMap tmap;
+  int rc = get_tensor_map(Wp, p.Np, p.nchunks * kChunkK, &tmap);
+  if (rc != MML_OK) return rc;
+  const KronShape s = make_kron_shape(d1, d2, d3);
+  TcArgs a{};
+  a.f1 = f1; a.f2 = f2; a.f3 = f3;
+  a.table = reinterpret_cast<const int4*>(table);
+  a.bias = bias;
+  a.out = p.ksplit == 1 ? y : static_cast<float*>(workspace);
+  a.B = B; a.d1 = d1; a.d2 = d2; a.d3 = d3; a.N = N; a.Np = p.Np;
+  a.nchunks = p.nchunks; a.chunks_per_split = p.chunks_per_split; a.ksplit = p.ksplit;
+  a.n_scal = p.n_scal; a.stages = p.stages; a.tmem_cols = p.tmem_cols;
+  a.idesc = make_idesc_tf32(kTileM, p.Np);
+  a.dr = make_kron_dropout(drop_p, seed, training, s.Kk);
+  const dim3 grid(static_cast<unsigned>((B + kTileM - 1) / kTileM), p.ksplit);
+  if (a.dr.thresh != 0u) {
+    MML_CUDA(cudaFuncSetAttribute(kron_fwd_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(p.smem)));
+    kron_fwd_tc_kernel<true><<<grid, kThreadsTc, p.smem, st>>>(tmap, a);
+  } else {
+    MML_CUDA(cudaFuncSetAttribute(kron_fwd_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(p.smem)));
+    kron_fwd_tc_kernel<false><<<grid, kThreadsTc, p.smem, st>>>(tmap, a);
+  }
+  rc = check_launch("kron_fwd_tc_kernel");
+  if (rc != MML_OK) return rc;
+  if (p.ksplit > 1) {
+    const int64_t BN = B * N;
+    int64_t g = (BN + 255) / 256;
+    if (g > 148 * 8) g = 148 * 8;
+    kron_reduce_kernel<<<static_cast<unsigned>(g), 256, 0, st>>>(static_cast<const float*>(workspace), p.ksplit, BN, N, bias, y);
+    rc = check_launch("kron_reduce_kernel");
+  }
+  return rc;
+}

@@ -1,0 +1,242 @@
+"""Gated Kronecker fusion -- host-side mirror of the reference's `MICCAI-2022/fusion.py`
+(`BilinearFusion` :6-63, `TrilinearFusion_A` :66-132, `TrilinearFusion_B` :135-201) with the
+same constructor keywords, `forward` signatures, sub-module / state_dict names and RNG
+consumption order (same seed => same initial weights).
+
+What runs where:
+  * gates (`linear_h*`, `linear_z*`, `linear_o*`), BatchNorm/ReLU/Dropout on [B, mmhid] and
+    `encoder2` are small and stay host-side PyTorch;
+  * the hot contraction -- append-1, outer product(s), flatten, `post_fusion_dropout`,
+    `encoder1[0]` -- is ONE kernel family that never materialises the (d+1)^2 / (d+1)^3 tensor:
+    forward on tcgen05 tensor cores (`mml_kron_linear_fwd`), backward on CUDA cores
+    (`mml_kron_linear_bwd_simt`) in this round.
+  * `post_fusion_dropout` masks come from a counter-based hash of (seed, b, k) instead of
+    torch's Philox stream (a tensor that is never stored cannot carry a torch mask); eval mode
+    and p=0 are bit-for-bit the reference's math.
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+import torch.nn as nn
+from torch.autograd.function import once_differentiable
+
+from . import _cabi
+
+
+def init_max_weights(module):
+    """utils.py:239-244 of the reference: every nn.Linear gets N(0, 1/sqrt(fan_in)) weights, zero bias."""
+    for m in module.modules():
+        if type(m) == nn.Linear:
+            stdv = 1. / math.sqrt(m.weight.size(1))
+            m.weight.data.normal_(0, stdv)
+            m.bias.data.zero_()
+
+
+# --------------------------------------------------------------------------- #
+# the Kronecker linear op
+# --------------------------------------------------------------------------- #
+class KronLinearState:
+    """Per-module cache: chunk table (device) and the packed TF32 copy of the weight, refreshed
+    whenever the dense weight's version counter or storage changes."""
+
+    def __init__(self, dims):
+        self.dims = tuple(int(d) for d in dims) + ((0,) if len(dims) == 2 else ())
+        self.table = None
+        self.packed = None
+        self.packed_key = None
+        self.path = "auto"          # "auto" | "simt" (tests use "simt" as the exact-fp32 cross-check)
+
+    def ensure(self, weight):
+        lib = _cabi.lib()
+        d1, d2, d3 = self.dims
+        dev = weight.device
+        if self.table is None or self.table.device != dev:
+            n = lib.mml_kron_num_chunks(d1, d2, d3)
+            host = torch.empty(n * 8, dtype=torch.int32)
+            _cabi.check(lib.mml_kron_chunk_table_host(d1, d2, d3, _cabi.hptr(host)), "mml_kron_chunk_table_host")
+            self.table = host.to(dev)
+            self.packed_key = None
+        key = (weight.data_ptr(), weight._version, tuple(weight.shape))
+        if key != self.packed_key:
+            N = weight.shape[0]
+            nfl = lib.mml_kron_packed_floats(N, d1, d2, d3)
+            if self.packed is None or self.packed.numel() != nfl or self.packed.device != dev:
+                self.packed = torch.empty(nfl, dtype=torch.float32, device=dev)
+            _cabi.check(lib.mml_kron_pack_weight(_cabi.dptr(weight.detach()), N, d1, d2, d3, _cabi.dptr(self.table),
+                                                 _cabi.dptr(self.packed), _cabi.cur_stream(dev)), "mml_kron_pack_weight")
+            self.packed_key = key
+
+
+def _tc_supported(B, N, dims):
+    return bool(_cabi.lib().mml_kron_fwd_supported(B, N, *dims))
+
+
+class _KronLinearFn(torch.autograd.Function):
+    """y = kron(append1(f1), append1(f2)[, append1(f3)]) * mask @ W^T + bias, without the Kronecker tensor."""
+
+    @staticmethod
+    def forward(ctx, state, weight, bias, drop_p, training, seed, *factors):
+        lib = _cabi.lib()
+        d1, d2, d3 = state.dims
+        fs = [f.contiguous() for f in factors]
+        B = fs[0].shape[0]
+        N = weight.shape[0]
+        dev = fs[0].device
+        st = _cabi.cur_stream(dev)
+        y = torch.empty(B, N, dtype=torch.float32, device=dev)
+        f3p = _cabi.dptr(fs[2]) if d3 > 0 else None
+        w = weight.detach().contiguous()
+        bptr = _cabi.dptr(bias.detach().contiguous()) if bias is not None else None
+        use_tc = state.path == "auto" and _tc_supported(B, N, state.dims)
+        if use_tc:
+            state.ensure(weight)
+            nws = lib.mml_kron_fwd_workspace_bytes(B, N, d1, d2, d3)
+            ws = torch.empty(nws, dtype=torch.uint8, device=dev)
+            rc = lib.mml_kron_linear_fwd(_cabi.dptr(fs[0]), _cabi.dptr(fs[1]), f3p, B, d1, d2, d3, _cabi.dptr(state.table),
+                                         _cabi.dptr(state.packed), bptr, N, float(drop_p), int(seed), int(training),
+                                         _cabi.dptr(y), _cabi.dptr(ws), nws, st)
+            _cabi.check(rc, "mml_kron_linear_fwd")
+        else:
+            rc = lib.mml_kron_linear_fwd_simt(_cabi.dptr(fs[0]), _cabi.dptr(fs[1]), f3p, B, d1, d2, d3, _cabi.dptr(w), bptr,
+                                              N, float(drop_p), int(seed), int(training), _cabi.dptr(y), st)
+            _cabi.check(rc, "mml_kron_linear_fwd_simt")
+        ctx.save_for_backward(w, *fs)
+        ctx.cfg = (state.dims, float(drop_p), int(training), int(seed), bias is not None)
+        return y
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dy):
+        lib = _cabi.lib()
+        w, *fs = ctx.saved_tensors
+        (d1, d2, d3), drop_p, training, seed, has_bias = ctx.cfg
+        dy = dy.contiguous()
+        B, N = dy.shape
+        dev = dy.device
+        need_w = ctx.needs_input_grad[1]
+        need_f = any(ctx.needs_input_grad[6:])
+        dW = torch.empty_like(w) if need_w else None
+        dfs = [torch.empty_like(f) for f in fs] if need_f else [None] * len(fs)
+        rc = lib.mml_kron_linear_bwd_simt(
+            _cabi.dptr(fs[0]), _cabi.dptr(fs[1]), _cabi.dptr(fs[2]) if d3 > 0 else None, B, d1, d2, d3, _cabi.dptr(w),
+            _cabi.dptr(dy), N, drop_p, seed, training, _cabi.dptr(dfs[0]), _cabi.dptr(dfs[1]),
+            _cabi.dptr(dfs[2]) if d3 > 0 else None, _cabi.dptr(dW), _cabi.cur_stream(dev))
+        _cabi.check(rc, "mml_kron_linear_bwd_simt")
+        dbias = dy.sum(0) if (has_bias and ctx.needs_input_grad[2]) else None
+        return (None, dW, dbias, None, None, None, *dfs)
+
+
+def kron_linear(state: KronLinearState, factors, weight, bias, drop_p=0.0, training=False, seed=None):
+    """Public functional form (used by the modules below and by the tests)."""
+    for f in factors:
+        if not f.is_cuda:
+            raise RuntimeError("Kronecker fusion runs on CUDA tensors only (no CPU fallback)")
+        if f.dtype != torch.float32:
+            raise RuntimeError(f"Kronecker fusion computes from fp32 factors; got {f.dtype}")
+    if seed is None:
+        seed = int(torch.randint(0, 2 ** 62, (1,)).item()) if (training and drop_p > 0) else 0
+    return _KronLinearFn.apply(state, weight, bias, drop_p, training, seed, *factors)
+
+
+# --------------------------------------------------------------------------- #
+# modules
+# --------------------------------------------------------------------------- #
+class _GatedKronFusion(nn.Module):
+    """Shared machinery of the three fusion modules.  Sub-modules are created in the reference's
+    order (h, z, o per branch; post_fusion_dropout; encoder1; encoder2) so that state_dict keys and
+    the global-RNG draws match fusion.py."""
+
+    def _build(self, dims_og, scales, gate_inputs, use_bilinear, skip, mmhid, dropout_rate, post_p, batchnorm):
+        dims = [d // s for d, s in zip(dims_og, scales)]                 # fusion.py:17 / :76
+        self._dims = dims
+        self._gate_inputs = gate_inputs                                  # per branch: which (a, b) feed linear_z
+        for t, (d_og, d) in enumerate(zip(dims_og, dims), start=1):
+            a, b = gate_inputs[t - 1]
+            setattr(self, f"linear_h{t}", nn.Sequential(nn.Linear(d_og, d), nn.ReLU()))
+            z = nn.Bilinear(dims_og[a], dims_og[b], d) if use_bilinear else nn.Sequential(nn.Linear(dims_og[a] + dims_og[b], d))
+            setattr(self, f"linear_z{t}", z)
+            setattr(self, f"linear_o{t}", nn.Sequential(nn.Linear(d, d), nn.ReLU(), nn.Dropout(p=dropout_rate)))
+        self.post_fusion_dropout = nn.Dropout(p=post_p)
+        kk = 1
+        for d in dims:
+            kk *= d + 1
+        skip_dim = (sum(dims) + len(dims)) if skip else 0
+        norm = (lambda: [nn.BatchNorm1d(mmhid)]) if batchnorm else (lambda: [])
+        self.encoder1 = nn.Sequential(nn.Linear(kk, mmhid), *norm(), nn.ReLU(), nn.Dropout(p=dropout_rate))
+        self.encoder2 = nn.Sequential(nn.Linear(mmhid + skip_dim, mmhid), *norm(), nn.ReLU(), nn.Dropout(p=dropout_rate))
+        init_max_weights(self)
+        self._kron = KronLinearState(dims)
+
+    def _branch(self, t, vecs, gated):
+        own = vecs[t - 1]
+        if gated:
+            a, b = self._gate_inputs[t - 1]
+            h = getattr(self, f"linear_h{t}")(own)
+            zmod = getattr(self, f"linear_z{t}")
+            z = zmod(vecs[a], vecs[b]) if self.use_bilinear else zmod(torch.cat((vecs[a], vecs[b]), dim=1))
+            return getattr(self, f"linear_o{t}")(torch.sigmoid(z) * h)
+        return getattr(self, f"linear_o{t}")(own)
+
+    def _fuse(self, outs):
+        lin = self.encoder1[0]
+        y = kron_linear(self._kron, outs, lin.weight, lin.bias, self.post_fusion_dropout.p, self.training)
+        out = self.encoder1[1:](y)
+        if self.skip:
+            ones = outs[0].new_ones(outs[0].shape[0], 1)
+            out = torch.cat([out] + [torch.cat((o, ones), 1) for o in outs], 1)
+        return self.encoder2(out)
+
+
+class BilinearFusion(_GatedKronFusion):
+    def __init__(self, skip=1, use_bilinear=1, gate1=1, gate2=1, dim1=32, dim2=32,
+                 scale_dim1=1, scale_dim2=1, mmhid=64, dropout_rate=0.25):
+        super(BilinearFusion, self).__init__()
+        self.skip = skip
+        self.use_bilinear = use_bilinear
+        self.gate1 = gate1
+        self.gate2 = gate2
+        self.relu = nn.ReLU(inplace=False)
+        self._build([dim1, dim2], [scale_dim1, scale_dim2], [(0, 1), (0, 1)], use_bilinear, skip, mmhid,
+                    dropout_rate, post_p=dropout_rate, batchnorm=True)
+
+    def forward(self, vec1, vec2):
+        vecs = [self.relu(vec1), self.relu(vec2)]                         # fusion.py:38-39
+        o1 = self._branch(1, vecs, self.gate1)
+        o2 = self._branch(2, vecs, self.gate2)
+        return self._fuse([o1, o2])
+
+
+class _TrilinearFusion(_GatedKronFusion):
+    _GRAPH_GATE = (1, 2)
+
+    def __init__(self, skip=1, use_bilinear=1, gate1=1, gate2=1, gate3=1, dim1=32, dim2=32, dim3=32,
+                 scale_dim1=1, scale_dim2=1, scale_dim3=1, mmhid=96, dropout_rate=0.25):
+        super().__init__()
+        self.skip = skip
+        self.use_bilinear = use_bilinear
+        self.gate1 = gate1
+        self.gate2 = gate2
+        self.gate3 = gate3
+        # path gated by omic, graph gated by omic (A) or path (B), omic gated by path; post-fusion p is a fixed 0.25;
+        # no input ReLU and no BatchNorm (fusion.py:93-95, :99-120)
+        self._build([dim1, dim2, dim3], [scale_dim1, scale_dim2, scale_dim3], [(0, 2), self._GRAPH_GATE, (0, 2)],
+                    use_bilinear, skip, mmhid, dropout_rate, post_p=0.25, batchnorm=False)
+
+    def forward(self, vec1, vec2, vec3):
+        vecs = [vec1, vec2, vec3]
+        o1 = self._branch(1, vecs, self.gate1)
+        o2 = self._branch(2, vecs, self.gate2)
+        o3 = self._branch(3, vecs, self.gate3)
+        return self._fuse([o1, o2, o3])
+
+
+class TrilinearFusion_A(_TrilinearFusion):
+    """fusion.py:66-132 -- graph branch gated with (vec2, vec3)."""
+    _GRAPH_GATE = (1, 2)
+
+
+class TrilinearFusion_B(_TrilinearFusion):
+    """fusion.py:135-201 -- graph branch gated with (vec2, vec1)."""
+    _GRAPH_GATE = (1, 0)

@@ -123,3 +123,33 @@ def distill_kl(y_s, y_t, T):
     p_s = F.log_softmax(y_s / T, dim=1)
     p_t = F.softmax(y_t / T, dim=1)
     return F.kl_div(p_s, p_t, reduction="sum") * (T ** 2) / y_s.shape[0]
+
+
+def kron_dropout_mask(seed: int, B: int, Kk: int, p: float) -> torch.Tensor:
+    """The counter-based `post_fusion_dropout` multiplier this repo DEFINES for the never-stored
+    Kronecker tensor (csrc/kron_common.cuh; torch's Philox mask stream cannot apply to a tensor
+    that does not exist, so mask parity with the reference is "unpinned" by construction).
+    Returns float32 [B, Kk] with entries 0 or 65536/(65536 - round(p*65536))."""
+    import numpy as np
+    thresh = min(int(p * 65536.0 + 0.5), 65535) if p > 0 else 0
+    if thresh == 0:
+        return torch.ones(B, Kk)
+    pairs = (Kk + 1) // 2
+    b = np.arange(B, dtype=np.uint64)[:, None]
+    k = np.arange(Kk, dtype=np.uint64)[None, :]
+    c = b * np.uint64(pairs) + (k >> np.uint64(1))
+    lo = (c & np.uint64(0xFFFFFFFF)).astype(np.uint32)
+    hi = (c >> np.uint64(32)).astype(np.uint32)
+    s_lo, s_hi = np.uint32(seed & 0xFFFFFFFF), np.uint32((seed >> 32) & 0xFFFFFFFF)
+    with np.errstate(over="ignore"):
+        h = lo ^ s_lo
+        h = h * np.uint32(0x9E3779B1)
+        h = h ^ (hi ^ s_hi)
+        h = h ^ (h >> np.uint32(16))
+        h = h * np.uint32(0x7FEB352D)
+        h = h ^ (h >> np.uint32(15))
+        h = h * np.uint32(0x846CA68B)
+        h = h ^ (h >> np.uint32(16))
+    r16 = np.where((k & np.uint64(1)) != 0, h >> np.uint32(16), h & np.uint32(0xFFFF))
+    scale = np.float32(65536.0) / np.float32(65536 - thresh)
+    return torch.from_numpy(np.where(r16 >= thresh, scale, np.float32(0)).astype(np.float32))

