@@ -34,8 +34,11 @@ namespace {
 
 constexpr int kTileM = 128;
 constexpr int kChunkK = 32;                 // tf32 elements per chunk = one 128-byte swizzle row
-constexpr int kGenThreads = 128;
-constexpr int kThreadsTc = 192;
+constexpr int kGenWarps = 8;                // warp g: TMEM lanes 32*(g%4).., chunk columns 16*(g/4)..
+constexpr int kGenThreads = kGenWarps * 32;
+constexpr int kThreadsTc = kGenThreads + 64;   // + TMA warp + MMA/alloc warp
+constexpr int kHalf = kChunkK / 2;          // columns of a chunk handled by one generator thread
+constexpr int kMaxSmemTable = 48 * 1024;    // chunk tables up to this size are staged in shared memory
 constexpr uint32_t kSpinLimit = 1u << 28;   // mbarrier spin guard: trap instead of hanging the GPU
 
 struct Chunk {                // 32 bytes, read as two int4
@@ -131,24 +134,18 @@ __device__ __forceinline__ void tc_mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem,
       ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
-__device__ __forceinline__ void tc_st_32x32b_x32(uint32_t taddr, const uint32_t (&r)[32]) {
+__device__ __forceinline__ void tc_st_32x32b_x16(uint32_t taddr, const uint32_t (&r)[16]) {
   asm volatile(
-      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
-      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
       ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
-      "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]),
-      "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]),
-      "r"(r[29]), "r"(r[30]), "r"(r[31])
+      "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
       : "memory");
 }
-__device__ __forceinline__ void tc_ld_32x32b_x32(uint32_t taddr, uint32_t (&r)[32]) {
+__device__ __forceinline__ void tc_ld_32x32b_x16(uint32_t taddr, uint32_t (&r)[16]) {
   asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
       : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
-        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
-        "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
-        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
       : "r"(taddr)
       : "memory");
 }
@@ -180,6 +177,7 @@ struct TcArgs {
   int32_t n_scal;           // 1 + d1 (+ d2 when trilinear)
   int32_t stages;
   int32_t tmem_cols;
+  int32_t table_in_smem;
   uint32_t idesc;
   KronDropout dr;
 };
@@ -187,13 +185,14 @@ struct TcArgs {
 template <bool kDropout>
 __global__ void __launch_bounds__(kThreadsTc, 1) kron_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const TcArgs a) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  // carve: B stages | scalars (transposed: [n_scal][128]) | barriers | tmem base
+  // carve: B stages | scalars (transposed: [n_scal][128]) | chunk table | barriers | tmem base
   const uint32_t stage_bytes = static_cast<uint32_t>(a.Np) * 128u;
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   uint8_t* sm_b = smem;
   float* sm_S = reinterpret_cast<float*>(smem + static_cast<size_t>(a.stages) * stage_bytes);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sm_S + static_cast<size_t>(a.n_scal) * kTileM);
-  uint64_t* bar_full = bars;                    // [stages]  A stored (128 arrivals) + B landed (1 arrival + tx bytes)
+  int4* sm_tab = reinterpret_cast<int4*>(sm_S + static_cast<size_t>(a.n_scal) * kTileM);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sm_tab + (a.table_in_smem ? 2 * a.nchunks : 0));
+  uint64_t* bar_full = bars;                    // [stages]  A stored (256 arrivals) + B landed (1 arrival + tx bytes)
   uint64_t* bar_empty = bars + a.stages;        // [stages]  MMAs that read the stage have completed
   uint64_t* bar_acc = bars + 2 * a.stages;      // accumulator complete
   uint32_t* sm_tmem = reinterpret_cast<uint32_t*>(bars + 2 * a.stages + 1);
@@ -204,7 +203,7 @@ __global__ void __launch_bounds__(kThreadsTc, 1) kron_fwd_tc_kernel(const __grid
   const int c_begin = blockIdx.y * a.chunks_per_split;
   const int c_end = min(a.nchunks, c_begin + a.chunks_per_split);
 
-  if (warp == 4 && lane == 0) {
+  if (warp == kGenWarps && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_w)) : "memory");
     for (int s = 0; s < a.stages; ++s) {
       mbar_init(&bar_full[s], kGenThreads + 1);
@@ -213,20 +212,37 @@ __global__ void __launch_bounds__(kThreadsTc, 1) kron_fwd_tc_kernel(const __grid
     mbar_init(bar_acc, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 5) {
+  if (warp == kGenWarps + 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(sm_tmem)), "r"(a.tmem_cols)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
-  if (warp < 4) {
-    // per-row scalars R = [1, f1, (f2)] transposed into shared memory: thread t owns row b0+t
-    const int t = threadIdx.x;
-    const int64_t b = b0 + t;
+  if (a.table_in_smem)
+    for (int i = c_begin * 2 + threadIdx.x; i < c_end * 2; i += kThreadsTc) sm_tab[i] = __ldg(a.table + i);
+  if (warp < kGenWarps) {
+    // per-row scalars R = [1, f1, (f2)] transposed into shared memory.  Row r is served by threads r and r+128,
+    // each loading half of the scalars, 8 independent loads at a time.
+    const int row = threadIdx.x & (kTileM - 1);
+    const int half = threadIdx.x >> 7;
+    const int64_t b = b0 + row;
     const bool live = b < a.B;
-    sm_S[t] = 1.0f;
-    for (int i = 0; i < a.d1; ++i) sm_S[(1 + i) * kTileM + t] = live ? __ldg(a.f1 + b * a.d1 + i) : 0.f;
-    if (a.d3 > 0)
-      for (int j = 0; j < a.d2; ++j) sm_S[(1 + a.d1 + j) * kTileM + t] = live ? __ldg(a.f2 + b * a.d2 + j) : 0.f;
+    const int ns = a.n_scal - 1;
+    const int per = (ns + 1) / 2;
+    const int lo = half * per, hi = min(ns, lo + per);
+    if (half == 0) sm_S[row] = 1.0f;
+    for (int i0 = lo; i0 < hi; i0 += 8) {
+      float tmp[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int i = i0 + u;
+        float x = 0.f;
+        if (live && i < hi) x = (i < a.d1) ? __ldg(a.f1 + b * a.d1 + i) : __ldg(a.f2 + b * a.d2 + (i - a.d1));
+        tmp[u] = x;
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+        if (i0 + u < hi) sm_S[(1 + i0 + u) * kTileM + row] = tmp[u];
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -234,8 +250,9 @@ __global__ void __launch_bounds__(kThreadsTc, 1) kron_fwd_tc_kernel(const __grid
   const uint32_t tmem_base = *sm_tmem;
   const uint32_t tmem_d = tmem_base;                                  // accumulator: columns [0, Np)
   const uint32_t tmem_a = tmem_base + static_cast<uint32_t>(a.Np);    // A ring: stages x 32 columns
+  const int4* tab = a.table_in_smem ? sm_tab : a.table;
 
-  if (warp == 4) {
+  if (warp == kGenWarps) {
     // ===================== TMA producer: weight tiles [Np x 32] =====================
     if (lane == 0) {
       for (int c = c_begin; c < c_end; ++c) {
@@ -247,7 +264,7 @@ __global__ void __launch_bounds__(kThreadsTc, 1) kron_fwd_tc_kernel(const __grid
         tma_load_2d(sm_b + static_cast<size_t>(s) * stage_bytes, &tmap_w, c * kChunkK, 0, &bar_full[s]);
       }
     }
-  } else if (warp == 5) {
+  } else if (warp == kGenWarps + 1) {
     // ===================== MMA issuer (one thread) =====================
     if (lane == 0) {
       for (int c = c_begin; c < c_end; ++c) {
@@ -267,77 +284,107 @@ __global__ void __launch_bounds__(kThreadsTc, 1) kron_fwd_tc_kernel(const __grid
       tc_commit(bar_acc);
     }
   } else {
-    // ===================== A generators (one thread per batch row / TMEM lane) =====================
-    const int t = threadIdx.x;
-    const int64_t b = b0 + t;
+    // ===================== A generators: thread = (batch row / TMEM lane, 16-column half of the chunk) =====================
+    const int row = threadIdx.x & (kTileM - 1);
+    const int half = threadIdx.x >> 7;
+    const int64_t b = b0 + row;
     const bool live = b < a.B;
-    const uint32_t lane_base = static_cast<uint32_t>(warp * 32) << 16;
-    float v[kChunkK];
+    const uint32_t lane_base = static_cast<uint32_t>((warp & 3) * 32) << 16;
+    const int ebase = half * kHalf;
+    float v[kHalf];
 #pragma unroll
-    for (int e = 0; e < kChunkK; ++e) v[e] = 0.f;
-    int cur_src = -1, cur_col = -1;
+    for (int u = 0; u < kHalf; ++u) v[u] = 0.f;
+    int cur_src = -1, cur_col = -1, s_prev = -1;
     for (int c = c_begin; c < c_end; ++c) {
       const int it = c - c_begin;
       const int s = it % a.stages;
       const uint32_t ph = (it / a.stages) & 1;
-      const int4 e0 = __ldg(a.table + 2 * c);
-      const int4 e1 = __ldg(a.table + 2 * c + 1);
-      if (e0.z != cur_src || e0.w != cur_col) {          // (re)load this row's 32-wide vector segment
+      const int4 e0 = tab[2 * c];
+      const int4 e1 = tab[2 * c + 1];
+      if (e0.z != cur_src || e0.w != cur_col) {          // (re)load this row's vector segment (rare: once per d1 or d1*d2 chunks)
         cur_src = e0.z;
         cur_col = e0.w;
         const float* src = cur_src == 1 ? a.f1 : (cur_src == 2 ? a.f2 : a.f3);
         const int d = cur_src == 1 ? a.d1 : (cur_src == 2 ? a.d2 : a.d3);
 #pragma unroll
-        for (int e = 0; e < kChunkK; ++e) {
+        for (int u = 0; u < kHalf; ++u) {
+          const int e = ebase + u;
           float x = 0.f;
           if (cur_src == 0) x = (e == 0) ? 1.0f : 0.f;
           else if (live && e < e1.x) x = __ldg(src + b * d + cur_col + e);
-          v[e] = x;
+          v[u] = x;
         }
       }
-      float sc = sm_S[e0.x * kTileM + t] * sm_S[e0.y * kTileM + t];
+      float sc = sm_S[e0.x * kTileM + row] * sm_S[e0.y * kTileM + row];
       if (kDropout) sc *= a.dr.scale;
-      uint32_t r[kChunkK];
+      uint32_t r[kHalf];
 #pragma unroll
-      for (int e = 0; e < kChunkK; ++e) {
-        float x = sc * v[e];
+      for (int u = 0; u < kHalf; ++u) {
+        float x = sc * v[u];
         if (kDropout) {
-          const int64_t cc = b * a.dr.pairs_per_row + ((e1.y + e * e1.z) >> 1);
+          const int klog = e1.y + (ebase + u) * e1.z;
+          const int64_t cc = b * a.dr.pairs_per_row + (klog >> 1);
           const uint32_t h = kron_hash(static_cast<uint32_t>(cc), static_cast<uint32_t>(static_cast<uint64_t>(cc) >> 32),
                                        a.dr.seed_lo, a.dr.seed_hi);
-          const uint32_t r16 = ((e1.y + e * e1.z) & 1) ? (h >> 16) : (h & 0xffffu);
+          const uint32_t r16 = (klog & 1) ? (h >> 16) : (h & 0xffffu);
           x = (r16 >= a.dr.thresh) ? x : 0.f;
         }
-        r[e] = __float_as_uint(x) + 0x1000u;              // round-to-nearest onto the TF32 grid (hardware truncates)
+        r[u] = __float_as_uint(x) + 0x1000u;              // round-to-nearest onto the TF32 grid (hardware truncates)
+      }
+      if (s_prev >= 0) {                                  // publish the PREVIOUS chunk: its TMEM store had this chunk's
+        tc_wait_st();                                     // arithmetic to complete in
+        tc_fence_before();
+        mbar_arrive(&bar_full[s_prev]);
       }
       mbar_wait(&bar_empty[s], ph ^ 1);
       tc_fence_after();
-      tc_st_32x32b_x32(tmem_a + lane_base + s * kChunkK, r);
+      tc_st_32x32b_x16(tmem_a + lane_base + s * kChunkK + ebase, r);
+      s_prev = s;
+    }
+    if (s_prev >= 0) {
       tc_wait_st();
       tc_fence_before();
-      mbar_arrive(&bar_full[s]);
+      mbar_arrive(&bar_full[s_prev]);
     }
     // ===================== epilogue: TMEM accumulator -> registers -> y =====================
     mbar_wait(bar_acc, 0);
     tc_fence_after();
     float* dst = a.out + (static_cast<int64_t>(blockIdx.y) * a.B + b) * a.N;
     const bool add_bias = (a.ksplit == 1) && (a.bias != nullptr);
-    for (int n0 = 0; n0 < a.Np; n0 += 32) {
-      uint32_t acc[32];
-      tc_ld_32x32b_x32(tmem_d + lane_base + n0, acc);
+    const bool vec_ok = (a.N % 4 == 0) && ((reinterpret_cast<uintptr_t>(a.out) & 15u) == 0);
+    const int split_col = ((a.Np / 2 + 15) / 16) * 16;               // warps 0-3: [0, split_col), warps 4-7: [split_col, Np)
+    const int n_lo = half == 0 ? 0 : split_col;
+    const int n_hi = half == 0 ? split_col : a.Np;
+    for (int n0 = n_lo; n0 < n_hi; n0 += 16) {
+      uint32_t acc[16];
+      tc_ld_32x32b_x16(tmem_d + lane_base + n0, acc);
       tc_wait_ld();
       if (live) {
+        if (vec_ok && n0 + 16 <= a.N) {
 #pragma unroll
-        for (int e = 0; e < 32; ++e) {
-          const int n = n0 + e;
-          if (n < a.N) dst[n] = __uint_as_float(acc[e]) + (add_bias ? __ldg(a.bias + n) : 0.f);
+          for (int e = 0; e < 16; e += 4) {
+            float4 o;
+            o.x = __uint_as_float(acc[e]);     o.y = __uint_as_float(acc[e + 1]);
+            o.z = __uint_as_float(acc[e + 2]); o.w = __uint_as_float(acc[e + 3]);
+            if (add_bias) {
+              const float4 bb = __ldg(reinterpret_cast<const float4*>(a.bias + n0 + e));
+              o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w;
+            }
+            *reinterpret_cast<float4*>(dst + n0 + e) = o;
+          }
+        } else {
+#pragma unroll
+          for (int e = 0; e < 16; ++e) {
+            const int n = n0 + e;
+            if (n < a.N) dst[n] = __uint_as_float(acc[e]) + (add_bias ? __ldg(a.bias + n) : 0.f);
+          }
         }
       }
     }
     tc_fence_before();
   }
   __syncthreads();
-  if (warp == 5) {
+  if (warp == kGenWarps + 1) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(a.tmem_cols) : "memory");
   }
@@ -430,7 +477,7 @@ int get_tensor_map(const float* Wp, int32_t Np, int32_t Kp, CUtensorMap* out) {
 }
 
 struct TcPlan {
-  int32_t nchunks, Np, n_scal, stages, tmem_cols, ksplit, chunks_per_split;
+  int32_t nchunks, Np, n_scal, stages, tmem_cols, ksplit, chunks_per_split, table_in_smem;
   size_t smem;
   bool ok;
 };
@@ -440,7 +487,9 @@ TcPlan make_tc_plan(int64_t B, int32_t N, int32_t d1, int32_t d2, int32_t d3) {
   p.nchunks = static_cast<int32_t>(build_chunks(d1, d2, d3).size());
   p.Np = round_np(N);
   p.n_scal = 1 + d1 + (d3 > 0 ? d2 : 0);
-  const size_t fixed = static_cast<size_t>(p.n_scal) * kTileM * sizeof(float) + 256 + 1024;
+  const size_t table_bytes = static_cast<size_t>(p.nchunks) * sizeof(Chunk);
+  p.table_in_smem = table_bytes <= static_cast<size_t>(kMaxSmemTable) ? 1 : 0;
+  const size_t fixed = static_cast<size_t>(p.n_scal) * kTileM * sizeof(float) + (p.table_in_smem ? table_bytes : 0) + 256 + 1024;
   const size_t budget = 227 * 1024;
   const size_t stage = static_cast<size_t>(p.Np) * 128;
   int stages = fixed < budget ? static_cast<int>((budget - fixed) / stage) : 0;
@@ -549,7 +598,7 @@ extern "C" int mml_kron_linear_fwd(const float* f1, const float* f2, const float
   a.out = p.ksplit == 1 ? y : static_cast<float*>(workspace);
   a.B = B; a.d1 = d1; a.d2 = d2; a.d3 = d3; a.N = N; a.Np = p.Np;
   a.nchunks = p.nchunks; a.chunks_per_split = p.chunks_per_split; a.ksplit = p.ksplit;
-  a.n_scal = p.n_scal; a.stages = p.stages; a.tmem_cols = p.tmem_cols;
+  a.n_scal = p.n_scal; a.stages = p.stages; a.tmem_cols = p.tmem_cols; a.table_in_smem = p.table_in_smem;
   a.idesc = make_idesc_tf32(kTileM, p.Np);
   a.dr = make_kron_dropout(drop_p, seed, training, s.Kk);
   const dim3 grid(static_cast<unsigned>((B + kTileM - 1) / kTileM), p.ksplit);

@@ -47,6 +47,15 @@ class KronLinearState:
         self.packed = None
         self.packed_key = None
         self.path = "auto"          # "auto" | "simt" (tests use "simt" as the exact-fp32 cross-check)
+        self._plans = {}            # (B, N) -> (tensor-core path usable, workspace bytes)
+
+    def plan(self, B, N):
+        key = (B, N)
+        if key not in self._plans:
+            lib = _cabi.lib()
+            ok = bool(lib.mml_kron_fwd_supported(B, N, *self.dims))
+            self._plans[key] = (ok, lib.mml_kron_fwd_workspace_bytes(B, N, *self.dims) if ok else 0)
+        return self._plans[key]
 
     def ensure(self, weight):
         lib = _cabi.lib()
@@ -69,10 +78,6 @@ class KronLinearState:
             self.packed_key = key
 
 
-def _tc_supported(B, N, dims):
-    return bool(_cabi.lib().mml_kron_fwd_supported(B, N, *dims))
-
-
 class _KronLinearFn(torch.autograd.Function):
     """y = kron(append1(f1), append1(f2)[, append1(f3)]) * mask @ W^T + bias, without the Kronecker tensor."""
 
@@ -89,10 +94,9 @@ class _KronLinearFn(torch.autograd.Function):
         f3p = _cabi.dptr(fs[2]) if d3 > 0 else None
         w = weight.detach().contiguous()
         bptr = _cabi.dptr(bias.detach().contiguous()) if bias is not None else None
-        use_tc = state.path == "auto" and _tc_supported(B, N, state.dims)
-        if use_tc:
+        tc_ok, nws = state.plan(B, N)
+        if state.path == "auto" and tc_ok:
             state.ensure(weight)
-            nws = lib.mml_kron_fwd_workspace_bytes(B, N, d1, d2, d3)
             ws = torch.empty(nws, dtype=torch.uint8, device=dev)
             rc = lib.mml_kron_linear_fwd(_cabi.dptr(fs[0]), _cabi.dptr(fs[1]), f3p, B, d1, d2, d3, _cabi.dptr(state.table),
                                          _cabi.dptr(state.packed), bptr, N, float(drop_p), int(seed), int(training),
