@@ -187,12 +187,12 @@ __global__ void __launch_bounds__(kThreadsTc, 1) kron_fwd_tc_kernel(const __grid
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // carve: B stages | scalars (transposed: [n_scal][128]) | chunk table | barriers | tmem base
   const uint32_t stage_bytes = static_cast<uint32_t>(a.Np) * 128u;
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);     // 1024-B aligned, still a shared pointer
   uint8_t* sm_b = smem;
   float* sm_S = reinterpret_cast<float*>(smem + static_cast<size_t>(a.stages) * stage_bytes);
   int4* sm_tab = reinterpret_cast<int4*>(sm_S + static_cast<size_t>(a.n_scal) * kTileM);
   uint64_t* bars = reinterpret_cast<uint64_t*>(sm_tab + (a.table_in_smem ? 2 * a.nchunks : 0));
-  uint64_t* bar_full = bars;                    // [stages]  A stored (256 arrivals) + B landed (1 arrival + tx bytes)
+  uint64_t* bar_full = bars;                    // [stages]  A stored (1 arrival per generator warp) + B landed (1 arrival + tx bytes)
   uint64_t* bar_empty = bars + a.stages;        // [stages]  MMAs that read the stage have completed
   uint64_t* bar_acc = bars + 2 * a.stages;      // accumulator complete
   uint32_t* sm_tmem = reinterpret_cast<uint32_t*>(bars + 2 * a.stages + 1);
@@ -206,7 +206,7 @@ __global__ void __launch_bounds__(kThreadsTc, 1) kron_fwd_tc_kernel(const __grid
   if (warp == kGenWarps && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_w)) : "memory");
     for (int s = 0; s < a.stages; ++s) {
-      mbar_init(&bar_full[s], kGenThreads + 1);
+      mbar_init(&bar_full[s], kGenWarps + 1);
       mbar_init(&bar_empty[s], 1);
     }
     mbar_init(bar_acc, 1);
@@ -255,31 +255,31 @@ __global__ void __launch_bounds__(kThreadsTc, 1) kron_fwd_tc_kernel(const __grid
   if (warp == kGenWarps) {
     // ===================== TMA producer: weight tiles [Np x 32] =====================
     if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
       for (int c = c_begin; c < c_end; ++c) {
-        const int it = c - c_begin;
-        const int s = it % a.stages;
-        const uint32_t ph = (it / a.stages) & 1;
         mbar_wait(&bar_empty[s], ph ^ 1);
         mbar_arrive_expect_tx(&bar_full[s], stage_bytes);
         tma_load_2d(sm_b + static_cast<size_t>(s) * stage_bytes, &tmap_w, c * kChunkK, 0, &bar_full[s]);
+        if (++s == a.stages) { s = 0; ph ^= 1; }
       }
     }
   } else if (warp == kGenWarps + 1) {
     // ===================== MMA issuer (one thread) =====================
     if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
       for (int c = c_begin; c < c_end; ++c) {
-        const int it = c - c_begin;
-        const int s = it % a.stages;
-        const uint32_t ph = (it / a.stages) & 1;
         mbar_wait(&bar_full[s], ph);
         tc_fence_after();
         const uint32_t b_addr = smem_u32(sm_b + static_cast<size_t>(s) * stage_bytes);
 #pragma unroll
         for (int j = 0; j < kChunkK / 8; ++j) {
           const uint64_t b_desc = umma_desc_k_sw128(b_addr + j * 32);            // +8 tf32 along K inside the swizzle row
-          tc_mma_tf32_ts(tmem_d, tmem_a + s * kChunkK + j * 8, b_desc, a.idesc, (it > 0 || j > 0) ? 1u : 0u);
+          tc_mma_tf32_ts(tmem_d, tmem_a + s * kChunkK + j * 8, b_desc, a.idesc, (c > c_begin || j > 0) ? 1u : 0u);
         }
         tc_commit(&bar_empty[s]);          // frees the A columns and the B tile of this stage
+        if (++s == a.stages) { s = 0; ph ^= 1; }
       }
       tc_commit(bar_acc);
     }
@@ -295,10 +295,9 @@ __global__ void __launch_bounds__(kThreadsTc, 1) kron_fwd_tc_kernel(const __grid
 #pragma unroll
     for (int u = 0; u < kHalf; ++u) v[u] = 0.f;
     int cur_src = -1, cur_col = -1, s_prev = -1;
+    int s = 0;
+    uint32_t ph = 0;
     for (int c = c_begin; c < c_end; ++c) {
-      const int it = c - c_begin;
-      const int s = it % a.stages;
-      const uint32_t ph = (it / a.stages) & 1;
       const int4 e0 = tab[2 * c];
       const int4 e1 = tab[2 * c + 1];
       if (e0.z != cur_src || e0.w != cur_col) {          // (re)load this row's vector segment (rare: once per d1 or d1*d2 chunks)
@@ -334,17 +333,20 @@ __global__ void __launch_bounds__(kThreadsTc, 1) kron_fwd_tc_kernel(const __grid
       if (s_prev >= 0) {                                  // publish the PREVIOUS chunk: its TMEM store had this chunk's
         tc_wait_st();                                     // arithmetic to complete in
         tc_fence_before();
-        mbar_arrive(&bar_full[s_prev]);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bar_full[s_prev]);    // one arrival per generator warp
       }
       mbar_wait(&bar_empty[s], ph ^ 1);
       tc_fence_after();
       tc_st_32x32b_x16(tmem_a + lane_base + s * kChunkK + ebase, r);
       s_prev = s;
+      if (++s == a.stages) { s = 0; ph ^= 1; }
     }
     if (s_prev >= 0) {
       tc_wait_st();
       tc_fence_before();
-      mbar_arrive(&bar_full[s_prev]);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bar_full[s_prev]);
     }
     // ===================== epilogue: TMEM accumulator -> registers -> y =====================
     mbar_wait(bar_acc, 0);
@@ -494,6 +496,13 @@ TcPlan make_tc_plan(int64_t B, int32_t N, int32_t d1, int32_t d2, int32_t d3) {
   const size_t stage = static_cast<size_t>(p.Np) * 128;
   int stages = fixed < budget ? static_cast<int>((budget - fixed) / stage) : 0;
   if (stages > 4) stages = 4;
+  const size_t half_budget = 113 * 1024;
+  if (fixed + 3 * stage <= half_budget && p.Np + 3 * kChunkK <= 256) {
+    int st2 = static_cast<int>((half_budget - fixed) / stage);
+    if (st2 > 4) st2 = 4;
+    while (p.Np + st2 * kChunkK > 256) --st2;
+    stages = st2;
+  }
   p.stages = stages;
   p.ok = p.Np <= 256 && stages >= 2;
   p.smem = fixed + static_cast<size_t>(stages > 0 ? stages : 0) * stage;
