@@ -50,6 +50,8 @@ int64_t     mml_launch_count(void);
  *   ragged (seg_ptr != NULL): seg_begin = seg_ptr[b], seg_len = seg_ptr[b+1] -
  *          seg_ptr[b]; `cols` is then an upper bound on seg_len.  Used by the
  *          row-sharded bank: a rank sees only the indices it owns.
+ * `idx` holds int64 (idx_bytes = 8, the reference's LongTensor) or int32 (idx_bytes = 4, local
+ * row ids of a bank shard) entries.
  * `pos_flag` (uint8[B], NULL = all ones) says whether the FIRST entry of
  * anchor b's segment is its positive (column 0 of the reference's idx).
  * Bank 1 rows are scored against v2 ("side 2", out_v2, Z_v2); bank 2 rows
@@ -73,7 +75,7 @@ size_t mml_crd_workspace_bytes(int64_t B, int64_t cols, int32_t D);
 int mml_crd_fused_loss_grad(
     const float* bank1, const float* bank2, int64_t n_rows, int32_t D,
     const float* v1, const float* v2,
-    const int64_t* idx, const int64_t* seg_ptr, const uint8_t* pos_flag,
+    const void* idx, int32_t idx_bytes, const int64_t* seg_ptr, const uint8_t* pos_flag,
     int64_t B, int64_t cols,
     float T, const float* Z, int64_t n_data, int64_t nce_k, int64_t batch_norm,
     float* loss, float* sums, float* grad_v1, float* grad_v2,
@@ -89,7 +91,7 @@ int mml_crd_fused_loss_grad(
 int mml_crd_scores(
     const float* bank1, const float* bank2, int64_t n_rows, int32_t D,
     const float* v1, const float* v2,
-    const int64_t* idx, const int64_t* seg_ptr,
+    const void* idx, int32_t idx_bytes, const int64_t* seg_ptr,
     int64_t B, int64_t cols,
     float T, const float* Z, float* sums, float* set_Z,
     float* out_v1, float* out_v2,
@@ -100,7 +102,7 @@ int mml_crd_scores(
  * CRD_criterion.py:43,48 for callers that use out_v1/out_v2 in their own loss. */
 int mml_crd_weighted_rows(
     const float* bank1, const float* bank2, int64_t n_rows, int32_t D,
-    const int64_t* idx, const int64_t* seg_ptr,
+    const void* idx, int32_t idx_bytes, const int64_t* seg_ptr,
     const float* coef1, const float* coef2,
     int64_t B, int64_t cols,
     float* g1, float* g2,
@@ -115,6 +117,17 @@ int mml_crd_memory_update(
     float* bank1, float* bank2, int32_t D,
     const float* v1, const float* v2, const int64_t* y, int64_t B,
     float momentum, int64_t row_begin, int64_t row_end, void* stream);
+
+/* Index routing for the row-sharded bank (rank o owns rows [o*rows_per_rank, (o+1)*rows_per_rank)):
+ * a stable counting sort of idx[B, cols] by owner, kept in (anchor, column) order inside each owner.
+ *   mml_shard_count:   counts[o*B + b] = #{k : idx[b,k] / rows_per_rank == o}          (int64[world*B])
+ *   mml_shard_scatter: out[offsets[o*B + b] + j] = (int32) local id of the j-th such column, where
+ *                      `offsets` is the caller's exclusive scan of `counts` in (o, b) order.
+ * world <= 32; every idx value must lie in [0, world*rows_per_rank).                         */
+int mml_shard_count(const int64_t* idx, int64_t B, int64_t cols, int64_t rows_per_rank, int32_t world,
+                    int64_t* counts, void* stream);
+int mml_shard_scatter(const int64_t* idx, int64_t B, int64_t cols, int64_t rows_per_rank, int32_t world,
+                      const int64_t* offsets, int32_t* out_local_ids, void* stream);
 
 /* ------------------------------------------------------------------------- *
  * AliasMethod (CRD_criterion.py:84-141)

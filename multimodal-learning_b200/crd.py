@@ -50,6 +50,13 @@ def _as_f32(t: torch.Tensor) -> torch.Tensor:
     return t.contiguous()
 
 
+def _idx_arg(idx: torch.Tensor):
+    """(device pointer, element size) of an int64 / int32 index tensor."""
+    if idx.dtype not in (torch.int64, torch.int32):
+        raise RuntimeError(f"index tensors must be int64 or int32; got {idx.dtype}")
+    return _cabi.dptr(idx), idx.element_size()
+
+
 def _as_i64(t: torch.Tensor) -> torch.Tensor:
     if t.dtype != torch.int64:
         raise RuntimeError(f"index tensors must be int64 (LongTensor); got {t.dtype}")
@@ -57,10 +64,10 @@ def _as_i64(t: torch.Tensor) -> torch.Tensor:
 
 
 def crd_fused_loss_grad(bank1, bank2, v1, v2, idx, T, Z, n_data, nce_k, *, seg_ptr=None, pos_flag=None,
-                        batch_norm=None, want_out=False, want_sums=False):
+                        batch_norm=None, want_out=False, want_sums=False, cols=None):
     """-> (loss[1] | None, sums[4] | None, g1[B,D], g2[B,D], out_v1 | None, out_v2 | None)"""
     B, D = v1.shape
-    cols = idx.shape[1] if seg_ptr is None else int(nce_k) + 1
+    cols = idx.shape[1] if seg_ptr is None else int(cols if cols is not None else nce_k + 1)
     dev = v1.device
     ws = _workspace(B, cols, D, dev)
     g1 = torch.empty_like(v1)
@@ -73,7 +80,7 @@ def crd_fused_loss_grad(bank1, bank2, v1, v2, idx, T, Z, n_data, nce_k, *, seg_p
         KERNEL_TIMER.start("crd_fused_loss_grad", dev)
     rc = _cabi.lib().mml_crd_fused_loss_grad(
         _cabi.dptr(bank1), _cabi.dptr(bank2), bank1.shape[0], D, _cabi.dptr(v1), _cabi.dptr(v2),
-        _cabi.dptr(idx, torch.int64), _cabi.dptr(seg_ptr), _cabi.dptr(pos_flag), B, cols,
+        *_idx_arg(idx), _cabi.dptr(seg_ptr), _cabi.dptr(pos_flag), B, cols,
         float(T), _cabi.dptr(Z), int(n_data), int(nce_k), int(batch_norm if batch_norm is not None else B),
         _cabi.dptr(loss), _cabi.dptr(sums), _cabi.dptr(g1), _cabi.dptr(g2), _cabi.dptr(out1), _cabi.dptr(out2),
         _cabi.dptr(ws), ws.numel(), _cabi.cur_stream(dev))
@@ -95,7 +102,7 @@ def crd_scores(bank1, bank2, v1, v2, idx, T, *, Z=None, set_Z=None, seg_ptr=None
     sums = torch.empty(4, dtype=torch.float32, device=dev) if want_sums else None
     rc = _cabi.lib().mml_crd_scores(
         _cabi.dptr(bank1), _cabi.dptr(bank2), bank1.shape[0], D, _cabi.dptr(v1), _cabi.dptr(v2),
-        _cabi.dptr(idx, torch.int64), _cabi.dptr(seg_ptr), B, cols, float(T), _cabi.dptr(Z),
+        *_idx_arg(idx), _cabi.dptr(seg_ptr), B, cols, float(T), _cabi.dptr(Z),
         _cabi.dptr(sums), _cabi.dptr(set_Z), _cabi.dptr(out1), _cabi.dptr(out2),
         _cabi.dptr(ws), ws.numel(), _cabi.cur_stream(dev))
     _cabi.check(rc, "mml_crd_scores")
@@ -112,7 +119,7 @@ def crd_weighted_rows(bank1, bank2, idx, coef1, coef2, *, seg_ptr=None, cols=Non
     g1 = torch.empty(B, D, dtype=torch.float32, device=dev)
     g2 = torch.empty(B, D, dtype=torch.float32, device=dev)
     rc = _cabi.lib().mml_crd_weighted_rows(
-        _cabi.dptr(bank1), _cabi.dptr(bank2), bank1.shape[0], D, _cabi.dptr(idx, torch.int64),
+        _cabi.dptr(bank1), _cabi.dptr(bank2), bank1.shape[0], D, *_idx_arg(idx),
         _cabi.dptr(seg_ptr), _cabi.dptr(coef1), _cabi.dptr(coef2), B, cols, _cabi.dptr(g1), _cabi.dptr(g2),
         _cabi.dptr(ws), ws.numel(), _cabi.cur_stream(dev))
     _cabi.check(rc, "mml_crd_weighted_rows")

@@ -32,7 +32,8 @@ struct GatherArgs {
   const float* bank2;
   const float* v1;
   const float* v2;
-  const int64_t* idx;
+  const int64_t* idx;       // int64 indices (the reference's LongTensor) ...
+  const int32_t* idx32;     // ... or int32 local row ids (row-sharded bank); exactly one is non-NULL
   const int64_t* seg_ptr;   // NULL -> dense [B, cols]
   const uint8_t* pos_flag;  // NULL -> first entry of every segment is the positive
   const float* Z;           // {Z_v1, Z_v2} or NULL (raw scores)
@@ -134,7 +135,8 @@ __global__ void __launch_bounds__(kCtaThreads) crd_gather_kernel(const GatherArg
     // one coalesced load of 32 indices per warp
     const int64_t mycol = cb + lane;
     const bool myvalid = mycol < c1;
-    const int32_t myrow = myvalid ? static_cast<int32_t>(a.idx[seg_begin + mycol]) : 0;
+    int32_t myrow = 0;
+    if (myvalid) myrow = a.idx32 ? a.idx32[seg_begin + mycol] : static_cast<int32_t>(a.idx[seg_begin + mycol]);
     float mycf1 = 0.f, mycf2 = 0.f;
     if (MODE == kWeighted && myvalid) {
       mycf1 = a.coef1[seg_begin + mycol];
@@ -289,7 +291,7 @@ __global__ void __launch_bounds__(kCtaThreads) crd_gather_generic_kernel(const G
   if (MODE != kWeighted && a.Z != nullptr) { inv_Z1 = 1.f / a.Z[0]; inv_Z2 = 1.f / a.Z[1]; }
   float loss1 = 0.f, loss2 = 0.f, sum1 = 0.f, sum2 = 0.f;
   for (int64_t col = c0 + warp; col < c1; col += kCtaWarps) {
-    const int64_t row = a.idx[seg_begin + col];
+    const int64_t row = a.idx32 ? static_cast<int64_t>(a.idx32[seg_begin + col]) : a.idx[seg_begin + col];
     const float* p1 = a.bank1 + row * D;
     const float* p2 = a.bank2 + row * D;
     float g1, g2;
@@ -458,9 +460,15 @@ int launch_gather(const GatherArgs& a, int64_t B, cudaStream_t st) {
   return check_launch("crd_gather_kernel");
 }
 
-int common_checks(const float* bank1, const float* bank2, int64_t n_rows, int32_t D, const int64_t* idx,
+void set_idx(GatherArgs& a, const void* idx, int32_t idx_bytes) {
+  a.idx = idx_bytes == 8 ? static_cast<const int64_t*>(idx) : nullptr;
+  a.idx32 = idx_bytes == 4 ? static_cast<const int32_t*>(idx) : nullptr;
+}
+
+int common_checks(const float* bank1, const float* bank2, int64_t n_rows, int32_t D, const void* idx, int32_t idx_bytes,
                   int64_t B, int64_t cols, void* ws, size_t ws_size) {
   MML_REQUIRE(bank1 && bank2 && idx && ws, MML_ERR_INVALID_ARG, "crd: null pointer argument");
+  MML_REQUIRE(idx_bytes == 8 || idx_bytes == 4, MML_ERR_INVALID_ARG, "crd: idx_bytes must be 8 (int64) or 4 (int32)");
   MML_REQUIRE(B >= 0 && cols >= 1 && n_rows >= 1, MML_ERR_INVALID_ARG, "crd: bad sizes B=%lld cols=%lld n_rows=%lld",
               (long long)B, (long long)cols, (long long)n_rows);
   MML_REQUIRE(D >= 1 && D <= 2048, MML_ERR_UNSUPPORTED, "crd: feature dim %d outside [1, 2048]", D);
@@ -485,10 +493,10 @@ extern "C" size_t mml_crd_workspace_bytes(int64_t B, int64_t cols, int32_t D) {
 
 extern "C" int mml_crd_fused_loss_grad(
     const float* bank1, const float* bank2, int64_t n_rows, int32_t D, const float* v1, const float* v2,
-    const int64_t* idx, const int64_t* seg_ptr, const uint8_t* pos_flag, int64_t B, int64_t cols, float T,
+    const void* idx, int32_t idx_bytes, const int64_t* seg_ptr, const uint8_t* pos_flag, int64_t B, int64_t cols, float T,
     const float* Z, int64_t n_data, int64_t nce_k, int64_t batch_norm, float* loss, float* sums, float* grad_v1,
     float* grad_v2, float* out_v1, float* out_v2, void* workspace, size_t workspace_bytes, void* stream) {
-  int rc = common_checks(bank1, bank2, n_rows, D, idx, B, cols, workspace, workspace_bytes);
+  int rc = common_checks(bank1, bank2, n_rows, D, idx, idx_bytes, B, cols, workspace, workspace_bytes);
   if (rc != MML_OK) return rc;
   MML_REQUIRE(v1 && v2 && Z && grad_v1 && grad_v2, MML_ERR_INVALID_ARG, "crd_fused: null pointer argument");
   MML_REQUIRE((out_v1 == nullptr) == (out_v2 == nullptr), MML_ERR_INVALID_ARG, "crd_fused: out_v1/out_v2 both or neither");
@@ -500,7 +508,7 @@ extern "C" int mml_crd_fused_loss_grad(
   const Plan p = make_plan(B, cols);
   const Workspace w = carve(workspace, B, D, p);
   GatherArgs a{};
-  a.bank1 = bank1; a.bank2 = bank2; a.v1 = v1; a.v2 = v2; a.idx = idx; a.seg_ptr = seg_ptr; a.pos_flag = pos_flag;
+  a.bank1 = bank1; a.bank2 = bank2; a.v1 = v1; a.v2 = v2; set_idx(a, idx, idx_bytes); a.seg_ptr = seg_ptr; a.pos_flag = pos_flag;
   a.Z = Z; a.out1 = out_v1; a.out2 = out_v2; a.part_grad = w.part_grad; a.part_scal = w.part_scal;
   a.cols = cols; a.D = D; a.chunk_cols = p.chunk_cols; a.chunks = p.chunks;
   a.inv_T = 1.0f / T;
@@ -523,10 +531,10 @@ extern "C" int mml_crd_fused_loss_grad(
 }
 
 extern "C" int mml_crd_scores(const float* bank1, const float* bank2, int64_t n_rows, int32_t D, const float* v1,
-                              const float* v2, const int64_t* idx, const int64_t* seg_ptr, int64_t B, int64_t cols,
-                              float T, const float* Z, float* sums, float* set_Z, float* out_v1, float* out_v2,
-                              void* workspace, size_t workspace_bytes, void* stream) {
-  int rc = common_checks(bank1, bank2, n_rows, D, idx, B, cols, workspace, workspace_bytes);
+                              const float* v2, const void* idx, int32_t idx_bytes, const int64_t* seg_ptr, int64_t B,
+                              int64_t cols, float T, const float* Z, float* sums, float* set_Z, float* out_v1,
+                              float* out_v2, void* workspace, size_t workspace_bytes, void* stream) {
+  int rc = common_checks(bank1, bank2, n_rows, D, idx, idx_bytes, B, cols, workspace, workspace_bytes);
   if (rc != MML_OK) return rc;
   MML_REQUIRE(v1 && v2, MML_ERR_INVALID_ARG, "crd_scores: null pointer argument");
   MML_REQUIRE((out_v1 == nullptr) == (out_v2 == nullptr), MML_ERR_INVALID_ARG, "crd_scores: out_v1/out_v2 both or neither");
@@ -538,7 +546,7 @@ extern "C" int mml_crd_scores(const float* bank1, const float* bank2, int64_t n_
   const Plan p = make_plan(B, cols);
   const Workspace w = carve(workspace, B, D, p);
   GatherArgs a{};
-  a.bank1 = bank1; a.bank2 = bank2; a.v1 = v1; a.v2 = v2; a.idx = idx; a.seg_ptr = seg_ptr;
+  a.bank1 = bank1; a.bank2 = bank2; a.v1 = v1; a.v2 = v2; set_idx(a, idx, idx_bytes); a.seg_ptr = seg_ptr;
   a.Z = Z; a.out1 = out_v1; a.out2 = out_v2; a.part_grad = w.part_grad; a.part_scal = w.part_scal;
   a.cols = cols; a.D = D; a.chunk_cols = p.chunk_cols; a.chunks = p.chunks;
   a.inv_T = 1.0f / T;
@@ -559,10 +567,10 @@ extern "C" int mml_crd_scores(const float* bank1, const float* bank2, int64_t n_
 }
 
 extern "C" int mml_crd_weighted_rows(const float* bank1, const float* bank2, int64_t n_rows, int32_t D,
-                                     const int64_t* idx, const int64_t* seg_ptr, const float* coef1,
+                                     const void* idx, int32_t idx_bytes, const int64_t* seg_ptr, const float* coef1,
                                      const float* coef2, int64_t B, int64_t cols, float* g1, float* g2,
                                      void* workspace, size_t workspace_bytes, void* stream) {
-  int rc = common_checks(bank1, bank2, n_rows, D, idx, B, cols, workspace, workspace_bytes);
+  int rc = common_checks(bank1, bank2, n_rows, D, idx, idx_bytes, B, cols, workspace, workspace_bytes);
   if (rc != MML_OK) return rc;
   MML_REQUIRE(coef1 && coef2 && g1 && g2, MML_ERR_INVALID_ARG, "crd_weighted_rows: null pointer argument");
   if (B == 0) return MML_OK;
@@ -570,7 +578,7 @@ extern "C" int mml_crd_weighted_rows(const float* bank1, const float* bank2, int
   const Plan p = make_plan(B, cols);
   const Workspace w = carve(workspace, B, D, p);
   GatherArgs a{};
-  a.bank1 = bank1; a.bank2 = bank2; a.idx = idx; a.seg_ptr = seg_ptr; a.coef1 = coef1; a.coef2 = coef2;
+  a.bank1 = bank1; a.bank2 = bank2; set_idx(a, idx, idx_bytes); a.seg_ptr = seg_ptr; a.coef1 = coef1; a.coef2 = coef2;
   a.part_grad = w.part_grad; a.part_scal = w.part_scal;
   a.cols = cols; a.D = D; a.chunk_cols = p.chunk_cols; a.chunks = p.chunks;
   rc = launch_gather<kWeighted>(a, B, st);

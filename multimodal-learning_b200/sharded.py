@@ -1,0 +1,257 @@
+"""Row-sharded ContrastMemory / CRDLoss over `torch.distributed` (one process per GPU, NCCL).
+
+The reference keeps both memory banks on one GPU (`CL_utils/CRD_criterion.py:20-23`; nothing in
+the reference is distributed).  Here rank r owns rows [r*rows_per, (r+1)*rows_per) of BOTH banks
+and the batch is data-parallel (each rank holds B_local anchors and their contrast_idx).  Rows
+never cross NVLink: INDICES and per-anchor partial results do.  One step is
+
+  1. all_gather      f_s, f_t, idx, contrast_idx[:, 0]         (features are [B, dim]: KBs..MBs)
+     Embed heads run REPLICATED on the global batch, so their parameter gradients are identical on
+     every rank without a gradient all-reduce.
+  2. route           contrast_idx -> per-owner int32 local row ids (stable counting sort,
+                     `mml_shard_count` / `mml_shard_scatter`), then ONE all_to_all of ids + counts.
+  3. local kernel    every rank scores ALL global anchors against the rows IT owns (ragged
+                     segments, `mml_crd_fused_loss_grad`): partial log-term sums, partial dL/dv.
+  4. all_reduce      [sums | dL/dv1 | dL/dv2] -> loss (replicated) and full gradients.
+  5. owner update    each rank updates the rows of idx it owns (`mml_crd_memory_update` with
+                     row_begin/row_end); gather-before-update ordering is stream order on each rank.
+
+Per-rank gather traffic is (K+1)/world columns for every global anchor = the single-GPU unit of
+work when the global batch grows with the world size (weak scaling), and there is no bulk row
+exchange at all.  Result == the single-GPU module on the same global batch (integer routing exact;
+float sums re-associated across ranks, tolerance 1e-4).
+
+The compute steps go through a small backend object so the collective choreography can be tested
+on CPU (gloo, world_size 2) with the oracle standing in for the CUDA kernels -- tests only; the
+default backend is CUDA-only and fails loudly without the library.
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+import torch.distributed as dist
+from torch import nn
+from torch.autograd.function import once_differentiable
+
+from . import _cabi
+from . import crd as _crd
+from .crd import AliasMethod, ContrastLoss, Embed
+
+
+class CudaBackend:
+    """The product backend: every compute step is a libmml_b200.so kernel."""
+
+    def route(self, cidx, rows_per, world):
+        """-> (counts int64 [world, B], ids int32 [B*cols] grouped by owner, (anchor, column)-stable)."""
+        lib = _cabi.lib()
+        B, cols = cidx.shape
+        dev = cidx.device
+        st = _cabi.cur_stream(dev)
+        counts = torch.empty(world, B, dtype=torch.int64, device=dev)
+        _cabi.check(lib.mml_shard_count(_cabi.dptr(cidx, torch.int64), B, cols, rows_per, world, _cabi.dptr(counts), st),
+                    "mml_shard_count")
+        flat = counts.reshape(-1)
+        offsets = (flat.cumsum(0) - flat).contiguous()
+        ids = torch.empty(B * cols, dtype=torch.int32, device=dev)
+        _cabi.check(lib.mml_shard_scatter(_cabi.dptr(cidx, torch.int64), B, cols, rows_per, world, _cabi.dptr(offsets),
+                                          _cabi.dptr(ids), st), "mml_shard_scatter")
+        return counts, ids
+
+    def stats(self, bank1, bank2, v1, v2, ids, seg_ptr, T, cols):
+        """-> sums[4] with raw exp sums in [2], [3] (first-step Z, CRD_criterion.py:52-59)."""
+        return _crd.crd_scores(bank1, bank2, v1, v2, ids, T, seg_ptr=seg_ptr, cols=cols, want_out=False, want_sums=True)[2]
+
+    def fused(self, bank1, bank2, v1, v2, ids, seg_ptr, pos_flag, T, Z, n_data, nce_k, batch):
+        """-> (sums[4], g1[B,D], g2[B,D]) partial over the rows of this shard."""
+        _, sums, g1, g2, _, _ = _crd.crd_fused_loss_grad(bank1, bank2, v1, v2, ids, T, Z, n_data, nce_k, seg_ptr=seg_ptr,
+                                                        pos_flag=pos_flag, batch_norm=batch, want_sums=True, cols=nce_k + 1)
+        return sums, g1, g2
+
+    def update(self, bank1, bank2, v1, v2, y, momentum, row_begin, row_end):
+        _crd.crd_memory_update(bank1, bank2, v1, v2, y, momentum, row_begin, row_end)
+
+
+class _AllGatherRows(torch.autograd.Function):
+    """all_gather along dim 0.  Backward takes the local slice: every rank computes the SAME full
+    gradient (the downstream computation is replicated), so no reduction is needed."""
+
+    @staticmethod
+    def forward(ctx, x, group):
+        world = dist.get_world_size(group)
+        ctx.rank, ctx.n = dist.get_rank(group), x.shape[0]
+        out = torch.empty((world * x.shape[0],) + tuple(x.shape[1:]), dtype=x.dtype, device=x.device)
+        dist.all_gather_into_tensor(out, x.contiguous(), group=group)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        return g[ctx.rank * ctx.n:(ctx.rank + 1) * ctx.n], None
+
+
+def _all_gather(x, group):
+    world = dist.get_world_size(group)
+    out = torch.empty((world * x.shape[0],) + tuple(x.shape[1:]), dtype=x.dtype, device=x.device)
+    dist.all_gather_into_tensor(out, x.contiguous(), group=group)
+    return out
+
+
+class _ShardedFusedFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, V1, V2, mem, Y, cidx_local, n_data):
+        loss, g1, g2 = mem._sharded_step(V1.detach().contiguous(), V2.detach().contiguous(), Y, cidx_local, n_data)
+        ctx.save_for_backward(g1, g2)
+        return loss
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, grad_loss):
+        g1, g2 = ctx.saved_tensors
+        return grad_loss * g1, grad_loss * g2, None, None, None, None
+
+
+class ShardedContrastMemory(nn.Module):
+    """ContrastMemory(inputSize, outputSize, K, T, momentum) with its rows split over the ranks of `group`.
+    Buffers: `params` (replicated, same layout as the reference), `memory_v1` / `memory_v2` = the LOCAL
+    row block [rows_local, inputSize] (`row_begin`, `row_end` say which)."""
+
+    def __init__(self, inputSize, outputSize, K, T=0.07, momentum=0.5, group=None, device=None, backend=None,
+                 init="rand"):
+        super().__init__()
+        self.group = group
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        self.nLem = outputSize
+        self.K = K
+        self.rows_per = (outputSize + self.world - 1) // self.world
+        self.row_begin = min(outputSize, self.rank * self.rows_per)
+        self.row_end = min(outputSize, self.row_begin + self.rows_per)
+        self.backend = backend if backend is not None else CudaBackend()
+        rows_local = self.row_end - self.row_begin
+        self.register_buffer("params", torch.tensor([K, T, -1, -1, momentum]))
+        stdv = 1. / math.sqrt(inputSize / 3)
+        dev = device if device is not None else "cpu"
+        if init == "rand":      # same distribution as CRD_criterion.py:21-23, drawn per shard on its device
+            m1 = torch.rand(rows_local, inputSize, device=dev).mul_(2 * stdv).add_(-stdv)
+            m2 = torch.rand(rows_local, inputSize, device=dev).mul_(2 * stdv).add_(-stdv)
+        else:
+            m1 = torch.empty(rows_local, inputSize, device=dev)
+            m2 = torch.empty(rows_local, inputSize, device=dev)
+        self.register_buffer("memory_v1", m1)
+        self.register_buffer("memory_v2", m2)
+        if device is not None:
+            self.params = self.params.to(device)
+        self.multinomial = None          # built lazily: only the idx=None branch samples
+        p = torch.tensor([K, T, -1, -1, momentum])
+        self._K, self._T, self._momentum = int(p[0].item()), p[1].item(), p[4].item()
+        self._z_ready = False
+
+    # ---- (de)sharding of the reference's state-dict layout ----
+    def load_full_banks(self, memory_v1, memory_v2, params=None):
+        """Take this rank's row block out of full [n, D] banks (e.g. a single-GPU checkpoint)."""
+        self.memory_v1.copy_(memory_v1[self.row_begin:self.row_end])
+        self.memory_v2.copy_(memory_v2[self.row_begin:self.row_end])
+        if params is not None:
+            self.params.copy_(params)
+            self._z_ready = bool(params[2].item() > 0 and params[3].item() > 0)
+
+    def gather_full_banks(self):
+        """-> (memory_v1, memory_v2) as full [n, D] tensors on every rank (the reference's layout)."""
+        outs = []
+        for bank in (self.memory_v1, self.memory_v2):
+            pad = torch.zeros(self.rows_per, bank.shape[1], dtype=bank.dtype, device=bank.device)
+            pad[:bank.shape[0]] = bank
+            outs.append(_all_gather(pad, self.group)[:self.nLem])
+        return tuple(outs)
+
+    # ---- one sharded step on replicated V1/V2 (global batch) ----
+    def _exchange(self, cidx_local):
+        """Route this rank's contrast_idx to the owners; receive every rank's requests for my rows.
+        -> (ids int32 [nnz], seg_ptr int64 [B_global+1]) in global anchor order."""
+        world, group = self.world, self.group
+        B, cols = cidx_local.shape
+        counts, ids = self.backend.route(cidx_local, self.rows_per, world)          # [world, B], [B*cols]
+        send_sizes = counts.sum(1)
+        recv_counts = torch.empty_like(counts)                                      # [src, B]
+        dist.all_to_all_single(recv_counts, counts, group=group)
+        recv_sizes = recv_counts.sum(1)
+        sizes = torch.stack((send_sizes, recv_sizes)).cpu()                         # the step's one host sync
+        send_l, recv_l = sizes[0].tolist(), sizes[1].tolist()
+        recv_ids = torch.empty(int(sum(recv_l)), dtype=torch.int32, device=ids.device)
+        dist.all_to_all_single(recv_ids, ids, output_split_sizes=recv_l, input_split_sizes=send_l, group=group)
+        flat = recv_counts.reshape(-1)
+        seg_ptr = torch.zeros(flat.numel() + 1, dtype=torch.int64, device=flat.device)
+        seg_ptr[1:] = flat.cumsum(0)
+        return recv_ids, seg_ptr
+
+    def _sharded_step(self, V1, V2, Y, cidx_local, n_data):
+        be, group = self.backend, self.group
+        Bg, D = V1.shape
+        cols = self._K + 1
+        if cidx_local.shape[1] != cols:
+            raise RuntimeError(f"contrast_idx must have nce_k+1 = {cols} columns, got {cidx_local.shape[1]}")   # :42
+        ids, seg_ptr = self._exchange(cidx_local)
+        pos_rows = _all_gather(cidx_local[:, 0].contiguous(), group)
+        pos_flag = ((pos_rows >= self.row_begin) & (pos_rows < self.row_end)).to(torch.uint8)
+        if not self._z_ready:                                                       # CRD_criterion.py:52-59
+            sums = be.stats(self.memory_v1, self.memory_v2, V1, V2, ids, seg_ptr, self._T, cols).clone()
+            dist.all_reduce(sums, group=group)
+            scale = float(self.nLem) / (float(Bg) * cols)
+            z = self.params[2:4]
+            new_z = sums[2:4] * scale
+            self.params[2:4] = torch.where(z < 0, new_z, z)
+            if self.rank == 0:
+                print("normalization constant Z_v1 is set to {:.1f}".format(self.params[2].item()))
+                print("normalization constant Z_v2 is set to {:.1f}".format(self.params[3].item()))
+            self._z_ready = True
+        sums, g1, g2 = be.fused(self.memory_v1, self.memory_v2, V1, V2, ids, seg_ptr, pos_flag, self._T,
+                                self.params[2:4], n_data, self._K, Bg)
+        packed = torch.cat((sums.reshape(-1)[:2], g1.reshape(-1), g2.reshape(-1)))
+        dist.all_reduce(packed, group=group)
+        loss = (-(packed[0] + packed[1]) / Bg).reshape(1)
+        g1 = packed[2:2 + Bg * D].view(Bg, D)
+        g2 = packed[2 + Bg * D:].view(Bg, D)
+        with torch.no_grad():                                                       # :66-79, owner applies
+            be.update(self.memory_v1, self.memory_v2, V1, V2, Y, self._momentum, self.row_begin, self.row_end)
+        return loss, g1, g2
+
+    def fused_nce_loss(self, V1, V2, Y, cidx_local, n_data):
+        return _ShardedFusedFn.apply(V1, V2, self, Y, cidx_local, n_data)
+
+
+class ShardedCRDLoss(nn.Module):
+    """CRDLoss(opt) over a row-sharded bank.  `forward(f_s, f_t, idx, contrast_idx)` takes this rank's LOCAL
+    batch and returns the loss of the GLOBAL batch (identical on every rank); `loss.backward()` leaves the
+    local rows' gradient in f_s.grad and identical Embed parameter gradients on every rank."""
+
+    def __init__(self, opt, group=None, device=None, backend=None):
+        super().__init__()
+        self.group = group
+        self.embed_s = Embed(opt.s_dim, opt.feat_dim)
+        self.embed_t = Embed(opt.t_dim, opt.feat_dim)
+        if dist.get_world_size(group) > 1:          # replicated heads must start identical
+            for p in list(self.embed_s.parameters()) + list(self.embed_t.parameters()):
+                dist.broadcast(p.data, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+        self.contrast = ShardedContrastMemory(opt.feat_dim, opt.n_data, opt.nce_k, opt.nce_t, opt.nce_m, group=group,
+                                              device=device, backend=backend)
+        self.criterion_t = ContrastLoss(opt.n_data)
+        self.criterion_s = ContrastLoss(opt.n_data)
+        if device is not None:
+            self.embed_s.to(device)
+            self.embed_t.to(device)
+
+    def forward(self, f_s, f_t, idx, contrast_idx=None):
+        g = self.group
+        F_s = _AllGatherRows.apply(f_s, g)
+        F_t = _AllGatherRows.apply(f_t, g)
+        Y = _all_gather(idx, g)
+        V1 = self.embed_s(F_s)
+        V2 = self.embed_t(F_t)
+        if contrast_idx is None:                    # CRD_criterion.py:37-39 on the local anchors
+            mem = self.contrast
+            if mem.multinomial is None:
+                mem.multinomial = AliasMethod(torch.ones(mem.nLem))
+                mem.multinomial.cuda(f_s.device)
+            B = idx.shape[0]
+            contrast_idx = mem.multinomial.draw(B * (mem.K + 1), y=idx, cols=mem.K + 1).view(B, -1)
+        return self.contrast.fused_nce_loss(V1, V2, Y, contrast_idx.contiguous(), self.criterion_s.n_data)

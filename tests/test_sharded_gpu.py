@@ -1,0 +1,28 @@
+"""Row-sharded bank on real GPUs (NCCL, one process per GPU): sharded result == reference golden of the
+single-bank module.  Needs >= 2 GPUs (`gpurun --gpus 2`); skipped on a 1-GPU box."""
+from __future__ import annotations
+
+import os
+import subprocess
+import sys
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.mark.parametrize("name", ["crd_small", "crd_d128"])
+def test_sharded_cuda_matches_reference_golden(tmp_path, name):
+    world = min(torch.cuda.device_count(), 4)
+    if world < 2:
+        pytest.skip("needs >= 2 GPUs")
+    while {"crd_small": 8, "crd_d128": 16}[name] % world:
+        world -= 1
+    out = tmp_path / "res.txt"
+    port = 29500 + os.getpid() % 400
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "_sharded_worker.py"), str(world), "cuda", name,
+                        str(port), str(out)], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+    assert out.read_text().startswith("ok")
