@@ -229,6 +229,9 @@ class ShardedCRDLoss(nn.Module):
         self.group = group
         self.embed_s = Embed(opt.s_dim, opt.feat_dim)
         self.embed_t = Embed(opt.t_dim, opt.feat_dim)
+        if device is not None:
+            self.embed_s.to(device)
+            self.embed_t.to(device)
         if dist.get_world_size(group) > 1:          # replicated heads must start identical
             for p in list(self.embed_s.parameters()) + list(self.embed_t.parameters()):
                 dist.broadcast(p.data, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
@@ -236,9 +239,6 @@ class ShardedCRDLoss(nn.Module):
                                               device=device, backend=backend)
         self.criterion_t = ContrastLoss(opt.n_data)
         self.criterion_s = ContrastLoss(opt.n_data)
-        if device is not None:
-            self.embed_s.to(device)
-            self.embed_t.to(device)
 
     def forward(self, f_s, f_t, idx, contrast_idx=None):
         g = self.group
