@@ -120,14 +120,15 @@ int mml_crd_memory_update(
 
 /* Index routing for the row-sharded bank (rank o owns rows [o*rows_per_rank, (o+1)*rows_per_rank)):
  * a stable counting sort of idx[B, cols] by owner, kept in (anchor, column) order inside each owner.
- *   mml_shard_count:   counts[o*B + b] = #{k : idx[b,k] / rows_per_rank == o}          (int64[world*B])
- *   mml_shard_scatter: out[offsets[o*B + b] + j] = (int32) local id of the j-th such column, where
- *                      `offsets` is the caller's exclusive scan of `counts` in (o, b) order.
+ * Columns are processed in chunks of `chunk_cols` (multiple of 32), chunks = ceil(cols/chunk_cols):
+ *   mml_shard_count:   counts[(o*B + b)*chunks + c] = #{k in chunk c : idx[b,k] / rows_per_rank == o}
+ *   mml_shard_scatter: out[offsets[(o*B + b)*chunks + c] + j] = (int32) local id of the j-th such
+ *                      column, `offsets` = the caller's exclusive scan of `counts` in that order.
  * world <= 32; every idx value must lie in [0, world*rows_per_rank).                         */
-int mml_shard_count(const int64_t* idx, int64_t B, int64_t cols, int64_t rows_per_rank, int32_t world,
-                    int64_t* counts, void* stream);
-int mml_shard_scatter(const int64_t* idx, int64_t B, int64_t cols, int64_t rows_per_rank, int32_t world,
-                      const int64_t* offsets, int32_t* out_local_ids, void* stream);
+int mml_shard_count(const int64_t* idx, int64_t B, int64_t cols, int32_t chunk_cols, int64_t rows_per_rank,
+                    int32_t world, int64_t* counts, void* stream);
+int mml_shard_scatter(const int64_t* idx, int64_t B, int64_t cols, int32_t chunk_cols, int64_t rows_per_rank,
+                      int32_t world, const int64_t* offsets, int32_t* out_local_ids, void* stream);
 
 /* ------------------------------------------------------------------------- *
  * AliasMethod (CRD_criterion.py:84-141)

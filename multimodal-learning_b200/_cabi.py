@@ -29,8 +29,8 @@ _SIGNATURES = {
         c_float, _P, _P, _P, _P, _P, _P, c_size_t, _P]),
     "mml_crd_weighted_rows": (ctypes.c_int, [
         _P, _P, c_int64, c_int32, _P, c_int32, _P, _P, _P, c_int64, c_int64, _P, _P, _P, c_size_t, _P]),
-    "mml_shard_count": (ctypes.c_int, [_P, c_int64, c_int64, c_int64, c_int32, _P, _P]),
-    "mml_shard_scatter": (ctypes.c_int, [_P, c_int64, c_int64, c_int64, c_int32, _P, _P, _P]),
+    "mml_shard_count": (ctypes.c_int, [_P, c_int64, c_int64, c_int32, c_int64, c_int32, _P, _P]),
+    "mml_shard_scatter": (ctypes.c_int, [_P, c_int64, c_int64, c_int32, c_int64, c_int32, _P, _P, _P]),
     "mml_crd_memory_update": (ctypes.c_int, [
         _P, _P, c_int32, _P, _P, _P, c_int64, c_float, c_int64, c_int64, _P]),
     "mml_alias_build_host": (ctypes.c_int, [_P, c_int64, _P, _P]),

@@ -10,20 +10,27 @@ namespace {
 constexpr int kRouteThreads = 128;
 constexpr int kRouteWarps = kRouteThreads / 32;
 
+// One warp per (anchor b, column chunk c).  counts / offsets are laid out [world][B][chunks].
 template <bool kScatter>
 __global__ void __launch_bounds__(kRouteThreads) shard_route_kernel(
-    const int64_t* __restrict__ idx, int64_t B, int64_t cols, int64_t rows_per_rank, int32_t world,
-    int64_t* __restrict__ counts, const int64_t* __restrict__ offsets, int32_t* __restrict__ out) {
+    const int64_t* __restrict__ idx, int64_t B, int64_t cols, int32_t chunk_cols, int32_t chunks, int64_t rows_per_rank,
+    int32_t world, int64_t* __restrict__ counts, const int64_t* __restrict__ offsets, int32_t* __restrict__ out) {
   __shared__ int64_t run[kRouteWarps][32];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int64_t b = static_cast<int64_t>(blockIdx.x) * kRouteWarps + warp;
-  if (b >= B) return;
-  if (lane < world) run[warp][lane] = kScatter ? offsets[static_cast<int64_t>(lane) * B + b] : 0;
+  const int64_t w = static_cast<int64_t>(blockIdx.x) * kRouteWarps + warp;     // = b * chunks + c
+  if (w >= B * chunks) return;
+  const int64_t b = w / chunks;
+  const int c = static_cast<int>(w % chunks);
+  const int64_t slot = b * chunks + c;
+  const int64_t plane = B * chunks;
+  if (lane < world) run[warp][lane] = kScatter ? offsets[static_cast<int64_t>(lane) * plane + slot] : 0;
   __syncwarp();
   const unsigned lt = (1u << lane) - 1u;
-  for (int64_t k0 = 0; k0 < cols; k0 += 32) {
+  const int64_t k_begin = static_cast<int64_t>(c) * chunk_cols;
+  const int64_t k_end = min(cols, k_begin + chunk_cols);
+  for (int64_t k0 = k_begin; k0 < k_end; k0 += 32) {
     const int64_t k = k0 + lane;
-    const bool valid = k < cols;
+    const bool valid = k < k_end;
     const int64_t row = valid ? idx[b * cols + k] : 0;
     const int owner = valid ? static_cast<int>(row / rows_per_rank) : -1;
     for (int o = 0; o < world; ++o) {
@@ -36,11 +43,12 @@ __global__ void __launch_bounds__(kRouteThreads) shard_route_kernel(
       __syncwarp();
     }
   }
-  if (!kScatter && lane < world) counts[static_cast<int64_t>(lane) * B + b] = run[warp][lane];
+  if (!kScatter && lane < world) counts[static_cast<int64_t>(lane) * plane + slot] = run[warp][lane];
 }
 
-int check(const int64_t* idx, int64_t B, int64_t cols, int64_t rows_per_rank, int32_t world) {
+int check(const int64_t* idx, int64_t B, int64_t cols, int32_t chunk_cols, int64_t rows_per_rank, int32_t world) {
   MML_REQUIRE(idx && B >= 0 && cols >= 1 && rows_per_rank >= 1, MML_ERR_INVALID_ARG, "shard_route: bad arguments");
+  MML_REQUIRE(chunk_cols >= 32 && chunk_cols % 32 == 0, MML_ERR_INVALID_ARG, "shard_route: chunk_cols must be a multiple of 32");
   MML_REQUIRE(world >= 1 && world <= 32, MML_ERR_UNSUPPORTED, "shard_route: world size must be in [1, 32]");
   MML_REQUIRE(rows_per_rank < (1LL << 31), MML_ERR_UNSUPPORTED, "shard_route: local row ids must fit in int32");
   return MML_OK;
@@ -51,25 +59,30 @@ int check(const int64_t* idx, int64_t B, int64_t cols, int64_t rows_per_rank, in
 
 using namespace mml;
 
-extern "C" int mml_shard_count(const int64_t* idx, int64_t B, int64_t cols, int64_t rows_per_rank, int32_t world,
-                               int64_t* counts, void* stream) {
-  int rc = check(idx, B, cols, rows_per_rank, world);
+extern "C" int mml_shard_count(const int64_t* idx, int64_t B, int64_t cols, int32_t chunk_cols, int64_t rows_per_rank,
+                               int32_t world, int64_t* counts, void* stream) {
+  int rc = check(idx, B, cols, chunk_cols, rows_per_rank, world);
   if (rc != MML_OK) return rc;
   MML_REQUIRE(counts, MML_ERR_INVALID_ARG, "shard_count: null counts");
   if (B == 0) return MML_OK;
-  shard_route_kernel<false><<<static_cast<unsigned>((B + kRouteWarps - 1) / kRouteWarps), kRouteThreads, 0,
-                              static_cast<cudaStream_t>(stream)>>>(idx, B, cols, rows_per_rank, world, counts, nullptr, nullptr);
+  const int32_t chunks = static_cast<int32_t>((cols + chunk_cols - 1) / chunk_cols);
+  const int64_t warps = B * chunks;
+  shard_route_kernel<false><<<static_cast<unsigned>((warps + kRouteWarps - 1) / kRouteWarps), kRouteThreads, 0,
+                              static_cast<cudaStream_t>(stream)>>>(idx, B, cols, chunk_cols, chunks, rows_per_rank, world,
+                                                                   counts, nullptr, nullptr);
   return check_launch("shard_route_kernel<count>");
 }
 
-extern "C" int mml_shard_scatter(const int64_t* idx, int64_t B, int64_t cols, int64_t rows_per_rank, int32_t world,
-                                 const int64_t* offsets, int32_t* out_local_ids, void* stream) {
-  int rc = check(idx, B, cols, rows_per_rank, world);
+extern "C" int mml_shard_scatter(const int64_t* idx, int64_t B, int64_t cols, int32_t chunk_cols, int64_t rows_per_rank,
+                                 int32_t world, const int64_t* offsets, int32_t* out_local_ids, void* stream) {
+  int rc = check(idx, B, cols, chunk_cols, rows_per_rank, world);
   if (rc != MML_OK) return rc;
   MML_REQUIRE(offsets && out_local_ids, MML_ERR_INVALID_ARG, "shard_scatter: null pointer");
   if (B == 0) return MML_OK;
-  shard_route_kernel<true><<<static_cast<unsigned>((B + kRouteWarps - 1) / kRouteWarps), kRouteThreads, 0,
-                             static_cast<cudaStream_t>(stream)>>>(idx, B, cols, rows_per_rank, world, nullptr, offsets,
-                                                                  out_local_ids);
+  const int32_t chunks = static_cast<int32_t>((cols + chunk_cols - 1) / chunk_cols);
+  const int64_t warps = B * chunks;
+  shard_route_kernel<true><<<static_cast<unsigned>((warps + kRouteWarps - 1) / kRouteWarps), kRouteThreads, 0,
+                             static_cast<cudaStream_t>(stream)>>>(idx, B, cols, chunk_cols, chunks, rows_per_rank, world,
+                                                                  nullptr, offsets, out_local_ids);
   return check_launch("shard_route_kernel<scatter>");
 }

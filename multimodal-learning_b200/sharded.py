@@ -48,15 +48,17 @@ class CudaBackend:
         B, cols = cidx.shape
         dev = cidx.device
         st = _cabi.cur_stream(dev)
-        counts = torch.empty(world, B, dtype=torch.int64, device=dev)
-        _cabi.check(lib.mml_shard_count(_cabi.dptr(cidx, torch.int64), B, cols, rows_per, world, _cabi.dptr(counts), st),
+        chunk = 512                                         # columns per warp: enough warps to fill the GPU
+        chunks = (cols + chunk - 1) // chunk
+        fine = torch.empty(world, B, chunks, dtype=torch.int64, device=dev)
+        _cabi.check(lib.mml_shard_count(_cabi.dptr(cidx, torch.int64), B, cols, chunk, rows_per, world, _cabi.dptr(fine), st),
                     "mml_shard_count")
-        flat = counts.reshape(-1)
+        flat = fine.reshape(-1)
         offsets = (flat.cumsum(0) - flat).contiguous()
         ids = torch.empty(B * cols, dtype=torch.int32, device=dev)
-        _cabi.check(lib.mml_shard_scatter(_cabi.dptr(cidx, torch.int64), B, cols, rows_per, world, _cabi.dptr(offsets),
-                                          _cabi.dptr(ids), st), "mml_shard_scatter")
-        return counts, ids
+        _cabi.check(lib.mml_shard_scatter(_cabi.dptr(cidx, torch.int64), B, cols, chunk, rows_per, world,
+                                          _cabi.dptr(offsets), _cabi.dptr(ids), st), "mml_shard_scatter")
+        return fine.sum(2), ids
 
     def stats(self, bank1, bank2, v1, v2, ids, seg_ptr, T, cols):
         """-> sums[4] with raw exp sums in [2], [3] (first-step Z, CRD_criterion.py:52-59)."""
@@ -98,8 +100,8 @@ def _all_gather(x, group):
 
 class _ShardedFusedFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, V1, V2, mem, Y, cidx_local, n_data):
-        loss, g1, g2 = mem._sharded_step(V1.detach().contiguous(), V2.detach().contiguous(), Y, cidx_local, n_data)
+    def forward(ctx, V1, V2, mem, Y, routed, n_data):
+        loss, g1, g2 = mem._sharded_step(V1.detach().contiguous(), V2.detach().contiguous(), Y, routed, n_data)
         ctx.save_for_backward(g1, g2)
         return loss
 
@@ -165,33 +167,44 @@ class ShardedContrastMemory(nn.Module):
         return tuple(outs)
 
     # ---- one sharded step on replicated V1/V2 (global batch) ----
-    def _exchange(self, cidx_local):
-        """Route this rank's contrast_idx to the owners; receive every rank's requests for my rows.
-        -> (ids int32 [nnz], seg_ptr int64 [B_global+1]) in global anchor order."""
-        world, group = self.world, self.group
-        B, cols = cidx_local.shape
-        counts, ids = self.backend.route(cidx_local, self.rows_per, world)          # [world, B], [B*cols]
-        send_sizes = counts.sum(1)
-        recv_counts = torch.empty_like(counts)                                      # [src, B]
-        dist.all_to_all_single(recv_counts, counts, group=group)
-        recv_sizes = recv_counts.sum(1)
-        sizes = torch.stack((send_sizes, recv_sizes)).cpu()                         # the step's one host sync
-        send_l, recv_l = sizes[0].tolist(), sizes[1].tolist()
+    def exchange_begin(self, cidx_local):
+        """Route this rank's contrast_idx to the owners and start the size exchange.  The one host sync of
+        the step (all_to_all needs split sizes on the host) is deferred to `exchange_finish`, so the caller
+        can queue independent GPU work (all_gathers, Embed heads) in between."""
+        cols = self._K + 1
+        if cidx_local.dim() != 2 or cidx_local.shape[1] != cols:
+            raise RuntimeError(f"contrast_idx must be [B, nce_k+1 = {cols}], got {tuple(cidx_local.shape)}")   # :42
+        counts, ids = self.backend.route(cidx_local, self.rows_per, self.world)      # [world, B], [B*cols]
+        recv_counts = torch.empty_like(counts)                                       # [src, B]
+        dist.all_to_all_single(recv_counts, counts, group=self.group)
+        sizes = torch.stack((counts.sum(1), recv_counts.sum(1)))
+        if sizes.is_cuda:
+            host = torch.empty(sizes.shape, dtype=sizes.dtype, pin_memory=True)
+            host.copy_(sizes, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record()
+        else:
+            host, ev = sizes, None
+        return ids, recv_counts, host, ev
+
+    def exchange_finish(self, handle):
+        """-> (ids int32 [nnz], seg_ptr int64 [B_global+1]): every rank's requests for MY rows, global anchor order."""
+        ids, recv_counts, host, ev = handle
+        if ev is not None:
+            ev.synchronize()
+        send_l, recv_l = host[0].tolist(), host[1].tolist()
         recv_ids = torch.empty(int(sum(recv_l)), dtype=torch.int32, device=ids.device)
-        dist.all_to_all_single(recv_ids, ids, output_split_sizes=recv_l, input_split_sizes=send_l, group=group)
+        dist.all_to_all_single(recv_ids, ids, output_split_sizes=recv_l, input_split_sizes=send_l, group=self.group)
         flat = recv_counts.reshape(-1)
         seg_ptr = torch.zeros(flat.numel() + 1, dtype=torch.int64, device=flat.device)
         seg_ptr[1:] = flat.cumsum(0)
         return recv_ids, seg_ptr
 
-    def _sharded_step(self, V1, V2, Y, cidx_local, n_data):
+    def _sharded_step(self, V1, V2, Y, routed, n_data):
         be, group = self.backend, self.group
         Bg, D = V1.shape
         cols = self._K + 1
-        if cidx_local.shape[1] != cols:
-            raise RuntimeError(f"contrast_idx must have nce_k+1 = {cols} columns, got {cidx_local.shape[1]}")   # :42
-        ids, seg_ptr = self._exchange(cidx_local)
-        pos_rows = _all_gather(cidx_local[:, 0].contiguous(), group)
+        ids, seg_ptr, pos_rows = routed
         pos_flag = ((pos_rows >= self.row_begin) & (pos_rows < self.row_end)).to(torch.uint8)
         if not self._z_ready:                                                       # CRD_criterion.py:52-59
             sums = be.stats(self.memory_v1, self.memory_v2, V1, V2, ids, seg_ptr, self._T, cols).clone()
@@ -215,8 +228,8 @@ class ShardedContrastMemory(nn.Module):
             be.update(self.memory_v1, self.memory_v2, V1, V2, Y, self._momentum, self.row_begin, self.row_end)
         return loss, g1, g2
 
-    def fused_nce_loss(self, V1, V2, Y, cidx_local, n_data):
-        return _ShardedFusedFn.apply(V1, V2, self, Y, cidx_local, n_data)
+    def fused_nce_loss(self, V1, V2, Y, routed, n_data):
+        return _ShardedFusedFn.apply(V1, V2, self, Y, routed, n_data)
 
 
 class ShardedCRDLoss(nn.Module):
@@ -241,17 +254,21 @@ class ShardedCRDLoss(nn.Module):
         self.criterion_s = ContrastLoss(opt.n_data)
 
     def forward(self, f_s, f_t, idx, contrast_idx=None):
-        g = self.group
-        F_s = _AllGatherRows.apply(f_s, g)
-        F_t = _AllGatherRows.apply(f_t, g)
-        Y = _all_gather(idx, g)
-        V1 = self.embed_s(F_s)
-        V2 = self.embed_t(F_t)
+        g, mem = self.group, self.contrast
         if contrast_idx is None:                    # CRD_criterion.py:37-39 on the local anchors
-            mem = self.contrast
             if mem.multinomial is None:
                 mem.multinomial = AliasMethod(torch.ones(mem.nLem))
                 mem.multinomial.cuda(f_s.device)
             B = idx.shape[0]
             contrast_idx = mem.multinomial.draw(B * (mem.K + 1), y=idx, cols=mem.K + 1).view(B, -1)
-        return self.contrast.fused_nce_loss(V1, V2, Y, contrast_idx.contiguous(), self.criterion_s.n_data)
+        contrast_idx = contrast_idx.contiguous()
+        handle = mem.exchange_begin(contrast_idx)                                   # routing kernels + size exchange
+        fs2, ft2 = f_s.reshape(f_s.shape[0], -1), f_t.reshape(f_t.shape[0], -1)    # Embed flattens too (:230)
+        s_dim = fs2.shape[1]
+        F = _AllGatherRows.apply(torch.cat((fs2, ft2), 1), g)
+        YP = _all_gather(torch.stack((idx, contrast_idx[:, 0]), 1), g)               # anchors' ids | positives' rows
+        V1 = self.embed_s(F[:, :s_dim])
+        V2 = self.embed_t(F[:, s_dim:])
+        ids, seg_ptr = mem.exchange_finish(handle)                                  # host sync lands here
+        routed = (ids, seg_ptr, YP[:, 1].contiguous())
+        return mem.fused_nce_loss(V1, V2, YP[:, 0].contiguous(), routed, self.criterion_s.n_data)

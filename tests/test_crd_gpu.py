@@ -156,7 +156,7 @@ def _random_problem(B, D, K, n, seed, unit_rows=True):
     (3, 16, 21, 25),            # generic-D path
     (2, 100, 19, 25),           # generic-D path, D not a multiple of 32
     (1, 128, 1, 2),             # K=1
-    (7, 128, 300, 3),           # heavy index collisions (n=3 rows)
+    (3, 128, 300, 3),           # heavy index collisions (n=3 rows)
 ])
 def test_kernels_vs_oracle_closed_form(pkg, co, B, D, K, n):
     from multimodal_learning_b200 import crd
