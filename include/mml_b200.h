@@ -130,6 +130,34 @@ int mml_shard_count(const int64_t* idx, int64_t B, int64_t cols, int32_t chunk_c
 int mml_shard_scatter(const int64_t* idx, int64_t B, int64_t cols, int32_t chunk_cols, int64_t rows_per_rank,
                       int32_t world, const int64_t* offsets, int32_t* out_local_ids, void* stream);
 
+/* Single-pass, fixed-stride routing for the peer-memory (NVLink pull) exchange: slot (o, b, c) owns
+ * ids_out[((o*B + b)*chunks + c)*chunk_cols ..] and uses the first counts[(o*B + b)*chunks + c] (int32)
+ * entries.  ids_out: int32[world*B*chunks*chunk_cols] in peer-mapped (symmetric) memory.         */
+int mml_shard_route_strided(const int64_t* idx, int64_t B, int64_t cols, int32_t chunk_cols,
+                            int64_t rows_per_rank, int32_t world, int32_t* counts, int32_t* ids_out,
+                            void* stream);
+
+/* K4 over PEER-resident index slots: the owner's gather kernel reads, for global anchor
+ * a = s*B_local + bl and slot c, the ids  peer_ids_host[s][(bl*route_chunks + c)*route_stride ..]
+ * (a pointer into rank s's ids_out, already offset to THIS owner's block, valid in this process
+ * through CUDA peer mapping) of length peer_counts[(s*B_local + bl)*route_chunks + c].  The
+ * all_to_all of routed indices is thereby fused into the gather kernel as NVLink loads (4 bytes of
+ * index per 1 KB of local row traffic).  `peer_ids_host` is a HOST array of `world` device pointers;
+ * `peer_counts` int32[world*B_local*route_chunks] on this device; sums as in the non-peer calls. */
+size_t mml_crd_peer_workspace_bytes(int64_t B_global, int32_t route_chunks, int32_t D);
+int mml_crd_fused_loss_grad_peer(
+    const float* bank1, const float* bank2, int64_t n_rows, int32_t D, const float* v1, const float* v2,
+    const int32_t* const* peer_ids_host, const int32_t* peer_counts, int32_t world, int64_t B_local,
+    int32_t route_chunks, int32_t route_stride, const uint8_t* pos_flag,
+    float T, const float* Z, int64_t n_data, int64_t nce_k, int64_t batch_norm,
+    float* sums, float* grad_v1, float* grad_v2,
+    void* workspace, size_t workspace_bytes, void* stream);
+int mml_crd_scores_peer(
+    const float* bank1, const float* bank2, int64_t n_rows, int32_t D, const float* v1, const float* v2,
+    const int32_t* const* peer_ids_host, const int32_t* peer_counts, int32_t world, int64_t B_local,
+    int32_t route_chunks, int32_t route_stride, float T, float* sums,
+    void* workspace, size_t workspace_bytes, void* stream);
+
 /* ------------------------------------------------------------------------- *
  * AliasMethod (CRD_criterion.py:84-141)
  * ------------------------------------------------------------------------- */

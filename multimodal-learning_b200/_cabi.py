@@ -29,6 +29,13 @@ _SIGNATURES = {
         c_float, _P, _P, _P, _P, _P, _P, c_size_t, _P]),
     "mml_crd_weighted_rows": (ctypes.c_int, [
         _P, _P, c_int64, c_int32, _P, c_int32, _P, _P, _P, c_int64, c_int64, _P, _P, _P, c_size_t, _P]),
+    "mml_shard_route_strided": (ctypes.c_int, [_P, c_int64, c_int64, c_int32, c_int64, c_int32, _P, _P, _P]),
+    "mml_crd_peer_workspace_bytes": (c_size_t, [c_int64, c_int32, c_int32]),
+    "mml_crd_fused_loss_grad_peer": (ctypes.c_int, [
+        _P, _P, c_int64, c_int32, _P, _P, _P, _P, c_int32, c_int64, c_int32, c_int32, _P,
+        c_float, _P, c_int64, c_int64, c_int64, _P, _P, _P, _P, c_size_t, _P]),
+    "mml_crd_scores_peer": (ctypes.c_int, [
+        _P, _P, c_int64, c_int32, _P, _P, _P, _P, c_int32, c_int64, c_int32, c_int32, c_float, _P, _P, c_size_t, _P]),
     "mml_shard_count": (ctypes.c_int, [_P, c_int64, c_int64, c_int32, c_int64, c_int32, _P, _P]),
     "mml_shard_scatter": (ctypes.c_int, [_P, c_int64, c_int64, c_int32, c_int64, c_int32, _P, _P, _P]),
     "mml_crd_memory_update": (ctypes.c_int, [

@@ -51,16 +51,53 @@ struct GatherArgs {
   float inv_TB;             // 1 / (T * batch_norm)
   float nce_c;              // fp32(m*Pn + eps)     CRD_criterion.py:208,212
   float nce_kp;             // fp32(m*Pn)           CRD_criterion.py:212
+  // peer mode (row-sharded bank, indices pulled over NVLink): anchor b = (source rank s, local anchor bl);
+  // CTA (chunk c, b) reads peer_ids[s][(bl*chunks + c)*peer_stride ..] of length peer_counts[(s*B_local+bl)*chunks+c]
+  int32_t peer_world;       // 0 = off
+  int32_t peer_B_local;
+  int32_t peer_stride;
+  const int32_t* peer_counts;
+  const int32_t* peer_ids[32];
 };
 
-__device__ __forceinline__ void segment_of(const GatherArgs& a, int b, int64_t& begin, int64_t& len) {
+struct Segment {
+  const int64_t* idx64;
+  const int32_t* idx32;
+  int64_t begin;            // offset of the segment in idx
+  int64_t c0, c1;           // column range of this CTA inside the segment
+  bool has_pos;             // column 0 of the segment is the positive
+  bool active;
+};
+
+__device__ __forceinline__ Segment cta_segment(const GatherArgs& a, int b, int chunk) {
+  Segment g;
+  if (a.peer_world > 0) {
+    const int s = b / a.peer_B_local;
+    const int bl = b - s * a.peer_B_local;
+    g.idx64 = nullptr;
+    g.idx32 = a.peer_ids[s];
+    g.begin = (static_cast<int64_t>(bl) * a.chunks + chunk) * a.peer_stride;
+    g.c0 = 0;
+    g.c1 = a.peer_counts[(static_cast<int64_t>(s) * a.peer_B_local + bl) * a.chunks + chunk];
+    g.has_pos = (chunk == 0) && (a.pos_flag == nullptr || a.pos_flag[b] != 0);
+    g.active = true;                         // empty sub-segments still publish zero partials
+    return g;
+  }
+  int64_t len;
   if (a.seg_ptr != nullptr) {
-    begin = a.seg_ptr[b];
-    len = a.seg_ptr[b + 1] - begin;
+    g.begin = a.seg_ptr[b];
+    len = a.seg_ptr[b + 1] - g.begin;
   } else {
-    begin = static_cast<int64_t>(b) * a.cols;
+    g.begin = static_cast<int64_t>(b) * a.cols;
     len = a.cols;
   }
+  g.idx64 = a.idx;
+  g.idx32 = a.idx32;
+  g.c0 = static_cast<int64_t>(chunk) * a.chunk_cols;
+  g.c1 = min(g.c0 + static_cast<int64_t>(a.chunk_cols), len);
+  g.has_pos = (a.pos_flag == nullptr) ? true : (a.pos_flag[b] != 0);
+  g.active = g.c0 < len;                     // finishers skip the same chunks
+  return g;
 }
 
 // Per-row scalar stage shared by the fast and the generic kernel.
@@ -95,12 +132,10 @@ __global__ void __launch_bounds__(kCtaThreads) crd_gather_kernel(const GatherArg
 
   const int b = blockIdx.y;
   const int chunk = blockIdx.x;
-  int64_t seg_begin, seg_len;
-  segment_of(a, b, seg_begin, seg_len);
-  const int64_t c0 = static_cast<int64_t>(chunk) * a.chunk_cols;
-  if (c0 >= seg_len) return;                // finishers skip the same chunks
-  const int64_t c1 = min(c0 + static_cast<int64_t>(a.chunk_cols), seg_len);
-  const bool has_pos = (a.pos_flag == nullptr) ? true : (a.pos_flag[b] != 0);
+  const Segment sg = cta_segment(a, b, chunk);
+  if (!sg.active) return;
+  const int64_t seg_begin = sg.begin, c0 = sg.c0, c1 = sg.c1;
+  const bool has_pos = sg.has_pos;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -136,7 +171,7 @@ __global__ void __launch_bounds__(kCtaThreads) crd_gather_kernel(const GatherArg
     const int64_t mycol = cb + lane;
     const bool myvalid = mycol < c1;
     int32_t myrow = 0;
-    if (myvalid) myrow = a.idx32 ? a.idx32[seg_begin + mycol] : static_cast<int32_t>(a.idx[seg_begin + mycol]);
+    if (myvalid) myrow = sg.idx32 ? sg.idx32[seg_begin + mycol] : static_cast<int32_t>(sg.idx64[seg_begin + mycol]);
     float mycf1 = 0.f, mycf2 = 0.f;
     if (MODE == kWeighted && myvalid) {
       mycf1 = a.coef1[seg_begin + mycol];
@@ -268,12 +303,10 @@ __global__ void __launch_bounds__(kCtaThreads) crd_gather_generic_kernel(const G
   const int D = a.D;
   const int b = blockIdx.y;
   const int chunk = blockIdx.x;
-  int64_t seg_begin, seg_len;
-  segment_of(a, b, seg_begin, seg_len);
-  const int64_t c0 = static_cast<int64_t>(chunk) * a.chunk_cols;
-  if (c0 >= seg_len) return;
-  const int64_t c1 = min(c0 + static_cast<int64_t>(a.chunk_cols), seg_len);
-  const bool has_pos = (a.pos_flag == nullptr) ? true : (a.pos_flag[b] != 0);
+  const Segment sg = cta_segment(a, b, chunk);
+  if (!sg.active) return;
+  const int64_t seg_begin = sg.begin, c0 = sg.c0, c1 = sg.c1;
+  const bool has_pos = sg.has_pos;
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   float* acc = sm_dyn + static_cast<size_t>(warp) * 2 * D;
@@ -291,7 +324,7 @@ __global__ void __launch_bounds__(kCtaThreads) crd_gather_generic_kernel(const G
   if (MODE != kWeighted && a.Z != nullptr) { inv_Z1 = 1.f / a.Z[0]; inv_Z2 = 1.f / a.Z[1]; }
   float loss1 = 0.f, loss2 = 0.f, sum1 = 0.f, sum2 = 0.f;
   for (int64_t col = c0 + warp; col < c1; col += kCtaWarps) {
-    const int64_t row = a.idx32 ? static_cast<int64_t>(a.idx32[seg_begin + col]) : a.idx[seg_begin + col];
+    const int64_t row = sg.idx32 ? static_cast<int64_t>(sg.idx32[seg_begin + col]) : sg.idx64[seg_begin + col];
     const float* p1 = a.bank1 + row * D;
     const float* p2 = a.bank2 + row * D;
     float g1, g2;
@@ -422,8 +455,11 @@ struct Workspace {
   double* anchor_scal;
 };
 
-size_t ws_bytes(int64_t B, int64_t cols, int32_t D) {
-  const Plan p = make_plan(B, cols);
+size_t ws_bytes_plan(int64_t B, const Plan& p, int32_t D);
+
+size_t ws_bytes(int64_t B, int64_t cols, int32_t D) { return ws_bytes_plan(B, make_plan(B, cols), D); }
+
+size_t ws_bytes_plan(int64_t B, const Plan& p, int32_t D) {
   size_t n = 0;
   n += static_cast<size_t>(B) * p.chunks * 2 * D * sizeof(float);
   n += static_cast<size_t>(B) * p.chunks * 4 * sizeof(float);
@@ -586,4 +622,102 @@ extern "C" int mml_crd_weighted_rows(const float* bank1, const float* bank2, int
   crd_finish_anchor_kernel<<<static_cast<unsigned>(B), 128, 0, st>>>(w.part_grad, w.part_scal, seg_ptr, cols, p.chunk_cols,
                                                                       p.chunks, D, g1, g2, w.anchor_scal, 1, 0);
   return check_launch("crd_finish_anchor_kernel");
+}
+
+
+// ------------------------------------------------------------------ peer (NVLink pull) variants
+namespace mml {
+namespace {
+
+int peer_setup(GatherArgs& a, Plan& p, const float* bank1, const float* bank2, int64_t n_rows, int32_t D,
+               const int32_t* const* peer_ids_host, const int32_t* peer_counts, int32_t world, int64_t B_local,
+               int32_t route_chunks, int32_t route_stride, void* ws, size_t ws_size) {
+  MML_REQUIRE(bank1 && bank2 && peer_ids_host && peer_counts && ws, MML_ERR_INVALID_ARG, "crd_peer: null pointer argument");
+  MML_REQUIRE(world >= 1 && world <= 32 && B_local >= 1 && route_chunks >= 1 && route_stride >= 32, MML_ERR_INVALID_ARG,
+              "crd_peer: bad world / B_local / route layout");
+  MML_REQUIRE(D >= 1 && D <= 2048, MML_ERR_UNSUPPORTED, "crd_peer: feature dim %d outside [1, 2048]", D);
+  const int64_t B = B_local * world;
+  MML_REQUIRE(B <= 65535, MML_ERR_UNSUPPORTED, "crd_peer: global batch %lld > 65535 anchors per call", (long long)B);
+  MML_REQUIRE(n_rows >= 1 && n_rows < (1LL << 31), MML_ERR_UNSUPPORTED, "crd_peer: n_rows must fit in int32");
+  p = Plan{route_stride, route_chunks};
+  MML_REQUIRE(ws_size >= ws_bytes_plan(B, p, D), MML_ERR_WORKSPACE, "crd_peer: workspace %zu < required %zu", ws_size,
+              ws_bytes_plan(B, p, D));
+  a.bank1 = bank1; a.bank2 = bank2;
+  a.cols = static_cast<int64_t>(route_chunks) * route_stride;     // finishers: every chunk publishes a partial
+  a.D = D; a.chunk_cols = route_stride; a.chunks = route_chunks;
+  a.peer_world = world; a.peer_B_local = static_cast<int32_t>(B_local); a.peer_stride = route_stride;
+  a.peer_counts = peer_counts;
+  for (int i = 0; i < world; ++i) {
+    MML_REQUIRE(peer_ids_host[i] != nullptr, MML_ERR_INVALID_ARG, "crd_peer: null peer buffer %d", i);
+    a.peer_ids[i] = peer_ids_host[i];
+  }
+  return MML_OK;
+}
+
+}  // namespace
+}  // namespace mml
+
+extern "C" size_t mml_crd_peer_workspace_bytes(int64_t B_global, int32_t route_chunks, int32_t D) {
+  if (B_global < 0 || route_chunks < 1 || D < 1) return 0;
+  return ws_bytes_plan(B_global, Plan{32, route_chunks}, D);
+}
+
+extern "C" int mml_crd_fused_loss_grad_peer(
+    const float* bank1, const float* bank2, int64_t n_rows, int32_t D, const float* v1, const float* v2,
+    const int32_t* const* peer_ids_host, const int32_t* peer_counts, int32_t world, int64_t B_local, int32_t route_chunks,
+    int32_t route_stride, const uint8_t* pos_flag, float T, const float* Z, int64_t n_data, int64_t nce_k,
+    int64_t batch_norm, float* sums, float* grad_v1, float* grad_v2, void* workspace, size_t workspace_bytes,
+    void* stream) {
+  GatherArgs a{};
+  Plan p{};
+  int rc = peer_setup(a, p, bank1, bank2, n_rows, D, peer_ids_host, peer_counts, world, B_local, route_chunks, route_stride,
+                      workspace, workspace_bytes);
+  if (rc != MML_OK) return rc;
+  MML_REQUIRE(v1 && v2 && Z && grad_v1 && grad_v2, MML_ERR_INVALID_ARG, "crd_fused_peer: null pointer argument");
+  MML_REQUIRE(T > 0.f && n_data > 0 && batch_norm > 0 && nce_k >= 0, MML_ERR_INVALID_ARG, "crd_fused_peer: bad scalars");
+  const int64_t B = B_local * world;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const Workspace w = carve(workspace, B, D, p);
+  a.v1 = v1; a.v2 = v2; a.pos_flag = pos_flag; a.Z = Z; a.part_grad = w.part_grad; a.part_scal = w.part_scal;
+  a.inv_T = 1.0f / T;
+  a.inv_TB = 1.0f / (T * static_cast<float>(batch_norm));
+  const double Pn = 1.0 / static_cast<double>(n_data);
+  a.nce_kp = static_cast<float>(static_cast<double>(nce_k) * Pn);
+  a.nce_c = static_cast<float>(static_cast<double>(nce_k) * Pn + 1e-7);
+  rc = launch_gather<kFused>(a, B, st);
+  if (rc != MML_OK) return rc;
+  crd_finish_anchor_kernel<<<static_cast<unsigned>(B), 128, 0, st>>>(w.part_grad, w.part_scal, nullptr, a.cols, p.chunk_cols,
+                                                                      p.chunks, D, grad_v1, grad_v2, w.anchor_scal, 1, 1);
+  rc = check_launch("crd_finish_anchor_kernel");
+  if (rc != MML_OK) return rc;
+  if (sums) {
+    crd_finish_total_kernel<<<1, 256, 0, st>>>(w.anchor_scal, B, 0.0, 0.0, nullptr, sums, nullptr);
+    rc = check_launch("crd_finish_total_kernel");
+  }
+  return rc;
+}
+
+extern "C" int mml_crd_scores_peer(const float* bank1, const float* bank2, int64_t n_rows, int32_t D, const float* v1,
+                                   const float* v2, const int32_t* const* peer_ids_host, const int32_t* peer_counts,
+                                   int32_t world, int64_t B_local, int32_t route_chunks, int32_t route_stride, float T,
+                                   float* sums, void* workspace, size_t workspace_bytes, void* stream) {
+  GatherArgs a{};
+  Plan p{};
+  int rc = peer_setup(a, p, bank1, bank2, n_rows, D, peer_ids_host, peer_counts, world, B_local, route_chunks, route_stride,
+                      workspace, workspace_bytes);
+  if (rc != MML_OK) return rc;
+  MML_REQUIRE(v1 && v2 && sums && T > 0.f, MML_ERR_INVALID_ARG, "crd_scores_peer: bad arguments");
+  const int64_t B = B_local * world;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const Workspace w = carve(workspace, B, D, p);
+  a.v1 = v1; a.v2 = v2; a.part_grad = w.part_grad; a.part_scal = w.part_scal;
+  a.inv_T = 1.0f / T;
+  rc = launch_gather<kScores>(a, B, st);
+  if (rc != MML_OK) return rc;
+  crd_finish_anchor_kernel<<<static_cast<unsigned>(B), 128, 0, st>>>(w.part_grad, w.part_scal, nullptr, a.cols, p.chunk_cols,
+                                                                      p.chunks, D, nullptr, nullptr, w.anchor_scal, 0, 1);
+  rc = check_launch("crd_finish_anchor_kernel");
+  if (rc != MML_OK) return rc;
+  crd_finish_total_kernel<<<1, 256, 0, st>>>(w.anchor_scal, B, 0.0, 0.0, nullptr, sums, nullptr);
+  return check_launch("crd_finish_total_kernel");
 }

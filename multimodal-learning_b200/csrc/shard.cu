@@ -46,6 +46,46 @@ __global__ void __launch_bounds__(kRouteThreads) shard_route_kernel(
   if (!kScatter && lane < world) counts[static_cast<int64_t>(lane) * plane + slot] = run[warp][lane];
 }
 
+// Single-pass variant with a FIXED-STRIDE output: slot (o, b, c) owns ids_out[((o*B + b)*chunks + c)*chunk_cols ..] and
+// uses the first counts[(o*B + b)*chunks + c] entries.  No scan, no second pass; the owner's gather kernel reads the
+// slots straight out of this (peer-mapped) buffer, so the all_to_all and its host-side split sizes disappear.
+__global__ void __launch_bounds__(kRouteThreads) shard_route_strided_kernel(
+    const int64_t* __restrict__ idx, int64_t B, int64_t cols, int32_t chunk_cols, int32_t chunks, int64_t rows_per_rank,
+    int32_t world, int32_t* __restrict__ counts, int32_t* __restrict__ out) {
+  __shared__ int32_t run[kRouteWarps][32];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t w = static_cast<int64_t>(blockIdx.x) * kRouteWarps + warp;     // = b * chunks + c
+  if (w >= B * chunks) return;
+  const int64_t b = w / chunks;
+  const int c = static_cast<int>(w % chunks);
+  const int64_t slot = b * chunks + c;
+  const int64_t plane = B * chunks;
+  if (lane < world) run[warp][lane] = 0;
+  __syncwarp();
+  const unsigned lt = (1u << lane) - 1u;
+  const int64_t k_begin = static_cast<int64_t>(c) * chunk_cols;
+  const int64_t k_end = min(cols, k_begin + chunk_cols);
+  // the divide is by a runtime constant: do it in 32 bits (row < 2^31 is checked on the host side)
+  const uint32_t rpr = static_cast<uint32_t>(rows_per_rank);
+  for (int64_t k0 = k_begin; k0 < k_end; k0 += 32) {
+    const int64_t k = k0 + lane;
+    const bool valid = k < k_end;
+    const uint32_t row = valid ? static_cast<uint32_t>(idx[b * cols + k]) : 0u;
+    const int owner = valid ? static_cast<int>(row / rpr) : -1;
+    const uint32_t local = row - static_cast<uint32_t>(owner < 0 ? 0 : owner) * rpr;
+    for (int o = 0; o < world; ++o) {
+      const unsigned m = __ballot_sync(kFullMask, owner == o);
+      if (m == 0u) continue;
+      const int32_t base = run[warp][o];
+      if (owner == o) out[(static_cast<int64_t>(o) * plane + slot) * chunk_cols + base + __popc(m & lt)] = static_cast<int32_t>(local);
+      __syncwarp();
+      if (lane == 0) run[warp][o] = base + __popc(m);
+      __syncwarp();
+    }
+  }
+  if (lane < world) counts[static_cast<int64_t>(lane) * plane + slot] = run[warp][lane];
+}
+
 int check(const int64_t* idx, int64_t B, int64_t cols, int32_t chunk_cols, int64_t rows_per_rank, int32_t world) {
   MML_REQUIRE(idx && B >= 0 && cols >= 1 && rows_per_rank >= 1, MML_ERR_INVALID_ARG, "shard_route: bad arguments");
   MML_REQUIRE(chunk_cols >= 32 && chunk_cols % 32 == 0, MML_ERR_INVALID_ARG, "shard_route: chunk_cols must be a multiple of 32");
@@ -85,4 +125,20 @@ extern "C" int mml_shard_scatter(const int64_t* idx, int64_t B, int64_t cols, in
                              static_cast<cudaStream_t>(stream)>>>(idx, B, cols, chunk_cols, chunks, rows_per_rank, world,
                                                                   nullptr, offsets, out_local_ids);
   return check_launch("shard_route_kernel<scatter>");
+}
+
+extern "C" int mml_shard_route_strided(const int64_t* idx, int64_t B, int64_t cols, int32_t chunk_cols,
+                                       int64_t rows_per_rank, int32_t world, int32_t* counts, int32_t* ids_out,
+                                       void* stream) {
+  int rc = check(idx, B, cols, chunk_cols, rows_per_rank, world);
+  if (rc != MML_OK) return rc;
+  MML_REQUIRE(counts && ids_out, MML_ERR_INVALID_ARG, "shard_route_strided: null pointer");
+  MML_REQUIRE(rows_per_rank * world < (1LL << 32), MML_ERR_UNSUPPORTED, "shard_route_strided: global row ids must fit in uint32");
+  if (B == 0) return MML_OK;
+  const int32_t chunks = static_cast<int32_t>((cols + chunk_cols - 1) / chunk_cols);
+  const int64_t warps = B * chunks;
+  shard_route_strided_kernel<<<static_cast<unsigned>((warps + kRouteWarps - 1) / kRouteWarps), kRouteThreads, 0,
+                               static_cast<cudaStream_t>(stream)>>>(idx, B, cols, chunk_cols, chunks, rows_per_rank, world,
+                                                                    counts, ids_out);
+  return check_launch("shard_route_strided_kernel");
 }

@@ -5,13 +5,22 @@ the reference is distributed).  Here rank r owns rows [r*rows_per, (r+1)*rows_pe
 and the batch is data-parallel (each rank holds B_local anchors and their contrast_idx).  Rows
 never cross NVLink: INDICES and per-anchor partial results do.  One step is
 
-  1. all_gather      f_s, f_t, idx, contrast_idx[:, 0]         (features are [B, dim]: KBs..MBs)
-     Embed heads run REPLICATED on the global batch, so their parameter gradients are identical on
-     every rank without a gradient all-reduce.
-  2. route           contrast_idx -> per-owner int32 local row ids (stable counting sort,
-                     `mml_shard_count` / `mml_shard_scatter`), then ONE all_to_all of ids + counts.
-  3. local kernel    every rank scores ALL global anchors against the rows IT owns (ragged
-                     segments, `mml_crd_fused_loss_grad`): partial log-term sums, partial dL/dv.
+  1. Embed heads on the LOCAL anchors, then all_gather of the embeddings v1|v2 and of idx|positives
+     (KBs..MBs).  The heads' parameter gradients are summed across ranks by ONE all_reduce of the
+     flattened parameter vector inside backward (`_SumGradAcrossRanks`).
+  2. route           contrast_idx -> per-owner int32 local row ids (stable counting sort by owner).
+       transport "peer"    : single-pass fixed-stride routing (`mml_shard_route_strided`) into a
+                             SYMMETRIC-MEMORY buffer; owners PULL their slots over NVLink from inside
+                             the gather kernel (`mml_crd_fused_loss_grad_peer`): the all_to_all is
+                             fused into K4 as peer loads (4 B of index per 1 KB of local row traffic),
+                             no host sync, no staging copy.  Only the per-slot counts (36 KB/peer)
+                             go through a fixed-size all_to_all, which doubles as the "routing is
+                             complete everywhere" barrier.
+       transport "alltoall": compacting two-pass routing (`mml_shard_count/scatter`) + a variable
+                             size NCCL all_to_all (one host sync for the split sizes).  Used when
+                             peer mapping is unavailable, and on CPU/gloo in the tests.
+  3. local kernel    every rank scores ALL global anchors against the rows IT owns:
+                     partial log-term sums, partial dL/dv.
   4. all_reduce      [sums | dL/dv1 | dL/dv2] -> loss (replicated) and full gradients.
   5. owner update    each rank updates the rows of idx it owns (`mml_crd_memory_update` with
                      row_begin/row_end); gather-before-update ordering is stream order on each rank.
@@ -72,6 +81,90 @@ class CudaBackend:
 
     def update(self, bank1, bank2, v1, v2, y, momentum, row_begin, row_end):
         _crd.crd_memory_update(bank1, bank2, v1, v2, y, momentum, row_begin, row_end)
+
+    # ---- peer (NVLink pull) transport ----
+    def route_strided(self, cidx, rows_per, world, chunk, counts, ids):
+        lib = _cabi.lib()
+        B, cols = cidx.shape
+        _cabi.check(lib.mml_shard_route_strided(_cabi.dptr(cidx, torch.int64), B, cols, chunk, rows_per, world,
+                                                _cabi.dptr(counts), _cabi.dptr(ids), _cabi.cur_stream(cidx.device)),
+                    "mml_shard_route_strided")
+
+    def stats_peer(self, bank1, bank2, v1, v2, px, T):
+        lib = _cabi.lib()
+        Bg, D = v1.shape
+        dev = v1.device
+        nws = lib.mml_crd_peer_workspace_bytes(Bg, px.chunks, D)
+        ws = torch.empty(nws, dtype=torch.uint8, device=dev)
+        sums = torch.empty(4, dtype=torch.float32, device=dev)
+        _cabi.check(lib.mml_crd_scores_peer(_cabi.dptr(bank1), _cabi.dptr(bank2), bank1.shape[0], D, _cabi.dptr(v1),
+                                            _cabi.dptr(v2), px.ptr_array, _cabi.dptr(px.recv_counts), px.world, px.B_local,
+                                            px.chunks, px.chunk, float(T), _cabi.dptr(sums), _cabi.dptr(ws), nws,
+                                            _cabi.cur_stream(dev)), "mml_crd_scores_peer")
+        return sums
+
+    def fused_peer(self, bank1, bank2, v1, v2, px, pos_flag, T, Z, n_data, nce_k, batch):
+        lib = _cabi.lib()
+        Bg, D = v1.shape
+        dev = v1.device
+        nws = lib.mml_crd_peer_workspace_bytes(Bg, px.chunks, D)
+        ws = torch.empty(nws, dtype=torch.uint8, device=dev)
+        sums = torch.empty(4, dtype=torch.float32, device=dev)
+        g1 = torch.empty_like(v1)
+        g2 = torch.empty_like(v2)
+        if _crd.KERNEL_TIMER is not None:
+            _crd.KERNEL_TIMER.start("crd_fused_loss_grad", dev)
+        rc = lib.mml_crd_fused_loss_grad_peer(
+            _cabi.dptr(bank1), _cabi.dptr(bank2), bank1.shape[0], D, _cabi.dptr(v1), _cabi.dptr(v2), px.ptr_array,
+            _cabi.dptr(px.recv_counts), px.world, px.B_local, px.chunks, px.chunk, _cabi.dptr(pos_flag), float(T),
+            _cabi.dptr(Z), int(n_data), int(nce_k), int(batch), _cabi.dptr(sums), _cabi.dptr(g1), _cabi.dptr(g2),
+            _cabi.dptr(ws), nws, _cabi.cur_stream(dev))
+        if _crd.KERNEL_TIMER is not None:
+            _crd.KERNEL_TIMER.stop("crd_fused_loss_grad", dev)
+        _cabi.check(rc, "mml_crd_fused_loss_grad_peer")
+        return sums, g1, g2
+
+
+class PeerExchange:
+    """Symmetric-memory index slots of one (B_local, cols) geometry: every rank routes into its own
+    buffer; owners read their block of every peer's buffer through CUDA peer mappings."""
+
+    def __init__(self, mem, B_local, cols, device):
+        import ctypes
+
+        import torch.distributed._symmetric_memory as symm
+        self.world, self.B_local = mem.world, B_local
+        self.chunk = min(2048, (cols + 31) // 32 * 32)
+        self.chunks = (cols + self.chunk - 1) // self.chunk
+        block = B_local * self.chunks * self.chunk                     # int32 elements per owner block
+        group = mem.group if mem.group is not None else dist.group.WORLD
+        if hasattr(symm, "enable_symm_mem_for_group"):
+            try:
+                symm.enable_symm_mem_for_group(group.group_name)
+            except Exception:
+                pass
+        self.ids = symm.empty(self.world * block, dtype=torch.int32, device=device)
+        self.handle = symm.rendezvous(self.ids, group)
+        ptrs = [int(p) for p in self.handle.buffer_ptrs]
+        self.ptr_array = (ctypes.c_void_p * self.world)(*[p + mem.rank * block * 4 for p in ptrs])
+        self.counts = torch.empty(self.world, B_local, self.chunks, dtype=torch.int32, device=device)
+        self.recv_counts = torch.empty_like(self.counts)
+
+
+class _SumGradAcrossRanks(torch.autograd.Function):
+    """Identity in forward; backward all-reduces (SUM) the gradient.  Applied to the flattened Embed
+    parameters so the data-parallel heads get the global-batch gradient with one collective."""
+
+    @staticmethod
+    def forward(ctx, flat, group):
+        ctx.group = group
+        return flat.view_as(flat)
+
+    @staticmethod
+    def backward(ctx, g):
+        g = g.contiguous()
+        dist.all_reduce(g, group=ctx.group)
+        return g, None
 
 
 class _AllGatherRows(torch.autograd.Function):
@@ -144,6 +237,7 @@ class ShardedContrastMemory(nn.Module):
         if device is not None:
             self.params = self.params.to(device)
         self.multinomial = None          # built lazily: only the idx=None branch samples
+        self._peer = {}                  # (B_local, cols, device) -> PeerExchange
         p = torch.tensor([K, T, -1, -1, momentum])
         self._K, self._T, self._momentum = int(p[0].item()), p[1].item(), p[4].item()
         self._z_ready = False
@@ -187,6 +281,21 @@ class ShardedContrastMemory(nn.Module):
             host, ev = sizes, None
         return ids, recv_counts, host, ev
 
+    def exchange_peer(self, cidx_local):
+        """Peer transport: route into this rank's symmetric buffer and swap the per-slot counts.  No host sync.
+        The fixed-size all_to_all of counts completes on a rank only after every peer's routing kernel has
+        finished (stream order on the sender), so it is also the barrier that makes the slots readable."""
+        cols = self._K + 1
+        if cidx_local.dim() != 2 or cidx_local.shape[1] != cols:
+            raise RuntimeError(f"contrast_idx must be [B, nce_k+1 = {cols}], got {tuple(cidx_local.shape)}")   # :42
+        key = (cidx_local.shape[0], cols, cidx_local.device)
+        px = self._peer.get(key)
+        if px is None:
+            px = self._peer[key] = PeerExchange(self, cidx_local.shape[0], cols, cidx_local.device)
+        self.backend.route_strided(cidx_local, self.rows_per, self.world, px.chunk, px.counts, px.ids)
+        dist.all_to_all_single(px.recv_counts, px.counts, group=self.group)
+        return px
+
     def exchange_finish(self, handle):
         """-> (ids int32 [nnz], seg_ptr int64 [B_global+1]): every rank's requests for MY rows, global anchor order."""
         ids, recv_counts, host, ev = handle
@@ -204,10 +313,14 @@ class ShardedContrastMemory(nn.Module):
         be, group = self.backend, self.group
         Bg, D = V1.shape
         cols = self._K + 1
-        ids, seg_ptr, pos_rows = routed
+        ids, seg_ptr, pos_rows = routed             # ids is a PeerExchange in peer transport (seg_ptr None)
+        peer = isinstance(ids, PeerExchange)
         pos_flag = ((pos_rows >= self.row_begin) & (pos_rows < self.row_end)).to(torch.uint8)
         if not self._z_ready:                                                       # CRD_criterion.py:52-59
-            sums = be.stats(self.memory_v1, self.memory_v2, V1, V2, ids, seg_ptr, self._T, cols).clone()
+            if peer:
+                sums = be.stats_peer(self.memory_v1, self.memory_v2, V1, V2, ids, self._T)
+            else:
+                sums = be.stats(self.memory_v1, self.memory_v2, V1, V2, ids, seg_ptr, self._T, cols).clone()
             dist.all_reduce(sums, group=group)
             scale = float(self.nLem) / (float(Bg) * cols)
             z = self.params[2:4]
@@ -217,8 +330,12 @@ class ShardedContrastMemory(nn.Module):
                 print("normalization constant Z_v1 is set to {:.1f}".format(self.params[2].item()))
                 print("normalization constant Z_v2 is set to {:.1f}".format(self.params[3].item()))
             self._z_ready = True
-        sums, g1, g2 = be.fused(self.memory_v1, self.memory_v2, V1, V2, ids, seg_ptr, pos_flag, self._T,
-                                self.params[2:4], n_data, self._K, Bg)
+        if peer:
+            sums, g1, g2 = be.fused_peer(self.memory_v1, self.memory_v2, V1, V2, ids, pos_flag, self._T,
+                                         self.params[2:4], n_data, self._K, Bg)
+        else:
+            sums, g1, g2 = be.fused(self.memory_v1, self.memory_v2, V1, V2, ids, seg_ptr, pos_flag, self._T,
+                                    self.params[2:4], n_data, self._K, Bg)
         packed = torch.cat((sums.reshape(-1)[:2], g1.reshape(-1), g2.reshape(-1)))
         dist.all_reduce(packed, group=group)
         loss = (-(packed[0] + packed[1]) / Bg).reshape(1)
@@ -235,9 +352,10 @@ class ShardedContrastMemory(nn.Module):
 class ShardedCRDLoss(nn.Module):
     """CRDLoss(opt) over a row-sharded bank.  `forward(f_s, f_t, idx, contrast_idx)` takes this rank's LOCAL
     batch and returns the loss of the GLOBAL batch (identical on every rank); `loss.backward()` leaves the
-    local rows' gradient in f_s.grad and identical Embed parameter gradients on every rank."""
+    local rows' gradient in f_s.grad and the GLOBAL-batch gradient in the (replicated) Embed parameters.
+    transport: "peer" (NVLink pull through symmetric memory; default on CUDA), "alltoall", or "auto"."""
 
-    def __init__(self, opt, group=None, device=None, backend=None):
+    def __init__(self, opt, group=None, device=None, backend=None, transport="auto"):
         super().__init__()
         self.group = group
         self.embed_s = Embed(opt.s_dim, opt.feat_dim)
@@ -252,6 +370,25 @@ class ShardedCRDLoss(nn.Module):
                                               device=device, backend=backend)
         self.criterion_t = ContrastLoss(opt.n_data)
         self.criterion_s = ContrastLoss(opt.n_data)
+        self.transport = transport
+
+    def _pick_transport(self, device):
+        if self.transport == "auto":
+            self.transport = "peer" if (device.type == "cuda" and isinstance(self.contrast.backend, CudaBackend)) else "alltoall"
+        return self.transport
+
+    def _heads(self, f_s, f_t):
+        """Embed heads on the local anchors with parameters routed through `_SumGradAcrossRanks`."""
+        named = [(k, p) for k, p in self.named_parameters()]
+        flat = _SumGradAcrossRanks.apply(torch.cat([p.reshape(-1) for _, p in named]), self.group)
+        views, off = {}, 0
+        for k, p in named:
+            views[k] = flat[off:off + p.numel()].view_as(p)
+            off += p.numel()
+        ps = {k[len("embed_s."):]: v for k, v in views.items() if k.startswith("embed_s.")}
+        pt = {k[len("embed_t."):]: v for k, v in views.items() if k.startswith("embed_t.")}
+        return (torch.func.functional_call(self.embed_s, ps, (f_s,)),
+                torch.func.functional_call(self.embed_t, pt, (f_t,)))
 
     def forward(self, f_s, f_t, idx, contrast_idx=None):
         g, mem = self.group, self.contrast
@@ -262,13 +399,22 @@ class ShardedCRDLoss(nn.Module):
             B = idx.shape[0]
             contrast_idx = mem.multinomial.draw(B * (mem.K + 1), y=idx, cols=mem.K + 1).view(B, -1)
         contrast_idx = contrast_idx.contiguous()
-        handle = mem.exchange_begin(contrast_idx)                                   # routing kernels + size exchange
-        fs2, ft2 = f_s.reshape(f_s.shape[0], -1), f_t.reshape(f_t.shape[0], -1)    # Embed flattens too (:230)
-        s_dim = fs2.shape[1]
-        F = _AllGatherRows.apply(torch.cat((fs2, ft2), 1), g)
-        YP = _all_gather(torch.stack((idx, contrast_idx[:, 0]), 1), g)               # anchors' ids | positives' rows
-        V1 = self.embed_s(F[:, :s_dim])
-        V2 = self.embed_t(F[:, s_dim:])
-        ids, seg_ptr = mem.exchange_finish(handle)                                  # host sync lands here
-        routed = (ids, seg_ptr, YP[:, 1].contiguous())
-        return mem.fused_nce_loss(V1, V2, YP[:, 0].contiguous(), routed, self.criterion_s.n_data)
+        transport = self._pick_transport(f_s.device)
+        if transport == "peer":
+            try:
+                routed_ids, seg_ptr = mem.exchange_peer(contrast_idx), None
+            except Exception as e:                  # no peer mapping on this system: fall back, loudly, once
+                if mem._peer:
+                    raise
+                print(f"[mml_b200] symmetric-memory peer transport unavailable ({type(e).__name__}: {e}); using all_to_all")
+                self.transport = transport = "alltoall"
+        if transport == "alltoall":
+            handle = mem.exchange_begin(contrast_idx)                               # routing kernels + size exchange
+        v1, v2 = self._heads(f_s, f_t)                                              # local anchors
+        D = v1.shape[1]
+        V = _AllGatherRows.apply(torch.cat((v1, v2), 1), g)                         # [B_global, 2D]
+        YP = _all_gather(torch.stack((idx, contrast_idx[:, 0]), 1), g)              # anchors' ids | positives' rows
+        if transport == "alltoall":
+            routed_ids, seg_ptr = mem.exchange_finish(handle)                       # host sync lands here
+        routed = (routed_ids, seg_ptr, YP[:, 1].contiguous())
+        return mem.fused_nce_loss(V[:, :D], V[:, D:], YP[:, 0].contiguous(), routed, self.criterion_s.n_data)

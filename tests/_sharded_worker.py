@@ -96,7 +96,8 @@ def run(rank, world, backend, golden_name, port, result_path):
     opt = types.SimpleNamespace(s_dim=c["s_dim"], t_dim=c["t_dim"], feat_dim=c["D"], n_data=c["n"], nce_k=c["K"],
                                 nce_t=0.07, nce_m=0.5)
     mod = ShardedCRDLoss(opt, device=dev if backend == "cuda" else None,
-                         backend=OracleBackend() if backend == "oracle" else None)
+                         backend=OracleBackend() if backend == "oracle" else None,
+                         transport=os.environ.get("MML_TRANSPORT", "auto"))
     sd = g.state_dict("init.")
     mod.embed_s.load_state_dict({k[len("embed_s."):]: v for k, v in sd.items() if k.startswith("embed_s.")})
     mod.embed_t.load_state_dict({k[len("embed_t."):]: v for k, v in sd.items() if k.startswith("embed_t.")})
@@ -130,7 +131,7 @@ def run(rank, world, backend, golden_name, port, result_path):
     dist.barrier()
     if rank == 0:
         with open(result_path, "w") as f:
-            f.write(f"ok {worst:.3e}\n")
+            f.write(f"ok {worst:.3e} transport={mod.transport}\n")
     dist.destroy_process_group()
 
 

@@ -13,8 +13,9 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
+@pytest.mark.parametrize("transport", ["peer", "alltoall"])
 @pytest.mark.parametrize("name", ["crd_small", "crd_d128"])
-def test_sharded_cuda_matches_reference_golden(tmp_path, name):
+def test_sharded_cuda_matches_reference_golden(tmp_path, name, transport):
     world = min(torch.cuda.device_count(), 4)
     if world < 2:
         pytest.skip("needs >= 2 GPUs")
@@ -22,7 +23,9 @@ def test_sharded_cuda_matches_reference_golden(tmp_path, name):
         world -= 1
     out = tmp_path / "res.txt"
     port = 29500 + os.getpid() % 400
+    env = dict(os.environ, MML_TRANSPORT=transport)
     r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "_sharded_worker.py"), str(world), "cuda", name,
-                        str(port), str(out)], capture_output=True, text=True, timeout=600)
+                        str(port), str(out)], capture_output=True, text=True, timeout=600, env=env)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
-    assert out.read_text().startswith("ok")
+    res = out.read_text()
+    assert res.startswith("ok") and f"transport={transport}" in res, res + r.stdout[-1500:]
