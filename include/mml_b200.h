@@ -211,6 +211,17 @@ int     mml_kron_linear_fwd(const float* f1, const float* f2, const float* f3, i
                             const float* bias, int32_t N, float drop_p, uint64_t seed, int32_t training,
                             float* y, void* workspace, size_t workspace_bytes, void* stream);
 
+/* Weight gradient on the tensor cores (same K permutation / chunk table as the forward):
+ *   dW[n,k] = sum_b dy[b,n] A[b,k] m[b,k]   -> dense float[N, Kk] (every entry written).
+ * Lanes = 128 packed k, contraction over the batch, A^T generated into TMEM, dy^T streamed by TMA.
+ * workspace (1024-byte aligned) holds dy^T and the per-batch-split partial tiles.              */
+int     mml_kron_wgrad_supported(int64_t B, int32_t N, int32_t d1, int32_t d2, int32_t d3);
+size_t  mml_kron_wgrad_workspace_bytes(int64_t B, int32_t N, int32_t d1, int32_t d2, int32_t d3);
+int     mml_kron_linear_wgrad(const float* f1, const float* f2, const float* f3, int64_t B,
+                              int32_t d1, int32_t d2, int32_t d3, const int32_t* table, const float* dy,
+                              int32_t N, float drop_p, uint64_t seed, int32_t training, float* dW,
+                              void* workspace, size_t workspace_bytes, void* stream);
+
 /* Exact-fp32 CUDA-core path on the dense weight (any N, any widths): forward, and backward
  *   dW[n,k] = sum_b dy[b,n] A[b,k] m[b,k]            (NULL to skip)
  *   df_x    = factor gradients through dA = m * (dy W), contracted on chip (all NULL to skip);

@@ -1,0 +1,404 @@
+// K3: weight gradient of the Kronecker-fusion encoder on tcgen05 tensor cores.
+//
+//   dW[n, k] = sum_b dy[b, n] * A[b, k] * m[b, k]                 (autograd of encoder1[0], fusion.py:60 / :129)
+//
+// Same machinery as the forward (kron_tc.cu) with the roles turned: the 128 TMEM lanes are 128
+// PACKED k (4 chunks of the K permutation), the contraction runs over the batch in blocks of 32
+// rows, the A operand A^T[k, b] is generated into tensor memory (thread = (k lane, 16 batch
+// columns)), and the B operand is dy^T [Np, B] streamed by TMA in [Np x 32] tiles.  The Kronecker
+// tensor is not materialised here either: per 32-row batch block the CTA stages only the <= 4
+// distinct 32-wide factor segments and the 4 per-row scalars of its chunks in shared memory.
+// Output: per-(batch split) partial tiles in the packed layout, reduced and scattered back to the
+// dense [N, Kk] layout by kron_unpack_kernel (fixed order -> deterministic).
+#include "kron_tc_common.cuh"
+
+namespace mml {
+namespace {
+
+using namespace tc;
+
+constexpr int kBlkB = 32;          // batch rows per pipeline stage (= 4 MMAs of K = 8)
+
+struct WgArgs {
+  const float* f1;
+  const float* f2;
+  const float* f3;
+  const int4* table;
+  float* part;                // [bsplit][N][Kp]
+  int64_t B;
+  int32_t d1, d2, d3;
+  int32_t N, Np, nchunks, Kp;
+  int32_t nblocks, blocks_per_split;
+  int32_t stages, tmem_cols;
+  uint32_t idesc;
+  KronDropout dr;
+};
+
+// R[b][idx] with R = [1, f1, f2] (the scalar sources of the chunk table)
+__device__ __forceinline__ float scal_src(const WgArgs& a, int64_t b, int idx) {
+  if (idx == 0) return 1.0f;
+  if (idx <= a.d1) return __ldg(a.f1 + b * a.d1 + (idx - 1));
+  return __ldg(a.f2 + b * a.d2 + (idx - 1 - a.d1));
+}
+
+template <bool kDropout>
+__global__ void __launch_bounds__(kThreadsTc, 1) kron_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_dyT, const WgArgs a) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t stage_bytes = static_cast<uint32_t>(a.Np) * 128u;
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* sm_b = smem;
+  float* sm_X = reinterpret_cast<float*>(smem + static_cast<size_t>(a.stages) * stage_bytes);   // [2][4][32 b][32 e]
+  float* sm_sc = sm_X + 2 * 4 * kBlkB * 32;                                                       // [2][4][32 b]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sm_sc + 2 * 4 * kBlkB);
+  uint64_t* bar_full = bars;
+  uint64_t* bar_empty = bars + a.stages;
+  uint64_t* bar_acc = bars + 2 * a.stages;
+  uint32_t* sm_tmem = reinterpret_cast<uint32_t*>(bars + 2 * a.stages + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int c_first = blockIdx.x * 4;                                   // this CTA's 4 chunks = 128 packed k
+  const int blk_begin = blockIdx.y * a.blocks_per_split;
+  const int blk_end = min(a.nblocks, blk_begin + a.blocks_per_split);
+
+  if (warp == kGenWarps && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_dyT)) : "memory");
+    for (int s = 0; s < a.stages; ++s) {
+      mbar_init(&bar_full[s], kGenWarps + 1);
+      mbar_init(&bar_empty[s], 1);
+    }
+    mbar_init(bar_acc, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == kGenWarps + 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(sm_tmem)), "r"(a.tmem_cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *sm_tmem;
+  const uint32_t tmem_d = tmem_base;
+  const uint32_t tmem_a = tmem_base + static_cast<uint32_t>(a.Np);
+
+  if (warp == kGenWarps) {
+    if (lane == 0) {                       // ===== TMA producer: dy^T tiles [Np x 32 batch rows] =====
+      int s = 0;
+      uint32_t ph = 0;
+      for (int blk = blk_begin; blk < blk_end; ++blk) {
+        mbar_wait(&bar_empty[s], ph ^ 1);
+        mbar_arrive_expect_tx(&bar_full[s], stage_bytes);
+        tma_load_2d(sm_b + static_cast<size_t>(s) * stage_bytes, &tmap_dyT, blk * kBlkB, 0, &bar_full[s]);
+        if (++s == a.stages) { s = 0; ph ^= 1; }
+      }
+    }
+  } else if (warp == kGenWarps + 1) {
+    if (lane == 0) {                       // ===== MMA issuer =====
+      int s = 0;
+      uint32_t ph = 0;
+      for (int blk = blk_begin; blk < blk_end; ++blk) {
+        mbar_wait(&bar_full[s], ph);
+        tc_fence_after();
+        const uint32_t b_addr = smem_u32(sm_b + static_cast<size_t>(s) * stage_bytes);
+#pragma unroll
+        for (int j = 0; j < kBlkB / 8; ++j) {
+          const uint64_t b_desc = umma_desc_k_sw128(b_addr + j * 32);
+          tc_mma_tf32_ts(tmem_d, tmem_a + s * kBlkB + j * 8, b_desc, a.idesc, (blk > blk_begin || j > 0) ? 1u : 0u);
+        }
+        tc_commit(&bar_empty[s]);
+        if (++s == a.stages) { s = 0; ph ^= 1; }
+      }
+      tc_commit(bar_acc);
+    }
+  } else {
+    // ===== generators: thread = (packed-k lane t, 16 batch columns of the stage) =====
+    const int gt = threadIdx.x;                        // 0..255
+    const int t = gt & (kTileM - 1);
+    const int half = gt >> 7;
+    const int ci = t >> 5, e = t & 31;
+    const uint32_t lane_base = static_cast<uint32_t>((warp & 3) * 32) << 16;
+    // the CTA's chunk descriptors (uniform) and the vector slot of each chunk (chunks sharing a segment share a slot)
+    int4 ce0[4], ce1[4];
+    int slot_of[4];
+    bool cvalid[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      cvalid[c] = (c_first + c) < a.nchunks;
+      ce0[c] = cvalid[c] ? __ldg(a.table + 2 * (c_first + c)) : make_int4(0, 0, 0, 0);
+      ce1[c] = cvalid[c] ? __ldg(a.table + 2 * (c_first + c) + 1) : make_int4(0, 0, 1, 0);
+      slot_of[c] = c;
+#pragma unroll
+      for (int p = c - 1; p >= 0; --p)
+        if (cvalid[c] && cvalid[p] && ce0[p].z == ce0[c].z && ce0[p].w == ce0[c].w) slot_of[c] = slot_of[p];
+    }
+    int my_slot = 0, my_klog = 0, my_kstride = 1;
+    bool my_valid = false;
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+      if (c == ci) {
+        my_slot = slot_of[c];
+        my_valid = cvalid[c] && e < ce1[c].x;
+        my_klog = ce1[c].y + e * ce1[c].z;
+        my_kstride = ce1[c].z;
+      }
+    (void)my_kstride;
+
+    // staging assignment: X elements (slot, r, e2) for idx = gt + 256*j, j < 16;  scalar (chunk, r) for gt < 128
+    auto stage_block = [&](int blk, int buf) {
+      const int64_t b0 = static_cast<int64_t>(blk) * kBlkB;
+      float* X = sm_X + buf * (4 * kBlkB * 32);
+#pragma unroll 4
+      for (int j = 0; j < 16; ++j) {
+        const int idx = gt + 256 * j;
+        const int sl = idx >> 10, r = (idx >> 5) & 31, e2 = idx & 31;
+        // slot sl is "owned" by the first chunk that maps to it
+        float x = 0.f;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          if (c == sl && slot_of[c] == c && cvalid[c]) {
+            const int64_t b = b0 + r;
+            if (b < a.B && e2 < ce1[c].x) {
+              const int vsrc = ce0[c].z, col = ce0[c].w + e2;
+              if (vsrc == 0) x = 1.0f;                                            // corner chunk: vlen == 1
+              else if (vsrc == 1) x = __ldg(a.f1 + b * a.d1 + col);
+              else if (vsrc == 2) x = __ldg(a.f2 + b * a.d2 + col);
+              else x = __ldg(a.f3 + b * a.d3 + col);
+            }
+          }
+        }
+        X[idx] = x;
+      }
+      if (gt < 128) {
+        const int c = gt >> 5, r = gt & 31;
+        const int64_t b = b0 + r;
+        float sc = 0.f;
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc)
+          if (cc == c && cvalid[cc] && b < a.B) sc = scal_src(a, b, ce0[cc].x) * scal_src(a, b, ce0[cc].y);
+        if (kDropout) sc *= a.dr.scale;
+        sm_sc[buf * (4 * kBlkB) + c * kBlkB + r] = sc;
+      }
+    };
+
+    int s = 0, s_prev = -1;
+    uint32_t ph = 0;
+    if (blk_begin < blk_end) stage_block(blk_begin, 0);
+    for (int blk = blk_begin; blk < blk_end; ++blk) {
+      const int buf = (blk - blk_begin) & 1;
+      asm volatile("bar.sync 1, 256;" ::: "memory");                 // staging of `buf` visible; other buffer free
+      if (blk + 1 < blk_end) stage_block(blk + 1, buf ^ 1);
+      const float* X = sm_X + buf * (4 * kBlkB * 32) + my_slot * (kBlkB * 32);
+      const float* S = sm_sc + buf * (4 * kBlkB) + ci * kBlkB;
+      const int64_t b0 = static_cast<int64_t>(blk) * kBlkB;
+      uint32_t r[kHalf];
+#pragma unroll
+      for (int u = 0; u < kHalf; ++u) {
+        const int bl = half * kHalf + u;
+        float x = my_valid ? S[bl] * X[bl * 32 + e] : 0.f;
+        if (kDropout) {
+          const int64_t cc = (b0 + bl) * a.dr.pairs_per_row + (my_klog >> 1);
+          const uint32_t h = kron_hash(static_cast<uint32_t>(cc), static_cast<uint32_t>(static_cast<uint64_t>(cc) >> 32),
+                                       a.dr.seed_lo, a.dr.seed_hi);
+          const uint32_t r16 = (my_klog & 1) ? (h >> 16) : (h & 0xffffu);
+          x = (r16 >= a.dr.thresh) ? x : 0.f;
+        }
+        r[u] = __float_as_uint(x) + 0x1000u;
+      }
+      if (s_prev >= 0) {
+        tc_wait_st();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bar_full[s_prev]);
+      }
+      mbar_wait(&bar_empty[s], ph ^ 1);
+      tc_fence_after();
+      tc_st_32x32b_x16(tmem_a + lane_base + s * kBlkB + half * kHalf, r);
+      s_prev = s;
+      if (++s == a.stages) { s = 0; ph ^= 1; }
+    }
+    if (s_prev >= 0) {
+      tc_wait_st();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bar_full[s_prev]);
+    }
+    // ===== epilogue: D[k lane][n] -> part[split][n][kp] (coalesced over the k lanes) =====
+    mbar_wait(bar_acc, 0);
+    tc_fence_after();
+    const int kp = blockIdx.x * kTileM + t;
+    float* dst = a.part + static_cast<int64_t>(blockIdx.y) * a.N * a.Kp + kp;
+    const int split_col = ((a.Np / 2 + 15) / 16) * 16;
+    const int n_lo = half == 0 ? 0 : split_col;
+    const int n_hi = half == 0 ? split_col : a.Np;
+    for (int n0 = n_lo; n0 < n_hi; n0 += 16) {
+      uint32_t acc[16];
+      tc_ld_32x32b_x16(tmem_d + lane_base + n0, acc);
+      tc_wait_ld();
+      if (kp < a.Kp) {
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+          const int n = n0 + u;
+          if (n < a.N) dst[static_cast<int64_t>(n) * a.Kp] = __uint_as_float(acc[u]);
+        }
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == kGenWarps + 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(a.tmem_cols) : "memory");
+  }
+}
+
+// dy [B, N] -> dyT [Np, Bpad] (TF32-rounded, zero padded): the K-major B operand of the wgrad MMA
+__global__ void kron_transpose_dy_kernel(const float* __restrict__ dy, int64_t B, int32_t N, int32_t Np, int64_t Bpad,
+                                         float* __restrict__ dyT) {
+  __shared__ float tile[32][33];
+  const int64_t b0 = static_cast<int64_t>(blockIdx.x) * 32;
+  const int n0 = blockIdx.y * 32;
+  for (int r = threadIdx.y; r < 32; r += 8) {
+    const int64_t b = b0 + r;
+    const int n = n0 + threadIdx.x;
+    tile[r][threadIdx.x] = (b < B && n < N) ? dy[b * N + n] : 0.f;
+  }
+  __syncthreads();
+  for (int r = threadIdx.y; r < 32; r += 8) {
+    const int n = n0 + r;
+    const int64_t b = b0 + threadIdx.x;
+    if (n < Np && b < Bpad) {
+      const uint32_t u = (__float_as_uint(tile[threadIdx.x][r]) + 0x1000u) & 0xFFFFE000u;
+      dyT[static_cast<int64_t>(n) * Bpad + b] = __uint_as_float(u);
+    }
+  }
+}
+
+// dW[n, klog] = sum_z part[z][n][kp]  for every valid packed position kp = (chunk, e)
+__global__ void kron_unpack_kernel(const float* __restrict__ part, int32_t bsplit, int32_t N, int32_t Kp, int32_t Kk,
+                                   const int4* __restrict__ table, float* __restrict__ dW) {
+  const int64_t total = static_cast<int64_t>(N) * Kp;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int n = static_cast<int>(i / Kp);
+    const int kp = static_cast<int>(i % Kp);
+    const int4 e1 = __ldg(table + 2 * (kp >> 5) + 1);
+    const int e = kp & 31;
+    if (e >= e1.x) continue;
+    float t = 0.f;
+    for (int z = 0; z < bsplit; ++z) t += part[(static_cast<int64_t>(z) * N + n) * Kp + kp];
+    dW[static_cast<int64_t>(n) * Kk + e1.y + e * e1.z] = t;
+  }
+}
+
+struct WgPlan {
+  int32_t nchunks, Np, Kp, stages, tmem_cols, ktiles, nblocks, bsplit, blocks_per_split;
+  int64_t Bpad;
+  size_t smem, dyT_bytes, part_bytes;
+  bool ok;
+};
+
+WgPlan make_wg_plan(int64_t B, int32_t N, int32_t d1, int32_t d2, int32_t d3) {
+  WgPlan p{};
+  p.nchunks = static_cast<int32_t>(build_chunks(d1, d2, d3).size());
+  p.Np = round_np(N);
+  p.Kp = p.nchunks * kChunkK;
+  p.ktiles = (p.nchunks + 3) / 4;
+  p.nblocks = static_cast<int32_t>((B + kBlkB - 1) / kBlkB);
+  p.Bpad = static_cast<int64_t>(p.nblocks) * kBlkB;
+  const size_t fixed = (2 * 4 * kBlkB * 32 + 2 * 4 * kBlkB) * sizeof(float) + 256 + 1024;
+  const size_t stage = static_cast<size_t>(p.Np) * 128;
+  int stages = static_cast<int>((227 * 1024 - fixed) / stage);
+  if (stages > 4) stages = 4;
+  const size_t half_budget = 113 * 1024;
+  if (fixed + 3 * stage <= half_budget && p.Np + 3 * kBlkB <= 256) {
+    int st2 = static_cast<int>((half_budget - fixed) / stage);
+    if (st2 > 4) st2 = 4;
+    while (p.Np + st2 * kBlkB > 256) --st2;
+    stages = st2;
+  }
+  p.stages = stages;
+  p.ok = p.Np <= 256 && stages >= 2;
+  p.smem = fixed + static_cast<size_t>(stages) * stage;
+  int cols = p.Np + stages * kBlkB, pow2 = 32;
+  while (pow2 < cols) pow2 <<= 1;
+  p.tmem_cols = pow2;
+  if (pow2 > 512) p.ok = false;
+  int64_t split = (148 * 2 + p.ktiles - 1) / p.ktiles;
+  const int64_t max_split = p.nblocks / 8 > 0 ? p.nblocks / 8 : 1;       // >= 8 batch blocks (256 rows) per split
+  if (split > max_split) split = max_split;
+  if (split > 64) split = 64;
+  if (split < 1) split = 1;
+  p.blocks_per_split = static_cast<int32_t>((p.nblocks + split - 1) / split);
+  p.bsplit = (p.nblocks + p.blocks_per_split - 1) / p.blocks_per_split;
+  p.dyT_bytes = (static_cast<size_t>(p.Np) * p.Bpad * sizeof(float) + 1023) / 1024 * 1024;
+  p.part_bytes = static_cast<size_t>(p.bsplit) * N * p.Kp * sizeof(float);
+  return p;
+}
+
+}  // namespace
+}  // namespace mml
+
+using namespace mml;
+
+extern "C" int mml_kron_wgrad_supported(int64_t B, int32_t N, int32_t d1, int32_t d2, int32_t d3) {
+  if (B < 1 || N < 1 || d1 < 1 || d2 < 1 || d3 < 0) return 0;
+  return make_wg_plan(B, N, d1, d2, d3).ok ? 1 : 0;
+}
+
+extern "C" size_t mml_kron_wgrad_workspace_bytes(int64_t B, int32_t N, int32_t d1, int32_t d2, int32_t d3) {
+  if (B < 1 || N < 1 || d1 < 1 || d2 < 1 || d3 < 0) return 0;
+  const WgPlan p = make_wg_plan(B, N, d1, d2, d3);
+  return p.dyT_bytes + p.part_bytes + 1024;
+}
+
+extern "C" int mml_kron_linear_wgrad(const float* f1, const float* f2, const float* f3, int64_t B, int32_t d1, int32_t d2,
+                                     int32_t d3, const int32_t* table, const float* dy, int32_t N, float drop_p,
+                                     uint64_t seed, int32_t training, float* dW, void* workspace, size_t workspace_bytes,
+                                     void* stream) {
+  MML_REQUIRE(f1 && f2 && table && dy && dW && workspace, MML_ERR_INVALID_ARG, "kron_linear_wgrad: null pointer");
+  MML_REQUIRE((d3 > 0) == (f3 != nullptr), MML_ERR_INVALID_ARG, "kron_linear_wgrad: f3 and d3 must both be set or both be absent");
+  MML_REQUIRE(B >= 1 && d1 >= 1 && d2 >= 1 && d3 >= 0 && N >= 1, MML_ERR_INVALID_ARG, "kron_linear_wgrad: bad sizes");
+  MML_REQUIRE(aligned16(table) && (reinterpret_cast<uintptr_t>(workspace) & 1023u) == 0, MML_ERR_INVALID_ARG,
+              "kron_linear_wgrad: table must be 16-byte and workspace 1024-byte aligned");
+  const WgPlan p = make_wg_plan(B, N, d1, d2, d3);
+  MML_REQUIRE(p.ok, MML_ERR_UNSUPPORTED, "kron_linear_wgrad: N=%d (<=256) exceeds the tile budget", N);
+  MML_REQUIRE(workspace_bytes >= p.dyT_bytes + p.part_bytes, MML_ERR_WORKSPACE, "kron_linear_wgrad: workspace too small");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  float* dyT = static_cast<float*>(workspace);
+  float* part = reinterpret_cast<float*>(static_cast<char*>(workspace) + p.dyT_bytes);
+  const KronShape s = make_kron_shape(d1, d2, d3);
+  {
+    const dim3 grid(static_cast<unsigned>(p.Bpad / 32), (p.Np + 31) / 32);
+    kron_transpose_dy_kernel<<<grid, dim3(32, 8), 0, st>>>(dy, B, N, p.Np, p.Bpad, dyT);
+    int rc = check_launch("kron_transpose_dy_kernel");
+    if (rc != MML_OK) return rc;
+  }
+  CUtensorMap tmap;
+  int rc = get_tensor_map(dyT, p.Np, static_cast<int32_t>(p.Bpad), &tmap);
+  if (rc != MML_OK) return rc;
+  WgArgs a{};
+  a.f1 = f1; a.f2 = f2; a.f3 = f3;
+  a.table = reinterpret_cast<const int4*>(table);
+  a.part = part;
+  a.B = B; a.d1 = d1; a.d2 = d2; a.d3 = d3; a.N = N; a.Np = p.Np; a.nchunks = p.nchunks; a.Kp = p.Kp;
+  a.nblocks = p.nblocks; a.blocks_per_split = p.blocks_per_split;
+  a.stages = p.stages; a.tmem_cols = p.tmem_cols;
+  a.idesc = make_idesc_tf32(kTileM, p.Np);
+  a.dr = make_kron_dropout(drop_p, seed, training, s.Kk);
+  const dim3 grid(p.ktiles, p.bsplit);
+  if (a.dr.thresh != 0u) {
+    MML_CUDA(cudaFuncSetAttribute(kron_wgrad_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(p.smem)));
+    kron_wgrad_tc_kernel<true><<<grid, kThreadsTc, p.smem, st>>>(tmap, a);
+  } else {
+    MML_CUDA(cudaFuncSetAttribute(kron_wgrad_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(p.smem)));
+    kron_wgrad_tc_kernel<false><<<grid, kThreadsTc, p.smem, st>>>(tmap, a);
+  }
+  rc = check_launch("kron_wgrad_tc_kernel");
+  if (rc != MML_OK) return rc;
+  const int64_t total = static_cast<int64_t>(N) * p.Kp;
+  int64_t g = (total + 255) / 256;
+  if (g > 148 * 16) g = 148 * 16;
+  kron_unpack_kernel<<<static_cast<unsigned>(g), 256, 0, st>>>(part, p.bsplit, N, p.Kp, s.Kk, a.table, dW);
+  return check_launch("kron_unpack_kernel");
+}

@@ -73,15 +73,16 @@ __global__ void __launch_bounds__(kRouteThreads) shard_route_strided_kernel(
     const uint32_t row = valid ? static_cast<uint32_t>(idx[b * cols + k]) : 0u;
     const int owner = valid ? static_cast<int>(row / rpr) : -1;
     const uint32_t local = row - static_cast<uint32_t>(owner < 0 ? 0 : owner) * rpr;
-    for (int o = 0; o < world; ++o) {
-      const unsigned m = __ballot_sync(kFullMask, owner == o);
-      if (m == 0u) continue;
-      const int32_t base = run[warp][o];
-      if (owner == o) out[(static_cast<int64_t>(o) * plane + slot) * chunk_cols + base + __popc(m & lt)] = static_cast<int32_t>(local);
-      __syncwarp();
-      if (lane == 0) run[warp][o] = base + __popc(m);
-      __syncwarp();
+    // lanes with the same owner form a group; rank inside the group = stable position
+    const unsigned peers = __match_any_sync(kFullMask, owner);
+    int32_t base = 0;
+    if (valid) {
+      base = run[warp][owner];
+      out[(static_cast<int64_t>(owner) * plane + slot) * chunk_cols + base + __popc(peers & lt)] = static_cast<int32_t>(local);
     }
+    __syncwarp();
+    if (valid && lane == __ffs(peers) - 1) run[warp][owner] = base + __popc(peers);
+    __syncwarp();
   }
   if (lane < world) counts[static_cast<int64_t>(lane) * plane + slot] = run[warp][lane];
 }

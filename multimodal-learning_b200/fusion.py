@@ -25,6 +25,11 @@ from torch.autograd.function import once_differentiable
 from . import _cabi
 
 
+def ctypes_ptr(addr):
+    import ctypes
+    return ctypes.c_void_p(addr)
+
+
 def init_max_weights(module):
     """utils.py:239-244 of the reference: every nn.Linear gets N(0, 1/sqrt(fan_in)) weights, zero bias."""
     for m in module.modules():
@@ -48,6 +53,25 @@ class KronLinearState:
         self.packed_key = None
         self.path = "auto"          # "auto" | "simt" (tests use "simt" as the exact-fp32 cross-check)
         self._plans = {}            # (B, N) -> (tensor-core path usable, workspace bytes)
+        self._wg_plans = {}         # (B, N) -> (tensor-core wgrad usable, workspace bytes)
+
+    def wgrad_plan(self, B, N):
+        key = (B, N)
+        if key not in self._wg_plans:
+            lib = _cabi.lib()
+            ok = bool(lib.mml_kron_wgrad_supported(B, N, *self.dims))
+            self._wg_plans[key] = (ok, lib.mml_kron_wgrad_workspace_bytes(B, N, *self.dims) if ok else 0)
+        return self._wg_plans[key]
+
+    def ensure_table(self, device):
+        if self.table is None or self.table.device != device:
+            lib = _cabi.lib()
+            d1, d2, d3 = self.dims
+            n = lib.mml_kron_num_chunks(d1, d2, d3)
+            host = torch.empty(n * 8, dtype=torch.int32)
+            _cabi.check(lib.mml_kron_chunk_table_host(d1, d2, d3, _cabi.hptr(host)), "mml_kron_chunk_table_host")
+            self.table = host.to(device)
+            self.packed_key = None
 
     def plan(self, B, N):
         key = (B, N)
@@ -61,12 +85,7 @@ class KronLinearState:
         lib = _cabi.lib()
         d1, d2, d3 = self.dims
         dev = weight.device
-        if self.table is None or self.table.device != dev:
-            n = lib.mml_kron_num_chunks(d1, d2, d3)
-            host = torch.empty(n * 8, dtype=torch.int32)
-            _cabi.check(lib.mml_kron_chunk_table_host(d1, d2, d3, _cabi.hptr(host)), "mml_kron_chunk_table_host")
-            self.table = host.to(dev)
-            self.packed_key = None
+        self.ensure_table(dev)
         key = (weight.data_ptr(), weight._version, tuple(weight.shape))
         if key != self.packed_key:
             N = weight.shape[0]
@@ -107,6 +126,7 @@ class _KronLinearFn(torch.autograd.Function):
                                               N, float(drop_p), int(seed), int(training), _cabi.dptr(y), st)
             _cabi.check(rc, "mml_kron_linear_fwd_simt")
         ctx.save_for_backward(w, *fs)
+        ctx.state = state
         ctx.cfg = (state.dims, float(drop_p), int(training), int(seed), bias is not None)
         return y
 
@@ -123,11 +143,26 @@ class _KronLinearFn(torch.autograd.Function):
         need_f = any(ctx.needs_input_grad[6:])
         dW = torch.empty_like(w) if need_w else None
         dfs = [torch.empty_like(f) for f in fs] if need_f else [None] * len(fs)
-        rc = lib.mml_kron_linear_bwd_simt(
-            _cabi.dptr(fs[0]), _cabi.dptr(fs[1]), _cabi.dptr(fs[2]) if d3 > 0 else None, B, d1, d2, d3, _cabi.dptr(w),
-            _cabi.dptr(dy), N, drop_p, seed, training, _cabi.dptr(dfs[0]), _cabi.dptr(dfs[1]),
-            _cabi.dptr(dfs[2]) if d3 > 0 else None, _cabi.dptr(dW), _cabi.cur_stream(dev))
-        _cabi.check(rc, "mml_kron_linear_bwd_simt")
+        state = ctx.state
+        f3p = _cabi.dptr(fs[2]) if d3 > 0 else None
+        st = _cabi.cur_stream(dev)
+        wg_ok, wg_ws = state.wgrad_plan(B, N)
+        simt_dW = dW
+        if need_w and state.path == "auto" and wg_ok:            # weight gradient on the tensor cores
+            state.ensure_table(dev)
+            ws = torch.empty(wg_ws + 1024, dtype=torch.uint8, device=dev)
+            off = (-ws.data_ptr()) % 1024
+            rc = lib.mml_kron_linear_wgrad(_cabi.dptr(fs[0]), _cabi.dptr(fs[1]), f3p, B, d1, d2, d3, _cabi.dptr(state.table),
+                                           _cabi.dptr(dy), N, drop_p, seed, training, _cabi.dptr(dW),
+                                           ctypes_ptr(ws.data_ptr() + off), wg_ws, st)
+            _cabi.check(rc, "mml_kron_linear_wgrad")
+            simt_dW = None
+        if need_f or simt_dW is not None:
+            rc = lib.mml_kron_linear_bwd_simt(
+                _cabi.dptr(fs[0]), _cabi.dptr(fs[1]), f3p, B, d1, d2, d3, _cabi.dptr(w), _cabi.dptr(dy), N, drop_p, seed,
+                training, _cabi.dptr(dfs[0]), _cabi.dptr(dfs[1]), _cabi.dptr(dfs[2]) if d3 > 0 else None,
+                _cabi.dptr(simt_dW), st)
+            _cabi.check(rc, "mml_kron_linear_bwd_simt")
         dbias = dy.sum(0) if (has_bias and ctx.needs_input_grad[2]) else None
         return (None, dW, dbias, None, None, None, *dfs)
 

@@ -8,14 +8,19 @@ from torch.profiler import profile, ProfilerActivity
 import bench
 
 def main():
-    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
     torch.cuda.set_device(rank)
     dev = torch.device("cuda", rank)
-    dist.init_process_group("nccl", device_id=dev)
-    from multimodal_learning_b200.sharded import ShardedCRDLoss
     cfg = dict(bench.C2)
-    n = bench.ROWS_PER_GPU_SHARDED * world
-    mod = ShardedCRDLoss(bench.make_opt(cfg, n), device=dev)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+        from multimodal_learning_b200.sharded import ShardedCRDLoss
+        n = bench.ROWS_PER_GPU_SHARDED * world
+        mod = ShardedCRDLoss(bench.make_opt(cfg, n), device=dev)
+    else:
+        import multimodal_learning_b200 as pkg
+        n = cfg["n"]
+        mod = pkg.CRDLoss(bench.make_opt(cfg, n)).to(dev)
     params = list(mod.parameters())
     optim = torch.optim.Adam(params, lr=2e-4, fused=True)
     gen = torch.Generator(device=dev).manual_seed(rank)
@@ -26,7 +31,8 @@ def main():
         for p in params: p.grad = None
         loss = mod(f_s, f_t, idx, cidx); loss.backward(); optim.step()
     for i in range(5): step(i)
-    torch.cuda.synchronize(); dist.barrier()
+    torch.cuda.synchronize()
+    if world > 1: dist.barrier()
     steps = 10
     with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
         for i in range(steps): step(i)
@@ -37,5 +43,5 @@ def main():
         t0 = min(e.time_range.start for e in ev); t1 = max(e.time_range.end for e in ev)
         busy = sum(e.time_range.end - e.time_range.start for e in ev)
         print(f"span {(t1-t0)/steps:.1f} us/step, sum of kernel time {busy/steps:.1f} us/step")
-    dist.destroy_process_group()
+    if world > 1: dist.destroy_process_group()
 main()

@@ -123,10 +123,10 @@ def test_kron_linear_forward_backward_vs_oracle(pkg, fo, B, dims, N):
         y = kron_linear(st, fd, Wd, bd)
         assert rel_err(y, want) < tol, path
         (y * G.float().to(DEV)).sum().backward()
-        # backward kernels are fp32 in both paths
+        # factor gradients are fp32 CUDA-core kernels in both paths; dW runs on the tensor cores (TF32) in "auto"
         for i in range(len(dims)):
             assert rel_err(fd[i].grad, fs64[i].grad) < TOL_FP32 * 5, (path, i)
-        assert rel_err(Wd.grad, W64.grad) < TOL_FP32 * 5, path
+        assert rel_err(Wd.grad, W64.grad) < (TOL_FP32 * 5 if path == "simt" else TOL_TC), path
         assert rel_err(bd.grad, b64.grad) < TOL_FP32 * 5, path
 
 
@@ -172,7 +172,7 @@ def test_dropout_mask_is_the_documented_counter_hash(pkg, fo, dims, N, p):
         (y * G.float().to(DEV)).sum().backward()
         for i in range(len(dims)):
             assert rel_err(fd[i].grad, fs64[i].grad) < TOL_FP32 * 5
-        assert rel_err(Wd.grad, W64.grad) < TOL_FP32 * 5
+        assert rel_err(Wd.grad, W64.grad) < (TOL_FP32 * 5 if path == "simt" else TOL_TC)
     # eval mode ignores p
     st = KronLinearState(dims)
     y_eval = kron_linear(st, [f.to(DEV) for f in fs], W.to(DEV), bias.to(DEV), drop_p=p, training=False)
