@@ -222,6 +222,22 @@ int     mml_kron_linear_wgrad(const float* f1, const float* f2, const float* f3,
                               int32_t N, float drop_p, uint64_t seed, int32_t training, float* dW,
                               void* workspace, size_t workspace_bytes, void* stream);
 
+/* Factor gradients on the tensor cores.  dA = m * (dy W) is accumulated tile by tile in TMEM
+ * (M = 128 batch rows, N = 128 packed k, K = n) and folded into df1/df2/df3 by the epilogue; it is
+ * never stored.  Needs the TRANSPOSED packed weight WpT [32*chunks, roundup(N,32)] (128-byte aligned,
+ * mml_kron_packed_t_floats floats, refreshed by mml_kron_pack_weight_t whenever W changes).
+ * The appended 1 of each factor receives no gradient.                                          */
+int     mml_kron_dgrad_supported(int64_t B, int32_t N, int32_t d1, int32_t d2, int32_t d3);
+int64_t mml_kron_packed_t_floats(int32_t N, int32_t d1, int32_t d2, int32_t d3);
+int     mml_kron_pack_weight_t(const float* W, int32_t N, int32_t d1, int32_t d2, int32_t d3,
+                               const int32_t* table, float* WpT, void* stream);
+size_t  mml_kron_dgrad_workspace_bytes(int64_t B, int32_t N, int32_t d1, int32_t d2, int32_t d3);
+int     mml_kron_linear_dgrad(const float* f1, const float* f2, const float* f3, int64_t B,
+                              int32_t d1, int32_t d2, int32_t d3, const int32_t* table, const float* WpT,
+                              const float* dy, int32_t N, float drop_p, uint64_t seed, int32_t training,
+                              float* df1, float* df2, float* df3,
+                              void* workspace, size_t workspace_bytes, void* stream);
+
 /* Exact-fp32 CUDA-core path on the dense weight (any N, any widths): forward, and backward
  *   dW[n,k] = sum_b dy[b,n] A[b,k] m[b,k]            (NULL to skip)
  *   df_x    = factor gradients through dA = m * (dy W), contracted on chip (all NULL to skip);

@@ -57,6 +57,13 @@ _SIGNATURES = {
     "mml_kron_linear_wgrad": (ctypes.c_int, [
         _P, _P, _P, c_int64, c_int32, c_int32, c_int32, _P, _P, c_int32, c_float, ctypes.c_uint64, c_int32,
         _P, _P, c_size_t, _P]),
+    "mml_kron_dgrad_supported": (ctypes.c_int, [c_int64, c_int32, c_int32, c_int32, c_int32]),
+    "mml_kron_packed_t_floats": (c_int64, [c_int32, c_int32, c_int32, c_int32]),
+    "mml_kron_pack_weight_t": (ctypes.c_int, [_P, c_int32, c_int32, c_int32, c_int32, _P, _P, _P]),
+    "mml_kron_dgrad_workspace_bytes": (c_size_t, [c_int64, c_int32, c_int32, c_int32, c_int32]),
+    "mml_kron_linear_dgrad": (ctypes.c_int, [
+        _P, _P, _P, c_int64, c_int32, c_int32, c_int32, _P, _P, _P, c_int32, c_float, ctypes.c_uint64, c_int32,
+        _P, _P, _P, _P, c_size_t, _P]),
     "mml_kron_linear_fwd_simt": (ctypes.c_int, [
         _P, _P, _P, c_int64, c_int32, c_int32, c_int32, _P, _P, c_int32, c_float, ctypes.c_uint64, c_int32, _P, _P]),
     "mml_kron_linear_bwd_simt": (ctypes.c_int, [

@@ -402,3 +402,431 @@ extern "C" int mml_kron_linear_wgrad(const float* f1, const float* f2, const flo
   kron_unpack_kernel<<<static_cast<unsigned>(g), 256, 0, st>>>(part, p.bsplit, N, p.Kp, s.Kk, a.table, dW);
   return check_launch("kron_unpack_kernel");
 }
+
+// =====================================================================================================
+// K2: factor gradients (dgrad) on tcgen05 tensor cores.
+//
+//   dA[b, k] = m[b,k] * sum_n dy[b,n] W[n,k]        -- never stored: each [128 rows x 128 packed k] tile is
+//   accumulated in TENSOR MEMORY (M = 128 batch lanes, N = 128 packed k, K = n) and folded on the spot into
+//   the per-row factor gradients by the epilogue warps (thread = batch row):
+//     chunk (p, q, vector segment x):  A = R[p] R[q] x[e]   =>   dx[e]   += dA[e] R[p] R[q]
+//                                                               dR[p]   += (sum_e dA[e] x[e]) R[q],   dR[q] likewise
+//   A operand = the dy tile, written ONCE per CTA into TMEM (tcgen05.st); B operand = [128 k x 32 n] boxes of
+//   the transposed packed weight WpT [Kp, Np32] streamed by TMA; two accumulator tiles alternate so the
+//   epilogue of tile t overlaps the MMAs of tile t+1.  Split over k tiles -> per-split partial gradients,
+//   summed in split order by kron_dgrad_reduce_kernel.
+// =====================================================================================================
+namespace mml {
+namespace {
+
+constexpr int kDgThreads = 192;           // 4 epilogue warps (one thread per batch row) + TMA warp + MMA warp
+constexpr int kDgTileK = 128;             // packed k per accumulator tile (4 chunks)
+constexpr int kDgBoxN = 32;               // n per TMA box / pipeline stage
+constexpr uint32_t kDgStageBytes = kDgTileK * kDgBoxN * 4;   // 16 KB
+
+struct DgArgs {
+  const float* f1;
+  const float* f2;
+  const float* f3;
+  const float* dy;            // [B, N]
+  const int4* table;
+  float* part;                // [ksplit][B][dsum]  (zero-initialised)
+  int64_t B;
+  int32_t d1, d2, d3, dsum;
+  int32_t N, Np32, nchunks;
+  int32_t ktiles, tiles_per_split;
+  int32_t n_scal, stages, tmem_cols, table_in_smem;
+  uint32_t idesc;
+  KronDropout dr;
+};
+
+template <bool kDropout>
+__global__ void __launch_bounds__(kDgThreads, 1) kron_dgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_wT, const DgArgs a) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* sm_b = smem;                                                              // [stages][16 KB]
+  float* sm_S = reinterpret_cast<float*>(smem + static_cast<size_t>(a.stages) * kDgStageBytes);   // R values  [n_scal][128]
+  float* sm_dR = sm_S + static_cast<size_t>(a.n_scal) * kTileM;                                   // dR accum  [n_scal][128]
+  int4* sm_tab = reinterpret_cast<int4*>(sm_dR + static_cast<size_t>(a.n_scal) * kTileM);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sm_tab + (a.table_in_smem ? 2 * a.nchunks : 0));
+  uint64_t* bar_full = bars;                     // [stages] weight box landed
+  uint64_t* bar_empty = bars + a.stages;         // [stages] MMAs reading the box done
+  uint64_t* bar_acc_full = bars + 2 * a.stages;  // [2] accumulator tile complete
+  uint64_t* bar_acc_empty = bar_acc_full + 2;    // [2] epilogue drained the tile (4 warp arrivals)
+  uint32_t* sm_tmem = reinterpret_cast<uint32_t*>(bar_acc_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int64_t b0 = static_cast<int64_t>(blockIdx.x) * kTileM;
+  const int t_begin = blockIdx.y * a.tiles_per_split;
+  const int t_end = min(a.ktiles, t_begin + a.tiles_per_split);
+  const int nbox = a.Np32 / kDgBoxN;
+
+  if (warp == 4 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_wT)) : "memory");
+    for (int s = 0; s < a.stages; ++s) {
+      mbar_init(&bar_full[s], 1);
+      mbar_init(&bar_empty[s], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&bar_acc_full[i], 1);
+      mbar_init(&bar_acc_empty[i], 4);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 5) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(sm_tmem)), "r"(a.tmem_cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (a.table_in_smem)
+    for (int i = t_begin * 8 + threadIdx.x; i < min(a.nchunks, t_end * 4) * 2; i += kDgThreads) sm_tab[i] = __ldg(a.table + i);
+  if (warp < 4) {
+    const int row = threadIdx.x;
+    const int64_t b = b0 + row;
+    const bool live = b < a.B;
+    const int ns = a.n_scal - 1;
+    sm_S[row] = 1.0f;
+    sm_dR[row] = 0.f;
+    for (int i0 = 0; i0 < ns; i0 += 8) {
+      float tmp[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int i = i0 + u;
+        float x = 0.f;
+        if (live && i < ns) x = (i < a.d1) ? __ldg(a.f1 + b * a.d1 + i) : __ldg(a.f2 + b * a.d2 + (i - a.d1));
+        tmp[u] = x;
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+        if (i0 + u < ns) {
+          sm_S[(1 + i0 + u) * kTileM + row] = tmp[u];
+          sm_dR[(1 + i0 + u) * kTileM + row] = 0.f;
+        }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *sm_tmem;
+  const uint32_t tmem_acc = tmem_base;                 // 2 x 128 accumulator columns
+  const uint32_t tmem_a = tmem_base + 2 * kDgTileK;    // dy tile: Np32 columns
+  const int4* tab = a.table_in_smem ? sm_tab : a.table;
+  uint64_t* bar_a_ready = bar_acc_empty;               // (reuse note: A readiness is signalled through __syncthreads below)
+  (void)bar_a_ready;
+
+  // ---- A operand: this CTA's dy rows -> TMEM, once (epilogue warps), then a CTA-wide sync publishes them ----
+  if (warp < 4) {
+    const int row = threadIdx.x;
+    const int64_t b = b0 + row;
+    const bool live = b < a.B;
+    const uint32_t lane_base = static_cast<uint32_t>(warp * 32) << 16;
+    for (int n0 = 0; n0 < a.Np32; n0 += 16) {
+      uint32_t r[16];
+#pragma unroll
+      for (int u = 0; u < 16; ++u) {
+        const int n = n0 + u;
+        const float x = (live && n < a.N) ? __ldg(a.dy + b * a.N + n) : 0.f;
+        r[u] = __float_as_uint(x) + 0x1000u;
+      }
+      tc_st_32x32b_x16(tmem_a + lane_base + n0, r);
+    }
+    tc_wait_st();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+
+  if (warp == 4) {
+    if (lane == 0) {                     // ===== TMA producer: [128 k x 32 n] boxes of WpT =====
+      int s = 0;
+      uint32_t ph = 0;
+      for (int t = t_begin; t < t_end; ++t)
+        for (int j = 0; j < nbox; ++j) {
+          mbar_wait(&bar_empty[s], ph ^ 1);
+          mbar_arrive_expect_tx(&bar_full[s], kDgStageBytes);
+          tma_load_2d(sm_b + static_cast<size_t>(s) * kDgStageBytes, &tmap_wT, j * kDgBoxN, t * kDgTileK, &bar_full[s]);
+          if (++s == a.stages) { s = 0; ph ^= 1; }
+        }
+    }
+  } else if (warp == 5) {
+    if (lane == 0) {                     // ===== MMA issuer =====
+      int s = 0;
+      uint32_t ph = 0;
+      for (int t = t_begin; t < t_end; ++t) {
+        const int it = t - t_begin;
+        const int buf = it & 1;
+        mbar_wait(&bar_acc_empty[buf], ((it >> 1) & 1) ^ 1);            // epilogue has drained this accumulator
+        tc_fence_after();
+        for (int j = 0; j < nbox; ++j) {
+          mbar_wait(&bar_full[s], ph);
+          tc_fence_after();
+          const uint32_t b_addr = smem_u32(sm_b + static_cast<size_t>(s) * kDgStageBytes);
+#pragma unroll
+          for (int i = 0; i < kDgBoxN / 8; ++i) {
+            const uint64_t b_desc = umma_desc_k_sw128(b_addr + i * 32);
+            tc_mma_tf32_ts(tmem_acc + buf * kDgTileK, tmem_a + j * kDgBoxN + i * 8, b_desc, a.idesc, (j > 0 || i > 0) ? 1u : 0u);
+          }
+          tc_commit(&bar_empty[s]);
+          if (++s == a.stages) { s = 0; ph ^= 1; }
+        }
+        tc_commit(&bar_acc_full[buf]);
+      }
+    }
+  } else {
+    // ===== epilogue: thread = batch row; fold dA tiles into factor gradients =====
+    const int row = threadIdx.x;
+    const int64_t b = b0 + row;
+    const bool live = b < a.B;
+    const uint32_t lane_base = static_cast<uint32_t>(warp * 32) << 16;
+    float* my_part = a.part + (static_cast<int64_t>(blockIdx.y) * a.B + b) * a.dsum;
+    float v[32], dv[32];
+#pragma unroll
+    for (int e = 0; e < 32; ++e) { v[e] = 0.f; dv[e] = 0.f; }
+    int cur_src = -1, cur_col = -1, cur_len = 0;
+    auto flush = [&]() {
+      if (cur_src > 0 && live) {
+        const int off = (cur_src == 1 ? 0 : (cur_src == 2 ? a.d1 : a.d1 + a.d2)) + cur_col;
+#pragma unroll
+        for (int e = 0; e < 32; ++e)
+          if (e < cur_len) my_part[off + e] += dv[e];
+      }
+    };
+    for (int t = t_begin; t < t_end; ++t) {
+      const int it = t - t_begin;
+      const int buf = it & 1;
+      mbar_wait(&bar_acc_full[buf], (it >> 1) & 1);
+      tc_fence_after();
+      for (int c = 0; c < 4; ++c) {
+        const int cg = t * 4 + c;
+        if (cg >= a.nchunks) break;
+        const int4 e0 = tab[2 * cg];
+        const int4 e1 = tab[2 * cg + 1];
+        if (e0.z != cur_src || e0.w != cur_col) {
+          flush();
+          cur_src = e0.z; cur_col = e0.w; cur_len = e1.x;
+          const float* src = cur_src == 1 ? a.f1 : (cur_src == 2 ? a.f2 : a.f3);
+          const int d = cur_src == 1 ? a.d1 : (cur_src == 2 ? a.d2 : a.d3);
+#pragma unroll
+          for (int e = 0; e < 32; ++e) {
+            float x = 0.f;
+            if (cur_src == 0) x = (e == 0) ? 1.0f : 0.f;
+            else if (live && e < cur_len) x = __ldg(src + b * d + cur_col + e);
+            v[e] = x;
+            dv[e] = 0.f;
+          }
+        }
+        uint32_t acc[32];
+        tc_ld_32x32b_x16(tmem_acc + lane_base + buf * kDgTileK + c * 32, *reinterpret_cast<uint32_t(*)[16]>(&acc[0]));
+        tc_ld_32x32b_x16(tmem_acc + lane_base + buf * kDgTileK + c * 32 + 16, *reinterpret_cast<uint32_t(*)[16]>(&acc[16]));
+        tc_wait_ld();
+        const float sp = sm_S[e0.x * kTileM + row], sq = sm_S[e0.y * kTileM + row];
+        float s = sp * sq;
+        if (kDropout) s *= a.dr.scale;
+        float ds = 0.f;
+#pragma unroll
+        for (int e = 0; e < 32; ++e) {
+          float g = __uint_as_float(acc[e]);
+          if (kDropout) {
+            const int klog = e1.y + e * e1.z;
+            const int64_t cc = b * a.dr.pairs_per_row + (klog >> 1);
+            const uint32_t h = kron_hash(static_cast<uint32_t>(cc), static_cast<uint32_t>(static_cast<uint64_t>(cc) >> 32),
+                                         a.dr.seed_lo, a.dr.seed_hi);
+            const uint32_t r16 = (klog & 1) ? (h >> 16) : (h & 0xffffu);
+            g = (r16 >= a.dr.thresh) ? g : 0.f;
+          }
+          ds = fmaf(g, v[e], ds);
+          dv[e] = fmaf(g, s, dv[e]);
+        }
+        if (kDropout) ds *= a.dr.scale;
+        if (e0.x != 0) sm_dR[e0.x * kTileM + row] += ds * sq;
+        if (e0.y != 0) sm_dR[e0.y * kTileM + row] += ds * sp;
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bar_acc_empty[buf]);
+    }
+    flush();
+    if (live) {
+      const int ns = a.n_scal - 1;                      // R[1..] = f1 (then f2 when trilinear): same offsets as the output layout
+      for (int i = 0; i < ns; ++i) my_part[i] += sm_dR[(1 + i) * kTileM + row];
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 5) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(a.tmem_cols) : "memory");
+  }
+}
+
+// WpT[kp][n] = TF32(W[n][klog(kp)]) (0 for padding), n < Np32
+__global__ void kron_pack_t_kernel(const float* __restrict__ W, int32_t N, int32_t Np32, int32_t Kk, const int4* __restrict__ table,
+                                   int32_t nchunks, float* __restrict__ WpT) {
+  const int64_t total = static_cast<int64_t>(nchunks) * kChunkK * Np32;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int n = static_cast<int>(i % Np32);
+    const int kp = static_cast<int>(i / Np32);
+    const int4 e1 = __ldg(table + 2 * (kp >> 5) + 1);
+    const int e = kp & 31;
+    float w = 0.f;
+    if (n < N && e < e1.x) w = __ldg(W + static_cast<int64_t>(n) * Kk + e1.y + e * e1.z);
+    const uint32_t u = (__float_as_uint(w) + 0x1000u) & 0xFFFFE000u;
+    WpT[i] = __uint_as_float(u);
+  }
+}
+
+__global__ void kron_dgrad_reduce_kernel(const float* __restrict__ part, int32_t ksplit, int64_t B, int32_t d1, int32_t d2,
+                                         int32_t d3, float* __restrict__ df1, float* __restrict__ df2, float* __restrict__ df3) {
+  const int dsum = d1 + d2 + d3;
+  const int64_t total = B * dsum;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    float t = 0.f;
+    for (int z = 0; z < ksplit; ++z) t += part[static_cast<int64_t>(z) * total + i];
+    const int64_t b = i / dsum;
+    const int x = static_cast<int>(i % dsum);
+    if (x < d1) df1[b * d1 + x] = t;
+    else if (x < d1 + d2) df2[b * d2 + (x - d1)] = t;
+    else df3[b * d3 + (x - d1 - d2)] = t;
+  }
+}
+
+struct DgPlan {
+  int32_t nchunks, Np32, Kp, n_scal, stages, tmem_cols, ktiles, ksplit, tiles_per_split, table_in_smem, dsum;
+  size_t smem, part_bytes;
+  bool ok;
+};
+
+DgPlan make_dg_plan(int64_t B, int32_t N, int32_t d1, int32_t d2, int32_t d3) {
+  DgPlan p{};
+  p.nchunks = static_cast<int32_t>(build_chunks(d1, d2, d3).size());
+  p.Kp = p.nchunks * kChunkK;
+  p.Np32 = (N + 31) / 32 * 32;
+  p.n_scal = 1 + d1 + (d3 > 0 ? d2 : 0);
+  p.dsum = d1 + d2 + d3;
+  p.ktiles = (p.nchunks + 3) / 4;
+  const size_t table_bytes = static_cast<size_t>(p.nchunks) * sizeof(Chunk);
+  p.table_in_smem = table_bytes <= static_cast<size_t>(kMaxSmemTable) ? 1 : 0;
+  const size_t fixed = 2 * static_cast<size_t>(p.n_scal) * kTileM * sizeof(float) + (p.table_in_smem ? table_bytes : 0) + 256 + 1024;
+  int stages = fixed + 2 * kDgStageBytes <= 227 * 1024 ? static_cast<int>((227 * 1024 - fixed) / kDgStageBytes) : 0;
+  if (stages > 6) stages = 6;
+  p.stages = stages;
+  p.tmem_cols = (2 * kDgTileK + p.Np32) <= 256 ? 256 : 512;
+  p.ok = p.Np32 <= 256 && stages >= 2;
+  p.smem = fixed + static_cast<size_t>(stages > 0 ? stages : 0) * kDgStageBytes;
+  const int64_t mtiles = (B + kTileM - 1) / kTileM;
+  int64_t ks = mtiles < 148 ? (148 + mtiles - 1) / mtiles : 1;
+  const int64_t max_ks = p.ktiles / 2 > 0 ? p.ktiles / 2 : 1;
+  if (ks > max_ks) ks = max_ks;
+  if (ks > 32) ks = 32;
+  p.tiles_per_split = static_cast<int32_t>((p.ktiles + ks - 1) / ks);
+  p.ksplit = (p.ktiles + p.tiles_per_split - 1) / p.tiles_per_split;
+  p.part_bytes = static_cast<size_t>(p.ksplit) * B * p.dsum * sizeof(float);
+  return p;
+}
+
+// TMA descriptor of WpT [Kp rows, Np32 cols]: boxes of 32 n x 128 k
+int get_tensor_map_wT(const float* WpT, int32_t Np32, int32_t Kp, CUtensorMap* out) {
+  static std::mutex mu;
+  static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> cache;
+  std::lock_guard<std::mutex> lock(mu);
+  const MapKey key{WpT, Np32, Kp};
+  auto it = cache.find(key);
+  if (it != cache.end()) { *out = it->second; return MML_OK; }
+  EncodeTiledFn enc = get_encode_fn();
+  MML_REQUIRE(enc != nullptr, MML_ERR_CUDA, "kron: cuTensorMapEncodeTiled entry point unavailable");
+  CUtensorMap m;
+  const cuuint64_t gdim[2] = {static_cast<cuuint64_t>(Np32), static_cast<cuuint64_t>(Kp)};
+  const cuuint64_t gstride[1] = {static_cast<cuuint64_t>(Np32) * sizeof(float)};
+  const cuuint32_t box[2] = {static_cast<cuuint32_t>(kDgBoxN), static_cast<cuuint32_t>(kDgTileK)};
+  const cuuint32_t estride[2] = {1, 1};
+  const CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(WpT), gdim, gstride, box, estride,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  MML_REQUIRE(r == CUDA_SUCCESS, MML_ERR_CUDA, "kron: cuTensorMapEncodeTiled(WpT) failed (%d)", static_cast<int>(r));
+  if (cache.size() > 256) cache.clear();
+  cache[key] = m;
+  *out = m;
+  return MML_OK;
+}
+
+}  // namespace
+}  // namespace mml
+
+extern "C" int mml_kron_dgrad_supported(int64_t B, int32_t N, int32_t d1, int32_t d2, int32_t d3) {
+  if (B < 1 || N < 1 || d1 < 1 || d2 < 1 || d3 < 0) return 0;
+  return make_dg_plan(B, N, d1, d2, d3).ok ? 1 : 0;
+}
+
+extern "C" int64_t mml_kron_packed_t_floats(int32_t N, int32_t d1, int32_t d2, int32_t d3) {
+  if (N < 1 || d1 < 1 || d2 < 1 || d3 < 0) return -1;
+  return static_cast<int64_t>(build_chunks(d1, d2, d3).size()) * kChunkK * ((N + 31) / 32 * 32);
+}
+
+extern "C" int mml_kron_pack_weight_t(const float* W, int32_t N, int32_t d1, int32_t d2, int32_t d3, const int32_t* table,
+                                      float* WpT, void* stream) {
+  MML_REQUIRE(W && table && WpT && N >= 1, MML_ERR_INVALID_ARG, "kron_pack_weight_t: bad arguments");
+  MML_REQUIRE(aligned16(table) && (reinterpret_cast<uintptr_t>(WpT) & 127u) == 0, MML_ERR_INVALID_ARG,
+              "kron_pack_weight_t: table must be 16-byte and WpT 128-byte aligned");
+  const KronShape s = make_kron_shape(d1, d2, d3);
+  const int32_t nchunks = static_cast<int32_t>(build_chunks(d1, d2, d3).size());
+  const int32_t Np32 = (N + 31) / 32 * 32;
+  const int64_t total = static_cast<int64_t>(nchunks) * kChunkK * Np32;
+  int64_t grid = (total + 255) / 256;
+  if (grid > 148 * 16) grid = 148 * 16;
+  kron_pack_t_kernel<<<static_cast<unsigned>(grid), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      W, N, Np32, s.Kk, reinterpret_cast<const int4*>(table), nchunks, WpT);
+  return check_launch("kron_pack_t_kernel");
+}
+
+extern "C" size_t mml_kron_dgrad_workspace_bytes(int64_t B, int32_t N, int32_t d1, int32_t d2, int32_t d3) {
+  if (B < 1 || N < 1 || d1 < 1 || d2 < 1 || d3 < 0) return 0;
+  return make_dg_plan(B, N, d1, d2, d3).part_bytes + 256;
+}
+
+extern "C" int mml_kron_linear_dgrad(const float* f1, const float* f2, const float* f3, int64_t B, int32_t d1, int32_t d2,
+                                     int32_t d3, const int32_t* table, const float* WpT, const float* dy, int32_t N,
+                                     float drop_p, uint64_t seed, int32_t training, float* df1, float* df2, float* df3,
+                                     void* workspace, size_t workspace_bytes, void* stream) {
+  MML_REQUIRE(f1 && f2 && table && WpT && dy && df1 && df2 && workspace, MML_ERR_INVALID_ARG, "kron_linear_dgrad: null pointer");
+  MML_REQUIRE((d3 > 0) == (f3 != nullptr) && (d3 > 0) == (df3 != nullptr), MML_ERR_INVALID_ARG,
+              "kron_linear_dgrad: f3/df3 and d3 must all be set or all be absent");
+  MML_REQUIRE(B >= 1 && d1 >= 1 && d2 >= 1 && d3 >= 0 && N >= 1, MML_ERR_INVALID_ARG, "kron_linear_dgrad: bad sizes");
+  MML_REQUIRE(aligned16(table) && (reinterpret_cast<uintptr_t>(WpT) & 127u) == 0, MML_ERR_INVALID_ARG,
+              "kron_linear_dgrad: table must be 16-byte and WpT 128-byte aligned");
+  const DgPlan p = make_dg_plan(B, N, d1, d2, d3);
+  MML_REQUIRE(p.ok, MML_ERR_UNSUPPORTED, "kron_linear_dgrad: N=%d / factor widths (%d,%d,%d) exceed the tile budget", N, d1, d2, d3);
+  MML_REQUIRE(workspace_bytes >= p.part_bytes, MML_ERR_WORKSPACE, "kron_linear_dgrad: workspace too small");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  MML_CUDA(cudaMemsetAsync(workspace, 0, p.part_bytes, st));
+  CUtensorMap tmap;
+  int rc = get_tensor_map_wT(WpT, p.Np32, p.Kp, &tmap);
+  if (rc != MML_OK) return rc;
+  const KronShape s = make_kron_shape(d1, d2, d3);
+  DgArgs a{};
+  a.f1 = f1; a.f2 = f2; a.f3 = f3; a.dy = dy;
+  a.table = reinterpret_cast<const int4*>(table);
+  a.part = static_cast<float*>(workspace);
+  a.B = B; a.d1 = d1; a.d2 = d2; a.d3 = d3; a.dsum = p.dsum; a.N = N; a.Np32 = p.Np32; a.nchunks = p.nchunks;
+  a.ktiles = p.ktiles; a.tiles_per_split = p.tiles_per_split;
+  a.n_scal = p.n_scal; a.stages = p.stages; a.tmem_cols = p.tmem_cols; a.table_in_smem = p.table_in_smem;
+  a.idesc = make_idesc_tf32(kTileM, kDgTileK);
+  a.dr = make_kron_dropout(drop_p, seed, training, s.Kk);
+  const dim3 grid(static_cast<unsigned>((B + kTileM - 1) / kTileM), p.ksplit);
+  if (a.dr.thresh != 0u) {
+    MML_CUDA(cudaFuncSetAttribute(kron_dgrad_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(p.smem)));
+    kron_dgrad_tc_kernel<true><<<grid, kDgThreads, p.smem, st>>>(tmap, a);
+  } else {
+    MML_CUDA(cudaFuncSetAttribute(kron_dgrad_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(p.smem)));
+    kron_dgrad_tc_kernel<false><<<grid, kDgThreads, p.smem, st>>>(tmap, a);
+  }
+  rc = check_launch("kron_dgrad_tc_kernel");
+  if (rc != MML_OK) return rc;
+  const int64_t total = B * p.dsum;
+  int64_t g = (total + 255) / 256;
+  if (g > 148 * 16) g = 148 * 16;
+  kron_dgrad_reduce_kernel<<<static_cast<unsigned>(g), 256, 0, st>>>(a.part, p.ksplit, B, d1, d2, d3, df1, df2, df3);
+  return check_launch("kron_dgrad_reduce_kernel");
+}

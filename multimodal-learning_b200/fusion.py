@@ -54,6 +54,32 @@ class KronLinearState:
         self.path = "auto"          # "auto" | "simt" (tests use "simt" as the exact-fp32 cross-check)
         self._plans = {}            # (B, N) -> (tensor-core path usable, workspace bytes)
         self._wg_plans = {}         # (B, N) -> (tensor-core wgrad usable, workspace bytes)
+        self._dg_plans = {}         # (B, N) -> (tensor-core dgrad usable, workspace bytes)
+        self.packed_t = None        # transposed packed weight (dgrad's B operand)
+        self.packed_t_key = None
+
+    def dgrad_plan(self, B, N):
+        key = (B, N)
+        if key not in self._dg_plans:
+            lib = _cabi.lib()
+            ok = bool(lib.mml_kron_dgrad_supported(B, N, *self.dims))
+            self._dg_plans[key] = (ok, lib.mml_kron_dgrad_workspace_bytes(B, N, *self.dims) if ok else 0)
+        return self._dg_plans[key]
+
+    def ensure_t(self, weight):
+        lib = _cabi.lib()
+        d1, d2, d3 = self.dims
+        dev = weight.device
+        self.ensure_table(dev)
+        key = (weight.data_ptr(), weight._version, tuple(weight.shape))
+        if key != self.packed_t_key:
+            N = weight.shape[0]
+            nfl = lib.mml_kron_packed_t_floats(N, d1, d2, d3)
+            if self.packed_t is None or self.packed_t.numel() != nfl or self.packed_t.device != dev:
+                self.packed_t = torch.empty(nfl, dtype=torch.float32, device=dev)
+            _cabi.check(lib.mml_kron_pack_weight_t(_cabi.dptr(weight.detach()), N, d1, d2, d3, _cabi.dptr(self.table),
+                                                   _cabi.dptr(self.packed_t), _cabi.cur_stream(dev)), "mml_kron_pack_weight_t")
+            self.packed_t_key = key
 
     def wgrad_plan(self, B, N):
         key = (B, N)
@@ -72,6 +98,7 @@ class KronLinearState:
             _cabi.check(lib.mml_kron_chunk_table_host(d1, d2, d3, _cabi.hptr(host)), "mml_kron_chunk_table_host")
             self.table = host.to(device)
             self.packed_key = None
+            self.packed_t_key = None
 
     def plan(self, B, N):
         key = (B, N)
@@ -157,10 +184,23 @@ class _KronLinearFn(torch.autograd.Function):
                                            ctypes_ptr(ws.data_ptr() + off), wg_ws, st)
             _cabi.check(rc, "mml_kron_linear_wgrad")
             simt_dW = None
-        if need_f or simt_dW is not None:
+        dg_ok, dg_ws = state.dgrad_plan(B, N)
+        if need_f and state.path == "auto" and dg_ok:            # factor gradients on the tensor cores
+            state.ensure_t(w)
+            ws = torch.empty(dg_ws, dtype=torch.uint8, device=dev)
+            rc = lib.mml_kron_linear_dgrad(_cabi.dptr(fs[0]), _cabi.dptr(fs[1]), f3p, B, d1, d2, d3, _cabi.dptr(state.table),
+                                           _cabi.dptr(state.packed_t), _cabi.dptr(dy), N, drop_p, seed, training,
+                                           _cabi.dptr(dfs[0]), _cabi.dptr(dfs[1]), _cabi.dptr(dfs[2]) if d3 > 0 else None,
+                                           _cabi.dptr(ws), dg_ws, st)
+            _cabi.check(rc, "mml_kron_linear_dgrad")
+            need_f_simt = False
+        else:
+            need_f_simt = need_f
+        if need_f_simt or simt_dW is not None:
+            sd = dfs if need_f_simt else [None] * len(fs)
             rc = lib.mml_kron_linear_bwd_simt(
                 _cabi.dptr(fs[0]), _cabi.dptr(fs[1]), f3p, B, d1, d2, d3, _cabi.dptr(w), _cabi.dptr(dy), N, drop_p, seed,
-                training, _cabi.dptr(dfs[0]), _cabi.dptr(dfs[1]), _cabi.dptr(dfs[2]) if d3 > 0 else None,
+                training, _cabi.dptr(sd[0]), _cabi.dptr(sd[1]), _cabi.dptr(sd[2]) if d3 > 0 else None,
                 _cabi.dptr(simt_dW), st)
             _cabi.check(rc, "mml_kron_linear_bwd_simt")
         dbias = dy.sum(0) if (has_bias and ctx.needs_input_grad[2]) else None
