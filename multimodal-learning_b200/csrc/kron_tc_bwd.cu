@@ -144,30 +144,29 @@ __global__ void __launch_bounds__(kThreadsTc, 1) kron_wgrad_tc_kernel(const __gr
       }
     (void)my_kstride;
 
-    // staging assignment: X elements (slot, r, e2) for idx = gt + 256*j, j < 16;  scalar (chunk, r) for gt < 128
-    auto stage_block = [&](int blk, int buf) {
+    // Staging of one 32-row batch block, software-pipelined: the global loads of block blk+1 are issued into
+    // registers BEFORE block blk is computed and stored to the other shared buffer AFTER it, so their latency
+    // hides behind the arithmetic.  Only slots that own a distinct vector segment are staged (usually one).
+    // X element (slot, r, e2): r = (gt >> 5) + 8*j, e2 = gt & 31, j < 4;  scalar (chunk, r): threads gt < 128.
+    const int sr = gt >> 5, se = gt & 31;
+    float xr[4][4];                    // [slot][j]
+    float scr = 0.f;
+    auto load_block = [&](int blk) {
       const int64_t b0 = static_cast<int64_t>(blk) * kBlkB;
-      float* X = sm_X + buf * (4 * kBlkB * 32);
-#pragma unroll 4
-      for (int j = 0; j < 16; ++j) {
-        const int idx = gt + 256 * j;
-        const int sl = idx >> 10, r = (idx >> 5) & 31, e2 = idx & 31;
-        // slot sl is "owned" by the first chunk that maps to it
-        float x = 0.f;
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          if (c == sl && slot_of[c] == c && cvalid[c]) {
-            const int64_t b = b0 + r;
-            if (b < a.B && e2 < ce1[c].x) {
-              const int vsrc = ce0[c].z, col = ce0[c].w + e2;
-              if (vsrc == 0) x = 1.0f;                                            // corner chunk: vlen == 1
-              else if (vsrc == 1) x = __ldg(a.f1 + b * a.d1 + col);
-              else if (vsrc == 2) x = __ldg(a.f2 + b * a.d2 + col);
-              else x = __ldg(a.f3 + b * a.d3 + col);
-            }
-          }
+      for (int c = 0; c < 4; ++c) {
+        if (slot_of[c] != c || !cvalid[c]) continue;                  // uniform
+        const int vsrc = ce0[c].z, col = ce0[c].w + se;
+        const bool ein = se < ce1[c].x;
+        const float* src = vsrc == 1 ? a.f1 : (vsrc == 2 ? a.f2 : a.f3);
+        const int d = vsrc == 1 ? a.d1 : (vsrc == 2 ? a.d2 : a.d3);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int64_t b = b0 + sr + 8 * j;
+          float x = 0.f;
+          if (b < a.B && ein) x = (vsrc == 0) ? 1.0f : __ldg(src + b * d + col);
+          xr[c][j] = x;
         }
-        X[idx] = x;
       }
       if (gt < 128) {
         const int c = gt >> 5, r = gt & 31;
@@ -177,17 +176,31 @@ __global__ void __launch_bounds__(kThreadsTc, 1) kron_wgrad_tc_kernel(const __gr
         for (int cc = 0; cc < 4; ++cc)
           if (cc == c && cvalid[cc] && b < a.B) sc = scal_src(a, b, ce0[cc].x) * scal_src(a, b, ce0[cc].y);
         if (kDropout) sc *= a.dr.scale;
-        sm_sc[buf * (4 * kBlkB) + c * kBlkB + r] = sc;
+        scr = sc;
       }
+    };
+    auto store_block = [&](int buf) {
+      float* X = sm_X + buf * (4 * kBlkB * 32);
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        if (slot_of[c] != c || !cvalid[c]) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) X[c * (kBlkB * 32) + (sr + 8 * j) * 32 + se] = xr[c][j];
+      }
+      if (gt < 128) sm_sc[buf * (4 * kBlkB) + gt] = scr;
     };
 
     int s = 0, s_prev = -1;
     uint32_t ph = 0;
-    if (blk_begin < blk_end) stage_block(blk_begin, 0);
+    if (blk_begin < blk_end) {
+      load_block(blk_begin);
+      store_block(0);
+    }
     for (int blk = blk_begin; blk < blk_end; ++blk) {
       const int buf = (blk - blk_begin) & 1;
       asm volatile("bar.sync 1, 256;" ::: "memory");                 // staging of `buf` visible; other buffer free
-      if (blk + 1 < blk_end) stage_block(blk + 1, buf ^ 1);
+      const bool more = blk + 1 < blk_end;
+      if (more) load_block(blk + 1);
       const float* X = sm_X + buf * (4 * kBlkB * 32) + my_slot * (kBlkB * 32);
       const float* S = sm_sc + buf * (4 * kBlkB) + ci * kBlkB;
       const int64_t b0 = static_cast<int64_t>(blk) * kBlkB;
@@ -216,6 +229,7 @@ __global__ void __launch_bounds__(kThreadsTc, 1) kron_wgrad_tc_kernel(const __gr
       tc_st_32x32b_x16(tmem_a + lane_base + s * kBlkB + half * kHalf, r);
       s_prev = s;
       if (++s == a.stages) { s = 0; ph ^= 1; }
+      if (more) store_block(buf ^ 1);
     }
     if (s_prev >= 0) {
       tc_wait_st();

@@ -73,8 +73,14 @@ def main():
             y = kron_linear(st, fsg, W, bias, drop_p=args.dropout, training=training, seed=7)
             G = torch.randn_like(y)
             bwd = lambda: torch.autograd.grad(y, [W] + fsg, G, retain_graph=True)
-            line["bwd_ms"] = round(time_ms(bwd, max(3, args.iters // 5), warmup=2), 3)
+            line["bwd_ms"] = round(time_ms(bwd, max(3, args.iters // 3), warmup=2), 3)
             line["bwd_tflops"] = round(2 * flops / line["bwd_ms"] / 1e9, 1)
+            wg = lambda: torch.autograd.grad(y, [W], G, retain_graph=True)
+            dg = lambda: torch.autograd.grad(y, fsg, G, retain_graph=True)
+            line["wgrad_ms"] = round(time_ms(wg, max(3, args.iters // 3), warmup=2), 3)
+            line["dgrad_ms"] = round(time_ms(dg, max(3, args.iters // 3), warmup=2), 3)
+            line["wgrad_tflops"] = round(flops / line["wgrad_ms"] / 1e9, 1)
+            line["dgrad_tflops"] = round(flops / line["dgrad_ms"] / 1e9, 1)
         print(json.dumps(line), flush=True)
 
 
