@@ -118,89 +118,90 @@ __global__ void __launch_bounds__(kThreadsTc, 1) kron_wgrad_tc_kernel(const __gr
     const int half = gt >> 7;
     const int ci = t >> 5, e = t & 31;
     const uint32_t lane_base = static_cast<uint32_t>((warp & 3) * 32) << 16;
-    // the CTA's chunk descriptors (uniform) and the vector slot of each chunk (chunks sharing a segment share a slot)
-    int4 ce0[4], ce1[4];
-    int slot_of[4];
-    bool cvalid[4];
-#pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      cvalid[c] = (c_first + c) < a.nchunks;
-      ce0[c] = cvalid[c] ? __ldg(a.table + 2 * (c_first + c)) : make_int4(0, 0, 0, 0);
-      ce1[c] = cvalid[c] ? __ldg(a.table + 2 * (c_first + c) + 1) : make_int4(0, 0, 1, 0);
-      slot_of[c] = c;
-#pragma unroll
-      for (int p = c - 1; p >= 0; --p)
-        if (cvalid[c] && cvalid[p] && ce0[p].z == ce0[c].z && ce0[p].w == ce0[c].w) slot_of[c] = slot_of[p];
-    }
-    int my_slot = 0, my_klog = 0, my_kstride = 1;
+    // the CTA's chunk descriptors (uniform) and the vector slot of each chunk (chunks sharing a segment share a slot).
+    // Everything below is indexed with compile-time constants only, so it stays in registers.
+    const int sr = gt >> 5, se = gt & 31;              // staging role: rows sr + 8j, column se
+    bool own[4];                                       // chunk c owns a distinct vector segment (slot c)
+    const float* xsrc[4];                              // per owned slot: this thread's column of the source factor
+    int xd[4];                                         // row pitch of that factor
+    bool xin[4], xone[4];                              // column inside the segment / constant-one segment
+    int sp_[4], sq_[4];                                // scalar source indices of chunk c
+    bool cval[4];
+    int my_slot = 0, my_klog = 0;
     bool my_valid = false;
-#pragma unroll
-    for (int c = 0; c < 4; ++c)
-      if (c == ci) {
-        my_slot = slot_of[c];
-        my_valid = cvalid[c] && e < ce1[c].x;
-        my_klog = ce1[c].y + e * ce1[c].z;
-        my_kstride = ce1[c].z;
-      }
-    (void)my_kstride;
-
-    // Staging of one 32-row batch block, software-pipelined: the global loads of block blk+1 are issued into
-    // registers BEFORE block blk is computed and stored to the other shared buffer AFTER it, so their latency
-    // hides behind the arithmetic.  Only slots that own a distinct vector segment are staged (usually one).
-    // X element (slot, r, e2): r = (gt >> 5) + 8*j, e2 = gt & 31, j < 4;  scalar (chunk, r): threads gt < 128.
-    const int sr = gt >> 5, se = gt & 31;
-    float xr[4][4];                    // [slot][j]
-    float scr = 0.f;
-    auto load_block = [&](int blk) {
-      const int64_t b0 = static_cast<int64_t>(blk) * kBlkB;
+    {
+      int4 ce0[4], ce1[4];
+      int slot_of[4];
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
-        if (slot_of[c] != c || !cvalid[c]) continue;                  // uniform
-        const int vsrc = ce0[c].z, col = ce0[c].w + se;
-        const bool ein = se < ce1[c].x;
-        const float* src = vsrc == 1 ? a.f1 : (vsrc == 2 ? a.f2 : a.f3);
-        const int d = vsrc == 1 ? a.d1 : (vsrc == 2 ? a.d2 : a.d3);
+        cval[c] = (c_first + c) < a.nchunks;
+        ce0[c] = cval[c] ? __ldg(a.table + 2 * (c_first + c)) : make_int4(0, 0, 0, 0);
+        ce1[c] = cval[c] ? __ldg(a.table + 2 * (c_first + c) + 1) : make_int4(0, 0, 1, 0);
+        slot_of[c] = c;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int64_t b = b0 + sr + 8 * j;
-          float x = 0.f;
-          if (b < a.B && ein) x = (vsrc == 0) ? 1.0f : __ldg(src + b * d + col);
-          xr[c][j] = x;
+        for (int p = c - 1; p >= 0; --p)
+          if (cval[c] && cval[p] && ce0[p].z == ce0[c].z && ce0[p].w == ce0[c].w) slot_of[c] = slot_of[p];
+        own[c] = cval[c] && slot_of[c] == c;
+        const int vsrc = ce0[c].z;
+        xd[c] = vsrc == 1 ? a.d1 : (vsrc == 2 ? a.d2 : a.d3);
+        xsrc[c] = (vsrc == 1 ? a.f1 : (vsrc == 2 ? a.f2 : a.f3)) + ce0[c].w + se;
+        xin[c] = se < ce1[c].x;
+        xone[c] = vsrc == 0;
+        sp_[c] = ce0[c].x;
+        sq_[c] = ce0[c].y;
+        if (c == ci) {
+          my_slot = slot_of[c];
+          my_valid = cval[c] && e < ce1[c].x;
+          my_klog = ce1[c].y + e * ce1[c].z;
         }
       }
-      if (gt < 128) {
-        const int c = gt >> 5, r = gt & 31;
-        const int64_t b = b0 + r;
-        float sc = 0.f;
-#pragma unroll
-        for (int cc = 0; cc < 4; ++cc)
-          if (cc == c && cvalid[cc] && b < a.B) sc = scal_src(a, b, ce0[cc].x) * scal_src(a, b, ce0[cc].y);
-        if (kDropout) sc *= a.dr.scale;
-        scr = sc;
-      }
-    };
-    auto store_block = [&](int buf) {
-      float* X = sm_X + buf * (4 * kBlkB * 32);
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        if (slot_of[c] != c || !cvalid[c]) continue;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) X[c * (kBlkB * 32) + (sr + 8 * j) * 32 + se] = xr[c][j];
-      }
-      if (gt < 128) sm_sc[buf * (4 * kBlkB) + gt] = scr;
-    };
+    }
+    // Staging of one 32-row batch block, software-pipelined: the global loads of block blk+1 are issued into
+    // REGISTERS before block blk is computed and stored to the other shared buffer after it, so their latency
+    // hides behind the arithmetic.  Only slots that own a distinct vector segment are staged (usually one).
+    float xr[4][4];                    // [slot][j]
+    float scr = 0.f;
+#define MML_WG_LOAD_BLOCK(BLK)                                                                          \
+    {                                                                                                   \
+      const int64_t lb0 = static_cast<int64_t>(BLK) * kBlkB;                                            \
+      _Pragma("unroll") for (int c = 0; c < 4; ++c) {                                                   \
+        _Pragma("unroll") for (int j = 0; j < 4; ++j) {                                                 \
+          const int64_t lb = lb0 + sr + 8 * j;                                                          \
+          float x = 0.f;                                                                                \
+          if (own[c] && lb < a.B && xin[c]) x = xone[c] ? 1.0f : __ldg(xsrc[c] + lb * xd[c]);           \
+          xr[c][j] = x;                                                                                 \
+        }                                                                                               \
+      }                                                                                                 \
+      if (gt < 128) {                                                                                   \
+        const int64_t lb = lb0 + (gt & 31);                                                             \
+        float sc = 0.f;                                                                                 \
+        _Pragma("unroll") for (int cc = 0; cc < 4; ++cc)                                                \
+          if (cc == (gt >> 5) && cval[cc] && lb < a.B) sc = scal_src(a, lb, sp_[cc]) * scal_src(a, lb, sq_[cc]); \
+        if (kDropout) sc *= a.dr.scale;                                                                 \
+        scr = sc;                                                                                       \
+      }                                                                                                 \
+    }
+#define MML_WG_STORE_BLOCK(BUF)                                                                         \
+    {                                                                                                   \
+      float* Xs = sm_X + (BUF) * (4 * kBlkB * 32);                                                      \
+      _Pragma("unroll") for (int c = 0; c < 4; ++c)                                                     \
+        if (own[c]) {                                                                                   \
+          _Pragma("unroll") for (int j = 0; j < 4; ++j) Xs[c * (kBlkB * 32) + (sr + 8 * j) * 32 + se] = xr[c][j]; \
+        }                                                                                               \
+      if (gt < 128) sm_sc[(BUF) * (4 * kBlkB) + gt] = scr;                                              \
+    }
 
     int s = 0, s_prev = -1;
     uint32_t ph = 0;
     if (blk_begin < blk_end) {
-      load_block(blk_begin);
-      store_block(0);
+      MML_WG_LOAD_BLOCK(blk_begin)
+      MML_WG_STORE_BLOCK(0)
     }
     for (int blk = blk_begin; blk < blk_end; ++blk) {
       const int buf = (blk - blk_begin) & 1;
       asm volatile("bar.sync 1, 256;" ::: "memory");                 // staging of `buf` visible; other buffer free
       const bool more = blk + 1 < blk_end;
-      if (more) load_block(blk + 1);
+      if (more) MML_WG_LOAD_BLOCK(blk + 1)
       const float* X = sm_X + buf * (4 * kBlkB * 32) + my_slot * (kBlkB * 32);
       const float* S = sm_sc + buf * (4 * kBlkB) + ci * kBlkB;
       const int64_t b0 = static_cast<int64_t>(blk) * kBlkB;
@@ -229,7 +230,7 @@ __global__ void __launch_bounds__(kThreadsTc, 1) kron_wgrad_tc_kernel(const __gr
       tc_st_32x32b_x16(tmem_a + lane_base + s * kBlkB + half * kHalf, r);
       s_prev = s;
       if (++s == a.stages) { s = 0; ph ^= 1; }
-      if (more) store_block(buf ^ 1);
+      if (more) MML_WG_STORE_BLOCK(buf ^ 1)
     }
     if (s_prev >= 0) {
       tc_wait_st();
