@@ -34,13 +34,6 @@ struct WgArgs {
   KronDropout dr;
 };
 
-// R[b][idx] with R = [1, f1, f2] (the scalar sources of the chunk table)
-__device__ __forceinline__ float scal_src(const WgArgs& a, int64_t b, int idx) {
-  if (idx == 0) return 1.0f;
-  if (idx <= a.d1) return __ldg(a.f1 + b * a.d1 + (idx - 1));
-  return __ldg(a.f2 + b * a.d2 + (idx - 1 - a.d1));
-}
-
 template <bool kDropout>
 __global__ void __launch_bounds__(kThreadsTc, 1) kron_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_dyT, const WgArgs a) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -118,41 +111,62 @@ __global__ void __launch_bounds__(kThreadsTc, 1) kron_wgrad_tc_kernel(const __gr
     const int half = gt >> 7;
     const int ci = t >> 5, e = t & 31;
     const uint32_t lane_base = static_cast<uint32_t>((warp & 3) * 32) << 16;
-    // the CTA's chunk descriptors (uniform) and the vector slot of each chunk (chunks sharing a segment share a slot).
-    // Everything below is indexed with compile-time constants only, so it stays in registers.
+    // The CTA's chunk descriptors (uniform) and the vector slot of each chunk (chunks sharing a segment share a
+    // slot).  Everything is indexed with compile-time constants and advanced incrementally (pointers += one
+    // block) so the per-stage instruction count stays small and the state lives in registers.
     const int sr = gt >> 5, se = gt & 31;              // staging role: rows sr + 8j, column se
     bool own[4];                                       // chunk c owns a distinct vector segment (slot c)
-    const float* xsrc[4];                              // per owned slot: this thread's column of the source factor
-    int xd[4];                                         // row pitch of that factor
-    bool xin[4], xone[4];                              // column inside the segment / constant-one segment
-    int sp_[4], sq_[4];                                // scalar source indices of chunk c
-    bool cval[4];
+    bool xld[4], xone[4];                              // this thread's column: load it / it is the constant 1
+    const float* xp[4];                                // next staging element (row b0 + sr) of slot c
+    int xrow[4];                                       // floats per batch row of that factor
     int my_slot = 0, my_klog = 0;
     bool my_valid = false;
+    const float* spp = nullptr;                        // scalar role (gt < 128): chunk gt>>5, row gt&31
+    const float* sqp = nullptr;
+    int sprow = 0, sqrow = 0;
+    bool sc_valid = false;
     {
-      int4 ce0[4], ce1[4];
-      int slot_of[4];
+      const int64_t bfirst = static_cast<int64_t>(blk_begin) * kBlkB;
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
-        cval[c] = (c_first + c) < a.nchunks;
-        ce0[c] = cval[c] ? __ldg(a.table + 2 * (c_first + c)) : make_int4(0, 0, 0, 0);
-        ce1[c] = cval[c] ? __ldg(a.table + 2 * (c_first + c) + 1) : make_int4(0, 0, 1, 0);
-        slot_of[c] = c;
+        const bool cv = (c_first + c) < a.nchunks;
+        const int4 q0 = cv ? __ldg(a.table + 2 * (c_first + c)) : make_int4(0, 0, 0, 0);
+        const int4 q1 = cv ? __ldg(a.table + 2 * (c_first + c) + 1) : make_int4(0, 0, 1, 0);
+        bool dup = false;
 #pragma unroll
-        for (int p = c - 1; p >= 0; --p)
-          if (cval[c] && cval[p] && ce0[p].z == ce0[c].z && ce0[p].w == ce0[c].w) slot_of[c] = slot_of[p];
-        own[c] = cval[c] && slot_of[c] == c;
-        const int vsrc = ce0[c].z;
-        xd[c] = vsrc == 1 ? a.d1 : (vsrc == 2 ? a.d2 : a.d3);
-        xsrc[c] = (vsrc == 1 ? a.f1 : (vsrc == 2 ? a.f2 : a.f3)) + ce0[c].w + se;
-        xin[c] = se < ce1[c].x;
-        xone[c] = vsrc == 0;
-        sp_[c] = ce0[c].x;
-        sq_[c] = ce0[c].y;
+        for (int p = 0; p < c; ++p) {
+          const bool pv = (c_first + p) < a.nchunks;
+          const int4 r0 = pv ? __ldg(a.table + 2 * (c_first + p)) : make_int4(0, 0, 0, 0);
+          if (cv && pv && !dup && r0.z == q0.z && r0.w == q0.w) {
+            dup = true;
+            if (c == ci) my_slot = p;                  // first chunk with the same segment owns the slot
+          }
+        }
+        own[c] = cv && !dup;
+        const int vsrc = q0.z;
+        xrow[c] = vsrc == 1 ? a.d1 : (vsrc == 2 ? a.d2 : a.d3);
+        xone[c] = (vsrc == 0) && (se < q1.x);
+        xld[c] = (vsrc != 0) && (se < q1.x);
+        xp[c] = (vsrc == 1 ? a.f1 : (vsrc == 2 ? a.f2 : a.f3));
+        if (vsrc != 0) xp[c] += (bfirst + sr) * xrow[c] + q0.w + se;
         if (c == ci) {
-          my_slot = slot_of[c];
-          my_valid = cval[c] && e < ce1[c].x;
-          my_klog = ce1[c].y + e * ce1[c].z;
+          if (!dup) my_slot = c;
+          my_valid = cv && e < q1.x;
+          my_klog = q1.y + e * q1.z;
+        }
+        if (c == (gt >> 5) && gt < 128) {
+          sc_valid = cv;
+          const int64_t rb = bfirst + (gt & 31);
+          if (q0.x != 0) {
+            const bool in1 = q0.x <= a.d1;
+            sprow = in1 ? a.d1 : a.d2;
+            spp = (in1 ? a.f1 + (q0.x - 1) : a.f2 + (q0.x - 1 - a.d1)) + rb * sprow;
+          }
+          if (q0.y != 0) {
+            const bool in1 = q0.y <= a.d1;
+            sqrow = in1 ? a.d1 : a.d2;
+            sqp = (in1 ? a.f1 + (q0.y - 1) : a.f2 + (q0.y - 1 - a.d1)) + rb * sqrow;
+          }
         }
       }
     }
@@ -160,33 +174,43 @@ __global__ void __launch_bounds__(kThreadsTc, 1) kron_wgrad_tc_kernel(const __gr
     // REGISTERS before block blk is computed and stored to the other shared buffer after it, so their latency
     // hides behind the arithmetic.  Only slots that own a distinct vector segment are staged (usually one).
     float xr[4][4];                    // [slot][j]
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) xr[c][j] = 0.f;
     float scr = 0.f;
 #define MML_WG_LOAD_BLOCK(BLK)                                                                          \
     {                                                                                                   \
-      const int64_t lb0 = static_cast<int64_t>(BLK) * kBlkB;                                            \
+      const int64_t left64 = a.B - static_cast<int64_t>(BLK) * kBlkB;                                   \
+      const int left = left64 > kBlkB ? kBlkB : static_cast<int>(left64);                               \
       _Pragma("unroll") for (int c = 0; c < 4; ++c) {                                                   \
-        _Pragma("unroll") for (int j = 0; j < 4; ++j) {                                                 \
-          const int64_t lb = lb0 + sr + 8 * j;                                                          \
-          float x = 0.f;                                                                                \
-          if (own[c] && lb < a.B && xin[c]) x = xone[c] ? 1.0f : __ldg(xsrc[c] + lb * xd[c]);           \
-          xr[c][j] = x;                                                                                 \
+        if (own[c]) {                                                                                   \
+          _Pragma("unroll") for (int j = 0; j < 4; ++j) {                                               \
+            const bool rv = (sr + 8 * j) < left;                                                        \
+            float x = (xone[c] && rv) ? 1.0f : 0.f;                                                     \
+            if (xld[c] && rv) x = __ldg(xp[c] + j * 8 * xrow[c]);                                       \
+            xr[c][j] = x;                                                                               \
+          }                                                                                             \
+          xp[c] += kBlkB * xrow[c];                                                                     \
         }                                                                                               \
       }                                                                                                 \
       if (gt < 128) {                                                                                   \
-        const int64_t lb = lb0 + (gt & 31);                                                             \
         float sc = 0.f;                                                                                 \
-        _Pragma("unroll") for (int cc = 0; cc < 4; ++cc)                                                \
-          if (cc == (gt >> 5) && cval[cc] && lb < a.B) sc = scal_src(a, lb, sp_[cc]) * scal_src(a, lb, sq_[cc]); \
-        if (kDropout) sc *= a.dr.scale;                                                                 \
+        if (sc_valid && (gt & 31) < left) {                                                             \
+          sc = (spp ? __ldg(spp) : 1.0f) * (sqp ? __ldg(sqp) : 1.0f);                                   \
+          if (kDropout) sc *= a.dr.scale;                                                               \
+        }                                                                                               \
+        if (spp) spp += kBlkB * sprow;                                                                  \
+        if (sqp) sqp += kBlkB * sqrow;                                                                  \
         scr = sc;                                                                                       \
       }                                                                                                 \
     }
 #define MML_WG_STORE_BLOCK(BUF)                                                                         \
     {                                                                                                   \
-      float* Xs = sm_X + (BUF) * (4 * kBlkB * 32);                                                      \
+      float* Xs = sm_X + (BUF) * (4 * kBlkB * 32) + sr * 32 + se;                                       \
       _Pragma("unroll") for (int c = 0; c < 4; ++c)                                                     \
         if (own[c]) {                                                                                   \
-          _Pragma("unroll") for (int j = 0; j < 4; ++j) Xs[c * (kBlkB * 32) + (sr + 8 * j) * 32 + se] = xr[c][j]; \
+          _Pragma("unroll") for (int j = 0; j < 4; ++j) Xs[c * (kBlkB * 32) + j * 8 * 32] = xr[c][j];   \
         }                                                                                               \
       if (gt < 128) sm_sc[(BUF) * (4 * kBlkB) + gt] = scr;                                              \
     }
@@ -206,10 +230,14 @@ __global__ void __launch_bounds__(kThreadsTc, 1) kron_wgrad_tc_kernel(const __gr
       const float* S = sm_sc + buf * (4 * kBlkB) + ci * kBlkB;
       const int64_t b0 = static_cast<int64_t>(blk) * kBlkB;
       uint32_t r[kHalf];
+      float sv[kHalf];
+#pragma unroll
+      for (int u = 0; u < kHalf; u += 4)
+        *reinterpret_cast<float4*>(&sv[u]) = *reinterpret_cast<const float4*>(S + half * kHalf + u);
 #pragma unroll
       for (int u = 0; u < kHalf; ++u) {
         const int bl = half * kHalf + u;
-        float x = my_valid ? S[bl] * X[bl * 32 + e] : 0.f;
+        float x = my_valid ? sv[u] * X[bl * 32 + e] : 0.f;
         if (kDropout) {
           const int64_t cc = (b0 + bl) * a.dr.pairs_per_row + (my_klog >> 1);
           const uint32_t h = kron_hash(static_cast<uint32_t>(cc), static_cast<uint32_t>(static_cast<uint64_t>(cc) >> 32),
