@@ -140,23 +140,40 @@ int mml_shard_route_strided(const int64_t* idx, int64_t B, int64_t cols, int32_t
 /* K4 over PEER-resident index slots: the owner's gather kernel reads, for global anchor
  * a = s*B_local + bl and slot c, the ids  peer_ids_host[s][(bl*route_chunks + c)*route_stride ..]
  * (a pointer into rank s's ids_out, already offset to THIS owner's block, valid in this process
- * through CUDA peer mapping) of length peer_counts[(s*B_local + bl)*route_chunks + c].  The
+ * through CUDA peer mapping) of length peer_counts_host[s][bl*route_chunks + c] (rank s's counts
+ * block for this owner: a local copy after an all_to_all, or the peer-mapped original).  The
  * all_to_all of routed indices is thereby fused into the gather kernel as NVLink loads (4 bytes of
- * index per 1 KB of local row traffic).  `peer_ids_host` is a HOST array of `world` device pointers;
- * `peer_counts` int32[world*B_local*route_chunks] on this device; sums as in the non-peer calls. */
+ * index per 1 KB of local row traffic).  `peer_ids_host` / `peer_counts_host` are HOST arrays of
+ * `world` device pointers; sums as in the non-peer calls.                                       */
 size_t mml_crd_peer_workspace_bytes(int64_t B_global, int32_t route_chunks, int32_t D);
 int mml_crd_fused_loss_grad_peer(
     const float* bank1, const float* bank2, int64_t n_rows, int32_t D, const float* v1, const float* v2,
-    const int32_t* const* peer_ids_host, const int32_t* peer_counts, int32_t world, int64_t B_local,
+    const int32_t* const* peer_ids_host, const int32_t* const* peer_counts_host, int32_t world, int64_t B_local,
     int32_t route_chunks, int32_t route_stride, const uint8_t* pos_flag,
     float T, const float* Z, int64_t n_data, int64_t nce_k, int64_t batch_norm,
     float* sums, float* grad_v1, float* grad_v2,
     void* workspace, size_t workspace_bytes, void* stream);
 int mml_crd_scores_peer(
     const float* bank1, const float* bank2, int64_t n_rows, int32_t D, const float* v1, const float* v2,
-    const int32_t* const* peer_ids_host, const int32_t* peer_counts, int32_t world, int64_t B_local,
+    const int32_t* const* peer_ids_host, const int32_t* const* peer_counts_host, int32_t world, int64_t B_local,
     int32_t route_chunks, int32_t route_stride, float T, float* sums,
     void* workspace, size_t workspace_bytes, void* stream);
+
+/* Small collectives over peer-mapped (symmetric) memory, for the sharded step's KB..MB messages
+ * where NCCL's launch + protocol latency dominates.  `peer_base_host`: HOST array of `world` base
+ * pointers of the same symmetric allocation on every rank (index = rank).  The caller separates
+ * the calls with cross-rank barriers (torch symmetric-memory `barrier()`).
+ *   mml_symm_push:        copy up to 4 local segments (src[i], bytes[i], 16-byte multiples) to byte
+ *                         offset dst_off[i] of EVERY rank's allocation (an all_gather by NVLink stores).
+ *   mml_symm_pull_reduce: out[r, :] = sum over ranks p (in rank order: deterministic) of the float
+ *                         rows [row_begin + r] of the two [rows_total, D] planes at byte offset
+ *                         `part_off` of rank p's allocation (a reduce_scatter by NVLink loads), for
+ *                         r < rows; tail[k] = sum_p of the nt floats at byte offset `tail_off`.     */
+int mml_symm_push(void* const* peer_base_host, int32_t world, const void* const* src, const int64_t* dst_off,
+                  const int64_t* bytes, int32_t nseg, void* stream);
+int mml_symm_pull_reduce(void* const* peer_base_host, int32_t world, int64_t part_off, int64_t rows_total,
+                         int64_t row_begin, int64_t rows, int32_t D, float* out1, float* out2,
+                         int64_t tail_off, int32_t nt, float* tail_out, void* stream);
 
 /* ------------------------------------------------------------------------- *
  * AliasMethod (CRD_criterion.py:84-141)

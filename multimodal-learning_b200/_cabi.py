@@ -36,6 +36,9 @@ _SIGNATURES = {
         c_float, _P, c_int64, c_int64, c_int64, _P, _P, _P, _P, c_size_t, _P]),
     "mml_crd_scores_peer": (ctypes.c_int, [
         _P, _P, c_int64, c_int32, _P, _P, _P, _P, c_int32, c_int64, c_int32, c_int32, c_float, _P, _P, c_size_t, _P]),
+    "mml_symm_push": (ctypes.c_int, [_P, c_int32, _P, _P, _P, c_int32, _P]),
+    "mml_symm_pull_reduce": (ctypes.c_int, [_P, c_int32, c_int64, c_int64, c_int64, c_int64, c_int32, _P, _P,
+                                            c_int64, c_int32, _P, _P]),
     "mml_shard_count": (ctypes.c_int, [_P, c_int64, c_int64, c_int32, c_int64, c_int32, _P, _P]),
     "mml_shard_scatter": (ctypes.c_int, [_P, c_int64, c_int64, c_int32, c_int64, c_int32, _P, _P, _P]),
     "mml_crd_memory_update": (ctypes.c_int, [

@@ -52,11 +52,11 @@ struct GatherArgs {
   float nce_c;              // fp32(m*Pn + eps)     CRD_criterion.py:208,212
   float nce_kp;             // fp32(m*Pn)           CRD_criterion.py:212
   // peer mode (row-sharded bank, indices pulled over NVLink): anchor b = (source rank s, local anchor bl);
-  // CTA (chunk c, b) reads peer_ids[s][(bl*chunks + c)*peer_stride ..] of length peer_counts[(s*B_local+bl)*chunks+c]
+  // CTA (chunk c, b) reads peer_ids[s][(bl*chunks + c)*peer_stride ..] of length peer_cnt[s][bl*chunks + c]
   int32_t peer_world;       // 0 = off
   int32_t peer_B_local;
   int32_t peer_stride;
-  const int32_t* peer_counts;
+  const int32_t* peer_cnt[32];   // per source rank: counts of ITS slots destined to this owner (local copy or peer-mapped)
   const int32_t* peer_ids[32];
 };
 
@@ -78,7 +78,7 @@ __device__ __forceinline__ Segment cta_segment(const GatherArgs& a, int b, int c
     g.idx32 = a.peer_ids[s];
     g.begin = (static_cast<int64_t>(bl) * a.chunks + chunk) * a.peer_stride;
     g.c0 = 0;
-    g.c1 = a.peer_counts[(static_cast<int64_t>(s) * a.peer_B_local + bl) * a.chunks + chunk];
+    g.c1 = a.peer_cnt[s][static_cast<int64_t>(bl) * a.chunks + chunk];
     g.has_pos = (chunk == 0) && (a.pos_flag == nullptr || a.pos_flag[b] != 0);
     g.active = true;                         // empty sub-segments still publish zero partials
     return g;
@@ -630,9 +630,9 @@ namespace mml {
 namespace {
 
 int peer_setup(GatherArgs& a, Plan& p, const float* bank1, const float* bank2, int64_t n_rows, int32_t D,
-               const int32_t* const* peer_ids_host, const int32_t* peer_counts, int32_t world, int64_t B_local,
+               const int32_t* const* peer_ids_host, const int32_t* const* peer_counts_host, int32_t world, int64_t B_local,
                int32_t route_chunks, int32_t route_stride, void* ws, size_t ws_size) {
-  MML_REQUIRE(bank1 && bank2 && peer_ids_host && peer_counts && ws, MML_ERR_INVALID_ARG, "crd_peer: null pointer argument");
+  MML_REQUIRE(bank1 && bank2 && peer_ids_host && peer_counts_host && ws, MML_ERR_INVALID_ARG, "crd_peer: null pointer argument");
   MML_REQUIRE(world >= 1 && world <= 32 && B_local >= 1 && route_chunks >= 1 && route_stride >= 32, MML_ERR_INVALID_ARG,
               "crd_peer: bad world / B_local / route layout");
   MML_REQUIRE(D >= 1 && D <= 2048, MML_ERR_UNSUPPORTED, "crd_peer: feature dim %d outside [1, 2048]", D);
@@ -646,10 +646,10 @@ int peer_setup(GatherArgs& a, Plan& p, const float* bank1, const float* bank2, i
   a.cols = static_cast<int64_t>(route_chunks) * route_stride;     // finishers: every chunk publishes a partial
   a.D = D; a.chunk_cols = route_stride; a.chunks = route_chunks;
   a.peer_world = world; a.peer_B_local = static_cast<int32_t>(B_local); a.peer_stride = route_stride;
-  a.peer_counts = peer_counts;
   for (int i = 0; i < world; ++i) {
-    MML_REQUIRE(peer_ids_host[i] != nullptr, MML_ERR_INVALID_ARG, "crd_peer: null peer buffer %d", i);
+    MML_REQUIRE(peer_ids_host[i] != nullptr && peer_counts_host[i] != nullptr, MML_ERR_INVALID_ARG, "crd_peer: null peer buffer %d", i);
     a.peer_ids[i] = peer_ids_host[i];
+    a.peer_cnt[i] = peer_counts_host[i];
   }
   return MML_OK;
 }
@@ -664,13 +664,13 @@ extern "C" size_t mml_crd_peer_workspace_bytes(int64_t B_global, int32_t route_c
 
 extern "C" int mml_crd_fused_loss_grad_peer(
     const float* bank1, const float* bank2, int64_t n_rows, int32_t D, const float* v1, const float* v2,
-    const int32_t* const* peer_ids_host, const int32_t* peer_counts, int32_t world, int64_t B_local, int32_t route_chunks,
+    const int32_t* const* peer_ids_host, const int32_t* const* peer_counts_host, int32_t world, int64_t B_local, int32_t route_chunks,
     int32_t route_stride, const uint8_t* pos_flag, float T, const float* Z, int64_t n_data, int64_t nce_k,
     int64_t batch_norm, float* sums, float* grad_v1, float* grad_v2, void* workspace, size_t workspace_bytes,
     void* stream) {
   GatherArgs a{};
   Plan p{};
-  int rc = peer_setup(a, p, bank1, bank2, n_rows, D, peer_ids_host, peer_counts, world, B_local, route_chunks, route_stride,
+  int rc = peer_setup(a, p, bank1, bank2, n_rows, D, peer_ids_host, peer_counts_host, world, B_local, route_chunks, route_stride,
                       workspace, workspace_bytes);
   if (rc != MML_OK) return rc;
   MML_REQUIRE(v1 && v2 && Z && grad_v1 && grad_v2, MML_ERR_INVALID_ARG, "crd_fused_peer: null pointer argument");
@@ -698,12 +698,13 @@ extern "C" int mml_crd_fused_loss_grad_peer(
 }
 
 extern "C" int mml_crd_scores_peer(const float* bank1, const float* bank2, int64_t n_rows, int32_t D, const float* v1,
-                                   const float* v2, const int32_t* const* peer_ids_host, const int32_t* peer_counts,
-                                   int32_t world, int64_t B_local, int32_t route_chunks, int32_t route_stride, float T,
+                                   const float* v2, const int32_t* const* peer_ids_host,
+                                   const int32_t* const* peer_counts_host, int32_t world, int64_t B_local,
+                                   int32_t route_chunks, int32_t route_stride, float T,
                                    float* sums, void* workspace, size_t workspace_bytes, void* stream) {
   GatherArgs a{};
   Plan p{};
-  int rc = peer_setup(a, p, bank1, bank2, n_rows, D, peer_ids_host, peer_counts, world, B_local, route_chunks, route_stride,
+  int rc = peer_setup(a, p, bank1, bank2, n_rows, D, peer_ids_host, peer_counts_host, world, B_local, route_chunks, route_stride,
                       workspace, workspace_bytes);
   if (rc != MML_OK) return rc;
   MML_REQUIRE(v1 && v2 && sums && T > 0.f, MML_ERR_INVALID_ARG, "crd_scores_peer: bad arguments");

@@ -21,7 +21,8 @@ never cross NVLink: INDICES and per-anchor partial results do. 
                              peer mapping is unavailable, and on CPU/gloo in the tests.
   3. local kernel    every rank scores ALL global anchors against the rows IT owns:
                      partial log-term sums, partial dL/dv.
-  4. all_reduce      [sums | dL/dv1 | dL/dv2] -> loss (replicated) and full gradients.
+  4. reduce          "peer": the anchors' home ranks pull-reduce their rows of every rank's partial buffer
+                     (`mml_symm_pull_reduce`); "alltoall": one NCCL all_reduce of [sums | dL/dv1 | dL/dv2].
   5. owner update    each rank updates the rows of idx it owns (`mml_crd_memory_update` with
                      row_begin/row_end); gather-before-update ordering is stream order on each rank.
 
@@ -98,57 +99,98 @@ class CudaBackend:
         ws = torch.empty(nws, dtype=torch.uint8, device=dev)
         sums = torch.empty(4, dtype=torch.float32, device=dev)
         _cabi.check(lib.mml_crd_scores_peer(_cabi.dptr(bank1), _cabi.dptr(bank2), bank1.shape[0], D, _cabi.dptr(v1),
-                                            _cabi.dptr(v2), px.ptr_array, _cabi.dptr(px.recv_counts), px.world, px.B_local,
+                                            _cabi.dptr(v2), px.ids_ptrs, px.cnt_ptrs, px.world, px.B_local,
                                             px.chunks, px.chunk, float(T), _cabi.dptr(sums), _cabi.dptr(ws), nws,
                                             _cabi.cur_stream(dev)), "mml_crd_scores_peer")
         return sums
 
-    def fused_peer(self, bank1, bank2, v1, v2, px, pos_flag, T, Z, n_data, nce_k, batch):
+    def fused_peer(self, bank1, bank2, v1, v2, px, pos_flag, T, Z, n_data, nce_k, batch, g1, g2, sums):
+        """Partial sums / gradients over this shard's rows, written into the caller's (symmetric) buffers."""
         lib = _cabi.lib()
         Bg, D = v1.shape
         dev = v1.device
         nws = lib.mml_crd_peer_workspace_bytes(Bg, px.chunks, D)
         ws = torch.empty(nws, dtype=torch.uint8, device=dev)
-        sums = torch.empty(4, dtype=torch.float32, device=dev)
-        g1 = torch.empty_like(v1)
-        g2 = torch.empty_like(v2)
         if _crd.KERNEL_TIMER is not None:
             _crd.KERNEL_TIMER.start("crd_fused_loss_grad", dev)
         rc = lib.mml_crd_fused_loss_grad_peer(
-            _cabi.dptr(bank1), _cabi.dptr(bank2), bank1.shape[0], D, _cabi.dptr(v1), _cabi.dptr(v2), px.ptr_array,
-            _cabi.dptr(px.recv_counts), px.world, px.B_local, px.chunks, px.chunk, _cabi.dptr(pos_flag), float(T),
+            _cabi.dptr(bank1), _cabi.dptr(bank2), bank1.shape[0], D, _cabi.dptr(v1), _cabi.dptr(v2), px.ids_ptrs,
+            px.cnt_ptrs, px.world, px.B_local, px.chunks, px.chunk, _cabi.dptr(pos_flag), float(T),
             _cabi.dptr(Z), int(n_data), int(nce_k), int(batch), _cabi.dptr(sums), _cabi.dptr(g1), _cabi.dptr(g2),
             _cabi.dptr(ws), nws, _cabi.cur_stream(dev))
         if _crd.KERNEL_TIMER is not None:
             _crd.KERNEL_TIMER.stop("crd_fused_loss_grad", dev)
         _cabi.check(rc, "mml_crd_fused_loss_grad_peer")
-        return sums, g1, g2
 
 
 class PeerExchange:
-    """Symmetric-memory index slots of one (B_local, cols) geometry: every rank routes into its own
-    buffer; owners read their block of every peer's buffer through CUDA peer mappings."""
+    """One symmetric-memory arena per (B_local, cols, D) geometry.  Every rank allocates the same layout; peers'
+    arenas are reachable through CUDA peer mappings (`buffer_ptrs`).  Regions:
+      ids  int32 [world][B_l][chunks][chunk]   routed local row ids, block o is read by owner o
+      cnt  int32 [world][B_l][chunks]          entries used in each slot
+      V    float [2][2][B_g][D]                all-gathered embeddings v1|v2, double-buffered by step parity
+      YP   int64 [2][2][B_g]                   all-gathered anchor ids | positive rows, double-buffered
+      P    float [2][B_g][D] + tail[16]        this rank's partial dL/dv1|dL/dv2 and its 4 partial sums"""
 
-    def __init__(self, mem, B_local, cols, device):
+    def __init__(self, mem, B_local, cols, D, device):
         import ctypes
 
         import torch.distributed._symmetric_memory as symm
-        self.world, self.B_local = mem.world, B_local
+        self.world, self.rank, self.B_local, self.D = mem.world, mem.rank, B_local, D
+        self.Bg = Bg = self.world * B_local
         self.chunk = min(2048, (cols + 31) // 32 * 32)
         self.chunks = (cols + self.chunk - 1) // self.chunk
-        block = B_local * self.chunks * self.chunk                     # int32 elements per owner block
+        al = lambda n: (n + 255) // 256 * 256
+        block = B_local * self.chunks * self.chunk * 4
+        cblock = B_local * self.chunks * 4
+        self.off_ids = 0
+        self.off_cnt = al(self.off_ids + self.world * block)
+        self.off_V = al(self.off_cnt + self.world * cblock)
+        self.off_YP = al(self.off_V + 2 * 2 * Bg * D * 4)
+        self.off_P = al(self.off_YP + 2 * 2 * Bg * 8)
+        self.off_tail = self.off_P + 2 * Bg * D * 4
+        total = al(self.off_tail + 64)
         group = mem.group if mem.group is not None else dist.group.WORLD
         if hasattr(symm, "enable_symm_mem_for_group"):
             try:
                 symm.enable_symm_mem_for_group(group.group_name)
             except Exception:
                 pass
-        self.ids = symm.empty(self.world * block, dtype=torch.int32, device=device)
-        self.handle = symm.rendezvous(self.ids, group)
-        ptrs = [int(p) for p in self.handle.buffer_ptrs]
-        self.ptr_array = (ctypes.c_void_p * self.world)(*[p + mem.rank * block * 4 for p in ptrs])
-        self.counts = torch.empty(self.world, B_local, self.chunks, dtype=torch.int32, device=device)
-        self.recv_counts = torch.empty_like(self.counts)
+        self.raw = symm.empty(total, dtype=torch.uint8, device=device)
+        self.raw.zero_()
+        self.handle = symm.rendezvous(self.raw, group)
+        bases = [int(p) for p in self.handle.buffer_ptrs]
+        P = ctypes.c_void_p
+        self.base_ptrs = (P * self.world)(*bases)
+        self.ids_ptrs = (P * self.world)(*[b + self.off_ids + self.rank * block for b in bases])
+        self.cnt_ptrs = (P * self.world)(*[b + self.off_cnt + self.rank * cblock for b in bases])
+        view = lambda off, nbytes, dt, shape: self.raw[off:off + nbytes].view(dt).view(shape)
+        self.ids = view(self.off_ids, self.world * block, torch.int32, (-1,))
+        self.counts = view(self.off_cnt, self.world * cblock, torch.int32, (self.world, B_local, self.chunks))
+        self.V = view(self.off_V, 2 * 2 * Bg * D * 4, torch.float32, (2, 2, Bg, D))
+        self.YP = view(self.off_YP, 2 * 2 * Bg * 8, torch.int64, (2, 2, Bg))
+        self.P = view(self.off_P, 2 * Bg * D * 4, torch.float32, (2, Bg, D))
+        self.tail = view(self.off_tail, 16, torch.float32, (4,))
+        self.step = 0
+        self._c = ctypes
+
+    def push(self, v1, v2, idx, pos, buf):
+        """all_gather by NVLink stores: my slices land in every rank's V / YP buffers of parity `buf`."""
+        c, Bl, Bg, D, r = self._c, self.B_local, self.Bg, self.D, self.rank
+        vb = self.off_V + buf * (2 * Bg * D * 4)
+        yb = self.off_YP + buf * (2 * Bg * 8)
+        srcs = (c.c_void_p * 4)(v1.data_ptr(), v2.data_ptr(), idx.data_ptr(), pos.data_ptr())
+        offs = (c.c_int64 * 4)(vb + r * Bl * D * 4, vb + (Bg + r * Bl) * D * 4, yb + r * Bl * 8, yb + (Bg + r * Bl) * 8)
+        nbytes = (c.c_int64 * 4)(Bl * D * 4, Bl * D * 4, Bl * 8, Bl * 8)
+        _cabi.check(_cabi.lib().mml_symm_push(self.base_ptrs, self.world, srcs, offs, nbytes, 4,
+                                              _cabi.cur_stream(v1.device)), "mml_symm_push")
+
+    def pull_reduce(self, g1, g2, tail):
+        """reduce_scatter by NVLink loads: my anchors' rows summed over every rank's partial buffer."""
+        _cabi.check(_cabi.lib().mml_symm_pull_reduce(
+            self.base_ptrs, self.world, self.off_P, self.Bg, self.rank * self.B_local, self.B_local, self.D,
+            _cabi.dptr(g1), _cabi.dptr(g2), self.off_tail, 4, _cabi.dptr(tail), _cabi.cur_stream(g1.device)),
+            "mml_symm_pull_reduce")
 
 
 class _SumGradAcrossRanks(torch.autograd.Function):
@@ -195,6 +237,22 @@ class _ShardedFusedFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, V1, V2, mem, Y, routed, n_data):
         loss, g1, g2 = mem._sharded_step(V1.detach().contiguous(), V2.detach().contiguous(), Y, routed, n_data)
+        ctx.save_for_backward(g1, g2)
+        return loss
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, grad_loss):
+        g1, g2 = ctx.saved_tensors
+        return grad_loss * g1, grad_loss * g2, None, None, None, None
+
+
+class _ShardedPeerFn(torch.autograd.Function):
+    """Sharded step with every exchange done over peer-mapped memory (see module docstring, transport "peer")."""
+
+    @staticmethod
+    def forward(ctx, v1, v2, mem, idx, cidx, n_data):
+        loss, g1, g2 = mem._peer_step(v1.detach().contiguous(), v2.detach().contiguous(), idx, cidx, n_data)
         ctx.save_for_backward(g1, g2)
         return loss
 
@@ -281,20 +339,52 @@ class ShardedContrastMemory(nn.Module):
             host, ev = sizes, None
         return ids, recv_counts, host, ev
 
-    def exchange_peer(self, cidx_local):
-        """Peer transport: route into this rank's symmetric buffer and swap the per-slot counts.  No host sync.
-        The fixed-size all_to_all of counts completes on a rank only after every peer's routing kernel has
-        finished (stream order on the sender), so it is also the barrier that makes the slots readable."""
-        cols = self._K + 1
-        if cidx_local.dim() != 2 or cidx_local.shape[1] != cols:
-            raise RuntimeError(f"contrast_idx must be [B, nce_k+1 = {cols}], got {tuple(cidx_local.shape)}")   # :42
-        key = (cidx_local.shape[0], cols, cidx_local.device)
+    def peer_arena(self, B_local, cols, D, device):
+        key = (B_local, cols, D, device)
         px = self._peer.get(key)
         if px is None:
-            px = self._peer[key] = PeerExchange(self, cidx_local.shape[0], cols, cidx_local.device)
-        self.backend.route_strided(cidx_local, self.rows_per, self.world, px.chunk, px.counts, px.ids)
-        dist.all_to_all_single(px.recv_counts, px.counts, group=self.group)
+            px = self._peer[key] = PeerExchange(self, B_local, cols, D, device)
         return px
+
+    def _peer_step(self, v1, v2, idx, cidx, n_data):
+        """Local embeddings in, loss (global batch) + local dL/dv out.  Exchanges: routed ids / counts are PULLED by
+        the owners inside K4; embeddings and anchor ids are PUSHED into every rank's buffers; partial gradients are
+        PULL-reduced by the anchors' home ranks.  Two symmetric-memory barriers per step, no NCCL, no host sync."""
+        be = self.backend
+        cols = self._K + 1
+        if cidx.dim() != 2 or cidx.shape[1] != cols:
+            raise RuntimeError(f"contrast_idx must be [B, nce_k+1 = {cols}], got {tuple(cidx.shape)}")   # :42
+        Bl, D = v1.shape
+        px = self.peer_arena(Bl, cols, D, v1.device)
+        buf = px.step & 1
+        px.step += 1
+        be.route_strided(cidx, self.rows_per, self.world, px.chunk, px.counts, px.ids)
+        px.push(v1, v2, idx.contiguous(), cidx[:, 0].contiguous(), buf)
+        px.handle.barrier(channel=0)                  # everyone's slots, counts and slices are in place
+        V1, V2, Y, pos_rows = px.V[buf, 0], px.V[buf, 1], px.YP[buf, 0], px.YP[buf, 1]
+        pos_flag = ((pos_rows >= self.row_begin) & (pos_rows < self.row_end)).to(torch.uint8)
+        Bg = px.Bg
+        if not self._z_ready:                                                       # CRD_criterion.py:52-59
+            sums = be.stats_peer(self.memory_v1, self.memory_v2, V1, V2, px, self._T)
+            dist.all_reduce(sums, group=self.group)
+            scale = float(self.nLem) / (float(Bg) * cols)
+            z = self.params[2:4]
+            self.params[2:4] = torch.where(z < 0, sums[2:4] * scale, z)
+            if self.rank == 0:
+                print("normalization constant Z_v1 is set to {:.1f}".format(self.params[2].item()))
+                print("normalization constant Z_v2 is set to {:.1f}".format(self.params[3].item()))
+            self._z_ready = True
+        be.fused_peer(self.memory_v1, self.memory_v2, V1, V2, px, pos_flag, self._T, self.params[2:4], n_data,
+                      self._K, Bg, px.P[0], px.P[1], px.tail)
+        px.handle.barrier(channel=1)                  # every rank's partials are complete
+        g1 = torch.empty(Bl, D, dtype=torch.float32, device=v1.device)
+        g2 = torch.empty(Bl, D, dtype=torch.float32, device=v1.device)
+        tail = torch.empty(4, dtype=torch.float32, device=v1.device)
+        px.pull_reduce(g1, g2, tail)
+        loss = (-(tail[0] + tail[1]) / Bg).reshape(1)
+        with torch.no_grad():                                                       # :66-79, owner applies
+            be.update(self.memory_v1, self.memory_v2, V1, V2, Y, self._momentum, self.row_begin, self.row_end)
+        return loss, g1, g2
 
     def exchange_finish(self, handle):
         """-> (ids int32 [nnz], seg_ptr int64 [B_global+1]): every rank's requests for MY rows, global anchor order."""
@@ -313,14 +403,10 @@ class ShardedContrastMemory(nn.Module):
         be, group = self.backend, self.group
         Bg, D = V1.shape
         cols = self._K + 1
-        ids, seg_ptr, pos_rows = routed             # ids is a PeerExchange in peer transport (seg_ptr None)
-        peer = isinstance(ids, PeerExchange)
+        ids, seg_ptr, pos_rows = routed
         pos_flag = ((pos_rows >= self.row_begin) & (pos_rows < self.row_end)).to(torch.uint8)
         if not self._z_ready:                                                       # CRD_criterion.py:52-59
-            if peer:
-                sums = be.stats_peer(self.memory_v1, self.memory_v2, V1, V2, ids, self._T)
-            else:
-                sums = be.stats(self.memory_v1, self.memory_v2, V1, V2, ids, seg_ptr, self._T, cols).clone()
+            sums = be.stats(self.memory_v1, self.memory_v2, V1, V2, ids, seg_ptr, self._T, cols).clone()
             dist.all_reduce(sums, group=group)
             scale = float(self.nLem) / (float(Bg) * cols)
             z = self.params[2:4]
@@ -330,12 +416,8 @@ class ShardedContrastMemory(nn.Module):
                 print("normalization constant Z_v1 is set to {:.1f}".format(self.params[2].item()))
                 print("normalization constant Z_v2 is set to {:.1f}".format(self.params[3].item()))
             self._z_ready = True
-        if peer:
-            sums, g1, g2 = be.fused_peer(self.memory_v1, self.memory_v2, V1, V2, ids, pos_flag, self._T,
-                                         self.params[2:4], n_data, self._K, Bg)
-        else:
-            sums, g1, g2 = be.fused(self.memory_v1, self.memory_v2, V1, V2, ids, seg_ptr, pos_flag, self._T,
-                                    self.params[2:4], n_data, self._K, Bg)
+        sums, g1, g2 = be.fused(self.memory_v1, self.memory_v2, V1, V2, ids, seg_ptr, pos_flag, self._T,
+                                self.params[2:4], n_data, self._K, Bg)
         packed = torch.cat((sums.reshape(-1)[:2], g1.reshape(-1), g2.reshape(-1)))
         dist.all_reduce(packed, group=group)
         loss = (-(packed[0] + packed[1]) / Bg).reshape(1)
@@ -400,21 +482,22 @@ class ShardedCRDLoss(nn.Module):
             contrast_idx = mem.multinomial.draw(B * (mem.K + 1), y=idx, cols=mem.K + 1).view(B, -1)
         contrast_idx = contrast_idx.contiguous()
         transport = self._pick_transport(f_s.device)
+        if transport == "peer" and idx.shape[0] % 2:
+            transport = "alltoall"                  # 16-byte push granularity needs an even local batch
         if transport == "peer":
+            v1, v2 = self._heads(f_s, f_t)
             try:
-                routed_ids, seg_ptr = mem.exchange_peer(contrast_idx), None
+                return _ShardedPeerFn.apply(v1, v2, mem, idx, contrast_idx, self.criterion_s.n_data)
             except Exception as e:                  # no peer mapping on this system: fall back, loudly, once
                 if mem._peer:
                     raise
                 print(f"[mml_b200] symmetric-memory peer transport unavailable ({type(e).__name__}: {e}); using all_to_all")
-                self.transport = transport = "alltoall"
-        if transport == "alltoall":
-            handle = mem.exchange_begin(contrast_idx)                               # routing kernels + size exchange
+                self.transport = "alltoall"
+        handle = mem.exchange_begin(contrast_idx)                                   # routing kernels + size exchange
         v1, v2 = self._heads(f_s, f_t)                                              # local anchors
         D = v1.shape[1]
         V = _AllGatherRows.apply(torch.cat((v1, v2), 1), g)                         # [B_global, 2D]
         YP = _all_gather(torch.stack((idx, contrast_idx[:, 0]), 1), g)              # anchors' ids | positives' rows
-        if transport == "alltoall":
-            routed_ids, seg_ptr = mem.exchange_finish(handle)                       # host sync lands here
+        routed_ids, seg_ptr = mem.exchange_finish(handle)                           # host sync lands here
         routed = (routed_ids, seg_ptr, YP[:, 1].contiguous())
         return mem.fused_nce_loss(V[:, :D], V[:, D:], YP[:, 0].contiguous(), routed, self.criterion_s.n_data)
