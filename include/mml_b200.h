@@ -118,6 +118,13 @@ int mml_crd_memory_update(
     const float* v1, const float* v2, const int64_t* y, int64_t B,
     float momentum, int64_t row_begin, int64_t row_end, void* stream);
 
+/* Normalize(2) of the Embed heads (CRD_criterion.py:242-245): y = x / ||x||_2 per row (no epsilon, as the
+ * reference), norm[b] kept for the backward  gx = (gy - y * <gy, y>) / norm.  One launch each instead of the
+ * reference's pow/sum/pow/div chain and its ~8-kernel autograd.                                          */
+int mml_l2norm_fwd(const float* x, int64_t B, int32_t D, float* y, float* norm, void* stream);
+int mml_l2norm_bwd(const float* gy, const float* y, const float* norm, int64_t B, int32_t D, float* gx,
+                   void* stream);
+
 /* Index routing for the row-sharded bank (rank o owns rows [o*rows_per_rank, (o+1)*rows_per_rank)):
  * a stable counting sort of idx[B, cols] by owner, kept in (anchor, column) order inside each owner.
  * Columns are processed in chunks of `chunk_cols` (multiple of 32), chunks = ceil(cols/chunk_cols):

@@ -419,13 +419,41 @@ class Embed(nn.Module):
         return self.l2norm(x)
 
 
+class _L2NormFn(torch.autograd.Function):
+    """Row-wise x / ||x||_2 as one kernel forward and one backward (`mml_l2norm_fwd/bwd`)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        x = x.contiguous()
+        B, D = x.shape
+        y = torch.empty_like(x)
+        nrm = torch.empty(B, dtype=torch.float32, device=x.device)
+        _cabi.check(_cabi.lib().mml_l2norm_fwd(_cabi.dptr(x), B, D, _cabi.dptr(y), _cabi.dptr(nrm), _cabi.cur_stream(x.device)),
+                    "mml_l2norm_fwd")
+        ctx.save_for_backward(y, nrm)
+        return y
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, gy):
+        y, nrm = ctx.saved_tensors
+        gy = gy.contiguous()
+        gx = torch.empty_like(gy)
+        _cabi.check(_cabi.lib().mml_l2norm_bwd(_cabi.dptr(gy), _cabi.dptr(y), _cabi.dptr(nrm), y.shape[0], y.shape[1],
+                                               _cabi.dptr(gx), _cabi.cur_stream(gy.device)), "mml_l2norm_bwd")
+        return gx
+
+
 class Normalize(nn.Module):
-    """normalization layer (no epsilon, as the reference)"""
+    """normalization layer (no epsilon, as the reference).  power=2 on a CUDA fp32 matrix runs as one fused kernel
+    (forward) / one (backward); any other use keeps the reference's op chain (host-side PyTorch)."""
 
     def __init__(self, power=2):
         super(Normalize, self).__init__()
         self.power = power
 
     def forward(self, x):
+        if self.power == 2 and x.is_cuda and x.dtype == torch.float32 and x.dim() == 2:
+            return _L2NormFn.apply(x)
         norm = x.pow(self.power).sum(1, keepdim=True).pow(1. / self.power)
         return x.div(norm)

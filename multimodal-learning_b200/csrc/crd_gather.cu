@@ -56,6 +56,8 @@ struct GatherArgs {
   int32_t peer_world;       // 0 = off
   int32_t peer_B_local;
   int32_t peer_stride;
+  int32_t peer_route_chunks;   // slots per (source, anchor) in the routed layout
+  int32_t peer_group;          // consecutive slots handled by one CTA (keeps >= ~1K rows per CTA at large world sizes)
   const int32_t* peer_cnt[32];   // per source rank: counts of ITS slots destined to this owner (local copy or peer-mapped)
   const int32_t* peer_ids[32];
 };
@@ -69,17 +71,24 @@ struct Segment {
   bool active;
 };
 
-__device__ __forceinline__ Segment cta_segment(const GatherArgs& a, int b, int chunk) {
+// number of sub-segments CTA (chunk, b) walks: 1 except in peer mode
+__device__ __forceinline__ int cta_subsegments(const GatherArgs& a, int chunk) {
+  if (a.peer_world == 0) return 1;
+  return min(a.peer_group, a.peer_route_chunks - chunk * a.peer_group);
+}
+
+__device__ __forceinline__ Segment cta_segment(const GatherArgs& a, int b, int chunk, int sub) {
   Segment g;
   if (a.peer_world > 0) {
     const int s = b / a.peer_B_local;
     const int bl = b - s * a.peer_B_local;
+    const int rc = chunk * a.peer_group + sub;                       // routed slot
     g.idx64 = nullptr;
     g.idx32 = a.peer_ids[s];
-    g.begin = (static_cast<int64_t>(bl) * a.chunks + chunk) * a.peer_stride;
+    g.begin = (static_cast<int64_t>(bl) * a.peer_route_chunks + rc) * a.peer_stride;
     g.c0 = 0;
-    g.c1 = a.peer_cnt[s][static_cast<int64_t>(bl) * a.chunks + chunk];
-    g.has_pos = (chunk == 0) && (a.pos_flag == nullptr || a.pos_flag[b] != 0);
+    g.c1 = a.peer_cnt[s][static_cast<int64_t>(bl) * a.peer_route_chunks + rc];
+    g.has_pos = (rc == 0) && (a.pos_flag == nullptr || a.pos_flag[b] != 0);
     g.active = true;                         // empty sub-segments still publish zero partials
     return g;
   }
@@ -132,10 +141,8 @@ __global__ void __launch_bounds__(kCtaThreads) crd_gather_kernel(const GatherArg
 
   const int b = blockIdx.y;
   const int chunk = blockIdx.x;
-  const Segment sg = cta_segment(a, b, chunk);
-  if (!sg.active) return;
-  const int64_t seg_begin = sg.begin, c0 = sg.c0, c1 = sg.c1;
-  const bool has_pos = sg.has_pos;
+  const int nsub = cta_subsegments(a, chunk);
+  if (!cta_segment(a, b, chunk, 0).active) return;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -166,6 +173,10 @@ __global__ void __launch_bounds__(kCtaThreads) crd_gather_kernel(const GatherArg
   const bool my_side1 = (s & 1) != 0;
   const float my_inv_Z = my_side1 ? inv_Z1 : inv_Z2;
 
+  for (int sub = 0; sub < nsub; ++sub) {
+  const Segment sg = cta_segment(a, b, chunk, sub);
+  const int64_t seg_begin = sg.begin, c0 = sg.c0, c1 = sg.c1;
+  const bool has_pos = sg.has_pos;
   for (int64_t cb = c0 + warp * 32; cb < c1; cb += kCtaWarps * 32) {
     // one coalesced load of 32 indices per warp
     const int64_t mycol = cb + lane;
@@ -246,6 +257,8 @@ __global__ void __launch_bounds__(kCtaThreads) crd_gather_kernel(const GatherArg
     }
   }
 
+  }  // sub-segments
+
   // ---- CTA epilogue: reduce over row slots (lanes), then over warps (smem) ----
   __shared__ float sm_grad[kCtaWarps][2][D];
   __shared__ float sm_scal[kCtaWarps][4];
@@ -303,10 +316,8 @@ __global__ void __launch_bounds__(kCtaThreads) crd_gather_generic_kernel(const G
   const int D = a.D;
   const int b = blockIdx.y;
   const int chunk = blockIdx.x;
-  const Segment sg = cta_segment(a, b, chunk);
-  if (!sg.active) return;
-  const int64_t seg_begin = sg.begin, c0 = sg.c0, c1 = sg.c1;
-  const bool has_pos = sg.has_pos;
+  const int nsub = cta_subsegments(a, chunk);
+  if (!cta_segment(a, b, chunk, 0).active) return;
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   float* acc = sm_dyn + static_cast<size_t>(warp) * 2 * D;
@@ -323,6 +334,10 @@ __global__ void __launch_bounds__(kCtaThreads) crd_gather_generic_kernel(const G
   float inv_Z1 = 1.f, inv_Z2 = 1.f;
   if (MODE != kWeighted && a.Z != nullptr) { inv_Z1 = 1.f / a.Z[0]; inv_Z2 = 1.f / a.Z[1]; }
   float loss1 = 0.f, loss2 = 0.f, sum1 = 0.f, sum2 = 0.f;
+  for (int sub = 0; sub < nsub; ++sub) {
+  const Segment sg = cta_segment(a, b, chunk, sub);
+  const int64_t seg_begin = sg.begin, c0 = sg.c0, c1 = sg.c1;
+  const bool has_pos = sg.has_pos;
   for (int64_t col = c0 + warp; col < c1; col += kCtaWarps) {
     const int64_t row = sg.idx32 ? static_cast<int64_t>(sg.idx32[seg_begin + col]) : sg.idx64[seg_begin + col];
     const float* p1 = a.bank1 + row * D;
@@ -358,6 +373,7 @@ __global__ void __launch_bounds__(kCtaThreads) crd_gather_generic_kernel(const G
       }
     }
   }
+  }  // sub-segments
   if (lane == 0) {
     sm_scal[warp][0] = loss1; sm_scal[warp][1] = loss2;
     sm_scal[warp][2] = sum1;  sm_scal[warp][3] = sum2;
@@ -639,13 +655,19 @@ int peer_setup(GatherArgs& a, Plan& p, const float* bank1, const float* bank2, i
   const int64_t B = B_local * world;
   MML_REQUIRE(B <= 65535, MML_ERR_UNSUPPORTED, "crd_peer: global batch %lld > 65535 anchors per call", (long long)B);
   MML_REQUIRE(n_rows >= 1 && n_rows < (1LL << 31), MML_ERR_UNSUPPORTED, "crd_peer: n_rows must fit in int32");
-  p = Plan{route_stride, route_chunks};
-  MML_REQUIRE(ws_size >= ws_bytes_plan(B, p, D), MML_ERR_WORKSPACE, "crd_peer: workspace %zu < required %zu", ws_size,
-              ws_bytes_plan(B, p, D));
+  // a CTA walks `group` consecutive slots so that it still sees ~>= 1K rows when each slot holds stride/world of them
+  int group = (1024 * world + route_stride - 1) / route_stride;
+  if (group < 1) group = 1;
+  if (group > route_chunks) group = route_chunks;
+  const int32_t ctas_per_anchor = (route_chunks + group - 1) / group;
+  p = Plan{route_stride, ctas_per_anchor};
+  MML_REQUIRE(ws_size >= ws_bytes_plan(B, Plan{route_stride, route_chunks}, D), MML_ERR_WORKSPACE,
+              "crd_peer: workspace %zu < required %zu", ws_size, ws_bytes_plan(B, Plan{route_stride, route_chunks}, D));
   a.bank1 = bank1; a.bank2 = bank2;
-  a.cols = static_cast<int64_t>(route_chunks) * route_stride;     // finishers: every chunk publishes a partial
-  a.D = D; a.chunk_cols = route_stride; a.chunks = route_chunks;
+  a.cols = static_cast<int64_t>(ctas_per_anchor) * route_stride;   // finishers: every CTA publishes a partial
+  a.D = D; a.chunk_cols = route_stride; a.chunks = ctas_per_anchor;
   a.peer_world = world; a.peer_B_local = static_cast<int32_t>(B_local); a.peer_stride = route_stride;
+  a.peer_route_chunks = route_chunks; a.peer_group = group;
   for (int i = 0; i < world; ++i) {
     MML_REQUIRE(peer_ids_host[i] != nullptr && peer_counts_host[i] != nullptr, MML_ERR_INVALID_ARG, "crd_peer: null peer buffer %d", i);
     a.peer_ids[i] = peer_ids_host[i];

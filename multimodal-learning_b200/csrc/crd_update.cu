@@ -150,3 +150,58 @@ extern "C" int mml_alias_select(const int64_t* alias, const int64_t* kk, const f
                                                                                         cols > 0 ? cols : 1, out);
   return check_launch("alias_select_kernel");
 }
+
+// ------------------------------------------------------------------ fused L2 normalisation (Normalize, CRD_criterion.py:236-245)
+namespace mml {
+namespace {
+
+// y = x / sqrt(sum x^2)  -- one warp per row; the reference's pow(2).sum(1).pow(0.5) + div as one kernel
+__global__ void __launch_bounds__(128) l2norm_fwd_kernel(const float* __restrict__ x, int64_t B, int32_t D,
+                                                         float* __restrict__ y, float* __restrict__ nrm) {
+  const int64_t row = (static_cast<int64_t>(blockIdx.x) * 128 + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= B) return;
+  const float* xr = x + row * D;
+  float ss = 0.f;
+  for (int d = lane; d < D; d += 32) { const float v = xr[d]; ss = fmaf(v, v, ss); }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) ss += __shfl_xor_sync(kFullMask, ss, off);
+  const float n = sqrtf(ss);
+  for (int d = lane; d < D; d += 32) y[row * D + d] = __fdiv_rn(xr[d], n);
+  if (lane == 0) nrm[row] = n;
+}
+
+// gx = (gy - y * sum(gy * y)) / norm
+__global__ void __launch_bounds__(128) l2norm_bwd_kernel(const float* __restrict__ gy, const float* __restrict__ y,
+                                                         const float* __restrict__ nrm, int64_t B, int32_t D,
+                                                         float* __restrict__ gx) {
+  const int64_t row = (static_cast<int64_t>(blockIdx.x) * 128 + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= B) return;
+  const float* g = gy + row * D;
+  const float* yr = y + row * D;
+  float dot = 0.f;
+  for (int d = lane; d < D; d += 32) dot = fmaf(g[d], yr[d], dot);
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) dot += __shfl_xor_sync(kFullMask, dot, off);
+  const float inv = 1.0f / nrm[row];
+  for (int d = lane; d < D; d += 32) gx[row * D + d] = (g[d] - yr[d] * dot) * inv;
+}
+
+}  // namespace
+}  // namespace mml
+
+extern "C" int mml_l2norm_fwd(const float* x, int64_t B, int32_t D, float* y, float* norm, void* stream) {
+  MML_REQUIRE(x && y && norm && B >= 0 && D >= 1, MML_ERR_INVALID_ARG, "l2norm_fwd: bad arguments");
+  if (B == 0) return MML_OK;
+  mml::l2norm_fwd_kernel<<<static_cast<unsigned>((B * 32 + 127) / 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(x, B, D, y, norm);
+  return check_launch("l2norm_fwd_kernel");
+}
+
+extern "C" int mml_l2norm_bwd(const float* gy, const float* y, const float* norm, int64_t B, int32_t D, float* gx,
+                              void* stream) {
+  MML_REQUIRE(gy && y && norm && gx && B >= 0 && D >= 1, MML_ERR_INVALID_ARG, "l2norm_bwd: bad arguments");
+  if (B == 0) return MML_OK;
+  mml::l2norm_bwd_kernel<<<static_cast<unsigned>((B * 32 + 127) / 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(gy, y, norm, B, D, gx);
+  return check_launch("l2norm_bwd_kernel");
+}
