@@ -334,6 +334,29 @@ def run_gpu_arm(args):
     staged.clear()
     e2e_value = world * 1000.0 / e2e_ms
 
+    # same public call with contrast_idx=None: negatives drawn on the device by AliasMethod (CRD_criterion.py:37-39),
+    # so only f_s, f_t, idx cross PCIe.  Reported beside `e2e`, not instead of it.
+    e2e_sampled = None
+    if world == 1:
+        small = [tuple(t for t in hp[:3]) for hp in host_pool]
+
+        def step_sampled(i):
+            f_s, f_t, idx = (t.to(dev, non_blocking=True) for t in small[i % len(small)])
+            f_s = f_s.requires_grad_(True)
+            for p in opt_params:
+                p.grad = None
+            loss = mod(f_s, f_t, idx, None)
+            loss.backward()
+            optim.step()
+            return loss.item()
+
+        for i in range(3):
+            step_sampled(i)
+        s_ms = timed(step_sampled, args.steps) / args.steps
+        e2e_sampled = {"value": 1000.0 / s_ms, "unit": "steps/s", "ms_per_step": s_ms,
+                       "h2d_bytes_per_step": sum(t.numel() * t.element_size() for t in small[0]),
+                       "note": "contrast_idx=None: K+1 indices per anchor sampled on the GPU each step"}
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -358,6 +381,8 @@ def run_gpu_arm(args):
                 "d2h_bytes_per_step": 4, "note": "pinned host inputs; upload of step i+1 overlaps step i on a copy stream"},
         "gpu_launches": launches, "clocks": clocks,
     }
+    if e2e_sampled is not None:
+        line["e2e_device_sampling"] = e2e_sampled
     if world == 1 and not args.no_cpu:
         sps, t_sample = cpu_port_steps_per_s(cfg, 6, 2, 64)
         line["cpu_baseline"] = {"value": sps, "unit": "steps/s", "cores": torch.get_num_threads(), "kind": "port",
@@ -375,8 +400,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--traffic", type=float, default=None,
-                    help="dram bytes/launch of the gather kernel from the committed ncu capture (profiles/)")
+    ap.add_argument("--traffic", type=float, default=16.634e9,
+                    help="dram__bytes_read+write per launch of the gather kernel from the committed ncu --set full "
+                         "capture at config 2 (profiles/r1_crd_gather_v2_full.txt: 16.626 GB read + 0.008 GB written)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)
