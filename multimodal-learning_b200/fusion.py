@@ -66,12 +66,12 @@ class KronLinearState:
             self._dg_plans[key] = (ok, lib.mml_kron_dgrad_workspace_bytes(B, N, *self.dims) if ok else 0)
         return self._dg_plans[key]
 
-    def ensure_t(self, weight):
+    def ensure_t(self, weight, key=None):
         lib = _cabi.lib()
         d1, d2, d3 = self.dims
         dev = weight.device
         self.ensure_table(dev)
-        key = (weight.data_ptr(), weight._version, tuple(weight.shape))
+        key = key if key is not None else (weight.data_ptr(), weight._version, tuple(weight.shape))
         if key != self.packed_t_key:
             N = weight.shape[0]
             nfl = lib.mml_kron_packed_t_floats(N, d1, d2, d3)
@@ -108,12 +108,12 @@ class KronLinearState:
             self._plans[key] = (ok, lib.mml_kron_fwd_workspace_bytes(B, N, *self.dims) if ok else 0)
         return self._plans[key]
 
-    def ensure(self, weight):
+    def ensure(self, weight, key=None):
         lib = _cabi.lib()
         d1, d2, d3 = self.dims
         dev = weight.device
         self.ensure_table(dev)
-        key = (weight.data_ptr(), weight._version, tuple(weight.shape))
+        key = key if key is not None else (weight.data_ptr(), weight._version, tuple(weight.shape))
         if key != self.packed_key:
             N = weight.shape[0]
             nfl = lib.mml_kron_packed_floats(N, d1, d2, d3)
@@ -128,7 +128,7 @@ class _KronLinearFn(torch.autograd.Function):
     """y = kron(append1(f1), append1(f2)[, append1(f3)]) * mask @ W^T + bias, without the Kronecker tensor."""
 
     @staticmethod
-    def forward(ctx, state, weight, bias, drop_p, training, seed, *factors):
+    def forward(ctx, state, weight, bias, drop_p, training, seed, wkey, *factors):
         lib = _cabi.lib()
         d1, d2, d3 = state.dims
         fs = [f.contiguous() for f in factors]
@@ -142,7 +142,7 @@ class _KronLinearFn(torch.autograd.Function):
         bptr = _cabi.dptr(bias.detach().contiguous()) if bias is not None else None
         tc_ok, nws = state.plan(B, N)
         if state.path == "auto" and tc_ok:
-            state.ensure(weight)
+            state.ensure(weight, wkey)
             ws = torch.empty(nws, dtype=torch.uint8, device=dev)
             rc = lib.mml_kron_linear_fwd(_cabi.dptr(fs[0]), _cabi.dptr(fs[1]), f3p, B, d1, d2, d3, _cabi.dptr(state.table),
                                          _cabi.dptr(state.packed), bptr, N, float(drop_p), int(seed), int(training),
@@ -154,6 +154,7 @@ class _KronLinearFn(torch.autograd.Function):
             _cabi.check(rc, "mml_kron_linear_fwd_simt")
         ctx.save_for_backward(w, *fs)
         ctx.state = state
+        ctx.wkey = wkey
         ctx.cfg = (state.dims, float(drop_p), int(training), int(seed), bias is not None)
         return y
 
@@ -167,7 +168,7 @@ class _KronLinearFn(torch.autograd.Function):
         B, N = dy.shape
         dev = dy.device
         need_w = ctx.needs_input_grad[1]
-        need_f = any(ctx.needs_input_grad[6:])
+        need_f = any(ctx.needs_input_grad[7:])
         dW = torch.empty_like(w) if need_w else None
         dfs = [torch.empty_like(f) for f in fs] if need_f else [None] * len(fs)
         state = ctx.state
@@ -186,7 +187,7 @@ class _KronLinearFn(torch.autograd.Function):
             simt_dW = None
         dg_ok, dg_ws = state.dgrad_plan(B, N)
         if need_f and state.path == "auto" and dg_ok:            # factor gradients on the tensor cores
-            state.ensure_t(w)
+            state.ensure_t(w, ctx.wkey)
             ws = torch.empty(dg_ws, dtype=torch.uint8, device=dev)
             rc = lib.mml_kron_linear_dgrad(_cabi.dptr(fs[0]), _cabi.dptr(fs[1]), f3p, B, d1, d2, d3, _cabi.dptr(state.table),
                                            _cabi.dptr(state.packed_t), _cabi.dptr(dy), N, drop_p, seed, training,
@@ -204,11 +205,13 @@ class _KronLinearFn(torch.autograd.Function):
                 _cabi.dptr(simt_dW), st)
             _cabi.check(rc, "mml_kron_linear_bwd_simt")
         dbias = dy.sum(0) if (has_bias and ctx.needs_input_grad[2]) else None
-        return (None, dW, dbias, None, None, None, *dfs)
+        return (None, dW, dbias, None, None, None, None, *dfs)
 
 
-def kron_linear(state: KronLinearState, factors, weight, bias, drop_p=0.0, training=False, seed=None):
-    """Public functional form (used by the modules below and by the tests)."""
+def kron_linear(state: KronLinearState, factors, weight, bias, drop_p=0.0, training=False, seed=None, weight_key=None):
+    """Public functional form (used by the modules below and by the tests).  `weight_key` identifies the weight's
+    CONTENT for the packed-copy cache when `weight` is a temporary derived from a parameter (defaults to the
+    tensor's own storage pointer + version counter)."""
     for f in factors:
         if not f.is_cuda:
             raise RuntimeError("Kronecker fusion runs on CUDA tensors only (no CPU fallback)")
@@ -216,7 +219,7 @@ def kron_linear(state: KronLinearState, factors, weight, bias, drop_p=0.0, train
             raise RuntimeError(f"Kronecker fusion computes from fp32 factors; got {f.dtype}")
     if seed is None:
         seed = int(torch.randint(0, 2 ** 62, (1,)).item()) if (training and drop_p > 0) else 0
-    return _KronLinearFn.apply(state, weight, bias, drop_p, training, seed, *factors)
+    return _KronLinearFn.apply(state, weight, bias, drop_p, training, seed, weight_key, *factors)
 
 
 # --------------------------------------------------------------------------- #
@@ -247,6 +250,25 @@ class _GatedKronFusion(nn.Module):
         self.encoder2 = nn.Sequential(nn.Linear(mmhid + skip_dim, mmhid), *norm(), nn.ReLU(), nn.Dropout(p=dropout_rate))
         init_max_weights(self)
         self._kron = KronLinearState(dims)
+        # the nn.Bilinear gates are the same contraction without the appended 1
+        self._zkron = {t: KronLinearState([dims_og[a], dims_og[b]]) for t, (a, b) in enumerate(gate_inputs, start=1)} \
+            if use_bilinear else {}
+
+    def set_kron_path(self, path):
+        """"auto" (tensor cores) or "simt" (exact fp32 CUDA cores) for every Kronecker contraction of the module."""
+        self._kron.path = path
+        for st in self._zkron.values():
+            st.path = path
+
+    def _bilinear_gate(self, t, zmod, va, vb):
+        """nn.Bilinear(va, vb) = kron(va, vb) @ W.view(d, -1)^T + b (fusion.py:21,25,43,50) through the Kronecker
+        kernels: the [d, da, db] weight is zero-padded to the append-1 layout [d, (da+1)(db+1)] (the border and
+        corner columns multiply the appended 1s and are zero), so forward, dW and the input gradients all reuse
+        K1/K2/K3; autograd slices dW back through the pad."""
+        w = zmod.weight
+        wpad = torch.nn.functional.pad(w, (0, 1, 0, 1)).flatten(1)
+        return kron_linear(self._zkron[t], [va, vb], wpad, zmod.bias,
+                           weight_key=("bilinear", w.data_ptr(), w._version, tuple(w.shape)))
 
     def _branch(self, t, vecs, gated):
         own = vecs[t - 1]
@@ -254,7 +276,10 @@ class _GatedKronFusion(nn.Module):
             a, b = self._gate_inputs[t - 1]
             h = getattr(self, f"linear_h{t}")(own)
             zmod = getattr(self, f"linear_z{t}")
-            z = zmod(vecs[a], vecs[b]) if self.use_bilinear else zmod(torch.cat((vecs[a], vecs[b]), dim=1))
+            if self.use_bilinear:
+                z = self._bilinear_gate(t, zmod, vecs[a].contiguous(), vecs[b].contiguous())
+            else:
+                z = zmod(torch.cat((vecs[a], vecs[b]), dim=1))
             return getattr(self, f"linear_o{t}")(torch.sigmoid(z) * h)
         return getattr(self, f"linear_o{t}")(own)
 

@@ -52,7 +52,7 @@ def test_fusion_modules_match_reference_golden(pkg, golden, name, path):
     modes = ["eval"] + (["train"] if any(k.startswith("train.") for k in g.keys()) else [])
     for tag in modes:
         mod = _make(pkg, g)
-        mod._kron.path = path
+        mod.set_kron_path(path)
         mod.train(tag == "train")
         ins = [g.t(f"vec{i + 1}", DEV).requires_grad_(True) for i in range(nvec)]
         before = pkg._cabi.launch_count()
