@@ -16,6 +16,7 @@
 // Per-CTA partial results (gradient [2,D], 4 scalars) go to a workspace and are
 // reduced in a fixed order by two small finisher kernels -> deterministic output.
 #include <math.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -132,8 +133,8 @@ __device__ __forceinline__ float score_row(const GatherArgs& a, float dot, float
   return g;
 }
 
-template <int VPL, int U, int MODE>
-__global__ void __launch_bounds__(kCtaThreads) crd_gather_kernel(const GatherArgs a) {
+template <int VPL, int U, int MODE, int MINB = 1>
+__global__ void __launch_bounds__(kCtaThreads, MINB) crd_gather_kernel(const GatherArgs a) {
   constexpr int D = 32 * VPL;
   constexpr int ROWS_PER_IT = 4 * U;        // rows of each bank per warp iteration
   constexpr int NSCAL = 2 * U;              // scalars per row-slot per iteration
@@ -502,7 +503,16 @@ int launch_gather(const GatherArgs& a, int64_t B, cudaStream_t st) {
   switch (a.D) {
     case 32:  crd_gather_kernel<1, 4, MODE><<<grid, kCtaThreads, 0, st>>>(a); break;
     case 64:  crd_gather_kernel<2, 4, MODE><<<grid, kCtaThreads, 0, st>>>(a); break;
-    case 128: crd_gather_kernel<4, 2, MODE><<<grid, kCtaThreads, 0, st>>>(a); break;
+    case 128: {
+      // tuning hook (scripts/exp_gather_variants.py): MML_CRD_VARIANT selects occupancy / unroll trade-offs
+      static const int variant = [] { const char* e = getenv("MML_CRD_VARIANT"); return e ? atoi(e) : 0; }();
+      if (variant == 1) crd_gather_kernel<4, 2, MODE, 4><<<grid, kCtaThreads, 0, st>>>(a);
+      else if (variant == 2) crd_gather_kernel<4, 1, MODE, 5><<<grid, kCtaThreads, 0, st>>>(a);
+      else if (variant == 3) crd_gather_kernel<4, 1, MODE, 6><<<grid, kCtaThreads, 0, st>>>(a);
+      else if (variant == 4) crd_gather_kernel<4, 2, MODE, 5><<<grid, kCtaThreads, 0, st>>>(a);
+      else crd_gather_kernel<4, 2, MODE, 3><<<grid, kCtaThreads, 0, st>>>(a);
+      break;
+    }
     case 256: crd_gather_kernel<8, 1, MODE><<<grid, kCtaThreads, 0, st>>>(a); break;
     default: {
       const size_t smem = (static_cast<size_t>(kCtaWarps) * 2 + 2) * a.D * sizeof(float);
