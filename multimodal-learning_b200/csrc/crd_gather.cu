@@ -78,9 +78,10 @@ __device__ __forceinline__ int cta_subsegments(const GatherArgs& a, int chunk) {
   return min(a.peer_group, a.peer_route_chunks - chunk * a.peer_group);
 }
 
+template <bool kPeer>
 __device__ __forceinline__ Segment cta_segment(const GatherArgs& a, int b, int chunk, int sub) {
   Segment g;
-  if (a.peer_world > 0) {
+  if (kPeer) {
     const int s = b / a.peer_B_local;
     const int bl = b - s * a.peer_B_local;
     const int rc = chunk * a.peer_group + sub;                       // routed slot
@@ -133,7 +134,7 @@ __device__ __forceinline__ float score_row(const GatherArgs& a, float dot, float
   return g;
 }
 
-template <int VPL, int U, int MODE, int MINB = 1>
+template <int VPL, int U, int MODE, int MINB = 1, bool kPeer = false>
 __global__ void __launch_bounds__(kCtaThreads, MINB) crd_gather_kernel(const GatherArgs a) {
   constexpr int D = 32 * VPL;
   constexpr int ROWS_PER_IT = 4 * U;        // rows of each bank per warp iteration
@@ -142,8 +143,8 @@ __global__ void __launch_bounds__(kCtaThreads, MINB) crd_gather_kernel(const Gat
 
   const int b = blockIdx.y;
   const int chunk = blockIdx.x;
-  const int nsub = cta_subsegments(a, chunk);
-  if (!cta_segment(a, b, chunk, 0).active) return;
+  const int nsub = kPeer ? cta_subsegments(a, chunk) : 1;
+  if (!kPeer && !cta_segment<false>(a, b, chunk, 0).active) return;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -175,7 +176,7 @@ __global__ void __launch_bounds__(kCtaThreads, MINB) crd_gather_kernel(const Gat
   const float my_inv_Z = my_side1 ? inv_Z1 : inv_Z2;
 
   for (int sub = 0; sub < nsub; ++sub) {
-  const Segment sg = cta_segment(a, b, chunk, sub);
+  const Segment sg = cta_segment<kPeer>(a, b, chunk, sub);
   const int64_t seg_begin = sg.begin, c0 = sg.c0, c1 = sg.c1;
   const bool has_pos = sg.has_pos;
   for (int64_t cb = c0 + warp * 32; cb < c1; cb += kCtaWarps * 32) {
@@ -317,8 +318,9 @@ __global__ void __launch_bounds__(kCtaThreads) crd_gather_generic_kernel(const G
   const int D = a.D;
   const int b = blockIdx.y;
   const int chunk = blockIdx.x;
+  const bool peer = a.peer_world > 0;
   const int nsub = cta_subsegments(a, chunk);
-  if (!cta_segment(a, b, chunk, 0).active) return;
+  if (!peer && !cta_segment<false>(a, b, chunk, 0).active) return;
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   float* acc = sm_dyn + static_cast<size_t>(warp) * 2 * D;
@@ -336,7 +338,7 @@ __global__ void __launch_bounds__(kCtaThreads) crd_gather_generic_kernel(const G
   if (MODE != kWeighted && a.Z != nullptr) { inv_Z1 = 1.f / a.Z[0]; inv_Z2 = 1.f / a.Z[1]; }
   float loss1 = 0.f, loss2 = 0.f, sum1 = 0.f, sum2 = 0.f;
   for (int sub = 0; sub < nsub; ++sub) {
-  const Segment sg = cta_segment(a, b, chunk, sub);
+  const Segment sg = peer ? cta_segment<true>(a, b, chunk, sub) : cta_segment<false>(a, b, chunk, sub);
   const int64_t seg_begin = sg.begin, c0 = sg.c0, c1 = sg.c1;
   const bool has_pos = sg.has_pos;
   for (int64_t col = c0 + warp; col < c1; col += kCtaWarps) {
@@ -500,20 +502,24 @@ Workspace carve(void* ws, int64_t B, int32_t D, const Plan& p) {
 template <int MODE>
 int launch_gather(const GatherArgs& a, int64_t B, cudaStream_t st) {
   const dim3 grid(a.chunks, static_cast<unsigned>(B));
+  const bool peer = a.peer_world > 0;
   switch (a.D) {
-    case 32:  crd_gather_kernel<1, 4, MODE><<<grid, kCtaThreads, 0, st>>>(a); break;
-    case 64:  crd_gather_kernel<2, 4, MODE><<<grid, kCtaThreads, 0, st>>>(a); break;
-    case 128: {
-      // tuning hook (scripts/exp_gather_variants.py): MML_CRD_VARIANT selects occupancy / unroll trade-offs
-      static const int variant = [] { const char* e = getenv("MML_CRD_VARIANT"); return e ? atoi(e) : 0; }();
-      if (variant == 1) crd_gather_kernel<4, 2, MODE, 4><<<grid, kCtaThreads, 0, st>>>(a);
-      else if (variant == 2) crd_gather_kernel<4, 1, MODE, 5><<<grid, kCtaThreads, 0, st>>>(a);
-      else if (variant == 3) crd_gather_kernel<4, 1, MODE, 6><<<grid, kCtaThreads, 0, st>>>(a);
-      else if (variant == 4) crd_gather_kernel<4, 2, MODE, 5><<<grid, kCtaThreads, 0, st>>>(a);
+    case 32:
+      if (peer) crd_gather_kernel<1, 4, MODE, 1, true><<<grid, kCtaThreads, 0, st>>>(a);
+      else crd_gather_kernel<1, 4, MODE><<<grid, kCtaThreads, 0, st>>>(a);
+      break;
+    case 64:
+      if (peer) crd_gather_kernel<2, 4, MODE, 1, true><<<grid, kCtaThreads, 0, st>>>(a);
+      else crd_gather_kernel<2, 4, MODE><<<grid, kCtaThreads, 0, st>>>(a);
+      break;
+    case 128:
+      if (peer) crd_gather_kernel<4, 2, MODE, 3, true><<<grid, kCtaThreads, 0, st>>>(a);
       else crd_gather_kernel<4, 2, MODE, 3><<<grid, kCtaThreads, 0, st>>>(a);
       break;
-    }
-    case 256: crd_gather_kernel<8, 1, MODE><<<grid, kCtaThreads, 0, st>>>(a); break;
+    case 256:
+      if (peer) crd_gather_kernel<8, 1, MODE, 1, true><<<grid, kCtaThreads, 0, st>>>(a);
+      else crd_gather_kernel<8, 1, MODE><<<grid, kCtaThreads, 0, st>>>(a);
+      break;
     default: {
       const size_t smem = (static_cast<size_t>(kCtaWarps) * 2 + 2) * a.D * sizeof(float);
       crd_gather_generic_kernel<MODE><<<grid, kCtaThreads, smem, st>>>(a);
