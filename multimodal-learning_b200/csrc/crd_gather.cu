@@ -25,6 +25,8 @@ namespace {
 
 constexpr int kCtaThreads = 128;
 constexpr int kCtaWarps = kCtaThreads / 32;
+constexpr int kPeerStageIds = 4096;      // routed ids one peer-mode CTA stages in shared memory (16 KB)
+constexpr int kPeerMaxGroup = 32;        // slots per CTA the staging prologue handles (one lane per slot)
 
 enum Mode : int { kFused = 0, kScores = 1, kWeighted = 2 };
 
@@ -175,8 +177,68 @@ __global__ void __launch_bounds__(kCtaThreads, MINB) crd_gather_kernel(const Gat
   const bool my_side1 = (s & 1) != 0;
   const float my_inv_Z = my_side1 ? inv_Z1 : inv_Z2;
 
-  for (int sub = 0; sub < nsub; ++sub) {
-  const Segment sg = cta_segment<kPeer>(a, b, chunk, sub);
+  // Peer mode: the routed ids of this CTA's slots live in the SOURCE rank's arena.  Pull them over NVLink ONCE, all
+  // loads in flight together (one remote round trip for the counts, one for the ids), compacted into shared memory;
+  // the row loop below then runs over one flat local list.  A per-block remote index load would put an NVLink
+  // latency in front of every 32 rows.  Slots too full for the staging buffer keep the direct (sub-segment) walk.
+  int nwalk = nsub;
+  const int32_t* peer_stage_ptr = nullptr;
+  bool staged = false;
+  int staged_total = 0;
+  if constexpr (kPeer) {
+    __shared__ int32_t sm_ids[kPeerStageIds];
+    __shared__ int32_t sm_off[kPeerMaxGroup + 1];
+    if (nsub <= kPeerMaxGroup) {
+      const int src_rank = b / a.peer_B_local;
+      const int bl = b - src_rank * a.peer_B_local;
+      const int64_t slot0 = static_cast<int64_t>(bl) * a.peer_route_chunks + chunk * a.peer_group;
+      if (warp == 0) {
+        const int32_t cnt = lane < nsub ? a.peer_cnt[src_rank][slot0 + lane] : 0;
+        int32_t incl = cnt;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+          const int32_t t = __shfl_up_sync(kFullMask, incl, off);
+          if (lane >= off) incl += t;
+        }
+        if (lane < nsub) sm_off[lane + 1] = incl;
+        if (lane == 0) sm_off[0] = 0;
+      }
+      __syncthreads();
+      staged_total = sm_off[nsub];
+      staged = staged_total <= kPeerStageIds;
+      if (staged) {
+        for (int sub = warp; sub < nsub; sub += kCtaWarps) {
+          const int32_t o0 = sm_off[sub], cnt = sm_off[sub + 1] - o0;
+          const int4* src = reinterpret_cast<const int4*>(a.peer_ids[src_rank] + (slot0 + sub) * a.peer_stride);
+          for (int i0 = 0; i0 < cnt; i0 += 256) {          // two 16-byte loads per lane in flight
+            const int ia = i0 + lane * 4, ib = ia + 128;
+            int4 va = make_int4(0, 0, 0, 0), vb = va;
+            if (ia < cnt) va = src[ia >> 2];
+            if (ib < cnt) vb = src[ib >> 2];
+            const int32_t ea[4] = {va.x, va.y, va.z, va.w}, eb[4] = {vb.x, vb.y, vb.z, vb.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              if (ia + e < cnt) sm_ids[o0 + ia + e] = ea[e];
+              if (ib + e < cnt) sm_ids[o0 + ib + e] = eb[e];
+            }
+          }
+        }
+        nwalk = 1;
+      }
+      __syncthreads();
+      if (staged) peer_stage_ptr = sm_ids;
+    }
+  }
+
+  for (int sub = 0; sub < nwalk; ++sub) {
+  Segment sg;
+  if (kPeer && staged) {
+    sg.idx64 = nullptr; sg.idx32 = peer_stage_ptr; sg.begin = 0; sg.c0 = 0; sg.c1 = staged_total;
+    sg.has_pos = (chunk == 0) && (a.pos_flag == nullptr || a.pos_flag[b] != 0);
+    sg.active = true;
+  } else {
+    sg = cta_segment<kPeer>(a, b, chunk, sub);
+  }
   const int64_t seg_begin = sg.begin, c0 = sg.c0, c1 = sg.c1;
   const bool has_pos = sg.has_pos;
   for (int64_t cb = c0 + warp * 32; cb < c1; cb += kCtaWarps * 32) {

@@ -250,6 +250,86 @@ def test_ragged_segments_equal_dense_and_shard_sum(pkg, co):
     assert torch.equal(f1.cpu(), u1) and torch.equal(f2.cpu(), u2)
 
 
+@pytest.mark.parametrize("W,Bl,D,K,n,chunk,skew", [
+    (8, 4, 128, 9000, 4000, 2048, False),    # config-5-like: 8 owners, CTAs walk several slots, staged in shared memory
+    (2, 6, 128, 700, 301, 256, False),       # two owners, one slot per CTA
+    (8, 1, 64, 9000, 64, 2048, True),        # every id owned by rank 0: 4 full slots overflow the staging buffer -> direct walk
+    (3, 2, 48, 90, 50, 32, False),           # generic-D kernel in peer mode
+])
+def test_peer_kernels_emulated_world_on_one_gpu(pkg, co, W, Bl, D, K, n, chunk, skew):
+    """The NVLink-pull kernels (`mml_shard_route_strided` -> `mml_crd_fused_loss_grad_peer`) with W 'ranks' emulated in
+    one process: every rank's routed arena is an ordinary local buffer, each owner scores all W*Bl anchors against its
+    row block, and the owners' partial sums add up to the dense single-bank result (integer routing exact: every
+    (anchor, column) pair lands in exactly one owner's slot, positives first)."""
+    import ctypes
+    from multimodal_learning_b200 import _cabi, crd
+    lib = _cabi.lib()
+    Bg = W * Bl
+    m1, m2, v1, v2, y, idx = _random_problem(Bg, D, K, n, seed=W * 100 + Bl)
+    rows_per = (n + W - 1) // W
+    if skew:
+        idx = idx % rows_per
+        y = idx[:, 0].clone()
+    T = float(torch.tensor(0.07).item())
+    d = lambda t: t.to(DEV)
+    Zt = torch.tensor([31.0, 29.0], device=DEV)
+    loss, _, g1, g2, _, _ = crd.crd_fused_loss_grad(d(m1), d(m2), d(v1), d(v2), d(idx), T, Zt, n, K)
+    cols = K + 1
+    chunks = (cols + chunk - 1) // chunk
+    st = _cabi.cur_stream(torch.device(DEV))
+    ids = [torch.full((W, Bl, chunks, chunk), -1, dtype=torch.int32, device=DEV) for _ in range(W)]     # per SOURCE rank
+    cnt = [torch.zeros(W, Bl, chunks, dtype=torch.int32, device=DEV) for _ in range(W)]
+    for s in range(W):
+        ci = d(idx[s * Bl:(s + 1) * Bl].contiguous())
+        _cabi.check(lib.mml_shard_route_strided(_cabi.dptr(ci), Bl, cols, chunk, rows_per, W, _cabi.dptr(cnt[s]),
+                                                _cabi.dptr(ids[s]), st), "route")
+    # routing is an exact stable partition
+    for s in range(W):
+        c = cnt[s].cpu()
+        assert int(c.sum()) == Bl * cols
+        for o in range(W):
+            lo = o * rows_per
+            for bl in range(Bl):
+                want = idx[s * Bl + bl]
+                got = torch.cat([ids[s][o, bl, ch, :c[o, bl, ch]].cpu() for ch in range(chunks)]).long() + lo
+                assert torch.equal(got, want[(want >= lo) & (want < lo + rows_per)])
+    V1, V2 = d(v1), d(v2)
+    tot = torch.zeros(4, dtype=torch.float64)
+    tg1 = torch.zeros(Bg, D, dtype=torch.float64)
+    tg2 = torch.zeros(Bg, D, dtype=torch.float64)
+    P = ctypes.c_void_p
+    for o in range(W):
+        lo, hi = o * rows_per, min(n, (o + 1) * rows_per)
+        if hi <= lo:
+            continue
+        b1, b2 = d(m1[lo:hi].contiguous()), d(m2[lo:hi].contiguous())
+        ids_ptrs = (P * W)(*[ids[s][o].data_ptr() for s in range(W)])
+        cnt_ptrs = (P * W)(*[cnt[s][o].data_ptr() for s in range(W)])
+        pos_flag = d(((idx[:, 0] >= lo) & (idx[:, 0] < hi)).to(torch.uint8))
+        nws = lib.mml_crd_peer_workspace_bytes(Bg, chunks, D)
+        ws = torch.empty(nws, dtype=torch.uint8, device=DEV)
+        sums = torch.empty(4, device=DEV)
+        pg1, pg2 = torch.empty(Bg, D, device=DEV), torch.empty(Bg, D, device=DEV)
+        _cabi.check(lib.mml_crd_fused_loss_grad_peer(
+            _cabi.dptr(b1), _cabi.dptr(b2), hi - lo, D, _cabi.dptr(V1), _cabi.dptr(V2), ids_ptrs, cnt_ptrs, W, Bl, chunks,
+            chunk, _cabi.dptr(pos_flag), T, _cabi.dptr(Zt), n, K, Bg, _cabi.dptr(sums), _cabi.dptr(pg1), _cabi.dptr(pg2),
+            _cabi.dptr(ws), nws, st), "fused_peer")
+        tot += sums.double().cpu()
+        tg1 += pg1.double().cpu()
+        tg2 += pg2.double().cpu()
+        # first-step statistics kernel over the same slots: raw exp sums
+        s2 = torch.empty(4, device=DEV)
+        _cabi.check(lib.mml_crd_scores_peer(_cabi.dptr(b1), _cabi.dptr(b2), hi - lo, D, _cabi.dptr(V1), _cabi.dptr(V2),
+                                            ids_ptrs, cnt_ptrs, W, Bl, chunks, chunk, T, _cabi.dptr(s2), _cabi.dptr(ws), nws,
+                                            st), "scores_peer")
+        tot[2:] += s2.double().cpu()[2:]
+    assert abs(-(tot[0] + tot[1]).item() / Bg - loss.item()) < TOL * abs(loss.item())
+    assert rel_err(tg1, g1) < TOL and rel_err(tg2, g2) < TOL
+    raw1, raw2 = co.contrast_scores(m1, m2, torch.tensor([K, T, -1, -1, 0.5]), v1, v2, idx)
+    assert abs(tot[2].item() - raw1.double().sum().item()) < TOL * raw1.double().sum().item()
+    assert abs(tot[3].item() - raw2.double().sum().item()) < TOL * raw2.double().sum().item()
+
+
 def test_alias_draw_bit_exact_given_raw_draws(pkg, co, golden):
     """Same generator state => same indices: replay the two torch RNG calls the reference makes
     (:133 random_, :137 bernoulli) and push them through the oracle's select."""
