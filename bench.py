@@ -59,31 +59,51 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md).  The sampler process is started
+    before the warm-up (nvidia-smi needs a moment to attach on an 8-GPU box); `mark()` at the start of the timed region
+    drops everything sampled before it."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
         self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.skip = 0
         try:
             self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                       "-lms", "20", "-i", str(index)], stdout=self.f, stderr=subprocess.DEVNULL)
+                                       "-lms", "10", "-i", str(index)], stdout=self.f, stderr=subprocess.DEVNULL)
         except OSError:
             self.p = None
+
+    def _lines(self):
+        with open(self.f.name) as g:
+            return g.read().splitlines()
+
+    def wait_ready(self, timeout_s=10.0):
+        t0 = time.perf_counter()
+        while self.p is not None and time.perf_counter() - t0 < timeout_s and not self._lines():
+            time.sleep(0.05)
+
+    def mark(self):
+        if self.p is not None:
+            self.skip = len(self._lines())
 
     def stop(self):
         if self.p is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.03)
         self.p.terminate()
         try:
             self.p.wait(timeout=5)
         except subprocess.TimeoutExpired:
             self.p.kill()
-        self.f.flush()
-        self.f.seek(0)
+        lines = self._lines()
+        if len(lines) > self.skip + 1:      # the line straddling mark() may predate the region
+            lines = lines[self.skip:]
+        else:
+            lines = lines[-2:]
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for line in self.f.read().splitlines():
+        for line in lines:
             parts = [x.strip() for x in line.split(",")]
             if len(parts) < 6:
                 continue
@@ -283,12 +303,19 @@ def run_gpu_arm(args):
         return ms.item()
 
     # ---- device-resident throughput (`value`) ----
+    sampler = ClockSampler(local_rank) if rank == 0 else None
     for i in range(max(args.warmup, 3)):
         step_device(i)
     timer = EventTimer()
     crd_mod.KERNEL_TIMER = timer
     launches0 = pkg._cabi.launch_count()
-    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        torch.cuda.synchronize(dev)
+        sampler.wait_ready()
+        for i in range(3):                  # the GPU is busy again when the region starts
+            step_device(i)
+        launches0 = pkg._cabi.launch_count()
+        sampler.mark()
     timer.enabled = True
     total_ms = timed(step_device, args.steps, profile=True)
     timer.enabled = False
@@ -333,6 +360,22 @@ def run_gpu_arm(args):
     e2e_ms = timed(step_e2e, args.steps) / args.steps
     staged.clear()
     e2e_value = world * 1000.0 / e2e_ms
+
+    # same call with the caller handing contrast_idx over as int32 (n_data < 2^31): half the PCIe bytes.  The reference's
+    # loader yields int64, so this is reported beside `e2e`, not instead of it.
+    e2e_i32 = None
+    if world == 1:
+        host_pool32 = [(hp[0], hp[1], hp[2], hp[3].to(torch.int32).pin_memory()) for hp in host_pool]
+        host_pool, host_pool64 = host_pool32, host_pool
+        for i in range(3):
+            step_e2e(i)
+        staged.clear()
+        i32_ms = timed(step_e2e, args.steps) / args.steps
+        staged.clear()
+        e2e_i32 = {"value": 1000.0 / i32_ms, "unit": "steps/s", "ms_per_step": i32_ms,
+                   "h2d_bytes_per_step": sum(t.numel() * t.element_size() for t in host_pool32[0]),
+                   "note": "contrast_idx supplied as int32 by the caller"}
+        host_pool = host_pool64
 
     # same public call with contrast_idx=None: negatives drawn on the device by AliasMethod (CRD_criterion.py:37-39),
     # so only f_s, f_t, idx cross PCIe.  Reported beside `e2e`, not instead of it.
@@ -381,13 +424,15 @@ def run_gpu_arm(args):
                 "d2h_bytes_per_step": 4, "note": "pinned host inputs; upload of step i+1 overlaps step i on a copy stream"},
         "gpu_launches": launches, "clocks": clocks,
     }
+    if e2e_i32 is not None:
+        line["e2e_int32_idx"] = e2e_i32
     if e2e_sampled is not None:
         line["e2e_device_sampling"] = e2e_sampled
     if world == 1 and not args.no_cpu:
-        sps, t_sample = cpu_port_steps_per_s(cfg, 6, 2, 64)
+        sps, t_sample = cpu_port_steps_per_s(cfg, 30, 2, 256)
         line["cpu_baseline"] = {"value": sps, "unit": "steps/s", "cores": torch.get_num_threads(), "kind": "port",
-                                "sample": f"64 of 1024 anchors per step at full K/n ({t_sample * 1e3:.0f} ms each), "
-                                          f"scaled x16 (work is linear in anchors)"}
+                                "sample": f"30 steps of 256 of the 1024 anchors at full K/n ({t_sample * 1e3:.0f} ms each), "
+                                          f"scaled x4 (work is linear in anchors)"}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -223,7 +223,7 @@ class _ScoresFn(torch.autograd.Function):
             uniq, inv = torch.unique(ys, return_inverse=True)
             first = torch.full((uniq.numel(),), ys.numel(), dtype=torch.long, device=ys.device)
             first.scatter_reduce_(0, inv, torch.arange(ys.numel(), device=ys.device), "amin")
-            flat = idx.reshape(-1)
+            flat = idx.reshape(-1).long()
             pos = torch.searchsorted(uniq, flat).clamp_(max=uniq.numel() - 1)
             hit = (uniq[pos] == flat).nonzero().flatten()
             if hit.numel():
@@ -294,6 +294,8 @@ class ContrastMemory(nn.Module):
         v1, v2, y = _as_f32(v1), _as_f32(v2), _as_i64(y)
         if idx is None:                                              # :37-39
             idx = self.multinomial.draw(B * (self.K + 1), y=y, cols=self.K + 1).view(B, -1)
+        elif idx.dtype == torch.int32:      # extension: int32 row ids (n_data < 2^31) halve the index traffic
+            idx = idx.contiguous()
         else:
             idx = _as_i64(idx)
         idx = idx.view(B, self._K + 1)          # same RuntimeError as :42 when idx has the wrong width

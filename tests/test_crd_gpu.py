@@ -124,6 +124,20 @@ def test_backward_is_repeatable_with_retain_graph(pkg, golden):
     assert rel_err(g1, g.t("step0.grad_f_s")) < TOL
 
 
+def test_int32_contrast_idx_gives_identical_bits(pkg, golden):
+    """Extension: the caller may hand contrast_idx over as int32 (half the H2D bytes); same kernels, same bits."""
+    g = golden("crd_d128")
+    res = []
+    for dt in (torch.int64, torch.int32):
+        mod = _make_module(pkg, g.cfg, g.state_dict("init."))
+        f_s = g.t("step0.f_s", DEV).requires_grad_(True)
+        loss = mod(f_s, g.t("step0.f_t", DEV), g.t("step0.idx", DEV), g.t("step0.contrast_idx", DEV).to(dt))
+        loss.backward()
+        res.append((loss.detach().clone(), f_s.grad.clone(), mod.contrast.memory_v1.clone(), mod.contrast.params.clone()))
+    for a, b in zip(*res):
+        assert torch.equal(a, b)
+
+
 def test_wrong_idx_width_raises_like_reference(pkg, golden):
     g = golden("crd_small")
     mod = _make_module(pkg, g.cfg, g.state_dict("init."))
