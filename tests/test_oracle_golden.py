@@ -167,3 +167,55 @@ def test_distill_kl(golden):
         loss.backward()
         assert rel_err(loss, g.t(f"c{i}.loss")) < FLOAT_TOL
         assert rel_err(y_s.grad, g.t(f"c{i}.grad_y_s")) < FLOAT_TOL
+
+
+# ---- selection variant (ContrastMemory_v3 / 5-arg CRDLoss / ContrastLoss_v2), oracle/crd_select_oracle.py ----
+SEL_CASES = ["crdsel_random", "crdsel_hard_d128", "crdsel_mid_d64", "crdsel_curriculum", "crdsel_allneg", "crdsel_sampleKD"]
+
+
+@pytest.mark.parametrize("name", SEL_CASES)
+def test_crd_selection_variant_matches_reference(golden, name):
+    from oracle import crd_select_oracle as so
+    g = golden(name)
+    c = g.cfg
+    sd = g.state_dict("init.")
+    for s in range(c["steps"]):
+        p = f"step{s}."
+        f_s = g.t(p + "f_s").requires_grad_(True)
+        f_t = g.t(p + "f_t").requires_grad_(True)
+        params = [k for k in sd if k.startswith("embed")]
+        for k in params:
+            sd[k] = sd[k].detach().requires_grad_(True)
+        pre1, pre2 = sd["contrast.memory_v1"].clone(), sd["contrast.memory_v2"].clone()
+        pre_params = sd["contrast.params"].clone()
+        np.random.seed(int(g.np(p + "np_seed")))
+        loss, out_s, out_t, sel = so.crd_loss_v3(
+            sd, float(g.np(p + "epoch")), f_s, f_t, g.t(p + "idx"), g.t(p + "contrast_idx"), c["n"], P2=c["P2"],
+            K2=c["K2"], select_pos_mode=c["mode"], select_neg_pairs=c["select_neg_pairs"], sample_KD=c["sample_KD"])
+        (loss * g.t(p + "G").reshape(loss.shape)).sum().backward()
+        assert rel_err(loss.reshape(-1), g.t(p + "loss")) < FLOAT_TOL
+        assert out_s.shape == g.t(p + "out_v1").shape
+        assert rel_err(out_s, g.t(p + "out_v1")) < FLOAT_TOL and rel_err(out_t, g.t(p + "out_v2")) < FLOAT_TOL
+        assert rel_err(f_s.grad, g.t(p + "grad_f_s")) < FLOAT_TOL
+        assert rel_err(f_t.grad, g.t(p + "grad_f_t")) < FLOAT_TOL
+        for k in params:
+            assert rel_err(sd[k].grad, g.t(p + "grad." + k)) < 1e-5, k
+        assert rel_err(sd["contrast.params"], g.t(p + "params")) < FLOAT_TOL
+        for bank, pre in (("memory_v1", pre1), ("memory_v2", pre2)):
+            got = sd["contrast." + bank]
+            assert rel_err(got, g.t(p + bank)) < FLOAT_TOL
+            changed = (got != pre).any(dim=1).nonzero().flatten().tolist()
+            assert sorted(changed) == sorted(g.t(p + "idx").tolist())
+        # integer work: column 0 is the exact positive, positives come from the first P columns, negatives from the rest
+        assert (sel[:, 0] == 0).all() and (sel[:, :c["P2"]] < c["P"]).all() and (sel[:, c["P2"]:] >= c["P"]).all()
+        # closed form (second oracle; what the fused CUDA kernel evaluates) vs the reference's autograd
+        if c["sample_KD"] == "False" and pre_params[2].item() > 0:
+            v1 = co.embed_forward(g.t(p + "f_s"), {k: v.detach() for k, v in sd.items()}, "embed_s.")
+            v2 = co.embed_forward(g.t(p + "f_t"), {k: v.detach() for k, v in sd.items()}, "embed_t.")
+            rows = g.t(p + "contrast_idx").gather(1, sel)
+            B, cols = rows.shape
+            r1 = pre1.index_select(0, rows.reshape(-1)).view(B, cols, -1)
+            r2 = pre2.index_select(0, rows.reshape(-1)).view(B, cols, -1)
+            cf, _, _ = so.closed_form_multi_pos(r1, r2, v1, v2, pre_params[1].item(), pre_params[2].item(),
+                                                pre_params[3].item(), c["n"], c["P2"])
+            assert abs(cf.item() - g.t(p + "loss").item()) < 1e-5 * abs(g.t(p + "loss").item())
