@@ -82,6 +82,29 @@ int mml_crd_fused_loss_grad(
     float* out_v1, float* out_v2,
     void* workspace, size_t workspace_bytes, void* stream);
 
+/* Multi-positive form of mml_crd_fused_loss_grad for the reference's selection variant (5-arg CRDLoss,
+ * CL_utils/CRD_loss.py:153-175 with ContrastLoss_v2 :221-241, sample_KD == "False"): the first `n_pos` columns of
+ * every dense idx[B, cols] row are positives, the remaining m = cols - n_pos are negatives;
+ *   loss = -(1/B) * [ (1/n_pos) * sum_{b,p<n_pos} log(x/(x+c)) + sum_{b,k>=n_pos} log(m*Pn/(x+c)) ],  c = m*Pn + 1e-7
+ * summed over both sides, plus dL/dv1, dL/dv2 in closed form.  n_pos = 1 is bit-identical to
+ * mml_crd_fused_loss_grad with nce_k = cols - 1.  Workspace: mml_crd_workspace_bytes(B, cols, D).            */
+int mml_crd_fused_loss_grad_multipos(
+    const float* bank1, const float* bank2, int64_t n_rows, int32_t D,
+    const float* v1, const float* v2,
+    const void* idx, int32_t idx_bytes, int64_t B, int64_t cols, int64_t n_pos,
+    float T, const float* Z, int64_t n_data,
+    float* loss, float* grad_v1, float* grad_v2, float* out_v1, float* out_v2,
+    void* workspace, size_t workspace_bytes, void* stream);
+
+/* Relation gap of ContrastMemory_v3 (CL_utils/memory_new.py:288-292,303,342), the quantity its positive / negative
+ * selection sorts by:  diff[b,k] = cos(bank1[idx[b,k]], v1[b]) - cos(bank2[idx[b,k]], v2[b])   for dense idx[B, cols].
+ * One pass over the rows; nothing of size [B, cols, D] is written.                                           */
+int mml_crd_relation_diff(
+    const float* bank1, const float* bank2, int64_t n_rows, int32_t D,
+    const float* v1, const float* v2,
+    const void* idx, int32_t idx_bytes, int64_t B, int64_t cols,
+    float* diff, void* stream);
+
 /* Scores only (ContrastMemory.forward :41-49 [+ :62-63 when Z != NULL]).
  *   Z == NULL : out = exp(dot/T) (raw);  Z != NULL: out = exp(dot/T)/Z.
  *   sums      float[4] or NULL: {0, 0, sum raw side1, sum raw side2}
@@ -214,7 +237,10 @@ int mml_alias_select(const int64_t* alias, const int64_t* kk, const float* b, in
  *   W          float[N, Kk] = encoder1[0].weight, Kk = (d1+1)(d2+1)(d3+1 | 1), row-major
  *   m          dropout multiplier of `post_fusion_dropout`: 0 or 1/(1-p'), a pure function of
  *              (seed, b, k) (counter-based hash; p' = round(p*65536)/65536); identity when
- *              training == 0 or drop_p == 0.
+ *              training == 0 or drop_p == 0.  The effective seed is `seed ^ *seed_dev` when `seed_dev`
+ *              (a DEVICE uint64, may be NULL) is given: a launch captured in a CUDA graph freezes `seed`
+ *              but re-reads `*seed_dev` on every replay, so each replay can draw a fresh mask.  Forward,
+ *              dgrad and wgrad of one step must see the same pair.
  * ------------------------------------------------------------------------- */
 
 /* Tensor-core path (tcgen05 kind::tf32, A generated into TMEM, W streamed by TMA).
@@ -232,7 +258,7 @@ int     mml_kron_fwd_supported(int64_t B, int32_t N, int32_t d1, int32_t d2, int
 size_t  mml_kron_fwd_workspace_bytes(int64_t B, int32_t N, int32_t d1, int32_t d2, int32_t d3);
 int     mml_kron_linear_fwd(const float* f1, const float* f2, const float* f3, int64_t B,
                             int32_t d1, int32_t d2, int32_t d3, const int32_t* table, const float* Wp,
-                            const float* bias, int32_t N, float drop_p, uint64_t seed, int32_t training,
+                            const float* bias, int32_t N, float drop_p, uint64_t seed, const uint64_t* seed_dev, int32_t training,
                             float* y, void* workspace, size_t workspace_bytes, void* stream);
 
 /* Weight gradient on the tensor cores (same K permutation / chunk table as the forward):
@@ -243,7 +269,7 @@ int     mml_kron_wgrad_supported(int64_t B, int32_t N, int32_t d1, int32_t d2, i
 size_t  mml_kron_wgrad_workspace_bytes(int64_t B, int32_t N, int32_t d1, int32_t d2, int32_t d3);
 int     mml_kron_linear_wgrad(const float* f1, const float* f2, const float* f3, int64_t B,
                               int32_t d1, int32_t d2, int32_t d3, const int32_t* table, const float* dy,
-                              int32_t N, float drop_p, uint64_t seed, int32_t training, float* dW,
+                              int32_t N, float drop_p, uint64_t seed, const uint64_t* seed_dev, int32_t training, float* dW,
                               void* workspace, size_t workspace_bytes, void* stream);
 
 /* Factor gradients on the tensor cores.  dA = m * (dy W) is accumulated tile by tile in TMEM
@@ -258,7 +284,7 @@ int     mml_kron_pack_weight_t(const float* W, int32_t N, int32_t d1, int32_t d2
 size_t  mml_kron_dgrad_workspace_bytes(int64_t B, int32_t N, int32_t d1, int32_t d2, int32_t d3);
 int     mml_kron_linear_dgrad(const float* f1, const float* f2, const float* f3, int64_t B,
                               int32_t d1, int32_t d2, int32_t d3, const int32_t* table, const float* WpT,
-                              const float* dy, int32_t N, float drop_p, uint64_t seed, int32_t training,
+                              const float* dy, int32_t N, float drop_p, uint64_t seed, const uint64_t* seed_dev, int32_t training,
                               float* df1, float* df2, float* df3,
                               void* workspace, size_t workspace_bytes, void* stream);
 
@@ -268,11 +294,11 @@ int     mml_kron_linear_dgrad(const float* f1, const float* f2, const float* f3,
  *             the appended 1 receives no gradient.                                         */
 int mml_kron_linear_fwd_simt(const float* f1, const float* f2, const float* f3, int64_t B,
                              int32_t d1, int32_t d2, int32_t d3, const float* W, const float* bias,
-                             int32_t N, float drop_p, uint64_t seed, int32_t training, float* y,
+                             int32_t N, float drop_p, uint64_t seed, const uint64_t* seed_dev, int32_t training, float* y,
                              void* stream);
 int mml_kron_linear_bwd_simt(const float* f1, const float* f2, const float* f3, int64_t B,
                              int32_t d1, int32_t d2, int32_t d3, const float* W, const float* dy,
-                             int32_t N, float drop_p, uint64_t seed, int32_t training,
+                             int32_t N, float drop_p, uint64_t seed, const uint64_t* seed_dev, int32_t training,
                              float* df1, float* df2, float* df3, float* dW, void* stream);
 
 #ifdef __cplusplus

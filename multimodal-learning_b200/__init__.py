@@ -1,7 +1,8 @@
 """multimodal-learning_b200: B200-native (sm_100a) fusion + CRD distillation hot path.
 
 Drop-in mirrors of the reference's modules (CityU-AIM-Group/MultiModal-learning,
-`MICCAI-2022/fusion.py`, `MICCAI-2022/CL_utils/CRD_criterion.py`, `MICCAI-2022/KD_loss.py`)
+`MICCAI-2022/fusion.py`, `MICCAI-2022/CL_utils/CRD_criterion.py`, `CL_utils/CRD_loss.py`, `CL_utils/memory_new.py`,
+`MICCAI-2022/KD_loss.py`)
 over hand-written CUDA kernels reached through the C ABI in `include/mml_b200.h`.
 The directory name has a hyphen (task-mandated); import it as `multimodal_learning_b200`
 (the repo-root shim `multimodal_learning_b200.py` registers it), or put
@@ -10,7 +11,10 @@ The directory name has a hyphen (task-mandated); import it as `multimodal_learni
 """
 from . import _cabi
 from .crd import (AliasMethod, ContrastLoss, ContrastMemory, CRDLoss, Embed, Normalize)
+from . import crd_select
+from .crd_select import ContrastLoss_v2, ContrastMemory_v2, ContrastMemory_v3
 from .fusion import BilinearFusion, TrilinearFusion_A, TrilinearFusion_B, init_max_weights, kron_linear
+from .graphed import GraphedTrainStep
 from .kd_loss import DistillKL
 
-__all__ = ["BilinearFusion", "TrilinearFusion_A", "TrilinearFusion_B", "init_max_weights", "kron_linear", "AliasMethod", "ContrastLoss", "ContrastMemory", "CRDLoss", "Embed", "Normalize", "DistillKL", "_cabi"]
+__all__ = ["BilinearFusion", "TrilinearFusion_A", "TrilinearFusion_B", "init_max_weights", "kron_linear", "AliasMethod", "ContrastLoss", "ContrastMemory", "CRDLoss", "Embed", "Normalize", "DistillKL", "GraphedTrainStep", "crd_select", "ContrastLoss_v2", "ContrastMemory_v2", "ContrastMemory_v3", "_cabi"]

@@ -24,6 +24,10 @@ _SIGNATURES = {
     "mml_crd_fused_loss_grad": (ctypes.c_int, [
         _P, _P, c_int64, c_int32, _P, _P, _P, c_int32, _P, _P, c_int64, c_int64,
         c_float, _P, c_int64, c_int64, c_int64, _P, _P, _P, _P, _P, _P, _P, c_size_t, _P]),
+    "mml_crd_fused_loss_grad_multipos": (ctypes.c_int, [
+        _P, _P, c_int64, c_int32, _P, _P, _P, c_int32, c_int64, c_int64, c_int64,
+        c_float, _P, c_int64, _P, _P, _P, _P, _P, _P, c_size_t, _P]),
+    "mml_crd_relation_diff": (ctypes.c_int, [_P, _P, c_int64, c_int32, _P, _P, _P, c_int32, c_int64, c_int64, _P, _P]),
     "mml_crd_scores": (ctypes.c_int, [
         _P, _P, c_int64, c_int32, _P, _P, _P, c_int32, _P, c_int64, c_int64,
         c_float, _P, _P, _P, _P, _P, _P, c_size_t, _P]),
@@ -55,24 +59,24 @@ _SIGNATURES = {
     "mml_kron_fwd_supported": (ctypes.c_int, [c_int64, c_int32, c_int32, c_int32, c_int32]),
     "mml_kron_fwd_workspace_bytes": (c_size_t, [c_int64, c_int32, c_int32, c_int32, c_int32]),
     "mml_kron_linear_fwd": (ctypes.c_int, [
-        _P, _P, _P, c_int64, c_int32, c_int32, c_int32, _P, _P, _P, c_int32, c_float, ctypes.c_uint64, c_int32,
+        _P, _P, _P, c_int64, c_int32, c_int32, c_int32, _P, _P, _P, c_int32, c_float, ctypes.c_uint64, _P, c_int32,
         _P, _P, c_size_t, _P]),
     "mml_kron_wgrad_supported": (ctypes.c_int, [c_int64, c_int32, c_int32, c_int32, c_int32]),
     "mml_kron_wgrad_workspace_bytes": (c_size_t, [c_int64, c_int32, c_int32, c_int32, c_int32]),
     "mml_kron_linear_wgrad": (ctypes.c_int, [
-        _P, _P, _P, c_int64, c_int32, c_int32, c_int32, _P, _P, c_int32, c_float, ctypes.c_uint64, c_int32,
+        _P, _P, _P, c_int64, c_int32, c_int32, c_int32, _P, _P, c_int32, c_float, ctypes.c_uint64, _P, c_int32,
         _P, _P, c_size_t, _P]),
     "mml_kron_dgrad_supported": (ctypes.c_int, [c_int64, c_int32, c_int32, c_int32, c_int32]),
     "mml_kron_packed_t_floats": (c_int64, [c_int32, c_int32, c_int32, c_int32]),
     "mml_kron_pack_weight_t": (ctypes.c_int, [_P, c_int32, c_int32, c_int32, c_int32, _P, _P, _P]),
     "mml_kron_dgrad_workspace_bytes": (c_size_t, [c_int64, c_int32, c_int32, c_int32, c_int32]),
     "mml_kron_linear_dgrad": (ctypes.c_int, [
-        _P, _P, _P, c_int64, c_int32, c_int32, c_int32, _P, _P, _P, c_int32, c_float, ctypes.c_uint64, c_int32,
+        _P, _P, _P, c_int64, c_int32, c_int32, c_int32, _P, _P, _P, c_int32, c_float, ctypes.c_uint64, _P, c_int32,
         _P, _P, _P, _P, c_size_t, _P]),
     "mml_kron_linear_fwd_simt": (ctypes.c_int, [
-        _P, _P, _P, c_int64, c_int32, c_int32, c_int32, _P, _P, c_int32, c_float, ctypes.c_uint64, c_int32, _P, _P]),
+        _P, _P, _P, c_int64, c_int32, c_int32, c_int32, _P, _P, c_int32, c_float, ctypes.c_uint64, _P, c_int32, _P, _P]),
     "mml_kron_linear_bwd_simt": (ctypes.c_int, [
-        _P, _P, _P, c_int64, c_int32, c_int32, c_int32, _P, _P, c_int32, c_float, ctypes.c_uint64, c_int32,
+        _P, _P, _P, c_int64, c_int32, c_int32, c_int32, _P, _P, c_int32, c_float, ctypes.c_uint64, _P, c_int32,
         _P, _P, _P, _P, _P]),
 }
 

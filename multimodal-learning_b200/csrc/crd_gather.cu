@@ -54,6 +54,8 @@ struct GatherArgs {
   float inv_TB;             // 1 / (T * batch_norm)
   float nce_c;              // fp32(m*Pn + eps)     CRD_criterion.py:208,212
   float nce_kp;             // fp32(m*Pn)           CRD_criterion.py:212
+  int64_t npos;             // leading columns of a segment that are positives (1 = CRD_criterion.py; P2 = CRD_loss.py:221-241)
+  float pos_w;              // weight of a positive's loss term: 1 / npos (ContrastLoss_v2 averages over the P positives)
   // peer mode (row-sharded bank, indices pulled over NVLink): anchor b = (source rank s, local anchor bl);
   // CTA (chunk c, b) reads peer_ids[s][(bl*chunks + c)*peer_stride ..] of length peer_cnt[s][bl*chunks + c]
   int32_t peer_world;       // 0 = off
@@ -128,8 +130,9 @@ __device__ __forceinline__ float score_row(const GatherArgs& a, float dot, float
     const float num_l = is_pos ? x : a.nce_kp;
     const float term = logf(num_l / denom);          // log_D1 / log_D0, :208,212
     const float num_g = is_pos ? -a.nce_c : x;       // dL/dx * x  (times 1/(T*bsz) below)
-    g = valid ? (num_g / denom) * a.inv_TB : 0.f;
-    loss_acc += valid ? term : 0.f;
+    const float w = is_pos ? a.pos_w : 1.f;          // exactly 1 for the single-positive criterion
+    g = valid ? (num_g / denom) * a.inv_TB * w : 0.f;
+    loss_acc += valid ? term * w : 0.f;
   } else {
     sum_acc += valid ? e : 0.f;
   }
@@ -298,7 +301,7 @@ __global__ void __launch_bounds__(kCtaThreads, MINB) crd_gather_kernel(const Gat
         for (int t = 1; t < NSCAL; ++t) mine = (s == t) ? p[t] : mine;
         const int64_t colm = cb + it * ROWS_PER_IT + (s >> 1) * 4 + q;
         const bool validm = (s < NSCAL) && (colm < c1);
-        const bool is_pos = has_pos && (colm == 0);
+        const bool is_pos = has_pos && (colm < a.npos);
         float x;
         const float g = score_row<MODE>(a, mine, my_inv_Z, validm, is_pos, loss_acc, sum_acc, x);
         if (validm && a.out1 != nullptr) {
@@ -422,7 +425,7 @@ __global__ void __launch_bounds__(kCtaThreads) crd_gather_generic_kernel(const G
         d_b1 += __shfl_xor_sync(kFullMask, d_b1, off);
         d_b2 += __shfl_xor_sync(kFullMask, d_b2, off);
       }
-      const bool is_pos = has_pos && (col == 0);
+      const bool is_pos = has_pos && (col < a.npos);
       float x1, x2;
       g2 = score_row<MODE>(a, d_b1, inv_Z2, true, is_pos, loss2, sum2, x2);
       g1 = score_row<MODE>(a, d_b2, inv_Z1, true, is_pos, loss1, sum1, x1);
@@ -621,10 +624,10 @@ extern "C" size_t mml_crd_workspace_bytes(int64_t B, int64_t cols, int32_t D) {
   return ws_bytes(B, cols, D);
 }
 
-extern "C" int mml_crd_fused_loss_grad(
+static int fused_loss_grad_impl(
     const float* bank1, const float* bank2, int64_t n_rows, int32_t D, const float* v1, const float* v2,
     const void* idx, int32_t idx_bytes, const int64_t* seg_ptr, const uint8_t* pos_flag, int64_t B, int64_t cols, float T,
-    const float* Z, int64_t n_data, int64_t nce_k, int64_t batch_norm, float* loss, float* sums, float* grad_v1,
+    const float* Z, int64_t n_data, int64_t nce_k, int64_t n_pos, int64_t batch_norm, float* loss, float* sums, float* grad_v1,
     float* grad_v2, float* out_v1, float* out_v2, void* workspace, size_t workspace_bytes, void* stream) {
   int rc = common_checks(bank1, bank2, n_rows, D, idx, idx_bytes, B, cols, workspace, workspace_bytes);
   if (rc != MML_OK) return rc;
@@ -646,6 +649,8 @@ extern "C" int mml_crd_fused_loss_grad(
   const double Pn = 1.0 / static_cast<double>(n_data);                       // :204
   a.nce_kp = static_cast<float>(static_cast<double>(nce_k) * Pn);            // fill_(m*Pn), :212
   a.nce_c = static_cast<float>(static_cast<double>(nce_k) * Pn + 1e-7);      // add(m*Pn+eps), :208,212
+  a.npos = n_pos;
+  a.pos_w = n_pos == 1 ? 1.0f : 1.0f / static_cast<float>(n_pos);
   rc = launch_gather<kFused>(a, B, st);
   if (rc != MML_OK) return rc;
   crd_finish_anchor_kernel<<<static_cast<unsigned>(B), 128, 0, st>>>(w.part_grad, w.part_scal, seg_ptr, cols, p.chunk_cols,
@@ -658,6 +663,28 @@ extern "C" int mml_crd_fused_loss_grad(
     rc = check_launch("crd_finish_total_kernel");
   }
   return rc;
+}
+
+extern "C" int mml_crd_fused_loss_grad(
+    const float* bank1, const float* bank2, int64_t n_rows, int32_t D, const float* v1, const float* v2,
+    const void* idx, int32_t idx_bytes, const int64_t* seg_ptr, const uint8_t* pos_flag, int64_t B, int64_t cols, float T,
+    const float* Z, int64_t n_data, int64_t nce_k, int64_t batch_norm, float* loss, float* sums, float* grad_v1,
+    float* grad_v2, float* out_v1, float* out_v2, void* workspace, size_t workspace_bytes, void* stream) {
+  return fused_loss_grad_impl(bank1, bank2, n_rows, D, v1, v2, idx, idx_bytes, seg_ptr, pos_flag, B, cols, T, Z, n_data, nce_k,
+                              1, batch_norm, loss, sums, grad_v1, grad_v2, out_v1, out_v2, workspace, workspace_bytes, stream);
+}
+
+extern "C" int mml_crd_fused_loss_grad_multipos(
+    const float* bank1, const float* bank2, int64_t n_rows, int32_t D, const float* v1, const float* v2,
+    const void* idx, int32_t idx_bytes, int64_t B, int64_t cols, int64_t n_pos, float T, const float* Z, int64_t n_data,
+    float* loss, float* grad_v1, float* grad_v2, float* out_v1, float* out_v2, void* workspace, size_t workspace_bytes,
+    void* stream) {
+  MML_REQUIRE(n_pos >= 1 && n_pos <= cols, MML_ERR_INVALID_ARG, "crd_fused_multipos: n_pos %lld outside [1, cols=%lld]",
+              (long long)n_pos, (long long)cols);
+  // ContrastLoss_v2 (CRD_loss.py:221-241): m = number of negative columns = cols - P
+  return fused_loss_grad_impl(bank1, bank2, n_rows, D, v1, v2, idx, idx_bytes, nullptr, nullptr, B, cols, T, Z, n_data,
+                              cols - n_pos, n_pos, B, loss, nullptr, grad_v1, grad_v2, out_v1, out_v2, workspace,
+                              workspace_bytes, stream);
 }
 
 extern "C" int mml_crd_scores(const float* bank1, const float* bank2, int64_t n_rows, int32_t D, const float* v1,
@@ -784,6 +811,7 @@ extern "C" int mml_crd_fused_loss_grad_peer(
   const double Pn = 1.0 / static_cast<double>(n_data);
   a.nce_kp = static_cast<float>(static_cast<double>(nce_k) * Pn);
   a.nce_c = static_cast<float>(static_cast<double>(nce_k) * Pn + 1e-7);
+  a.npos = 1; a.pos_w = 1.0f;
   rc = launch_gather<kFused>(a, B, st);
   if (rc != MML_OK) return rc;
   crd_finish_anchor_kernel<<<static_cast<unsigned>(B), 128, 0, st>>>(w.part_grad, w.part_scal, nullptr, a.cols, p.chunk_cols,

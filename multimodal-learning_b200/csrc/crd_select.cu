@@ -1,0 +1,185 @@
+// Selection variant of the contrast memory (reference: MICCAI-2022/CL_utils/memory_new.py:225-397, ContrastMemory_v3).
+//
+// Before it scores anything, the variant ranks the K+P sampled columns of every anchor by the gap between two cosine
+// "relations" (memory_new.py:288-292):
+//     t_relation[b,k] = cos(memory_v1[idx[b,k]], v1[b])        s_relation[b,k] = cos(memory_v2[idx[b,k]], v2[b])
+// and keeps P2 positives / K2 negatives by the order of  diff = t_relation - s_relation  (:298-357).  The reference
+// materialises both gathered [B, K+P, D] tensors, their normalised copies and two bmm outputs; here ONE pass over the
+// rows (same 8-lanes-per-row, 128-bit streaming loads as K4 in crd_gather.cu) emits only diff[B, K+P].
+// HBM-bound: algorithmic bytes = 2*B*(K+P)*D*4 (rows) + B*(K+P)*(8 + 4) (indices in, diff out).
+#include <math.h>
+
+#include "common.cuh"
+
+namespace mml {
+namespace {
+
+constexpr int kThreads = 128;
+constexpr int kWarps = kThreads / 32;
+
+struct RelArgs {
+  const float* bank1;
+  const float* bank2;
+  const float* v1;
+  const float* v2;
+  const int64_t* idx64;
+  const int32_t* idx32;
+  float* diff;
+  int64_t cols;
+  int32_t D;
+  int32_t chunk_cols;
+};
+
+template <int VPL, int U>
+__global__ void __launch_bounds__(kThreads) crd_relation_kernel(const RelArgs a) {
+  constexpr int D = 32 * VPL;
+  constexpr int ROWS_PER_IT = 4 * U;
+  const int b = blockIdx.y;
+  const int64_t c0 = static_cast<int64_t>(blockIdx.x) * a.chunk_cols;
+  const int64_t c1 = min(c0 + static_cast<int64_t>(a.chunk_cols), a.cols);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int s = lane & 7, q = lane >> 3;
+
+  float4 fv1[VPL], fv2[VPL];
+  float n1 = 0.f, n2 = 0.f;
+#pragma unroll
+  for (int j = 0; j < VPL; ++j) {
+    fv1[j] = __ldg(reinterpret_cast<const float4*>(a.v1 + static_cast<int64_t>(b) * D) + j * 8 + s);
+    fv2[j] = __ldg(reinterpret_cast<const float4*>(a.v2 + static_cast<int64_t>(b) * D) + j * 8 + s);
+    n1 = dot4(fv1[j], fv1[j], n1);
+    n2 = dot4(fv2[j], fv2[j], n2);
+  }
+#pragma unroll
+  for (int off = 1; off < 8; off <<= 1) {
+    n1 += __shfl_xor_sync(kFullMask, n1, off);
+    n2 += __shfl_xor_sync(kFullMask, n2, off);
+  }
+  const float nv1 = sqrtf(n1), nv2 = sqrtf(n2);          // torch.norm(v, dim=1), :289,292
+
+  const int64_t base = static_cast<int64_t>(b) * a.cols;
+  for (int64_t cb = c0 + warp * 32; cb < c1; cb += kWarps * 32) {
+    const int64_t mycol = cb + lane;
+    int32_t myrow = 0;
+    if (mycol < c1) myrow = a.idx32 ? a.idx32[base + mycol] : static_cast<int32_t>(a.idx64[base + mycol]);
+    const int n_it = (static_cast<int>(min(static_cast<int64_t>(32), c1 - cb)) + ROWS_PER_IT - 1) / ROWS_PER_IT;
+    for (int it = 0; it < n_it; ++it) {
+      float4 r1[U][VPL], r2[U][VPL];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int32_t row = __shfl_sync(kFullMask, myrow, it * ROWS_PER_IT + u * 4 + q);
+        const float* p1 = a.bank1 + static_cast<int64_t>(row) * D + s * 4;
+        const float* p2 = a.bank2 + static_cast<int64_t>(row) * D + s * 4;
+#pragma unroll
+        for (int j = 0; j < VPL; ++j) r1[u][j] = ldg_stream_f4(p1 + j * 32);
+#pragma unroll
+        for (int j = 0; j < VPL; ++j) r2[u][j] = ldg_stream_f4(p2 + j * 32);
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        float t_dot = 0.f, t_sq = 0.f, s_dot = 0.f, s_sq = 0.f;
+#pragma unroll
+        for (int j = 0; j < VPL; ++j) {
+          t_dot = dot4(r1[u][j], fv1[j], t_dot);       // bank-1 row . v1   (:288)
+          t_sq = dot4(r1[u][j], r1[u][j], t_sq);
+          s_dot = dot4(r2[u][j], fv2[j], s_dot);       // bank-2 row . v2   (:291)
+          s_sq = dot4(r2[u][j], r2[u][j], s_sq);
+        }
+#pragma unroll
+        for (int off = 1; off < 8; off <<= 1) {
+          t_dot += __shfl_xor_sync(kFullMask, t_dot, off);
+          t_sq += __shfl_xor_sync(kFullMask, t_sq, off);
+          s_dot += __shfl_xor_sync(kFullMask, s_dot, off);
+          s_sq += __shfl_xor_sync(kFullMask, s_sq, off);
+        }
+        const int64_t col = cb + it * ROWS_PER_IT + u * 4 + q;
+        if (s == 0 && col < c1) a.diff[base + col] = t_dot / (sqrtf(t_sq) * nv1) - s_dot / (sqrtf(s_sq) * nv2);
+      }
+    }
+  }
+}
+
+// Any-D path: one warp per column.
+__global__ void __launch_bounds__(kThreads) crd_relation_generic_kernel(const RelArgs a) {
+  const int D = a.D;
+  const int b = blockIdx.y;
+  const int64_t c0 = static_cast<int64_t>(blockIdx.x) * a.chunk_cols;
+  const int64_t c1 = min(c0 + static_cast<int64_t>(a.chunk_cols), a.cols);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const float* v1 = a.v1 + static_cast<int64_t>(b) * D;
+  const float* v2 = a.v2 + static_cast<int64_t>(b) * D;
+  float n1 = 0.f, n2 = 0.f;
+  for (int i = lane; i < D; i += 32) {
+    n1 = fmaf(v1[i], v1[i], n1);
+    n2 = fmaf(v2[i], v2[i], n2);
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    n1 += __shfl_xor_sync(kFullMask, n1, off);
+    n2 += __shfl_xor_sync(kFullMask, n2, off);
+  }
+  const float nv1 = sqrtf(n1), nv2 = sqrtf(n2);
+  const int64_t base = static_cast<int64_t>(b) * a.cols;
+  for (int64_t col = c0 + warp; col < c1; col += kWarps) {
+    const int64_t row = a.idx32 ? static_cast<int64_t>(a.idx32[base + col]) : a.idx64[base + col];
+    const float* p1 = a.bank1 + row * D;
+    const float* p2 = a.bank2 + row * D;
+    float t_dot = 0.f, t_sq = 0.f, s_dot = 0.f, s_sq = 0.f;
+    for (int i = lane; i < D; i += 32) {
+      const float x1 = __ldg(p1 + i), x2 = __ldg(p2 + i);
+      t_dot = fmaf(x1, v1[i], t_dot);
+      t_sq = fmaf(x1, x1, t_sq);
+      s_dot = fmaf(x2, v2[i], s_dot);
+      s_sq = fmaf(x2, x2, s_sq);
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      t_dot += __shfl_xor_sync(kFullMask, t_dot, off);
+      t_sq += __shfl_xor_sync(kFullMask, t_sq, off);
+      s_dot += __shfl_xor_sync(kFullMask, s_dot, off);
+      s_sq += __shfl_xor_sync(kFullMask, s_sq, off);
+    }
+    if (lane == 0) a.diff[base + col] = t_dot / (sqrtf(t_sq) * nv1) - s_dot / (sqrtf(s_sq) * nv2);
+  }
+}
+
+}  // namespace
+}  // namespace mml
+
+using namespace mml;
+
+extern "C" int mml_crd_relation_diff(const float* bank1, const float* bank2, int64_t n_rows, int32_t D, const float* v1,
+                                     const float* v2, const void* idx, int32_t idx_bytes, int64_t B, int64_t cols,
+                                     float* diff, void* stream) {
+  MML_REQUIRE(bank1 && bank2 && v1 && v2 && idx && diff, MML_ERR_INVALID_ARG, "crd_relation_diff: null pointer argument");
+  MML_REQUIRE(idx_bytes == 8 || idx_bytes == 4, MML_ERR_INVALID_ARG, "crd_relation_diff: idx_bytes must be 8 or 4");
+  MML_REQUIRE(B >= 0 && cols >= 1 && n_rows >= 1 && n_rows < (1LL << 31), MML_ERR_INVALID_ARG, "crd_relation_diff: bad sizes");
+  MML_REQUIRE(D >= 1 && D <= 2048, MML_ERR_UNSUPPORTED, "crd_relation_diff: feature dim %d outside [1, 2048]", D);
+  MML_REQUIRE(B <= 65535, MML_ERR_UNSUPPORTED, "crd_relation_diff: batch %lld > 65535 anchors per call", (long long)B);
+  if (B == 0) return MML_OK;
+  const bool fast = (D == 32 || D == 64 || D == 128 || D == 256);
+  if (fast)
+    MML_REQUIRE(aligned16(bank1) && aligned16(bank2) && aligned16(v1) && aligned16(v2), MML_ERR_INVALID_ARG,
+                "crd_relation_diff: banks and v1/v2 must be 16-byte aligned");
+  RelArgs a{};
+  a.bank1 = bank1; a.bank2 = bank2; a.v1 = v1; a.v2 = v2; a.diff = diff; a.cols = cols; a.D = D;
+  a.idx64 = idx_bytes == 8 ? static_cast<const int64_t*>(idx) : nullptr;
+  a.idx32 = idx_bytes == 4 ? static_cast<const int32_t*>(idx) : nullptr;
+  // >= ~8 waves of 148 SMs x 4 CTAs when the problem allows; chunks of whole 128-column CTA passes
+  int64_t chunks = (148LL * 4 * 8 + B - 1) / B;
+  const int64_t max_chunks = (cols + 127) / 128;
+  if (chunks > max_chunks) chunks = max_chunks;
+  if (chunks < 1) chunks = 1;
+  int64_t cc = ((cols + chunks - 1) / chunks + 127) / 128 * 128;
+  chunks = (cols + cc - 1) / cc;
+  a.chunk_cols = static_cast<int32_t>(cc);
+  const dim3 grid(static_cast<unsigned>(chunks), static_cast<unsigned>(B));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  switch (fast ? D : 0) {
+    case 32: crd_relation_kernel<1, 4><<<grid, kThreads, 0, st>>>(a); break;
+    case 64: crd_relation_kernel<2, 4><<<grid, kThreads, 0, st>>>(a); break;
+    case 128: crd_relation_kernel<4, 2><<<grid, kThreads, 0, st>>>(a); break;
+    case 256: crd_relation_kernel<8, 1><<<grid, kThreads, 0, st>>>(a); break;
+    default: crd_relation_generic_kernel<<<grid, kThreads, 0, st>>>(a);
+  }
+  return check_launch("crd_relation_kernel");
+}

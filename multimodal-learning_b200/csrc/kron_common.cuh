@@ -32,9 +32,11 @@ struct KronDropout {
   float scale;        // 65536 / (65536 - thresh)
   uint32_t seed_lo, seed_hi;
   int64_t pairs_per_row;   // ceil(Kk / 2): one 32-bit hash serves two neighbouring k
+  const unsigned long long* seed_dev;   // optional DEVICE word xor-ed into the seed at run time: lets a captured CUDA graph
+                                        // draw a fresh mask on every replay (the host `seed` is frozen into the graph)
 };
 
-inline KronDropout make_kron_dropout(float p, uint64_t seed, int training, int32_t Kk) {
+inline KronDropout make_kron_dropout(float p, uint64_t seed, int training, int32_t Kk, const uint64_t* seed_dev = nullptr) {
   KronDropout d;
   double t = (training && p > 0.f) ? static_cast<double>(p) * 65536.0 + 0.5 : 0.0;
   if (t > 65535.0) t = 65535.0;
@@ -43,6 +45,7 @@ inline KronDropout make_kron_dropout(float p, uint64_t seed, int training, int32
   d.seed_lo = static_cast<uint32_t>(seed);
   d.seed_hi = static_cast<uint32_t>(seed >> 32);
   d.pairs_per_row = (static_cast<int64_t>(Kk) + 1) / 2;
+  d.seed_dev = (d.thresh != 0u) ? reinterpret_cast<const unsigned long long*>(seed_dev) : nullptr;
   return d;
 }
 
@@ -58,8 +61,19 @@ __host__ __device__ __forceinline__ uint32_t kron_hash(uint32_t lo, uint32_t hi,
   return h;
 }
 
+// effective 64-bit seed of this launch: host seed xor the optional device word
+__device__ __forceinline__ void kron_seed(const KronDropout& dr, uint32_t& lo, uint32_t& hi) {
+  lo = dr.seed_lo;
+  hi = dr.seed_hi;
+  if (dr.seed_dev != nullptr) {
+    const unsigned long long s = __ldg(dr.seed_dev);
+    lo ^= static_cast<uint32_t>(s);
+    hi ^= static_cast<uint32_t>(s >> 32);
+  }
+}
+
 // multiplier of A[b,k] under dropout: 0 or scale
-__device__ __forceinline__ float kron_keep(const KronDropout& dr, int64_t b, int32_t k) {
+__device__ __forceinline__ float kron_keep(const KronDropout& dr, int64_t b, int32_t k) {   // dr: kron_seed() already folded in
   if (dr.thresh == 0u) return 1.0f;
   const int64_t c = b * dr.pairs_per_row + (k >> 1);
   const uint32_t h = kron_hash(static_cast<uint32_t>(c), static_cast<uint32_t>(static_cast<uint64_t>(c) >> 32),

@@ -17,6 +17,8 @@ __global__ void __launch_bounds__(kThreads) kron_fwd_simt_kernel(
     KronShape s, KronDropout dr, const float* __restrict__ f1, const float* __restrict__ f2,
     const float* __restrict__ f3, int64_t B, const float* __restrict__ W, const float* __restrict__ bias, int32_t N,
     float* __restrict__ y) {
+  kron_seed(dr, dr.seed_lo, dr.seed_hi);
+  dr.seed_dev = nullptr;
   constexpr int BM = 64, BN = 64, BK = 16;
   __shared__ float As[BK][BM + 1];
   __shared__ float Ws[BK][BN + 1];
@@ -73,6 +75,8 @@ __global__ void __launch_bounds__(kThreads) kron_wgrad_simt_kernel(
     KronShape s, KronDropout dr, const float* __restrict__ f1, const float* __restrict__ f2,
     const float* __restrict__ f3, int64_t B, const float* __restrict__ dy, int32_t N, float* __restrict__ dW,
     int64_t rows_per_split, int use_atomic) {
+  kron_seed(dr, dr.seed_lo, dr.seed_hi);
+  dr.seed_dev = nullptr;
   constexpr int BM = 64, BN = 64, BK = 16;   // BM: n, BN: k, BK: batch rows per step
   __shared__ float Ds[BK][BM + 1];
   __shared__ float As[BK][BN + 1];
@@ -137,6 +141,8 @@ __global__ void __launch_bounds__(kThreads) kron_dgrad_simt_kernel(
     KronShape s, KronDropout dr, const float* __restrict__ f1, const float* __restrict__ f2,
     const float* __restrict__ f3, int64_t B, const float* __restrict__ W, const float* __restrict__ dy, int32_t N,
     float* __restrict__ df1, float* __restrict__ df2, float* __restrict__ df3) {
+  kron_seed(dr, dr.seed_lo, dr.seed_hi);
+  dr.seed_dev = nullptr;
   constexpr int BM = 32, BN = 64, BK = 16;   // BM: batch rows, BN: k, BK: n per step
   extern __shared__ float sm_df[];            // [BM][d1 + d2 + d3]
   __shared__ float Ds[BK][BM + 1];
@@ -236,13 +242,13 @@ using namespace mml;
 
 extern "C" int mml_kron_linear_fwd_simt(const float* f1, const float* f2, const float* f3, int64_t B, int32_t d1,
                                         int32_t d2, int32_t d3, const float* W, const float* bias, int32_t N,
-                                        float drop_p, uint64_t seed, int32_t training, float* y, void* stream) {
+                                        float drop_p, uint64_t seed, const uint64_t* seed_dev, int32_t training, float* y, void* stream) {
   int rc = check_shape(f1, f2, f3, B, d1, d2, d3, N);
   if (rc != MML_OK) return rc;
   MML_REQUIRE(W && y, MML_ERR_INVALID_ARG, "kron_fwd_simt: null pointer");
   if (B == 0) return MML_OK;
   const KronShape s = make_kron_shape(d1, d2, d3);
-  const KronDropout dr = make_kron_dropout(drop_p, seed, training, s.Kk);
+  const KronDropout dr = make_kron_dropout(drop_p, seed, training, s.Kk, seed_dev);
   const dim3 grid(static_cast<unsigned>((B + 63) / 64), (N + 63) / 64);
   kron_fwd_simt_kernel<<<grid, kThreads, 0, static_cast<cudaStream_t>(stream)>>>(s, dr, f1, f2, f3, B, W, bias, N, y);
   return check_launch("kron_fwd_simt_kernel");
@@ -250,7 +256,7 @@ extern "C" int mml_kron_linear_fwd_simt(const float* f1, const float* f2, const 
 
 extern "C" int mml_kron_linear_bwd_simt(const float* f1, const float* f2, const float* f3, int64_t B, int32_t d1,
                                         int32_t d2, int32_t d3, const float* W, const float* dy, int32_t N,
-                                        float drop_p, uint64_t seed, int32_t training, float* df1, float* df2,
+                                        float drop_p, uint64_t seed, const uint64_t* seed_dev, int32_t training, float* df1, float* df2,
                                         float* df3, float* dW, void* stream) {
   int rc = check_shape(f1, f2, f3, B, d1, d2, d3, N);
   if (rc != MML_OK) return rc;
@@ -260,7 +266,7 @@ extern "C" int mml_kron_linear_bwd_simt(const float* f1, const float* f2, const 
   if (B == 0) return MML_OK;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const KronShape s = make_kron_shape(d1, d2, d3);
-  const KronDropout dr = make_kron_dropout(drop_p, seed, training, s.Kk);
+  const KronDropout dr = make_kron_dropout(drop_p, seed, training, s.Kk, seed_dev);
   if (dW != nullptr) {
     const int tiles = ((s.Kk + 63) / 64) * ((N + 63) / 64);
     int64_t split = (148 * 2 + tiles - 1) / tiles;

@@ -48,6 +48,8 @@ struct TcArgs {
 
 template <bool kDropout>
 __global__ void __launch_bounds__(kThreadsTc, 1) kron_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const TcArgs a) {
+  uint32_t seed_lo = 0u, seed_hi = 0u;
+  if (kDropout) kron_seed(a.dr, seed_lo, seed_hi);
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // carve: B stages | scalars (transposed: [n_scal][128]) | chunk table | barriers | tmem base
   const uint32_t stage_bytes = static_cast<uint32_t>(a.Np) * 128u;
@@ -188,7 +190,7 @@ __global__ void __launch_bounds__(kThreadsTc, 1) kron_fwd_tc_kernel(const __grid
           const int klog = e1.y + (ebase + u) * e1.z;
           const int64_t cc = b * a.dr.pairs_per_row + (klog >> 1);
           const uint32_t h = kron_hash(static_cast<uint32_t>(cc), static_cast<uint32_t>(static_cast<uint64_t>(cc) >> 32),
-                                       a.dr.seed_lo, a.dr.seed_hi);
+                                       seed_lo, seed_hi);
           const uint32_t r16 = (klog & 1) ? (h >> 16) : (h & 0xffffu);
           x = (r16 >= a.dr.thresh) ? x : 0.f;
         }
@@ -379,7 +381,7 @@ extern "C" size_t mml_kron_fwd_workspace_bytes(int64_t B, int32_t N, int32_t d1,
 
 extern "C" int mml_kron_linear_fwd(const float* f1, const float* f2, const float* f3, int64_t B, int32_t d1, int32_t d2,
                                    int32_t d3, const int32_t* table, const float* Wp, const float* bias, int32_t N,
-                                   float drop_p, uint64_t seed, int32_t training, float* y, void* workspace,
+                                   float drop_p, uint64_t seed, const uint64_t* seed_dev, int32_t training, float* y, void* workspace,
                                    size_t workspace_bytes, void* stream) {
   MML_REQUIRE(f1 && f2 && table && Wp && y, MML_ERR_INVALID_ARG, "kron_linear_fwd: null pointer");
   MML_REQUIRE((d3 > 0) == (f3 != nullptr), MML_ERR_INVALID_ARG, "kron_linear_fwd: f3 and d3 must both be set or both be absent");
@@ -406,7 +408,7 @@ extern "C" int mml_kron_linear_fwd(const float* f1, const float* f2, const float
   a.nchunks = p.nchunks; a.chunks_per_split = p.chunks_per_split; a.ksplit = p.ksplit;
   a.n_scal = p.n_scal; a.stages = p.stages; a.tmem_cols = p.tmem_cols; a.table_in_smem = p.table_in_smem;
   a.idesc = make_idesc_tf32(kTileM, p.Np);
-  a.dr = make_kron_dropout(drop_p, seed, training, s.Kk);
+  a.dr = make_kron_dropout(drop_p, seed, training, s.Kk, seed_dev);
   const dim3 grid(static_cast<unsigned>((B + kTileM - 1) / kTileM), p.ksplit);
   if (a.dr.thresh != 0u) {
     MML_CUDA(cudaFuncSetAttribute(kron_fwd_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(p.smem)));

@@ -36,6 +36,8 @@ struct WgArgs {
 
 template <bool kDropout>
 __global__ void __launch_bounds__(kThreadsTc, 1) kron_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_dyT, const WgArgs a) {
+  uint32_t seed_lo = 0u, seed_hi = 0u;
+  if (kDropout) kron_seed(a.dr, seed_lo, seed_hi);
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t stage_bytes = static_cast<uint32_t>(a.Np) * 128u;
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -241,7 +243,7 @@ __global__ void __launch_bounds__(kThreadsTc, 1) kron_wgrad_tc_kernel(const __gr
         if (kDropout) {
           const int64_t cc = (b0 + bl) * a.dr.pairs_per_row + (my_klog >> 1);
           const uint32_t h = kron_hash(static_cast<uint32_t>(cc), static_cast<uint32_t>(static_cast<uint64_t>(cc) >> 32),
-                                       a.dr.seed_lo, a.dr.seed_hi);
+                                       seed_lo, seed_hi);
           const uint32_t r16 = (my_klog & 1) ? (h >> 16) : (h & 0xffffu);
           x = (r16 >= a.dr.thresh) ? x : 0.f;
         }
@@ -397,7 +399,7 @@ extern "C" size_t mml_kron_wgrad_workspace_bytes(int64_t B, int32_t N, int32_t d
 
 extern "C" int mml_kron_linear_wgrad(const float* f1, const float* f2, const float* f3, int64_t B, int32_t d1, int32_t d2,
                                      int32_t d3, const int32_t* table, const float* dy, int32_t N, float drop_p,
-                                     uint64_t seed, int32_t training, float* dW, void* workspace, size_t workspace_bytes,
+                                     uint64_t seed, const uint64_t* seed_dev, int32_t training, float* dW, void* workspace, size_t workspace_bytes,
                                      void* stream) {
   MML_REQUIRE(f1 && f2 && table && dy && dW && workspace, MML_ERR_INVALID_ARG, "kron_linear_wgrad: null pointer");
   MML_REQUIRE((d3 > 0) == (f3 != nullptr), MML_ERR_INVALID_ARG, "kron_linear_wgrad: f3 and d3 must both be set or both be absent");
@@ -428,7 +430,7 @@ extern "C" int mml_kron_linear_wgrad(const float* f1, const float* f2, const flo
   a.nblocks = p.nblocks; a.blocks_per_split = p.blocks_per_split;
   a.stages = p.stages; a.tmem_cols = p.tmem_cols;
   a.idesc = make_idesc_tf32(kTileM, p.Np);
-  a.dr = make_kron_dropout(drop_p, seed, training, s.Kk);
+  a.dr = make_kron_dropout(drop_p, seed, training, s.Kk, seed_dev);
   const dim3 grid(p.ktiles, p.bsplit);
   if (a.dr.thresh != 0u) {
     MML_CUDA(cudaFuncSetAttribute(kron_wgrad_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(p.smem)));
@@ -485,6 +487,8 @@ struct DgArgs {
 
 template <bool kDropout>
 __global__ void __launch_bounds__(kDgThreads, 1) kron_dgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_wT, const DgArgs a) {
+  uint32_t seed_lo = 0u, seed_hi = 0u;
+  if (kDropout) kron_seed(a.dr, seed_lo, seed_hi);
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* sm_b = smem;                                                              // [stages][16 KB]
@@ -674,7 +678,7 @@ __global__ void __launch_bounds__(kDgThreads, 1) kron_dgrad_tc_kernel(const __gr
             const int klog = e1.y + e * e1.z;
             const int64_t cc = b * a.dr.pairs_per_row + (klog >> 1);
             const uint32_t h = kron_hash(static_cast<uint32_t>(cc), static_cast<uint32_t>(static_cast<uint64_t>(cc) >> 32),
-                                         a.dr.seed_lo, a.dr.seed_hi);
+                                         seed_lo, seed_hi);
             const uint32_t r16 = (klog & 1) ? (h >> 16) : (h & 0xffffu);
             g = (r16 >= a.dr.thresh) ? g : 0.f;
           }
@@ -831,7 +835,7 @@ extern "C" size_t mml_kron_dgrad_workspace_bytes(int64_t B, int32_t N, int32_t d
 
 extern "C" int mml_kron_linear_dgrad(const float* f1, const float* f2, const float* f3, int64_t B, int32_t d1, int32_t d2,
                                      int32_t d3, const int32_t* table, const float* WpT, const float* dy, int32_t N,
-                                     float drop_p, uint64_t seed, int32_t training, float* df1, float* df2, float* df3,
+                                     float drop_p, uint64_t seed, const uint64_t* seed_dev, int32_t training, float* df1, float* df2, float* df3,
                                      void* workspace, size_t workspace_bytes, void* stream) {
   MML_REQUIRE(f1 && f2 && table && WpT && dy && df1 && df2 && workspace, MML_ERR_INVALID_ARG, "kron_linear_dgrad: null pointer");
   MML_REQUIRE((d3 > 0) == (f3 != nullptr) && (d3 > 0) == (df3 != nullptr), MML_ERR_INVALID_ARG,
@@ -856,7 +860,7 @@ extern "C" int mml_kron_linear_dgrad(const float* f1, const float* f2, const flo
   a.ktiles = p.ktiles; a.tiles_per_split = p.tiles_per_split;
   a.n_scal = p.n_scal; a.stages = p.stages; a.tmem_cols = p.tmem_cols; a.table_in_smem = p.table_in_smem;
   a.idesc = make_idesc_tf32(kTileM, kDgTileK);
-  a.dr = make_kron_dropout(drop_p, seed, training, s.Kk);
+  a.dr = make_kron_dropout(drop_p, seed, training, s.Kk, seed_dev);
   const dim3 grid(static_cast<unsigned>((B + kTileM - 1) / kTileM), p.ksplit);
   if (a.dr.thresh != 0u) {
     MML_CUDA(cudaFuncSetAttribute(kron_dgrad_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(p.smem)));

@@ -140,22 +140,26 @@ class _KronLinearFn(torch.autograd.Function):
         f3p = _cabi.dptr(fs[2]) if d3 > 0 else None
         w = weight.detach().contiguous()
         bptr = _cabi.dptr(bias.detach().contiguous()) if bias is not None else None
+        seed_t = seed if torch.is_tensor(seed) else None        # device word: fresh mask on every CUDA-graph replay
+        seed = 0 if seed_t is not None else int(seed)
+        sdev = _cabi.dptr(seed_t, torch.int64) if seed_t is not None else None
         tc_ok, nws = state.plan(B, N)
         if state.path == "auto" and tc_ok:
             state.ensure(weight, wkey)
             ws = torch.empty(nws, dtype=torch.uint8, device=dev)
             rc = lib.mml_kron_linear_fwd(_cabi.dptr(fs[0]), _cabi.dptr(fs[1]), f3p, B, d1, d2, d3, _cabi.dptr(state.table),
-                                         _cabi.dptr(state.packed), bptr, N, float(drop_p), int(seed), int(training),
+                                         _cabi.dptr(state.packed), bptr, N, float(drop_p), seed, sdev, int(training),
                                          _cabi.dptr(y), _cabi.dptr(ws), nws, st)
             _cabi.check(rc, "mml_kron_linear_fwd")
         else:
             rc = lib.mml_kron_linear_fwd_simt(_cabi.dptr(fs[0]), _cabi.dptr(fs[1]), f3p, B, d1, d2, d3, _cabi.dptr(w), bptr,
-                                              N, float(drop_p), int(seed), int(training), _cabi.dptr(y), st)
+                                              N, float(drop_p), seed, sdev, int(training), _cabi.dptr(y), st)
             _cabi.check(rc, "mml_kron_linear_fwd_simt")
         ctx.save_for_backward(w, *fs)
         ctx.state = state
         ctx.wkey = wkey
-        ctx.cfg = (state.dims, float(drop_p), int(training), int(seed), bias is not None)
+        ctx.cfg = (state.dims, float(drop_p), int(training), seed, bias is not None)
+        ctx.seed_t = seed_t
         return y
 
     @staticmethod
@@ -164,6 +168,7 @@ class _KronLinearFn(torch.autograd.Function):
         lib = _cabi.lib()
         w, *fs = ctx.saved_tensors
         (d1, d2, d3), drop_p, training, seed, has_bias = ctx.cfg
+        sdev = _cabi.dptr(ctx.seed_t, torch.int64) if ctx.seed_t is not None else None
         dy = dy.contiguous()
         B, N = dy.shape
         dev = dy.device
@@ -181,7 +186,7 @@ class _KronLinearFn(torch.autograd.Function):
             ws = torch.empty(wg_ws + 1024, dtype=torch.uint8, device=dev)
             off = (-ws.data_ptr()) % 1024
             rc = lib.mml_kron_linear_wgrad(_cabi.dptr(fs[0]), _cabi.dptr(fs[1]), f3p, B, d1, d2, d3, _cabi.dptr(state.table),
-                                           _cabi.dptr(dy), N, drop_p, seed, training, _cabi.dptr(dW),
+                                           _cabi.dptr(dy), N, drop_p, seed, sdev, training, _cabi.dptr(dW),
                                            ctypes_ptr(ws.data_ptr() + off), wg_ws, st)
             _cabi.check(rc, "mml_kron_linear_wgrad")
             simt_dW = None
@@ -190,7 +195,7 @@ class _KronLinearFn(torch.autograd.Function):
             state.ensure_t(w, ctx.wkey)
             ws = torch.empty(dg_ws, dtype=torch.uint8, device=dev)
             rc = lib.mml_kron_linear_dgrad(_cabi.dptr(fs[0]), _cabi.dptr(fs[1]), f3p, B, d1, d2, d3, _cabi.dptr(state.table),
-                                           _cabi.dptr(state.packed_t), _cabi.dptr(dy), N, drop_p, seed, training,
+                                           _cabi.dptr(state.packed_t), _cabi.dptr(dy), N, drop_p, seed, sdev, training,
                                            _cabi.dptr(dfs[0]), _cabi.dptr(dfs[1]), _cabi.dptr(dfs[2]) if d3 > 0 else None,
                                            _cabi.dptr(ws), dg_ws, st)
             _cabi.check(rc, "mml_kron_linear_dgrad")
@@ -201,7 +206,7 @@ class _KronLinearFn(torch.autograd.Function):
             sd = dfs if need_f_simt else [None] * len(fs)
             rc = lib.mml_kron_linear_bwd_simt(
                 _cabi.dptr(fs[0]), _cabi.dptr(fs[1]), f3p, B, d1, d2, d3, _cabi.dptr(w), _cabi.dptr(dy), N, drop_p, seed,
-                training, _cabi.dptr(sd[0]), _cabi.dptr(sd[1]), _cabi.dptr(sd[2]) if d3 > 0 else None,
+                sdev, training, _cabi.dptr(sd[0]), _cabi.dptr(sd[1]), _cabi.dptr(sd[2]) if d3 > 0 else None,
                 _cabi.dptr(simt_dW), st)
             _cabi.check(rc, "mml_kron_linear_bwd_simt")
         dbias = dy.sum(0) if (has_bias and ctx.needs_input_grad[2]) else None
@@ -218,7 +223,10 @@ def kron_linear(state: KronLinearState, factors, weight, bias, drop_p=0.0, train
         if f.dtype != torch.float32:
             raise RuntimeError(f"Kronecker fusion computes from fp32 factors; got {f.dtype}")
     if seed is None:
-        seed = int(torch.randint(0, 2 ** 62, (1,)).item()) if (training and drop_p > 0) else 0
+        # one 64-bit word per call from torch's CUDA generator: no host sync, reproducible under torch.manual_seed, and
+        # graph-safe (a captured step re-draws it on every replay; the kernels read it from device memory)
+        seed = (torch.randint(0, 2 ** 62, (1,), dtype=torch.int64, device=factors[0].device)
+                if (training and drop_p > 0) else 0)
     return _KronLinearFn.apply(state, weight, bias, drop_p, training, seed, weight_key, *factors)
 
 

@@ -218,3 +218,63 @@ def test_cpu_inputs_are_rejected(pkg):
     fs, W, bias = _problem(4, (8, 8), 8, seed=0)
     with pytest.raises(RuntimeError):
         kron_linear(KronLinearState((8, 8)), fs, W, bias)
+
+
+@pytest.mark.parametrize("dims,N", [((32, 32), 64), ((8, 6, 10), 24)])
+def test_device_seed_word_equals_host_seed(pkg, dims, N):
+    """The seed may live in device memory (graph-safe): host seed S and device word S give the same mask, forward
+    and backward, on the tensor-core and the CUDA-core kernels."""
+    from multimodal_learning_b200.fusion import KronLinearState, kron_linear
+    B, seed = 200, 0x0BAD_C0DE_1234
+    fs, W, bias = _problem(B, dims, N, seed=21)
+    G = torch.randn(B, N, generator=torch.Generator().manual_seed(4)).to(DEV)
+    for path in ("simt", "auto"):
+        outs = []
+        for sd in (seed, torch.tensor([seed], dtype=torch.int64, device=DEV)):
+            st = KronLinearState(dims)
+            st.path = path
+            fd = [f.to(DEV).requires_grad_(True) for f in fs]
+            Wd = W.to(DEV).requires_grad_(True)
+            y = kron_linear(st, fd, Wd, bias.to(DEV), drop_p=0.3, training=True, seed=sd)
+            (y * G).sum().backward()
+            outs.append([y.detach(), Wd.grad] + [f.grad for f in fd])
+        for a, b in zip(*outs):
+            assert torch.equal(a, b), path
+
+
+def test_graphed_fusion_crd_step_redraws_dropout_and_trains(pkg):
+    """Whole fused step (BilinearFusion in train mode WITH dropout -> CRDLoss -> backward -> Adam) captured in one
+    CUDA graph: every replay draws a fresh Kronecker-dropout mask from device state, parameters and banks move."""
+    import types
+    torch.manual_seed(7)
+    B, d, N, D, K, n = 32, 32, 64, 128, 256, 1024
+    fusion = pkg.BilinearFusion(skip=0, dim1=d, dim2=d, mmhid=N, dropout_rate=0.25).to(DEV).train()
+    opt = types.SimpleNamespace(s_dim=N, t_dim=N, feat_dim=D, n_data=n, nce_k=K, nce_t=0.07, nce_m=0.5)
+    crd = pkg.CRDLoss(opt).to(DEV)
+    params = list(fusion.parameters()) + list(crd.parameters())
+    optim = torch.optim.Adam(params, lr=1e-3, capturable=True, fused=True)
+    v1, v2, f_t = torch.randn(B, d, device=DEV), torch.randn(B, d, device=DEV), torch.randn(B, N, device=DEV)
+    idx = torch.randperm(n, device=DEV)[:B].contiguous()
+    cidx = torch.randint(0, n, (B, K + 1), device=DEV)
+    cidx[:, 0] = idx
+    captured = {}
+
+    def loss_fn(a, b, t, i, ci):
+        f = fusion(a, b)
+        captured["f"] = f
+        return crd(f, t, i, ci)
+    step = pkg.GraphedTrainStep(loss_fn, params, optim, (v1, v2, f_t, idx, cidx), warmup=2)
+    w0 = fusion.encoder1[0].weight.detach().clone()
+    bank0 = crd.contrast.memory_v1.clone()
+    launches0 = pkg._cabi.launch_count()
+    feats, losses = [], []
+    for _ in range(3):
+        losses.append(step(v1, v2, f_t, idx, cidx).clone())
+        feats.append(captured["f"].detach().clone())
+    assert pkg._cabi.launch_count() == launches0            # replays issue no launches through the C ABI: one graph each
+    assert all(torch.isfinite(l).all() for l in losses)
+    assert not torch.equal(feats[0], feats[1]) and not torch.equal(feats[1], feats[2])
+    assert not torch.equal(fusion.encoder1[0].weight.detach(), w0)
+    assert not torch.equal(crd.contrast.memory_v1, bank0)
+    # same inputs, same weights, dropout off => replays differ only through the optimizer: loss decreases
+    assert losses[-1].item() < losses[0].item() * 1.5
