@@ -121,22 +121,27 @@ class ClockSampler:
 
 
 class EventTimer:
-    """CUDA events on the launching (current) stream around the gather kernel's launches."""
+    """CUDA events on the launching (current) stream around the gather kernel's launches.  While a CUDA graph is being
+    captured the events are created `external=True`: they become event-record nodes of the graph and every replay
+    re-records them, so after the timed region each pair holds the kernel time of that graph's LAST replay."""
 
     def __init__(self):
         self.pairs = []
         self.enabled = False
         self._open = None
 
+    def _event(self):
+        return torch.cuda.Event(enable_timing=True, external=torch.cuda.is_current_stream_capturing())
+
     def start(self, name, dev):
         if self.enabled:
-            e = torch.cuda.Event(enable_timing=True)
+            e = self._event()
             e.record(torch.cuda.current_stream(dev))
             self._open = e
 
     def stop(self, name, dev):
         if self.enabled and self._open is not None:
-            e = torch.cuda.Event(enable_timing=True)
+            e = self._event()
             e.record(torch.cuda.current_stream(dev))
             self.pairs.append((self._open, e))
             self._open = None
@@ -303,24 +308,59 @@ def run_gpu_arm(args):
         return ms.item()
 
     # ---- device-resident throughput (`value`) ----
+    # Default: the whole step (Embed heads, routing / gather / finishers / row update, backward, Adam; on N > 1 also the
+    # symmetric-memory barriers and the NCCL gradient all_reduce) is captured ONCE per input set into a CUDA graph
+    # (`GraphedTrainStep`) and replayed: one launch per step instead of ~65.  `--eager` times the eager launches instead.
     sampler = ClockSampler(local_rank) if rank == 0 else None
     for i in range(max(args.warmup, 3)):
         step_device(i)
     timer = EventTimer()
-    crd_mod.KERNEL_TIMER = timer
+    mode = "eager"
+    captured_launches = None
+    step_fn = step_device
+    if not args.eager:
+        try:
+            barrier()
+            g_optim = torch.optim.Adam(opt_params, lr=2e-4, betas=(0.9, 0.999), fused=True, capturable=True)
+            mark = {}
+
+            def before_capture():
+                crd_mod.KERNEL_TIMER = timer
+                timer.enabled = True
+                mark["l0"] = pkg._cabi.launch_count()
+            gstep = pkg.GraphedTrainStep(lambda a, b, c, d: mod(a, b, c, d), opt_params, g_optim, pool[0], grad_inputs=(0,),
+                                         warmup=3, n_buffers=len(pool), before_capture=before_capture)
+            timer.enabled = False
+            crd_mod.KERNEL_TIMER = None
+            captured_launches = (pkg._cabi.launch_count() - mark["l0"]) // len(pool)
+            for slot, entry in enumerate(pool):
+                for dst, src in zip(gstep.buffers(slot), entry):
+                    dst.detach().copy_(src)
+            barrier()
+            mode = "cuda_graph"
+            step_fn = lambda i: gstep.replay()       # round-robin over the captured input sets  # noqa: E731
+            for i in range(max(args.warmup, 3)):
+                step_fn(i)
+        except Exception as e:                       # noqa: BLE001 -- report and fall back to eager launches
+            print(f"[bench] CUDA-graph capture failed ({type(e).__name__}: {e}); timing eager launches", file=sys.stderr)
+            timer = EventTimer()
+            mode, step_fn = "eager", step_device
+    if mode == "eager":
+        crd_mod.KERNEL_TIMER = timer
+    torch.cuda.synchronize(dev)
+    if sampler:
+        sampler.wait_ready()
+    for i in range(3):                      # the GPU is busy again when the region starts (all ranks: collectives inside)
+        step_fn(i)
     launches0 = pkg._cabi.launch_count()
     if sampler:
-        torch.cuda.synchronize(dev)
-        sampler.wait_ready()
-        for i in range(3):                  # the GPU is busy again when the region starts
-            step_device(i)
-        launches0 = pkg._cabi.launch_count()
         sampler.mark()
-    timer.enabled = True
-    total_ms = timed(step_device, args.steps, profile=True)
+    if mode == "eager":
+        timer.enabled = True
+    total_ms = timed(step_fn, args.steps, profile=True)
     timer.enabled = False
     clocks = sampler.stop() if sampler else None
-    launches = pkg._cabi.launch_count() - launches0
+    launches = (pkg._cabi.launch_count() - launches0) if mode == "eager" else captured_launches * args.steps
     crd_mod.KERNEL_TIMER = None
     ms_per_step = total_ms / args.steps
     value = world * 1000.0 / ms_per_step
@@ -362,10 +402,12 @@ def run_gpu_arm(args):
     # Same step through `GraphedTrainStep` (the package's public whole-step CUDA graph): with a host sync per step the
     # eager path is bound by the host issuing ~65 launches, the graph is one launch.  Two captured graphs over two
     # static input sets: the H2D of step i+1 lands in the other set while step i replays.
-    if world == 1:
+    if mode == "cuda_graph":
+        barrier()
         g_optim = torch.optim.Adam(opt_params, lr=2e-4, betas=(0.9, 0.999), fused=True, capturable=True)
         gstep = pkg.GraphedTrainStep(lambda a, b, c, d: mod(a, b, c, d), opt_params, g_optim, pool[0], grad_inputs=(0,),
                                      warmup=3, n_buffers=2)
+        barrier()
         up_done = [torch.cuda.Event(), torch.cuda.Event()]
         run_done = [torch.cuda.Event(), torch.cuda.Event()]
 
@@ -397,7 +439,7 @@ def run_gpu_arm(args):
         for i in range(4):
             step_e2e_graph(i)
         primed.clear()
-        torch.cuda.synchronize(dev)
+        barrier()
         e2e_ms = timed(step_e2e_graph, args.steps) / args.steps
         primed.clear()
         e2e_note = ("pinned host inputs -> static device buffers (H2D of step i+1 overlaps the replay of step i), whole step "
@@ -456,12 +498,15 @@ def run_gpu_arm(args):
     line = {
         "metric": METRIC, "value": value, "unit": "steps/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "launch_mode": mode,
         "config": {"workload": workload, "l2": "inputs exceed L2: 1.02 GB of bank rows gathered at random per GPU, "
                    "4 rotating 134 MB index sets; no explicit flush", "algorithmic_bytes_per_step": total_bytes},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": (achieved / peak) if achieved else None, "traffic": args.traffic,
                      "kernel": "crd_gather_kernel<4,2,fused> (+2 finisher launches)", "kernel_ms": k_ms,
+                     "timing": ("CUDA events recorded as external event nodes around the gather launch inside the replayed graphs "
+                                "(last replay of each captured graph)" if mode == "cuda_graph" else
+                                "CUDA events on the launching stream around every gather launch of the timed steps"),
                      "bytes_per_launch": gather_bytes, "peak_source": f"MEASURED_PEAKS.json ({peak_kind}, burst copy)"},
         "e2e": {"value": e2e_value, "unit": "steps/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": h2d_bytes,
                 "d2h_bytes_per_step": 4, "note": e2e_note, "eager_ms_per_step": e2e_eager_ms},
@@ -488,6 +533,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--eager", action="store_true", help="time eager kernel launches instead of CUDA-graph replays")
     ap.add_argument("--traffic", type=float, default=16.634e9,
                     help="dram__bytes_read+write per launch of the gather kernel from the committed ncu --set full "
                          "capture at config 2 (profiles/r1_crd_gather_v2_full.txt: 16.626 GB read + 0.008 GB written)")

@@ -67,22 +67,34 @@ __global__ void __launch_bounds__(kRouteThreads) shard_route_strided_kernel(
   const int64_t k_end = min(cols, k_begin + chunk_cols);
   // the divide is by a runtime constant: do it in 32 bits (row < 2^31 is checked on the host side)
   const uint32_t rpr = static_cast<uint32_t>(rows_per_rank);
-  for (int64_t k0 = k_begin; k0 < k_end; k0 += 32) {
-    const int64_t k = k0 + lane;
-    const bool valid = k < k_end;
-    const uint32_t row = valid ? static_cast<uint32_t>(idx[b * cols + k]) : 0u;
-    const int owner = valid ? static_cast<int>(row / rpr) : -1;
-    const uint32_t local = row - static_cast<uint32_t>(owner < 0 ? 0 : owner) * rpr;
-    // lanes with the same owner form a group; rank inside the group = stable position
-    const unsigned peers = __match_any_sync(kFullMask, owner);
-    int32_t base = 0;
-    if (valid) {
-      base = run[warp][owner];
-      out[(static_cast<int64_t>(owner) * plane + slot) * chunk_cols + base + __popc(peers & lt)] = static_cast<int32_t>(local);
+  // 4 independent coalesced index loads in flight per lane before the (serial, shared-memory) ranking of each of them
+  constexpr int kPre = 4;
+  for (int64_t kg = k_begin; kg < k_end; kg += 32 * kPre) {
+    uint32_t rowv[kPre];
+#pragma unroll
+    for (int u = 0; u < kPre; ++u) {
+      const int64_t k = kg + u * 32 + lane;
+      rowv[u] = (k < k_end) ? static_cast<uint32_t>(__ldg(idx + b * cols + k)) : 0u;
     }
-    __syncwarp();
-    if (valid && lane == __ffs(peers) - 1) run[warp][owner] = base + __popc(peers);
-    __syncwarp();
+#pragma unroll
+    for (int u = 0; u < kPre; ++u) {
+      const int64_t k = kg + u * 32 + lane;
+      if (kg + u * 32 >= k_end) break;                 // warp-uniform
+      const bool valid = k < k_end;
+      const uint32_t row = rowv[u];
+      const int owner = valid ? static_cast<int>(row / rpr) : -1;
+      const uint32_t local = row - static_cast<uint32_t>(owner < 0 ? 0 : owner) * rpr;
+      // lanes with the same owner form a group; rank inside the group = stable position
+      const unsigned peers = __match_any_sync(kFullMask, owner);
+      int32_t base = 0;
+      if (valid) {
+        base = run[warp][owner];
+        out[(static_cast<int64_t>(owner) * plane + slot) * chunk_cols + base + __popc(peers & lt)] = static_cast<int32_t>(local);
+      }
+      __syncwarp();
+      if (valid && lane == __ffs(peers) - 1) run[warp][owner] = base + __popc(peers);
+      __syncwarp();
+    }
   }
   if (lane < world) counts[static_cast<int64_t>(lane) * plane + slot] = run[warp][lane];
 }

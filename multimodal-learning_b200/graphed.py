@@ -12,6 +12,8 @@ no equivalent (eager PyTorch 1.10); this is the B200-side answer to its five `.i
 
 Rules (checked where possible):
   * shapes are fixed at construction; inputs are copied into the static buffers (device or pinned-host sources);
+  * drop every reference to losses / outputs of earlier eager steps before constructing (a live autograd graph pins
+    the parameters' AccumulateGrad nodes to the stream those steps ran on, which breaks the capture);
   * run >= 1 eager step first (the constructor does `warmup` of them): the first CRD call sets Z with a host sync
     (`CRD_criterion.py:52-59`), the optimizer allocates its state, the Kronecker weights get packed;
   * the optimizer must be capturable (`torch.optim.Adam(..., capturable=True)`; fused or foreach);
@@ -35,7 +37,8 @@ class GraphedTrainStep:
     `n_buffers=2` keeps two captured graphs over two static input sets so that the upload of step i+1 (on another
     stream) can overlap the replay of step i."""
 
-    def __init__(self, loss_fn, params, optimizer, example_inputs, grad_inputs=(), warmup=3, n_buffers=1):
+    def __init__(self, loss_fn, params, optimizer, example_inputs, grad_inputs=(), warmup=3, n_buffers=1,
+                 before_capture=None):
         self.params = [p for p in params]
         self.optimizer = optimizer
         self.loss_fn = loss_fn
@@ -58,6 +61,8 @@ class GraphedTrainStep:
                 self._eager(self.static_in[0])
         torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.synchronize(dev)
+        if before_capture is not None:
+            before_capture()
         pool = None
         for ins in self.static_in:
             g = torch.cuda.CUDAGraph()
@@ -65,7 +70,10 @@ class GraphedTrainStep:
                 p.grad = None
             for i in grad_inputs:
                 ins[i].grad = None
-            with torch.cuda.graph(g, pool=pool):
+            # thread_local: a NCCL watchdog thread polling events must not invalidate the capture
+            # ... and capture on the stream the warm-up ran on: AccumulateGrad nodes that outlive the warm-up keep its
+            # stream, and autograd may not make another (let alone the legacy) stream wait on a capturing one
+            with torch.cuda.graph(g, pool=pool, stream=side, capture_error_mode="thread_local"):
                 loss = self.loss_fn(*ins)
                 loss.backward()
                 self.optimizer.step()

@@ -38,6 +38,7 @@ default backend is CUDA-only and fails loudly without the library.
 from __future__ import annotations
 
 import math
+import os
 
 import torch
 import torch.distributed as dist
@@ -132,7 +133,7 @@ class PeerExchange:
       YP   int64 [2][2][B_g]                   all-gathered anchor ids | positive rows, double-buffered
       P    float [2][B_g][D] + tail[16]        this rank's partial dL/dv1|dL/dv2 and its 4 partial sums"""
 
-    def __init__(self, mem, B_local, cols, D, device):
+    def __init__(self, mem, B_local, cols, D, device, grad_floats=0):
         import ctypes
 
         import torch.distributed._symmetric_memory as symm
@@ -149,7 +150,9 @@ class PeerExchange:
         self.off_YP = al(self.off_V + 2 * 2 * Bg * D * 4)
         self.off_P = al(self.off_YP + 2 * 2 * Bg * 8)
         self.off_tail = self.off_P + 2 * Bg * D * 4
-        total = al(self.off_tail + 64)
+        self.grad_pad = (int(grad_floats) + 3) // 4 * 4                 # G float [world][grad_pad]: every rank's head gradients
+        self.off_G = al(self.off_tail + 64)
+        total = al(self.off_G + self.world * self.grad_pad * 4 + 64)
         group = mem.group if mem.group is not None else dist.group.WORLD
         if hasattr(symm, "enable_symm_mem_for_group"):
             try:
@@ -171,6 +174,8 @@ class PeerExchange:
         self.YP = view(self.off_YP, 2 * 2 * Bg * 8, torch.int64, (2, 2, Bg))
         self.P = view(self.off_P, 2 * Bg * D * 4, torch.float32, (2, Bg, D))
         self.tail = view(self.off_tail, 16, torch.float32, (4,))
+        self.G = (view(self.off_G, self.world * self.grad_pad * 4, torch.float32, (self.world, self.grad_pad))
+                  if self.grad_pad else None)
         self.step = 0
         self._c = ctypes
 
@@ -185,6 +190,24 @@ class PeerExchange:
         _cabi.check(_cabi.lib().mml_symm_push(self.base_ptrs, self.world, srcs, offs, nbytes, 4,
                                               _cabi.cur_stream(v1.device)), "mml_symm_push")
 
+    def allreduce_sum(self, g):
+        """Sum of a small flat fp32 vector over the ranks without NCCL: every rank STORES its vector into slice `rank` of
+        every peer's G region (NVLink), one barrier, then each rank adds the `world` slices of its OWN region in rank
+        order -- the same operands in the same order everywhere, so replicated parameters stay bit-identical.  Reuse
+        across steps is ordered by the two barriers of the next step's forward."""
+        n = g.numel()
+        if self.G is None or n > self.grad_pad:
+            raise RuntimeError("PeerExchange was built without room for this gradient vector")
+        c = self._c
+        src = g if n == self.grad_pad else torch.cat((g.reshape(-1), g.new_zeros(self.grad_pad - n)))
+        srcs = (c.c_void_p * 1)(src.data_ptr())
+        offs = (c.c_int64 * 1)(self.off_G + self.rank * self.grad_pad * 4)
+        nbytes = (c.c_int64 * 1)(self.grad_pad * 4)
+        _cabi.check(_cabi.lib().mml_symm_push(self.base_ptrs, self.world, srcs, offs, nbytes, 1,
+                                              _cabi.cur_stream(g.device)), "mml_symm_push")
+        self.handle.barrier(channel=2)
+        return self.G[:, :n].sum(0).view_as(g)
+
     def pull_reduce(self, g1, g2, tail):
         """reduce_scatter by NVLink loads: my anchors' rows summed over every rank's partial buffer."""
         _cabi.check(_cabi.lib().mml_symm_pull_reduce(
@@ -198,15 +221,17 @@ class _SumGradAcrossRanks(torch.autograd.Function):
     parameters so the data-parallel heads get the global-batch gradient with one collective."""
 
     @staticmethod
-    def forward(ctx, flat, group):
-        ctx.group = group
+    def forward(ctx, flat, group, reducer=None):
+        ctx.group, ctx.reducer = group, reducer
         return flat.view_as(flat)
 
     @staticmethod
     def backward(ctx, g):
         g = g.contiguous()
+        if ctx.reducer is not None:          # peer transport: symmetric-memory exchange, no NCCL on the step
+            return ctx.reducer(g), None, None
         dist.all_reduce(g, group=ctx.group)
-        return g, None
+        return g, None, None
 
 
 class _AllGatherRows(torch.autograd.Function):
@@ -296,6 +321,7 @@ class ShardedContrastMemory(nn.Module):
             self.params = self.params.to(device)
         self.multinomial = None          # built lazily: only the idx=None branch samples
         self._peer = {}                  # (B_local, cols, device) -> PeerExchange
+        self.grad_floats = 0             # room for the data-parallel heads' flattened gradient in each arena
         p = torch.tensor([K, T, -1, -1, momentum])
         self._K, self._T, self._momentum = int(p[0].item()), p[1].item(), p[4].item()
         self._z_ready = False
@@ -339,11 +365,11 @@ class ShardedContrastMemory(nn.Module):
             host, ev = sizes, None
         return ids, recv_counts, host, ev
 
-    def peer_arena(self, B_local, cols, D, device):
+    def peer_arena(self, B_local, cols, D, device, grad_floats=0):
         key = (B_local, cols, D, device)
         px = self._peer.get(key)
         if px is None:
-            px = self._peer[key] = PeerExchange(self, B_local, cols, D, device)
+            px = self._peer[key] = PeerExchange(self, B_local, cols, D, device, grad_floats=max(grad_floats, self.grad_floats))
         return px
 
     def _peer_step(self, v1, v2, idx, cidx, n_data):
@@ -453,16 +479,19 @@ class ShardedCRDLoss(nn.Module):
         self.criterion_t = ContrastLoss(opt.n_data)
         self.criterion_s = ContrastLoss(opt.n_data)
         self.transport = transport
+        # "symm": the heads' gradient is summed over peer-mapped memory (no NCCL anywhere on the step); "nccl": all_reduce
+        self.heads_reduce = os.environ.get("MML_HEADS_REDUCE", "symm")
+        self._feat_dim = opt.feat_dim
 
     def _pick_transport(self, device):
         if self.transport == "auto":
             self.transport = "peer" if (device.type == "cuda" and isinstance(self.contrast.backend, CudaBackend)) else "alltoall"
         return self.transport
 
-    def _heads(self, f_s, f_t):
+    def _heads(self, f_s, f_t, reducer=None):
         """Embed heads on the local anchors with parameters routed through `_SumGradAcrossRanks`."""
         named = [(k, p) for k, p in self.named_parameters()]
-        flat = _SumGradAcrossRanks.apply(torch.cat([p.reshape(-1) for _, p in named]), self.group)
+        flat = _SumGradAcrossRanks.apply(torch.cat([p.reshape(-1) for _, p in named]), self.group, reducer)
         views, off = {}, 0
         for k, p in named:
             views[k] = flat[off:off + p.numel()].view_as(p)
@@ -485,8 +514,13 @@ class ShardedCRDLoss(nn.Module):
         if transport == "peer" and idx.shape[0] % 2:
             transport = "alltoall"                  # 16-byte push granularity needs an even local batch
         if transport == "peer":
-            v1, v2 = self._heads(f_s, f_t)
             try:
+                reducer = None
+                if self.heads_reduce == "symm":
+                    mem.grad_floats = sum(p.numel() for p in self.parameters())
+                    px = mem.peer_arena(idx.shape[0], mem._K + 1, self._feat_dim, f_s.device)
+                    reducer = px.allreduce_sum
+                v1, v2 = self._heads(f_s, f_t, reducer)
                 return _ShardedPeerFn.apply(v1, v2, mem, idx, contrast_idx, self.criterion_s.n_data)
             except Exception as e:                  # no peer mapping on this system: fall back, loudly, once
                 if mem._peer:
