@@ -150,6 +150,14 @@ class EventTimer:
         return statistics.mean(a.elapsed_time(b) for a, b in self.pairs) if self.pairs else None
 
 
+def workload_name(world):
+    if world == 1:
+        return "config 2: CRD step feat_dim=128 batch=1024 n_data=1M nce_k=16384, fwd+bwd+bank update"
+    n, Bg = ROWS_PER_GPU_SHARDED * world, C2["B"] * world
+    return (f"config-2 unit per GPU on the row-sharded bank: global batch {Bg}, n_data {n} "
+            f"({ROWS_PER_GPU_SHARDED} rows/GPU), nce_k 16384" + (" = BASELINE config 5" if world == 8 else ""))
+
+
 def make_opt(cfg, n):
     return types.SimpleNamespace(s_dim=cfg["s_dim"], t_dim=cfg["t_dim"], feat_dim=cfg["D"], n_data=n,
                                  nce_k=cfg["K"], nce_t=0.07, nce_m=0.5)
@@ -218,7 +226,9 @@ def run_reference_arm(args):
         "impl": "reference", "metric": METRIC, "value": sps, "unit": "steps/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 / sps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "config 2: CRD step feat_dim=128 batch=1024 n_data=1M nce_k=16384 (CPU, sliced)"},
+        "config": {"workload": workload_name(args.gpus),
+                   "cpu_note": "one config-2 unit (1024 anchors x 16385 columns, n_data 1M) per step on the host cores; the "
+                               "row-sharded bank of N > 1 is the same unit per GPU, the CPU arm runs one unit"},
         "cpu_baseline": {"value": sps, "unit": "steps/s", "cores": cores, "kind": "port",
                          "sample": f"{sample_B} of 1024 anchors per step at full K=16384/n=1M "
                                    f"({t_sample * 1e3:.0f} ms each), scaled x{cfg['B'] // sample_B} (work is linear in anchors)"},
@@ -256,14 +266,13 @@ def run_gpu_arm(args):
         n = cfg["n"]
         mod = pkg.CRDLoss(make_opt(cfg, n)).to(dev)
         B_local, B_global = B, B
-        workload = "config 2: CRD step feat_dim=128 batch=1024 n_data=1M nce_k=16384, fwd+bwd+bank update"
+        workload = workload_name(1)
     else:
         from multimodal_learning_b200.sharded import ShardedCRDLoss
         n = ROWS_PER_GPU_SHARDED * world
         B_local, B_global = B, B * world
         mod = ShardedCRDLoss(make_opt(cfg, n), device=dev)
-        workload = (f"config-2 unit per GPU on the row-sharded bank: global batch {B_global}, n_data {n} "
-                    f"({ROWS_PER_GPU_SHARDED} rows/GPU), nce_k 16384" + (" = BASELINE config 5" if world == 8 else ""))
+        workload = workload_name(world)
     opt_params = [p for p in mod.parameters()]
     optim = torch.optim.Adam(opt_params, lr=2e-4, betas=(0.9, 0.999), fused=True)   # networks_new.py:85
 

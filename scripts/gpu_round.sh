@@ -1,5 +1,5 @@
 #!/bin/bash
-# One GPU-box visit: parity tests, smoke, bench, ncu launch list + full capture of the gather kernel.
+# One GPU-box visit: parity tests, smoke, bench, ncu launch list + full captures of the gather and relation kernels.
 # Usage (from the repo root, under gpurun):  bash scripts/gpu_round.sh <tag>
 set -u
 TAG=${1:-r1}
@@ -9,10 +9,15 @@ nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > $O
 echo "== pytest -m gpu" ; timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -25 | tee $OUT/${TAG}_pytest.txt
 echo "== smoke" ; timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -8 | tee $OUT/${TAG}_smoke.txt
 echo "== bench" ; timeout 600 python bench.py --steps 100 --warmup 10 2>&1 | tail -3 | tee $OUT/${TAG}_bench.json
+echo "== bench --eager" ; timeout 300 python bench.py --steps 100 --warmup 10 --eager --no-cpu 2>&1 | tail -1 | tee $OUT/${TAG}_bench_eager.json
+echo "== selection variant" ; timeout 300 python scripts/bench_select.py 2>&1 | grep config | tee $OUT/${TAG}_bench_select.jsonl
 echo "== ncu launches (timed region only: cudaProfilerStart/Stop around the K steps)"
 MML_BENCH_PROFILE=1 timeout 600 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv \
     --log-file $OUT/${TAG}_launches.csv python bench.py --steps 3 --warmup 3 --no-cpu > $OUT/${TAG}_ncu_launch.log 2>&1
-echo "== ncu full"
+echo "== ncu full: gather"
 MML_BENCH_PROFILE=1 timeout 900 ncu --profile-from-start off --set full --clock-control none --import-source on \
     -k regex:crd_gather_kernel -c 2 -f -o $OUT/${TAG}_prof_crd python bench.py --steps 2 --warmup 3 --no-cpu > $OUT/${TAG}_ncu_full.log 2>&1
-ls -la $OUT | tail -12
+echo "== ncu full: relation"
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:crd_relation_kernel -s 8 -c 1 -f -o $OUT/${TAG}_prof_rel \
+    python scripts/bench_select.py > $OUT/${TAG}_ncu_rel.log 2>&1
+ls -la $OUT | tail -14
