@@ -238,7 +238,7 @@ class _GatedKronFusion(nn.Module):
     order (h, z, o per branch; post_fusion_dropout; encoder1; encoder2) so that state_dict keys and
     the global-RNG draws match fusion.py."""
 
-    def _build(self, dims_og, scales, gate_inputs, use_bilinear, skip, mmhid, dropout_rate, post_p, batchnorm):
+    def _build(self, dims_og, scales, gate_inputs, use_bilinear, skip, mmhid, dropout_rate, post_p, batchnorm, poly=False):
         dims = [d // s for d, s in zip(dims_og, scales)]                 # fusion.py:17 / :76
         self._dims = dims
         self._gate_inputs = gate_inputs                                  # per branch: which (a, b) feed linear_z
@@ -255,7 +255,12 @@ class _GatedKronFusion(nn.Module):
         skip_dim = (sum(dims) + len(dims)) if skip else 0
         norm = (lambda: [nn.BatchNorm1d(mmhid)]) if batchnorm else (lambda: [])
         self.encoder1 = nn.Sequential(nn.Linear(kk, mmhid), *norm(), nn.ReLU(), nn.Dropout(p=dropout_rate))
-        self.encoder2 = nn.Sequential(nn.Linear(mmhid + skip_dim, mmhid), *norm(), nn.ReLU(), nn.Dropout(p=dropout_rate))
+        if poly:     # stage-2 PolynomialFusion: a second Kronecker encoder, then the skip encoder (its fusion.py:31-34)
+            self.encoder2 = nn.Sequential(nn.Linear(kk, mmhid), *norm(), nn.ReLU(), nn.Dropout(p=dropout_rate))
+            self.encoder3 = nn.Sequential(nn.Linear(mmhid + skip_dim, mmhid), *norm(), nn.ReLU(), nn.Dropout(p=dropout_rate))
+            self._kron2 = KronLinearState([mmhid, mmhid])
+        else:
+            self.encoder2 = nn.Sequential(nn.Linear(mmhid + skip_dim, mmhid), *norm(), nn.ReLU(), nn.Dropout(p=dropout_rate))
         init_max_weights(self)
         self._kron = KronLinearState(dims)
         # the nn.Bilinear gates are the same contraction without the appended 1
@@ -265,6 +270,8 @@ class _GatedKronFusion(nn.Module):
     def set_kron_path(self, path):
         """"auto" (tensor cores) or "simt" (exact fp32 CUDA cores) for every Kronecker contraction of the module."""
         self._kron.path = path
+        if hasattr(self, "_kron2"):
+            self._kron2.path = path
         for st in self._zkron.values():
             st.path = path
 
@@ -318,6 +325,41 @@ class BilinearFusion(_GatedKronFusion):
         o1 = self._branch(1, vecs, self.gate1)
         o2 = self._branch(2, vecs, self.gate2)
         return self._fuse([o1, o2])
+
+
+class PolynomialFusion(_GatedKronFusion):
+    """`MIA 2023/stage2_unimodal_student/fusion.py:6-73`: BilinearFusion whose encoder1 output, with a 1 appended, is
+    Kronecker-multiplied with ITSELF and contracted by a second encoder (4th-order fusion, :63-68), then the skip
+    encoder.  Both Kronecker tensors stay on chip (K1/K2/K3, the second with both factors = encoder1's output).  As in
+    the reference, `encoder2` is sized by (dim1+1)(dim2+1), so the module only runs when that equals (mmhid+1)^2."""
+
+    def __init__(self, skip=1, use_bilinear=1, gate1=1, gate2=1, dim1=32, dim2=32,
+                 scale_dim1=1, scale_dim2=1, mmhid=64, dropout_rate=0.25):
+        super(PolynomialFusion, self).__init__()
+        self.skip = skip
+        self.use_bilinear = use_bilinear
+        self.gate1 = gate1
+        self.gate2 = gate2
+        self.relu = nn.ReLU(inplace=False)
+        self._build([dim1, dim2], [scale_dim1, scale_dim2], [(0, 1), (0, 1)], use_bilinear, skip, mmhid,
+                    dropout_rate, post_p=dropout_rate, batchnorm=True, poly=True)
+
+    def forward(self, vec1, vec2):
+        vecs = [self.relu(vec1), self.relu(vec2)]
+        o1 = self._branch(1, vecs, self.gate1)
+        o2 = self._branch(2, vecs, self.gate2)
+        lin1, lin2 = self.encoder1[0], self.encoder2[0]
+        p = self.post_fusion_dropout.p
+        out12 = self.encoder1[1:](kron_linear(self._kron, [o1, o2], lin1.weight, lin1.bias, p, self.training))
+        if lin2.weight.shape[1] != (out12.shape[1] + 1) ** 2:          # the reference fails in F.linear the same way
+            raise RuntimeError(f"mat1 and mat2 shapes cannot be multiplied ({out12.shape[0]}x{(out12.shape[1] + 1) ** 2} "
+                               f"and {lin2.weight.shape[1]}x{lin2.weight.shape[0]})")
+        out12 = out12.contiguous()
+        out = self.encoder2[1:](kron_linear(self._kron2, [out12, out12], lin2.weight, lin2.bias, p, self.training))
+        if self.skip:
+            ones = o1.new_ones(o1.shape[0], 1)
+            out = torch.cat((out, torch.cat((o1, ones), 1), torch.cat((o2, ones), 1)), 1)
+        return self.encoder3(out)
 
 
 class _TrilinearFusion(_GatedKronFusion):

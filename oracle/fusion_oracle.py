@@ -92,6 +92,26 @@ def bilinear_fusion_forward(sd, vec1, vec2, *, skip=1, use_bilinear=1, gate1=1, 
     return torch.relu(_bn(sd, "encoder2.1", out, training))
 
 
+def polynomial_fusion_forward(sd, vec1, vec2, *, skip=1, use_bilinear=1, gate1=1, gate2=1, training=False):
+    """PolynomialFusion.forward, `MIA 2023/stage2_unimodal_student/fusion.py:38-72` (every Dropout as identity):
+    BilinearFusion's gated Kronecker + encoder1, then a SECOND Kronecker of [encoder1_out, 1] with itself (:64-68)."""
+    vec1 = torch.relu(vec1)                 # :40
+    vec2 = torch.relu(vec2)                 # :41
+    o1 = _gate(sd, 1, vec1, vec1, vec2, gate1, use_bilinear)
+    o2 = _gate(sd, 2, vec2, vec1, vec2, gate2, use_bilinear)
+    o1, o2 = _append_one(o1), _append_one(o2)
+    o12 = kron_rows(o1, o2)                 # :60
+    out12 = F.linear(o12, sd["encoder1.0.weight"], sd["encoder1.0.bias"])
+    out12 = _append_one(torch.relu(_bn(sd, "encoder1.1", out12, training)))     # :62-64
+    o1212 = kron_rows(out12, out12)         # :65
+    out = F.linear(o1212, sd["encoder2.0.weight"], sd["encoder2.0.bias"])
+    out = torch.relu(_bn(sd, "encoder2.1", out, training))
+    if skip:
+        out = torch.cat((out, o1, o2), 1)   # :68
+    out = F.linear(out, sd["encoder3.0.weight"], sd["encoder3.0.bias"])
+    return torch.relu(_bn(sd, "encoder3.1", out, training))
+
+
 def trilinear_fusion_forward(sd, vec1, vec2, vec3, *, variant="A", skip=1, use_bilinear=1,
                              gate1=1, gate2=1, gate3=1):
     """TrilinearFusion_A.forward (fusion.py:99-132) / _B (:168-201), Dropout as

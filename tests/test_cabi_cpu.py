@@ -115,3 +115,67 @@ def test_contrast_loss_standalone_matches_oracle():
     got = pkg.ContrastLoss(100)(x)
     assert got.shape == (1,)
     assert torch.allclose(got, co.nce_loss(x, 100), rtol=1e-6)
+
+
+def test_selection_variant_state_dict_layout_matches_reference(golden):
+    """5-arg CRDLoss(opt, n_data) (CL_utils/CRD_loss.py:133-151): same seed -> same initial state, same keys/shapes
+    (params has 6 entries [K, T, Z_v1, Z_v2, momentum, P]; single-Linear Embed heads)."""
+    import types
+    g = golden("crdsel_random")
+    c = g.cfg
+    torch.manual_seed(2019)
+    opt = types.SimpleNamespace(s_dim=c["s_dim"], t_dim=c["t_dim"], feat_dim=c["D"], nce_p=c["P"], nce_p2=c["P2"], nce_k=c["K"],
+                                nce_k2=c["K2"], nce_t=0.07, nce_m=0.5, select_pos_pairs=True, select_neg_pairs="True",
+                                sample_KD="False", select_pos_mode=c["mode"])
+    mod = pkg.crd_select.CRDLoss(opt, c["n"])
+    want, got = g.state_dict("init."), mod.state_dict()
+    assert list(got.keys()) == list(want.keys())
+    for k in want:
+        assert got[k].shape == want[k].shape and torch.equal(got[k], want[k]), k
+    assert mod.contrast.params.numel() == 6
+    # the criterion modules on host tensors (pure elementwise torch) agree with the oracle restatement
+    from oracle import crd_select_oracle as so
+    x = torch.rand(5, 3 + 7, 1) * 1e-2
+    for kd in ("False", "True"):
+        assert torch.allclose(pkg.ContrastLoss_v2(50, kd)(x, 3), so.contrast_loss_v2(x, 3, 50, kd), rtol=1e-6)
+
+
+@pytest.mark.parametrize("name", ["bilinear_skip", "polynomial_16", "trilinear_A"])
+def test_fusion_state_dict_layout_matches_reference(golden, name):
+    """Fusion modules: same seed -> same initial weights as the reference constructor (global-RNG order: nn.Bilinear /
+    nn.Linear defaults, then init_max_weights), same state_dict keys -- incl. the stage-2 PolynomialFusion."""
+    g = golden(name)
+    c = g.cfg
+    kw = {k: v for k, v in c.items() if k not in ("B", "kind", "variant")}
+    cls = {"bilinear": pkg.BilinearFusion, "polynomial": pkg.PolynomialFusion}.get(c["kind"]) or pkg.TrilinearFusion_A
+    torch.manual_seed(2019)
+    mod = cls(**kw)
+    want, got = g.state_dict("init."), mod.state_dict()
+    assert list(got.keys()) == list(want.keys())
+    for k in want:
+        assert got[k].shape == want[k].shape, k
+        if "encoder" not in k or ".0." in k:      # the goldens re-randomise the BatchNorm affine / running stats afterwards
+            assert torch.equal(got[k], want[k]), k
+
+
+def test_dropin_modules_resolve_to_the_package():
+    import importlib
+    import sys
+    d = os.path.join(ROOT, "multimodal-learning_b200", "dropin")
+    sys.path.insert(0, d)
+    saved = {k: sys.modules.pop(k) for k in list(sys.modules) if k in ("fusion", "KD_loss") or k.startswith("CL_utils")}
+    try:
+        fusion = importlib.import_module("fusion")
+        crit = importlib.import_module("CL_utils.CRD_criterion")
+        loss5 = importlib.import_module("CL_utils.CRD_loss")
+        mem = importlib.import_module("CL_utils.memory_new")
+        kd = importlib.import_module("KD_loss")
+        assert fusion.BilinearFusion is pkg.BilinearFusion and fusion.PolynomialFusion is pkg.PolynomialFusion
+        assert crit.CRDLoss is pkg.CRDLoss and loss5.CRDLoss is pkg.crd_select.CRDLoss
+        assert mem.ContrastMemory_v3 is pkg.ContrastMemory_v3 and mem.ContrastMemory is pkg.ContrastMemory
+        assert kd.DistillKL is pkg.DistillKL
+    finally:
+        sys.path.remove(d)
+        for k in [k for k in sys.modules if k in ("fusion", "KD_loss") or k.startswith("CL_utils")]:
+            sys.modules.pop(k)
+        sys.modules.update(saved)

@@ -33,14 +33,15 @@ def fo():
 def _make(pkg, g):
     c = g.cfg
     kw = {k: v for k, v in c.items() if k not in ("B", "kind", "variant")}
-    cls = pkg.BilinearFusion if c["kind"] == "bilinear" else (
+    cls = pkg.BilinearFusion if c["kind"] == "bilinear" else pkg.PolynomialFusion if c["kind"] == "polynomial" else (
         pkg.TrilinearFusion_A if c["variant"] == "A" else pkg.TrilinearFusion_B)
     mod = cls(**kw)
     mod.load_state_dict(g.state_dict("init."))
     return mod.to(DEV)
 
 
-GOLDENS = ["bilinear_c1", "bilinear_skip", "bilinear_odd", "bilinear_scaled", "trilinear_A", "trilinear_B"]
+GOLDENS = ["bilinear_c1", "bilinear_skip", "bilinear_odd", "bilinear_scaled", "trilinear_A", "trilinear_B",
+           "polynomial_16", "polynomial_gate"]
 
 
 @pytest.mark.parametrize("path", ["simt", "auto"])

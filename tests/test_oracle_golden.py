@@ -219,3 +219,16 @@ def test_crd_selection_variant_matches_reference(golden, name):
             cf, _, _ = so.closed_form_multi_pos(r1, r2, v1, v2, pre_params[1].item(), pre_params[2].item(),
                                                 pre_params[3].item(), c["n"], c["P2"])
             assert abs(cf.item() - g.t(p + "loss").item()) < 1e-5 * abs(g.t(p + "loss").item())
+
+
+@pytest.mark.parametrize("name", ["polynomial_16", "polynomial_gate"])
+def test_polynomial_fusion_matches_reference(golden, name):
+    """`MIA 2023/stage2_unimodal_student/fusion.py:6-73` (4th-order fusion) -- oracle/make_golden_poly.py."""
+    g = golden(name)
+    kw = {k: g.cfg[k] for k in ("skip", "use_bilinear", "gate1", "gate2") if k in g.cfg}
+    for tag in ("eval", "train"):
+        sd = _fusion_sd(g)
+        ins = [g.t("vec1").requires_grad_(True), g.t("vec2").requires_grad_(True)]
+        run_sd = {k: v.clone() if ("running" in k or "num_batches" in k) else v for k, v in sd.items()}
+        out = fo.polynomial_fusion_forward(run_sd, *ins, training=(tag == "train"), **kw)
+        _check_fusion(g, sd, out, ins, tag)
