@@ -1,0 +1,87 @@
+"""Worker for the sharded CUDA-graph test: the row-sharded step (routing, NVLink pulls, symmetric-memory barriers and the
+NCCL-free head-gradient reduction) replayed from `GraphedTrainStep` must equal the same steps launched eagerly."""
+from __future__ import annotations
+
+import os
+import sys
+import types
+
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+
+def run(rank, world, port, result_path):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    import multimodal_learning_b200 as pkg
+    from conftest import rel_err
+    from multimodal_learning_b200.sharded import ShardedCRDLoss
+    Bl, D, K, n = 8, 128, 256, 1000 * world
+    opt = types.SimpleNamespace(s_dim=40, t_dim=24, feat_dim=D, n_data=n, nce_k=K, nce_t=0.07, nce_m=0.5)
+    gen = torch.Generator(device=dev).manual_seed(100 + rank)
+
+    def inputs():
+        idx = torch.randperm(n, device=dev, generator=gen)[:Bl].contiguous()
+        cidx = torch.randint(0, n, (Bl, K + 1), device=dev, generator=gen)
+        cidx[:, 0] = idx
+        return (torch.randn(Bl, 40, device=dev, generator=gen), torch.randn(Bl, 24, device=dev, generator=gen), idx, cidx)
+    batches = [inputs() for _ in range(7)]
+    results = []
+    for mode in ("eager", "graph"):
+        torch.manual_seed(5)                      # same heads and the same bank shards in both arms
+        mod = ShardedCRDLoss(opt, device=dev)
+        params = list(mod.parameters())
+        optim = torch.optim.Adam(params, lr=1e-3, capturable=True, fused=True)
+        losses, grads = [], []
+        if mode == "graph":
+            step = pkg.GraphedTrainStep(lambda a, b, i, ci: mod(a, b, i, ci), params, optim, batches[0], grad_inputs=(0,),
+                                        warmup=1, n_buffers=2)
+            torch.cuda.synchronize()
+            dist.barrier()
+            for b in batches[1:]:
+                losses.append(step(*b).clone())
+                grads.append(step.static_in[(step._next - 1) % 2][0].grad.clone())
+        else:
+            for i, b in enumerate(batches):
+                f_s = b[0].clone().requires_grad_(True)
+                for p in params:
+                    p.grad = None
+                loss = mod(f_s, *b[1:])
+                loss.backward()
+                optim.step()
+                if i > 0:
+                    losses.append(loss.detach().clone())
+                    grads.append(f_s.grad.clone())
+                del loss
+        torch.cuda.synchronize()
+        dist.barrier()
+        m1, m2 = mod.contrast.gather_full_banks()
+        results.append((losses, grads, m1.clone(), [p.detach().clone() for p in params]))
+    (l0, g0, b0, p0), (l1, g1, b1, p1) = results
+    worst = 0.0
+    for a, b in list(zip(l0, l1)) + list(zip(g0, g1)) + [(b0, b1)] + list(zip(p0, p1)):
+        e = rel_err(b, a)
+        assert e < 1e-5, f"rank {rank}: graph vs eager rel {e:.3e}"
+        worst = max(worst, e)
+    # replicated heads stay bit-identical across ranks (same operands, same order in the symmetric-memory reduction)
+    w = p1[0].contiguous()
+    ws = [torch.empty_like(w) for _ in range(world)]
+    dist.all_gather(ws, w)
+    assert all(torch.equal(ws[0], x) for x in ws)
+    dist.barrier()
+    if rank == 0:
+        with open(result_path, "w") as f:
+            f.write(f"ok {worst:.3e}\n")
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    import torch.multiprocessing as mp
+    world, port, out = int(sys.argv[1]), int(sys.argv[2]), sys.argv[3]
+    mp.spawn(run, args=(world, port, out), nprocs=world, join=True)

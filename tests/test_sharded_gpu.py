@@ -29,3 +29,15 @@ def test_sharded_cuda_matches_reference_golden(tmp_path, name, transport):
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
     res = out.read_text()
     assert res.startswith("ok") and f"transport={transport}" in res, res + r.stdout[-1500:]
+
+
+def test_sharded_step_replayed_from_cuda_graph_equals_eager(tmp_path):
+    world = min(torch.cuda.device_count(), 4)
+    if world < 2:
+        pytest.skip("needs >= 2 GPUs")
+    out = tmp_path / "res.txt"
+    port = 29900 + os.getpid() % 90
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "_sharded_graph_worker.py"), str(world), str(port),
+                        str(out)], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+    assert out.read_text().startswith("ok")
