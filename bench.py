@@ -455,6 +455,33 @@ def run_gpu_arm(args):
                     "replayed as one CUDA graph (GraphedTrainStep), loss read back every step")
     e2e_value = world * 1000.0 / e2e_ms
 
+    # N3: contrast_idx produced ON THE DEVICE by the class-conditional sampler (what the reference's loader workers do with
+    # numpy, data_loaders_MT.py:222-249) inside the captured step: only f_s, f_t, idx cross PCIe.  Reported beside `e2e`.
+    e2e_sampler = None
+    if mode == "cuda_graph":
+        barrier()
+        labels = torch.randint(0, 3, (n,), generator=torch.Generator().manual_seed(7))
+        sampler_mod = pkg.InstanceSampler(labels, nce_k=K).cuda(dev)
+        s_optim = torch.optim.Adam(opt_params, lr=2e-4, betas=(0.9, 0.999), fused=True, capturable=True)
+        sstep = pkg.GraphedTrainStep(lambda a, b, c: mod(a, b, c, sampler_mod(c)), opt_params, s_optim, pool[0][:3],
+                                     grad_inputs=(0,), warmup=3, n_buffers=2)
+        barrier()
+        small_host = [hp[:3] for hp in host_pool]
+
+        def step_sampler(i):
+            for dst, src in zip(sstep.buffers(), small_host[i % len(small_host)]):
+                dst.detach().copy_(src, non_blocking=True)
+            return sstep.replay().item()
+
+        for i in range(4):
+            step_sampler(i)
+        barrier()
+        sm_ms = timed(step_sampler, args.steps) / args.steps
+        e2e_sampler = {"value": world * 1000.0 / sm_ms, "unit": "steps/s", "ms_per_step": sm_ms,
+                       "h2d_bytes_per_step": sum(t.numel() * t.element_size() for t in small_host[0]),
+                       "note": "contrast_idx drawn on the GPU by InstanceSampler (3 classes, exact positive, K negatives from "
+                               "the other classes) inside the replayed graph; loss read back every step"}
+
     # same call with the caller handing contrast_idx over as int32 (n_data < 2^31): half the PCIe bytes.  The reference's
     # loader yields int64, so this is reported beside `e2e`, not instead of it.
     e2e_i32 = None
@@ -521,6 +548,8 @@ def run_gpu_arm(args):
                 "d2h_bytes_per_step": 4, "note": e2e_note, "eager_ms_per_step": e2e_eager_ms},
         "gpu_launches": launches, "clocks": clocks,
     }
+    if e2e_sampler is not None:
+        line["e2e_instance_sampler"] = e2e_sampler
     if e2e_i32 is not None:
         line["e2e_int32_idx"] = e2e_i32
     if e2e_sampled is not None:

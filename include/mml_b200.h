@@ -141,6 +141,22 @@ int mml_crd_memory_update(
     const float* v1, const float* v2, const int64_t* y, int64_t B,
     float momentum, int64_t row_begin, int64_t row_end, void* stream);
 
+/* Class-conditional contrast indices on the device: what `Pathomic_InstanceSample.__getitem__`
+ * (data_loaders_MT.py:222-249) returns as `sample_idx = hstack(pos_idx, neg_idx)` for every anchor of the batch, written
+ * by one kernel instead of numpy draws in loader workers + a [B, P+K] int64 upload per step.
+ *   index      int64[B] anchors;  out int64[B, P+K]
+ *   labels     int32[n] class per sample ('grad' task) or NULL ('surv' task: negatives = every other sample, :222-227)
+ *   order      int32[n] sample ids sorted by class (stable), cls_ptr int32[num_classes+1]: cls_positive[c] =
+ *              order[cls_ptr[c]:cls_ptr[c+1]] (:193-195); cls_negative[c] = order without that segment (:197-202)
+ *   pos_mode   0 'exact' (pos = anchor), 1 'relax' (one member of the class), 2 'multi_pos' (P distinct members, first
+ *              overwritten by the anchor, :229-241)
+ *   negatives  K members of the pool, with replacement iff K > |pool| (:243), else distinct
+ * Randomness: Philox4x32-10 keyed by (seed ^ *seed_dev, anchor row, column); distinct draws = keyed Feistel bijection
+ * with cycle walking.  Restated bit-for-bit in oracle/sampler_oracle.py.  Pool members must be >= 1 where drawn from. */
+int mml_instance_sample(const int64_t* index, int64_t B, const int32_t* labels, const int32_t* order,
+                        const int32_t* cls_ptr, int32_t num_classes, int64_t n, int32_t P, int32_t K,
+                        int32_t pos_mode, uint64_t seed, const uint64_t* seed_dev, int64_t* out, void* stream);
+
 /* Normalize(2) of the Embed heads (CRD_criterion.py:242-245): y = x / ||x||_2 per row (no epsilon, as the
  * reference), norm[b] kept for the backward  gx = (gy - y * <gy, y>) / norm.  One launch each instead of the
  * reference's pow/sum/pow/div chain and its ~8-kernel autograd.                                          */

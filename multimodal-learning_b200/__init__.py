@@ -16,5 +16,6 @@ from .crd_select import ContrastLoss_v2, ContrastMemory_v2, ContrastMemory_v3
 from .fusion import BilinearFusion, PolynomialFusion, TrilinearFusion_A, TrilinearFusion_B, init_max_weights, kron_linear
 from .graphed import GraphedTrainStep
 from .kd_loss import DistillKL
+from .sampler import InstanceSampler
 
-__all__ = ["BilinearFusion", "PolynomialFusion", "TrilinearFusion_A", "TrilinearFusion_B", "init_max_weights", "kron_linear", "AliasMethod", "ContrastLoss", "ContrastMemory", "CRDLoss", "Embed", "Normalize", "DistillKL", "GraphedTrainStep", "crd_select", "ContrastLoss_v2", "ContrastMemory_v2", "ContrastMemory_v3", "_cabi"]
+__all__ = ["BilinearFusion", "PolynomialFusion", "TrilinearFusion_A", "TrilinearFusion_B", "init_max_weights", "kron_linear", "AliasMethod", "ContrastLoss", "ContrastMemory", "CRDLoss", "Embed", "Normalize", "DistillKL", "GraphedTrainStep", "InstanceSampler", "crd_select", "ContrastLoss_v2", "ContrastMemory_v2", "ContrastMemory_v3", "_cabi"]

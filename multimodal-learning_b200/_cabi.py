@@ -47,6 +47,8 @@ _SIGNATURES = {
     "mml_shard_scatter": (ctypes.c_int, [_P, c_int64, c_int64, c_int32, c_int64, c_int32, _P, _P, _P]),
     "mml_crd_memory_update": (ctypes.c_int, [
         _P, _P, c_int32, _P, _P, _P, c_int64, c_float, c_int64, c_int64, _P]),
+    "mml_instance_sample": (ctypes.c_int, [_P, c_int64, _P, _P, _P, c_int32, c_int64, c_int32, c_int32, c_int32,
+                                           ctypes.c_uint64, _P, _P, _P]),
     "mml_l2norm_fwd": (ctypes.c_int, [_P, c_int64, c_int32, _P, _P, _P]),
     "mml_l2norm_bwd": (ctypes.c_int, [_P, _P, _P, c_int64, c_int32, _P, _P]),
     "mml_alias_build_host": (ctypes.c_int, [_P, c_int64, _P, _P]),

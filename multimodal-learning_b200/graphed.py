@@ -16,7 +16,7 @@ Rules (checked where possible):
     the parameters' AccumulateGrad nodes to the stream those steps ran on, which breaks the capture);
   * run >= 1 eager step first (the constructor does `warmup` of them): the first CRD call sets Z with a host sync
     (`CRD_criterion.py:52-59`), the optimizer allocates its state, the Kronecker weights get packed;
-  * the optimizer must be capturable (`torch.optim.Adam(..., capturable=True)`; fused or foreach);
+  * the optimizer must be capturable (`torch.optim.Adam(..., capturable=True)`; plain SGD is as it is);
   * randomness must come from device state: torch's own dropout is graph-safe, and the Kronecker dropout of the fusion
     modules draws its per-call seed word on the device (`fusion.kron_linear`), so every replay gets a fresh mask;
   * replays change the parameters without bumping their autograd version counters; `replay` bumps them so that
@@ -45,8 +45,8 @@ class GraphedTrainStep:
         dev = example_inputs[0].device
         if dev.type != "cuda":
             raise RuntimeError("GraphedTrainStep needs CUDA tensors (no CPU path)")
-        for g in optimizer.param_groups:
-            if not g.get("capturable", False):
+        for g in optimizer.param_groups:       # Adam-family optimizers keep `step` on the host unless capturable=True
+            if "capturable" in g and not g["capturable"]:
                 raise RuntimeError("optimizer must be constructed with capturable=True to be replayed from a CUDA graph")
         self.static_in, self.static_loss, self.graphs = [], [], []
         side = torch.cuda.Stream(dev)

@@ -18,6 +18,6 @@ echo "== ncu full: gather"
 MML_BENCH_PROFILE=1 timeout 900 ncu --profile-from-start off --set full --clock-control none --import-source on \
     -k regex:crd_gather_kernel -c 2 -f -o $OUT/${TAG}_prof_crd python bench.py --steps 2 --warmup 3 --no-cpu > $OUT/${TAG}_ncu_full.log 2>&1
 echo "== ncu full: relation"
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:crd_relation_kernel -s 8 -c 1 -f -o $OUT/${TAG}_prof_rel \
-    python scripts/bench_select.py > $OUT/${TAG}_ncu_rel.log 2>&1
+MML_SELECT_ONLY=big timeout 600 ncu --set full --clock-control none --import-source on -k regex:crd_relation_kernel -s 4 -c 1 -f \
+    -o $OUT/${TAG}_prof_rel python scripts/bench_select.py > $OUT/${TAG}_ncu_rel.log 2>&1
 ls -la $OUT | tail -14
