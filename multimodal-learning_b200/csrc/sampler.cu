@@ -59,7 +59,7 @@ __host__ __device__ __forceinline__ uint32_t mix32(uint32_t h) {
 }
 
 // j-th element of a uniform draw of distinct members of [0, M): keyed Feistel bijection + cycle walking
-__device__ __forceinline__ uint32_t perm_element(uint32_t j, uint32_t M, const uint32_t key[4]) {
+__device__ __forceinline__ uint32_t perm_element(uint32_t j, uint32_t M, const uint32_t* key) {
   int bits = 32 - __clz(M - 1 > 0 ? M - 1 : 1);
   if (M <= 2) bits = 2;
   bits = (bits + 1) & ~1;                       // even
@@ -88,7 +88,6 @@ __global__ void __launch_bounds__(256) instance_sample_kernel(const SamplerArgs 
   const int64_t b = blockIdx.y;
   const int col = blockIdx.x * blockDim.x + threadIdx.x;
   const int cols = a.P + a.K;
-  if (col >= cols) return;
   uint32_t k0 = a.seed_lo, k1 = a.seed_hi;
   if (a.seed_dev != nullptr) {
     const unsigned long long s = __ldg(a.seed_dev);
@@ -97,7 +96,17 @@ __global__ void __launch_bounds__(256) instance_sample_kernel(const SamplerArgs 
   }
   const int64_t anchor = a.index[b];
   const uint32_t blo = static_cast<uint32_t>(b), bhi = static_cast<uint32_t>(static_cast<uint64_t>(b) >> 32);
-  uint32_t rnd[4], key[4];
+  // the Feistel keys depend on the anchor row only: one Philox evaluation per CTA, not per thread
+  __shared__ uint32_t sm_key[3][4];            // [0] survival negatives, [1] multi_pos positives, [2] class negatives
+  if (threadIdx.x < 3) {
+    const uint32_t c1 = threadIdx.x == 0 ? 1u : (threadIdx.x == 1 ? 3u : 5u);
+    const uint32_t tag = threadIdx.x == 0 ? 0x20000000u : (threadIdx.x == 1 ? 0x40000000u : 0x60000000u);
+    philox4x32_10(0u, c1, blo, bhi ^ tag, k0, k1, sm_key[threadIdx.x]);
+  }
+  __syncthreads();
+  if (col >= cols) return;
+  uint32_t rnd[4];
+  const uint32_t* key;
   int64_t result;
   if (a.labels == nullptr) {                                   // survival task (:222-227)
     if (col < a.P) {
@@ -110,7 +119,7 @@ __global__ void __launch_bounds__(256) instance_sample_kernel(const SamplerArgs 
         philox4x32_10(j, 0u, blo, bhi ^ 0x10000000u, k0, k1, rnd);
         e = bounded(rnd[0], M);
       } else {
-        philox4x32_10(0u, 1u, blo, bhi ^ 0x20000000u, k0, k1, key);
+        key = sm_key[0];
         e = perm_element(j, M, key);
       }
       result = e < anchor ? e : e + 1;                           // all_neg_idx.remove(index)
@@ -126,7 +135,7 @@ __global__ void __launch_bounds__(256) instance_sample_kernel(const SamplerArgs 
         philox4x32_10(static_cast<uint32_t>(col), 2u, blo, bhi ^ 0x30000000u, k0, k1, rnd);
         result = a.order[seg0 + bounded(rnd[0], Mp)];            // 'relax': one member of the anchor's class (:232)
       } else {
-        philox4x32_10(0u, 3u, blo, bhi ^ 0x40000000u, k0, k1, key);
+        key = sm_key[1];
         result = a.order[seg0 + perm_element(static_cast<uint32_t>(col), Mp, key)];   // 'multi_pos', replace=False (:237)
       }
     } else {
@@ -136,7 +145,7 @@ __global__ void __launch_bounds__(256) instance_sample_kernel(const SamplerArgs 
         philox4x32_10(j, 4u, blo, bhi ^ 0x50000000u, k0, k1, rnd);
         e = bounded(rnd[0], Mn);
       } else {
-        philox4x32_10(0u, 5u, blo, bhi ^ 0x60000000u, k0, k1, key);
+        key = sm_key[2];
         e = perm_element(j, Mn, key);
       }
       result = a.order[e < seg0 ? e : e + Mp];                   // cls_negative[c] = order minus class c's segment
