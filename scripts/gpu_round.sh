@@ -9,7 +9,6 @@ nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > $O
 echo "== pytest -m gpu" ; timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -25 | tee $OUT/${TAG}_pytest.txt
 echo "== smoke" ; timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -8 | tee $OUT/${TAG}_smoke.txt
 echo "== bench" ; timeout 600 python bench.py --steps 100 --warmup 10 2>&1 | tail -3 | tee $OUT/${TAG}_bench.json
-echo "== bench --eager" ; timeout 300 python bench.py --steps 100 --warmup 10 --eager --no-cpu 2>&1 | tail -1 | tee $OUT/${TAG}_bench_eager.json
 echo "== selection variant" ; timeout 300 python scripts/bench_select.py 2>&1 | grep config | tee $OUT/${TAG}_bench_select.jsonl
 echo "== ncu launches (timed region only: cudaProfilerStart/Stop around the K steps)"
 MML_BENCH_PROFILE=1 timeout 600 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv \

@@ -49,6 +49,8 @@ GOLDENS = ["bilinear_c1", "bilinear_skip", "bilinear_odd", "bilinear_scaled", "t
 def test_fusion_modules_match_reference_golden(pkg, golden, name, path):
     g = golden(name)
     tol = TOL_FP32 * 5 if path == "simt" else TOL_TC
+    if g.cfg["kind"] == "polynomial" and path == "auto":
+        tol = 2 * TOL_TC        # TWO chained TF32 contractions (2e-3 each, north_star) with a batch-12 BatchNorm between them
     nvec = 3 if g.cfg["kind"] == "trilinear" else 2
     modes = ["eval"] + (["train"] if any(k.startswith("train.") for k in g.keys()) else [])
     for tag in modes:
