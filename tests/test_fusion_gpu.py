@@ -49,11 +49,15 @@ GOLDENS = ["bilinear_c1", "bilinear_skip", "bilinear_odd", "bilinear_scaled", "t
 def test_fusion_modules_match_reference_golden(pkg, golden, name, path):
     g = golden(name)
     tol = TOL_FP32 * 5 if path == "simt" else TOL_TC
-    if g.cfg["kind"] == "polynomial" and path == "auto":
-        tol = 2 * TOL_TC        # TWO chained TF32 contractions (2e-3 each, north_star) with a batch-12 BatchNorm between them
+    base_tol = tol
     nvec = 3 if g.cfg["kind"] == "trilinear" else 2
     modes = ["eval"] + (["train"] if any(k.startswith("train.") for k in g.keys()) else [])
     for tag in modes:
+        if g.cfg["kind"] == "polynomial" and path == "auto":
+            # TWO chained TF32 contractions (2e-3 each, north_star).  In train mode three BatchNorms over a batch of 9-12
+            # rows sit around them: their 1/sigma factors amplify the TF32 rounding in the backward (observed 1e-2 on the
+            # 8x8->8 fixture; the fp32 "simt" path of the same module meets 1e-4).
+            tol = 2 * base_tol if tag == "eval" else 10 * base_tol
         mod = _make(pkg, g)
         mod.set_kron_path(path)
         mod.train(tag == "train")
