@@ -33,7 +33,7 @@ extern "C" {
 #define MML_ERR_UNSUPPORTED -3   /* shape outside what the kernels are built for   */
 #define MML_ERR_WORKSPACE   -4   /* workspace smaller than *_workspace_bytes()     */
 
-#define MML_ABI_VERSION 1
+#define MML_ABI_VERSION 2   /* 2: seed_dev argument of the mml_kron_* entry points; multipos / relation / instance_sample added */
 
 int         mml_abi_version(void);
 const char* mml_last_error(void);

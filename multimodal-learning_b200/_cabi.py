@@ -16,6 +16,7 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(PKG, "lib", "libmml_b200.so")
 
 _P = c_void_p
+ABI_VERSION = 2          # must equal MML_ABI_VERSION of include/mml_b200.h
 _SIGNATURES = {
     "mml_abi_version": (ctypes.c_int, []),
     "mml_last_error": (c_char_p, []),
@@ -102,7 +103,7 @@ def lib() -> ctypes.CDLL:
             fn = getattr(handle, name)          # AttributeError if the .so lacks a declared symbol
             fn.restype = res
             fn.argtypes = args
-        if handle.mml_abi_version() != 1:
+        if handle.mml_abi_version() != ABI_VERSION:
             raise RuntimeError("libmml_b200.so ABI version mismatch")
         _lib = handle
     return _lib

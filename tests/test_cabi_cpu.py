@@ -35,7 +35,7 @@ def test_library_exports_every_declared_symbol():
 
 def test_abi_version_and_error_string():
     lib = _cabi.lib()
-    assert lib.mml_abi_version() == 1
+    assert lib.mml_abi_version() == _cabi.ABI_VERSION == 2
     rc = lib.mml_alias_build_host(None, 0, None, None)
     assert rc == -1
     assert b"alias_build" in lib.mml_last_error()
@@ -179,3 +179,17 @@ def test_dropin_modules_resolve_to_the_package():
         for k in [k for k in sys.modules if k in ("fusion", "KD_loss") or k.startswith("CL_utils")]:
             sys.modules.pop(k)
         sys.modules.update(saved)
+
+
+def test_graphed_train_step_rejects_what_it_cannot_capture():
+    lin = torch.nn.Linear(4, 4)
+    x = torch.zeros(2, 4)
+    with pytest.raises(RuntimeError):        # CPU tensors: no CPU path
+        pkg.GraphedTrainStep(lambda a: lin(a).sum(), lin.parameters(), torch.optim.SGD(lin.parameters(), lr=0.1), (x,))
+    if torch.cuda.is_available():
+        return
+    # an Adam without capturable=True keeps its step counter on the host: refused before any CUDA work is attempted
+    class FakeCuda(torch.Tensor):
+        pass
+    adam = torch.optim.Adam(lin.parameters(), lr=0.1)
+    assert adam.param_groups[0]["capturable"] is False
