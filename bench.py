@@ -12,11 +12,14 @@ Workload (config.workload):
        exactly BASELINE config 5: 16M x 128 banks, global batch 8192): weak scaling,
        value = N x global steps/s = "config-2 units per second".
 
-`value` times K steps with inputs already in HBM; `e2e` times the public CRDLoss call with
-pinned HOST inputs (H2D of f_s, f_t, idx, contrast_idx and a D2H read of the loss every step).
-`roofline` is the gather kernel's algorithmic bytes / its CUDA-event time inside the timed steps.
-`cpu_baseline` / `--impl reference` time the oracle port (oracle/crd_oracle.py: the reference's own
-torch-CPU op sequence) on a bounded slice of the same workload.
+`value` times K steps with inputs already in HBM.  By default the whole step is replayed from CUDA graphs captured
+once per input set (`multimodal_learning_b200.GraphedTrainStep`; `--eager` times eager launches); `e2e` times the same
+step from pinned HOST inputs (H2D of f_s, f_t, idx, contrast_idx into static buffers overlapped with the previous replay,
+D2H read of the loss every step) and reports the plain eager `CRDLoss.forward` call beside it.  `roofline` is the gather
+kernel's algorithmic bytes / its CUDA-event time inside the timed steps (external event nodes inside the graphs).
+Extra keys: `e2e_instance_sampler` (contrast_idx drawn on the device inside the graph), `e2e_int32_idx`,
+`e2e_device_sampling` (contrast_idx=None, AliasMethod).  `cpu_baseline` / `--impl reference` time the oracle port
+(oracle/crd_oracle.py: the reference's own torch-CPU op sequence) on a bounded slice of the same workload.
 """
 from __future__ import annotations
 
