@@ -63,7 +63,7 @@ __global__ void __launch_bounds__(kThreadsTc, 1) kron_fwd_tc_kernel(const __grid
   uint64_t* bar_acc = bars + 2 * a.stages;      // accumulator complete
   uint32_t* sm_tmem = reinterpret_cast<uint32_t*>(bars + 2 * a.stages + 1);
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = warp_idx_sync();
   const int lane = threadIdx.x & 31;
   const int64_t b0 = static_cast<int64_t>(blockIdx.x) * kTileM;
   const int c_begin = blockIdx.y * a.chunks_per_split;
@@ -120,35 +120,38 @@ __global__ void __launch_bounds__(kThreadsTc, 1) kron_fwd_tc_kernel(const __grid
 
   if (warp == kGenWarps) {
     // ===================== TMA producer: weight tiles [Np x 32] =====================
-    if (lane == 0) {
-      int s = 0;
-      uint32_t ph = 0;
-      for (int c = c_begin; c < c_end; ++c) {
-        mbar_wait(&bar_empty[s], ph ^ 1);
+    int s = 0;
+    uint32_t ph = 0;
+    for (int c = c_begin; c < c_end; ++c) {
+      mbar_wait(&bar_empty[s], ph ^ 1);
+      if (elect_one_sync()) {
         mbar_arrive_expect_tx(&bar_full[s], stage_bytes);
         tma_load_2d(sm_b + static_cast<size_t>(s) * stage_bytes, &tmap_w, c * kChunkK, 0, &bar_full[s]);
-        if (++s == a.stages) { s = 0; ph ^= 1; }
       }
+      __syncwarp();
+      if (++s == a.stages) { s = 0; ph ^= 1; }
     }
   } else if (warp == kGenWarps + 1) {
-    // ===================== MMA issuer (one thread) =====================
-    if (lane == 0) {
-      int s = 0;
-      uint32_t ph = 0;
-      for (int c = c_begin; c < c_end; ++c) {
-        mbar_wait(&bar_full[s], ph);
-        tc_fence_after();
-        const uint32_t b_addr = smem_u32(sm_b + static_cast<size_t>(s) * stage_bytes);
+    // ===================== MMA issuer: the whole warp walks the ring, one elected lane issues =====================
+    int s = 0;
+    uint32_t ph = 0;
+    const uint32_t b_base = smem_u32(sm_b);
+    for (int c = c_begin; c < c_end; ++c) {
+      mbar_wait(&bar_full[s], ph);
+      tc_fence_after();
+      if (elect_one_sync()) {
+        const uint64_t b_desc = umma_desc_k_sw128(b_base + static_cast<uint32_t>(s) * stage_bytes);
+        const uint32_t a_col = tmem_a + s * kChunkK;
 #pragma unroll
-        for (int j = 0; j < kChunkK / 8; ++j) {
-          const uint64_t b_desc = umma_desc_k_sw128(b_addr + j * 32);            // +8 tf32 along K inside the swizzle row
-          tc_mma_tf32_ts(tmem_d, tmem_a + s * kChunkK + j * 8, b_desc, a.idesc, (c > c_begin || j > 0) ? 1u : 0u);
-        }
+        for (int j = 0; j < kChunkK / 8; ++j)                  // +8 tf32 along K = +32 B inside the swizzle row = +2 in the descriptor
+          tc_mma_tf32_ts(tmem_d, a_col + j * 8, b_desc + 2 * j, a.idesc, (c > c_begin || j > 0) ? 1u : 0u);
         tc_commit(&bar_empty[s]);          // frees the A columns and the B tile of this stage
-        if (++s == a.stages) { s = 0; ph ^= 1; }
       }
-      tc_commit(bar_acc);
+      __syncwarp();
+      if (++s == a.stages) { s = 0; ph ^= 1; }
     }
+    if (elect_one_sync()) tc_commit(bar_acc);
+    __syncwarp();
   } else {
     // ===================== A generators: thread = (batch row / TMEM lane, 16-column half of the chunk) =====================
     const int row = threadIdx.x & (kTileM - 1);

@@ -42,15 +42,15 @@ __global__ void __launch_bounds__(kThreadsTc, 1) kron_wgrad_tc_kernel(const __gr
   const uint32_t stage_bytes = static_cast<uint32_t>(a.Np) * 128u;
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* sm_b = smem;
-  float* sm_X = reinterpret_cast<float*>(smem + static_cast<size_t>(a.stages) * stage_bytes);   // [2][4][32 b][32 e]
-  float* sm_sc = sm_X + 2 * 4 * kBlkB * 32;                                                       // [2][4][32 b]
+  float* sm_X = reinterpret_cast<float*>(smem + static_cast<size_t>(a.stages) * stage_bytes);   // [3][4][32 b][32 e]
+  float* sm_sc = sm_X + 3 * 4 * kBlkB * 32;                                                       // [2][4][32 b]
   uint64_t* bars = reinterpret_cast<uint64_t*>(sm_sc + 2 * 4 * kBlkB);
   uint64_t* bar_full = bars;
   uint64_t* bar_empty = bars + a.stages;
   uint64_t* bar_acc = bars + 2 * a.stages;
   uint32_t* sm_tmem = reinterpret_cast<uint32_t*>(bars + 2 * a.stages + 1);
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = warp_idx_sync();
   const int lane = threadIdx.x & 31;
   const int c_first = blockIdx.x * 4;                                   // this CTA's 4 chunks = 128 packed k
   const int blk_begin = blockIdx.y * a.blocks_per_split;
@@ -78,34 +78,39 @@ __global__ void __launch_bounds__(kThreadsTc, 1) kron_wgrad_tc_kernel(const __gr
   const uint32_t tmem_a = tmem_base + static_cast<uint32_t>(a.Np);
 
   if (warp == kGenWarps) {
-    if (lane == 0) {                       // ===== TMA producer: dy^T tiles [Np x 32 batch rows] =====
-      int s = 0;
-      uint32_t ph = 0;
-      for (int blk = blk_begin; blk < blk_end; ++blk) {
-        mbar_wait(&bar_empty[s], ph ^ 1);
+    // ===== TMA producer: dy^T tiles [Np x 32 batch rows] (whole warp walks the ring, one elected lane issues) =====
+    int s = 0;
+    uint32_t ph = 0;
+    for (int blk = blk_begin; blk < blk_end; ++blk) {
+      mbar_wait(&bar_empty[s], ph ^ 1);
+      if (elect_one_sync()) {
         mbar_arrive_expect_tx(&bar_full[s], stage_bytes);
         tma_load_2d(sm_b + static_cast<size_t>(s) * stage_bytes, &tmap_dyT, blk * kBlkB, 0, &bar_full[s]);
-        if (++s == a.stages) { s = 0; ph ^= 1; }
       }
+      __syncwarp();
+      if (++s == a.stages) { s = 0; ph ^= 1; }
     }
   } else if (warp == kGenWarps + 1) {
-    if (lane == 0) {                       // ===== MMA issuer =====
-      int s = 0;
-      uint32_t ph = 0;
-      for (int blk = blk_begin; blk < blk_end; ++blk) {
-        mbar_wait(&bar_full[s], ph);
-        tc_fence_after();
-        const uint32_t b_addr = smem_u32(sm_b + static_cast<size_t>(s) * stage_bytes);
+    // ===== MMA issuer =====
+    int s = 0;
+    uint32_t ph = 0;
+    const uint32_t b_base = smem_u32(sm_b);
+    for (int blk = blk_begin; blk < blk_end; ++blk) {
+      mbar_wait(&bar_full[s], ph);
+      tc_fence_after();
+      if (elect_one_sync()) {
+        const uint64_t b_desc = umma_desc_k_sw128(b_base + static_cast<uint32_t>(s) * stage_bytes);
+        const uint32_t a_col = tmem_a + s * kBlkB;
 #pragma unroll
-        for (int j = 0; j < kBlkB / 8; ++j) {
-          const uint64_t b_desc = umma_desc_k_sw128(b_addr + j * 32);
-          tc_mma_tf32_ts(tmem_d, tmem_a + s * kBlkB + j * 8, b_desc, a.idesc, (blk > blk_begin || j > 0) ? 1u : 0u);
-        }
+        for (int j = 0; j < kBlkB / 8; ++j)
+          tc_mma_tf32_ts(tmem_d, a_col + j * 8, b_desc + 2 * j, a.idesc, (blk > blk_begin || j > 0) ? 1u : 0u);
         tc_commit(&bar_empty[s]);
-        if (++s == a.stages) { s = 0; ph ^= 1; }
       }
-      tc_commit(bar_acc);
+      __syncwarp();
+      if (++s == a.stages) { s = 0; ph ^= 1; }
     }
+    if (elect_one_sync()) tc_commit(bar_acc);
+    __syncwarp();
   } else {
     // ===== generators: thread = (packed-k lane t, 16 batch columns of the stage) =====
     const int gt = threadIdx.x;                        // 0..255
@@ -172,64 +177,76 @@ __global__ void __launch_bounds__(kThreadsTc, 1) kron_wgrad_tc_kernel(const __gr
         }
       }
     }
-    // Staging of one 32-row batch block, software-pipelined: the global loads of block blk+1 are issued into
-    // REGISTERS before block blk is computed and stored to the other shared buffer after it, so their latency
-    // hides behind the arithmetic.  Only slots that own a distinct vector segment are staged (usually one).
-    float xr[4][4];                    // [slot][j]
-#pragma unroll
-    for (int c = 0; c < 4; ++c)
-#pragma unroll
-      for (int j = 0; j < 4; ++j) xr[c][j] = 0.f;
-    float scr = 0.f;
-#define MML_WG_LOAD_BLOCK(BLK)                                                                          \
+    // Staging of 32-row batch blocks runs TWO blocks ahead of the arithmetic: the vector segments go global -> shared
+    // with cp.async (4-byte copies, zero-filled past the batch tail; three buffers), the per-row scalar factors ride in
+    // registers for two iterations and their product is parked in shared memory one block ahead.  Nothing in the loop
+    // waits on a global load it has just issued.
+    float scp1 = 1.f, scq1 = 1.f, scp2 = 1.f, scq2 = 1.f;      // raw scalar factors of blocks blk+1, blk+2 (gt < 128)
+    bool scv1 = false, scv2 = false;
+#define MML_WG_ISSUE_X(BLK, BUF)                                                                        \
     {                                                                                                   \
       const int64_t left64 = a.B - static_cast<int64_t>(BLK) * kBlkB;                                   \
-      const int left = left64 > kBlkB ? kBlkB : static_cast<int>(left64);                               \
+      const int left = left64 > kBlkB ? kBlkB : (left64 < 0 ? 0 : static_cast<int>(left64));            \
+      float* Xs = sm_X + (BUF) * (4 * kBlkB * 32) + sr * 32 + se;                                       \
       _Pragma("unroll") for (int c = 0; c < 4; ++c) {                                                   \
         if (own[c]) {                                                                                   \
           _Pragma("unroll") for (int j = 0; j < 4; ++j) {                                               \
             const bool rv = (sr + 8 * j) < left;                                                        \
-            float x = (xone[c] && rv) ? 1.0f : 0.f;                                                     \
-            if (xld[c] && rv) x = __ldg(xp[c] + j * 8 * xrow[c]);                                       \
-            xr[c][j] = x;                                                                               \
+            float* dstp = Xs + c * (kBlkB * 32) + j * 8 * 32;                                           \
+            if (xld[c]) {                                                                               \
+              const float* srcp = rv ? xp[c] + j * 8 * xrow[c] : a.f1;                                  \
+              asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(smem_u32(dstp)),        \
+                           "l"(srcp), "r"(rv ? 4 : 0) : "memory");                                      \
+            } else {                                                                                    \
+              *dstp = (xone[c] && rv) ? 1.0f : 0.f;                                                     \
+            }                                                                                           \
           }                                                                                             \
           xp[c] += kBlkB * xrow[c];                                                                     \
         }                                                                                               \
       }                                                                                                 \
+      asm volatile("cp.async.commit_group;" ::: "memory");                                              \
+    }
+#define MML_WG_LOAD_SC(BLK, P, Q, V)                                                                    \
+    {                                                                                                   \
       if (gt < 128) {                                                                                   \
-        float sc = 0.f;                                                                                 \
-        if (sc_valid && (gt & 31) < left) {                                                             \
-          sc = (spp ? __ldg(spp) : 1.0f) * (sqp ? __ldg(sqp) : 1.0f);                                   \
-          if (kDropout) sc *= a.dr.scale;                                                               \
-        }                                                                                               \
+        const int64_t left64 = a.B - static_cast<int64_t>(BLK) * kBlkB;                                 \
+        V = sc_valid && static_cast<int64_t>(gt & 31) < left64;                                         \
+        P = (V && spp) ? __ldg(spp) : 1.0f;                                                             \
+        Q = (V && sqp) ? __ldg(sqp) : 1.0f;                                                             \
         if (spp) spp += kBlkB * sprow;                                                                  \
         if (sqp) sqp += kBlkB * sqrow;                                                                  \
-        scr = sc;                                                                                       \
       }                                                                                                 \
     }
-#define MML_WG_STORE_BLOCK(BUF)                                                                         \
+#define MML_WG_STORE_SC(BUF, P, Q, V)                                                                   \
     {                                                                                                   \
-      float* Xs = sm_X + (BUF) * (4 * kBlkB * 32) + sr * 32 + se;                                       \
-      _Pragma("unroll") for (int c = 0; c < 4; ++c)                                                     \
-        if (own[c]) {                                                                                   \
-          _Pragma("unroll") for (int j = 0; j < 4; ++j) Xs[c * (kBlkB * 32) + j * 8 * 32] = xr[c][j];   \
-        }                                                                                               \
-      if (gt < 128) sm_sc[(BUF) * (4 * kBlkB) + gt] = scr;                                              \
+      if (gt < 128) {                                                                                   \
+        float sc = V ? P * Q : 0.f;                                                                     \
+        if (kDropout) sc *= a.dr.scale;                                                                 \
+        sm_sc[(BUF) * (4 * kBlkB) + gt] = sc;                                                           \
+      }                                                                                                 \
     }
 
     int s = 0, s_prev = -1;
     uint32_t ph = 0;
     if (blk_begin < blk_end) {
-      MML_WG_LOAD_BLOCK(blk_begin)
-      MML_WG_STORE_BLOCK(0)
+      MML_WG_ISSUE_X(blk_begin, 0)
+      MML_WG_ISSUE_X(blk_begin + 1, 1)
+      MML_WG_LOAD_SC(blk_begin, scp1, scq1, scv1)
+      MML_WG_STORE_SC(0, scp1, scq1, scv1)
+      MML_WG_LOAD_SC(blk_begin + 1, scp1, scq1, scv1)
     }
+    int xbuf = 0;                                                    // (blk - blk_begin) % 3
     for (int blk = blk_begin; blk < blk_end; ++blk) {
-      const int buf = (blk - blk_begin) & 1;
-      asm volatile("bar.sync 1, 256;" ::: "memory");                 // staging of `buf` visible; other buffer free
-      const bool more = blk + 1 < blk_end;
-      if (more) MML_WG_LOAD_BLOCK(blk + 1)
-      const float* X = sm_X + buf * (4 * kBlkB * 32) + my_slot * (kBlkB * 32);
-      const float* S = sm_sc + buf * (4 * kBlkB) + ci * kBlkB;
+      const int it = blk - blk_begin;
+      asm volatile("cp.async.wait_group 1;" ::: "memory");           // this thread's copies of block blk have landed
+      asm volatile("bar.sync 1, 256;" ::: "memory");                 // everyone's have; buffers of block blk-1 are free
+      {
+        const int nbuf = xbuf == 0 ? 2 : xbuf - 1;                   // (it + 2) % 3
+        MML_WG_ISSUE_X(blk + 2, nbuf)
+      }
+      MML_WG_LOAD_SC(blk + 2, scp2, scq2, scv2)
+      const float* X = sm_X + xbuf * (4 * kBlkB * 32) + my_slot * (kBlkB * 32);
+      const float* S = sm_sc + (it & 1) * (4 * kBlkB) + ci * kBlkB;
       const int64_t b0 = static_cast<int64_t>(blk) * kBlkB;
       uint32_t r[kHalf];
       float sv[kHalf];
@@ -260,8 +277,11 @@ __global__ void __launch_bounds__(kThreadsTc, 1) kron_wgrad_tc_kernel(const __gr
       tc_st_32x32b_x16(tmem_a + lane_base + s * kBlkB + half * kHalf, r);
       s_prev = s;
       if (++s == a.stages) { s = 0; ph ^= 1; }
-      if (more) MML_WG_STORE_BLOCK(buf ^ 1)
+      MML_WG_STORE_SC((it + 1) & 1, scp1, scq1, scv1)                // block blk+1's scalars, loaded one iteration ago
+      scp1 = scp2; scq1 = scq2; scv1 = scv2;
+      xbuf = xbuf == 2 ? 0 : xbuf + 1;
     }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
     if (s_prev >= 0) {
       tc_wait_st();
       tc_fence_before();
@@ -351,7 +371,7 @@ WgPlan make_wg_plan(int64_t B, int32_t N, int32_t d1, int32_t d2, int32_t d3) {
   p.ktiles = (p.nchunks + 3) / 4;
   p.nblocks = static_cast<int32_t>((B + kBlkB - 1) / kBlkB);
   p.Bpad = static_cast<int64_t>(p.nblocks) * kBlkB;
-  const size_t fixed = (2 * 4 * kBlkB * 32 + 2 * 4 * kBlkB) * sizeof(float) + 256 + 1024;
+  const size_t fixed = (3 * 4 * kBlkB * 32 + 2 * 4 * kBlkB) * sizeof(float) + 256 + 1024;
   const size_t stage = static_cast<size_t>(p.Np) * 128;
   int stages = static_cast<int>((227 * 1024 - fixed) / stage);
   if (stages > 4) stages = 4;
@@ -464,10 +484,13 @@ extern "C" int mml_kron_linear_wgrad(const float* f1, const float* f2, const flo
 namespace mml {
 namespace {
 
-constexpr int kDgThreads = 192;           // 4 epilogue warps (one thread per batch row) + TMA warp + MMA warp
+constexpr int kDgEpiWarps = 8;            // epilogue warp g: TMEM lanes 32*(g%4).., elements 16*(g/4).. of every chunk
+constexpr int kDgEpiThreads = kDgEpiWarps * 32;
+constexpr int kDgThreads = kDgEpiThreads + 64;   // + TMA warp + MMA warp
 constexpr int kDgTileK = 128;             // packed k per accumulator tile (4 chunks)
 constexpr int kDgBoxN = 32;               // n per TMA box / pipeline stage
 constexpr uint32_t kDgStageBytes = kDgTileK * kDgBoxN * 4;   // 16 KB
+constexpr int kDgDsFloats = 2 * 4 * 2 * kTileM;              // sm_ds [tile parity][chunk][half][row]
 
 struct DgArgs {
   const float* f1;
@@ -485,6 +508,15 @@ struct DgArgs {
   KronDropout dr;
 };
 
+// two fp32 FMAs per issue slot (FFMA2): d = a * b + d on a pair of registers
+__device__ __forceinline__ void ffma2(float& d0, float& d1, float a0, float a1, float b0, float b1) {
+  asm("{\n\t.reg .b64 ra, rb, rc;\n\t"
+      "mov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tmov.b64 rc, {%0, %1};\n\t"
+      "fma.rn.f32x2 rc, ra, rb, rc;\n\tmov.b64 {%0, %1}, rc;\n\t}"
+      : "+f"(d0), "+f"(d1)
+      : "f"(a0), "f"(a1), "f"(b0), "f"(b1));
+}
+
 template <bool kDropout>
 __global__ void __launch_bounds__(kDgThreads, 1) kron_dgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_wT, const DgArgs a) {
   uint32_t seed_lo = 0u, seed_hi = 0u;
@@ -494,22 +526,23 @@ __global__ void __launch_bounds__(kDgThreads, 1) kron_dgrad_tc_kernel(const __gr
   uint8_t* sm_b = smem;                                                              // [stages][16 KB]
   float* sm_S = reinterpret_cast<float*>(smem + static_cast<size_t>(a.stages) * kDgStageBytes);   // R values  [n_scal][128]
   float* sm_dR = sm_S + static_cast<size_t>(a.n_scal) * kTileM;                                   // dR accum  [n_scal][128]
-  int4* sm_tab = reinterpret_cast<int4*>(sm_dR + static_cast<size_t>(a.n_scal) * kTileM);
+  float* sm_ds = sm_dR + static_cast<size_t>(a.n_scal) * kTileM;                                  // per-chunk <dA, x> halves
+  int4* sm_tab = reinterpret_cast<int4*>(sm_ds + kDgDsFloats);
   uint64_t* bars = reinterpret_cast<uint64_t*>(sm_tab + (a.table_in_smem ? 2 * a.nchunks : 0));
   uint64_t* bar_full = bars;                     // [stages] weight box landed
   uint64_t* bar_empty = bars + a.stages;         // [stages] MMAs reading the box done
   uint64_t* bar_acc_full = bars + 2 * a.stages;  // [2] accumulator tile complete
-  uint64_t* bar_acc_empty = bar_acc_full + 2;    // [2] epilogue drained the tile (4 warp arrivals)
+  uint64_t* bar_acc_empty = bar_acc_full + 2;    // [2] epilogue has read the tile out of TMEM (8 warp arrivals)
   uint32_t* sm_tmem = reinterpret_cast<uint32_t*>(bar_acc_empty + 2);
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = warp_idx_sync();
   const int lane = threadIdx.x & 31;
   const int64_t b0 = static_cast<int64_t>(blockIdx.x) * kTileM;
   const int t_begin = blockIdx.y * a.tiles_per_split;
   const int t_end = min(a.ktiles, t_begin + a.tiles_per_split);
   const int nbox = a.Np32 / kDgBoxN;
 
-  if (warp == 4 && lane == 0) {
+  if (warp == kDgEpiWarps && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_wT)) : "memory");
     for (int s = 0; s < a.stages; ++s) {
       mbar_init(&bar_full[s], 1);
@@ -517,36 +550,42 @@ __global__ void __launch_bounds__(kDgThreads, 1) kron_dgrad_tc_kernel(const __gr
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&bar_acc_full[i], 1);
-      mbar_init(&bar_acc_empty[i], 4);
+      mbar_init(&bar_acc_empty[i], kDgEpiWarps);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 5) {
+  if (warp == kDgEpiWarps + 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(sm_tmem)), "r"(a.tmem_cols)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   if (a.table_in_smem)
     for (int i = t_begin * 8 + threadIdx.x; i < min(a.nchunks, t_end * 4) * 2; i += kDgThreads) sm_tab[i] = __ldg(a.table + i);
-  if (warp < 4) {
-    const int row = threadIdx.x;
+  if (warp < kDgEpiWarps) {
+    // per-row scalars R = [1, f1, (f2)] transposed into shared memory; row r is served by threads r and r + 128
+    const int row = threadIdx.x & (kTileM - 1);
+    const int half = threadIdx.x >> 7;
     const int64_t b = b0 + row;
     const bool live = b < a.B;
     const int ns = a.n_scal - 1;
-    sm_S[row] = 1.0f;
-    sm_dR[row] = 0.f;
-    for (int i0 = 0; i0 < ns; i0 += 8) {
+    const int per = (ns + 1) / 2;
+    const int lo = half * per, hi = min(ns, lo + per);
+    if (half == 0) {
+      sm_S[row] = 1.0f;
+      sm_dR[row] = 0.f;
+    }
+    for (int i0 = lo; i0 < hi; i0 += 8) {
       float tmp[8];
 #pragma unroll
       for (int u = 0; u < 8; ++u) {
         const int i = i0 + u;
         float x = 0.f;
-        if (live && i < ns) x = (i < a.d1) ? __ldg(a.f1 + b * a.d1 + i) : __ldg(a.f2 + b * a.d2 + (i - a.d1));
+        if (live && i < hi) x = (i < a.d1) ? __ldg(a.f1 + b * a.d1 + i) : __ldg(a.f2 + b * a.d2 + (i - a.d1));
         tmp[u] = x;
       }
 #pragma unroll
       for (int u = 0; u < 8; ++u)
-        if (i0 + u < ns) {
+        if (i0 + u < hi) {
           sm_S[(1 + i0 + u) * kTileM + row] = tmp[u];
           sm_dR[(1 + i0 + u) * kTileM + row] = 0.f;
         }
@@ -559,16 +598,15 @@ __global__ void __launch_bounds__(kDgThreads, 1) kron_dgrad_tc_kernel(const __gr
   const uint32_t tmem_acc = tmem_base;                 // 2 x 128 accumulator columns
   const uint32_t tmem_a = tmem_base + 2 * kDgTileK;    // dy tile: Np32 columns
   const int4* tab = a.table_in_smem ? sm_tab : a.table;
-  uint64_t* bar_a_ready = bar_acc_empty;               // (reuse note: A readiness is signalled through __syncthreads below)
-  (void)bar_a_ready;
 
   // ---- A operand: this CTA's dy rows -> TMEM, once (epilogue warps), then a CTA-wide sync publishes them ----
-  if (warp < 4) {
-    const int row = threadIdx.x;
+  if (warp < kDgEpiWarps) {
+    const int row = threadIdx.x & (kTileM - 1);
+    const int half = threadIdx.x >> 7;
     const int64_t b = b0 + row;
     const bool live = b < a.B;
-    const uint32_t lane_base = static_cast<uint32_t>(warp * 32) << 16;
-    for (int n0 = 0; n0 < a.Np32; n0 += 16) {
+    const uint32_t lane_base = static_cast<uint32_t>((warp & 3) * 32) << 16;
+    for (int n0 = half * 16; n0 < a.Np32; n0 += 32) {
       uint32_t r[16];
 #pragma unroll
       for (int u = 0; u < 16; ++u) {
@@ -584,124 +622,165 @@ __global__ void __launch_bounds__(kDgThreads, 1) kron_dgrad_tc_kernel(const __gr
   __syncthreads();
   tc_fence_after();
 
-  if (warp == 4) {
-    if (lane == 0) {                     // ===== TMA producer: [128 k x 32 n] boxes of WpT =====
-      int s = 0;
-      uint32_t ph = 0;
-      for (int t = t_begin; t < t_end; ++t)
-        for (int j = 0; j < nbox; ++j) {
-          mbar_wait(&bar_empty[s], ph ^ 1);
+  if (warp == kDgEpiWarps) {
+    // ===== TMA producer: [128 k x 32 n] boxes of WpT (whole warp walks the ring, one elected lane issues) =====
+    int s = 0;
+    uint32_t ph = 0;
+    for (int t = t_begin; t < t_end; ++t)
+      for (int j = 0; j < nbox; ++j) {
+        mbar_wait(&bar_empty[s], ph ^ 1);
+        if (elect_one_sync()) {
           mbar_arrive_expect_tx(&bar_full[s], kDgStageBytes);
           tma_load_2d(sm_b + static_cast<size_t>(s) * kDgStageBytes, &tmap_wT, j * kDgBoxN, t * kDgTileK, &bar_full[s]);
-          if (++s == a.stages) { s = 0; ph ^= 1; }
         }
-    }
-  } else if (warp == 5) {
-    if (lane == 0) {                     // ===== MMA issuer =====
-      int s = 0;
-      uint32_t ph = 0;
-      for (int t = t_begin; t < t_end; ++t) {
-        const int it = t - t_begin;
-        const int buf = it & 1;
-        mbar_wait(&bar_acc_empty[buf], ((it >> 1) & 1) ^ 1);            // epilogue has drained this accumulator
+        __syncwarp();
+        if (++s == a.stages) { s = 0; ph ^= 1; }
+      }
+  } else if (warp == kDgEpiWarps + 1) {
+    // ===== MMA issuer =====
+    int s = 0;
+    uint32_t ph = 0;
+    const uint32_t b_base = smem_u32(sm_b);
+    for (int t = t_begin; t < t_end; ++t) {
+      const int it = t - t_begin;
+      const int buf = it & 1;
+      mbar_wait(&bar_acc_empty[buf], ((it >> 1) & 1) ^ 1);            // epilogue has drained this accumulator
+      tc_fence_after();
+      for (int j = 0; j < nbox; ++j) {
+        mbar_wait(&bar_full[s], ph);
         tc_fence_after();
-        for (int j = 0; j < nbox; ++j) {
-          mbar_wait(&bar_full[s], ph);
-          tc_fence_after();
-          const uint32_t b_addr = smem_u32(sm_b + static_cast<size_t>(s) * kDgStageBytes);
+        if (elect_one_sync()) {
+          const uint64_t b_desc = umma_desc_k_sw128(b_base + static_cast<uint32_t>(s) * kDgStageBytes);
+          const uint32_t a_col = tmem_a + j * kDgBoxN;
 #pragma unroll
-          for (int i = 0; i < kDgBoxN / 8; ++i) {
-            const uint64_t b_desc = umma_desc_k_sw128(b_addr + i * 32);
-            tc_mma_tf32_ts(tmem_acc + buf * kDgTileK, tmem_a + j * kDgBoxN + i * 8, b_desc, a.idesc, (j > 0 || i > 0) ? 1u : 0u);
-          }
+          for (int i = 0; i < kDgBoxN / 8; ++i)
+            tc_mma_tf32_ts(tmem_acc + buf * kDgTileK, a_col + i * 8, b_desc + 2 * i, a.idesc, (j > 0 || i > 0) ? 1u : 0u);
           tc_commit(&bar_empty[s]);
-          if (++s == a.stages) { s = 0; ph ^= 1; }
+          if (j == nbox - 1) tc_commit(&bar_acc_full[buf]);
         }
-        tc_commit(&bar_acc_full[buf]);
+        __syncwarp();
+        if (++s == a.stages) { s = 0; ph ^= 1; }
       }
     }
   } else {
-    // ===== epilogue: thread = batch row; fold dA tiles into factor gradients =====
-    const int row = threadIdx.x;
+    // ===== epilogue: thread = (batch row, 16-element half of every chunk); fold dA tiles into factor gradients =====
+    const int row = threadIdx.x & (kTileM - 1);
+    const int half = threadIdx.x >> 7;
+    const int eb = half * kHalf;
     const int64_t b = b0 + row;
     const bool live = b < a.B;
-    const uint32_t lane_base = static_cast<uint32_t>(warp * 32) << 16;
+    const uint32_t lane_base = static_cast<uint32_t>((warp & 3) * 32) << 16;
     float* my_part = a.part + (static_cast<int64_t>(blockIdx.y) * a.B + b) * a.dsum;
-    float v[32], dv[32];
+    float v[kHalf], dv[kHalf];
 #pragma unroll
-    for (int e = 0; e < 32; ++e) { v[e] = 0.f; dv[e] = 0.f; }
+    for (int e = 0; e < kHalf; ++e) { v[e] = 0.f; dv[e] = 0.f; }
     int cur_src = -1, cur_col = -1, cur_len = 0;
-    auto flush = [&]() {
+    auto flush = [&]() {            // read-modify-write of <= 16 floats: all loads in flight together, then the stores
       if (cur_src > 0 && live) {
-        const int off = (cur_src == 1 ? 0 : (cur_src == 2 ? a.d1 : a.d1 + a.d2)) + cur_col;
+        float* dst = my_part + (cur_src == 1 ? 0 : (cur_src == 2 ? a.d1 : a.d1 + a.d2)) + cur_col + eb;
+        float old[kHalf];
 #pragma unroll
-        for (int e = 0; e < 32; ++e)
-          if (e < cur_len) my_part[off + e] += dv[e];
+        for (int e = 0; e < kHalf; ++e) old[e] = (eb + e < cur_len) ? dst[e] : 0.f;
+#pragma unroll
+        for (int e = 0; e < kHalf; ++e)
+          if (eb + e < cur_len) dst[e] = old[e] + dv[e];
       }
     };
     for (int t = t_begin; t < t_end; ++t) {
       const int it = t - t_begin;
       const int buf = it & 1;
+      float* ds_slot = sm_ds + (it & 1) * (4 * 2 * kTileM) + half * kTileM + row;     // + c * 2 * kTileM
       mbar_wait(&bar_acc_full[buf], (it >> 1) & 1);
       tc_fence_after();
+      const uint32_t t_addr = tmem_acc + lane_base + buf * kDgTileK + eb;
+      uint32_t acc[kHalf];
+      tc_ld_32x32b_x16(t_addr, acc);
+#pragma unroll 1
       for (int c = 0; c < 4; ++c) {
         const int cg = t * 4 + c;
-        if (cg >= a.nchunks) break;
-        const int4 e0 = tab[2 * cg];
-        const int4 e1 = tab[2 * cg + 1];
-        if (e0.z != cur_src || e0.w != cur_col) {
+        const bool cvalid = cg < a.nchunks;
+        const int4 e0 = cvalid ? tab[2 * cg] : make_int4(0, 0, 0, 0);
+        const int4 e1 = cvalid ? tab[2 * cg + 1] : make_int4(0, 0, 1, 0);
+        if (cvalid && (e0.z != cur_src || e0.w != cur_col)) {
           flush();
           cur_src = e0.z; cur_col = e0.w; cur_len = e1.x;
           const float* src = cur_src == 1 ? a.f1 : (cur_src == 2 ? a.f2 : a.f3);
           const int d = cur_src == 1 ? a.d1 : (cur_src == 2 ? a.d2 : a.d3);
 #pragma unroll
-          for (int e = 0; e < 32; ++e) {
+          for (int e = 0; e < kHalf; ++e) {
             float x = 0.f;
-            if (cur_src == 0) x = (e == 0) ? 1.0f : 0.f;
-            else if (live && e < cur_len) x = __ldg(src + b * d + cur_col + e);
+            if (cur_src == 0) x = (eb + e == 0) ? 1.0f : 0.f;
+            else if (live && eb + e < cur_len) x = __ldg(src + b * d + cur_col + eb + e);
             v[e] = x;
             dv[e] = 0.f;
           }
         }
-        uint32_t acc[32];
-        tc_ld_32x32b_x16(tmem_acc + lane_base + buf * kDgTileK + c * 32, *reinterpret_cast<uint32_t(*)[16]>(&acc[0]));
-        tc_ld_32x32b_x16(tmem_acc + lane_base + buf * kDgTileK + c * 32 + 16, *reinterpret_cast<uint32_t(*)[16]>(&acc[16]));
-        tc_wait_ld();
         const float sp = sm_S[e0.x * kTileM + row], sq = sm_S[e0.y * kTileM + row];
         float s = sp * sq;
         if (kDropout) s *= a.dr.scale;
-        float ds = 0.f;
+        tc_wait_ld();
+        float g[kHalf];
 #pragma unroll
-        for (int e = 0; e < 32; ++e) {
-          float g = __uint_as_float(acc[e]);
-          if (kDropout) {
-            const int klog = e1.y + e * e1.z;
+        for (int e = 0; e < kHalf; ++e) g[e] = __uint_as_float(acc[e]);
+        if (c < 3) tc_ld_32x32b_x16(t_addr + (c + 1) * 32, acc);          // next chunk's dA in flight behind this one's math
+        if (kDropout) {
+#pragma unroll
+          for (int e = 0; e < kHalf; ++e) {
+            const int klog = e1.y + (eb + e) * e1.z;
             const int64_t cc = b * a.dr.pairs_per_row + (klog >> 1);
             const uint32_t h = kron_hash(static_cast<uint32_t>(cc), static_cast<uint32_t>(static_cast<uint64_t>(cc) >> 32),
                                          seed_lo, seed_hi);
             const uint32_t r16 = (klog & 1) ? (h >> 16) : (h & 0xffffu);
-            g = (r16 >= a.dr.thresh) ? g : 0.f;
+            g[e] = (r16 >= a.dr.thresh) ? g[e] : 0.f;
           }
-          ds = fmaf(g, v[e], ds);
-          dv[e] = fmaf(g, s, dv[e]);
         }
-        if (kDropout) ds *= a.dr.scale;
-        if (e0.x != 0) sm_dR[e0.x * kTileM + row] += ds * sq;
-        if (e0.y != 0) sm_dR[e0.y * kTileM + row] += ds * sp;
+        float ds0 = 0.f, ds1 = 0.f, ds2 = 0.f, ds3 = 0.f;
+#pragma unroll
+        for (int e = 0; e < kHalf; e += 4) {
+          ffma2(ds0, ds1, g[e], g[e + 1], v[e], v[e + 1]);
+          ffma2(ds2, ds3, g[e + 2], g[e + 3], v[e + 2], v[e + 3]);
+          ffma2(dv[e], dv[e + 1], g[e], g[e + 1], s, s);
+          ffma2(dv[e + 2], dv[e + 3], g[e + 2], g[e + 3], s, s);
+        }
+        ds_slot[c * 2 * kTileM] = cvalid ? (ds0 + ds1) + (ds2 + ds3) : 0.f;
       }
-      tc_fence_before();
+      tc_fence_before();                    // this warp's TMEM reads of the tile are complete (wait::ld above)
       __syncwarp();
       if (lane == 0) mbar_arrive(&bar_acc_empty[buf]);
+      asm volatile("bar.sync 1, %0;" ::"n"(kDgEpiThreads) : "memory");      // both halves of every row have posted <dA, x>
+      if (half == 0) {
+        // dR[p] += <dA, x> R[q],  dR[q] += <dA, x> R[p]; one thread per row owns the dR columns -> fixed summation order
+        const float* dsr = sm_ds + (it & 1) * (4 * 2 * kTileM) + row;
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+          const int cg = t * 4 + c;
+          if (cg >= a.nchunks) break;
+          const int4 e0 = tab[2 * cg];
+          if ((e0.x | e0.y) == 0) continue;
+          float ds = dsr[c * 2 * kTileM] + dsr[c * 2 * kTileM + kTileM];
+          if (kDropout) ds *= a.dr.scale;
+          const float sp = sm_S[e0.x * kTileM + row], sq = sm_S[e0.y * kTileM + row];
+          if (e0.x != 0) sm_dR[e0.x * kTileM + row] += ds * sq;
+          if (e0.y != 0) sm_dR[e0.y * kTileM + row] += ds * sp;
+        }
+      }
     }
     flush();
-    if (live) {
+    if (live && half == 0) {
       const int ns = a.n_scal - 1;                      // R[1..] = f1 (then f2 when trilinear): same offsets as the output layout
-      for (int i = 0; i < ns; ++i) my_part[i] += sm_dR[(1 + i) * kTileM + row];
+      for (int i0 = 0; i0 < ns; i0 += 16) {
+        float old[16];
+#pragma unroll
+        for (int u = 0; u < 16; ++u) old[u] = (i0 + u < ns) ? my_part[i0 + u] : 0.f;
+#pragma unroll
+        for (int u = 0; u < 16; ++u)
+          if (i0 + u < ns) my_part[i0 + u] = old[u] + sm_dR[(1 + i0 + u) * kTileM + row];
+      }
     }
     tc_fence_before();
   }
   __syncthreads();
-  if (warp == 5) {
+  if (warp == kDgEpiWarps + 1) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(a.tmem_cols) : "memory");
   }
@@ -756,7 +835,8 @@ DgPlan make_dg_plan(int64_t B, int32_t N, int32_t d1, int32_t d2, int32_t d3) {
   p.ktiles = (p.nchunks + 3) / 4;
   const size_t table_bytes = static_cast<size_t>(p.nchunks) * sizeof(Chunk);
   p.table_in_smem = table_bytes <= static_cast<size_t>(kMaxSmemTable) ? 1 : 0;
-  const size_t fixed = 2 * static_cast<size_t>(p.n_scal) * kTileM * sizeof(float) + (p.table_in_smem ? table_bytes : 0) + 256 + 1024;
+  const size_t fixed = 2 * static_cast<size_t>(p.n_scal) * kTileM * sizeof(float) + kDgDsFloats * sizeof(float) +
+                       (p.table_in_smem ? table_bytes : 0) + 256 + 1024;
   int stages = fixed + 2 * kDgStageBytes <= 227 * 1024 ? static_cast<int>((227 * 1024 - fixed) / kDgStageBytes) : 0;
   if (stages > 6) stages = 6;
   p.stages = stages;

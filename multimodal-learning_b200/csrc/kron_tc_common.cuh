@@ -101,6 +101,21 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* t
       ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(c0), "r"(c1), "r"(smem_u32(bar))
       : "memory");
 }
+// One lane of a fully converged warp.  ptxas knows the region guarded by elect.sync runs on a single thread, so the
+// uniform-datapath instructions inside it (UTCHMMA / UTCBAR / UTMALDG) are issued directly; guarding them with
+// `lane == 0` instead makes the compiler wrap every one of them in an ELECT / R2UR.BROADCAST / BRA.U.ANY loop, which
+// costs ~150 issue cycles per MMA and was THE bound of the round-1 kernels (profiles/r2_*).
+__device__ __forceinline__ bool elect_one_sync() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred)::"memory");
+  return pred != 0;
+}
+// warp index as a provably warp-uniform value (role dispatch without divergence)
+__device__ __forceinline__ int warp_idx_sync() { return __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint64_t* bar) {

@@ -151,13 +151,21 @@ def kron_dropout_mask(seed: int, B: int, Kk: int, p: float) -> torch.Tensor:
     that does not exist, so mask parity with the reference is "unpinned" by construction).
     Returns float32 [B, Kk] with entries 0 or 65536/(65536 - round(p*65536))."""
     import numpy as np
+    return kron_dropout_mask_at(seed, np.arange(B)[:, None], np.arange(Kk)[None, :], Kk, p)
+
+
+def kron_dropout_mask_at(seed: int, rows, cols, Kk: int, p: float) -> torch.Tensor:
+    """Same mask evaluated only at (rows, cols) -- numpy-broadcastable integer arrays of batch rows b and flattened
+    Kronecker columns k -- so that tests at BASELINE sizes need not build the whole [B, Kk] mask."""
+    import numpy as np
+    rows = np.asarray(rows, dtype=np.uint64)
+    cols = np.asarray(cols, dtype=np.uint64)
+    shape = np.broadcast(rows, cols).shape
     thresh = min(int(p * 65536.0 + 0.5), 65535) if p > 0 else 0
     if thresh == 0:
-        return torch.ones(B, Kk)
+        return torch.ones(shape)
     pairs = (Kk + 1) // 2
-    b = np.arange(B, dtype=np.uint64)[:, None]
-    k = np.arange(Kk, dtype=np.uint64)[None, :]
-    c = b * np.uint64(pairs) + (k >> np.uint64(1))
+    c = rows * np.uint64(pairs) + (cols >> np.uint64(1))
     lo = (c & np.uint64(0xFFFFFFFF)).astype(np.uint32)
     hi = (c >> np.uint64(32)).astype(np.uint32)
     s_lo, s_hi = np.uint32(seed & 0xFFFFFFFF), np.uint32((seed >> 32) & 0xFFFFFFFF)
@@ -170,6 +178,6 @@ def kron_dropout_mask(seed: int, B: int, Kk: int, p: float) -> torch.Tensor:
         h = h ^ (h >> np.uint32(15))
         h = h * np.uint32(0x846CA68B)
         h = h ^ (h >> np.uint32(16))
-    r16 = np.where((k & np.uint64(1)) != 0, h >> np.uint32(16), h & np.uint32(0xFFFF))
+    r16 = np.where((np.broadcast_to(cols, shape) & np.uint64(1)) != 0, h >> np.uint32(16), h & np.uint32(0xFFFF))
     scale = np.float32(65536.0) / np.float32(65536 - thresh)
     return torch.from_numpy(np.where(r16 >= thresh, scale, np.float32(0)).astype(np.float32))

@@ -58,7 +58,7 @@ def main():
             kk *= d + 1
         gen = torch.Generator(device=dev).manual_seed(0)
         fs = [torch.rand(B, d, device=dev, generator=gen) for d in dims]
-        W = (torch.randn(N, kk, device=dev, generator=gen) / kk ** 0.5).requires_grad_(args.bwd)
+        W = torch.randn(N, kk, device=dev, generator=gen) / kk ** 0.5
         bias = torch.zeros(N, device=dev)
         st = KronLinearState(dims)
         training = args.dropout > 0
@@ -69,18 +69,23 @@ def main():
                 "frac_of_tf32_peak": round(flops / ms / 1e9 / tf32_peak, 3), "tf32_peak": tf32_peak,
                 "dropout": args.dropout}
         if args.bwd:
+            # `_KronLinearFn.backward` runs the kernels of whichever inputs required grad at FORWARD time, so three
+            # separate graphs time (wgrad + dgrad), wgrad alone (K3 + transpose + unpack) and dgrad alone (K2 + reduce).
+            n_b = max(3, args.iters // 3)
             fsg = [f.clone().requires_grad_(True) for f in fs]
-            y = kron_linear(st, fsg, W, bias, drop_p=args.dropout, training=training, seed=7)
-            G = torch.randn_like(y)
-            bwd = lambda: torch.autograd.grad(y, [W] + fsg, G, retain_graph=True)
-            line["bwd_ms"] = round(time_ms(bwd, max(3, args.iters // 3), warmup=2), 3)
+            Wg = W.detach().clone().requires_grad_(True)
+            Wc = W.detach()
+            y_all = kron_linear(st, fsg, Wg, bias, drop_p=args.dropout, training=training, seed=7)
+            y_w = kron_linear(st, fs, Wg, bias, drop_p=args.dropout, training=training, seed=7)
+            y_f = kron_linear(st, fsg, Wc, bias, drop_p=args.dropout, training=training, seed=7)
+            G = torch.randn_like(y_all)
+            line["bwd_ms"] = round(time_ms(lambda: torch.autograd.grad(y_all, [Wg] + fsg, G, retain_graph=True), n_b, warmup=2), 4)
+            line["wgrad_ms"] = round(time_ms(lambda: torch.autograd.grad(y_w, [Wg], G, retain_graph=True), n_b, warmup=2), 4)
+            line["dgrad_ms"] = round(time_ms(lambda: torch.autograd.grad(y_f, fsg, G, retain_graph=True), n_b, warmup=2), 4)
             line["bwd_tflops"] = round(2 * flops / line["bwd_ms"] / 1e9, 1)
-            wg = lambda: torch.autograd.grad(y, [W], G, retain_graph=True)
-            dg = lambda: torch.autograd.grad(y, fsg, G, retain_graph=True)
-            line["wgrad_ms"] = round(time_ms(wg, max(3, args.iters // 3), warmup=2), 3)
-            line["dgrad_ms"] = round(time_ms(dg, max(3, args.iters // 3), warmup=2), 3)
             line["wgrad_tflops"] = round(flops / line["wgrad_ms"] / 1e9, 1)
             line["dgrad_tflops"] = round(flops / line["dgrad_ms"] / 1e9, 1)
+            line["bwd_frac_of_tf32_peak"] = round(line["bwd_tflops"] / tf32_peak, 3)
         print(json.dumps(line), flush=True)
 
 

@@ -220,6 +220,67 @@ def test_sweep_size_rows_vs_oracle(pkg, fo):
     assert torch.isfinite(y).all()
 
 
+BENCH_SIZES = [
+    # B, dims, N  -- the points bench.py / scripts/bench_kron.py time (BASELINE configs 3 and 4)
+    (16384, (128, 128), 256),
+    (65536, (32, 32), 64),
+    (65536, (64, 64), 128),
+    (8192, (32, 32, 32), 96),
+]
+
+
+@pytest.mark.parametrize("p_drop", [0.0, 0.25])
+@pytest.mark.parametrize("B,dims,N", BENCH_SIZES)
+def test_backward_at_bench_sizes_sampled_vs_oracle(pkg, fo, B, dims, N, p_drop):
+    """K1/K2/K3 at the sizes they are timed on (many batch splits, k splits, the unpack / reduce finishers), with the
+    counter-hash dropout on and off: the whole problem runs on the GPU, the float64 oracle recomputes
+      * y and the factor gradients for 48 sampled batch rows (all columns), and
+      * dW for 96 sampled Kronecker columns (all rows n, the contraction over the FULL batch),
+    from fusion.py:58-60 / :126-129 restated with the Kronecker rows materialised only for the sample."""
+    import numpy as np
+    from multimodal_learning_b200.fusion import KronLinearState, kron_linear
+    seed = 0x5EED_0000 + B + N
+    fs, W, bias = _problem(B, dims, N, seed=B % 1000 + N)
+    Kk = W.shape[1]
+    G = torch.randn(B, N, generator=torch.Generator().manual_seed(5))
+    st = KronLinearState(dims)
+    fd = [f.to(DEV).requires_grad_(True) for f in fs]
+    Wd = W.to(DEV).requires_grad_(True)
+    before = pkg._cabi.launch_count()
+    y = kron_linear(st, fd, Wd, bias.to(DEV), drop_p=p_drop, training=p_drop > 0, seed=seed)
+    (y * G.to(DEV)).sum().backward()
+    assert pkg._cabi.launch_count() >= before + 5
+    assert all(getattr(pkg._cabi.lib(), f)(B, N, *st.dims) == 1 for f in
+               ("mml_kron_fwd_supported", "mml_kron_wgrad_supported", "mml_kron_dgrad_supported"))   # tensor-core kernels
+    g = torch.Generator().manual_seed(9)
+    rows = torch.randperm(B, generator=g)[:48]
+    rows[0], rows[1] = 0, B - 1
+    cols = torch.randperm(Kk, generator=g)[:96]
+    cols[0], cols[1], cols[2] = 0, Kk - 1, Kk - 2                     # first core column, corner, an edge next to it
+    # ---- sampled rows: forward + factor gradients ----
+    aug = [torch.cat((f[rows].double(), torch.ones(len(rows), 1, dtype=torch.float64)), 1).requires_grad_(True) for f in fs]
+    mask_r = fo.kron_dropout_mask_at(seed, rows.numpy()[:, None], np.arange(Kk)[None, :], Kk, p_drop).double()
+    A = fo.kron_rows(*aug) * mask_r
+    want_y = A @ W.double().t() + bias.double()
+    (want_y * G[rows].double()).sum().backward()
+    assert rel_err(y[rows.to(DEV)], want_y) < TOL_TC
+    for i, d in enumerate(dims):
+        assert rel_err(fd[i].grad[rows.to(DEV)], aug[i].grad[:, :d]) < TOL_TC, f"factor {i}"
+    assert torch.isfinite(fd[0].grad).all()
+    # ---- sampled Kronecker columns: dW[:, k] = sum_b dy[b, :] A[b, k] m[b, k] over the whole batch ----
+    e = [d + 1 for d in dims]
+    full = [torch.cat((f.double(), torch.ones(B, 1, dtype=torch.float64)), 1) for f in fs]
+    k = cols.clone()
+    Acol = torch.ones(B, len(cols), dtype=torch.float64)
+    for t in range(len(dims) - 1, -1, -1):                           # row-major flatten: last factor varies fastest
+        Acol *= full[t][:, k % e[t]]
+        k = k // e[t]
+    Acol *= fo.kron_dropout_mask_at(seed, np.arange(B)[:, None], cols.numpy()[None, :], Kk, p_drop).double()
+    want_dW = G.double().t() @ Acol                                   # [N, |cols|]
+    assert rel_err(Wd.grad[:, cols.to(DEV)], want_dW) < TOL_TC
+    assert torch.isfinite(Wd.grad).all()
+
+
 def test_cpu_inputs_are_rejected(pkg):
     from multimodal_learning_b200.fusion import KronLinearState, kron_linear
     fs, W, bias = _problem(4, (8, 8), 8, seed=0)
