@@ -236,50 +236,55 @@ __global__ void __launch_bounds__(kThreadsTc, 1) kron_wgrad_tc_kernel(const __gr
       MML_WG_LOAD_SC(blk_begin + 1, scp1, scq1, scv1)
     }
     int xbuf = 0;                                                    // (blk - blk_begin) % 3
-    for (int blk = blk_begin; blk < blk_end; ++blk) {
-      const int it = blk - blk_begin;
-      asm volatile("cp.async.wait_group 1;" ::: "memory");           // this thread's copies of block blk have landed
-      asm volatile("bar.sync 1, 256;" ::: "memory");                 // everyone's have; buffers of block blk-1 are free
-      {
-        const int nbuf = xbuf == 0 ? 2 : xbuf - 1;                   // (it + 2) % 3
-        MML_WG_ISSUE_X(blk + 2, nbuf)
-      }
-      MML_WG_LOAD_SC(blk + 2, scp2, scq2, scv2)
-      const float* X = sm_X + xbuf * (4 * kBlkB * 32) + my_slot * (kBlkB * 32);
-      const float* S = sm_sc + (it & 1) * (4 * kBlkB) + ci * kBlkB;
-      const int64_t b0 = static_cast<int64_t>(blk) * kBlkB;
-      uint32_t r[kHalf];
-      float sv[kHalf];
-#pragma unroll
-      for (int u = 0; u < kHalf; u += 4)
-        *reinterpret_cast<float4*>(&sv[u]) = *reinterpret_cast<const float4*>(S + half * kHalf + u);
-#pragma unroll
-      for (int u = 0; u < kHalf; ++u) {
-        const int bl = half * kHalf + u;
-        float x = my_valid ? sv[u] * X[bl * 32 + e] : 0.f;
-        if (kDropout) {
-          const int64_t cc = (b0 + bl) * a.dr.pairs_per_row + (my_klog >> 1);
-          const uint32_t h = kron_hash(static_cast<uint32_t>(cc), static_cast<uint32_t>(static_cast<uint64_t>(cc) >> 32),
-                                       seed_lo, seed_hi);
-          const uint32_t r16 = (my_klog & 1) ? (h >> 16) : (h & 0xffffu);
-          x = (r16 >= a.dr.thresh) ? x : 0.f;
-        }
-        r[u] = __float_as_uint(x) + 0x1000u;
-      }
-      if (s_prev >= 0) {
-        tc_wait_st();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&bar_full[s_prev]);
-      }
-      mbar_wait(&bar_empty[s], ph ^ 1);
-      tc_fence_after();
-      tc_st_32x32b_x16(tmem_a + lane_base + s * kBlkB + half * kHalf, r);
-      s_prev = s;
-      if (++s == a.stages) { s = 0; ph ^= 1; }
-      MML_WG_STORE_SC((it + 1) & 1, scp1, scq1, scv1)                // block blk+1's scalars, loaded one iteration ago
-      scp1 = scp2; scq1 = scq2; scv1 = scv2;
-      xbuf = xbuf == 2 ? 0 : xbuf + 1;
+    // One pipeline stage.  LP/LQ/LV: register set that receives the scalar factors of block BLK+2; SP/SQ/SV: the set loaded
+    // one stage earlier (block BLK+1), whose product is parked in shared memory at the end.  The two sets alternate
+    // between consecutive stages (loop unrolled by two) so that no register is copied -- a copy would wait for its load.
+#define MML_WG_STAGE(BLK, LP, LQ, LV, SP, SQ, SV)                                                       \
+    {                                                                                                   \
+      const int it = (BLK) - blk_begin;                                                                 \
+      asm volatile("cp.async.wait_group 1;" ::: "memory");  /* this thread's copies of block BLK landed */ \
+      asm volatile("bar.sync 1, 256;" ::: "memory");        /* everyone's have; block BLK-1's buffers free */ \
+      {                                                                                                 \
+        const int nbuf = xbuf == 0 ? 2 : xbuf - 1;           /* (it + 2) % 3 */                         \
+        MML_WG_ISSUE_X((BLK) + 2, nbuf)                                                                 \
+      }                                                                                                 \
+      MML_WG_LOAD_SC((BLK) + 2, LP, LQ, LV)                                                             \
+      const float* X = sm_X + xbuf * (4 * kBlkB * 32) + my_slot * (kBlkB * 32);                         \
+      const float* S = sm_sc + (it & 1) * (4 * kBlkB) + ci * kBlkB;                                     \
+      const int64_t b0 = static_cast<int64_t>(BLK) * kBlkB;                                             \
+      uint32_t r[kHalf];                                                                                \
+      float sv[kHalf];                                                                                  \
+      _Pragma("unroll") for (int u = 0; u < kHalf; u += 4)                                              \
+        *reinterpret_cast<float4*>(&sv[u]) = *reinterpret_cast<const float4*>(S + half * kHalf + u);    \
+      _Pragma("unroll") for (int u = 0; u < kHalf; ++u) {                                               \
+        const int bl = half * kHalf + u;                                                                \
+        float x = my_valid ? sv[u] * X[bl * 32 + e] : 0.f;                                              \
+        if (kDropout) {                                                                                 \
+          const int64_t cc = (b0 + bl) * a.dr.pairs_per_row + (my_klog >> 1);                           \
+          const uint32_t h = kron_hash(static_cast<uint32_t>(cc),                                       \
+                                       static_cast<uint32_t>(static_cast<uint64_t>(cc) >> 32), seed_lo, seed_hi); \
+          const uint32_t r16 = (my_klog & 1) ? (h >> 16) : (h & 0xffffu);                               \
+          x = (r16 >= a.dr.thresh) ? x : 0.f;                                                           \
+        }                                                                                               \
+        r[u] = __float_as_uint(x) + 0x1000u;                                                            \
+      }                                                                                                 \
+      if (s_prev >= 0) {                                                                                \
+        tc_wait_st();                                                                                   \
+        tc_fence_before();                                                                              \
+        __syncwarp();                                                                                   \
+        if (lane == 0) mbar_arrive(&bar_full[s_prev]);                                                  \
+      }                                                                                                 \
+      mbar_wait(&bar_empty[s], ph ^ 1);                                                                 \
+      tc_fence_after();                                                                                 \
+      tc_st_32x32b_x16(tmem_a + lane_base + s * kBlkB + half * kHalf, r);                               \
+      s_prev = s;                                                                                       \
+      if (++s == a.stages) { s = 0; ph ^= 1; }                                                          \
+      MML_WG_STORE_SC((it + 1) & 1, SP, SQ, SV)             /* block BLK+1's scalars, loaded a stage ago */ \
+      xbuf = xbuf == 2 ? 0 : xbuf + 1;                                                                  \
+    }
+    for (int blk = blk_begin; blk < blk_end; blk += 2) {
+      MML_WG_STAGE(blk, scp2, scq2, scv2, scp1, scq1, scv1)
+      if (blk + 1 < blk_end) MML_WG_STAGE(blk + 1, scp1, scq1, scv1, scp2, scq2, scv2)
     }
     asm volatile("cp.async.wait_group 0;" ::: "memory");
     if (s_prev >= 0) {
@@ -675,15 +680,39 @@ __global__ void __launch_bounds__(kDgThreads, 1) kron_dgrad_tc_kernel(const __gr
 #pragma unroll
     for (int e = 0; e < kHalf; ++e) { v[e] = 0.f; dv[e] = 0.f; }
     int cur_src = -1, cur_col = -1, cur_len = 0;
-    auto flush = [&]() {            // read-modify-write of <= 16 floats: all loads in flight together, then the stores
-      if (cur_src > 0 && live) {
-        float* dst = my_part + (cur_src == 1 ? 0 : (cur_src == 2 ? a.d1 : a.d1 + a.d2)) + cur_col + eb;
-        float old[kHalf];
-#pragma unroll
-        for (int e = 0; e < kHalf; ++e) old[e] = (eb + e < cur_len) ? dst[e] : 0.f;
+    // A vector segment is one contiguous run of chunks (build_chunks), so its gradient leaves the registers once per CTA:
+    //   * factors that are not among the per-row scalars R (f2 when bilinear, f3 when trilinear): plain stores into the
+    //     zero-initialised partial buffer -- no read-modify-write anywhere on the global side;
+    //   * factors inside R (f1; f2 when trilinear): added to the dR accumulator in shared memory.  The barrier orders the
+    //     add after the other half-thread's fold of the previous tile (flush points are uniform over the 256 threads).
+    const bool tri = a.d3 > 0;
+    auto flush = [&]() {
+      if (cur_src <= 0) return;
+      if (cur_src == 1 || (cur_src == 2 && tri)) {
+        asm volatile("bar.sync 2, %0;" ::"n"(kDgEpiThreads) : "memory");
+        float* acc_r = sm_dR + static_cast<size_t>((cur_src == 1 ? 1 : 1 + a.d1) + cur_col + eb) * kTileM + row;
 #pragma unroll
         for (int e = 0; e < kHalf; ++e)
-          if (eb + e < cur_len) dst[e] = old[e] + dv[e];
+          if (eb + e < cur_len) acc_r[e * kTileM] += dv[e];
+      } else if (live) {
+        float* dst = my_part + (cur_src == 2 ? a.d1 : a.d1 + a.d2) + cur_col + eb;
+#pragma unroll
+        for (int e = 0; e < kHalf; ++e)
+          if (eb + e < cur_len) dst[e] = dv[e];
+      }
+    };
+    auto new_segment = [&](const int4& e0, const int4& e1) {      // rare: once per run of chunks sharing a vector segment
+      flush();
+      cur_src = e0.z; cur_col = e0.w; cur_len = e1.x;
+      const float* src = cur_src == 1 ? a.f1 : (cur_src == 2 ? a.f2 : a.f3);
+      const int d = cur_src == 1 ? a.d1 : (cur_src == 2 ? a.d2 : a.d3);
+#pragma unroll
+      for (int e = 0; e < kHalf; ++e) {
+        float x = 0.f;
+        if (cur_src == 0) x = (eb + e == 0) ? 1.0f : 0.f;
+        else if (live && eb + e < cur_len) x = __ldg(src + b * d + cur_col + eb + e);
+        v[e] = x;
+        dv[e] = 0.f;
       }
     };
     for (int t = t_begin; t < t_end; ++t) {
@@ -693,57 +722,47 @@ __global__ void __launch_bounds__(kDgThreads, 1) kron_dgrad_tc_kernel(const __gr
       mbar_wait(&bar_acc_full[buf], (it >> 1) & 1);
       tc_fence_after();
       const uint32_t t_addr = tmem_acc + lane_base + buf * kDgTileK + eb;
-      uint32_t acc[kHalf];
-      tc_ld_32x32b_x16(t_addr, acc);
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        const int cg = t * 4 + c;
-        const bool cvalid = cg < a.nchunks;
-        const int4 e0 = cvalid ? tab[2 * cg] : make_int4(0, 0, 0, 0);
-        const int4 e1 = cvalid ? tab[2 * cg + 1] : make_int4(0, 0, 1, 0);
-        if (cvalid && (e0.z != cur_src || e0.w != cur_col)) {
-          flush();
-          cur_src = e0.z; cur_col = e0.w; cur_len = e1.x;
-          const float* src = cur_src == 1 ? a.f1 : (cur_src == 2 ? a.f2 : a.f3);
-          const int d = cur_src == 1 ? a.d1 : (cur_src == 2 ? a.d2 : a.d3);
-#pragma unroll
-          for (int e = 0; e < kHalf; ++e) {
-            float x = 0.f;
-            if (cur_src == 0) x = (eb + e == 0) ? 1.0f : 0.f;
-            else if (live && eb + e < cur_len) x = __ldg(src + b * d + cur_col + eb + e);
-            v[e] = x;
-            dv[e] = 0.f;
-          }
-        }
-        const float sp = sm_S[e0.x * kTileM + row], sq = sm_S[e0.y * kTileM + row];
-        float s = sp * sq;
-        if (kDropout) s *= a.dr.scale;
-        tc_wait_ld();
-        float g[kHalf];
-#pragma unroll
-        for (int e = 0; e < kHalf; ++e) g[e] = __uint_as_float(acc[e]);
-        if (c < 3) tc_ld_32x32b_x16(t_addr + (c + 1) * 32, acc);          // next chunk's dA in flight behind this one's math
-        if (kDropout) {
-#pragma unroll
-          for (int e = 0; e < kHalf; ++e) {
-            const int klog = e1.y + (eb + e) * e1.z;
-            const int64_t cc = b * a.dr.pairs_per_row + (klog >> 1);
-            const uint32_t h = kron_hash(static_cast<uint32_t>(cc), static_cast<uint32_t>(static_cast<uint64_t>(cc) >> 32),
-                                         seed_lo, seed_hi);
-            const uint32_t r16 = (klog & 1) ? (h >> 16) : (h & 0xffffu);
-            g[e] = (r16 >= a.dr.thresh) ? g[e] : 0.f;
-          }
-        }
-        float ds0 = 0.f, ds1 = 0.f, ds2 = 0.f, ds3 = 0.f;
-#pragma unroll
-        for (int e = 0; e < kHalf; e += 4) {
-          ffma2(ds0, ds1, g[e], g[e + 1], v[e], v[e + 1]);
-          ffma2(ds2, ds3, g[e + 2], g[e + 3], v[e + 2], v[e + 3]);
-          ffma2(dv[e], dv[e + 1], g[e], g[e + 1], s, s);
-          ffma2(dv[e + 2], dv[e + 3], g[e + 2], g[e + 3], s, s);
-        }
-        ds_slot[c * 2 * kTileM] = cvalid ? (ds0 + ds1) + (ds2 + ds3) : 0.f;
+      // The tile's four chunks, fully unrolled over two register buffers: the tcgen05.ld of chunk c+1 is in flight while
+      // chunk c is folded, and no register is copied (a rolled loop has to move the 16 loaded words every iteration).
+      uint32_t accA[kHalf], accB[kHalf];
+#define MML_DG_CHUNK(C, ACC, NEXT_LD)                                                                   \
+      {                                                                                                 \
+        const int cg = t * 4 + (C);                                                                     \
+        const bool cvalid = cg < a.nchunks;                                                             \
+        const int4 e0 = cvalid ? tab[2 * cg] : make_int4(0, 0, 0, 0);                                   \
+        const int4 e1 = cvalid ? tab[2 * cg + 1] : make_int4(0, 0, 1, 0);                               \
+        if (cvalid && (e0.z != cur_src || e0.w != cur_col)) new_segment(e0, e1);                        \
+        const float sp = sm_S[e0.x * kTileM + row], sq = sm_S[e0.y * kTileM + row];                     \
+        float s = sp * sq;                                                                              \
+        if (kDropout) s *= a.dr.scale;                                                                  \
+        tc_wait_ld();                                                                                   \
+        NEXT_LD;                                                                                        \
+        float g[kHalf];                                                                                 \
+        _Pragma("unroll") for (int e = 0; e < kHalf; ++e) g[e] = __uint_as_float(ACC[e]);               \
+        if (kDropout) {                                                                                 \
+          _Pragma("unroll") for (int e = 0; e < kHalf; ++e) {                                           \
+            const int klog = e1.y + (eb + e) * e1.z;                                                    \
+            const int64_t cc = b * a.dr.pairs_per_row + (klog >> 1);                                    \
+            const uint32_t h = kron_hash(static_cast<uint32_t>(cc),                                     \
+                                         static_cast<uint32_t>(static_cast<uint64_t>(cc) >> 32), seed_lo, seed_hi); \
+            const uint32_t r16 = (klog & 1) ? (h >> 16) : (h & 0xffffu);                                \
+            g[e] = (r16 >= a.dr.thresh) ? g[e] : 0.f;                                                   \
+          }                                                                                             \
+        }                                                                                               \
+        float ds0 = 0.f, ds1 = 0.f, ds2 = 0.f, ds3 = 0.f;                                               \
+        _Pragma("unroll") for (int e = 0; e < kHalf; e += 4) {                                          \
+          ffma2(ds0, ds1, g[e], g[e + 1], v[e], v[e + 1]);                                              \
+          ffma2(ds2, ds3, g[e + 2], g[e + 3], v[e + 2], v[e + 3]);                                      \
+          ffma2(dv[e], dv[e + 1], g[e], g[e + 1], s, s);                                                \
+          ffma2(dv[e + 2], dv[e + 3], g[e + 2], g[e + 3], s, s);                                        \
+        }                                                                                               \
+        ds_slot[(C) * 2 * kTileM] = cvalid ? (ds0 + ds1) + (ds2 + ds3) : 0.f;                           \
       }
+      tc_ld_32x32b_x16(t_addr, accA);
+      MML_DG_CHUNK(0, accA, tc_ld_32x32b_x16(t_addr + 32, accB))
+      MML_DG_CHUNK(1, accB, tc_ld_32x32b_x16(t_addr + 64, accA))
+      MML_DG_CHUNK(2, accA, tc_ld_32x32b_x16(t_addr + 96, accB))
+      MML_DG_CHUNK(3, accB, (void)0)
       tc_fence_before();                    // this warp's TMEM reads of the tile are complete (wait::ld above)
       __syncwarp();
       if (lane == 0) mbar_arrive(&bar_acc_empty[buf]);
@@ -766,16 +785,12 @@ __global__ void __launch_bounds__(kDgThreads, 1) kron_dgrad_tc_kernel(const __gr
       }
     }
     flush();
-    if (live && half == 0) {
+    asm volatile("bar.sync 1, %0;" ::"n"(kDgEpiThreads) : "memory");      // every fold and shared-memory flush has landed
+    if (live) {
       const int ns = a.n_scal - 1;                      // R[1..] = f1 (then f2 when trilinear): same offsets as the output layout
-      for (int i0 = 0; i0 < ns; i0 += 16) {
-        float old[16];
-#pragma unroll
-        for (int u = 0; u < 16; ++u) old[u] = (i0 + u < ns) ? my_part[i0 + u] : 0.f;
-#pragma unroll
-        for (int u = 0; u < 16; ++u)
-          if (i0 + u < ns) my_part[i0 + u] = old[u] + sm_dR[(1 + i0 + u) * kTileM + row];
-      }
+      const int per = (ns + 1) / 2;
+      const int lo = half * per, hi = min(ns, lo + per);
+      for (int i = lo; i < hi; ++i) my_part[i] = sm_dR[(1 + i) * kTileM + row];
     }
     tc_fence_before();
   }

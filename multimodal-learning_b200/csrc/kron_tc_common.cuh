@@ -36,31 +36,33 @@ inline std::vector<Chunk> build_chunks(int d1, int d2, int d3) {
   auto add = [&](int p, int q, int vsrc, int vcol, int vlen, int kbase, int kstride) {
     out.push_back(Chunk{p, q, vsrc, vcol, vlen, kbase, kstride, 0});
   };
+  // Chunks that share a vector segment (vsrc, vcol) are emitted as ONE contiguous run: the dgrad epilogue keeps the
+  // segment's gradient in registers and writes it out once per run (a plain store, no read-modify-write).
   if (d3 == 0) {
-    for (int js = 0; js < d2; js += kChunkK)          // core: o1[i] * o2[js..]
-      for (int i = 0; i < d1; ++i) add(P1 + i, 0, 2, js, seg(d2, js), i * e2 + js, 1);
+    for (int js = 0; js < d2; js += kChunkK) {
+      for (int i = 0; i < d1; ++i) add(P1 + i, 0, 2, js, seg(d2, js), i * e2 + js, 1);          // core: o1[i] * o2[js..]
+      add(0, 0, 2, js, seg(d2, js), d1 * e2 + js, 1);                                            // i = d1 border: 1 * o2[js..]
+    }
     for (int is = 0; is < d1; is += kChunkK)          // j = d2 border: o1[is..] * 1
       add(0, 0, 1, is, seg(d1, is), is * e2 + d2, e2);
-    for (int js = 0; js < d2; js += kChunkK)          // i = d1 border: 1 * o2[js..]
-      add(0, 0, 2, js, seg(d2, js), d1 * e2 + js, 1);
     add(0, 0, 0, 0, 1, d1 * e2 + d2, 1);              // corner 1*1
   } else {
-    for (int ls = 0; ls < d3; ls += kChunkK)          // core: o1[i] o2[j] * o3[ls..]
-      for (int i = 0; i < d1; ++i)
-        for (int j = 0; j < d2; ++j) add(P1 + i, P2 + j, 3, ls, seg(d3, ls), (i * e2 + j) * e3 + ls, 1);
-    for (int js = 0; js < d2; js += kChunkK)          // l = d3 face: o1[i] * o2[js..]
-      for (int i = 0; i < d1; ++i) add(P1 + i, 0, 2, js, seg(d2, js), (i * e2 + js) * e3 + d3, e3);
     for (int ls = 0; ls < d3; ls += kChunkK) {
+      for (int i = 0; i < d1; ++i)                    // core: o1[i] o2[j] * o3[ls..]
+        for (int j = 0; j < d2; ++j) add(P1 + i, P2 + j, 3, ls, seg(d3, ls), (i * e2 + j) * e3 + ls, 1);
       for (int i = 0; i < d1; ++i)                    // j = d2 face: o1[i] * o3[ls..]
         add(P1 + i, 0, 3, ls, seg(d3, ls), (i * e2 + d2) * e3 + ls, 1);
       for (int j = 0; j < d2; ++j)                    // i = d1 face: o2[j] * o3[ls..]
         add(P2 + j, 0, 3, ls, seg(d3, ls), (d1 * e2 + j) * e3 + ls, 1);
       add(0, 0, 3, ls, seg(d3, ls), (d1 * e2 + d2) * e3 + ls, 1);     // i = d1, j = d2 edge: o3[ls..]
     }
+    for (int js = 0; js < d2; js += kChunkK) {
+      for (int i = 0; i < d1; ++i)                    // l = d3 face: o1[i] * o2[js..]
+        add(P1 + i, 0, 2, js, seg(d2, js), (i * e2 + js) * e3 + d3, e3);
+      add(0, 0, 2, js, seg(d2, js), (d1 * e2 + js) * e3 + d3, e3);    // i = d1, l = d3 edge: o2[js..]
+    }
     for (int is = 0; is < d1; is += kChunkK)          // j = d2, l = d3 edge: o1[is..]
       add(0, 0, 1, is, seg(d1, is), (is * e2 + d2) * e3 + d3, e2 * e3);
-    for (int js = 0; js < d2; js += kChunkK)          // i = d1, l = d3 edge: o2[js..]
-      add(0, 0, 2, js, seg(d2, js), (d1 * e2 + js) * e3 + d3, e3);
     add(0, 0, 0, 0, 1, (d1 * e2 + d2) * e3 + d3, 1);  // corner
   }
   return out;
