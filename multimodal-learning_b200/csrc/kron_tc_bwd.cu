@@ -2,14 +2,21 @@
 //
 //   dW[n, k] = sum_b dy[b, n] * A[b, k] * m[b, k]                 (autograd of encoder1[0], fusion.py:60 / :129)
 //
-// Same machinery as the forward (kron_tc.cu) with the roles turned: the 128 TMEM lanes are 128
-// PACKED k (4 chunks of the K permutation), the contraction runs over the batch in blocks of 32
-// rows, the A operand A^T[k, b] is generated into tensor memory (thread = (k lane, 16 batch
-// columns)), and the B operand is dy^T [Np, B] streamed by TMA in [Np x 32] tiles.  The Kronecker
-// tensor is not materialised here either: per 32-row batch block the CTA stages only the <= 4
-// distinct 32-wide factor segments and the 4 per-row scalars of its chunks in shared memory.
-// Output: per-(batch split) partial tiles in the packed layout, reduced and scattered back to the
-// dense [N, Kk] layout by kron_unpack_kernel (fixed order -> deterministic).
+// Same machinery as the forward (kron_tc.cu) with the roles turned: the 128 TMEM lanes are 128 PACKED k (4 chunks of
+// the K permutation), the contraction runs over the batch in stages of 32 rows, the A operand A^T[k, b] is generated
+// into tensor memory (thread = (k lane, 16 batch columns)), and the B operand is dy^T [Np, B] streamed by TMA in
+// [Np x 32] tiles.  The Kronecker tensor is not materialised here either.  Everything the generators read arrives by
+// TMA from ONE transposed copy of the factors, FT [1 + d1 + d2 + d3][Bpad] (row 0 = ones, then the columns of f1, f2,
+// f3: row r < n_scal is exactly the per-row scalar R[r]):
+//   * per chunk two [1 x 32] boxes -- the rows of its scalars R[p], R[q] -- and
+//   * per distinct vector segment of the tile one [32 rows x 32 b] box (128-byte swizzled),
+// so a generator thread does 12 128-bit shared loads, 24 multiplies and one tcgen05.st per stage; there is no global
+// load, cp.async or CTA barrier in the loop (mbarriers only).  Lanes past a chunk's length hold finite garbage that the
+// unpack kernel never reads.  Operand rounding: dy^T is rounded to nearest onto the TF32 grid; A^T is truncated by the
+// tensor core, and the mean of that truncation (-0.5 ulp over log-uniform mantissas) is cancelled by scaling dy^T with
+// 1 + 0.69 * 2^-11 before it is rounded -- same RMS error as round-to-nearest, no per-element integer add.
+// Output: per-(batch split) partial tiles in the packed layout, reduced and scattered back to the dense [N, Kk] layout
+// by kron_unpack_kernel (fixed order -> deterministic).
 #include "kron_tc_common.cuh"
 
 namespace mml {
@@ -18,11 +25,11 @@ namespace {
 using namespace tc;
 
 constexpr int kBlkB = 32;          // batch rows per pipeline stage (= 4 MMAs of K = 8)
+constexpr uint32_t kWgXBytes = 4 * kBlkB * 32 * 4;     // 4 vector-segment slots of [32 rows x 32 b] fp32
+constexpr uint32_t kWgSBytes = 8 * kBlkB * 4;          // 8 scalar rows of 32 b
+constexpr float kTruncComp = 1.0f + 0.69f / 2048.0f;   // see header comment
 
 struct WgArgs {
-  const float* f1;
-  const float* f2;
-  const float* f3;
   const int4* table;
   float* part;                // [bsplit][N][Kp]
   int64_t B;
@@ -35,20 +42,21 @@ struct WgArgs {
 };
 
 template <bool kDropout>
-__global__ void __launch_bounds__(kThreadsTc, 1) kron_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_dyT, const WgArgs a) {
+__global__ void __launch_bounds__(kThreadsTc, 1)
+kron_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_dyT, const __grid_constant__ CUtensorMap tmap_x,
+                     const __grid_constant__ CUtensorMap tmap_s, const WgArgs a) {
   uint32_t seed_lo = 0u, seed_hi = 0u;
   if (kDropout) kron_seed(a.dr, seed_lo, seed_hi);
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  const uint32_t stage_bytes = static_cast<uint32_t>(a.Np) * 128u;
+  const uint32_t dy_bytes = static_cast<uint32_t>(a.Np) * 128u;
+  const uint32_t stage_bytes = dy_bytes + kWgXBytes + 1024u;         // dy^T tile | X slots | S rows (1 KB, 1024-aligned)
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  uint8_t* sm_b = smem;
-  float* sm_X = reinterpret_cast<float*>(smem + static_cast<size_t>(a.stages) * stage_bytes);   // [3][4][32 b][32 e]
-  float* sm_sc = sm_X + 3 * 4 * kBlkB * 32;                                                       // [2][4][32 b]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sm_sc + 2 * 4 * kBlkB);
-  uint64_t* bar_full = bars;
-  uint64_t* bar_empty = bars + a.stages;
-  uint64_t* bar_acc = bars + 2 * a.stages;
-  uint32_t* sm_tmem = reinterpret_cast<uint32_t*>(bars + 2 * a.stages + 1);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + static_cast<size_t>(a.stages) * stage_bytes);
+  uint64_t* bar_full = bars;                    // [stages] A^T stored (8 warp arrivals) + dy^T landed (1 arrival + tx)
+  uint64_t* bar_empty = bars + a.stages;        // [stages] MMAs of the stage complete
+  uint64_t* bar_xfull = bars + 2 * a.stages;    // [stages] factor boxes landed (1 arrival + tx)
+  uint64_t* bar_acc = bars + 3 * a.stages;
+  uint32_t* sm_tmem = reinterpret_cast<uint32_t*>(bar_acc + 1);
 
   const int warp = warp_idx_sync();
   const int lane = threadIdx.x & 31;
@@ -58,9 +66,12 @@ __global__ void __launch_bounds__(kThreadsTc, 1) kron_wgrad_tc_kernel(const __gr
 
   if (warp == kGenWarps && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_dyT)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_x)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_s)) : "memory");
     for (int s = 0; s < a.stages; ++s) {
       mbar_init(&bar_full[s], kGenWarps + 1);
       mbar_init(&bar_empty[s], 1);
+      mbar_init(&bar_xfull[s], 1);
     }
     mbar_init(bar_acc, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -77,15 +88,46 @@ __global__ void __launch_bounds__(kThreadsTc, 1) kron_wgrad_tc_kernel(const __gr
   const uint32_t tmem_d = tmem_base;
   const uint32_t tmem_a = tmem_base + static_cast<uint32_t>(a.Np);
 
+  // The tile's chunk descriptors (uniform over the CTA).  Chunks that share a vector segment share a slot.
+  int rp[4], rq[4], xrow[4], slot[4];
+  bool own[4];
+  int nown = 0;
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    const bool cv = (c_first + c) < a.nchunks;
+    const int4 q0 = cv ? __ldg(a.table + 2 * (c_first + c)) : make_int4(0, 0, 0, 0);
+    rp[c] = q0.x;
+    rq[c] = q0.y;                                  // FT row of a scalar = its index in R = [1, f1, f2]
+    xrow[c] = q0.z == 0 ? 0 : (q0.z == 1 ? 1 : (q0.z == 2 ? 1 + a.d1 : 1 + a.d1 + a.d2)) + q0.w;
+    slot[c] = c;
+    own[c] = true;
+#pragma unroll
+    for (int p = 0; p < c; ++p)
+      if (own[c] && own[p] && xrow[p] == xrow[c]) {
+        slot[c] = p;
+        own[c] = false;
+      }
+    nown += own[c] ? 1 : 0;
+  }
+
   if (warp == kGenWarps) {
-    // ===== TMA producer: dy^T tiles [Np x 32 batch rows] (whole warp walks the ring, one elected lane issues) =====
+    // ===== TMA producer: per stage the factor boxes (generators) and the dy^T tile (MMA) =====
     int s = 0;
     uint32_t ph = 0;
     for (int blk = blk_begin; blk < blk_end; ++blk) {
       mbar_wait(&bar_empty[s], ph ^ 1);
       if (elect_one_sync()) {
-        mbar_arrive_expect_tx(&bar_full[s], stage_bytes);
-        tma_load_2d(sm_b + static_cast<size_t>(s) * stage_bytes, &tmap_dyT, blk * kBlkB, 0, &bar_full[s]);
+        uint8_t* st = smem + static_cast<size_t>(s) * stage_bytes;
+        const int b0 = blk * kBlkB;
+        mbar_arrive_expect_tx(&bar_xfull[s], static_cast<uint32_t>(nown) * (kBlkB * 32 * 4) + kWgSBytes);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          tma_load_2d(st + dy_bytes + kWgXBytes + (2 * c) * 128, &tmap_s, b0, rp[c], &bar_xfull[s]);
+          tma_load_2d(st + dy_bytes + kWgXBytes + (2 * c + 1) * 128, &tmap_s, b0, rq[c], &bar_xfull[s]);
+          if (own[c]) tma_load_2d(st + dy_bytes + c * (kBlkB * 32 * 4), &tmap_x, b0, xrow[c], &bar_xfull[s]);
+        }
+        mbar_arrive_expect_tx(&bar_full[s], dy_bytes);
+        tma_load_2d(st, &tmap_dyT, b0, 0, &bar_full[s]);
       }
       __syncwarp();
       if (++s == a.stages) { s = 0; ph ^= 1; }
@@ -94,7 +136,7 @@ __global__ void __launch_bounds__(kThreadsTc, 1) kron_wgrad_tc_kernel(const __gr
     // ===== MMA issuer =====
     int s = 0;
     uint32_t ph = 0;
-    const uint32_t b_base = smem_u32(sm_b);
+    const uint32_t b_base = smem_u32(smem);
     for (int blk = blk_begin; blk < blk_end; ++blk) {
       mbar_wait(&bar_full[s], ph);
       tc_fence_after();
@@ -112,181 +154,66 @@ __global__ void __launch_bounds__(kThreadsTc, 1) kron_wgrad_tc_kernel(const __gr
     if (elect_one_sync()) tc_commit(bar_acc);
     __syncwarp();
   } else {
-    // ===== generators: thread = (packed-k lane t, 16 batch columns of the stage) =====
+    // ===== generators: thread = (packed-k lane t = 32 ci + e, 16 batch columns of the stage) =====
     const int gt = threadIdx.x;                        // 0..255
     const int t = gt & (kTileM - 1);
     const int half = gt >> 7;
-    const int ci = t >> 5, e = t & 31;
-    const uint32_t lane_base = static_cast<uint32_t>((warp & 3) * 32) << 16;
-    // The CTA's chunk descriptors (uniform) and the vector slot of each chunk (chunks sharing a segment share a
-    // slot).  Everything is indexed with compile-time constants and advanced incrementally (pointers += one
-    // block) so the per-stage instruction count stays small and the state lives in registers.
-    const int sr = gt >> 5, se = gt & 31;              // staging role: rows sr + 8j, column se
-    bool own[4];                                       // chunk c owns a distinct vector segment (slot c)
-    bool xld[4], xone[4];                              // this thread's column: load it / it is the constant 1
-    const float* xp[4];                                // next staging element (row b0 + sr) of slot c
-    int xrow[4];                                       // floats per batch row of that factor
+    const int ci = warp & 3, e = lane;
+    const uint32_t lane_base = static_cast<uint32_t>(ci * 32) << 16;
     int my_slot = 0, my_klog = 0;
-    bool my_valid = false;
-    const float* spp = nullptr;                        // scalar role (gt < 128): chunk gt>>5, row gt&31
-    const float* sqp = nullptr;
-    int sprow = 0, sqrow = 0;
-    bool sc_valid = false;
-    {
-      const int64_t bfirst = static_cast<int64_t>(blk_begin) * kBlkB;
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        const bool cv = (c_first + c) < a.nchunks;
-        const int4 q0 = cv ? __ldg(a.table + 2 * (c_first + c)) : make_int4(0, 0, 0, 0);
-        const int4 q1 = cv ? __ldg(a.table + 2 * (c_first + c) + 1) : make_int4(0, 0, 1, 0);
-        bool dup = false;
-#pragma unroll
-        for (int p = 0; p < c; ++p) {
-          const bool pv = (c_first + p) < a.nchunks;
-          const int4 r0 = pv ? __ldg(a.table + 2 * (c_first + p)) : make_int4(0, 0, 0, 0);
-          if (cv && pv && !dup && r0.z == q0.z && r0.w == q0.w) {
-            dup = true;
-            if (c == ci) my_slot = p;                  // first chunk with the same segment owns the slot
-          }
-        }
-        own[c] = cv && !dup;
-        const int vsrc = q0.z;
-        xrow[c] = vsrc == 1 ? a.d1 : (vsrc == 2 ? a.d2 : a.d3);
-        xone[c] = (vsrc == 0) && (se < q1.x);
-        xld[c] = (vsrc != 0) && (se < q1.x);
-        xp[c] = (vsrc == 1 ? a.f1 : (vsrc == 2 ? a.f2 : a.f3));
-        if (vsrc != 0) xp[c] += (bfirst + sr) * xrow[c] + q0.w + se;
-        if (c == ci) {
-          if (!dup) my_slot = c;
-          my_valid = cv && e < q1.x;
-          my_klog = q1.y + e * q1.z;
-        }
-        if (c == (gt >> 5) && gt < 128) {
-          sc_valid = cv;
-          const int64_t rb = bfirst + (gt & 31);
-          if (q0.x != 0) {
-            const bool in1 = q0.x <= a.d1;
-            sprow = in1 ? a.d1 : a.d2;
-            spp = (in1 ? a.f1 + (q0.x - 1) : a.f2 + (q0.x - 1 - a.d1)) + rb * sprow;
-          }
-          if (q0.y != 0) {
-            const bool in1 = q0.y <= a.d1;
-            sqrow = in1 ? a.d1 : a.d2;
-            sqp = (in1 ? a.f1 + (q0.y - 1) : a.f2 + (q0.y - 1 - a.d1)) + rb * sqrow;
-          }
-        }
-      }
+    for (int c = 0; c < 4; ++c)
+      if (c == ci) my_slot = slot[c];
+    if (kDropout) {
+      const bool cv = (c_first + ci) < a.nchunks;
+      const int4 q1 = cv ? __ldg(a.table + 2 * (c_first + ci) + 1) : make_int4(0, 0, 1, 0);
+      my_klog = q1.y + (e < q1.x ? e : 0) * q1.z;      // lanes past the chunk's length: any valid counter (never read)
     }
-    // Staging of 32-row batch blocks runs TWO blocks ahead of the arithmetic: the vector segments go global -> shared
-    // with cp.async (4-byte copies, zero-filled past the batch tail; three buffers), the per-row scalar factors ride in
-    // registers for two iterations and their product is parked in shared memory one block ahead.  Nothing in the loop
-    // waits on a global load it has just issued.
-    float scp1 = 1.f, scq1 = 1.f, scp2 = 1.f, scq2 = 1.f;      // raw scalar factors of blocks blk+1, blk+2 (gt < 128)
-    bool scv1 = false, scv2 = false;
-#define MML_WG_ISSUE_X(BLK, BUF)                                                                        \
-    {                                                                                                   \
-      const int64_t left64 = a.B - static_cast<int64_t>(BLK) * kBlkB;                                   \
-      const int left = left64 > kBlkB ? kBlkB : (left64 < 0 ? 0 : static_cast<int>(left64));            \
-      float* Xs = sm_X + (BUF) * (4 * kBlkB * 32) + sr * 32 + se;                                       \
-      _Pragma("unroll") for (int c = 0; c < 4; ++c) {                                                   \
-        if (own[c]) {                                                                                   \
-          _Pragma("unroll") for (int j = 0; j < 4; ++j) {                                               \
-            const bool rv = (sr + 8 * j) < left;                                                        \
-            float* dstp = Xs + c * (kBlkB * 32) + j * 8 * 32;                                           \
-            if (xld[c]) {                                                                               \
-              const float* srcp = rv ? xp[c] + j * 8 * xrow[c] : a.f1;                                  \
-              asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(smem_u32(dstp)),        \
-                           "l"(srcp), "r"(rv ? 4 : 0) : "memory");                                      \
-            } else {                                                                                    \
-              *dstp = (xone[c] && rv) ? 1.0f : 0.f;                                                     \
-            }                                                                                           \
-          }                                                                                             \
-          xp[c] += kBlkB * xrow[c];                                                                     \
-        }                                                                                               \
-      }                                                                                                 \
-      asm volatile("cp.async.commit_group;" ::: "memory");                                              \
-    }
-#define MML_WG_LOAD_SC(BLK, P, Q, V)                                                                    \
-    {                                                                                                   \
-      if (gt < 128) {                                                                                   \
-        const int64_t left64 = a.B - static_cast<int64_t>(BLK) * kBlkB;                                 \
-        V = sc_valid && static_cast<int64_t>(gt & 31) < left64;                                         \
-        P = (V && spp) ? __ldg(spp) : 1.0f;                                                             \
-        Q = (V && sqp) ? __ldg(sqp) : 1.0f;                                                             \
-        if (spp) spp += kBlkB * sprow;                                                                  \
-        if (sqp) sqp += kBlkB * sqrow;                                                                  \
-      }                                                                                                 \
-    }
-#define MML_WG_STORE_SC(BUF, P, Q, V)                                                                   \
-    {                                                                                                   \
-      if (gt < 128) {                                                                                   \
-        float sc = V ? P * Q : 0.f;                                                                     \
-        if (kDropout) sc *= a.dr.scale;                                                                 \
-        sm_sc[(BUF) * (4 * kBlkB) + gt] = sc;                                                           \
-      }                                                                                                 \
-    }
-
+    // byte offsets inside a stage: scalar rows (broadcast reads) and this lane's swizzled row of its vector slot
+    const uint32_t off_sp = dy_bytes + kWgXBytes + (2 * ci) * 128 + half * 64;
+    const uint32_t off_sq = off_sp + 128;
+    const uint32_t off_x = dy_bytes + my_slot * (kBlkB * 32 * 4) + e * 128;
+    const uint32_t sw = static_cast<uint32_t>(e & 7);
     int s = 0, s_prev = -1;
     uint32_t ph = 0;
-    if (blk_begin < blk_end) {
-      MML_WG_ISSUE_X(blk_begin, 0)
-      MML_WG_ISSUE_X(blk_begin + 1, 1)
-      MML_WG_LOAD_SC(blk_begin, scp1, scq1, scv1)
-      MML_WG_STORE_SC(0, scp1, scq1, scv1)
-      MML_WG_LOAD_SC(blk_begin + 1, scp1, scq1, scv1)
+    for (int blk = blk_begin; blk < blk_end; ++blk) {
+      const uint8_t* st = smem + static_cast<size_t>(s) * stage_bytes;
+      mbar_wait(&bar_xfull[s], ph);                    // implies the stage's previous MMAs are complete (producer waited)
+      uint32_t r[kHalf];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const float4 p4 = *reinterpret_cast<const float4*>(st + off_sp + u * 16);
+        const float4 q4 = *reinterpret_cast<const float4*>(st + off_sq + u * 16);
+        const float4 x4 = *reinterpret_cast<const float4*>(st + off_x + (((half * 4 + u) ^ sw) << 4));
+        float y0 = p4.x * q4.x * x4.x, y1 = p4.y * q4.y * x4.y, y2 = p4.z * q4.z * x4.z, y3 = p4.w * q4.w * x4.w;
+        if (kDropout) {
+          const int64_t bb = static_cast<int64_t>(blk) * kBlkB + half * kHalf + u * 4;
+          float* yy[4] = {&y0, &y1, &y2, &y3};
+#pragma unroll
+          for (int w = 0; w < 4; ++w) {
+            const int64_t cc = (bb + w) * a.dr.pairs_per_row + (my_klog >> 1);
+            const uint32_t h = kron_hash(static_cast<uint32_t>(cc), static_cast<uint32_t>(static_cast<uint64_t>(cc) >> 32),
+                                         seed_lo, seed_hi);
+            const uint32_t r16 = (my_klog & 1) ? (h >> 16) : (h & 0xffffu);
+            *yy[w] = (r16 >= a.dr.thresh) ? *yy[w] * a.dr.scale : 0.f;
+          }
+        }
+        r[u * 4 + 0] = __float_as_uint(y0);
+        r[u * 4 + 1] = __float_as_uint(y1);
+        r[u * 4 + 2] = __float_as_uint(y2);
+        r[u * 4 + 3] = __float_as_uint(y3);
+      }
+      if (s_prev >= 0) {                                 // publish the PREVIOUS stage: its TMEM store had this stage's
+        tc_wait_st();                                    // loads and multiplies to complete in
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bar_full[s_prev]);
+      }
+      tc_fence_after();
+      tc_st_32x32b_x16(tmem_a + lane_base + s * kBlkB + half * kHalf, r);
+      s_prev = s;
+      if (++s == a.stages) { s = 0; ph ^= 1; }
     }
-    int xbuf = 0;                                                    // (blk - blk_begin) % 3
-    // One pipeline stage.  LP/LQ/LV: register set that receives the scalar factors of block BLK+2; SP/SQ/SV: the set loaded
-    // one stage earlier (block BLK+1), whose product is parked in shared memory at the end.  The two sets alternate
-    // between consecutive stages (loop unrolled by two) so that no register is copied -- a copy would wait for its load.
-#define MML_WG_STAGE(BLK, LP, LQ, LV, SP, SQ, SV)                                                       \
-    {                                                                                                   \
-      const int it = (BLK) - blk_begin;                                                                 \
-      asm volatile("cp.async.wait_group 1;" ::: "memory");  /* this thread's copies of block BLK landed */ \
-      asm volatile("bar.sync 1, 256;" ::: "memory");        /* everyone's have; block BLK-1's buffers free */ \
-      {                                                                                                 \
-        const int nbuf = xbuf == 0 ? 2 : xbuf - 1;           /* (it + 2) % 3 */                         \
-        MML_WG_ISSUE_X((BLK) + 2, nbuf)                                                                 \
-      }                                                                                                 \
-      MML_WG_LOAD_SC((BLK) + 2, LP, LQ, LV)                                                             \
-      const float* X = sm_X + xbuf * (4 * kBlkB * 32) + my_slot * (kBlkB * 32);                         \
-      const float* S = sm_sc + (it & 1) * (4 * kBlkB) + ci * kBlkB;                                     \
-      const int64_t b0 = static_cast<int64_t>(BLK) * kBlkB;                                             \
-      uint32_t r[kHalf];                                                                                \
-      float sv[kHalf];                                                                                  \
-      _Pragma("unroll") for (int u = 0; u < kHalf; u += 4)                                              \
-        *reinterpret_cast<float4*>(&sv[u]) = *reinterpret_cast<const float4*>(S + half * kHalf + u);    \
-      _Pragma("unroll") for (int u = 0; u < kHalf; ++u) {                                               \
-        const int bl = half * kHalf + u;                                                                \
-        float x = my_valid ? sv[u] * X[bl * 32 + e] : 0.f;                                              \
-        if (kDropout) {                                                                                 \
-          const int64_t cc = (b0 + bl) * a.dr.pairs_per_row + (my_klog >> 1);                           \
-          const uint32_t h = kron_hash(static_cast<uint32_t>(cc),                                       \
-                                       static_cast<uint32_t>(static_cast<uint64_t>(cc) >> 32), seed_lo, seed_hi); \
-          const uint32_t r16 = (my_klog & 1) ? (h >> 16) : (h & 0xffffu);                               \
-          x = (r16 >= a.dr.thresh) ? x : 0.f;                                                           \
-        }                                                                                               \
-        r[u] = __float_as_uint(x) + 0x1000u;                                                            \
-      }                                                                                                 \
-      if (s_prev >= 0) {                                                                                \
-        tc_wait_st();                                                                                   \
-        tc_fence_before();                                                                              \
-        __syncwarp();                                                                                   \
-        if (lane == 0) mbar_arrive(&bar_full[s_prev]);                                                  \
-      }                                                                                                 \
-      mbar_wait(&bar_empty[s], ph ^ 1);                                                                 \
-      tc_fence_after();                                                                                 \
-      tc_st_32x32b_x16(tmem_a + lane_base + s * kBlkB + half * kHalf, r);                               \
-      s_prev = s;                                                                                       \
-      if (++s == a.stages) { s = 0; ph ^= 1; }                                                          \
-      MML_WG_STORE_SC((it + 1) & 1, SP, SQ, SV)             /* block BLK+1's scalars, loaded a stage ago */ \
-      xbuf = xbuf == 2 ? 0 : xbuf + 1;                                                                  \
-    }
-    for (int blk = blk_begin; blk < blk_end; blk += 2) {
-      MML_WG_STAGE(blk, scp2, scq2, scv2, scp1, scq1, scv1)
-      if (blk + 1 < blk_end) MML_WG_STAGE(blk + 1, scp1, scq1, scv1, scp2, scq2, scv2)
-    }
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
     if (s_prev >= 0) {
       tc_wait_st();
       tc_fence_before();
@@ -322,8 +249,8 @@ __global__ void __launch_bounds__(kThreadsTc, 1) kron_wgrad_tc_kernel(const __gr
   }
 }
 
-// dy [B, N] -> dyT [Np, Bpad] (TF32-rounded, zero padded): the K-major B operand of the wgrad MMA
-__global__ void kron_transpose_dy_kernel(const float* __restrict__ dy, int64_t B, int32_t N, int32_t Np, int64_t Bpad,
+// dy [B, N] -> dyT [Np, Bpad] (scaled by `comp`, TF32-rounded, zero padded): the K-major B operand of the wgrad MMA
+__global__ void kron_transpose_dy_kernel(const float* __restrict__ dy, int64_t B, int32_t N, int32_t Np, int64_t Bpad, float comp,
                                          float* __restrict__ dyT) {
   __shared__ float tile[32][33];
   const int64_t b0 = static_cast<int64_t>(blockIdx.x) * 32;
@@ -331,7 +258,7 @@ __global__ void kron_transpose_dy_kernel(const float* __restrict__ dy, int64_t B
   for (int r = threadIdx.y; r < 32; r += 8) {
     const int64_t b = b0 + r;
     const int n = n0 + threadIdx.x;
-    tile[r][threadIdx.x] = (b < B && n < N) ? dy[b * N + n] : 0.f;
+    tile[r][threadIdx.x] = (b < B && n < N) ? dy[b * N + n] * comp : 0.f;
   }
   __syncthreads();
   for (int r = threadIdx.y; r < 32; r += 8) {
@@ -341,6 +268,34 @@ __global__ void kron_transpose_dy_kernel(const float* __restrict__ dy, int64_t B
       const uint32_t u = (__float_as_uint(tile[threadIdx.x][r]) + 0x1000u) & 0xFFFFE000u;
       dyT[static_cast<int64_t>(n) * Bpad + b] = __uint_as_float(u);
     }
+  }
+}
+
+// FT[r][b]: r = 0 -> 1, then the columns of f1, f2 (, f3); zero for b >= B.  Exact fp32 copies.
+__global__ void kron_transpose_factors_kernel(const float* __restrict__ f1, const float* __restrict__ f2, const float* __restrict__ f3,
+                                              int64_t B, int32_t d1, int32_t d2, int32_t d3, int64_t Bpad, int32_t rows_alloc,
+                                              float* __restrict__ FT) {
+  __shared__ float tile[32][33];
+  const int rows = 1 + d1 + d2 + d3;
+  const int64_t b0 = static_cast<int64_t>(blockIdx.x) * 32;
+  const int r0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += 8) {
+    const int64_t b = b0 + i;
+    const int r = r0 + threadIdx.x;
+    float x = 0.f;
+    if (b < B && r < rows) {
+      if (r == 0) x = 1.0f;
+      else if (r <= d1) x = f1[b * d1 + (r - 1)];
+      else if (r <= d1 + d2) x = f2[b * d2 + (r - 1 - d1)];
+      else x = f3[b * d3 + (r - 1 - d1 - d2)];
+    }
+    tile[i][threadIdx.x] = x;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += 8) {
+    const int r = r0 + i;
+    const int64_t b = b0 + threadIdx.x;
+    if (r < rows_alloc && b < Bpad) FT[static_cast<int64_t>(r) * Bpad + b] = tile[threadIdx.x][i];
   }
 }
 
@@ -362,11 +317,28 @@ __global__ void kron_unpack_kernel(const float* __restrict__ part, int32_t bspli
 }
 
 struct WgPlan {
-  int32_t nchunks, Np, Kp, stages, tmem_cols, ktiles, nblocks, bsplit, blocks_per_split;
+  int32_t nchunks, Np, Kp, stages, tmem_cols, ktiles, nblocks, bsplit, blocks_per_split, ft_rows;
   int64_t Bpad;
-  size_t smem, dyT_bytes, part_bytes;
+  size_t smem, dyT_bytes, ft_bytes, part_bytes;
   bool ok;
 };
+
+// Number of batch splits: fill whole waves of CTAs, pay for every split's partial tile (written and re-read once).
+inline int32_t pick_split(int64_t units, int64_t tiles, int64_t slots, int64_t min_units, double split_cost, int64_t max_split) {
+  int64_t best = 1;
+  double best_cost = 1e300;
+  for (int64_t sp = 1; sp <= max_split; ++sp) {
+    const int64_t per = (units + sp - 1) / sp;
+    if (sp > 1 && per < min_units) break;
+    const int64_t waves = (tiles * sp + slots - 1) / slots;
+    const double cost = static_cast<double>(waves) * (static_cast<double>(per) + 4.0) + split_cost * static_cast<double>(sp - 1);
+    if (cost < best_cost - 1e-9) {
+      best_cost = cost;
+      best = sp;
+    }
+  }
+  return static_cast<int32_t>(best);
+}
 
 WgPlan make_wg_plan(int64_t B, int32_t N, int32_t d1, int32_t d2, int32_t d3) {
   WgPlan p{};
@@ -376,14 +348,16 @@ WgPlan make_wg_plan(int64_t B, int32_t N, int32_t d1, int32_t d2, int32_t d3) {
   p.ktiles = (p.nchunks + 3) / 4;
   p.nblocks = static_cast<int32_t>((B + kBlkB - 1) / kBlkB);
   p.Bpad = static_cast<int64_t>(p.nblocks) * kBlkB;
-  const size_t fixed = (3 * 4 * kBlkB * 32 + 2 * 4 * kBlkB) * sizeof(float) + 256 + 1024;
-  const size_t stage = static_cast<size_t>(p.Np) * 128;
+  p.ft_rows = 1 + d1 + d2 + d3 < 32 ? 32 : 1 + d1 + d2 + d3;       // at least one whole [32 x 32] box (zero rows below the factors)
+  const size_t fixed = 512 + 1024;
+  const size_t stage = static_cast<size_t>(p.Np) * 128 + kWgXBytes + 1024;
   int stages = static_cast<int>((227 * 1024 - fixed) / stage);
-  if (stages > 4) stages = 4;
+  if (stages > 8) stages = 8;
+  while (stages > 2 && p.Np + stages * kBlkB > 512) --stages;
+  // two CTAs per SM (their generators and MMAs interleave) when each still gets a deep enough ring
   const size_t half_budget = 113 * 1024;
   if (fixed + 3 * stage <= half_budget && p.Np + 3 * kBlkB <= 256) {
     int st2 = static_cast<int>((half_budget - fixed) / stage);
-    if (st2 > 4) st2 = 4;
     while (p.Np + st2 * kBlkB > 256) --st2;
     stages = st2;
   }
@@ -394,14 +368,16 @@ WgPlan make_wg_plan(int64_t B, int32_t N, int32_t d1, int32_t d2, int32_t d3) {
   while (pow2 < cols) pow2 <<= 1;
   p.tmem_cols = pow2;
   if (pow2 > 512) p.ok = false;
-  int64_t split = (148 * 2 + p.ktiles - 1) / p.ktiles;
-  const int64_t max_split = p.nblocks / 8 > 0 ? p.nblocks / 8 : 1;       // >= 8 batch blocks (256 rows) per split
-  if (split > max_split) split = max_split;
-  if (split > 64) split = 64;
-  if (split < 1) split = 1;
-  p.blocks_per_split = static_cast<int32_t>((p.nblocks + split - 1) / split);
+  const int ctas_per_sm = (p.smem <= half_budget && pow2 <= 256) ? 2 : 1;
+  // one split's partial tile costs N*Kp*8 bytes of traffic ~ N*Kp*8 / 6.5e12 s; a stage costs ~2*Np cycles at 1.9 GHz per SM slot
+  const double stage_s = 2.0 * p.Np / 1.9e9;
+  const double split_cost = (static_cast<double>(N) * p.Kp * 8.0 / 6.5e12) / stage_s;
+  const int64_t max_split = p.nblocks / 8 > 0 ? (p.nblocks / 8 < 64 ? p.nblocks / 8 : 64) : 1;
+  p.bsplit = pick_split(p.nblocks, p.ktiles, 148 * ctas_per_sm, 8, split_cost, max_split);
+  p.blocks_per_split = static_cast<int32_t>((p.nblocks + p.bsplit - 1) / p.bsplit);
   p.bsplit = (p.nblocks + p.blocks_per_split - 1) / p.blocks_per_split;
   p.dyT_bytes = (static_cast<size_t>(p.Np) * p.Bpad * sizeof(float) + 1023) / 1024 * 1024;
+  p.ft_bytes = (static_cast<size_t>(p.ft_rows) * p.Bpad * sizeof(float) + 1023) / 1024 * 1024;
   p.part_bytes = static_cast<size_t>(p.bsplit) * N * p.Kp * sizeof(float);
   return p;
 }
@@ -419,7 +395,7 @@ extern "C" int mml_kron_wgrad_supported(int64_t B, int32_t N, int32_t d1, int32_
 extern "C" size_t mml_kron_wgrad_workspace_bytes(int64_t B, int32_t N, int32_t d1, int32_t d2, int32_t d3) {
   if (B < 1 || N < 1 || d1 < 1 || d2 < 1 || d3 < 0) return 0;
   const WgPlan p = make_wg_plan(B, N, d1, d2, d3);
-  return p.dyT_bytes + p.part_bytes + 1024;
+  return p.dyT_bytes + p.ft_bytes + p.part_bytes + 1024;
 }
 
 extern "C" int mml_kron_linear_wgrad(const float* f1, const float* f2, const float* f3, int64_t B, int32_t d1, int32_t d2,
@@ -433,22 +409,30 @@ extern "C" int mml_kron_linear_wgrad(const float* f1, const float* f2, const flo
               "kron_linear_wgrad: table must be 16-byte and workspace 1024-byte aligned");
   const WgPlan p = make_wg_plan(B, N, d1, d2, d3);
   MML_REQUIRE(p.ok, MML_ERR_UNSUPPORTED, "kron_linear_wgrad: N=%d (<=256) exceeds the tile budget", N);
-  MML_REQUIRE(workspace_bytes >= p.dyT_bytes + p.part_bytes, MML_ERR_WORKSPACE, "kron_linear_wgrad: workspace too small");
+  MML_REQUIRE(workspace_bytes >= p.dyT_bytes + p.ft_bytes + p.part_bytes, MML_ERR_WORKSPACE, "kron_linear_wgrad: workspace too small");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   float* dyT = static_cast<float*>(workspace);
-  float* part = reinterpret_cast<float*>(static_cast<char*>(workspace) + p.dyT_bytes);
+  float* FT = reinterpret_cast<float*>(static_cast<char*>(workspace) + p.dyT_bytes);
+  float* part = reinterpret_cast<float*>(static_cast<char*>(workspace) + p.dyT_bytes + p.ft_bytes);
   const KronShape s = make_kron_shape(d1, d2, d3);
   {
     const dim3 grid(static_cast<unsigned>(p.Bpad / 32), (p.Np + 31) / 32);
-    kron_transpose_dy_kernel<<<grid, dim3(32, 8), 0, st>>>(dy, B, N, p.Np, p.Bpad, dyT);
+    kron_transpose_dy_kernel<<<grid, dim3(32, 8), 0, st>>>(dy, B, N, p.Np, p.Bpad, kTruncComp, dyT);
     int rc = check_launch("kron_transpose_dy_kernel");
     if (rc != MML_OK) return rc;
+    const dim3 gridf(static_cast<unsigned>(p.Bpad / 32), (p.ft_rows + 31) / 32);
+    kron_transpose_factors_kernel<<<gridf, dim3(32, 8), 0, st>>>(f1, f2, f3, B, d1, d2, d3, p.Bpad, p.ft_rows, FT);
+    rc = check_launch("kron_transpose_factors_kernel");
+    if (rc != MML_OK) return rc;
   }
-  CUtensorMap tmap;
+  CUtensorMap tmap, tmap_x, tmap_s;
   int rc = get_tensor_map(dyT, p.Np, static_cast<int32_t>(p.Bpad), &tmap);
   if (rc != MML_OK) return rc;
+  rc = get_tensor_map_2d(FT, p.Bpad, p.ft_rows, kBlkB, 32, true, &tmap_x);
+  if (rc != MML_OK) return rc;
+  rc = get_tensor_map_2d(FT, p.Bpad, p.ft_rows, kBlkB, 1, false, &tmap_s);
+  if (rc != MML_OK) return rc;
   WgArgs a{};
-  a.f1 = f1; a.f2 = f2; a.f3 = f3;
   a.table = reinterpret_cast<const int4*>(table);
   a.part = part;
   a.B = B; a.d1 = d1; a.d2 = d2; a.d3 = d3; a.N = N; a.Np = p.Np; a.nchunks = p.nchunks; a.Kp = p.Kp;
@@ -459,10 +443,10 @@ extern "C" int mml_kron_linear_wgrad(const float* f1, const float* f2, const flo
   const dim3 grid(p.ktiles, p.bsplit);
   if (a.dr.thresh != 0u) {
     MML_CUDA(cudaFuncSetAttribute(kron_wgrad_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(p.smem)));
-    kron_wgrad_tc_kernel<true><<<grid, kThreadsTc, p.smem, st>>>(tmap, a);
+    kron_wgrad_tc_kernel<true><<<grid, kThreadsTc, p.smem, st>>>(tmap, tmap_x, tmap_s, a);
   } else {
     MML_CUDA(cudaFuncSetAttribute(kron_wgrad_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(p.smem)));
-    kron_wgrad_tc_kernel<false><<<grid, kThreadsTc, p.smem, st>>>(tmap, a);
+    kron_wgrad_tc_kernel<false><<<grid, kThreadsTc, p.smem, st>>>(tmap, tmap_x, tmap_s, a);
   }
   rc = check_launch("kron_wgrad_tc_kernel");
   if (rc != MML_OK) return rc;

@@ -181,21 +181,30 @@ inline EncodeTiledFn get_encode_fn() {
 
 struct MapKey {
   const void* ptr;
-  int32_t Np, Kp;
-  bool operator==(const MapKey& o) const { return ptr == o.ptr && Np == o.Np && Kp == o.Kp; }
+  int64_t dim0, dim1;           // elements along the contiguous / the strided dimension
+  int32_t box0, box1, swizzle;
+  bool operator==(const MapKey& o) const {
+    return ptr == o.ptr && dim0 == o.dim0 && dim1 == o.dim1 && box0 == o.box0 && box1 == o.box1 && swizzle == o.swizzle;
+  }
 };
 struct MapKeyHash {
   size_t operator()(const MapKey& k) const {
-    return std::hash<const void*>()(k.ptr) ^ (static_cast<size_t>(k.Np) << 40) ^ static_cast<size_t>(k.Kp);
+    size_t h = std::hash<const void*>()(k.ptr);
+    h = h * 1000003u ^ static_cast<size_t>(k.dim0);
+    h = h * 1000003u ^ static_cast<size_t>(k.dim1);
+    h = h * 1000003u ^ static_cast<size_t>(k.box0 * 4099 + k.box1 * 2 + k.swizzle);
+    return h;
   }
 };
 
-// cached TMA descriptors keyed by pointer + shape (the only global state of the library)
-inline int get_tensor_map(const float* Wp, int32_t Np, int32_t Kp, CUtensorMap* out) {
+// TMA descriptor of a row-major fp32 matrix [dim1 rows][dim0 contiguous], boxes of box0 x box1 elements, 128-byte swizzle
+// or none.  Cached by pointer + geometry (the only global state of the library).
+inline int get_tensor_map_2d(const float* base, int64_t dim0, int64_t dim1, int32_t box0, int32_t box1, bool swizzle128,
+                             CUtensorMap* out) {
   static std::mutex mu;
   static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> cache;
   std::lock_guard<std::mutex> lock(mu);
-  const MapKey key{Wp, Np, Kp};
+  const MapKey key{base, dim0, dim1, box0, box1, swizzle128 ? 1 : 0};
   auto it = cache.find(key);
   if (it != cache.end()) {
     *out = it->second;
@@ -204,18 +213,23 @@ inline int get_tensor_map(const float* Wp, int32_t Np, int32_t Kp, CUtensorMap* 
   EncodeTiledFn enc = get_encode_fn();
   MML_REQUIRE(enc != nullptr, MML_ERR_CUDA, "kron: cuTensorMapEncodeTiled entry point unavailable");
   CUtensorMap m;
-  const cuuint64_t gdim[2] = {static_cast<cuuint64_t>(Kp), static_cast<cuuint64_t>(Np)};
-  const cuuint64_t gstride[1] = {static_cast<cuuint64_t>(Kp) * sizeof(float)};
-  const cuuint32_t box[2] = {static_cast<cuuint32_t>(kChunkK), static_cast<cuuint32_t>(Np)};
+  const cuuint64_t gdim[2] = {static_cast<cuuint64_t>(dim0), static_cast<cuuint64_t>(dim1)};
+  const cuuint64_t gstride[1] = {static_cast<cuuint64_t>(dim0) * sizeof(float)};
+  const cuuint32_t box[2] = {static_cast<cuuint32_t>(box0), static_cast<cuuint32_t>(box1)};
   const cuuint32_t estride[2] = {1, 1};
-  const CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(Wp), gdim, gstride, box, estride,
-                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  const CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstride, box, estride,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   MML_REQUIRE(r == CUDA_SUCCESS, MML_ERR_CUDA, "kron: cuTensorMapEncodeTiled failed (%d)", static_cast<int>(r));
-  if (cache.size() > 256) cache.clear();
+  if (cache.size() > 512) cache.clear();
   cache[key] = m;
   *out = m;
   return MML_OK;
+}
+
+// packed operand [Np rows][Kp contiguous]: boxes of [Np x 32] (one 128-byte swizzle row per operand row)
+inline int get_tensor_map(const float* Wp, int32_t Np, int32_t Kp, CUtensorMap* out) {
+  return get_tensor_map_2d(Wp, Kp, Np, kChunkK, Np, true, out);
 }
 
 inline uint32_t make_idesc_tf32(int M, int N) {
