@@ -27,7 +27,6 @@ using namespace tc;
 constexpr int kBlkB = 32;          // batch rows per pipeline stage (= 4 MMAs of K = 8)
 constexpr uint32_t kWgXBytes = 4 * kBlkB * 32 * 4;     // 4 vector-segment slots of [32 rows x 32 b] fp32
 constexpr uint32_t kWgSBytes = 8 * kBlkB * 4;          // 8 scalar rows of 32 b
-constexpr float kTruncComp = 1.0f + 0.69f / 2048.0f;   // see header comment
 
 struct WgArgs {
   const int4* table;
@@ -324,15 +323,16 @@ struct WgPlan {
 };
 
 // Number of batch splits: fill whole waves of CTAs, pay for every split's partial tile (written and re-read once).
-inline int32_t pick_split(int64_t units, int64_t tiles, int64_t slots, int64_t min_units, double split_cost, int64_t max_split) {
+inline int32_t pick_split(int64_t units, int64_t tiles, int64_t slots, int64_t min_units, double split_cost, int64_t max_split,
+                          double cta_overhead = 4.0) {
   int64_t best = 1;
   double best_cost = 1e300;
   for (int64_t sp = 1; sp <= max_split; ++sp) {
     const int64_t per = (units + sp - 1) / sp;
     if (sp > 1 && per < min_units) break;
     const int64_t waves = (tiles * sp + slots - 1) / slots;
-    const double cost = static_cast<double>(waves) * (static_cast<double>(per) + 4.0) + split_cost * static_cast<double>(sp - 1);
-    if (cost < best_cost - 1e-9) {
+    const double cost = static_cast<double>(waves) * (static_cast<double>(per) + cta_overhead) + split_cost * static_cast<double>(sp - 1);
+    if (cost < best_cost * (sp == 1 ? 1.0 : 0.95)) {        // more splits only for a clear (> 5 %) win
       best_cost = cost;
       best = sp;
     }
@@ -462,13 +462,17 @@ extern "C" int mml_kron_linear_wgrad(const float* f1, const float* f2, const flo
 //
 //   dA[b, k] = m[b,k] * sum_n dy[b,n] W[n,k]        -- never stored: each [128 rows x 128 packed k] tile is
 //   accumulated in TENSOR MEMORY (M = 128 batch lanes, N = 128 packed k, K = n) and folded on the spot into
-//   the per-row factor gradients by the epilogue warps (thread = batch row):
+//   the per-row factor gradients by the epilogue warps:
 //     chunk (p, q, vector segment x):  A = R[p] R[q] x[e]   =>   dx[e]   += dA[e] R[p] R[q]
 //                                                               dR[p]   += (sum_e dA[e] x[e]) R[q],   dR[q] likewise
 //   A operand = the dy tile, written ONCE per CTA into TMEM (tcgen05.st); B operand = [128 k x 32 n] boxes of
-//   the transposed packed weight WpT [Kp, Np32] streamed by TMA; two accumulator tiles alternate so the
-//   epilogue of tile t overlaps the MMAs of tile t+1.  Split over k tiles -> per-split partial gradients,
-//   summed in split order by kron_dgrad_reduce_kernel.
+//   the transposed packed weight WpT [Kp, Np32] streamed by TMA, 1-3 boxes per pipeline stage; two accumulator
+//   tiles alternate so the epilogue of tile t overlaps the MMAs of tile t+1.
+//   Epilogue: 8 warps, thread = (batch row, 16-element half of every chunk).  The per-row scalars R[p], R[q] and the
+//   vector segments come from the transposed factor copy FT [1 + d1 + d2 + d3][Bpad] (coalesced over the rows of
+//   the tile; issued before the accumulator is waited for), dx lives in registers for a whole run of chunks
+//   (build_chunks emits each vector segment as one run), dR accumulates in shared memory.  Packed FFMA2 math.
+//   Split over k tiles -> per-split partial gradients, summed in split order by kron_dgrad_reduce_kernel.
 // =====================================================================================================
 namespace mml {
 namespace {
@@ -477,22 +481,21 @@ constexpr int kDgEpiWarps = 8;            // epilogue warp g: TMEM lanes 32*(g%4
 constexpr int kDgEpiThreads = kDgEpiWarps * 32;
 constexpr int kDgThreads = kDgEpiThreads + 64;   // + TMA warp + MMA warp
 constexpr int kDgTileK = 128;             // packed k per accumulator tile (4 chunks)
-constexpr int kDgBoxN = 32;               // n per TMA box / pipeline stage
-constexpr uint32_t kDgStageBytes = kDgTileK * kDgBoxN * 4;   // 16 KB
+constexpr int kDgBoxN = 32;               // n per TMA box
+constexpr uint32_t kDgBoxBytes = kDgTileK * kDgBoxN * 4;     // 16 KB
 constexpr int kDgDsFloats = 2 * 4 * 2 * kTileM;              // sm_ds [tile parity][chunk][half][row]
+constexpr int kDgScFloats = 2 * 8 * kTileM;                  // sm_sc [tile parity][chunk, p|q][row]
 
 struct DgArgs {
-  const float* f1;
-  const float* f2;
-  const float* f3;
+  const float* FT;            // [1 + d1 + d2 + d3][Bpad], row 0 = ones
   const float* dy;            // [B, N]
   const int4* table;
   float* part;                // [ksplit][B][dsum]  (zero-initialised)
-  int64_t B;
+  int64_t B, Bpad;
   int32_t d1, d2, d3, dsum;
   int32_t N, Np32, nchunks;
   int32_t ktiles, tiles_per_split;
-  int32_t n_scal, stages, tmem_cols, table_in_smem;
+  int32_t n_scal, stages, bps, tmem_cols, table_in_smem, fold_mode;
   uint32_t idesc;
   KronDropout dr;
 };
@@ -506,20 +509,25 @@ __device__ __forceinline__ void ffma2(float& d0, float& d1, float a0, float a1, 
       : "f"(a0), "f"(a1), "f"(b0), "f"(b1));
 }
 
+__device__ __forceinline__ int dg_xrow(const int4& e0, int32_t d1, int32_t d2) {      // FT row of a vector segment's first element
+  return (e0.z == 0 ? 0 : (e0.z == 1 ? 1 : (e0.z == 2 ? 1 + d1 : 1 + d1 + d2))) + e0.w;
+}
+
 template <bool kDropout>
 __global__ void __launch_bounds__(kDgThreads, 1) kron_dgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_wT, const DgArgs a) {
   uint32_t seed_lo = 0u, seed_hi = 0u;
   if (kDropout) kron_seed(a.dr, seed_lo, seed_hi);
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  uint8_t* sm_b = smem;                                                              // [stages][16 KB]
-  float* sm_S = reinterpret_cast<float*>(smem + static_cast<size_t>(a.stages) * kDgStageBytes);   // R values  [n_scal][128]
-  float* sm_dR = sm_S + static_cast<size_t>(a.n_scal) * kTileM;                                   // dR accum  [n_scal][128]
+  const uint32_t stage_bytes = static_cast<uint32_t>(a.bps) * kDgBoxBytes;
+  uint8_t* sm_b = smem;                                                              // [stages][bps x 16 KB]
+  float* sm_dR = reinterpret_cast<float*>(smem + static_cast<size_t>(a.stages) * stage_bytes);    // dR accum  [n_scal][128]
   float* sm_ds = sm_dR + static_cast<size_t>(a.n_scal) * kTileM;                                  // per-chunk <dA, x> halves
-  int4* sm_tab = reinterpret_cast<int4*>(sm_ds + kDgDsFloats);
+  float* sm_sc = sm_ds + kDgDsFloats;                                                             // R[p], R[q] of the tile's chunks [2][8][128]
+  int4* sm_tab = reinterpret_cast<int4*>(sm_sc + kDgScFloats);
   uint64_t* bars = reinterpret_cast<uint64_t*>(sm_tab + (a.table_in_smem ? 2 * a.nchunks : 0));
-  uint64_t* bar_full = bars;                     // [stages] weight box landed
-  uint64_t* bar_empty = bars + a.stages;         // [stages] MMAs reading the box done
+  uint64_t* bar_full = bars;                     // [stages] weight boxes landed
+  uint64_t* bar_empty = bars + a.stages;         // [stages] MMAs reading the boxes done
   uint64_t* bar_acc_full = bars + 2 * a.stages;  // [2] accumulator tile complete
   uint64_t* bar_acc_empty = bar_acc_full + 2;    // [2] epilogue has read the tile out of TMEM (8 warp arrivals)
   uint32_t* sm_tmem = reinterpret_cast<uint32_t*>(bar_acc_empty + 2);
@@ -550,36 +558,7 @@ __global__ void __launch_bounds__(kDgThreads, 1) kron_dgrad_tc_kernel(const __gr
   }
   if (a.table_in_smem)
     for (int i = t_begin * 8 + threadIdx.x; i < min(a.nchunks, t_end * 4) * 2; i += kDgThreads) sm_tab[i] = __ldg(a.table + i);
-  if (warp < kDgEpiWarps) {
-    // per-row scalars R = [1, f1, (f2)] transposed into shared memory; row r is served by threads r and r + 128
-    const int row = threadIdx.x & (kTileM - 1);
-    const int half = threadIdx.x >> 7;
-    const int64_t b = b0 + row;
-    const bool live = b < a.B;
-    const int ns = a.n_scal - 1;
-    const int per = (ns + 1) / 2;
-    const int lo = half * per, hi = min(ns, lo + per);
-    if (half == 0) {
-      sm_S[row] = 1.0f;
-      sm_dR[row] = 0.f;
-    }
-    for (int i0 = lo; i0 < hi; i0 += 8) {
-      float tmp[8];
-#pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        const int i = i0 + u;
-        float x = 0.f;
-        if (live && i < hi) x = (i < a.d1) ? __ldg(a.f1 + b * a.d1 + i) : __ldg(a.f2 + b * a.d2 + (i - a.d1));
-        tmp[u] = x;
-      }
-#pragma unroll
-      for (int u = 0; u < 8; ++u)
-        if (i0 + u < hi) {
-          sm_S[(1 + i0 + u) * kTileM + row] = tmp[u];
-          sm_dR[(1 + i0 + u) * kTileM + row] = 0.f;
-        }
-    }
-  }
+  for (int i = threadIdx.x; i < a.n_scal * kTileM; i += kDgThreads) sm_dR[i] = 0.f;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -595,13 +574,25 @@ __global__ void __launch_bounds__(kDgThreads, 1) kron_dgrad_tc_kernel(const __gr
     const int64_t b = b0 + row;
     const bool live = b < a.B;
     const uint32_t lane_base = static_cast<uint32_t>((warp & 3) * 32) << 16;
+    const bool vec = (a.N % 4 == 0) && ((reinterpret_cast<uintptr_t>(a.dy) & 15u) == 0);
     for (int n0 = half * 16; n0 < a.Np32; n0 += 32) {
       uint32_t r[16];
+      if (vec && live && n0 + 16 <= a.N) {
 #pragma unroll
-      for (int u = 0; u < 16; ++u) {
-        const int n = n0 + u;
-        const float x = (live && n < a.N) ? __ldg(a.dy + b * a.N + n) : 0.f;
-        r[u] = __float_as_uint(x) + 0x1000u;
+        for (int u = 0; u < 16; u += 4) {
+          const float4 x4 = __ldg(reinterpret_cast<const float4*>(a.dy + b * a.N + n0 + u));
+          r[u] = __float_as_uint(x4.x) + 0x1000u;
+          r[u + 1] = __float_as_uint(x4.y) + 0x1000u;
+          r[u + 2] = __float_as_uint(x4.z) + 0x1000u;
+          r[u + 3] = __float_as_uint(x4.w) + 0x1000u;
+        }
+      } else {
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+          const int n = n0 + u;
+          const float x = (live && n < a.N) ? __ldg(a.dy + b * a.N + n) : 0.f;
+          r[u] = __float_as_uint(x) + 0x1000u;
+        }
       }
       tc_st_32x32b_x16(tmem_a + lane_base + n0, r);
     }
@@ -612,15 +603,17 @@ __global__ void __launch_bounds__(kDgThreads, 1) kron_dgrad_tc_kernel(const __gr
   tc_fence_after();
 
   if (warp == kDgEpiWarps) {
-    // ===== TMA producer: [128 k x 32 n] boxes of WpT (whole warp walks the ring, one elected lane issues) =====
+    // ===== TMA producer: bps boxes of [128 k x 32 n] per stage (whole warp walks the ring, one elected lane issues) =====
     int s = 0;
     uint32_t ph = 0;
     for (int t = t_begin; t < t_end; ++t)
-      for (int j = 0; j < nbox; ++j) {
+      for (int j = 0; j < nbox; j += a.bps) {
         mbar_wait(&bar_empty[s], ph ^ 1);
         if (elect_one_sync()) {
-          mbar_arrive_expect_tx(&bar_full[s], kDgStageBytes);
-          tma_load_2d(sm_b + static_cast<size_t>(s) * kDgStageBytes, &tmap_wT, j * kDgBoxN, t * kDgTileK, &bar_full[s]);
+          mbar_arrive_expect_tx(&bar_full[s], stage_bytes);
+          for (int i = 0; i < a.bps; ++i)
+            tma_load_2d(sm_b + static_cast<size_t>(s) * stage_bytes + i * kDgBoxBytes, &tmap_wT, (j + i) * kDgBoxN, t * kDgTileK,
+                        &bar_full[s]);
         }
         __syncwarp();
         if (++s == a.stages) { s = 0; ph ^= 1; }
@@ -635,17 +628,19 @@ __global__ void __launch_bounds__(kDgThreads, 1) kron_dgrad_tc_kernel(const __gr
       const int buf = it & 1;
       mbar_wait(&bar_acc_empty[buf], ((it >> 1) & 1) ^ 1);            // epilogue has drained this accumulator
       tc_fence_after();
-      for (int j = 0; j < nbox; ++j) {
+      for (int j = 0; j < nbox; j += a.bps) {
         mbar_wait(&bar_full[s], ph);
         tc_fence_after();
         if (elect_one_sync()) {
-          const uint64_t b_desc = umma_desc_k_sw128(b_base + static_cast<uint32_t>(s) * kDgStageBytes);
-          const uint32_t a_col = tmem_a + j * kDgBoxN;
+          for (int i = 0; i < a.bps; ++i) {
+            const uint64_t b_desc = umma_desc_k_sw128(b_base + static_cast<uint32_t>(s) * stage_bytes + i * kDgBoxBytes);
+            const uint32_t a_col = tmem_a + (j + i) * kDgBoxN;
 #pragma unroll
-          for (int i = 0; i < kDgBoxN / 8; ++i)
-            tc_mma_tf32_ts(tmem_acc + buf * kDgTileK, a_col + i * 8, b_desc + 2 * i, a.idesc, (j > 0 || i > 0) ? 1u : 0u);
+            for (int k = 0; k < kDgBoxN / 8; ++k)
+              tc_mma_tf32_ts(tmem_acc + buf * kDgTileK, a_col + k * 8, b_desc + 2 * k, a.idesc, (j + i > 0 || k > 0) ? 1u : 0u);
+          }
           tc_commit(&bar_empty[s]);
-          if (j == nbox - 1) tc_commit(&bar_acc_full[buf]);
+          if (j + a.bps >= nbox) tc_commit(&bar_acc_full[buf]);
         }
         __syncwarp();
         if (++s == a.stages) { s = 0; ph ^= 1; }
@@ -660,10 +655,11 @@ __global__ void __launch_bounds__(kDgThreads, 1) kron_dgrad_tc_kernel(const __gr
     const bool live = b < a.B;
     const uint32_t lane_base = static_cast<uint32_t>((warp & 3) * 32) << 16;
     float* my_part = a.part + (static_cast<int64_t>(blockIdx.y) * a.B + b) * a.dsum;
+    const float* ft_b = a.FT + b;                       // column b of FT: ft_b[r * Bpad] (b < Bpad always; zero past B)
     float v[kHalf], dv[kHalf];
 #pragma unroll
     for (int e = 0; e < kHalf; ++e) { v[e] = 0.f; dv[e] = 0.f; }
-    int cur_src = -1, cur_col = -1, cur_len = 0;
+    int cur_src = -1, cur_col = -1, cur_len = 0, cur_row = -1;
     // A vector segment is one contiguous run of chunks (build_chunks), so its gradient leaves the registers once per CTA:
     //   * factors that are not among the per-row scalars R (f2 when bilinear, f3 when trilinear): plain stores into the
     //     zero-initialised partial buffer -- no read-modify-write anywhere on the global side;
@@ -674,7 +670,7 @@ __global__ void __launch_bounds__(kDgThreads, 1) kron_dgrad_tc_kernel(const __gr
       if (cur_src <= 0) return;
       if (cur_src == 1 || (cur_src == 2 && tri)) {
         asm volatile("bar.sync 2, %0;" ::"n"(kDgEpiThreads) : "memory");
-        float* acc_r = sm_dR + static_cast<size_t>((cur_src == 1 ? 1 : 1 + a.d1) + cur_col + eb) * kTileM + row;
+        float* acc_r = sm_dR + static_cast<size_t>(cur_row + eb) * kTileM + row;
 #pragma unroll
         for (int e = 0; e < kHalf; ++e)
           if (eb + e < cur_len) acc_r[e * kTileM] += dv[e];
@@ -685,24 +681,67 @@ __global__ void __launch_bounds__(kDgThreads, 1) kron_dgrad_tc_kernel(const __gr
           if (eb + e < cur_len) dst[e] = dv[e];
       }
     };
-    auto new_segment = [&](const int4& e0, const int4& e1) {      // rare: once per run of chunks sharing a vector segment
+    auto new_segment = [&](int cg) {      // rare: once per run of chunks sharing a vector segment
       flush();
+      const int4 e0 = tab[2 * cg];
+      const int4 e1 = tab[2 * cg + 1];
       cur_src = e0.z; cur_col = e0.w; cur_len = e1.x;
-      const float* src = cur_src == 1 ? a.f1 : (cur_src == 2 ? a.f2 : a.f3);
-      const int d = cur_src == 1 ? a.d1 : (cur_src == 2 ? a.d2 : a.d3);
+      cur_row = dg_xrow(e0, a.d1, a.d2);
 #pragma unroll
       for (int e = 0; e < kHalf; ++e) {
         float x = 0.f;
         if (cur_src == 0) x = (eb + e == 0) ? 1.0f : 0.f;
-        else if (live && eb + e < cur_len) x = __ldg(src + b * d + cur_col + eb + e);
+        else if (eb + e < cur_len) x = __ldg(ft_b + static_cast<int64_t>(cur_row + eb + e) * a.Bpad);
         v[e] = x;
         dv[e] = 0.f;
       }
     };
+    // The per-row scalars R[p], R[q] of a tile's chunks travel FT -> shared memory with cp.async ONE TILE AHEAD (half h of
+    // a row fetches chunks 2h, 2h+1): by the time a tile starts they are a shared-memory read away, and the shared array
+    // is 8 KB instead of the [n_scal][128] copy of every scalar.
+    auto stage_scalars = [&](int tt, int par) {
+      if (tt < t_end) {
+#pragma unroll
+        for (int cc = 0; cc < 2; ++cc) {
+          const int c = 2 * half + cc;
+          const int cg = tt * 4 + c;
+          const int4 e0 = cg < a.nchunks ? tab[2 * cg] : make_int4(0, 0, 0, 0);
+          float* dstp = sm_sc + par * (8 * kTileM) + (2 * c) * kTileM + row;
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dstp)),
+                       "l"(ft_b + static_cast<int64_t>(e0.x) * a.Bpad) : "memory");
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dstp + kTileM)),
+                       "l"(ft_b + static_cast<int64_t>(e0.y) * a.Bpad) : "memory");
+        }
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    stage_scalars(t_begin, 0);
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    asm volatile("bar.sync 1, %0;" ::"n"(kDgEpiThreads) : "memory");
     for (int t = t_begin; t < t_end; ++t) {
       const int it = t - t_begin;
       const int buf = it & 1;
       float* ds_slot = sm_ds + (it & 1) * (4 * 2 * kTileM) + half * kTileM + row;     // + c * 2 * kTileM
+      stage_scalars(t + 1, (it + 1) & 1);
+      // chunk descriptors and this row's scalars of the tile
+      int P[4], Q[4], XR[4], KB[4], KS[4];
+      float SP[4], SQ[4];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const int cg = t * 4 + c;
+        const bool cvalid = cg < a.nchunks;
+        const int4 e0 = cvalid ? tab[2 * cg] : make_int4(0, 0, 0, 0);
+        P[c] = e0.x;
+        Q[c] = e0.y;
+        XR[c] = cvalid ? dg_xrow(e0, a.d1, a.d2) : -1;
+        if (kDropout) {
+          const int4 e1 = cvalid ? tab[2 * cg + 1] : make_int4(0, 0, 1, 0);
+          KB[c] = e1.y;
+          KS[c] = e1.z;
+        }
+        SP[c] = sm_sc[(it & 1) * (8 * kTileM) + (2 * c) * kTileM + row];
+        SQ[c] = sm_sc[(it & 1) * (8 * kTileM) + (2 * c + 1) * kTileM + row];
+      }
       mbar_wait(&bar_acc_full[buf], (it >> 1) & 1);
       tc_fence_after();
       const uint32_t t_addr = tmem_acc + lane_base + buf * kDgTileK + eb;
@@ -711,13 +750,8 @@ __global__ void __launch_bounds__(kDgThreads, 1) kron_dgrad_tc_kernel(const __gr
       uint32_t accA[kHalf], accB[kHalf];
 #define MML_DG_CHUNK(C, ACC, NEXT_LD)                                                                   \
       {                                                                                                 \
-        const int cg = t * 4 + (C);                                                                     \
-        const bool cvalid = cg < a.nchunks;                                                             \
-        const int4 e0 = cvalid ? tab[2 * cg] : make_int4(0, 0, 0, 0);                                   \
-        const int4 e1 = cvalid ? tab[2 * cg + 1] : make_int4(0, 0, 1, 0);                               \
-        if (cvalid && (e0.z != cur_src || e0.w != cur_col)) new_segment(e0, e1);                        \
-        const float sp = sm_S[e0.x * kTileM + row], sq = sm_S[e0.y * kTileM + row];                     \
-        float s = sp * sq;                                                                              \
+        if (XR[C] >= 0 && XR[C] != cur_row) new_segment(t * 4 + (C));                                   \
+        float s = SP[C] * SQ[C];                                                                        \
         if (kDropout) s *= a.dr.scale;                                                                  \
         tc_wait_ld();                                                                                   \
         NEXT_LD;                                                                                        \
@@ -725,7 +759,7 @@ __global__ void __launch_bounds__(kDgThreads, 1) kron_dgrad_tc_kernel(const __gr
         _Pragma("unroll") for (int e = 0; e < kHalf; ++e) g[e] = __uint_as_float(ACC[e]);               \
         if (kDropout) {                                                                                 \
           _Pragma("unroll") for (int e = 0; e < kHalf; ++e) {                                           \
-            const int klog = e1.y + (eb + e) * e1.z;                                                    \
+            const int klog = KB[C] + (eb + e) * KS[C];                                                  \
             const int64_t cc = b * a.dr.pairs_per_row + (klog >> 1);                                    \
             const uint32_t h = kron_hash(static_cast<uint32_t>(cc),                                     \
                                          static_cast<uint32_t>(static_cast<uint64_t>(cc) >> 32), seed_lo, seed_hi); \
@@ -740,7 +774,7 @@ __global__ void __launch_bounds__(kDgThreads, 1) kron_dgrad_tc_kernel(const __gr
           ffma2(dv[e], dv[e + 1], g[e], g[e + 1], s, s);                                                \
           ffma2(dv[e + 2], dv[e + 3], g[e + 2], g[e + 3], s, s);                                        \
         }                                                                                               \
-        ds_slot[(C) * 2 * kTileM] = cvalid ? (ds0 + ds1) + (ds2 + ds3) : 0.f;                           \
+        ds_slot[(C) * 2 * kTileM] = (ds0 + ds1) + (ds2 + ds3);                                          \
       }
       tc_ld_32x32b_x16(t_addr, accA);
       MML_DG_CHUNK(0, accA, tc_ld_32x32b_x16(t_addr + 32, accB))
@@ -750,21 +784,24 @@ __global__ void __launch_bounds__(kDgThreads, 1) kron_dgrad_tc_kernel(const __gr
       tc_fence_before();                    // this warp's TMEM reads of the tile are complete (wait::ld above)
       __syncwarp();
       if (lane == 0) mbar_arrive(&bar_acc_empty[buf]);
+      asm volatile("cp.async.wait_group 0;" ::: "memory");                  // next tile's scalars (issued a tile ago) have landed
       asm volatile("bar.sync 1, %0;" ::"n"(kDgEpiThreads) : "memory");      // both halves of every row have posted <dA, x>
-      if (half == 0) {
-        // dR[p] += <dA, x> R[q],  dR[q] += <dA, x> R[p]; one thread per row owns the dR columns -> fixed summation order
+      // dR[p] += <dA, x> R[q],  dR[q] += <dA, x> R[p].  Every dR element is touched by ONE thread per tile (fixed order):
+      // fold_mode 1 (bilinear, q == 0): half h folds chunks 2h, 2h+1;  2 (trilinear): half 0 folds the p side, half 1 the
+      // q side;  0 (factor widths below 4, where those sets could overlap inside a tile): half 0 folds everything.
+      {
         const float* dsr = sm_ds + (it & 1) * (4 * 2 * kTileM) + row;
-#pragma unroll 1
+#pragma unroll
         for (int c = 0; c < 4; ++c) {
-          const int cg = t * 4 + c;
-          if (cg >= a.nchunks) break;
-          const int4 e0 = tab[2 * cg];
-          if ((e0.x | e0.y) == 0) continue;
-          float ds = dsr[c * 2 * kTileM] + dsr[c * 2 * kTileM + kTileM];
-          if (kDropout) ds *= a.dr.scale;
-          const float sp = sm_S[e0.x * kTileM + row], sq = sm_S[e0.y * kTileM + row];
-          if (e0.x != 0) sm_dR[e0.x * kTileM + row] += ds * sq;
-          if (e0.y != 0) sm_dR[e0.y * kTileM + row] += ds * sp;
+          const bool mine_p = a.fold_mode == 1 ? (c >> 1) == half : half == 0;
+          const bool mine_q = a.fold_mode == 1 ? (c >> 1) == half : (a.fold_mode == 2 ? half == 1 : half == 0);
+          const bool do_p = mine_p && P[c] != 0, do_q = mine_q && Q[c] != 0;
+          if (do_p || do_q) {
+            float ds = dsr[c * 2 * kTileM] + dsr[c * 2 * kTileM + kTileM];
+            if (kDropout) ds *= a.dr.scale;
+            if (do_p) sm_dR[P[c] * kTileM + row] += ds * SQ[c];
+            if (do_q) sm_dR[Q[c] * kTileM + row] += ds * SP[c];
+          }
         }
       }
     }
@@ -819,8 +856,10 @@ __global__ void kron_dgrad_reduce_kernel(const float* __restrict__ part, int32_t
 }
 
 struct DgPlan {
-  int32_t nchunks, Np32, Kp, n_scal, stages, tmem_cols, ktiles, ksplit, tiles_per_split, table_in_smem, dsum;
-  size_t smem, part_bytes;
+  int32_t nchunks, Np32, Kp, n_scal, stages, bps, tmem_cols, ktiles, ksplit, tiles_per_split, table_in_smem, dsum, fold_mode;
+  int32_t ft_rows;
+  int64_t Bpad;
+  size_t smem, part_bytes, ft_bytes;
   bool ok;
 };
 
@@ -832,50 +871,33 @@ DgPlan make_dg_plan(int64_t B, int32_t N, int32_t d1, int32_t d2, int32_t d3) {
   p.n_scal = 1 + d1 + (d3 > 0 ? d2 : 0);
   p.dsum = d1 + d2 + d3;
   p.ktiles = (p.nchunks + 3) / 4;
+  p.fold_mode = d3 > 0 ? ((d1 >= 4 && d2 >= 4) ? 2 : 0) : (d1 >= 4 ? 1 : 0);
+  const int nbox = p.Np32 / kDgBoxN;
+  p.bps = nbox % 3 == 0 ? 3 : (nbox % 2 == 0 ? 2 : 1);
+  const size_t stage = static_cast<size_t>(p.bps) * kDgBoxBytes;
   const size_t table_bytes = static_cast<size_t>(p.nchunks) * sizeof(Chunk);
   p.table_in_smem = table_bytes <= static_cast<size_t>(kMaxSmemTable) ? 1 : 0;
-  const size_t fixed = 2 * static_cast<size_t>(p.n_scal) * kTileM * sizeof(float) + kDgDsFloats * sizeof(float) +
+  const size_t fixed = static_cast<size_t>(p.n_scal) * kTileM * sizeof(float) + (kDgDsFloats + kDgScFloats) * sizeof(float) +
                        (p.table_in_smem ? table_bytes : 0) + 256 + 1024;
-  int stages = fixed + 2 * kDgStageBytes <= 227 * 1024 ? static_cast<int>((227 * 1024 - fixed) / kDgStageBytes) : 0;
+  int stages = fixed + 2 * stage <= 227 * 1024 ? static_cast<int>((227 * 1024 - fixed) / stage) : 0;
   if (stages > 6) stages = 6;
   p.stages = stages;
   p.tmem_cols = (2 * kDgTileK + p.Np32) <= 256 ? 256 : 512;
   p.ok = p.Np32 <= 256 && stages >= 2;
-  p.smem = fixed + static_cast<size_t>(stages > 0 ? stages : 0) * kDgStageBytes;
+  p.smem = fixed + static_cast<size_t>(stages > 0 ? stages : 0) * stage;
   const int64_t mtiles = (B + kTileM - 1) / kTileM;
-  int64_t ks = mtiles < 148 ? (148 + mtiles - 1) / mtiles : 1;
-  const int64_t max_ks = p.ktiles / 2 > 0 ? p.ktiles / 2 : 1;
-  if (ks > max_ks) ks = max_ks;
-  if (ks > 32) ks = 32;
+  p.Bpad = mtiles * kTileM;
+  p.ft_rows = 1 + p.dsum;
+  // k split: fill whole waves of CTAs; every split costs one more [B, dsum] partial (memset, written, re-read)
+  const double tile_s = 8.0 * p.Np32 / 1.9e9;
+  const double split_cost = (static_cast<double>(B) * p.dsum * 12.0 / 6.5e12) / tile_s;
+  const int64_t max_ks = p.ktiles / 2 > 0 ? (p.ktiles / 2 < 32 ? p.ktiles / 2 : 32) : 1;
+  const int64_t ks = pick_split(p.ktiles, mtiles, 148, 2, split_cost, max_ks, 6e-6 / tile_s);   // ~6 us of per-CTA set-up
   p.tiles_per_split = static_cast<int32_t>((p.ktiles + ks - 1) / ks);
   p.ksplit = (p.ktiles + p.tiles_per_split - 1) / p.tiles_per_split;
-  p.part_bytes = static_cast<size_t>(p.ksplit) * B * p.dsum * sizeof(float);
+  p.part_bytes = (static_cast<size_t>(p.ksplit) * B * p.dsum * sizeof(float) + 1023) / 1024 * 1024;
+  p.ft_bytes = static_cast<size_t>(p.ft_rows) * p.Bpad * sizeof(float);
   return p;
-}
-
-// TMA descriptor of WpT [Kp rows, Np32 cols]: boxes of 32 n x 128 k
-int get_tensor_map_wT(const float* WpT, int32_t Np32, int32_t Kp, CUtensorMap* out) {
-  static std::mutex mu;
-  static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> cache;
-  std::lock_guard<std::mutex> lock(mu);
-  const MapKey key{WpT, Np32, Kp};
-  auto it = cache.find(key);
-  if (it != cache.end()) { *out = it->second; return MML_OK; }
-  EncodeTiledFn enc = get_encode_fn();
-  MML_REQUIRE(enc != nullptr, MML_ERR_CUDA, "kron: cuTensorMapEncodeTiled entry point unavailable");
-  CUtensorMap m;
-  const cuuint64_t gdim[2] = {static_cast<cuuint64_t>(Np32), static_cast<cuuint64_t>(Kp)};
-  const cuuint64_t gstride[1] = {static_cast<cuuint64_t>(Np32) * sizeof(float)};
-  const cuuint32_t box[2] = {static_cast<cuuint32_t>(kDgBoxN), static_cast<cuuint32_t>(kDgTileK)};
-  const cuuint32_t estride[2] = {1, 1};
-  const CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(WpT), gdim, gstride, box, estride,
-                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  MML_REQUIRE(r == CUDA_SUCCESS, MML_ERR_CUDA, "kron: cuTensorMapEncodeTiled(WpT) failed (%d)", static_cast<int>(r));
-  if (cache.size() > 256) cache.clear();
-  cache[key] = m;
-  *out = m;
-  return MML_OK;
 }
 
 }  // namespace
@@ -909,7 +931,8 @@ extern "C" int mml_kron_pack_weight_t(const float* W, int32_t N, int32_t d1, int
 
 extern "C" size_t mml_kron_dgrad_workspace_bytes(int64_t B, int32_t N, int32_t d1, int32_t d2, int32_t d3) {
   if (B < 1 || N < 1 || d1 < 1 || d2 < 1 || d3 < 0) return 0;
-  return make_dg_plan(B, N, d1, d2, d3).part_bytes + 256;
+  const DgPlan p = make_dg_plan(B, N, d1, d2, d3);
+  return p.part_bytes + p.ft_bytes + 256;
 }
 
 extern "C" int mml_kron_linear_dgrad(const float* f1, const float* f2, const float* f3, int64_t B, int32_t d1, int32_t d2,
@@ -920,24 +943,32 @@ extern "C" int mml_kron_linear_dgrad(const float* f1, const float* f2, const flo
   MML_REQUIRE((d3 > 0) == (f3 != nullptr) && (d3 > 0) == (df3 != nullptr), MML_ERR_INVALID_ARG,
               "kron_linear_dgrad: f3/df3 and d3 must all be set or all be absent");
   MML_REQUIRE(B >= 1 && d1 >= 1 && d2 >= 1 && d3 >= 0 && N >= 1, MML_ERR_INVALID_ARG, "kron_linear_dgrad: bad sizes");
-  MML_REQUIRE(aligned16(table) && (reinterpret_cast<uintptr_t>(WpT) & 127u) == 0, MML_ERR_INVALID_ARG,
-              "kron_linear_dgrad: table must be 16-byte and WpT 128-byte aligned");
+  MML_REQUIRE(aligned16(table) && (reinterpret_cast<uintptr_t>(WpT) & 127u) == 0 && aligned16(workspace), MML_ERR_INVALID_ARG,
+              "kron_linear_dgrad: table / workspace must be 16-byte and WpT 128-byte aligned");
   const DgPlan p = make_dg_plan(B, N, d1, d2, d3);
   MML_REQUIRE(p.ok, MML_ERR_UNSUPPORTED, "kron_linear_dgrad: N=%d / factor widths (%d,%d,%d) exceed the tile budget", N, d1, d2, d3);
-  MML_REQUIRE(workspace_bytes >= p.part_bytes, MML_ERR_WORKSPACE, "kron_linear_dgrad: workspace too small");
+  MML_REQUIRE(workspace_bytes >= p.part_bytes + p.ft_bytes, MML_ERR_WORKSPACE, "kron_linear_dgrad: workspace too small");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   MML_CUDA(cudaMemsetAsync(workspace, 0, p.part_bytes, st));
+  float* FT = reinterpret_cast<float*>(static_cast<char*>(workspace) + p.part_bytes);
+  {
+    const dim3 gridf(static_cast<unsigned>(p.Bpad / 32), (p.ft_rows + 31) / 32);
+    kron_transpose_factors_kernel<<<gridf, dim3(32, 8), 0, st>>>(f1, f2, f3, B, d1, d2, d3, p.Bpad, p.ft_rows, FT);
+    const int rc = check_launch("kron_transpose_factors_kernel");
+    if (rc != MML_OK) return rc;
+  }
   CUtensorMap tmap;
-  int rc = get_tensor_map_wT(WpT, p.Np32, p.Kp, &tmap);
+  int rc = get_tensor_map_2d(WpT, p.Np32, p.Kp, kDgBoxN, kDgTileK, true, &tmap);
   if (rc != MML_OK) return rc;
   const KronShape s = make_kron_shape(d1, d2, d3);
   DgArgs a{};
-  a.f1 = f1; a.f2 = f2; a.f3 = f3; a.dy = dy;
+  a.FT = FT; a.dy = dy;
   a.table = reinterpret_cast<const int4*>(table);
   a.part = static_cast<float*>(workspace);
-  a.B = B; a.d1 = d1; a.d2 = d2; a.d3 = d3; a.dsum = p.dsum; a.N = N; a.Np32 = p.Np32; a.nchunks = p.nchunks;
+  a.B = B; a.Bpad = p.Bpad; a.d1 = d1; a.d2 = d2; a.d3 = d3; a.dsum = p.dsum; a.N = N; a.Np32 = p.Np32; a.nchunks = p.nchunks;
   a.ktiles = p.ktiles; a.tiles_per_split = p.tiles_per_split;
-  a.n_scal = p.n_scal; a.stages = p.stages; a.tmem_cols = p.tmem_cols; a.table_in_smem = p.table_in_smem;
+  a.n_scal = p.n_scal; a.stages = p.stages; a.bps = p.bps; a.tmem_cols = p.tmem_cols; a.table_in_smem = p.table_in_smem;
+  a.fold_mode = p.fold_mode;
   a.idesc = make_idesc_tf32(kTileM, kDgTileK);
   a.dr = make_kron_dropout(drop_p, seed, training, s.Kk, seed_dev);
   const dim3 grid(static_cast<unsigned>((B + kTileM - 1) / kTileM), p.ksplit);

@@ -21,6 +21,14 @@ constexpr int kThreadsTc = kGenThreads + 64;   // + TMA warp + MMA/alloc warp
 constexpr int kHalf = kChunkK / 2;          // columns of a chunk handled by one generator thread
 constexpr int kMaxSmemTable = 48 * 1024;    // chunk tables up to this size are staged in shared memory
 constexpr uint32_t kSpinLimit = 1u << 28;   // mbarrier spin guard: trap instead of hanging the GPU
+// Operand rounding.  The tensor core TRUNCATES fp32 operands to TF32 (10 mantissa bits).  Operands that are packed once
+// (weights, dy^T) are rounded to nearest when they are packed, and so is the forward's generated Kronecker operand (one
+// integer add per element).  In the weight-gradient kernel the generated operand A^T is summed over thousands of batch
+// rows, so there it is left to the truncation, and the mean of the truncation error (-0.5 ulp, i.e. -0.5 * 2^-10 / m relative for mantissa m,
+// -0.69 * 2^-11 averaged over log-uniform mantissas) is cancelled by scaling the OTHER, packed operand with this
+// constant before it is rounded: the per-element error keeps the RMS of round-to-nearest (0.29-0.31 ulp) and the sum has no
+// systematic bias although all Kronecker factors are >= 0 (post-ReLU).
+constexpr float kTruncComp = 1.0f + 0.69f / 2048.0f;
 
 struct Chunk {                // 32 bytes, read as two int4
   int32_t p, q, vsrc, vcol;
