@@ -255,16 +255,21 @@ class _FusedLossFn(torch.autograd.Function):
 class ContrastMemory(nn.Module):
     """memory buffer that supplies large amount of negative samples."""
 
-    def __init__(self, inputSize, outputSize, K, T=0.07, momentum=0.5):
+    def __init__(self, inputSize, outputSize, K, T=0.07, momentum=0.5, device=None):
+        """`device` (extension, default None = the reference's behaviour: buffers drawn on the host from the global torch
+        RNG in the reference's order) draws the banks directly on that device -- for banks too large to stage through host
+        memory (16M x 128 x 2 = 16 GB at BASELINE config 5)."""
         super(ContrastMemory, self).__init__()
         self.nLem = outputSize
         self.unigrams = torch.ones(self.nLem)
         self.multinomial = AliasMethod(self.unigrams)
         self.K = K
-        self.register_buffer('params', torch.tensor([K, T, -1, -1, momentum]))
+        self.register_buffer('params', torch.tensor([K, T, -1, -1, momentum], device=device))
         stdv = 1. / math.sqrt(inputSize / 3)
-        self.register_buffer('memory_v1', torch.rand(outputSize, inputSize).mul_(2 * stdv).add_(-stdv))
-        self.register_buffer('memory_v2', torch.rand(outputSize, inputSize).mul_(2 * stdv).add_(-stdv))
+        self.register_buffer('memory_v1', torch.rand(outputSize, inputSize, device=device).mul_(2 * stdv).add_(-stdv))
+        self.register_buffer('memory_v2', torch.rand(outputSize, inputSize, device=device).mul_(2 * stdv).add_(-stdv))
+        if device is not None and torch.device(device).type == "cuda":
+            self.multinomial.cuda(device)
         self._refresh_scalars()
         self._pending = weakref.WeakSet()     # undo logs of differentiable forwards still alive
 
@@ -364,7 +369,8 @@ class CRDLoss(nn.Module):
         super(CRDLoss, self).__init__()
         self.embed_s = Embed(opt.s_dim, opt.feat_dim)
         self.embed_t = Embed(opt.t_dim, opt.feat_dim)
-        self.contrast = ContrastMemory(opt.feat_dim, opt.n_data, opt.nce_k, opt.nce_t, opt.nce_m)
+        self.contrast = ContrastMemory(opt.feat_dim, opt.n_data, opt.nce_k, opt.nce_t, opt.nce_m,
+                                       device=getattr(opt, "bank_device", None))     # optional, see ContrastMemory
         self.criterion_t = ContrastLoss(opt.n_data)
         self.criterion_s = ContrastLoss(opt.n_data)
 

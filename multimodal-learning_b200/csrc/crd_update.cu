@@ -1,7 +1,7 @@
 // K5: fused momentum row update + L2 renormalisation of both memory banks.
 //
 // Replaces the 2 x (index_select, mul_, add_, pow, sum, pow, div, index_copy_) chain of
-// CL_utils/CRD_criterion.py:66-79 with one launch: one warp per (anchor, bank).
+// CL_utils/CRD_criterion.py:66-79 with one launch: one warp per (anchor, bank); repeated ids: last occurrence wins.
 // Arithmetic follows the reference op for op in fp32 (separate multiply and add, no
 // FMA contraction) so a row differs from torch's only by the order of the norm's sum.
 #include "common.cuh"
@@ -21,6 +21,15 @@ __global__ void __launch_bounds__(kUpdThreads) crd_update_kernel(
   const int64_t i = w >> 1;
   const int64_t row = y[i];
   if (row < row_begin || row >= row_end) return;          // not owned by this rank
+  // Duplicate ids in y (replacement sampling, DistributedSampler padding, the same id on two ranks of a sharded batch):
+  // the reference reads every old row first and then index_copy_s, so the stored row is ONE well-formed candidate.  Here
+  // only the LAST occurrence of an id updates its row (what index_copy_ does when it runs in order), the earlier ones
+  // step aside -- no two warps ever write the same row.
+  {
+    bool later = false;
+    for (int64_t j = i + 1 + lane; j < B; j += 32) later |= (y[j] == row);
+    if (__any_sync(kFullMask, later)) return;
+  }
   float* r = ((w & 1) ? bank2 : bank1) + (row - row_begin) * D;
   const float* v = ((w & 1) ? v2 : v1) + i * D;
   float ss = 0.f;

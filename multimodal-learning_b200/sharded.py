@@ -326,6 +326,18 @@ class ShardedContrastMemory(nn.Module):
         self._K, self._T, self._momentum = int(p[0].item()), p[1].item(), p[4].item()
         self._z_ready = False
 
+    # -- host-side scalar cache, as ContrastMemory: K, T, momentum and the Z state follow `params` wherever it is loaded from
+    def _refresh_scalars(self):
+        p = self.params.detach().cpu()
+        self._K = int(p[0].item())
+        self._T = p[1].item()
+        self._momentum = p[4].item()
+        self._z_ready = bool(p[2].item() > 0 and p[3].item() > 0)
+
+    def _load_from_state_dict(self, *args, **kwargs):
+        super()._load_from_state_dict(*args, **kwargs)
+        self._refresh_scalars()
+
     # ---- (de)sharding of the reference's state-dict layout ----
     def load_full_banks(self, memory_v1, memory_v2, params=None):
         """Take this rank's row block out of full [n, D] banks (e.g. a single-GPU checkpoint)."""
@@ -333,7 +345,7 @@ class ShardedContrastMemory(nn.Module):
         self.memory_v2.copy_(memory_v2[self.row_begin:self.row_end])
         if params is not None:
             self.params.copy_(params)
-            self._z_ready = bool(params[2].item() > 0 and params[3].item() > 0)
+            self._refresh_scalars()
 
     def gather_full_banks(self):
         """-> (memory_v1, memory_v2) as full [n, D] tensors on every rank (the reference's layout)."""

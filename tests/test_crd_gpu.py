@@ -412,6 +412,25 @@ def test_full_size_config2_properties(pkg, co):
     # closed form divides by its own B (=4); the kernel divided by 1024
     assert rel_err(g1[sub] * (B / len(sub)), w_g1) < TOL
     assert rel_err(g2[sub] * (B / len(sub)), w_g2) < TOL
+    # (i') loss, Z and both gradients of a 48-anchor slice at full K / n vs the float64 oracle: Z from the slice's own
+    #      Monte-Carlo estimate (CRD_criterion.py:52-59), the loss normalised by the slice (batch_norm = 48)
+    sub2 = torch.arange(200, 248, device=DEV)
+    pz = torch.tensor([K, T, -1, -1, 0.5], device=DEV)
+    v1s, v2s, idxs = v1[sub2].contiguous(), v2[sub2].contiguous(), idx[sub2].contiguous()
+    crd.crd_scores(m1, m2, v1s, v2s, idxs, T, set_Z=pz[2:4], want_out=False)
+    l_sub, _, gs1, gs2, _, _ = crd.crd_fused_loss_grad(m1, m2, v1s, v2s, idxs, T, Z, n, K)
+    rows2 = idxs.cpu()
+    uniq2, inv2 = torch.unique(rows2, return_inverse=True)
+    w_l, w_s1, w_s2, x1, x2 = co.crd_closed_form(m1[uniq2.to(DEV)].cpu(), m2[uniq2.to(DEV)].cpu(), v1s.cpu(), v2s.cpu(), inv2, T,
+                                                 Z[0].item(), Z[1].item(), n)
+    assert abs(l_sub.item() - w_l.item()) < TOL * abs(w_l.item())
+    assert rel_err(gs1, w_s1) < TOL and rel_err(gs2, w_s2) < TOL
+    # x = exp(dot/T)/Z  =>  the slice's Z estimate is mean(x) * Z * n
+    assert abs(pz[2].item() - x1.mean().item() * Z[0].item() * n) < TOL * pz[2].item()
+    assert abs(pz[3].item() - x2.mean().item() * Z[1].item() * n) < TOL * pz[3].item()
+    # ... and the full-batch loss is the batch-weighted sum of slice losses: (ii) below ties every slice to the full call
+    l_chk, _, _, _, _, _ = crd.crd_fused_loss_grad(m1, m2, v1s, v2s, idxs, T, Z, n, K, batch_norm=B)
+    assert abs(l_chk.item() * (B / len(sub2)) - l_sub.item()) < 1e-5 * abs(l_sub.item())
     # (ii) linearity over anchors
     h = B // 2
     la, _, ga1, _, _, _ = crd.crd_fused_loss_grad(m1, m2, v1[:h].contiguous(), v2[:h].contiguous(), idx[:h].contiguous(),
@@ -428,3 +447,25 @@ def test_full_size_config2_properties(pkg, co):
     mask = torch.ones(n, dtype=torch.bool, device=DEV)
     mask[y] = False
     assert torch.equal(m1.double().sum(1)[mask], chk1[mask])
+
+
+def test_duplicate_anchor_ids_update_rows_once(pkg, co):
+    """y with repeated ids (replacement sampling, DistributedSampler padding): the reference gathers all old rows first and
+    index_copy_s the candidates (CRD_criterion.py:66-79); on the host that is 'the last occurrence wins'.  The kernel must
+    leave exactly that well-formed, unit-norm row -- never a torn mix of two warps' writes."""
+    from multimodal_learning_b200 import crd
+    n, D, B = 50, 128, 64
+    gen = torch.Generator().manual_seed(3)
+    m1, m2 = co.memory_init(n, D, gen)
+    v1 = torch.nn.functional.normalize(torch.randn(B, D, generator=gen), dim=1)
+    v2 = torch.nn.functional.normalize(torch.randn(B, D, generator=gen), dim=1)
+    y = torch.randint(0, 12, (B,), generator=gen)                      # 64 draws from 12 ids: every id repeats
+    want1, want2 = m1.clone(), m2.clone()
+    co.momentum_update_(want1, y, v1, 0.5)
+    co.momentum_update_(want2, y, v2, 0.5)
+    for _ in range(5):                                                 # racy code would differ from run to run
+        d1, d2 = m1.to(DEV), m2.to(DEV)
+        crd.crd_memory_update(d1, d2, v1.to(DEV), v2.to(DEV), y.to(DEV), 0.5)
+        assert rel_err(d1, want1) < 1e-6 and rel_err(d2, want2) < 1e-6
+        touched = torch.unique(y)
+        assert (d1[touched.to(DEV)].norm(dim=1) - 1).abs().max().item() < 1e-5
