@@ -40,24 +40,83 @@ def _make(pkg, g):
     return mod.to(DEV)
 
 
+def _tf32(x):
+    """fp32 -> TF32 (10 explicit mantissa bits), round to nearest, returned as float64."""
+    i = x.float().contiguous().view(torch.int32)
+    return ((i + 0x1000) & ~0x1FFF).view(torch.float32).double()
+
+
+class _TF32Linear(torch.autograd.Function):
+    """y = A W^T + b with BOTH operands of every GEMM (forward, dgrad, wgrad) rounded to TF32 and float64 accumulation:
+    what an ideal TF32 tensor-core implementation of the contraction computes."""
+
+    @staticmethod
+    def forward(ctx, A, W, b):
+        Ar, Wr = _tf32(A), _tf32(W)
+        ctx.save_for_backward(Ar, Wr)
+        return Ar @ Wr.t() + b
+
+    @staticmethod
+    def backward(ctx, dy):
+        Ar, Wr = ctx.saved_tensors
+        dr = _tf32(dy)
+        return dr @ Wr, dr.t() @ Ar, dy.sum(0)
+
+
+def _tf32_error_bound(fo, g, tag):
+    """Per output / gradient: rel_err between the float64 oracle with exact contractions and the SAME oracle with ideal-TF32
+    contractions (encoders and nn.Bilinear gates), on the fixture's own inputs.  This is the error the north_star's TF32
+    allowance produces on this fixture; three BatchNorms over 9-12 rows amplify it well past 2e-3 in train mode."""
+    class Ops:
+        @staticmethod
+        def linear(A, W, b):
+            return _TF32Linear.apply(A, W, b)
+
+        @staticmethod
+        def bilinear(a, b, W, bias):
+            return _TF32Linear.apply(fo.kron_rows(a, b), W.flatten(1), bias)
+
+    def run(ops):
+        sd = {}
+        for k, v in g.state_dict("init.").items():
+            sd[k] = v.double() if v.is_floating_point() else v.clone()
+            if v.is_floating_point() and "running" not in k:
+                sd[k].requires_grad_(True)
+        vs = [g.t(f"vec{i + 1}").double().requires_grad_(True) for i in range(2)]
+        kw = {k: g.cfg[k] for k in ("skip", "use_bilinear", "gate1", "gate2") if k in g.cfg}
+        out = fo.polynomial_fusion_forward(sd, *vs, training=(tag == "train"), ops=ops, **kw)
+        (out * g.t(f"{tag}.G").double()).sum().backward()
+        res = {"out": out.detach(), "vec1": vs[0].grad, "vec2": vs[1].grad}
+        res.update({k: v.grad for k, v in sd.items() if v.is_floating_point() and v.requires_grad and v.grad is not None})
+        return res
+    exact, emu = run(fo.ExactOps), run(Ops)
+    assert rel_err(exact["out"], g.t(f"{tag}.out")) < 1e-5            # the float64 oracle IS the reference
+    return {k: rel_err(emu[k], exact[k]) for k in exact}
+
+
 GOLDENS = ["bilinear_c1", "bilinear_skip", "bilinear_odd", "bilinear_scaled", "trilinear_A", "trilinear_B",
            "polynomial_16", "polynomial_gate"]
 
 
 @pytest.mark.parametrize("path", ["simt", "auto"])
 @pytest.mark.parametrize("name", GOLDENS)
-def test_fusion_modules_match_reference_golden(pkg, golden, name, path):
+def test_fusion_modules_match_reference_golden(pkg, fo, golden, name, path):
     g = golden(name)
     tol = TOL_FP32 * 5 if path == "simt" else TOL_TC
-    base_tol = tol
     nvec = 3 if g.cfg["kind"] == "trilinear" else 2
     modes = ["eval"] + (["train"] if any(k.startswith("train.") for k in g.keys()) else [])
     for tag in modes:
+        bound = {}
         if g.cfg["kind"] == "polynomial" and path == "auto":
-            # TWO chained TF32 contractions (2e-3 each, north_star).  In train mode three BatchNorms over a batch of 9-12
-            # rows sit around them: their 1/sigma factors amplify the TF32 rounding in the backward (observed 1e-2 on the
-            # 8x8->8 fixture; the fp32 "simt" path of the same module meets 1e-4).
-            tol = 2 * base_tol if tag == "eval" else 10 * base_tol
+            # TWO chained TF32 contractions with three BatchNorms over 9-12 rows around them: the 2e-3 allowance of the
+            # north_star is a per-contraction figure on well-conditioned data.  Instead of a looser constant, every output
+            # and gradient is held to max(2e-3, 1.5 x the error an IDEAL TF32 implementation has on this very fixture),
+            # computed from the float64 oracle (observed: this repo's kernels sit within 5 % of that ideal, e.g. 1.24e-2 vs
+            # 1.24e-2 on polynomial_gate / train / linear_o2.0.weight; the fp32 "simt" path of the same module meets 1e-4).
+            bound = _tf32_error_bound(fo, g, tag)
+
+        def tol_for(key, tol=tol, bound=bound):
+            return max(tol, 1.5 * bound.get(key, 0.0))
         mod = _make(pkg, g)
         mod.set_kron_path(path)
         mod.train(tag == "train")
@@ -67,20 +126,20 @@ def test_fusion_modules_match_reference_golden(pkg, golden, name, path):
         (out * g.t(f"{tag}.G", DEV)).sum().backward()
         assert pkg._cabi.launch_count() >= before + 2          # forward + backward kernels really ran
         assert out.shape == g.t(f"{tag}.out").shape
-        assert rel_err(out, g.t(f"{tag}.out")) < tol
+        assert rel_err(out, g.t(f"{tag}.out")) < tol_for("out")
         for i, x in enumerate(ins):
-            assert rel_err(x.grad, g.t(f"{tag}.grad_vec{i + 1}")) < tol, f"vec{i + 1}"
+            assert rel_err(x.grad, g.t(f"{tag}.grad_vec{i + 1}")) < tol_for(f"vec{i + 1}"), f"vec{i + 1}"
         for k, v in mod.named_parameters():
             want = g.t(f"{tag}.grad.{k}")
             got = v.grad if v.grad is not None else torch.zeros_like(v)
             if want.abs().max() < 1e-4:          # bias feeding BatchNorm: exact gradient is 0 (rounding noise)
                 assert got.abs().max() < 1e-3, k
             else:
-                assert rel_err(got, want) < tol, k
+                assert rel_err(got, want) < tol_for(k), k
         if tag == "train":
             for k in g.keys():
                 if k.startswith("train.after."):
-                    assert rel_err(mod.state_dict()[k[12:]].float(), g.t(k).float()) < tol, k
+                    assert rel_err(mod.state_dict()[k[12:]].float(), g.t(k).float()) < max(tol, 1.5 * bound.get("out", 0.0)), k
 
 
 SHAPES = [
