@@ -902,7 +902,7 @@ def run_gpu_arm(args):
 
     # same call with the caller handing contrast_idx over as int32 (n_data < 2^31): half the PCIe bytes, same graph path.
     e2e_i32 = None
-    if mode == "cuda_graph":
+    if mode == "cuda_graph" and world == 1:          # the sharded module routes int64 ids (the reference's dtype) only
         try:
             host_pool32 = [(hp[0], hp[1], hp[2], hp[3].to(torch.int32).pin_memory()) for hp in host_pool]
             ex32 = (pool[0][0], pool[0][1], pool[0][2], pool[0][3].to(torch.int32))
@@ -1048,12 +1048,20 @@ def main():
     if args.impl == "reference":
         run_reference_arm(args)
         return
-    buf = _Tee()                  # modules print Z once (as the reference does): stdout carries ONE JSON line, the rest goes to stderr
+    # stdout carries ONE JSON line.  The modules print Z once (as the reference does) and NCCL prints its version banner
+    # from C: python-level prints are collected by _Tee, and file descriptor 1 itself points at stderr while the arm runs.
+    buf = _Tee()
+    sys.stdout.flush()
+    real_fd = os.dup(1)
+    os.dup2(2, 1)
     real_stdout, sys.stdout = sys.stdout, buf
     try:
         run_gpu_arm(args)
     finally:
         sys.stdout = real_stdout
+        sys.stdout.flush()
+        os.dup2(real_fd, 1)
+        os.close(real_fd)
     for ln in buf.lines:
         print(ln)
     sys.stdout.flush()
