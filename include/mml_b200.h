@@ -33,12 +33,22 @@ extern "C" {
 #define MML_ERR_UNSUPPORTED -3   /* shape outside what the kernels are built for   */
 #define MML_ERR_WORKSPACE   -4   /* workspace smaller than *_workspace_bytes()     */
 
-#define MML_ABI_VERSION 2   /* 2: seed_dev argument of the mml_kron_* entry points; multipos / relation / instance_sample added */
+#define MML_ABI_VERSION 3   /* 2: seed_dev argument of the mml_kron_* entry points; multipos / relation / instance_sample added
+                             * 3: mml_device_error_flags */
 
 int         mml_abi_version(void);
 const char* mml_last_error(void);
 /* Number of kernels this library has launched in this process (bench `gpu_launches`). */
 int64_t     mml_launch_count(void);
+
+/* Sticky per-device error flags.  Kernels that index memory with caller-supplied ids never read or write out of bounds:
+ * an id outside the bank is clamped to row 0 (gather / relation kernels) or dropped (routing kernels) and a bit is OR-ed
+ * into the current device's flag word -- the reference's index_select raises a device-side assert in the same situation
+ * (CRD_criterion.py:41,46).  mml_device_error_flags copies the word to *flags_host (this synchronises with the device)
+ * and clears it when `reset` != 0. */
+#define MML_DEVERR_CRD_INDEX   1u   /* contrast_idx / idx entry outside [0, n_rows) */
+#define MML_DEVERR_SHARD_OWNER 2u   /* routed id outside [0, rows_per_rank * world) */
+int         mml_device_error_flags(uint32_t* flags_host, int32_t reset);
 
 /* ------------------------------------------------------------------------- *
  * CRD contrastive memory (CL_utils/CRD_criterion.py)

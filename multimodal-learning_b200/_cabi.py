@@ -16,11 +16,12 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(PKG, "lib", "libmml_b200.so")
 
 _P = c_void_p
-ABI_VERSION = 2          # must equal MML_ABI_VERSION of include/mml_b200.h
+ABI_VERSION = 3          # must equal MML_ABI_VERSION of include/mml_b200.h
 _SIGNATURES = {
     "mml_abi_version": (ctypes.c_int, []),
     "mml_last_error": (c_char_p, []),
     "mml_launch_count": (c_int64, []),
+    "mml_device_error_flags": (ctypes.c_int, [_P, c_int32]),
     "mml_crd_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int32]),
     "mml_crd_fused_loss_grad": (ctypes.c_int, [
         _P, _P, c_int64, c_int32, _P, _P, _P, c_int32, _P, _P, c_int64, c_int64,
@@ -139,3 +140,24 @@ def cur_stream(device) -> c_void_p:
 
 def launch_count() -> int:
     return int(lib().mml_launch_count())
+
+
+DEVERR_CRD_INDEX = 1
+DEVERR_SHARD_OWNER = 2
+
+
+def device_error_flags(reset: bool = True) -> int:
+    """Sticky error flags of the current CUDA device (synchronises with it); see include/mml_b200.h MML_DEVERR_*."""
+    out = ctypes.c_uint32(0)
+    check(lib().mml_device_error_flags(ctypes.byref(out), int(reset)), "mml_device_error_flags")
+    return int(out.value)
+
+
+def check_device_errors() -> None:
+    """Raise if a kernel saw an out-of-range row id since the last check (the reference's index_select would have hit a
+    device-side assert; these kernels clamp / drop the id and set a flag instead of touching memory out of bounds)."""
+    f = device_error_flags(reset=True)
+    if f & DEVERR_CRD_INDEX:
+        raise IndexError("mml_b200: contrast_idx / idx holds a row id outside [0, n_data) (clamped to row 0 by the kernels)")
+    if f & DEVERR_SHARD_OWNER:
+        raise IndexError("mml_b200: a contrast_idx entry lies outside the sharded bank (dropped by the routing kernel)")

@@ -13,6 +13,11 @@ namespace mml {
 
 void set_error(const char* fmt, ...);
 extern std::atomic<int64_t> g_launch_count;
+uint32_t* device_error_word();          // core.cu: sticky per-device error flags (MML_DEVERR_*), may be NULL
+
+__device__ __forceinline__ void flag_device_error(uint32_t* word, uint32_t bit) {
+  if (word != nullptr) atomicOr(word, bit);
+}
 
 inline int check_launch(const char* what) {
   g_launch_count.fetch_add(1, std::memory_order_relaxed);

@@ -47,6 +47,8 @@ struct GatherArgs {
   float* part_grad;         // [B, chunks, 2, D]
   float* part_scal;         // [B, chunks, 4]
   int64_t cols;
+  int64_t n_rows;           // rows of each bank: ids outside [0, n_rows) are flagged (MML_DEVERR_CRD_INDEX) and read row 0
+  uint32_t* err;
   int32_t D;
   int32_t chunk_cols;
   int32_t chunks;
@@ -249,7 +251,11 @@ __global__ void __launch_bounds__(kCtaThreads, MINB) crd_gather_kernel(const Gat
     const int64_t mycol = cb + lane;
     const bool myvalid = mycol < c1;
     int32_t myrow = 0;
-    if (myvalid) myrow = sg.idx32 ? sg.idx32[seg_begin + mycol] : static_cast<int32_t>(sg.idx64[seg_begin + mycol]);
+    if (myvalid) {
+      const int64_t r64 = sg.idx32 ? static_cast<int64_t>(sg.idx32[seg_begin + mycol]) : sg.idx64[seg_begin + mycol];
+      if (static_cast<uint64_t>(r64) >= static_cast<uint64_t>(a.n_rows)) flag_device_error(a.err, MML_DEVERR_CRD_INDEX);
+      else myrow = static_cast<int32_t>(r64);
+    }
     float mycf1 = 0.f, mycf2 = 0.f;
     if (MODE == kWeighted && myvalid) {
       mycf1 = a.coef1[seg_begin + mycol];
@@ -407,7 +413,11 @@ __global__ void __launch_bounds__(kCtaThreads) crd_gather_generic_kernel(const G
   const int64_t seg_begin = sg.begin, c0 = sg.c0, c1 = sg.c1;
   const bool has_pos = sg.has_pos;
   for (int64_t col = c0 + warp; col < c1; col += kCtaWarps) {
-    const int64_t row = sg.idx32 ? static_cast<int64_t>(sg.idx32[seg_begin + col]) : sg.idx64[seg_begin + col];
+    int64_t row = sg.idx32 ? static_cast<int64_t>(sg.idx32[seg_begin + col]) : sg.idx64[seg_begin + col];
+    if (static_cast<uint64_t>(row) >= static_cast<uint64_t>(a.n_rows)) {
+      if (lane == 0) flag_device_error(a.err, MML_DEVERR_CRD_INDEX);
+      row = 0;
+    }
     const float* p1 = a.bank1 + row * D;
     const float* p2 = a.bank2 + row * D;
     float g1, g2;
@@ -587,6 +597,8 @@ int launch_gather(const GatherArgs& a, int64_t B, cudaStream_t st) {
       break;
     default: {
       const size_t smem = (static_cast<size_t>(kCtaWarps) * 2 + 2) * a.D * sizeof(float);
+      if (smem > 48 * 1024)      // D > 1228: above the default dynamic shared-memory limit (D <= 2048 needs 80 KB)
+        cudaFuncSetAttribute(crd_gather_generic_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
       crd_gather_generic_kernel<MODE><<<grid, kCtaThreads, smem, st>>>(a);
     }
   }
@@ -644,6 +656,7 @@ static int fused_loss_grad_impl(
   a.bank1 = bank1; a.bank2 = bank2; a.v1 = v1; a.v2 = v2; set_idx(a, idx, idx_bytes); a.seg_ptr = seg_ptr; a.pos_flag = pos_flag;
   a.Z = Z; a.out1 = out_v1; a.out2 = out_v2; a.part_grad = w.part_grad; a.part_scal = w.part_scal;
   a.cols = cols; a.D = D; a.chunk_cols = p.chunk_cols; a.chunks = p.chunks;
+  a.n_rows = n_rows; a.err = device_error_word();
   a.inv_T = 1.0f / T;
   a.inv_TB = 1.0f / (T * static_cast<float>(batch_norm));
   const double Pn = 1.0 / static_cast<double>(n_data);                       // :204
@@ -706,6 +719,7 @@ extern "C" int mml_crd_scores(const float* bank1, const float* bank2, int64_t n_
   a.bank1 = bank1; a.bank2 = bank2; a.v1 = v1; a.v2 = v2; set_idx(a, idx, idx_bytes); a.seg_ptr = seg_ptr;
   a.Z = Z; a.out1 = out_v1; a.out2 = out_v2; a.part_grad = w.part_grad; a.part_scal = w.part_scal;
   a.cols = cols; a.D = D; a.chunk_cols = p.chunk_cols; a.chunks = p.chunks;
+  a.n_rows = n_rows; a.err = device_error_word();
   a.inv_T = 1.0f / T;
   rc = launch_gather<kScores>(a, B, st);
   if (rc != MML_OK) return rc;
@@ -738,6 +752,7 @@ extern "C" int mml_crd_weighted_rows(const float* bank1, const float* bank2, int
   a.bank1 = bank1; a.bank2 = bank2; set_idx(a, idx, idx_bytes); a.seg_ptr = seg_ptr; a.coef1 = coef1; a.coef2 = coef2;
   a.part_grad = w.part_grad; a.part_scal = w.part_scal;
   a.cols = cols; a.D = D; a.chunk_cols = p.chunk_cols; a.chunks = p.chunks;
+  a.n_rows = n_rows; a.err = device_error_word();
   rc = launch_gather<kWeighted>(a, B, st);
   if (rc != MML_OK) return rc;
   crd_finish_anchor_kernel<<<static_cast<unsigned>(B), 128, 0, st>>>(w.part_grad, w.part_scal, seg_ptr, cols, p.chunk_cols,
@@ -771,6 +786,7 @@ int peer_setup(GatherArgs& a, Plan& p, const float* bank1, const float* bank2, i
   a.bank1 = bank1; a.bank2 = bank2;
   a.cols = static_cast<int64_t>(ctas_per_anchor) * route_stride;   // finishers: every CTA publishes a partial
   a.D = D; a.chunk_cols = route_stride; a.chunks = ctas_per_anchor;
+  a.n_rows = n_rows; a.err = device_error_word();
   a.peer_world = world; a.peer_B_local = static_cast<int32_t>(B_local); a.peer_stride = route_stride;
   a.peer_route_chunks = route_chunks; a.peer_group = group;
   for (int i = 0; i < world; ++i) {

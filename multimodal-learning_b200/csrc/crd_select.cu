@@ -26,6 +26,8 @@ struct RelArgs {
   const int32_t* idx32;
   float* diff;
   int64_t cols;
+  int64_t n_rows;           // ids outside [0, n_rows) are flagged (MML_DEVERR_CRD_INDEX) and read row 0
+  uint32_t* err;
   int32_t D;
   int32_t chunk_cols;
 };
@@ -60,7 +62,11 @@ __global__ void __launch_bounds__(kThreads) crd_relation_kernel(const RelArgs a)
   for (int64_t cb = c0 + warp * 32; cb < c1; cb += kWarps * 32) {
     const int64_t mycol = cb + lane;
     int32_t myrow = 0;
-    if (mycol < c1) myrow = a.idx32 ? a.idx32[base + mycol] : static_cast<int32_t>(a.idx64[base + mycol]);
+    if (mycol < c1) {
+      const int64_t r64 = a.idx32 ? static_cast<int64_t>(a.idx32[base + mycol]) : a.idx64[base + mycol];
+      if (static_cast<uint64_t>(r64) >= static_cast<uint64_t>(a.n_rows)) flag_device_error(a.err, MML_DEVERR_CRD_INDEX);
+      else myrow = static_cast<int32_t>(r64);
+    }
     const int n_it = (static_cast<int>(min(static_cast<int64_t>(32), c1 - cb)) + ROWS_PER_IT - 1) / ROWS_PER_IT;
     for (int it = 0; it < n_it; ++it) {
       float4 r1[U][VPL], r2[U][VPL];
@@ -120,7 +126,11 @@ __global__ void __launch_bounds__(kThreads) crd_relation_generic_kernel(const Re
   const float nv1 = sqrtf(n1), nv2 = sqrtf(n2);
   const int64_t base = static_cast<int64_t>(b) * a.cols;
   for (int64_t col = c0 + warp; col < c1; col += kWarps) {
-    const int64_t row = a.idx32 ? static_cast<int64_t>(a.idx32[base + col]) : a.idx64[base + col];
+    int64_t row = a.idx32 ? static_cast<int64_t>(a.idx32[base + col]) : a.idx64[base + col];
+    if (static_cast<uint64_t>(row) >= static_cast<uint64_t>(a.n_rows)) {
+      if (lane == 0) flag_device_error(a.err, MML_DEVERR_CRD_INDEX);
+      row = 0;
+    }
     const float* p1 = a.bank1 + row * D;
     const float* p2 = a.bank2 + row * D;
     float t_dot = 0.f, t_sq = 0.f, s_dot = 0.f, s_sq = 0.f;
@@ -162,6 +172,7 @@ extern "C" int mml_crd_relation_diff(const float* bank1, const float* bank2, int
                 "crd_relation_diff: banks and v1/v2 must be 16-byte aligned");
   RelArgs a{};
   a.bank1 = bank1; a.bank2 = bank2; a.v1 = v1; a.v2 = v2; a.diff = diff; a.cols = cols; a.D = D;
+  a.n_rows = n_rows; a.err = device_error_word();
   a.idx64 = idx_bytes == 8 ? static_cast<const int64_t*>(idx) : nullptr;
   a.idx32 = idx_bytes == 4 ? static_cast<const int32_t*>(idx) : nullptr;
   // >= ~8 waves of 148 SMs x 4 CTAs when the problem allows; chunks of whole 128-column CTA passes

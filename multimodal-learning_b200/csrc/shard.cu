@@ -14,7 +14,8 @@ constexpr int kRouteWarps = kRouteThreads / 32;
 template <bool kScatter>
 __global__ void __launch_bounds__(kRouteThreads) shard_route_kernel(
     const int64_t* __restrict__ idx, int64_t B, int64_t cols, int32_t chunk_cols, int32_t chunks, int64_t rows_per_rank,
-    int32_t world, int64_t* __restrict__ counts, const int64_t* __restrict__ offsets, int32_t* __restrict__ out) {
+    int32_t world, int64_t* __restrict__ counts, const int64_t* __restrict__ offsets, int32_t* __restrict__ out,
+    uint32_t* __restrict__ err) {
   __shared__ int64_t run[kRouteWarps][32];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t w = static_cast<int64_t>(blockIdx.x) * kRouteWarps + warp;     // = b * chunks + c
@@ -32,7 +33,11 @@ __global__ void __launch_bounds__(kRouteThreads) shard_route_kernel(
     const int64_t k = k0 + lane;
     const bool valid = k < k_end;
     const int64_t row = valid ? idx[b * cols + k] : 0;
-    const int owner = valid ? static_cast<int>(row / rows_per_rank) : -1;
+    int owner = valid ? static_cast<int>(row / rows_per_rank) : -1;
+    if (valid && (row < 0 || owner >= world)) {        // id outside the bank: flagged and dropped (no slot, no write)
+      flag_device_error(err, MML_DEVERR_SHARD_OWNER);
+      owner = -1;
+    }
     for (int o = 0; o < world; ++o) {
       const unsigned m = __ballot_sync(kFullMask, owner == o);
       if (m == 0u) continue;
@@ -51,7 +56,7 @@ __global__ void __launch_bounds__(kRouteThreads) shard_route_kernel(
 // slots straight out of this (peer-mapped) buffer, so the all_to_all and its host-side split sizes disappear.
 __global__ void __launch_bounds__(kRouteThreads) shard_route_strided_kernel(
     const int64_t* __restrict__ idx, int64_t B, int64_t cols, int32_t chunk_cols, int32_t chunks, int64_t rows_per_rank,
-    int32_t world, int32_t* __restrict__ counts, int32_t* __restrict__ out) {
+    int32_t world, int32_t* __restrict__ counts, int32_t* __restrict__ out, uint32_t* __restrict__ err) {
   __shared__ int32_t run[kRouteWarps][32];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t w = static_cast<int64_t>(blockIdx.x) * kRouteWarps + warp;     // = b * chunks + c
@@ -74,14 +79,19 @@ __global__ void __launch_bounds__(kRouteThreads) shard_route_strided_kernel(
 #pragma unroll
     for (int u = 0; u < kPre; ++u) {
       const int64_t k = kg + u * 32 + lane;
-      rowv[u] = (k < k_end) ? static_cast<uint32_t>(__ldg(idx + b * cols + k)) : 0u;
+      int64_t r64 = (k < k_end) ? __ldg(idx + b * cols + k) : 0;
+      if (static_cast<uint64_t>(r64) >= static_cast<uint64_t>(rows_per_rank) * static_cast<uint64_t>(world)) {
+        flag_device_error(err, MML_DEVERR_SHARD_OWNER);       // id outside the bank: flagged and dropped below
+        r64 = -1;
+      }
+      rowv[u] = static_cast<uint32_t>(r64);                    // 0xffffffff marks a dropped id (global ids fit in 31 bits)
     }
 #pragma unroll
     for (int u = 0; u < kPre; ++u) {
       const int64_t k = kg + u * 32 + lane;
       if (kg + u * 32 >= k_end) break;                 // warp-uniform
-      const bool valid = k < k_end;
       const uint32_t row = rowv[u];
+      const bool valid = k < k_end && row != 0xffffffffu;
       const int owner = valid ? static_cast<int>(row / rpr) : -1;
       const uint32_t local = row - static_cast<uint32_t>(owner < 0 ? 0 : owner) * rpr;
       // lanes with the same owner form a group; rank inside the group = stable position
@@ -122,7 +132,7 @@ extern "C" int mml_shard_count(const int64_t* idx, int64_t B, int64_t cols, int3
   const int64_t warps = B * chunks;
   shard_route_kernel<false><<<static_cast<unsigned>((warps + kRouteWarps - 1) / kRouteWarps), kRouteThreads, 0,
                               static_cast<cudaStream_t>(stream)>>>(idx, B, cols, chunk_cols, chunks, rows_per_rank, world,
-                                                                   counts, nullptr, nullptr);
+                                                                   counts, nullptr, nullptr, device_error_word());
   return check_launch("shard_route_kernel<count>");
 }
 
@@ -136,7 +146,7 @@ extern "C" int mml_shard_scatter(const int64_t* idx, int64_t B, int64_t cols, in
   const int64_t warps = B * chunks;
   shard_route_kernel<true><<<static_cast<unsigned>((warps + kRouteWarps - 1) / kRouteWarps), kRouteThreads, 0,
                              static_cast<cudaStream_t>(stream)>>>(idx, B, cols, chunk_cols, chunks, rows_per_rank, world,
-                                                                  nullptr, offsets, out_local_ids);
+                                                                  nullptr, offsets, out_local_ids, device_error_word());
   return check_launch("shard_route_kernel<scatter>");
 }
 
@@ -146,12 +156,12 @@ extern "C" int mml_shard_route_strided(const int64_t* idx, int64_t B, int64_t co
   int rc = check(idx, B, cols, chunk_cols, rows_per_rank, world);
   if (rc != MML_OK) return rc;
   MML_REQUIRE(counts && ids_out, MML_ERR_INVALID_ARG, "shard_route_strided: null pointer");
-  MML_REQUIRE(rows_per_rank * world < (1LL << 32), MML_ERR_UNSUPPORTED, "shard_route_strided: global row ids must fit in uint32");
+  MML_REQUIRE(rows_per_rank * world < (1LL << 31), MML_ERR_UNSUPPORTED, "shard_route_strided: global row ids must fit in int32");
   if (B == 0) return MML_OK;
   const int32_t chunks = static_cast<int32_t>((cols + chunk_cols - 1) / chunk_cols);
   const int64_t warps = B * chunks;
   shard_route_strided_kernel<<<static_cast<unsigned>((warps + kRouteWarps - 1) / kRouteWarps), kRouteThreads, 0,
                                static_cast<cudaStream_t>(stream)>>>(idx, B, cols, chunk_cols, chunks, rows_per_rank, world,
-                                                                    counts, ids_out);
+                                                                    counts, ids_out, device_error_word());
   return check_launch("shard_route_strided_kernel");
 }

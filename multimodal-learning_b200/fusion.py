@@ -8,8 +8,9 @@ What runs where:
     `encoder2` are small and stay host-side PyTorch (SURVEY.md §2.3 rows F5/F6, F4);
   * the hot contraction -- append-1, outer product(s), flatten, `post_fusion_dropout`,
     `encoder1[0]` -- is ONE kernel family that never materialises the (d+1)^2 / (d+1)^3 tensor:
-    forward on tcgen05 tensor cores (`mml_kron_linear_fwd`), backward on CUDA cores
-    (`mml_kron_linear_bwd_simt`) in this round.
+    forward, weight gradient and factor gradients all on tcgen05 tensor cores (`mml_kron_linear_fwd`,
+    `mml_kron_linear_wgrad`, `mml_kron_linear_dgrad`); exact-fp32 CUDA-core kernels (`*_simt`) for shapes the
+    tensor kernels do not take and as the on-GPU cross-check of the tests.
   * `post_fusion_dropout` masks come from a counter-based hash of (seed, b, k) instead of
     torch's Philox stream (a tensor that is never stored cannot carry a torch mask); eval mode
     and p=0 are bit-for-bit the reference's math.
@@ -37,14 +38,18 @@ def init_max_weights(module):
             stdv = 1. / math.sqrt(m.weight.size(1))
             m.weight.data.normal_(0, stdv)
             m.bias.data.zero_()
+        if hasattr(m, "invalidate_kron_caches"):      # `.data` writes do not bump the version the packed copies are keyed on
+            m.invalidate_kron_caches()
 
 
 # --------------------------------------------------------------------------- #
 # the Kronecker linear op
 # --------------------------------------------------------------------------- #
 class KronLinearState:
-    """Per-module cache: chunk table (device) and the packed TF32 copy of the weight, refreshed
-    whenever the dense weight's version counter or storage changes."""
+    """Per-module cache: chunk table (device) and the packed TF32 copies of the weight, refreshed whenever the dense
+    weight's version counter or storage changes.  Writes through `.data` (`init_max_weights`, `p.data.clamp_()`, EMA
+    updates) do not bump the version counter: call `invalidate()` after them (the modules' `init_max_weights`,
+    `load_state_dict` and `_apply` hooks do)."""
 
     def __init__(self, dims):
         self.dims = tuple(int(d) for d in dims) + ((0,) if len(dims) == 2 else ())
@@ -56,6 +61,11 @@ class KronLinearState:
         self._wg_plans = {}         # (B, N) -> (tensor-core wgrad usable, workspace bytes)
         self._dg_plans = {}         # (B, N) -> (tensor-core dgrad usable, workspace bytes)
         self.packed_t = None        # transposed packed weight (dgrad's B operand)
+        self.packed_t_key = None
+
+    def invalidate(self):
+        """Forget the packed weight copies (next forward / backward repacks from the dense weight)."""
+        self.packed_key = None
         self.packed_t_key = None
 
     def dgrad_plan(self, B, N):
@@ -266,6 +276,21 @@ class _GatedKronFusion(nn.Module):
         # the nn.Bilinear gates are the same contraction without the appended 1
         self._zkron = {t: KronLinearState([dims_og[a], dims_og[b]]) for t, (a, b) in enumerate(gate_inputs, start=1)} \
             if use_bilinear else {}
+
+    def invalidate_kron_caches(self):
+        """Drop the packed TF32 weight copies: call after writing weights through `.data` (no version bump)."""
+        for st in [getattr(self, "_kron", None), getattr(self, "_kron2", None), *getattr(self, "_zkron", {}).values()]:
+            if st is not None:
+                st.invalidate()
+
+    def _load_from_state_dict(self, *args, **kwargs):
+        super()._load_from_state_dict(*args, **kwargs)
+        self.invalidate_kron_caches()
+
+    def _apply(self, fn, *args, **kwargs):
+        out = super()._apply(fn, *args, **kwargs)
+        self.invalidate_kron_caches()
+        return out
 
     def set_kron_path(self, path):
         """"auto" (tensor cores) or "simt" (exact fp32 CUDA cores) for every Kronecker contraction of the module."""

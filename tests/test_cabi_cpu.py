@@ -35,7 +35,7 @@ def test_library_exports_every_declared_symbol():
 
 def test_abi_version_and_error_string():
     lib = _cabi.lib()
-    assert lib.mml_abi_version() == _cabi.ABI_VERSION == 2
+    assert lib.mml_abi_version() == _cabi.ABI_VERSION == 3
     rc = lib.mml_alias_build_host(None, 0, None, None)
     assert rc == -1
     assert b"alias_build" in lib.mml_last_error()

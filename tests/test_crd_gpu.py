@@ -469,3 +469,24 @@ def test_duplicate_anchor_ids_update_rows_once(pkg, co):
         assert rel_err(d1, want1) < 1e-6 and rel_err(d2, want2) < 1e-6
         touched = torch.unique(y)
         assert (d1[touched.to(DEV)].norm(dim=1) - 1).abs().max().item() < 1e-5
+
+
+def test_out_of_range_ids_are_flagged_not_dereferenced(pkg, golden):
+    """The reference's index_select device-asserts on an id outside the bank (CRD_criterion.py:41,46).  The kernels clamp
+    the id to row 0 -- no out-of-bounds read -- and raise a sticky flag that `check_device_errors()` turns into an IndexError."""
+    g = golden("crd_d128")
+    mod = _make_module(pkg, g.cfg, g.state_dict("init."))
+    pkg.device_error_flags(reset=True)
+    f_s, f_t = g.t("step0.f_s", DEV), g.t("step0.f_t", DEV)
+    idx, cidx = g.t("step0.idx", DEV), g.t("step0.contrast_idx", DEV).clone()
+    loss = mod(f_s, f_t, idx, cidx)
+    assert torch.isfinite(loss).all()
+    pkg.check_device_errors()                                   # clean run: nothing raised
+    cidx[3, 5] = g.cfg["n"] + 12345                              # beyond the bank
+    cidx[7, 9] = -4                                              # negative
+    loss = mod(f_s, f_t, idx, cidx)
+    assert torch.isfinite(loss).all()
+    assert pkg.device_error_flags(reset=False) & pkg._cabi.DEVERR_CRD_INDEX
+    with pytest.raises(IndexError):
+        pkg.check_device_errors()
+    assert pkg.device_error_flags() == 0                         # the check cleared the flag

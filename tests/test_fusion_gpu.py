@@ -1,7 +1,7 @@
 """GPU parity tests of the Kronecker-fusion path vs the CPU oracle and the reference goldens.
 
-Tolerances (north_star): rel 2e-3 where TF32 tensor cores are used (the tcgen05 forward, path
-"auto"); the exact-fp32 CUDA-core kernels (path "simt", and every backward) are held to 2e-5.
+Tolerances (north_star): rel 2e-3 where TF32 tensor cores are used (path "auto": tcgen05 forward, weight gradient and
+factor gradients); the exact-fp32 CUDA-core kernels (path "simt") are held to 2e-5.
 `rel` = max|a-b| / max|b|."""
 from __future__ import annotations
 
@@ -210,6 +210,26 @@ def test_tensor_core_path_is_taken_and_weight_repack_tracks_updates(pkg, fo):
     Wd.mul_(2.0)                                        # in-place update (what an optimizer does) bumps ._version
     y1 = kron_linear(st, fd, Wd, bd)
     assert rel_err(y1, fo.kron_linear(fs, W * 2, bias)) < TOL_TC
+
+
+def test_data_writes_are_seen_after_invalidate(pkg, fo):
+    """Writes through `.data` (init_max_weights, EMA updates) do not bump the autograd version the packed TF32 weight copies
+    are keyed on: the modules drop their caches in init_max_weights / load_state_dict / .to(); `invalidate_kron_caches()` is
+    the explicit hook for everything else.  Forward (packed) and weight gradient (dense) must agree afterwards."""
+    torch.manual_seed(0)
+    mod = pkg.BilinearFusion(skip=0, dim1=32, dim2=32, mmhid=64, dropout_rate=0.0).to(DEV).eval()
+    v1, v2 = torch.randn(40, 32, device=DEV), torch.randn(40, 32, device=DEV)
+    y0 = mod(v1, v2)
+    pkg.init_max_weights(mod)                                    # new weights through .data
+    y1 = mod(v1, v2)
+    assert not torch.allclose(y0, y1)
+    sd = {k: v.detach().cpu() for k, v in mod.state_dict().items()}
+    want = fo.bilinear_fusion_forward(sd, v1.cpu(), v2.cpu(), skip=0)
+    assert rel_err(y1, want) < TOL_TC
+    mod.encoder1[0].weight.data.mul_(0.5)                        # silent write: stale until invalidated
+    mod.invalidate_kron_caches()
+    sd = {k: v.detach().cpu() for k, v in mod.state_dict().items()}
+    assert rel_err(mod(v1, v2), fo.bilinear_fusion_forward(sd, v1.cpu(), v2.cpu(), skip=0)) < TOL_TC
 
 
 @pytest.mark.parametrize("dims,N,p", [((32, 32), 64, 0.25), ((16, 24), 40, 0.1), ((8, 6, 10), 24, 0.25)])
