@@ -46,13 +46,17 @@ struct TcArgs {
   KronDropout dr;
 };
 
-template <bool kDropout>
+// kCps = chunks per pipeline stage (1 or 2).  With narrow outputs (Np <= 128) one chunk is only 2*Np <= 256 tensor-pipe
+// cycles, about what one round trip through the stage barriers costs the issuing threads: two chunks per stage halve
+// the number of waits / fences / arrivals / commits per MMA.
+template <bool kDropout, int kCps>
 __global__ void __launch_bounds__(kThreadsTc, 1) kron_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const TcArgs a) {
   uint32_t seed_lo = 0u, seed_hi = 0u;
   if (kDropout) kron_seed(a.dr, seed_lo, seed_hi);
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // carve: B stages | scalars (transposed: [n_scal][128]) | chunk table | barriers | tmem base
-  const uint32_t stage_bytes = static_cast<uint32_t>(a.Np) * 128u;
+  const uint32_t tile_bytes = static_cast<uint32_t>(a.Np) * 128u;          // one [Np x 32] weight tile
+  const uint32_t stage_bytes = tile_bytes * kCps;
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);     // 1024-B aligned, still a shared pointer
   uint8_t* sm_b = smem;
   float* sm_S = reinterpret_cast<float*>(smem + static_cast<size_t>(a.stages) * stage_bytes);
@@ -116,17 +120,19 @@ __global__ void __launch_bounds__(kThreadsTc, 1) kron_fwd_tc_kernel(const __grid
   const uint32_t tmem_base = *sm_tmem;
   const uint32_t tmem_d = tmem_base;                                  // accumulator: columns [0, Np)
   const uint32_t tmem_a = tmem_base + static_cast<uint32_t>(a.Np);    // A ring: stages x 32 columns
-  const int4* tab = a.table_in_smem ? sm_tab : a.table;
+  auto tab_at = [&](int i) -> int4 { return a.table_in_smem ? sm_tab[i] : __ldg(a.table + i); };   // explicit LDS / LDG
 
   if (warp == kGenWarps) {
     // ===================== TMA producer: weight tiles [Np x 32] =====================
     int s = 0;
     uint32_t ph = 0;
-    for (int c = c_begin; c < c_end; ++c) {
+    for (int c = c_begin; c < c_end; c += kCps) {
       mbar_wait(&bar_empty[s], ph ^ 1);
       if (elect_one_sync()) {
         mbar_arrive_expect_tx(&bar_full[s], stage_bytes);
-        tma_load_2d(sm_b + static_cast<size_t>(s) * stage_bytes, &tmap_w, c * kChunkK, 0, &bar_full[s]);
+#pragma unroll
+        for (int i = 0; i < kCps; ++i)        // a chunk index past the table reads zero weights (TMA out-of-bounds fill)
+          tma_load_2d(sm_b + static_cast<size_t>(s) * stage_bytes + i * tile_bytes, &tmap_w, (c + i) * kChunkK, 0, &bar_full[s]);
       }
       __syncwarp();
       if (++s == a.stages) { s = 0; ph ^= 1; }
@@ -136,16 +142,19 @@ __global__ void __launch_bounds__(kThreadsTc, 1) kron_fwd_tc_kernel(const __grid
     int s = 0;
     uint32_t ph = 0;
     const uint32_t b_base = smem_u32(sm_b);
-    for (int c = c_begin; c < c_end; ++c) {
+    for (int c = c_begin; c < c_end; c += kCps) {
       mbar_wait(&bar_full[s], ph);
       tc_fence_after();
       if (elect_one_sync()) {
-        const uint64_t b_desc = umma_desc_k_sw128(b_base + static_cast<uint32_t>(s) * stage_bytes);
-        const uint32_t a_col = tmem_a + s * kChunkK;
 #pragma unroll
-        for (int j = 0; j < kChunkK / 8; ++j)                  // +8 tf32 along K = +32 B inside the swizzle row = +2 in the descriptor
-          tc_mma_tf32_ts(tmem_d, a_col + j * 8, b_desc + 2 * j, a.idesc, (c > c_begin || j > 0) ? 1u : 0u);
-        tc_commit(&bar_empty[s]);          // frees the A columns and the B tile of this stage
+        for (int i = 0; i < kCps; ++i) {
+          const uint64_t b_desc = umma_desc_k_sw128(b_base + static_cast<uint32_t>(s) * stage_bytes + i * tile_bytes);
+          const uint32_t a_col = tmem_a + (s * kCps + i) * kChunkK;
+#pragma unroll
+          for (int j = 0; j < kChunkK / 8; ++j)                // +8 tf32 along K = +32 B inside the swizzle row = +2 in the descriptor
+            tc_mma_tf32_ts(tmem_d, a_col + j * 8, b_desc + 2 * j, a.idesc, (c > c_begin || i > 0 || j > 0) ? 1u : 0u);
+        }
+        tc_commit(&bar_empty[s]);          // frees the A columns and the B tiles of this stage
       }
       __syncwarp();
       if (++s == a.stages) { s = 0; ph ^= 1; }
@@ -166,40 +175,49 @@ __global__ void __launch_bounds__(kThreadsTc, 1) kron_fwd_tc_kernel(const __grid
     int cur_src = -1, cur_col = -1, s_prev = -1;
     int s = 0;
     uint32_t ph = 0;
-    for (int c = c_begin; c < c_end; ++c) {
-      const int4 e0 = tab[2 * c];
-      const int4 e1 = tab[2 * c + 1];
-      if (e0.z != cur_src || e0.w != cur_col) {          // (re)load this row's vector segment (rare: once per d1 or d1*d2 chunks)
-        cur_src = e0.z;
-        cur_col = e0.w;
-        const float* src = cur_src == 1 ? a.f1 : (cur_src == 2 ? a.f2 : a.f3);
-        const int d = cur_src == 1 ? a.d1 : (cur_src == 2 ? a.d2 : a.d3);
+    for (int c0 = c_begin; c0 < c_end; c0 += kCps) {
+      uint32_t r[kCps][kHalf];
+#pragma unroll
+      for (int i = 0; i < kCps; ++i) {
+        const int c = c0 + i;
+        if (kCps > 1 && c >= c_end) {                      // odd tail: the stage's second chunk does not exist
+#pragma unroll
+          for (int u = 0; u < kHalf; ++u) r[i][u] = 0u;
+          continue;
+        }
+        const int4 e0 = tab_at(2 * c);
+        const int4 e1 = tab_at(2 * c + 1);
+        if (e0.z != cur_src || e0.w != cur_col) {          // (re)load this row's vector segment (rare: once per d1 or d1*d2 chunks)
+          cur_src = e0.z;
+          cur_col = e0.w;
+          const float* src = cur_src == 1 ? a.f1 : (cur_src == 2 ? a.f2 : a.f3);
+          const int d = cur_src == 1 ? a.d1 : (cur_src == 2 ? a.d2 : a.d3);
+#pragma unroll
+          for (int u = 0; u < kHalf; ++u) {
+            const int e = ebase + u;
+            float x = 0.f;
+            if (cur_src == 0) x = (e == 0) ? 1.0f : 0.f;
+            else if (live && e < e1.x) x = __ldg(src + b * d + cur_col + e);
+            v[u] = x;
+          }
+        }
+        float sc = sm_S[e0.x * kTileM + row] * sm_S[e0.y * kTileM + row];
+        if (kDropout) sc *= a.dr.scale;
 #pragma unroll
         for (int u = 0; u < kHalf; ++u) {
-          const int e = ebase + u;
-          float x = 0.f;
-          if (cur_src == 0) x = (e == 0) ? 1.0f : 0.f;
-          else if (live && e < e1.x) x = __ldg(src + b * d + cur_col + e);
-          v[u] = x;
+          float x = sc * v[u];
+          if (kDropout) {
+            const int klog = e1.y + (ebase + u) * e1.z;
+            const int64_t cc = b * a.dr.pairs_per_row + (klog >> 1);
+            const uint32_t h = kron_hash(static_cast<uint32_t>(cc), static_cast<uint32_t>(static_cast<uint64_t>(cc) >> 32),
+                                         seed_lo, seed_hi);
+            const uint32_t r16 = (klog & 1) ? (h >> 16) : (h & 0xffffu);
+            x = (r16 >= a.dr.thresh) ? x : 0.f;
+          }
+          r[i][u] = __float_as_uint(x) + 0x1000u;          // round-to-nearest onto the TF32 grid (hardware truncates)
         }
       }
-      float sc = sm_S[e0.x * kTileM + row] * sm_S[e0.y * kTileM + row];
-      if (kDropout) sc *= a.dr.scale;
-      uint32_t r[kHalf];
-#pragma unroll
-      for (int u = 0; u < kHalf; ++u) {
-        float x = sc * v[u];
-        if (kDropout) {
-          const int klog = e1.y + (ebase + u) * e1.z;
-          const int64_t cc = b * a.dr.pairs_per_row + (klog >> 1);
-          const uint32_t h = kron_hash(static_cast<uint32_t>(cc), static_cast<uint32_t>(static_cast<uint64_t>(cc) >> 32),
-                                       seed_lo, seed_hi);
-          const uint32_t r16 = (klog & 1) ? (h >> 16) : (h & 0xffffu);
-          x = (r16 >= a.dr.thresh) ? x : 0.f;
-        }
-        r[u] = __float_as_uint(x) + 0x1000u;              // round-to-nearest onto the TF32 grid (hardware truncates)
-      }
-      if (s_prev >= 0) {                                  // publish the PREVIOUS chunk: its TMEM store had this chunk's
+      if (s_prev >= 0) {                                  // publish the PREVIOUS stage: its TMEM stores had this stage's
         tc_wait_st();                                     // arithmetic to complete in
         tc_fence_before();
         __syncwarp();
@@ -207,7 +225,8 @@ __global__ void __launch_bounds__(kThreadsTc, 1) kron_fwd_tc_kernel(const __grid
       }
       mbar_wait(&bar_empty[s], ph ^ 1);
       tc_fence_after();
-      tc_st_32x32b_x16(tmem_a + lane_base + s * kChunkK + ebase, r);
+#pragma unroll
+      for (int i = 0; i < kCps; ++i) tc_st_32x32b_x16(tmem_a + lane_base + (s * kCps + i) * kChunkK + ebase, r[i]);
       s_prev = s;
       if (++s == a.stages) { s = 0; ph ^= 1; }
     }
@@ -291,7 +310,7 @@ __global__ void kron_pack_kernel(const float* __restrict__ W, int32_t N, int32_t
 }
 
 struct TcPlan {
-  int32_t nchunks, Np, n_scal, stages, tmem_cols, ksplit, chunks_per_split, table_in_smem;
+  int32_t nchunks, Np, n_scal, stages, tmem_cols, ksplit, chunks_per_split, table_in_smem, cps;
   size_t smem;
   bool ok;
 };
@@ -305,20 +324,23 @@ TcPlan make_tc_plan(int64_t B, int32_t N, int32_t d1, int32_t d2, int32_t d3) {
   p.table_in_smem = table_bytes <= static_cast<size_t>(kMaxSmemTable) ? 1 : 0;
   const size_t fixed = static_cast<size_t>(p.n_scal) * kTileM * sizeof(float) + (p.table_in_smem ? table_bytes : 0) + 256 + 1024;
   const size_t budget = 227 * 1024;
-  const size_t stage = static_cast<size_t>(p.Np) * 128;
+  p.cps = 1;      // two chunks per stage measured SLOWER on B200 (r2i: N=128 0.154 -> 0.194 ms; the wider TMEM ring costs the second CTA per SM)
+  const size_t stage = static_cast<size_t>(p.Np) * 128 * p.cps;
+  const int stage_cols = kChunkK * p.cps;
   int stages = fixed < budget ? static_cast<int>((budget - fixed) / stage) : 0;
   if (stages > 4) stages = 4;
+  while (stages > 2 && p.Np + stages * stage_cols > 512) --stages;
   const size_t half_budget = 113 * 1024;
-  if (fixed + 3 * stage <= half_budget && p.Np + 3 * kChunkK <= 256) {
+  if (fixed + 3 * stage <= half_budget && p.Np + 3 * stage_cols <= 256) {     // two CTAs per SM
     int st2 = static_cast<int>((half_budget - fixed) / stage);
     if (st2 > 4) st2 = 4;
-    while (p.Np + st2 * kChunkK > 256) --st2;
+    while (p.Np + st2 * stage_cols > 256) --st2;
     stages = st2;
   }
   p.stages = stages;
   p.ok = p.Np <= 256 && stages >= 2;
   p.smem = fixed + static_cast<size_t>(stages > 0 ? stages : 0) * stage;
-  int cols = p.Np + stages * kChunkK;
+  int cols = p.Np + stages * stage_cols;
   int pow2 = 32;
   while (pow2 < cols) pow2 <<= 1;
   p.tmem_cols = pow2;
@@ -331,6 +353,7 @@ TcPlan make_tc_plan(int64_t B, int32_t N, int32_t d1, int32_t d2, int32_t d3) {
   if (ks > max_ks) ks = max_ks;
   if (ks > 32) ks = 32;
   p.chunks_per_split = static_cast<int32_t>((p.nchunks + ks - 1) / ks);
+  p.chunks_per_split = (p.chunks_per_split + p.cps - 1) / p.cps * p.cps;     // splits start on a stage boundary
   p.ksplit = (p.nchunks + p.chunks_per_split - 1) / p.chunks_per_split;
   return p;
 }
@@ -413,13 +436,18 @@ extern "C" int mml_kron_linear_fwd(const float* f1, const float* f2, const float
   a.idesc = make_idesc_tf32(kTileM, p.Np);
   a.dr = make_kron_dropout(drop_p, seed, training, s.Kk, seed_dev);
   const dim3 grid(static_cast<unsigned>((B + kTileM - 1) / kTileM), p.ksplit);
-  if (a.dr.thresh != 0u) {
-    MML_CUDA(cudaFuncSetAttribute(kron_fwd_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(p.smem)));
-    kron_fwd_tc_kernel<true><<<grid, kThreadsTc, p.smem, st>>>(tmap, a);
-  } else {
-    MML_CUDA(cudaFuncSetAttribute(kron_fwd_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(p.smem)));
-    kron_fwd_tc_kernel<false><<<grid, kThreadsTc, p.smem, st>>>(tmap, a);
+#define MML_LAUNCH_FWD(DROP, CPS)                                                                                        \
+  {                                                                                                                      \
+    MML_CUDA(cudaFuncSetAttribute(kron_fwd_tc_kernel<DROP, CPS>, cudaFuncAttributeMaxDynamicSharedMemorySize,             \
+                                  static_cast<int>(p.smem)));                                                            \
+    kron_fwd_tc_kernel<DROP, CPS><<<grid, kThreadsTc, p.smem, st>>>(tmap, a);                                            \
   }
+  if (a.dr.thresh != 0u) {
+    if (p.cps == 2) MML_LAUNCH_FWD(true, 2) else MML_LAUNCH_FWD(true, 1)
+  } else {
+    if (p.cps == 2) MML_LAUNCH_FWD(false, 2) else MML_LAUNCH_FWD(false, 1)
+  }
+#undef MML_LAUNCH_FWD
   rc = check_launch("kron_fwd_tc_kernel");
   if (rc != MML_OK) return rc;
   if (p.ksplit > 1) {

@@ -8,7 +8,8 @@
 // [Np x 32] tiles.  The Kronecker tensor is not materialised here either.  Everything the generators read arrives by
 // TMA from ONE transposed copy of the factors, FT [1 + d1 + d2 + d3][Bpad] (row 0 = ones, then the columns of f1, f2,
 // f3: row r < n_scal is exactly the per-row scalar R[r]):
-//   * per chunk two [1 x 32] boxes -- the rows of its scalars R[p], R[q] -- and
+//   * the rows of the chunks' scalars R[p], R[q] (one [1 x 32] or [4 x 32] box each when the four chunks share a row or
+//     use consecutive rows -- the common case -- else four single rows) and
 //   * per distinct vector segment of the tile one [32 rows x 32 b] box (128-byte swizzled),
 // so a generator thread does 12 128-bit shared loads, 24 multiplies and one tcgen05.st per stage; there is no global
 // load, cp.async or CTA barrier in the loop (mbarriers only).  Lanes past a chunk's length hold finite garbage that the
@@ -25,6 +26,7 @@ namespace {
 using namespace tc;
 
 constexpr int kBlkB = 32;          // batch rows per pipeline stage (= 4 MMAs of K = 8)
+constexpr int kWgThreads = kGenThreads + 96;   // 8 generator warps + factor-box TMA warp + MMA warp + dy^T TMA warp
 constexpr uint32_t kWgXBytes = 4 * kBlkB * 32 * 4;     // 4 vector-segment slots of [32 rows x 32 b] fp32
 constexpr uint32_t kWgSBytes = 8 * kBlkB * 4;          // 8 scalar rows of 32 b
 
@@ -35,26 +37,33 @@ struct WgArgs {
   int32_t d1, d2, d3;
   int32_t N, Np, nchunks, Kp;
   int32_t nblocks, blocks_per_split;
-  int32_t stages, tmem_cols;
+  int32_t stages, xstages, tmem_cols;      // stages: dy^T tiles + TMEM A slots;  xstages: factor-box ring (deeper)
   uint32_t idesc;
   KronDropout dr;
 };
 
 template <bool kDropout>
-__global__ void __launch_bounds__(kThreadsTc, 1)
+__global__ void __launch_bounds__(kWgThreads, 2)
 kron_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_dyT, const __grid_constant__ CUtensorMap tmap_x,
-                     const __grid_constant__ CUtensorMap tmap_s, const WgArgs a) {
+                     const __grid_constant__ CUtensorMap tmap_s, const __grid_constant__ CUtensorMap tmap_s4, const WgArgs a) {
   uint32_t seed_lo = 0u, seed_hi = 0u;
   if (kDropout) kron_seed(a.dr, seed_lo, seed_hi);
   extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // Two rings.  D ring (a.stages): dy^T tile [Np x 32] + 32 TMEM columns of A^T per stage, recycled when the stage's MMAs
+  // complete.  X ring (a.xstages, deeper): the factor boxes a stage's generators read, recycled as soon as they have read
+  // them -- deep enough that the ~1 us TMA round trip of the next boxes hides behind several stages of arithmetic
+  // (with one shared ring the generators sat 35 % of the time waiting for their boxes at N = 96).
   const uint32_t dy_bytes = static_cast<uint32_t>(a.Np) * 128u;
-  const uint32_t stage_bytes = dy_bytes + kWgXBytes + 1024u;         // dy^T tile | X slots | S rows (1 KB, 1024-aligned)
+  const uint32_t x_bytes = kWgXBytes + 1024u;                        // X slots | S rows (1 KB)
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + static_cast<size_t>(a.stages) * stage_bytes);
+  uint8_t* sm_dy = smem;
+  uint8_t* sm_x = smem + static_cast<size_t>(a.stages) * dy_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sm_x + static_cast<size_t>(a.xstages) * x_bytes);
   uint64_t* bar_full = bars;                    // [stages] A^T stored (8 warp arrivals) + dy^T landed (1 arrival + tx)
   uint64_t* bar_empty = bars + a.stages;        // [stages] MMAs of the stage complete
-  uint64_t* bar_xfull = bars + 2 * a.stages;    // [stages] factor boxes landed (1 arrival + tx)
-  uint64_t* bar_acc = bars + 3 * a.stages;
+  uint64_t* bar_xfull = bars + 2 * a.stages;    // [xstages] factor boxes landed (1 arrival + tx)
+  uint64_t* bar_xempty = bar_xfull + a.xstages; // [xstages] generators have read the boxes (8 warp arrivals)
+  uint64_t* bar_acc = bar_xempty + a.xstages;
   uint32_t* sm_tmem = reinterpret_cast<uint32_t*>(bar_acc + 1);
 
   const int warp = warp_idx_sync();
@@ -67,10 +76,14 @@ kron_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_dyT, const __grid_
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_dyT)) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_x)) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_s)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_s4)) : "memory");
     for (int s = 0; s < a.stages; ++s) {
       mbar_init(&bar_full[s], kGenWarps + 1);
       mbar_init(&bar_empty[s], 1);
+    }
+    for (int s = 0; s < a.xstages; ++s) {
       mbar_init(&bar_xfull[s], 1);
+      mbar_init(&bar_xempty[s], kGenWarps);
     }
     mbar_init(bar_acc, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -108,25 +121,51 @@ kron_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_dyT, const __grid_
       }
     nown += own[c] ? 1 : 0;
   }
+  // Scalar rows of the four chunks: usually ONE row shared by all four (mode 0: one [32 x 1] box) or four consecutive rows
+  // (mode 1: one [32 x 4] box) -- bilinear tiles are (p consecutive, q = 0), trilinear core tiles (p shared, q consecutive) --
+  // so a stage costs 4 TMA instructions instead of 10; anything else (mode 2) loads four single rows.
+  auto row_mode = [](const int (&r)[4]) {
+    if (r[1] == r[0] && r[2] == r[0] && r[3] == r[0]) return 0;
+    if (r[1] == r[0] + 1 && r[2] == r[0] + 2 && r[3] == r[0] + 3) return 1;
+    return 2;
+  };
+  const int p_mode = row_mode(rp), q_mode = row_mode(rq);
 
   if (warp == kGenWarps) {
-    // ===== TMA producer: per stage the factor boxes (generators) and the dy^T tile (MMA) =====
+    // ===== TMA producer of the X ring: the factor boxes the generators read =====
+    int k = 0;
+    uint32_t ph = 0;
+    for (int blk = blk_begin; blk < blk_end; ++blk) {
+      mbar_wait(&bar_xempty[k], ph ^ 1);
+      if (elect_one_sync()) {
+        uint8_t* st = sm_x + static_cast<size_t>(k) * x_bytes;
+        const int b0 = blk * kBlkB;
+        uint8_t* sp_rows = st + kWgXBytes;                      // R[p] rows at [0, 512), R[q] rows at [512, 1024)
+        mbar_arrive_expect_tx(&bar_xfull[k], static_cast<uint32_t>(nown) * (kBlkB * 32 * 4) +
+                                                 (p_mode == 0 ? 128u : 512u) + (q_mode == 0 ? 128u : 512u));
+        if (p_mode == 0) tma_load_2d(sp_rows, &tmap_s, b0, rp[0], &bar_xfull[k]);
+        else if (p_mode == 1) tma_load_2d(sp_rows, &tmap_s4, b0, rp[0], &bar_xfull[k]);
+        if (q_mode == 0) tma_load_2d(sp_rows + 512, &tmap_s, b0, rq[0], &bar_xfull[k]);
+        else if (q_mode == 1) tma_load_2d(sp_rows + 512, &tmap_s4, b0, rq[0], &bar_xfull[k]);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          if (p_mode == 2) tma_load_2d(sp_rows + c * 128, &tmap_s, b0, rp[c], &bar_xfull[k]);
+          if (q_mode == 2) tma_load_2d(sp_rows + 512 + c * 128, &tmap_s, b0, rq[c], &bar_xfull[k]);
+          if (own[c]) tma_load_2d(st + c * (kBlkB * 32 * 4), &tmap_x, b0, xrow[c], &bar_xfull[k]);
+        }
+      }
+      __syncwarp();
+      if (++k == a.xstages) { k = 0; ph ^= 1; }
+    }
+  } else if (warp == kGenWarps + 2) {
+    // ===== TMA producer of the D ring: dy^T tiles for the MMAs =====
     int s = 0;
     uint32_t ph = 0;
     for (int blk = blk_begin; blk < blk_end; ++blk) {
       mbar_wait(&bar_empty[s], ph ^ 1);
       if (elect_one_sync()) {
-        uint8_t* st = smem + static_cast<size_t>(s) * stage_bytes;
-        const int b0 = blk * kBlkB;
-        mbar_arrive_expect_tx(&bar_xfull[s], static_cast<uint32_t>(nown) * (kBlkB * 32 * 4) + kWgSBytes);
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          tma_load_2d(st + dy_bytes + kWgXBytes + (2 * c) * 128, &tmap_s, b0, rp[c], &bar_xfull[s]);
-          tma_load_2d(st + dy_bytes + kWgXBytes + (2 * c + 1) * 128, &tmap_s, b0, rq[c], &bar_xfull[s]);
-          if (own[c]) tma_load_2d(st + dy_bytes + c * (kBlkB * 32 * 4), &tmap_x, b0, xrow[c], &bar_xfull[s]);
-        }
         mbar_arrive_expect_tx(&bar_full[s], dy_bytes);
-        tma_load_2d(st, &tmap_dyT, b0, 0, &bar_full[s]);
+        tma_load_2d(sm_dy + static_cast<size_t>(s) * dy_bytes, &tmap_dyT, blk * kBlkB, 0, &bar_full[s]);
       }
       __syncwarp();
       if (++s == a.stages) { s = 0; ph ^= 1; }
@@ -135,12 +174,12 @@ kron_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_dyT, const __grid_
     // ===== MMA issuer =====
     int s = 0;
     uint32_t ph = 0;
-    const uint32_t b_base = smem_u32(smem);
+    const uint32_t b_base = smem_u32(sm_dy);
     for (int blk = blk_begin; blk < blk_end; ++blk) {
       mbar_wait(&bar_full[s], ph);
       tc_fence_after();
       if (elect_one_sync()) {
-        const uint64_t b_desc = umma_desc_k_sw128(b_base + static_cast<uint32_t>(s) * stage_bytes);
+        const uint64_t b_desc = umma_desc_k_sw128(b_base + static_cast<uint32_t>(s) * dy_bytes);
         const uint32_t a_col = tmem_a + s * kBlkB;
 #pragma unroll
         for (int j = 0; j < kBlkB / 8; ++j)
@@ -169,15 +208,15 @@ kron_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_dyT, const __grid_
       my_klog = q1.y + (e < q1.x ? e : 0) * q1.z;      // lanes past the chunk's length: any valid counter (never read)
     }
     // byte offsets inside a stage: scalar rows (broadcast reads) and this lane's swizzled row of its vector slot
-    const uint32_t off_sp = dy_bytes + kWgXBytes + (2 * ci) * 128 + half * 64;
-    const uint32_t off_sq = off_sp + 128;
-    const uint32_t off_x = dy_bytes + my_slot * (kBlkB * 32 * 4) + e * 128;
+    const uint32_t off_sp = kWgXBytes + (p_mode == 0 ? 0 : ci) * 128 + half * 64;
+    const uint32_t off_sq = kWgXBytes + 512 + (q_mode == 0 ? 0 : ci) * 128 + half * 64;
+    const uint32_t off_x = my_slot * (kBlkB * 32 * 4) + e * 128;
     const uint32_t sw = static_cast<uint32_t>(e & 7);
-    int s = 0, s_prev = -1;
-    uint32_t ph = 0;
+    int s = 0, s_prev = -1, k = 0;
+    uint32_t ph = 0, xph = 0;
     for (int blk = blk_begin; blk < blk_end; ++blk) {
-      const uint8_t* st = smem + static_cast<size_t>(s) * stage_bytes;
-      mbar_wait(&bar_xfull[s], ph);                    // implies the stage's previous MMAs are complete (producer waited)
+      const uint8_t* st = sm_x + static_cast<size_t>(k) * x_bytes;
+      mbar_wait(&bar_xfull[k], xph);
       uint32_t r[kHalf];
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
@@ -202,12 +241,16 @@ kron_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_dyT, const __grid_
         r[u * 4 + 2] = __float_as_uint(y2);
         r[u * 4 + 3] = __float_as_uint(y3);
       }
+      __syncwarp();                                      // every lane's shared-memory reads of the boxes are done
+      if (lane == 0) mbar_arrive(&bar_xempty[k]);        // X slot back to its producer
+      if (++k == a.xstages) { k = 0; xph ^= 1; }
       if (s_prev >= 0) {                                 // publish the PREVIOUS stage: its TMEM store had this stage's
         tc_wait_st();                                    // loads and multiplies to complete in
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&bar_full[s_prev]);
       }
+      mbar_wait(&bar_empty[s], ph ^ 1);                  // the MMAs that read this TMEM slot last time around are complete
       tc_fence_after();
       tc_st_32x32b_x16(tmem_a + lane_base + s * kBlkB + half * kHalf, r);
       s_prev = s;
@@ -316,7 +359,7 @@ __global__ void kron_unpack_kernel(const float* __restrict__ part, int32_t bspli
 }
 
 struct WgPlan {
-  int32_t nchunks, Np, Kp, stages, tmem_cols, ktiles, nblocks, bsplit, blocks_per_split, ft_rows;
+  int32_t nchunks, Np, Kp, stages, xstages, tmem_cols, ktiles, nblocks, bsplit, blocks_per_split, ft_rows;
   int64_t Bpad;
   size_t smem, dyT_bytes, ft_bytes, part_bytes;
   bool ok;
@@ -349,26 +392,36 @@ WgPlan make_wg_plan(int64_t B, int32_t N, int32_t d1, int32_t d2, int32_t d3) {
   p.nblocks = static_cast<int32_t>((B + kBlkB - 1) / kBlkB);
   p.Bpad = static_cast<int64_t>(p.nblocks) * kBlkB;
   p.ft_rows = 1 + d1 + d2 + d3 < 32 ? 32 : 1 + d1 + d2 + d3;       // at least one whole [32 x 32] box (zero rows below the factors)
-  const size_t fixed = 512 + 1024;
-  const size_t stage = static_cast<size_t>(p.Np) * 128 + kWgXBytes + 1024;
-  int stages = static_cast<int>((227 * 1024 - fixed) / stage);
-  if (stages > 8) stages = 8;
-  while (stages > 2 && p.Np + stages * kBlkB > 512) --stages;
-  // two CTAs per SM (their generators and MMAs interleave) when each still gets a deep enough ring
-  const size_t half_budget = 113 * 1024;
-  if (fixed + 3 * stage <= half_budget && p.Np + 3 * kBlkB <= 256) {
-    int st2 = static_cast<int>((half_budget - fixed) / stage);
-    while (p.Np + st2 * kBlkB > 256) --st2;
-    stages = st2;
+  // one CTA per SM: D ring of 4-6 stages (dy^T tile + 32 TMEM columns each), the rest of the 227 KB goes to the X ring
+  const size_t fixed = 1024 + 1024;
+  const size_t dstage = static_cast<size_t>(p.Np) * 128;
+  const size_t xstage = kWgXBytes + 1024;
+  int stages = p.Np <= 128 ? 6 : 4;
+  while (stages > 2 && (p.Np + stages * kBlkB > 512 || fixed + stages * dstage + 3 * xstage > 227 * 1024)) --stages;
+  int xstages = static_cast<int>((227 * 1024 - fixed - stages * dstage) / xstage);
+  if (xstages > 10) xstages = 10;
+  int ctas_per_sm = 1;
+  if (p.Np <= 128) {
+    // narrow outputs: a stage is only 2*Np <= 256 tensor-pipe cycles, less than one generator pass -- TWO CTAs per SM
+    // (<= 113 KB shared memory and <= 256 TMEM columns each) let one CTA's generators run under the other's MMAs
+    // (measured: 1 CTA with deep rings 0.207 ms vs 2 CTAs 0.164 ms at 33^3 -> 96, B = 8192)
+    int st2 = 5;
+    while (st2 > 2 && (p.Np + st2 * kBlkB > 256 || fixed + st2 * dstage + 3 * xstage > 113 * 1024)) --st2;
+    const int xs2 = static_cast<int>((113 * 1024 - fixed - st2 * dstage) / xstage);
+    if (p.Np + st2 * kBlkB <= 256 && xs2 >= 3) {
+      stages = st2;
+      xstages = xs2 > 6 ? 6 : xs2;
+      ctas_per_sm = 2;
+    }
   }
   p.stages = stages;
-  p.ok = p.Np <= 256 && stages >= 2;
-  p.smem = fixed + static_cast<size_t>(stages) * stage;
+  p.xstages = xstages;
+  p.ok = p.Np <= 256 && stages >= 2 && xstages >= 3;
+  p.smem = fixed + static_cast<size_t>(stages) * dstage + static_cast<size_t>(xstages > 0 ? xstages : 0) * xstage;
   int cols = p.Np + stages * kBlkB, pow2 = 32;
   while (pow2 < cols) pow2 <<= 1;
   p.tmem_cols = pow2;
   if (pow2 > 512) p.ok = false;
-  const int ctas_per_sm = (p.smem <= half_budget && pow2 <= 256) ? 2 : 1;
   // one split's partial tile costs N*Kp*8 bytes of traffic ~ N*Kp*8 / 6.5e12 s; a stage costs ~2*Np cycles at 1.9 GHz per SM slot
   const double stage_s = 2.0 * p.Np / 1.9e9;
   const double split_cost = (static_cast<double>(N) * p.Kp * 8.0 / 6.5e12) / stage_s;
@@ -432,21 +485,24 @@ extern "C" int mml_kron_linear_wgrad(const float* f1, const float* f2, const flo
   if (rc != MML_OK) return rc;
   rc = get_tensor_map_2d(FT, p.Bpad, p.ft_rows, kBlkB, 1, false, &tmap_s);
   if (rc != MML_OK) return rc;
+  CUtensorMap tmap_s4;
+  rc = get_tensor_map_2d(FT, p.Bpad, p.ft_rows, kBlkB, 4, false, &tmap_s4);
+  if (rc != MML_OK) return rc;
   WgArgs a{};
   a.table = reinterpret_cast<const int4*>(table);
   a.part = part;
   a.B = B; a.d1 = d1; a.d2 = d2; a.d3 = d3; a.N = N; a.Np = p.Np; a.nchunks = p.nchunks; a.Kp = p.Kp;
   a.nblocks = p.nblocks; a.blocks_per_split = p.blocks_per_split;
-  a.stages = p.stages; a.tmem_cols = p.tmem_cols;
+  a.stages = p.stages; a.xstages = p.xstages; a.tmem_cols = p.tmem_cols;
   a.idesc = make_idesc_tf32(kTileM, p.Np);
   a.dr = make_kron_dropout(drop_p, seed, training, s.Kk, seed_dev);
   const dim3 grid(p.ktiles, p.bsplit);
   if (a.dr.thresh != 0u) {
     MML_CUDA(cudaFuncSetAttribute(kron_wgrad_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(p.smem)));
-    kron_wgrad_tc_kernel<true><<<grid, kThreadsTc, p.smem, st>>>(tmap, tmap_x, tmap_s, a);
+    kron_wgrad_tc_kernel<true><<<grid, kWgThreads, p.smem, st>>>(tmap, tmap_x, tmap_s, tmap_s4, a);
   } else {
     MML_CUDA(cudaFuncSetAttribute(kron_wgrad_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(p.smem)));
-    kron_wgrad_tc_kernel<false><<<grid, kThreadsTc, p.smem, st>>>(tmap, tmap_x, tmap_s, a);
+    kron_wgrad_tc_kernel<false><<<grid, kWgThreads, p.smem, st>>>(tmap, tmap_x, tmap_s, tmap_s4, a);
   }
   rc = check_launch("kron_wgrad_tc_kernel");
   if (rc != MML_OK) return rc;
@@ -565,7 +621,8 @@ __global__ void __launch_bounds__(kDgThreads, 1) kron_dgrad_tc_kernel(const __gr
   const uint32_t tmem_base = *sm_tmem;
   const uint32_t tmem_acc = tmem_base;                 // 2 x 128 accumulator columns
   const uint32_t tmem_a = tmem_base + 2 * kDgTileK;    // dy tile: Np32 columns
-  const int4* tab = a.table_in_smem ? sm_tab : a.table;
+  // chunk descriptor i (two int4 per chunk): an explicit shared or read-only global load, never a generic one
+  auto tab_at = [&](int i) -> int4 { return a.table_in_smem ? sm_tab[i] : __ldg(a.table + i); };
 
   // ---- A operand: this CTA's dy rows -> TMEM, once (epilogue warps), then a CTA-wide sync publishes them ----
   if (warp < kDgEpiWarps) {
@@ -660,6 +717,8 @@ __global__ void __launch_bounds__(kDgThreads, 1) kron_dgrad_tc_kernel(const __gr
 #pragma unroll
     for (int e = 0; e < kHalf; ++e) { v[e] = 0.f; dv[e] = 0.f; }
     int cur_src = -1, cur_col = -1, cur_len = 0, cur_row = -1;
+    int run_p = 0;                 // fold_mode 2: scalar whose gradient is being accumulated in run_acc
+    float run_acc = 0.f;
     // A vector segment is one contiguous run of chunks (build_chunks), so its gradient leaves the registers once per CTA:
     //   * factors that are not among the per-row scalars R (f2 when bilinear, f3 when trilinear): plain stores into the
     //     zero-initialised partial buffer -- no read-modify-write anywhere on the global side;
@@ -683,8 +742,8 @@ __global__ void __launch_bounds__(kDgThreads, 1) kron_dgrad_tc_kernel(const __gr
     };
     auto new_segment = [&](int cg) {      // rare: once per run of chunks sharing a vector segment
       flush();
-      const int4 e0 = tab[2 * cg];
-      const int4 e1 = tab[2 * cg + 1];
+      const int4 e0 = tab_at(2 * cg);
+      const int4 e1 = tab_at(2 * cg + 1);
       cur_src = e0.z; cur_col = e0.w; cur_len = e1.x;
       cur_row = dg_xrow(e0, a.d1, a.d2);
 #pragma unroll
@@ -705,7 +764,7 @@ __global__ void __launch_bounds__(kDgThreads, 1) kron_dgrad_tc_kernel(const __gr
         for (int cc = 0; cc < 2; ++cc) {
           const int c = 2 * half + cc;
           const int cg = tt * 4 + c;
-          const int4 e0 = cg < a.nchunks ? tab[2 * cg] : make_int4(0, 0, 0, 0);
+          const int4 e0 = cg < a.nchunks ? tab_at(2 * cg) : make_int4(0, 0, 0, 0);
           float* dstp = sm_sc + par * (8 * kTileM) + (2 * c) * kTileM + row;
           asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dstp)),
                        "l"(ft_b + static_cast<int64_t>(e0.x) * a.Bpad) : "memory");
@@ -730,12 +789,12 @@ __global__ void __launch_bounds__(kDgThreads, 1) kron_dgrad_tc_kernel(const __gr
       for (int c = 0; c < 4; ++c) {
         const int cg = t * 4 + c;
         const bool cvalid = cg < a.nchunks;
-        const int4 e0 = cvalid ? tab[2 * cg] : make_int4(0, 0, 0, 0);
+        const int4 e0 = cvalid ? tab_at(2 * cg) : make_int4(0, 0, 0, 0);
         P[c] = e0.x;
         Q[c] = e0.y;
         XR[c] = cvalid ? dg_xrow(e0, a.d1, a.d2) : -1;
         if (kDropout) {
-          const int4 e1 = cvalid ? tab[2 * cg + 1] : make_int4(0, 0, 1, 0);
+          const int4 e1 = cvalid ? tab_at(2 * cg + 1) : make_int4(0, 0, 1, 0);
           KB[c] = e1.y;
           KS[c] = e1.z;
         }
@@ -787,24 +846,58 @@ __global__ void __launch_bounds__(kDgThreads, 1) kron_dgrad_tc_kernel(const __gr
       asm volatile("cp.async.wait_group 0;" ::: "memory");                  // next tile's scalars (issued a tile ago) have landed
       asm volatile("bar.sync 1, %0;" ::"n"(kDgEpiThreads) : "memory");      // both halves of every row have posted <dA, x>
       // dR[p] += <dA, x> R[q],  dR[q] += <dA, x> R[p].  Every dR element is touched by ONE thread per tile (fixed order):
-      // fold_mode 1 (bilinear, q == 0): half h folds chunks 2h, 2h+1;  2 (trilinear): half 0 folds the p side, half 1 the
-      // q side;  0 (factor widths below 4, where those sets could overlap inside a tile): half 0 folds everything.
+      //   fold_mode 1 (bilinear: q == 0 everywhere, p distinct inside a tile): half h folds chunks 2h, 2h+1;
+      //   fold_mode 2 (trilinear): half 0 folds the p side -- p repeats over runs of chunks, so the sum rides in a register
+      //     (run_p, run_acc) across tiles and reaches shared memory once per run -- half 1 the q side (distinct inside a tile:
+      //     four independent read-modify-writes in flight);
+      //   fold_mode 0 (factor widths below 4, where those sets could overlap inside a tile): half 0 folds everything.
+      // Row 0 of sm_dR (the constant 1) is a scratch row: written, never read out.
       {
         const float* dsr = sm_ds + (it & 1) * (4 * 2 * kTileM) + row;
+        float ds[4];
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
-          const bool mine_p = a.fold_mode == 1 ? (c >> 1) == half : half == 0;
-          const bool mine_q = a.fold_mode == 1 ? (c >> 1) == half : (a.fold_mode == 2 ? half == 1 : half == 0);
-          const bool do_p = mine_p && P[c] != 0, do_q = mine_q && Q[c] != 0;
-          if (do_p || do_q) {
-            float ds = dsr[c * 2 * kTileM] + dsr[c * 2 * kTileM + kTileM];
-            if (kDropout) ds *= a.dr.scale;
-            if (do_p) sm_dR[P[c] * kTileM + row] += ds * SQ[c];
-            if (do_q) sm_dR[Q[c] * kTileM + row] += ds * SP[c];
+          ds[c] = dsr[c * 2 * kTileM] + dsr[c * 2 * kTileM + kTileM];
+          if (kDropout) ds[c] *= a.dr.scale;
+        }
+        if (a.fold_mode == 1) {
+          float* r0 = sm_dR + (half == 0 ? P[0] : P[2]) * kTileM + row;
+          float* r1 = sm_dR + (half == 0 ? P[1] : P[3]) * kTileM + row;
+          const float o0 = *r0, o1 = *r1;
+          *r0 = o0 + (half == 0 ? ds[0] * SQ[0] : ds[2] * SQ[2]);
+          *r1 = o1 + (half == 0 ? ds[1] * SQ[1] : ds[3] * SQ[3]);
+        } else if (a.fold_mode == 2) {
+          if (half == 0) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              if (P[c] != run_p) {
+                if (run_p != 0) sm_dR[run_p * kTileM + row] += run_acc;
+                run_p = P[c];
+                run_acc = 0.f;
+              }
+              run_acc = fmaf(ds[c], SQ[c], run_acc);
+            }
+          } else {
+            float* rq[4];
+            float old[4];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              rq[c] = sm_dR + Q[c] * kTileM + row;
+              old[c] = *rq[c];
+            }
+#pragma unroll
+            for (int c = 0; c < 4; ++c) *rq[c] = fmaf(ds[c], SP[c], old[c]);
+          }
+        } else if (half == 0) {
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            if (P[c] != 0) sm_dR[P[c] * kTileM + row] += ds[c] * SQ[c];
+            if (Q[c] != 0) sm_dR[Q[c] * kTileM + row] += ds[c] * SP[c];
           }
         }
       }
     }
+    if (run_p != 0) sm_dR[run_p * kTileM + row] += run_acc;       // (fold_mode 2, half 0) the last run
     flush();
     asm volatile("bar.sync 1, %0;" ::"n"(kDgEpiThreads) : "memory");      // every fold and shared-memory flush has landed
     if (live) {

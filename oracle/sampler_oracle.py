@@ -5,7 +5,7 @@
 Parity status: the reference draws with numpy's mt19937 inside DataLoader workers; that stream cannot be reproduced by
 a counter-based GPU generator, so **the RNG stream is unpinned by construction**.  What IS pinned:
   * integer work, bit for bit: the kernel's output equals `instance_sample` below for the same seed
-    (Philox4x32-10 + multiply-shift for draws with replacement; keyed 4-round Feistel bijection + cycle walking for
+    (Philox4x32-10 + multiply-shift for draws with replacement; keyed 8-round Feistel bijection + cycle walking for
     draws without replacement);
   * the reference's contract, checked against pools built exactly like the reference builds them
     (`reference_pools`): column 0 = the anchor, positives from the anchor's class, negatives from the other classes,
@@ -60,8 +60,9 @@ def perm_element(j, M, key):
     todo = np.ones(x.shape, dtype=bool)
     while todo.any():
         L, R = x[todo] >> half, x[todo] & mask
-        for r in range(4):
-            t = L ^ (mix32(R ^ np.uint64(int(key[r]))) & mask)
+        for r in range(8):      # 8 rounds: 4 leave the first two images of a small domain far from jointly uniform
+            rk = np.uint64((int(key[r & 3]) + 0x9E3779B9 * (r >> 2)) & 0xFFFFFFFF)
+            t = L ^ (mix32(R ^ rk) & mask)
             L, R = R, t
         x[todo] = (L << half) | R
         todo = x >= np.uint64(M)

@@ -20,4 +20,9 @@ timeout 600 ncu --set full --clock-control none --import-source on -k 'regex:kro
     -o $OUT/${TAG}_prof_kron python scripts/ncu_kron.py 16384,128,128,256 > $OUT/${TAG}_ncu_kron.log 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k 'regex:kron_(fwd|wgrad|dgrad)_tc_kernel' -s 3 -c 3 -f \
     -o $OUT/${TAG}_prof_kron_c4 python scripts/ncu_kron.py 8192,32,32,32,96 > $OUT/${TAG}_ncu_kron_c4.log 2>&1
+for shp in 65536,64,64,128 65536,128,128,64; do
+  tagn=$(echo $shp | tr ',' '_')
+  timeout 600 ncu --set full --clock-control none --import-source on -k 'regex:kron_(fwd|wgrad|dgrad)_tc_kernel' -s 3 -c 3 -f \
+      -o $OUT/${TAG}_prof_kron_$tagn python scripts/ncu_kron.py $shp > $OUT/${TAG}_ncu_kron_$tagn.log 2>&1
+done
 ls -la $OUT | tail -8
