@@ -851,7 +851,7 @@ __global__ void __launch_bounds__(kDgThreads, 1) kron_dgrad_tc_kernel(const __gr
       //     (run_p, run_acc) across tiles and reaches shared memory once per run -- half 1 the q side (distinct inside a tile:
       //     four independent read-modify-writes in flight);
       //   fold_mode 0 (factor widths below 4, where those sets could overlap inside a tile): half 0 folds everything.
-      // Row 0 of sm_dR (the constant 1) is a scratch row: written, never read out.
+      // Row 0 of sm_dR (the constant 1, p or q == 0) is read but never written.
       {
         const float* dsr = sm_ds + (it & 1) * (4 * 2 * kTileM) + row;
         float ds[4];
@@ -861,11 +861,12 @@ __global__ void __launch_bounds__(kDgThreads, 1) kron_dgrad_tc_kernel(const __gr
           if (kDropout) ds[c] *= a.dr.scale;
         }
         if (a.fold_mode == 1) {
-          float* r0 = sm_dR + (half == 0 ? P[0] : P[2]) * kTileM + row;
-          float* r1 = sm_dR + (half == 0 ? P[1] : P[3]) * kTileM + row;
-          const float o0 = *r0, o1 = *r1;
-          *r0 = o0 + (half == 0 ? ds[0] * SQ[0] : ds[2] * SQ[2]);
-          *r1 = o1 + (half == 0 ? ds[1] * SQ[1] : ds[3] * SQ[3]);
+          const int pa = half == 0 ? P[0] : P[2], pb = half == 0 ? P[1] : P[3];
+          float* r0 = sm_dR + pa * kTileM + row;
+          float* r1 = sm_dR + pb * kTileM + row;
+          const float o0 = *r0, o1 = *r1;                         // two independent read-modify-writes in flight
+          if (pa != 0) *r0 = o0 + (half == 0 ? ds[0] * SQ[0] : ds[2] * SQ[2]);
+          if (pb != 0) *r1 = o1 + (half == 0 ? ds[1] * SQ[1] : ds[3] * SQ[3]);
         } else if (a.fold_mode == 2) {
           if (half == 0) {
 #pragma unroll
@@ -886,7 +887,8 @@ __global__ void __launch_bounds__(kDgThreads, 1) kron_dgrad_tc_kernel(const __gr
               old[c] = *rq[c];
             }
 #pragma unroll
-            for (int c = 0; c < 4; ++c) *rq[c] = fmaf(ds[c], SP[c], old[c]);
+            for (int c = 0; c < 4; ++c)
+              if (Q[c] != 0) *rq[c] = fmaf(ds[c], SP[c], old[c]);
           }
         } else if (half == 0) {
 #pragma unroll
