@@ -34,7 +34,7 @@ extern "C" {
 #define MML_ERR_WORKSPACE   -4   /* workspace smaller than *_workspace_bytes()     */
 
 #define MML_ABI_VERSION 3   /* 2: seed_dev argument of the mml_kron_* entry points; multipos / relation / instance_sample added
-                             * 3: mml_device_error_flags */
+                             * 3: mml_device_error_flags, mml_kron_linear_fwd_stats / mml_kron_fwd_stat_tiles / mml_bn_relu_fwd */
 
 int         mml_abi_version(void);
 const char* mml_last_error(void);
@@ -286,6 +286,22 @@ int     mml_kron_linear_fwd(const float* f1, const float* f2, const float* f3, i
                             int32_t d1, int32_t d2, int32_t d3, const int32_t* table, const float* Wp,
                             const float* bias, int32_t N, float drop_p, uint64_t seed, const uint64_t* seed_dev, int32_t training,
                             float* y, void* workspace, size_t workspace_bytes, void* stream);
+
+/* encoder1 = Linear -> BatchNorm1d -> ReLU (fusion.py:29,60): the forward can emit the per-column sums of y and y^2 of
+ * every 128-row tile from its epilogue (col_stats float[tiles][2][N], tiles = mml_kron_fwd_stat_tiles(...) > 0, i.e. the
+ * forward is not split over K), and mml_bn_relu_fwd finishes: batch statistics (from those partials when n_part > 0,
+ * else from y itself), the nn.BatchNorm1d running-statistics update (running_* may be NULL; momentum, eps as the module's;
+ * biased variance for normalisation, unbiased for running_var), then out = relu((y - mean) * invstd * gamma + beta).
+ * save_mean / save_invstd [N] are what the BatchNorm backward needs. */
+int64_t mml_kron_fwd_stat_tiles(int64_t B, int32_t N, int32_t d1, int32_t d2, int32_t d3);
+int     mml_kron_linear_fwd_stats(const float* f1, const float* f2, const float* f3, int64_t B,
+                                  int32_t d1, int32_t d2, int32_t d3, const int32_t* table, const float* Wp,
+                                  const float* bias, int32_t N, float drop_p, uint64_t seed, const uint64_t* seed_dev,
+                                  int32_t training, float* y, float* col_stats, void* workspace, size_t workspace_bytes,
+                                  void* stream);
+int     mml_bn_relu_fwd(const float* y, int64_t B, int32_t N, const float* col_stats, int32_t n_part,
+                        const float* gamma, const float* beta, float* running_mean, float* running_var,
+                        float momentum, float eps, float* out, float* save_mean, float* save_invstd, void* stream);
 
 /* Weight gradient on the tensor cores (same K permutation / chunk table as the forward):
  *   dW[n,k] = sum_b dy[b,n] A[b,k] m[b,k]   -> dense float[N, Kk] (every entry written).

@@ -65,6 +65,11 @@ _SIGNATURES = {
     "mml_kron_linear_fwd": (ctypes.c_int, [
         _P, _P, _P, c_int64, c_int32, c_int32, c_int32, _P, _P, _P, c_int32, c_float, ctypes.c_uint64, _P, c_int32,
         _P, _P, c_size_t, _P]),
+    "mml_kron_fwd_stat_tiles": (c_int64, [c_int64, c_int32, c_int32, c_int32, c_int32]),
+    "mml_kron_linear_fwd_stats": (ctypes.c_int, [
+        _P, _P, _P, c_int64, c_int32, c_int32, c_int32, _P, _P, _P, c_int32, c_float, ctypes.c_uint64, _P, c_int32,
+        _P, _P, _P, c_size_t, _P]),
+    "mml_bn_relu_fwd": (ctypes.c_int, [_P, c_int64, c_int32, _P, c_int32, _P, _P, _P, _P, c_float, c_float, _P, _P, _P, _P]),
     "mml_kron_wgrad_supported": (ctypes.c_int, [c_int64, c_int32, c_int32, c_int32, c_int32]),
     "mml_kron_wgrad_workspace_bytes": (c_size_t, [c_int64, c_int32, c_int32, c_int32, c_int32]),
     "mml_kron_linear_wgrad": (ctypes.c_int, [

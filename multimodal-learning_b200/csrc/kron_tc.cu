@@ -34,6 +34,7 @@ struct TcArgs {
   const int4* table;        // [nchunks][2]
   const float* bias;        // may be NULL
   float* out;               // y [B,N] (ksplit == 1) or partials [ksplit, B, N]
+  float* col_stats;         // optional [gridDim.x][2][N]: per-tile column sums of y and y^2 (ksplit == 1 only)
   int64_t B;
   int32_t d1, d2, d3;
   int32_t N, Np;
@@ -245,10 +246,46 @@ __global__ void __launch_bounds__(kThreadsTc, 1) kron_fwd_tc_kernel(const __grid
     const int split_col = ((a.Np / 2 + 15) / 16) * 16;               // warps 0-3: [0, split_col), warps 4-7: [split_col, Np)
     const int n_lo = half == 0 ? 0 : split_col;
     const int n_hi = half == 0 ? split_col : a.Np;
+    // BatchNorm batch statistics (fusion.py:29): per-column sums of y and y^2 over the tile's 128 rows.  Each warp reduces
+    // its 32 rows x 16 columns with a transposing butterfly (31 shuffles per quantity: after the steps over lane bits 4..0
+    // lane l holds column n0 + (l & 15)), the four row-warps meet in shared memory (the weight ring is idle by now) and
+    // the tile's partial goes to col_stats[tile][2][N]; a finisher kernel sums the tiles in a fixed order.
+    const bool stats = a.col_stats != nullptr;
+    float* sm_stat = reinterpret_cast<float*>(sm_b);                  // [4 row-warps][2][Np]
     for (int n0 = n_lo; n0 < n_hi; n0 += 16) {
       uint32_t acc[16];
       tc_ld_32x32b_x16(tmem_d + lane_base + n0, acc);
       tc_wait_ld();
+      if (stats) {
+        float sv[16], sq[16];
+#pragma unroll
+        for (int e = 0; e < 16; ++e) {
+          const int n = n0 + e;
+          const float yv = (live && n < a.N) ? __uint_as_float(acc[e]) + (add_bias ? __ldg(a.bias + n) : 0.f) : 0.f;
+          sv[e] = yv;
+          sq[e] = yv * yv;
+        }
+#pragma unroll
+        for (int e = 0; e < 16; ++e) {
+          sv[e] += __shfl_xor_sync(kFullMask, sv[e], 16);
+          sq[e] += __shfl_xor_sync(kFullMask, sq[e], 16);
+        }
+#pragma unroll
+        for (int w = 8; w >= 1; w >>= 1) {                         // halve the value set, keep the half this lane's bit selects
+          const bool up = (lane & w) != 0;
+#pragma unroll
+          for (int e = 0; e < w; ++e) {
+            const float s_send = up ? sv[e] : sv[e + w], q_send = up ? sq[e] : sq[e + w];
+            const float s_keep = up ? sv[e + w] : sv[e], q_keep = up ? sq[e + w] : sq[e];
+            sv[e] = s_keep + __shfl_xor_sync(kFullMask, s_send, w);
+            sq[e] = q_keep + __shfl_xor_sync(kFullMask, q_send, w);
+          }
+        }
+        if (lane < 16) {
+          sm_stat[((warp & 3) * 2 + 0) * a.Np + n0 + lane] = sv[0];
+          sm_stat[((warp & 3) * 2 + 1) * a.Np + n0 + lane] = sq[0];
+        }
+      }
       if (live) {
         if (vec_ok && n0 + 16 <= a.N) {
 #pragma unroll
@@ -269,6 +306,16 @@ __global__ void __launch_bounds__(kThreadsTc, 1) kron_fwd_tc_kernel(const __grid
             if (n < a.N) dst[n] = __uint_as_float(acc[e]) + (add_bias ? __ldg(a.bias + n) : 0.f);
           }
         }
+      }
+    }
+    if (stats) {
+      asm volatile("bar.sync 1, %0;" ::"n"(kGenThreads) : "memory");
+      for (int i = threadIdx.x; i < 2 * a.N; i += kGenThreads) {
+        const int qd = i / a.N, n = i - qd * a.N;
+        float t = 0.f;
+#pragma unroll
+        for (int w = 0; w < 4; ++w) t += sm_stat[(w * 2 + qd) * a.Np + n];
+        a.col_stats[(static_cast<int64_t>(blockIdx.x) * 2 + qd) * a.N + n] = t;
       }
     }
     tc_fence_before();
@@ -405,10 +452,24 @@ extern "C" size_t mml_kron_fwd_workspace_bytes(int64_t B, int32_t N, int32_t d1,
   return (p.ksplit > 1 ? static_cast<size_t>(p.ksplit) * B * N * sizeof(float) : 0) + 256;
 }
 
+extern "C" int64_t mml_kron_fwd_stat_tiles(int64_t B, int32_t N, int32_t d1, int32_t d2, int32_t d3) {
+  if (B < 1 || N < 1 || d1 < 1 || d2 < 1 || d3 < 0) return 0;
+  const TcPlan p = make_tc_plan(B, N, d1, d2, d3);
+  return (p.ok && p.ksplit == 1) ? (B + kTileM - 1) / kTileM : 0;
+}
+
 extern "C" int mml_kron_linear_fwd(const float* f1, const float* f2, const float* f3, int64_t B, int32_t d1, int32_t d2,
                                    int32_t d3, const int32_t* table, const float* Wp, const float* bias, int32_t N,
                                    float drop_p, uint64_t seed, const uint64_t* seed_dev, int32_t training, float* y, void* workspace,
                                    size_t workspace_bytes, void* stream) {
+  return mml_kron_linear_fwd_stats(f1, f2, f3, B, d1, d2, d3, table, Wp, bias, N, drop_p, seed, seed_dev, training, y, nullptr,
+                                   workspace, workspace_bytes, stream);
+}
+
+extern "C" int mml_kron_linear_fwd_stats(const float* f1, const float* f2, const float* f3, int64_t B, int32_t d1, int32_t d2,
+                                         int32_t d3, const int32_t* table, const float* Wp, const float* bias, int32_t N,
+                                         float drop_p, uint64_t seed, const uint64_t* seed_dev, int32_t training, float* y,
+                                         float* col_stats, void* workspace, size_t workspace_bytes, void* stream) {
   MML_REQUIRE(f1 && f2 && table && Wp && y, MML_ERR_INVALID_ARG, "kron_linear_fwd: null pointer");
   MML_REQUIRE((d3 > 0) == (f3 != nullptr), MML_ERR_INVALID_ARG, "kron_linear_fwd: f3 and d3 must both be set or both be absent");
   MML_REQUIRE(B >= 0 && d1 >= 1 && d2 >= 1 && d3 >= 0 && N >= 1, MML_ERR_INVALID_ARG, "kron_linear_fwd: bad sizes");
@@ -430,6 +491,9 @@ extern "C" int mml_kron_linear_fwd(const float* f1, const float* f2, const float
   a.table = reinterpret_cast<const int4*>(table);
   a.bias = bias;
   a.out = p.ksplit == 1 ? y : static_cast<float*>(workspace);
+  MML_REQUIRE(col_stats == nullptr || p.ksplit == 1, MML_ERR_UNSUPPORTED,
+              "kron_linear_fwd_stats: column statistics need an unsplit forward (mml_kron_fwd_stat_tiles() > 0)");
+  a.col_stats = col_stats;
   a.B = B; a.d1 = d1; a.d2 = d2; a.d3 = d3; a.N = N; a.Np = p.Np;
   a.nchunks = p.nchunks; a.chunks_per_split = p.chunks_per_split; a.ksplit = p.ksplit;
   a.n_scal = p.n_scal; a.stages = p.stages; a.tmem_cols = p.tmem_cols; a.table_in_smem = p.table_in_smem;

@@ -61,6 +61,7 @@ class KronLinearState:
         self._wg_plans = {}         # (B, N) -> (tensor-core wgrad usable, workspace bytes)
         self._dg_plans = {}         # (B, N) -> (tensor-core dgrad usable, workspace bytes)
         self.packed_t = None        # transposed packed weight (dgrad's B operand)
+        self.last_stats = None      # per-tile column sums of the last forward (consumed by the BatchNorm finisher)
         self.packed_t_key = None
 
     def invalidate(self):
@@ -138,8 +139,9 @@ class _KronLinearFn(torch.autograd.Function):
     """y = kron(append1(f1), append1(f2)[, append1(f3)]) * mask @ W^T + bias, without the Kronecker tensor."""
 
     @staticmethod
-    def forward(ctx, state, weight, bias, drop_p, training, seed, wkey, *factors):
+    def forward(ctx, state, weight, bias, drop_p, training, seed, wkey, want_stats, *factors):
         lib = _cabi.lib()
+        state.last_stats = None
         d1, d2, d3 = state.dims
         fs = [f.contiguous() for f in factors]
         B = fs[0].shape[0]
@@ -157,10 +159,13 @@ class _KronLinearFn(torch.autograd.Function):
         if state.path == "auto" and tc_ok:
             state.ensure(weight, wkey)
             ws = torch.empty(nws, dtype=torch.uint8, device=dev)
-            rc = lib.mml_kron_linear_fwd(_cabi.dptr(fs[0]), _cabi.dptr(fs[1]), f3p, B, d1, d2, d3, _cabi.dptr(state.table),
-                                         _cabi.dptr(state.packed), bptr, N, float(drop_p), seed, sdev, int(training),
-                                         _cabi.dptr(y), _cabi.dptr(ws), nws, st)
-            _cabi.check(rc, "mml_kron_linear_fwd")
+            tiles = int(lib.mml_kron_fwd_stat_tiles(B, N, d1, d2, d3)) if want_stats else 0
+            stats = torch.empty(tiles, 2, N, dtype=torch.float32, device=dev) if tiles > 0 else None
+            rc = lib.mml_kron_linear_fwd_stats(_cabi.dptr(fs[0]), _cabi.dptr(fs[1]), f3p, B, d1, d2, d3, _cabi.dptr(state.table),
+                                               _cabi.dptr(state.packed), bptr, N, float(drop_p), seed, sdev, int(training),
+                                               _cabi.dptr(y), _cabi.dptr(stats), _cabi.dptr(ws), nws, st)
+            _cabi.check(rc, "mml_kron_linear_fwd_stats")
+            state.last_stats = stats         # per-tile column sums of y, y^2 from the epilogue (BatchNorm finisher)
         else:
             rc = lib.mml_kron_linear_fwd_simt(_cabi.dptr(fs[0]), _cabi.dptr(fs[1]), f3p, B, d1, d2, d3, _cabi.dptr(w), bptr,
                                               N, float(drop_p), seed, sdev, int(training), _cabi.dptr(y), st)
@@ -183,7 +188,7 @@ class _KronLinearFn(torch.autograd.Function):
         B, N = dy.shape
         dev = dy.device
         need_w = ctx.needs_input_grad[1]
-        need_f = any(ctx.needs_input_grad[7:])
+        need_f = any(ctx.needs_input_grad[8:])
         dW = torch.empty_like(w) if need_w else None
         dfs = [torch.empty_like(f) for f in fs] if need_f else [None] * len(fs)
         state = ctx.state
@@ -220,10 +225,47 @@ class _KronLinearFn(torch.autograd.Function):
                 _cabi.dptr(simt_dW), st)
             _cabi.check(rc, "mml_kron_linear_bwd_simt")
         dbias = dy.sum(0) if (has_bias and ctx.needs_input_grad[2]) else None
-        return (None, dW, dbias, None, None, None, None, *dfs)
+        return (None, dW, dbias, None, None, None, None, None, *dfs)
 
 
-def kron_linear(state: KronLinearState, factors, weight, bias, drop_p=0.0, training=False, seed=None, weight_key=None):
+class _BNReLUFn(torch.autograd.Function):
+    """relu(batch_norm(y)) in training mode through `mml_bn_relu_fwd`: batch statistics from the Kronecker kernel's epilogue
+    partials when it emitted them (else from y), running-statistics update, normalise + affine + ReLU in one pass.
+    Backward: the ReLU mask and torch's native batch-norm backward on [B, N] (small; SURVEY.md §7.2 keeps it host-side)."""
+
+    @staticmethod
+    def forward(ctx, y, stats, weight, bias, bn):
+        lib = _cabi.lib()
+        y = y.contiguous()
+        B, N = y.shape
+        out = torch.empty_like(y)
+        mean = torch.empty(N, dtype=torch.float32, device=y.device)
+        invstd = torch.empty(N, dtype=torch.float32, device=y.device)
+        track = bn.track_running_stats and bn.running_mean is not None
+        rc = lib.mml_bn_relu_fwd(_cabi.dptr(y), B, N, _cabi.dptr(stats), 0 if stats is None else stats.shape[0],
+                                 _cabi.dptr(weight.detach()), _cabi.dptr(bias.detach()),
+                                 _cabi.dptr(bn.running_mean) if track else None, _cabi.dptr(bn.running_var) if track else None,
+                                 float(bn.momentum), float(bn.eps), _cabi.dptr(out), _cabi.dptr(mean), _cabi.dptr(invstd),
+                                 _cabi.cur_stream(y.device))
+        _cabi.check(rc, "mml_bn_relu_fwd")
+        if track and bn.num_batches_tracked is not None:
+            bn.num_batches_tracked.add_(1)
+        ctx.save_for_backward(y, out, mean, invstd, weight)
+        ctx.eps = float(bn.eps)
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        y, out, mean, invstd, weight = ctx.saved_tensors
+        g = (g * (out > 0)).contiguous()
+        dy, dw, db = torch.ops.aten.native_batch_norm_backward(g, y, weight, None, None, mean, invstd, True, ctx.eps,
+                                                               [True, True, True])
+        return dy, None, dw, db, None
+
+
+def kron_linear(state: KronLinearState, factors, weight, bias, drop_p=0.0, training=False, seed=None, weight_key=None,
+                want_stats=False):
     """Public functional form (used by the modules below and by the tests).  `weight_key` identifies the weight's
     CONTENT for the packed-copy cache when `weight` is a temporary derived from a parameter (defaults to the
     tensor's own storage pointer + version counter)."""
@@ -237,7 +279,7 @@ def kron_linear(state: KronLinearState, factors, weight, bias, drop_p=0.0, train
         # graph-safe (a captured step re-draws it on every replay; the kernels read it from device memory)
         seed = (torch.randint(0, 2 ** 62, (1,), dtype=torch.int64, device=factors[0].device)
                 if (training and drop_p > 0) else 0)
-    return _KronLinearFn.apply(state, weight, bias, drop_p, training, seed, weight_key, *factors)
+    return _KronLinearFn.apply(state, weight, bias, drop_p, training, seed, weight_key, bool(want_stats), *factors)
 
 
 # --------------------------------------------------------------------------- #
@@ -323,10 +365,24 @@ class _GatedKronFusion(nn.Module):
             return getattr(self, f"linear_o{t}")(torch.sigmoid(z) * h)
         return getattr(self, f"linear_o{t}")(own)
 
+    def _encode(self, enc, state, factors):
+        """Linear(kron) [-> BatchNorm1d -> ReLU] -> Dropout of one Kronecker encoder (fusion.py:29-30 / :94).  In training mode
+        the BatchNorm batch statistics come out of the Kronecker kernel's epilogue and one finisher kernel does
+        statistics + running-stat update + normalise + ReLU; eval mode, BatchNorm variants the
+        finisher does not cover (no affine, cumulative momentum) and the exact-fp32 path keep the modules' own ops."""
+        lin = enc[0]
+        bn = enc[1] if isinstance(enc[1], nn.BatchNorm1d) else None
+        fused = (bn is not None and self.training and bn.affine and bn.momentum is not None and state.path == "auto"
+                 and isinstance(enc[2], nn.ReLU))
+        y = kron_linear(state, factors, lin.weight, lin.bias, self.post_fusion_dropout.p, self.training, want_stats=fused)
+        if not fused:
+            return enc[1:](y)
+        out = _BNReLUFn.apply(y, state.last_stats, bn.weight, bn.bias, bn)
+        state.last_stats = None
+        return enc[3:](out)
+
     def _fuse(self, outs):
-        lin = self.encoder1[0]
-        y = kron_linear(self._kron, outs, lin.weight, lin.bias, self.post_fusion_dropout.p, self.training)
-        out = self.encoder1[1:](y)
+        out = self._encode(self.encoder1, self._kron, outs)
         if self.skip:
             ones = outs[0].new_ones(outs[0].shape[0], 1)
             out = torch.cat([out] + [torch.cat((o, ones), 1) for o in outs], 1)
@@ -373,14 +429,13 @@ class PolynomialFusion(_GatedKronFusion):
         vecs = [self.relu(vec1), self.relu(vec2)]
         o1 = self._branch(1, vecs, self.gate1)
         o2 = self._branch(2, vecs, self.gate2)
-        lin1, lin2 = self.encoder1[0], self.encoder2[0]
-        p = self.post_fusion_dropout.p
-        out12 = self.encoder1[1:](kron_linear(self._kron, [o1, o2], lin1.weight, lin1.bias, p, self.training))
+        lin2 = self.encoder2[0]
+        out12 = self._encode(self.encoder1, self._kron, [o1, o2])
         if lin2.weight.shape[1] != (out12.shape[1] + 1) ** 2:          # the reference fails in F.linear the same way
             raise RuntimeError(f"mat1 and mat2 shapes cannot be multiplied ({out12.shape[0]}x{(out12.shape[1] + 1) ** 2} "
                                f"and {lin2.weight.shape[1]}x{lin2.weight.shape[0]})")
         out12 = out12.contiguous()
-        out = self.encoder2[1:](kron_linear(self._kron2, [out12, out12], lin2.weight, lin2.bias, p, self.training))
+        out = self._encode(self.encoder2, self._kron2, [out12, out12])
         if self.skip:
             ones = o1.new_ones(o1.shape[0], 1)
             out = torch.cat((out, torch.cat((o1, ones), 1), torch.cat((o2, ones), 1)), 1)

@@ -321,6 +321,8 @@ class ShardedContrastMemory(nn.Module):
             self.params = self.params.to(device)
         self.multinomial = None          # built lazily: only the idx=None branch samples
         self._peer = {}                  # (B_local, cols, device) -> PeerExchange
+        self._side_stream = None         # routing runs here, under the Embed heads
+        self._route_side = None          # set by route_ahead, consumed by _peer_step
         self.grad_floats = 0             # room for the data-parallel heads' flattened gradient in each arena
         p = torch.tensor([K, T, -1, -1, momentum])
         self._K, self._T, self._momentum = int(p[0].item()), p[1].item(), p[4].item()
@@ -384,6 +386,26 @@ class ShardedContrastMemory(nn.Module):
             px = self._peer[key] = PeerExchange(self, B_local, cols, D, device, grad_floats=max(grad_floats, self.grad_floats))
         return px
 
+    def route_ahead(self, cidx, D):
+        """Start the routing of this step's contrast_idx on a side stream.  Routing needs nothing but the indices, so it
+        runs UNDER the Embed heads (small GEMMs that leave most SMs idle) instead of in front of the gather; `_peer_step`
+        joins the side stream before it publishes the slots.  The fork happens after everything already queued on the
+        current stream -- in particular after the previous step's post-gather barrier, so no peer is still reading the
+        slots that get overwritten.  Works inside a CUDA-graph capture (fork / join become graph dependencies)."""
+        cols = self._K + 1
+        if cidx.dim() != 2 or cidx.shape[1] != cols or not cidx.is_cuda:
+            return
+        dev = cidx.device
+        px = self.peer_arena(cidx.shape[0], cols, D, dev)
+        if self._side_stream is None:
+            self._side_stream = torch.cuda.Stream(dev)
+        side = self._side_stream
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            self.backend.route_strided(cidx, self.rows_per, self.world, px.chunk, px.counts, px.ids)
+        cidx.record_stream(side)
+        self._route_side = side
+
     def _peer_step(self, v1, v2, idx, cidx, n_data):
         """Local embeddings in, loss (global batch) + local dL/dv out.  Exchanges: routed ids / counts are PULLED by
         the owners inside K4; embeddings and anchor ids are PUSHED into every rank's buffers; partial gradients are
@@ -396,7 +418,11 @@ class ShardedContrastMemory(nn.Module):
         px = self.peer_arena(Bl, cols, D, v1.device)
         buf = px.step & 1
         px.step += 1
-        be.route_strided(cidx, self.rows_per, self.world, px.chunk, px.counts, px.ids)
+        if self._route_side is not None:          # routed ahead of the Embed heads on a side stream (route_ahead): join it
+            torch.cuda.current_stream(v1.device).wait_stream(self._route_side)
+            self._route_side = None
+        else:
+            be.route_strided(cidx, self.rows_per, self.world, px.chunk, px.counts, px.ids)
         px.push(v1, v2, idx.contiguous(), cidx[:, 0].contiguous(), buf)
         px.handle.barrier(channel=0)                  # everyone's slots, counts and slices are in place
         V1, V2, Y, pos_rows = px.V[buf, 0], px.V[buf, 1], px.YP[buf, 0], px.YP[buf, 1]
@@ -532,6 +558,8 @@ class ShardedCRDLoss(nn.Module):
                     mem.grad_floats = sum(p.numel() for p in self.parameters())
                     px = mem.peer_arena(idx.shape[0], mem._K + 1, self._feat_dim, f_s.device)
                     reducer = px.allreduce_sum
+                if os.environ.get("MML_ROUTE_AHEAD", "1") == "1":
+                    mem.route_ahead(contrast_idx, self._feat_dim)
                 v1, v2 = self._heads(f_s, f_t, reducer)
                 return _ShardedPeerFn.apply(v1, v2, mem, idx, contrast_idx, self.criterion_s.n_data)
             except Exception as e:                  # no peer mapping on this system: fall back, loudly, once

@@ -360,6 +360,50 @@ def test_backward_at_bench_sizes_sampled_vs_oracle(pkg, fo, B, dims, N, p_drop):
     assert torch.isfinite(Wd.grad).all()
 
 
+@pytest.mark.parametrize("B,dims,N", [(20000, (32, 32), 64), (19000, (16, 24), 40), (300, (32, 32), 64), (130, (8, 6, 10), 24)])
+def test_batchnorm_epilogue_and_finisher_match_torch(pkg, B, dims, N):
+    """encoder1 = Linear -> BatchNorm1d -> ReLU (fusion.py:29,60), training mode: K1 emits per-tile column sums of y, y^2 from
+    its epilogue (large batches: the forward is not split over K) or the finisher reduces them from y (small batches);
+    `mml_bn_relu_fwd` then does statistics, running-stat update (momentum 0.1, unbiased running_var), normalise, ReLU.
+    Checked against torch's own batch_norm on the SAME pre-activation: output, save statistics, running statistics,
+    num_batches_tracked, and the gradients that flow back into y and the BatchNorm parameters."""
+    from multimodal_learning_b200.fusion import KronLinearState, _BNReLUFn, kron_linear
+    fs, W, bias = _problem(B, dims, N, seed=B + 7)
+    st = KronLinearState(dims)
+    fd = [f.to(DEV) for f in fs]
+    tiles = pkg._cabi.lib().mml_kron_fwd_stat_tiles(B, N, *st.dims)
+    assert (tiles > 0) == (B >= 19000)
+    y = kron_linear(st, fd, W.to(DEV), bias.to(DEV), want_stats=True)
+    assert (st.last_stats is not None) == (tiles > 0)
+    if tiles > 0:                                                        # the epilogue's partials add up to the column sums
+        assert st.last_stats.shape == (tiles, 2, N)
+        assert rel_err(st.last_stats[:, 0].double().sum(0), y.double().sum(0)) < 1e-5
+        assert rel_err(st.last_stats[:, 1].double().sum(0), (y.double() ** 2).sum(0)) < 1e-5
+    torch.manual_seed(1)
+    bn = torch.nn.BatchNorm1d(N).to(DEV).train()
+    with torch.no_grad():
+        bn.weight.uniform_(0.5, 1.5)
+        bn.bias.uniform_(-0.5, 0.5)
+        bn.running_mean.uniform_(-1, 1)
+        bn.running_var.uniform_(0.5, 2)
+    ref = torch.nn.BatchNorm1d(N).to(DEV).train()
+    ref.load_state_dict(bn.state_dict())
+    ya = y.detach().clone().requires_grad_(True)
+    yb = y.detach().clone().requires_grad_(True)
+    before = pkg._cabi.launch_count()
+    out = _BNReLUFn.apply(ya, st.last_stats, bn.weight, bn.bias, bn)
+    assert pkg._cabi.launch_count() == before + 2
+    want = torch.relu(ref(yb))
+    G = torch.randn(B, N, generator=torch.Generator().manual_seed(2)).to(DEV)
+    (out * G).sum().backward()
+    (want * G).sum().backward()
+    assert rel_err(out, want) < 2e-5
+    assert rel_err(bn.running_mean, ref.running_mean) < 1e-5 and rel_err(bn.running_var, ref.running_var) < 1e-5
+    assert int(bn.num_batches_tracked) == int(ref.num_batches_tracked) == 1
+    assert rel_err(ya.grad, yb.grad) < 5e-5
+    assert rel_err(bn.weight.grad, ref.weight.grad) < 5e-5 and rel_err(bn.bias.grad, ref.bias.grad) < 5e-5
+
+
 def test_cpu_inputs_are_rejected(pkg):
     from multimodal_learning_b200.fusion import KronLinearState, kron_linear
     fs, W, bias = _problem(4, (8, 8), 8, seed=0)
