@@ -115,6 +115,14 @@ int mml_crd_relation_diff(
     const void* idx, int32_t idx_bytes, int64_t B, int64_t cols,
     float* diff, void* stream);
 
+/* Per-anchor ordering of the relation gaps (memory_new.py:303, :342-345): for every anchor b, sort the n columns
+ * diff[b*ld + col0 .. + n) -- descending != 0: largest first -- and write the first m column numbers as
+ * out[b*out_ld + j] = label0 + (column - col0).  Equal gaps are ordered by column (total, deterministic order).
+ * One CTA per anchor, bitonic network in shared memory; n <= mml_crd_sort_columns_max() (16384). */
+int32_t mml_crd_sort_columns_max(void);
+int     mml_crd_sort_columns(const float* diff, int64_t B, int64_t ld, int64_t col0, int32_t n, int32_t descending,
+                             int32_t m, int64_t label0, int64_t* out, int64_t out_ld, void* stream);
+
 /* Scores only (ContrastMemory.forward :41-49 [+ :62-63 when Z != NULL]).
  *   Z == NULL : out = exp(dot/T) (raw);  Z != NULL: out = exp(dot/T)/Z.
  *   sums      float[4] or NULL: {0, 0, sum raw side1, sum raw side2}

@@ -30,6 +30,8 @@ _SIGNATURES = {
         _P, _P, c_int64, c_int32, _P, _P, _P, c_int32, c_int64, c_int64, c_int64,
         c_float, _P, c_int64, _P, _P, _P, _P, _P, _P, c_size_t, _P]),
     "mml_crd_relation_diff": (ctypes.c_int, [_P, _P, c_int64, c_int32, _P, _P, _P, c_int32, c_int64, c_int64, _P, _P]),
+    "mml_crd_sort_columns_max": (c_int32, []),
+    "mml_crd_sort_columns": (ctypes.c_int, [_P, c_int64, c_int64, c_int64, c_int32, c_int32, c_int32, c_int64, _P, c_int64, _P]),
     "mml_crd_scores": (ctypes.c_int, [
         _P, _P, c_int64, c_int32, _P, _P, _P, c_int32, _P, c_int64, c_int64,
         c_float, _P, _P, _P, _P, _P, _P, c_size_t, _P]),

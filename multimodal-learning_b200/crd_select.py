@@ -38,6 +38,26 @@ from .crd import AliasMethod, ContrastMemory, Normalize
 eps = 1e-7      # CRD_loss.py:5
 
 
+def sort_columns(diff, col0, n, *, descending, first=None, label0=0):
+    """Column numbers of diff[:, col0:col0+n] in sorted order (the first `first` of them), per anchor, + label0:
+    `torch.sort(diff[:, col0:col0+n], descending=...)[1][:, :first] + label0` with exact ties ordered by column.
+    One CTA per anchor (`mml_crd_sort_columns`: bitonic network in shared memory) for n <= 16384 columns; wider
+    problems fall back to the library sort."""
+    lib = _cabi.lib()
+    B, ld = diff.shape
+    first = n if first is None else int(first)
+    if n > lib.mml_crd_sort_columns_max():
+        part = diff[:, col0:col0 + n]
+        order = torch.sort(part, dim=1, descending=descending, stable=True)[1] if first == n else \
+            torch.topk(part, first, dim=1, largest=descending, sorted=True)[1]
+        return order[:, :first] + label0
+    out = torch.empty(B, first, dtype=torch.int64, device=diff.device)
+    _cabi.check(lib.mml_crd_sort_columns(_cabi.dptr(diff, torch.float32), B, ld, int(col0), int(n), int(bool(descending)), first,
+                                         int(label0), _cabi.dptr(out), first, _cabi.cur_stream(diff.device)),
+                "mml_crd_sort_columns")
+    return out
+
+
 def crd_relation_diff(bank1, bank2, v1, v2, idx):
     """diff[b,k] = cos(bank1[idx[b,k]], v1[b]) - cos(bank2[idx[b,k]], v2[b])   (memory_new.py:288-292)."""
     B, D = v1.shape
@@ -141,7 +161,7 @@ class ContrastMemory_v3(ContrastMemory):
             raise RuntimeError("select_pos_pairs must be True: the reference's forward needs out_v2_pos (memory_new.py:363)")
         P, K = self._P, self._K
         diff = crd_relation_diff(self.memory_v1, self.memory_v2, v1.detach(), v2.detach(), idx)
-        order = torch.sort(diff[:, :P], dim=1, descending=True)[1]                          # :303
+        order = sort_columns(diff, 0, P, descending=True)                                   # :303
         picks = self._positive_picks(epoch, select_pos_mode)
         if picks is None:
             sel_pos = order[:, :self.P2].clone()                                            # :307
@@ -150,7 +170,7 @@ class ContrastMemory_v3(ContrastMemory):
         sel_pos[:, 0] = 0                                                                   # :325
         if self._neg_selected():
             # ascending order of diff, first K2 (:342-345) == top-K2 smallest, returned sorted
-            sel_neg = P + torch.topk(diff[:, P:P + K], min(self.K2, K), dim=1, largest=False, sorted=True)[1]
+            sel_neg = sort_columns(diff, P, K, descending=False, first=min(self.K2, K), label0=P)
         else:
             sel_neg = torch.arange(P, P + K, device=idx.device).view(1, -1).expand(idx.shape[0], -1)   # :359-361
         sel = torch.cat((sel_pos, sel_neg), 1)

@@ -194,3 +194,75 @@ extern "C" int mml_crd_relation_diff(const float* bank1, const float* bank2, int
   }
   return check_launch("crd_relation_kernel");
 }
+
+// =====================================================================================================
+// Per-anchor ordering of the relation gaps (memory_new.py:303 `torch.sort(diff_pos, descending=True)`, :342
+// `torch.sort(diff_neg)` + `[:, :K2]`): one CTA per anchor sorts n <= 16384 columns of diff[b, col0 .. col0+n) in shared
+// memory -- a bitonic network over 64-bit composites (order-preserving image of the float in the high word, column number in
+// the low word) -- and writes the first m column numbers.  The composite makes the order TOTAL (equal gaps are ordered by
+// column), so the result is deterministic; the library sort the reference calls may order exact ties either way, which is
+// why parity is defined on the selected ROWS (equal gaps come from the same bank row sampled twice).
+// =====================================================================================================
+namespace mml {
+namespace {
+
+constexpr int kSortThreads = 1024;
+
+__global__ void __launch_bounds__(kSortThreads) crd_sort_columns_kernel(const float* __restrict__ diff, int64_t ld, int64_t col0,
+                                                                        int32_t n, int32_t npow2, int32_t descending, int32_t m,
+                                                                        int64_t label0, int64_t* __restrict__ out, int64_t out_ld) {
+  extern __shared__ unsigned long long sm_keys[];
+  const int64_t b = blockIdx.x;
+  const float* src = diff + b * ld + col0;
+  for (int i = threadIdx.x; i < npow2; i += kSortThreads) {
+    unsigned long long key = ~0ull;                                   // padding sorts last
+    if (i < n) {
+      uint32_t u = __float_as_uint(src[i]);
+      u ^= (u >> 31) ? 0xFFFFFFFFu : 0x80000000u;                     // unsigned order == float order (ascending)
+      if (descending) u = ~u;
+      key = (static_cast<unsigned long long>(u) << 32) | static_cast<uint32_t>(i);
+    }
+    sm_keys[i] = key;
+  }
+  __syncthreads();
+  for (int k = 2; k <= npow2; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int t = threadIdx.x; t < (npow2 >> 1); t += kSortThreads) {
+        const int lo = ((t & ~(j - 1)) << 1) | (t & (j - 1));         // index with bit j clear
+        const int hi = lo | j;
+        const bool up = (lo & k) == 0;
+        const unsigned long long x = sm_keys[lo], y = sm_keys[hi];
+        if ((x > y) == up) {
+          sm_keys[lo] = y;
+          sm_keys[hi] = x;
+        }
+      }
+      __syncthreads();
+    }
+  }
+  for (int i = threadIdx.x; i < m; i += kSortThreads)
+    out[b * out_ld + i] = label0 + static_cast<int64_t>(static_cast<uint32_t>(sm_keys[i]));
+}
+
+}  // namespace
+}  // namespace mml
+
+extern "C" int32_t mml_crd_sort_columns_max(void) { return 16384; }
+
+extern "C" int mml_crd_sort_columns(const float* diff, int64_t B, int64_t ld, int64_t col0, int32_t n, int32_t descending,
+                                    int32_t m, int64_t label0, int64_t* out, int64_t out_ld, void* stream) {
+  MML_REQUIRE(diff && out, MML_ERR_INVALID_ARG, "crd_sort_columns: null pointer");
+  MML_REQUIRE(B >= 0 && n >= 1 && m >= 0 && m <= n && col0 >= 0 && col0 + n <= ld && out_ld >= m, MML_ERR_INVALID_ARG,
+              "crd_sort_columns: bad sizes");
+  MML_REQUIRE(n <= mml_crd_sort_columns_max(), MML_ERR_UNSUPPORTED, "crd_sort_columns: at most %d columns per anchor (got %d)",
+              mml_crd_sort_columns_max(), n);
+  if (B == 0 || m == 0) return MML_OK;
+  int32_t npow2 = 2;
+  while (npow2 < n) npow2 <<= 1;
+  const size_t smem = static_cast<size_t>(npow2) * sizeof(unsigned long long);
+  if (smem > 48 * 1024)
+    MML_CUDA(cudaFuncSetAttribute(mml::crd_sort_columns_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  mml::crd_sort_columns_kernel<<<static_cast<unsigned>(B), mml::kSortThreads, smem, static_cast<cudaStream_t>(stream)>>>(
+      diff, ld, col0, n, npow2, descending, m, label0, out, out_ld);
+  return mml::check_launch("crd_sort_columns_kernel");
+}

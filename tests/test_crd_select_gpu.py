@@ -268,3 +268,28 @@ def test_graphed_train_step_matches_eager(pkg, golden):
     assert rel_err(m1, m0) < 1e-6
     for a, b in zip(p0, p1):
         assert rel_err(b, a) < 1e-5
+
+
+@pytest.mark.parametrize("B,P,K,K2", [(7, 300, 700, 256), (5, 40, 200, 64), (3, 1, 33, 33), (16, 150, 16384, 8192)])
+def test_sort_columns_kernel_matches_library_sort(pkg, B, P, K, K2):
+    """`mml_crd_sort_columns` (per-anchor bitonic network in shared memory) against torch.sort on the same gaps: the
+    descending order of the P positive columns (memory_new.py:303) and the K2 smallest of the K negative columns in
+    ascending order (:342-345).  Distinct values: identical column numbers; exact ties: ordered by column."""
+    from multimodal_learning_b200.crd_select import sort_columns
+    gen = torch.Generator(device=DEV).manual_seed(B + K)
+    diff = torch.randn(B, P + K, device=DEV, generator=gen)
+    before = pkg._cabi.launch_count()
+    pos = sort_columns(diff, 0, P, descending=True)
+    neg = sort_columns(diff, P, K, descending=False, first=K2, label0=P)
+    assert pkg._cabi.launch_count() == before + 2
+    assert torch.equal(pos, torch.sort(diff[:, :P], dim=1, descending=True, stable=True)[1])
+    assert torch.equal(neg, P + torch.sort(diff[:, P:], dim=1, stable=True)[1][:, :K2])
+    # ties (the same bank row sampled twice gives bit-identical gaps): ordered by column number, values still sorted
+    tied = diff.clone()
+    tied[:, 3] = tied[:, 0]
+    tied[:, P + 5] = tied[:, P + 1]
+    tied[:, P + 9] = tied[:, P + 1]
+    pos_t = sort_columns(tied, 0, P, descending=True)
+    neg_t = sort_columns(tied, P, K, descending=False, first=K2, label0=P)
+    assert torch.equal(pos_t, torch.sort(tied[:, :P], dim=1, descending=True, stable=True)[1])
+    assert torch.equal(neg_t, P + torch.sort(tied[:, P:], dim=1, stable=True)[1][:, :K2])
