@@ -225,6 +225,131 @@ class ContrastMemory_v2(ContrastMemory_v3):
         super().__init__(inputSize, outputSize, P, K, T, momentum, select_pos_pairs, P2, select_neg_pairs="False", K2=K)
 
 
+class ContrastMemory_v4(ContrastMemory_v3):
+    """`MIA 2022/CL_utils/memory_new.py:398-561`: P2 selected positives + ALL K negatives, the negatives re-weighted by how much
+    more similar they look to the student than to the teacher (`relation_diff = s_relation - t_relation + 1`, :493-497).
+    Relations here are (bank-1 rows, v1) for the student side and (bank-2 rows, v2) for the teacher side (:462-466), i.e.
+    the MIRROR of ContrastMemory_v3's: positives are ordered by (t - s) = -(gap the relation kernel emits), the weight of a
+    negative is gap + 1.  Same kernels as v3 (relation gaps, per-anchor sort, scores with autograd, row update); the
+    selection / re-weighting glue on [B, P+K] stays host-side PyTorch."""
+
+    _mid_rule = "choice_30_100"                                                             # :478
+
+    def __init__(self, inputSize, outputSize, P, K, T=0.07, momentum=0.5, select_pos_pairs=True, P2=10,
+                 select_neg_pairs=False, neg_reweight=True, K2=512):
+        super().__init__(inputSize, outputSize, P, K, T, momentum, select_pos_pairs, P2, select_neg_pairs, K2)
+        self.neg_reweight = neg_reweight
+
+    def _reweight(self):
+        if self.neg_reweight == "True":
+            return True
+        if self.neg_reweight == "False":
+            return False
+        raise RuntimeError(f"neg_reweight must be 'True' or 'False' (memory_new.py:493,502); got {self.neg_reweight!r}")
+
+    def _select_v4(self, epoch, v1, v2, idx, select_pos_mode, sign):
+        """-> (sel_pos [B, P2] columns, w [B, K] negative weights or None).  `sign` = -1: positives by descending (t - s)
+        with this class's relation roles; +1: the v3 / mono roles."""
+        if self.select_pos_pairs is not True:
+            raise RuntimeError("select_pos_pairs must be True: the reference's forward needs out_v2_pos")
+        P = self._P
+        diff = crd_relation_diff(self.memory_v1, self.memory_v2, v1.detach(), v2.detach(), idx)
+        order = sort_columns(diff, 0, P, descending=(sign > 0))
+        picks = self._positive_picks(epoch, select_pos_mode)
+        if picks is None:
+            sel_pos = order[:, :self.P2].clone()
+        else:
+            sel_pos = order.index_select(1, torch.as_tensor(np.asarray(picks), dtype=torch.long).to(idx.device))
+        sel_pos[:, 0] = 0
+        return sel_pos, diff
+
+    def _combine(self, o, sel_pos, w):
+        """[B, P+K] scores -> cat(selected positives, (re-weighted) negatives) [B, P2+K, 1]  (:489-507)."""
+        P, K = self._P, self._K
+        neg = o[:, P:P + K]
+        if w is not None:
+            neg = neg * w
+        return torch.cat((o.gather(1, sel_pos), neg), 1).unsqueeze(2)
+
+    def forward(self, epoch, v1, v2, y, idx=None, select_pos_mode="mid"):
+        "v1 is the feature of the student model, v2 refer to the teacher feature."
+        v1, v2, y, idx = self._check_inputs_v3(v1, v2, y, idx)
+        reweight = self._reweight()
+        sel_pos, diff = self._select_v4(epoch, v1, v2, idx, select_pos_mode, sign=-1)
+        w = (diff[:, self._P:self._P + self._K] + 1.0) if reweight else None                # s_relation - t_relation + 1
+        if not self._z_ready:                                                               # :512-519, over the COMBINED scores
+            r1, r2, _ = _crd.crd_scores(self.memory_v1, self.memory_v2, v1.detach(), v2.detach(), idx, self._T)
+            self.params[2] = self._combine(r1, sel_pos, w).mean() * self.nLem
+            self.params[3] = self._combine(r2, sel_pos, w).mean() * self.nLem
+            print("normalization constant Z_v1 is set to {:.1f}".format(self.params[2].item()))
+            print("normalization constant Z_v2 is set to {:.1f}".format(self.params[3].item()))
+            self._z_ready = True
+        if torch.is_grad_enabled() and (v1.requires_grad or v2.requires_grad):
+            undo = _crd._UndoLog()
+            self._pending.add(undo)
+            o1, o2 = _crd._ScoresFn.apply(v1, v2, self, idx, undo)
+            o1, o2 = o1.squeeze(2), o2.squeeze(2)
+        else:
+            o1, o2, _ = _crd.crd_scores(self.memory_v1, self.memory_v2, v1, v2, idx, self._T, Z=self.params[2:4])
+        out_v1, out_v2 = self._combine(o1, sel_pos, w), self._combine(o2, sel_pos, w)
+        self._update(v1, v2, y)
+        return out_v1.contiguous(), out_v2.contiguous()
+
+
+class ContrastMemory_mono(ContrastMemory_v4):
+    """`MIA 2022/CL_utils/memory_new.py:565-698`: one-directional bank -- queries from the student (v2), keys from the
+    teacher bank (memory_v1); `forward(epoch, v1 = teacher, v2 = student, y, idx)` returns `(out_v2, memory_v1)`.
+    params = [P, K, T, Z_v2, momentum] (:586).  Positives by descending (t - s) with t = (bank-1 rows, v1), s = (bank-2
+    rows, v2) -- the relation kernel's own gap; every negative is kept, none re-weighted; 'mid' draws randint(50, 100)."""
+
+    _mid_rule = "randint_50_100"                                                            # :643
+
+    def __init__(self, inputSize, outputSize, P, K, T=0.07, momentum=0.5, select_pos_pairs=True, P2=10,
+                 select_neg_pairs=False, neg_reweight=True, K2=512):
+        super().__init__(inputSize, outputSize, P, K, T, momentum, select_pos_pairs, P2, select_neg_pairs, neg_reweight, K2)
+        del self.params
+        self.register_buffer('params', torch.tensor([P, K, T, -1, momentum]))
+        self._refresh_scalars()
+
+    def _refresh_scalars(self):
+        p = self.params.detach().cpu()
+        if p.numel() == 6:                      # called from the parents' constructors before the layout is replaced
+            return super()._refresh_scalars()
+        self._P, self._K = int(p[0].item()), int(p[1].item())
+        self._T = p[2].item()
+        self._momentum = p[4].item()
+        self._z_ready = bool(p[3].item() > 0)
+
+    def forward(self, epoch, v1, v2, y, idx=None, select_pos_mode="hard"):
+        v1, v2, y, idx = self._check_inputs_v3(v1, v2, y, idx)
+        sel_pos, _ = self._select_v4(epoch, v1, v2, idx, select_pos_mode, sign=+1)
+        if not self._z_ready:                                                               # :668-671
+            _, r2, _ = _crd.crd_scores(self.memory_v1, self.memory_v2, v1.detach(), v2.detach(), idx, self._T)
+            self.params[3] = self._combine(r2, sel_pos, None).mean() * self.nLem
+            print("normalization constant Z_v2 is set to {:.1f}".format(self.params[3].item()))
+            self._z_ready = True
+        zpair = torch.stack((torch.ones_like(self.params[3]), self.params[3]))             # side 1 is not used
+        if torch.is_grad_enabled() and v2.requires_grad:
+            undo = _crd._UndoLog()
+            self._pending.add(undo)
+            proxy = _MonoScores(self, zpair)
+            _, o2 = _crd._ScoresFn.apply(v1.detach(), v2, proxy, idx, undo)
+            o2 = o2.squeeze(2)
+        else:
+            _, o2, _ = _crd.crd_scores(self.memory_v1, self.memory_v2, v1, v2, idx, self._T, Z=zpair)
+        out_v2 = self._combine(o2, sel_pos, None)
+        self._update(v1, v2, y)
+        return out_v2.contiguous(), self.memory_v1
+
+
+class _MonoScores:
+    """What `_ScoresFn` reads from a memory module, with the [.., .., Z_v1, Z_v2] parameter layout it expects."""
+
+    def __init__(self, mem, zpair):
+        self.memory_v1, self.memory_v2, self._T = mem.memory_v1, mem.memory_v2, mem._T
+        self.params = torch.cat((zpair.new_zeros(2), zpair))
+
+
 class ContrastLoss_v2(nn.Module):
     """supervised contrastive loss (CRD_loss.py:212-252) -- stand-alone form for callers that hold out_v1/out_v2."""
 

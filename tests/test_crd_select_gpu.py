@@ -293,3 +293,99 @@ def test_sort_columns_kernel_matches_library_sort(pkg, B, P, K, K2):
     neg_t = sort_columns(tied, P, K, descending=False, first=K2, label0=P)
     assert torch.equal(pos_t, torch.sort(tied[:, :P], dim=1, descending=True, stable=True)[1])
     assert torch.equal(neg_t, P + torch.sort(tied[:, P:], dim=1, stable=True)[1][:, :K2])
+
+
+# ---- MIA 2022 variants: CRD_loss_v2.py CRDLoss (ContrastMemory_v4) and CRDLoss_v2 (ContrastMemory_mono) ----
+V4_CASES = ["crdv4_hard", "crdv4_mid_d128", "crdv4_plain", "crdv4_curriculum_KD"]
+MONO_CASES = ["crdmono_hard", "crdmono_mid_d128", "crdmono_random_KD"]
+
+
+def _opt_v4(c):
+    return types.SimpleNamespace(s_dim=c["s_dim"], t_dim=c["t_dim"], feat_dim=c["D"], nce_p=c["P"], nce_p2=c["P2"],
+                                 nce_k=c["K"], nce_k2=c["K"], nce_t=c["T"], nce_m=c["momentum"], select_pos_pairs=True,
+                                 select_neg_pairs="False", neg_reweight=c["neg_reweight"], sample_KD=c["sample_KD"],
+                                 select_pos_mode=c["mode"])
+
+
+@pytest.mark.parametrize("name", V4_CASES + MONO_CASES)
+def test_crd_loss_v2_modules_match_reference_golden(pkg, golden, name, capsys):
+    """Reference fixtures from oracle/make_golden_select_v4.py (unmodified `MIA 2022/CL_utils/CRD_loss_v2.py`)."""
+    g = golden(name)
+    c = g.cfg
+    mono = c["kind"] == "mono"
+    cls = pkg.crd_loss_v2.CRDLoss_v2 if mono else pkg.crd_loss_v2.CRDLoss
+    mod = cls(_opt_v4(c), c["n"])
+    mod.load_state_dict(g.state_dict("init."))
+    mod = mod.to(DEV)
+    captured = {}
+    mod.contrast.register_forward_hook(lambda m, i, o: captured.update(out=o))
+    before = pkg._cabi.launch_count()
+    for s in range(c["steps"]):
+        p = f"step{s}."
+        f_s = g.t(p + "f_s", DEV).requires_grad_(True)
+        f_t = g.t(p + "f_t", DEV).requires_grad_(True)
+        idx, cidx = g.t(p + "idx", DEV), g.t(p + "contrast_idx", DEV)
+        pre1 = mod.contrast.memory_v1.clone()
+        mod.zero_grad()
+        np.random.seed(int(g.np(p + "np_seed")))
+        loss = mod(float(g.np(p + "epoch")), f_s, f_t, idx, cidx)
+        assert loss.shape == (() if c["sample_KD"] == "False" else (c["B"],))
+        (loss * g.t(p + "G", DEV).reshape(loss.shape)).sum().backward()
+        if mono:
+            out_t, bank = captured["out"]
+            assert bank is mod.contrast.memory_v1 and mod.memory_t is bank            # CRD_loss_v2.py:100
+            assert f_t.grad is None
+        else:
+            out_s, out_t = captured["out"]
+            assert rel_err(out_s, g.t(p + "out_v1")) < TOL
+            assert rel_err(f_t.grad, g.t(p + "grad_f_t")) < TOL
+        assert out_t.shape == (c["B"], c["P2"] + c["K"], 1) and out_t.is_contiguous()
+        assert rel_err(out_t, g.t(p + "out_v2")) < TOL
+        assert rel_err(loss.reshape(-1), g.t(p + "loss")) < TOL
+        assert rel_err(f_s.grad, g.t(p + "grad_f_s")) < TOL
+        for k, v in mod.named_parameters():
+            assert rel_err(v.grad, g.t(p + "grad." + k)) < TOL, k
+        assert rel_err(mod.contrast.params, g.t(p + "params")) < TOL
+        assert rel_err(mod.contrast.memory_v1, g.t(p + "memory_v1")) < TOL
+        assert rel_err(mod.contrast.memory_v2, g.t(p + "memory_v2")) < TOL
+        changed = (mod.contrast.memory_v1 != pre1).any(dim=1).nonzero().flatten().cpu().tolist()
+        assert sorted(changed) == sorted(g.t(p + "idx").tolist())
+    assert pkg._cabi.launch_count() > before
+    assert "normalization constant Z_v2 is set to" in capsys.readouterr().out
+
+
+@pytest.mark.parametrize("name", ["crdv4_hard", "crdmono_hard"])
+def test_v4_and_mono_no_grad_path_and_state_dict_round_trip(pkg, so, golden, name):
+    """Evaluation (no autograd) goes through the scores kernel directly; a reloaded state dict keeps Z and the layout."""
+    g = golden(name)
+    c = g.cfg
+    mono = c["kind"] == "mono"
+    cls = pkg.ContrastMemory_mono if mono else pkg.ContrastMemory_v4
+    mem = cls(c["D"], c["n"], c["P"], c["K"], c["T"], c["momentum"], True, c["P2"], "False", c["neg_reweight"], c["K"])
+    sd = {k[len("contrast."):]: v for k, v in g.state_dict("init.").items() if k.startswith("contrast.")}
+    mem.load_state_dict(sd)
+    mem = mem.to(DEV)
+    gen = torch.Generator().manual_seed(5)
+    for step in range(2):
+        v1 = torch.nn.functional.normalize(torch.randn(c["B"], c["D"], generator=gen))
+        v2 = torch.nn.functional.normalize(torch.randn(c["B"], c["D"], generator=gen))
+        y = torch.randperm(c["n"], generator=gen)[:c["B"]]
+        idx = torch.randint(0, c["n"], (c["B"], c["P"] + c["K"]), generator=gen)
+        idx[:, 0] = y
+        ref = {k: v.clone() for k, v in sd.items()}
+        if mono:
+            want, _ = so.contrast_memory_mono_forward(ref["memory_v1"], ref["memory_v2"], ref["params"], 0.0, v1, v2, y, idx,
+                                                      P2=c["P2"], select_pos_mode="hard")
+        else:
+            _, want, _ = so.contrast_memory_v4_forward(ref["memory_v1"], ref["memory_v2"], ref["params"], 0.0, v1, v2, y,
+                                                       idx, P2=c["P2"], select_pos_mode="hard",
+                                                       neg_reweight=c["neg_reweight"])
+        with torch.no_grad():
+            got = mem(0.0, v1.to(DEV), v2.to(DEV), y.to(DEV), idx.to(DEV), "hard")
+        got = got[0] if mono else got[1]
+        assert rel_err(got, want) < TOL
+        assert rel_err(mem.params, ref["params"]) < TOL and rel_err(mem.memory_v1, ref["memory_v1"]) < TOL
+        sd = ref
+        clone = cls(c["D"], c["n"], c["P"], c["K"], c["T"], c["momentum"], True, c["P2"], "False", c["neg_reweight"], c["K"])
+        clone.load_state_dict(mem.state_dict())
+        assert clone._z_ready and clone._P == c["P"] and clone._K == c["K"]

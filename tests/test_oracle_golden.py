@@ -232,3 +232,50 @@ def test_polynomial_fusion_matches_reference(golden, name):
         run_sd = {k: v.clone() if ("running" in k or "num_batches" in k) else v for k, v in sd.items()}
         out = fo.polynomial_fusion_forward(run_sd, *ins, training=(tag == "train"), **kw)
         _check_fusion(g, sd, out, ins, tag)
+
+
+# ---- MIA 2022 variants (ContrastMemory_v4 / ContrastMemory_mono, CRD_loss_v2.py), oracle/crd_select_oracle.py ----
+V4_CASES = ["crdv4_hard", "crdv4_mid_d128", "crdv4_plain", "crdv4_curriculum_KD"]
+MONO_CASES = ["crdmono_hard", "crdmono_mid_d128", "crdmono_random_KD"]
+
+
+@pytest.mark.parametrize("name", V4_CASES + MONO_CASES)
+def test_crd_reweighted_and_mono_variants_match_reference(golden, name):
+    from oracle import crd_select_oracle as so
+    g = golden(name)
+    c = g.cfg
+    mono = c["kind"] == "mono"
+    sd = g.state_dict("init.")
+    for s in range(c["steps"]):
+        p = f"step{s}."
+        f_s = g.t(p + "f_s").requires_grad_(True)
+        f_t = g.t(p + "f_t").requires_grad_(True)
+        params = [k for k in sd if k.startswith("embed")]
+        for k in params:
+            sd[k] = sd[k].detach().requires_grad_(True)
+        pre1 = sd["contrast.memory_v1"].clone()
+        np.random.seed(int(g.np(p + "np_seed")))
+        args = (sd, float(g.np(p + "epoch")), f_s, f_t, g.t(p + "idx"), g.t(p + "contrast_idx"), c["n"])
+        if mono:
+            loss, out_t, sel_pos = so.crd_loss_mono(*args, P2=c["P2"], select_pos_mode=c["mode"], sample_KD=c["sample_KD"])
+        else:
+            loss, out_s, out_t, sel_pos = so.crd_loss_v4(*args, P2=c["P2"], select_pos_mode=c["mode"],
+                                                         neg_reweight=c["neg_reweight"], sample_KD=c["sample_KD"])
+            assert rel_err(out_s, g.t(p + "out_v1")) < FLOAT_TOL
+        (loss * g.t(p + "G").reshape(loss.shape)).sum().backward()
+        assert out_t.shape == (c["B"], c["P2"] + c["K"], 1)
+        assert rel_err(out_t, g.t(p + "out_v2")) < FLOAT_TOL
+        assert rel_err(loss.reshape(-1), g.t(p + "loss")) < FLOAT_TOL
+        assert rel_err(f_s.grad, g.t(p + "grad_f_s")) < FLOAT_TOL
+        if mono:
+            assert f_t.grad is None
+        else:
+            assert rel_err(f_t.grad, g.t(p + "grad_f_t")) < FLOAT_TOL
+        for k in params:
+            assert rel_err(sd[k].grad, g.t(p + "grad." + k)) < 1e-5, k
+        assert rel_err(sd["contrast.params"], g.t(p + "params")) < FLOAT_TOL
+        for bank in ("memory_v1", "memory_v2"):
+            assert rel_err(sd["contrast." + bank], g.t(p + bank)) < FLOAT_TOL
+        changed = (sd["contrast.memory_v1"] != pre1).any(dim=1).nonzero().flatten().tolist()
+        assert sorted(changed) == sorted(g.t(p + "idx").tolist())
+        assert (sel_pos[:, 0] == 0).all() and (sel_pos < c["P"]).all()
