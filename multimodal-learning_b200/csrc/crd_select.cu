@@ -244,6 +244,92 @@ __global__ void __launch_bounds__(kSortThreads) crd_sort_columns_kernel(const fl
     out[b * out_ld + i] = label0 + static_cast<int64_t>(static_cast<uint32_t>(sm_keys[i]));
 }
 
+// ---- register-blocked variant for 2^LOGN in [2048, 16384] columns ----
+// 16 keys per thread.  In "layout s" a thread owns the 16 indices that differ in bits [s, s+3]; the compare-exchange
+// stages on those four bits run in registers, and only a change of layout is a trip through shared memory
+// (sum over phases of ceil(phase / 4) ~ 30 trips for 16384 keys instead of 105 stage-by-stage passes).  Shared addresses are
+// padded by one key per 16 (idx + idx / 16): every layout's 64-bit accesses are bank-conflict free, and because the index
+// fields of thread and register are disjoint bits, a key's address is (thread base) + (compile-time offset).
+__device__ __forceinline__ constexpr int sort_layout(int phase, int bit) {      // s of the layout that stage (phase, bit) runs in
+  const int top = phase - 1 - ((phase - 1 - bit) / 4) * 4;                      // top bit of this stage's group of four
+  return top - 3 > 0 ? top - 3 : 0;
+}
+__device__ __forceinline__ constexpr int sort_index(int s, int t, int r) {
+  return ((t >> s) << (s + 4)) | (r << s) | (t & ((1 << s) - 1));
+}
+__device__ __forceinline__ constexpr int sort_phys(int idx) { return idx + (idx >> 4); }
+
+template <int LOGN>
+__global__ void __launch_bounds__(1 << (LOGN - 4)) crd_sort_columns_blocked_kernel(
+    const float* __restrict__ diff, int64_t ld, int64_t col0, int32_t n, int32_t descending, int32_t m, int64_t label0,
+    int64_t* __restrict__ out, int64_t out_ld) {
+  constexpr int N = 1 << LOGN, T = N >> 4;
+  extern __shared__ unsigned long long sm_keys[];
+  const int64_t b = blockIdx.x;
+  const int t = threadIdx.x;
+  const float* src = diff + b * ld + col0;
+  for (int i = t; i < N; i += T) {
+    unsigned long long key = ~0ull;                                   // padding sorts last
+    if (i < n) {
+      uint32_t u = __float_as_uint(src[i]);
+      u ^= (u >> 31) ? 0xFFFFFFFFu : 0x80000000u;
+      if (descending) u = ~u;
+      key = (static_cast<unsigned long long>(u) << 32) | static_cast<uint32_t>(i);
+    }
+    sm_keys[sort_phys(i)] = key;
+  }
+  __syncthreads();
+  unsigned long long v[16];
+#pragma unroll
+  for (int r = 0; r < 16; ++r) v[r] = sm_keys[sort_phys(sort_index(0, t, 0)) + sort_phys(sort_index(0, 0, r))];
+#pragma unroll
+  for (int phase = 1; phase <= LOGN; ++phase) {
+#pragma unroll
+    for (int bit = phase - 1; bit >= 0; --bit) {
+      const int s = sort_layout(phase, bit);
+      const int s_prev = bit == phase - 1 ? 0 : sort_layout(phase, bit + 1);
+      if (s != s_prev) {                                              // compile-time after unrolling
+        __syncthreads();                                              // everyone has read the previous layout
+#pragma unroll
+        for (int r = 0; r < 16; ++r) sm_keys[sort_phys(sort_index(s_prev, t, 0)) + sort_phys(sort_index(s_prev, 0, r))] = v[r];
+        __syncthreads();
+#pragma unroll
+        for (int r = 0; r < 16; ++r) v[r] = sm_keys[sort_phys(sort_index(s, t, 0)) + sort_phys(sort_index(s, 0, r))];
+      }
+      const int lb = bit - s;
+      // direction of the pair: bit `phase` of its index -- one of the register bits, or a thread bit, or (last phase) 0
+      const bool dir_in_regs = phase >= s && phase <= s + 3;
+      const bool up_t = phase >= LOGN ? true : ((t >> (phase - 4 > 0 ? phase - 4 : 0)) & 1) == 0;
+#pragma unroll
+      for (int r = 0; r < 16; ++r) {
+        if (r & (1 << lb)) continue;
+        const bool up = dir_in_regs ? ((r >> (phase - s)) & 1) == 0 : up_t;
+        const unsigned long long x = v[r], y = v[r | (1 << lb)];
+        const bool sw = (x > y) == up;
+        v[r] = sw ? y : x;
+        v[r | (1 << lb)] = sw ? x : y;
+      }
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int r = 0; r < 16; ++r) sm_keys[sort_phys(sort_index(0, t, 0)) + sort_phys(sort_index(0, 0, r))] = v[r];
+  __syncthreads();
+  for (int i = t; i < m; i += T) out[b * out_ld + i] = label0 + static_cast<int64_t>(static_cast<uint32_t>(sm_keys[sort_phys(i)]));
+}
+
+template <int LOGN>
+int launch_sort_blocked(const float* diff, int64_t B, int64_t ld, int64_t col0, int32_t n, int32_t descending, int32_t m,
+                        int64_t label0, int64_t* out, int64_t out_ld, cudaStream_t stream) {
+  constexpr size_t smem = ((static_cast<size_t>(1) << LOGN) + (static_cast<size_t>(1) << (LOGN - 4))) * sizeof(unsigned long long);
+  if (smem > 48 * 1024)
+    MML_CUDA(cudaFuncSetAttribute(crd_sort_columns_blocked_kernel<LOGN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  static_cast<int>(smem)));
+  crd_sort_columns_blocked_kernel<LOGN><<<static_cast<unsigned>(B), 1 << (LOGN - 4), smem, stream>>>(diff, ld, col0, n, descending,
+                                                                                                   m, label0, out, out_ld);
+  return check_launch("crd_sort_columns_blocked_kernel");
+}
+
 }  // namespace
 }  // namespace mml
 
@@ -257,12 +343,20 @@ extern "C" int mml_crd_sort_columns(const float* diff, int64_t B, int64_t ld, in
   MML_REQUIRE(n <= mml_crd_sort_columns_max(), MML_ERR_UNSUPPORTED, "crd_sort_columns: at most %d columns per anchor (got %d)",
               mml_crd_sort_columns_max(), n);
   if (B == 0 || m == 0) return MML_OK;
-  int32_t npow2 = 2;
-  while (npow2 < n) npow2 <<= 1;
+  int32_t npow2 = 2, logn = 1;
+  while (npow2 < n) { npow2 <<= 1; ++logn; }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  switch (logn) {
+    case 11: return mml::launch_sort_blocked<11>(diff, B, ld, col0, n, descending, m, label0, out, out_ld, st);
+    case 12: return mml::launch_sort_blocked<12>(diff, B, ld, col0, n, descending, m, label0, out, out_ld, st);
+    case 13: return mml::launch_sort_blocked<13>(diff, B, ld, col0, n, descending, m, label0, out, out_ld, st);
+    case 14: return mml::launch_sort_blocked<14>(diff, B, ld, col0, n, descending, m, label0, out, out_ld, st);
+    default: break;
+  }
   const size_t smem = static_cast<size_t>(npow2) * sizeof(unsigned long long);
   if (smem > 48 * 1024)
     MML_CUDA(cudaFuncSetAttribute(mml::crd_sort_columns_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-  mml::crd_sort_columns_kernel<<<static_cast<unsigned>(B), mml::kSortThreads, smem, static_cast<cudaStream_t>(stream)>>>(
+  mml::crd_sort_columns_kernel<<<static_cast<unsigned>(B), mml::kSortThreads, smem, st>>>(
       diff, ld, col0, n, npow2, descending, m, label0, out, out_ld);
   return mml::check_launch("crd_sort_columns_kernel");
 }

@@ -176,6 +176,8 @@ __global__ void __launch_bounds__(kThreadsTc, 1) kron_fwd_tc_kernel(const __grid
     int cur_src = -1, cur_col = -1, s_prev = -1;
     int s = 0;
     uint32_t ph = 0;
+    const int64_t row_words = b * a.dr.words_per_row;
+    KronDropCache dcache = {-1, 0u};
     for (int c0 = c_begin; c0 < c_end; c0 += kCps) {
       uint32_t r[kCps][kHalf];
 #pragma unroll
@@ -203,18 +205,15 @@ __global__ void __launch_bounds__(kThreadsTc, 1) kron_fwd_tc_kernel(const __grid
           }
         }
         float sc = sm_S[e0.x * kTileM + row] * sm_S[e0.y * kTileM + row];
-        if (kDropout) sc *= a.dr.scale;
+        uint32_t drop = 0u;
+        if (kDropout) {
+          sc *= a.dr.scale;
+          drop = kron_drop_bits16(a.dr, seed_lo, seed_hi, row_words, e1.y + ebase * e1.z, e1.z, dcache);
+        }
 #pragma unroll
         for (int u = 0; u < kHalf; ++u) {
           float x = sc * v[u];
-          if (kDropout) {
-            const int klog = e1.y + (ebase + u) * e1.z;
-            const int64_t cc = b * a.dr.pairs_per_row + (klog >> 1);
-            const uint32_t h = kron_hash(static_cast<uint32_t>(cc), static_cast<uint32_t>(static_cast<uint64_t>(cc) >> 32),
-                                         seed_lo, seed_hi);
-            const uint32_t r16 = (klog & 1) ? (h >> 16) : (h & 0xffffu);
-            x = (r16 >= a.dr.thresh) ? x : 0.f;
-          }
+          if (kDropout) x = (drop & (1u << u)) ? 0.f : x;
           r[i][u] = __float_as_uint(x) + 0x1000u;          // round-to-nearest onto the TF32 grid (hardware truncates)
         }
       }

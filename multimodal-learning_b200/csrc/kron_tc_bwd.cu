@@ -198,7 +198,8 @@ kron_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_dyT, const __grid_
     const int half = gt >> 7;
     const int ci = warp & 3, e = lane;
     const uint32_t lane_base = static_cast<uint32_t>(ci * 32) << 16;
-    int my_slot = 0, my_klog = 0;
+    int my_slot = 0, my_klog = 0, drop_w0 = 0, drop_src = 0, drop_bit = 0;
+    bool drop_coop = false;
 #pragma unroll
     for (int c = 0; c < 4; ++c)
       if (c == ci) my_slot = slot[c];
@@ -206,6 +207,10 @@ kron_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_dyT, const __grid_
       const bool cv = (c_first + ci) < a.nchunks;
       const int4 q1 = cv ? __ldg(a.table + 2 * (c_first + ci) + 1) : make_int4(0, 0, 1, 0);
       my_klog = q1.y + (e < q1.x ? e : 0) * q1.z;      // lanes past the chunk's length: any valid counter (never read)
+      drop_coop = q1.z == 1;                           // warp-uniform: the chunk's 32 columns are consecutive
+      drop_w0 = q1.y >> 5;
+      drop_src = ((my_klog >> 5) - drop_w0) << 4;
+      drop_bit = my_klog & 31;
     }
     // byte offsets inside a stage: scalar rows (broadcast reads) and this lane's swizzled row of its vector slot
     const uint32_t off_sp = kWgXBytes + (p_mode == 0 ? 0 : ci) * 128 + half * 64;
@@ -216,6 +221,22 @@ kron_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_dyT, const __grid_
     uint32_t ph = 0, xph = 0;
     for (int blk = blk_begin; blk < blk_end; ++blk) {
       const uint8_t* st = sm_x + static_cast<size_t>(k) * x_bytes;
+      // DROP flags of this lane's k for the 16 rows of its half (bit j = row j).  A stride-1 chunk spans at most two mask
+      // words per row: lane l hashes the word (row l & 15, w0 + (l >> 4)) and every lane collects its 16 by shuffle;
+      // the strided faces hash a word per (lane, row).
+      uint32_t drop = 0u;
+      if (kDropout) {
+        const int64_t bb = static_cast<int64_t>(blk) * kBlkB + half * kHalf;
+        if (drop_coop) {
+          const uint32_t mine = kron_drop_word(a.dr, seed_lo, seed_hi, (bb + (lane & 15)) * a.dr.words_per_row, drop_w0 + (lane >> 4));
+#pragma unroll
+          for (int j = 0; j < kHalf; ++j) drop |= ((__shfl_sync(0xffffffffu, mine, j + drop_src) >> drop_bit) & 1u) << j;
+        } else {
+#pragma unroll 4
+          for (int j = 0; j < kHalf; ++j)
+            drop |= ((kron_drop_word(a.dr, seed_lo, seed_hi, (bb + j) * a.dr.words_per_row, my_klog >> 5) >> drop_bit) & 1u) << j;
+        }
+      }
       mbar_wait(&bar_xfull[k], xph);
       uint32_t r[kHalf];
 #pragma unroll
@@ -225,16 +246,11 @@ kron_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_dyT, const __grid_
         const float4 x4 = *reinterpret_cast<const float4*>(st + off_x + (((half * 4 + u) ^ sw) << 4));
         float y0 = p4.x * q4.x * x4.x, y1 = p4.y * q4.y * x4.y, y2 = p4.z * q4.z * x4.z, y3 = p4.w * q4.w * x4.w;
         if (kDropout) {
-          const int64_t bb = static_cast<int64_t>(blk) * kBlkB + half * kHalf + u * 4;
-          float* yy[4] = {&y0, &y1, &y2, &y3};
-#pragma unroll
-          for (int w = 0; w < 4; ++w) {
-            const int64_t cc = (bb + w) * a.dr.pairs_per_row + (my_klog >> 1);
-            const uint32_t h = kron_hash(static_cast<uint32_t>(cc), static_cast<uint32_t>(static_cast<uint64_t>(cc) >> 32),
-                                         seed_lo, seed_hi);
-            const uint32_t r16 = (my_klog & 1) ? (h >> 16) : (h & 0xffffu);
-            *yy[w] = (r16 >= a.dr.thresh) ? *yy[w] * a.dr.scale : 0.f;
-          }
+          const uint32_t d4 = drop >> (u * 4);
+          y0 = (d4 & 1u) ? 0.f : y0 * a.dr.scale;
+          y1 = (d4 & 2u) ? 0.f : y1 * a.dr.scale;
+          y2 = (d4 & 4u) ? 0.f : y2 * a.dr.scale;
+          y3 = (d4 & 8u) ? 0.f : y3 * a.dr.scale;
         }
         r[u * 4 + 0] = __float_as_uint(y0);
         r[u * 4 + 1] = __float_as_uint(y1);
@@ -719,6 +735,8 @@ __global__ void __launch_bounds__(kDgThreads, 1) kron_dgrad_tc_kernel(const __gr
     int cur_src = -1, cur_col = -1, cur_len = 0, cur_row = -1;
     int run_p = 0;                 // fold_mode 2: scalar whose gradient is being accumulated in run_acc
     float run_acc = 0.f;
+    const int64_t row_words = b * a.dr.words_per_row;
+    KronDropCache dcache = {-1, 0u};
     // A vector segment is one contiguous run of chunks (build_chunks), so its gradient leaves the registers once per CTA:
     //   * factors that are not among the per-row scalars R (f2 when bilinear, f3 when trilinear): plain stores into the
     //     zero-initialised partial buffer -- no read-modify-write anywhere on the global side;
@@ -817,14 +835,8 @@ __global__ void __launch_bounds__(kDgThreads, 1) kron_dgrad_tc_kernel(const __gr
         float g[kHalf];                                                                                 \
         _Pragma("unroll") for (int e = 0; e < kHalf; ++e) g[e] = __uint_as_float(ACC[e]);               \
         if (kDropout) {                                                                                 \
-          _Pragma("unroll") for (int e = 0; e < kHalf; ++e) {                                           \
-            const int klog = KB[C] + (eb + e) * KS[C];                                                  \
-            const int64_t cc = b * a.dr.pairs_per_row + (klog >> 1);                                    \
-            const uint32_t h = kron_hash(static_cast<uint32_t>(cc),                                     \
-                                         static_cast<uint32_t>(static_cast<uint64_t>(cc) >> 32), seed_lo, seed_hi); \
-            const uint32_t r16 = (klog & 1) ? (h >> 16) : (h & 0xffffu);                                \
-            g[e] = (r16 >= a.dr.thresh) ? g[e] : 0.f;                                                   \
-          }                                                                                             \
+          const uint32_t drop = kron_drop_bits16(a.dr, seed_lo, seed_hi, row_words, KB[C] + eb * KS[C], KS[C], dcache); \
+          _Pragma("unroll") for (int e = 0; e < kHalf; ++e) g[e] = (drop & (1u << e)) ? 0.f : g[e];       \
         }                                                                                               \
         float ds0 = 0.f, ds1 = 0.f, ds2 = 0.f, ds3 = 0.f;                                               \
         _Pragma("unroll") for (int e = 0; e < kHalf; e += 4) {                                          \

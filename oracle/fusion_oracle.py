@@ -168,18 +168,9 @@ def kron_dropout_mask(seed: int, B: int, Kk: int, p: float) -> torch.Tensor:
     return kron_dropout_mask_at(seed, np.arange(B)[:, None], np.arange(Kk)[None, :], Kk, p)
 
 
-def kron_dropout_mask_at(seed: int, rows, cols, Kk: int, p: float) -> torch.Tensor:
-    """Same mask evaluated only at (rows, cols) -- numpy-broadcastable integer arrays of batch rows b and flattened
-    Kronecker columns k -- so that tests at BASELINE sizes need not build the whole [B, Kk] mask."""
+def _kron_hash(c, seed: int):
+    """csrc/kron_common.cuh kron_hash on a uint64 counter array -> uint32."""
     import numpy as np
-    rows = np.asarray(rows, dtype=np.uint64)
-    cols = np.asarray(cols, dtype=np.uint64)
-    shape = np.broadcast(rows, cols).shape
-    thresh = min(int(p * 65536.0 + 0.5), 65535) if p > 0 else 0
-    if thresh == 0:
-        return torch.ones(shape)
-    pairs = (Kk + 1) // 2
-    c = rows * np.uint64(pairs) + (cols >> np.uint64(1))
     lo = (c & np.uint64(0xFFFFFFFF)).astype(np.uint32)
     hi = (c >> np.uint64(32)).astype(np.uint32)
     s_lo, s_hi = np.uint32(seed & 0xFFFFFFFF), np.uint32((seed >> 32) & 0xFFFFFFFF)
@@ -192,6 +183,35 @@ def kron_dropout_mask_at(seed: int, rows, cols, Kk: int, p: float) -> torch.Tens
         h = h ^ (h >> np.uint32(15))
         h = h * np.uint32(0x846CA68B)
         h = h ^ (h >> np.uint32(16))
-    r16 = np.where((np.broadcast_to(cols, shape) & np.uint64(1)) != 0, h >> np.uint32(16), h & np.uint32(0xFFFF))
+    return h
+
+
+def kron_dropout_mask_at(seed: int, rows, cols, Kk: int, p: float) -> torch.Tensor:
+    """Same mask evaluated only at (rows, cols) -- numpy-broadcastable integer arrays of batch rows b and flattened
+    Kronecker columns k -- so that tests at BASELINE sizes need not build the whole [B, Kk] mask.
+
+    Definition (kron_common.cuh): element (b, k) is DROPPED iff bit (k & 31) of word (b, k >> 5) is set; a word is the
+    bit-sliced comparison U < thresh of 32 independent 16-bit uniforms, thresh = round(p * 65536): from the lowest set bit
+    i of thresh upwards, lt = (plane_i | lt) if bit i of thresh is set else (plane_i & lt), with
+    plane_i = hash(((b * ceil(Kk / 32) + (k >> 5)) << 4) + i, seed)."""
+    import numpy as np
+    rows = np.asarray(rows, dtype=np.uint64)
+    cols = np.asarray(cols, dtype=np.uint64)
+    shape = np.broadcast(rows, cols).shape
+    thresh = min(int(p * 65536.0 + 0.5), 65535) if p > 0 else 0
+    if thresh == 0:
+        return torch.ones(shape)
+    words = (Kk + 31) // 32
+    c0 = (rows * np.uint64(words) + (cols >> np.uint64(5))) << np.uint64(4)
+    lt = np.zeros(shape, dtype=np.uint32)
+    started = False
+    for i in range(16):
+        bit = (thresh >> i) & 1
+        if not started and not bit:
+            continue                     # planes below the lowest set bit cannot change the outcome
+        started = True
+        plane = _kron_hash(np.broadcast_to(c0 + np.uint64(i), shape), seed)
+        lt = (plane | lt) if bit else (plane & lt)
+    dropped = (lt >> (np.broadcast_to(cols, shape) & np.uint64(31)).astype(np.uint32)) & np.uint32(1)
     scale = np.float32(65536.0) / np.float32(65536 - thresh)
-    return torch.from_numpy(np.where(r16 >= thresh, scale, np.float32(0)).astype(np.float32))
+    return torch.from_numpy(np.where(dropped == 0, scale, np.float32(0)).astype(np.float32))

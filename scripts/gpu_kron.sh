@@ -3,6 +3,7 @@
 # Usage (under gpurun, from the repo root):  bash scripts/gpu_kron.sh <tag> [quick]
 set -u
 TAG=${1:-r2}
+MODE=${2:-all}
 OUT=gpurun_out
 mkdir -p $OUT
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > $OUT/${TAG}_smi.txt 2>&1
@@ -15,6 +16,7 @@ done
 for shp in 16384,128,128,256 8192,32,32,32,96; do
   timeout 300 python scripts/bench_kron.py --bwd --iters 20 --dropout 0.25 --only $shp 2>&1 | tail -1 | tee -a $OUT/${TAG}_kron.jsonl
 done
+[ "$MODE" = "quick" ] && exit 0
 echo "== ncu full K1/K2/K3"
 timeout 600 ncu --set full --clock-control none --import-source on -k 'regex:kron_(fwd|wgrad|dgrad)_tc_kernel' -s 3 -c 3 -f \
     -o $OUT/${TAG}_prof_kron python scripts/ncu_kron.py 16384,128,128,256 > $OUT/${TAG}_ncu_kron.log 2>&1

@@ -276,7 +276,7 @@ def test_module_train_mode_dropout_statistics(pkg):
     Wd, bd = W.to(DEV), bias.to(DEV)
     base = kron_linear(st, fd, Wd, bd)
     acc = torch.zeros_like(base)
-    n = 200
+    n = 600          # relative error of the mean ~ 0.7 / sqrt(n) for this problem: 0.029
     for s in range(n):
         acc += kron_linear(st, fd, Wd, bd, drop_p=0.25, training=True, seed=1000 + s)
     assert rel_err(acc / n, base) < 0.05
