@@ -27,20 +27,21 @@ inline KronShape make_kron_shape(int32_t d1, int32_t d2, int32_t d3) {
   return s;
 }
 
-// post_fusion_dropout on the never-stored operand: the DROP flag of (row b, logical column k) is bit (k & 31) of a 32-bit
-// word shared by the 32 columns [32w, 32w + 32) of that row.  A word is the bit-sliced comparison U < thresh of 32
-// independent 16-bit uniforms whose bit planes are counter-hash words: going from the lowest SET bit of thresh upwards,
-//   lt = thresh_i ? (plane_i | lt) : (plane_i & lt),     plane_i = hash((b * words_per_row + w) * 16 + i, seed)
+// post_fusion_dropout on the never-stored operand: the DROP flag of (row b, logical column k) is bit (b & 31) of a 32-bit
+// word shared by the 32 rows [32g, 32g + 32) of that column (g = b >> 5).  A word is the bit-sliced comparison U < thresh
+// of 32 independent 16-bit uniforms whose bit planes are counter-hash words: going from the lowest SET bit of thresh upwards,
+//   lt = thresh_i ? (plane_i | lt) : (plane_i & lt),     plane_i = hash(((g * Kk + k) << 4) + i, seed)
 // (planes below the lowest set bit cannot change the outcome and are never drawn), so a word costs 16 - ctz(thresh) hashes:
-// 2 for p = 0.25, 1 for p = 0.5.  K1/K2 (thread = row, 16 consecutive k) need about one new word per chunk, K3
-// (thread = k, 16 consecutive rows) shares the words of a warp's rows by shuffle.  Restated in numpy in
-// oracle/fusion_oracle.kron_dropout_mask.
+// 2 for p = 0.25, 1 for p = 0.5 -- against 16 for a hash per two elements.  K3 (thread = column, 16 consecutive rows) uses
+// half a word directly; in K1/K2 (thread = row, 16 columns) the 32 lanes of a warp are the 32 rows of one group: lane j
+// hashes the word of the warp's j-th column, the 16 words cross the warp through shared memory and every lane tests its
+// own bit.  Restated in numpy in oracle/fusion_oracle.kron_dropout_mask.
 struct KronDropout {
   uint32_t thresh;    // drop iff U16 < thresh;  thresh = round(p * 65536); 0 = no dropout
   float scale;        // 65536 / (65536 - thresh)
   uint32_t seed_lo, seed_hi;
-  int64_t words_per_row;   // ceil(Kk / 32)
-  int32_t plane0;          // ctz(thresh): the first bit plane that matters
+  int64_t Kk;         // columns per row: the counter of (group g, column k) is g * Kk + k
+  int32_t plane0;     // ctz(thresh): the first bit plane that matters
   const unsigned long long* seed_dev;   // optional DEVICE word xor-ed into the seed at run time: lets a captured CUDA graph
                                         // draw a fresh mask on every replay (the host `seed` is frozen into the graph)
 };
@@ -53,7 +54,7 @@ inline KronDropout make_kron_dropout(float p, uint64_t seed, int training, int32
   d.scale = 65536.0f / static_cast<float>(65536u - d.thresh);
   d.seed_lo = static_cast<uint32_t>(seed);
   d.seed_hi = static_cast<uint32_t>(seed >> 32);
-  d.words_per_row = (static_cast<int64_t>(Kk) + 31) / 32;
+  d.Kk = Kk;
   d.plane0 = 0;
   while (d.thresh != 0u && ((d.thresh >> d.plane0) & 1u) == 0u) ++d.plane0;
   d.seed_dev = (d.thresh != 0u) ? reinterpret_cast<const unsigned long long*>(seed_dev) : nullptr;
@@ -83,16 +84,14 @@ __device__ __forceinline__ void kron_seed(const KronDropout& dr, uint32_t& lo, u
   }
 }
 
-// DROP flags of row b (row_words = b * words_per_row), columns [32w, 32w + 32); seed_lo/hi from kron_seed()
-__device__ __forceinline__ uint32_t kron_drop_word(const KronDropout& dr, uint32_t seed_lo, uint32_t seed_hi, int64_t row_words,
-                                                   int32_t w) {
-  const uint64_t c0 = static_cast<uint64_t>(row_words + w) << 4;
+// DROP flags of column k for the 32 rows of group g (bit r = row 32 g + r); seed_lo/hi from kron_seed()
+__device__ __forceinline__ uint32_t kron_drop_word(const KronDropout& dr, uint32_t seed_lo, uint32_t seed_hi, int64_t g, int32_t k) {
+  const uint64_t c0 = static_cast<uint64_t>(g * dr.Kk + k) << 4;
   if (dr.plane0 >= 14) {           // one or two planes (p = 0.5, 0.25, 0.75): straight-line code, the two hashes independent
     const uint64_t ca = c0 + static_cast<uint32_t>(dr.plane0), cb = c0 + 15u;
     const uint32_t ra = kron_hash(static_cast<uint32_t>(ca), static_cast<uint32_t>(ca >> 32), seed_lo, seed_hi);
-    if (dr.plane0 == 15) return ra;
     const uint32_t rb = kron_hash(static_cast<uint32_t>(cb), static_cast<uint32_t>(cb >> 32), seed_lo, seed_hi);
-    return (dr.thresh & 0x8000u) ? (rb | ra) : (rb & ra);
+    return dr.plane0 == 15 ? ra : ((dr.thresh & 0x8000u) ? (rb | ra) : (rb & ra));
   }
   uint32_t lt = 0u;
   for (int i = dr.plane0; i < 16; ++i) {
@@ -106,43 +105,23 @@ __device__ __forceinline__ uint32_t kron_drop_word(const KronDropout& dr, uint32
 // multiplier of A[b,k] under dropout: 0 or scale (per-element form for the CUDA-core kernels; dr.seed_* already folded)
 __device__ __forceinline__ float kron_keep(const KronDropout& dr, int64_t b, int32_t k) {
   if (dr.thresh == 0u) return 1.0f;
-  const uint32_t word = kron_drop_word(dr, dr.seed_lo, dr.seed_hi, b * dr.words_per_row, k >> 5);
-  return ((word >> (k & 31)) & 1u) ? 0.0f : dr.scale;
+  const uint32_t word = kron_drop_word(dr, dr.seed_lo, dr.seed_hi, b >> 5, k);
+  return ((word >> (b & 31)) & 1u) ? 0.0f : dr.scale;
 }
 
-// The word a row computed last: consecutive chunks of a run cover consecutive k, so the upper word of one chunk is the
-// lower word of the next.
-struct KronDropCache {
-  int32_t w;
-  uint32_t v;
-};
-
-// DROP flags (bit u = element u) of the 16 columns k0 + u * kstride of one row.  kstride == 1 (every core chunk): one or
-// two words and a funnel shift; other strides (the faces that hold an appended 1): a word per element.  All branches are
-// uniform over threads that walk the same chunks.
-__device__ __forceinline__ uint32_t kron_drop_bits16(const KronDropout& dr, uint32_t seed_lo, uint32_t seed_hi, int64_t row_words,
-                                                     int32_t k0, int32_t kstride, KronDropCache& cache) {
-  if (kstride == 1) {
-    const int32_t w0 = k0 >> 5, sh = k0 & 31;
-    const uint32_t lo = (cache.w == w0) ? cache.v : kron_drop_word(dr, seed_lo, seed_hi, row_words, w0);
-    uint32_t hi = 0u;
-    if (sh > 16) {
-      hi = kron_drop_word(dr, seed_lo, seed_hi, row_words, w0 + 1);
-      cache.w = w0 + 1;
-      cache.v = hi;
-    } else {
-      cache.w = w0;
-      cache.v = lo;
-    }
-    return __funnelshift_r(lo, hi, sh) & 0xffffu;
+// K1 / K2: the 16 words of a warp's 16 columns k0 + j * kstride (j = 0..15) for the warp's 32 rows (group g), exchanged
+// through the warp's 16-word shared slot `xw`.  Lane l hashes column l & 15; afterwards every lane holds all 16 words and
+// tests bit `lane` of word j for its element j.  Must be called by all 32 lanes.
+__device__ __forceinline__ void kron_drop_words16(const KronDropout& dr, uint32_t seed_lo, uint32_t seed_hi, int64_t g, int32_t k0,
+                                                  int32_t kstride, uint32_t* xw, int lane, uint32_t (&w)[16]) {
+  const uint32_t mine = kron_drop_word(dr, seed_lo, seed_hi, g, k0 + (lane & 15) * kstride);
+  if (lane < 16) xw[lane] = mine;
+  __syncwarp();
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const uint4 t = *reinterpret_cast<const uint4*>(xw + 4 * q);
+    w[4 * q + 0] = t.x; w[4 * q + 1] = t.y; w[4 * q + 2] = t.z; w[4 * q + 3] = t.w;
   }
-  uint32_t bits = 0u;
-#pragma unroll 4
-  for (int u = 0; u < 16; ++u) {
-    const int32_t k = k0 + u * kstride;
-    bits |= ((kron_drop_word(dr, seed_lo, seed_hi, row_words, k >> 5) >> (k & 31)) & 1u) << u;
-  }
-  return bits;
 }
 
 __device__ __forceinline__ void kron_decode(const KronShape& s, int32_t k, int32_t& i, int32_t& j, int32_t& l) {

@@ -67,6 +67,8 @@ __global__ void __launch_bounds__(kThreadsTc, 1) kron_fwd_tc_kernel(const __grid
   uint64_t* bar_empty = bars + a.stages;        // [stages]  MMAs that read the stage have completed
   uint64_t* bar_acc = bars + 2 * a.stages;      // accumulator complete
   uint32_t* sm_tmem = reinterpret_cast<uint32_t*>(bars + 2 * a.stages + 1);
+  uint32_t* sm_drop = reinterpret_cast<uint32_t*>((reinterpret_cast<uintptr_t>(sm_tmem) + 4 + 15) & ~static_cast<uintptr_t>(15));
+                                                // [8 warps][2][16] dropout words crossing a warp (kron_drop_words16)
 
   const int warp = warp_idx_sync();
   const int lane = threadIdx.x & 31;
@@ -176,8 +178,8 @@ __global__ void __launch_bounds__(kThreadsTc, 1) kron_fwd_tc_kernel(const __grid
     int cur_src = -1, cur_col = -1, s_prev = -1;
     int s = 0;
     uint32_t ph = 0;
-    const int64_t row_words = b * a.dr.words_per_row;
-    KronDropCache dcache = {-1, 0u};
+    const int64_t row_group = (b0 >> 5) + (warp & 3);      // the warp's 32 rows are one group of the dropout mask
+    const uint32_t lane_bit = 1u << lane;
     for (int c0 = c_begin; c0 < c_end; c0 += kCps) {
       uint32_t r[kCps][kHalf];
 #pragma unroll
@@ -205,15 +207,15 @@ __global__ void __launch_bounds__(kThreadsTc, 1) kron_fwd_tc_kernel(const __grid
           }
         }
         float sc = sm_S[e0.x * kTileM + row] * sm_S[e0.y * kTileM + row];
-        uint32_t drop = 0u;
+        uint32_t dw[16];
         if (kDropout) {
           sc *= a.dr.scale;
-          drop = kron_drop_bits16(a.dr, seed_lo, seed_hi, row_words, e1.y + ebase * e1.z, e1.z, dcache);
+          kron_drop_words16(a.dr, seed_lo, seed_hi, row_group, e1.y + ebase * e1.z, e1.z, sm_drop + (warp * 2 + (c & 1)) * 16, lane, dw);
         }
 #pragma unroll
         for (int u = 0; u < kHalf; ++u) {
           float x = sc * v[u];
-          if (kDropout) x = (drop & (1u << u)) ? 0.f : x;
+          if (kDropout) x = (dw[u] & lane_bit) ? 0.f : x;
           r[i][u] = __float_as_uint(x) + 0x1000u;          // round-to-nearest onto the TF32 grid (hardware truncates)
         }
       }
@@ -368,7 +370,8 @@ TcPlan make_tc_plan(int64_t B, int32_t N, int32_t d1, int32_t d2, int32_t d3) {
   p.n_scal = 1 + d1 + (d3 > 0 ? d2 : 0);
   const size_t table_bytes = static_cast<size_t>(p.nchunks) * sizeof(Chunk);
   p.table_in_smem = table_bytes <= static_cast<size_t>(kMaxSmemTable) ? 1 : 0;
-  const size_t fixed = static_cast<size_t>(p.n_scal) * kTileM * sizeof(float) + (p.table_in_smem ? table_bytes : 0) + 256 + 1024;
+  const size_t fixed = static_cast<size_t>(p.n_scal) * kTileM * sizeof(float) + (p.table_in_smem ? table_bytes : 0) + 256 + 1024 +
+                       1024;      // barriers, alignment slack, dropout word exchange
   const size_t budget = 227 * 1024;
   p.cps = 1;      // two chunks per stage measured SLOWER on B200 (r2i: N=128 0.154 -> 0.194 ms; the wider TMEM ring costs the second CTA per SM)
   const size_t stage = static_cast<size_t>(p.Np) * 128 * p.cps;

@@ -198,8 +198,7 @@ kron_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_dyT, const __grid_
     const int half = gt >> 7;
     const int ci = warp & 3, e = lane;
     const uint32_t lane_base = static_cast<uint32_t>(ci * 32) << 16;
-    int my_slot = 0, my_klog = 0, drop_w0 = 0, drop_src = 0, drop_bit = 0;
-    bool drop_coop = false;
+    int my_slot = 0, my_klog = 0;
 #pragma unroll
     for (int c = 0; c < 4; ++c)
       if (c == ci) my_slot = slot[c];
@@ -207,10 +206,6 @@ kron_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_dyT, const __grid_
       const bool cv = (c_first + ci) < a.nchunks;
       const int4 q1 = cv ? __ldg(a.table + 2 * (c_first + ci) + 1) : make_int4(0, 0, 1, 0);
       my_klog = q1.y + (e < q1.x ? e : 0) * q1.z;      // lanes past the chunk's length: any valid counter (never read)
-      drop_coop = q1.z == 1;                           // warp-uniform: the chunk's 32 columns are consecutive
-      drop_w0 = q1.y >> 5;
-      drop_src = ((my_klog >> 5) - drop_w0) << 4;
-      drop_bit = my_klog & 31;
     }
     // byte offsets inside a stage: scalar rows (broadcast reads) and this lane's swizzled row of its vector slot
     const uint32_t off_sp = kWgXBytes + (p_mode == 0 ? 0 : ci) * 128 + half * 64;
@@ -221,22 +216,9 @@ kron_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_dyT, const __grid_
     uint32_t ph = 0, xph = 0;
     for (int blk = blk_begin; blk < blk_end; ++blk) {
       const uint8_t* st = sm_x + static_cast<size_t>(k) * x_bytes;
-      // DROP flags of this lane's k for the 16 rows of its half (bit j = row j).  A stride-1 chunk spans at most two mask
-      // words per row: lane l hashes the word (row l & 15, w0 + (l >> 4)) and every lane collects its 16 by shuffle;
-      // the strided faces hash a word per (lane, row).
+      // DROP flags of this lane's column for the 16 rows of its half: the block's 32 rows are one mask group
       uint32_t drop = 0u;
-      if (kDropout) {
-        const int64_t bb = static_cast<int64_t>(blk) * kBlkB + half * kHalf;
-        if (drop_coop) {
-          const uint32_t mine = kron_drop_word(a.dr, seed_lo, seed_hi, (bb + (lane & 15)) * a.dr.words_per_row, drop_w0 + (lane >> 4));
-#pragma unroll
-          for (int j = 0; j < kHalf; ++j) drop |= ((__shfl_sync(0xffffffffu, mine, j + drop_src) >> drop_bit) & 1u) << j;
-        } else {
-#pragma unroll 4
-          for (int j = 0; j < kHalf; ++j)
-            drop |= ((kron_drop_word(a.dr, seed_lo, seed_hi, (bb + j) * a.dr.words_per_row, my_klog >> 5) >> drop_bit) & 1u) << j;
-        }
-      }
+      if (kDropout) drop = kron_drop_word(a.dr, seed_lo, seed_hi, blk, my_klog) >> (half * kHalf);
       mbar_wait(&bar_xfull[k], xph);
       uint32_t r[kHalf];
 #pragma unroll
@@ -603,6 +585,8 @@ __global__ void __launch_bounds__(kDgThreads, 1) kron_dgrad_tc_kernel(const __gr
   uint64_t* bar_acc_full = bars + 2 * a.stages;  // [2] accumulator tile complete
   uint64_t* bar_acc_empty = bar_acc_full + 2;    // [2] epilogue has read the tile out of TMEM (8 warp arrivals)
   uint32_t* sm_tmem = reinterpret_cast<uint32_t*>(bar_acc_empty + 2);
+  uint32_t* sm_drop = reinterpret_cast<uint32_t*>((reinterpret_cast<uintptr_t>(sm_tmem) + 4 + 15) & ~static_cast<uintptr_t>(15));
+                                                 // [8 warps][2][16] dropout words crossing a warp (kron_drop_words16)
 
   const int warp = warp_idx_sync();
   const int lane = threadIdx.x & 31;
@@ -735,8 +719,8 @@ __global__ void __launch_bounds__(kDgThreads, 1) kron_dgrad_tc_kernel(const __gr
     int cur_src = -1, cur_col = -1, cur_len = 0, cur_row = -1;
     int run_p = 0;                 // fold_mode 2: scalar whose gradient is being accumulated in run_acc
     float run_acc = 0.f;
-    const int64_t row_words = b * a.dr.words_per_row;
-    KronDropCache dcache = {-1, 0u};
+    const int64_t row_group = (b0 >> 5) + (warp & 3);      // the warp's 32 rows are one group of the dropout mask
+    const uint32_t lane_bit = 1u << lane;
     // A vector segment is one contiguous run of chunks (build_chunks), so its gradient leaves the registers once per CTA:
     //   * factors that are not among the per-row scalars R (f2 when bilinear, f3 when trilinear): plain stores into the
     //     zero-initialised partial buffer -- no read-modify-write anywhere on the global side;
@@ -835,8 +819,10 @@ __global__ void __launch_bounds__(kDgThreads, 1) kron_dgrad_tc_kernel(const __gr
         float g[kHalf];                                                                                 \
         _Pragma("unroll") for (int e = 0; e < kHalf; ++e) g[e] = __uint_as_float(ACC[e]);               \
         if (kDropout) {                                                                                 \
-          const uint32_t drop = kron_drop_bits16(a.dr, seed_lo, seed_hi, row_words, KB[C] + eb * KS[C], KS[C], dcache); \
-          _Pragma("unroll") for (int e = 0; e < kHalf; ++e) g[e] = (drop & (1u << e)) ? 0.f : g[e];       \
+          uint32_t dw[16];                                                                              \
+          kron_drop_words16(a.dr, seed_lo, seed_hi, row_group, KB[C] + eb * KS[C], KS[C],               \
+                            sm_drop + (warp * 2 + ((C) & 1)) * 16, lane, dw);                           \
+          _Pragma("unroll") for (int e = 0; e < kHalf; ++e) g[e] = (dw[e] & lane_bit) ? 0.f : g[e];     \
         }                                                                                               \
         float ds0 = 0.f, ds1 = 0.f, ds2 = 0.f, ds3 = 0.f;                                               \
         _Pragma("unroll") for (int e = 0; e < kHalf; e += 4) {                                          \
@@ -985,7 +971,7 @@ DgPlan make_dg_plan(int64_t B, int32_t N, int32_t d1, int32_t d2, int32_t d3) {
   const size_t table_bytes = static_cast<size_t>(p.nchunks) * sizeof(Chunk);
   p.table_in_smem = table_bytes <= static_cast<size_t>(kMaxSmemTable) ? 1 : 0;
   const size_t fixed = static_cast<size_t>(p.n_scal) * kTileM * sizeof(float) + (kDgDsFloats + kDgScFloats) * sizeof(float) +
-                       (p.table_in_smem ? table_bytes : 0) + 256 + 1024;
+                       (p.table_in_smem ? table_bytes : 0) + 256 + 1024 + 1024;    // + the dropout word exchange
   int stages = fixed + 2 * stage <= 227 * 1024 ? static_cast<int>((227 * 1024 - fixed) / stage) : 0;
   if (stages > 6) stages = 6;
   p.stages = stages;

@@ -190,10 +190,10 @@ def kron_dropout_mask_at(seed: int, rows, cols, Kk: int, p: float) -> torch.Tens
     """Same mask evaluated only at (rows, cols) -- numpy-broadcastable integer arrays of batch rows b and flattened
     Kronecker columns k -- so that tests at BASELINE sizes need not build the whole [B, Kk] mask.
 
-    Definition (kron_common.cuh): element (b, k) is DROPPED iff bit (k & 31) of word (b, k >> 5) is set; a word is the
+    Definition (kron_common.cuh): element (b, k) is DROPPED iff bit (b & 31) of word (b >> 5, k) is set; a word is the
     bit-sliced comparison U < thresh of 32 independent 16-bit uniforms, thresh = round(p * 65536): from the lowest set bit
     i of thresh upwards, lt = (plane_i | lt) if bit i of thresh is set else (plane_i & lt), with
-    plane_i = hash(((b * ceil(Kk / 32) + (k >> 5)) << 4) + i, seed)."""
+    plane_i = hash((((b >> 5) * Kk + k) << 4) + i, seed)."""
     import numpy as np
     rows = np.asarray(rows, dtype=np.uint64)
     cols = np.asarray(cols, dtype=np.uint64)
@@ -201,8 +201,7 @@ def kron_dropout_mask_at(seed: int, rows, cols, Kk: int, p: float) -> torch.Tens
     thresh = min(int(p * 65536.0 + 0.5), 65535) if p > 0 else 0
     if thresh == 0:
         return torch.ones(shape)
-    words = (Kk + 31) // 32
-    c0 = (rows * np.uint64(words) + (cols >> np.uint64(5))) << np.uint64(4)
+    c0 = ((rows >> np.uint64(5)) * np.uint64(Kk) + cols) << np.uint64(4)
     lt = np.zeros(shape, dtype=np.uint32)
     started = False
     for i in range(16):
@@ -212,6 +211,6 @@ def kron_dropout_mask_at(seed: int, rows, cols, Kk: int, p: float) -> torch.Tens
         started = True
         plane = _kron_hash(np.broadcast_to(c0 + np.uint64(i), shape), seed)
         lt = (plane | lt) if bit else (plane & lt)
-    dropped = (lt >> (np.broadcast_to(cols, shape) & np.uint64(31)).astype(np.uint32)) & np.uint32(1)
+    dropped = (lt >> (np.broadcast_to(rows, shape) & np.uint64(31)).astype(np.uint32)) & np.uint32(1)
     scale = np.float32(65536.0) / np.float32(65536 - thresh)
     return torch.from_numpy(np.where(dropped == 0, scale, np.float32(0)).astype(np.float32))
