@@ -67,7 +67,7 @@ __global__ void __launch_bounds__(kThreadsTc, 1) kron_fwd_tc_kernel(const __grid
   uint64_t* bar_empty = bars + a.stages;        // [stages]  MMAs that read the stage have completed
   uint64_t* bar_acc = bars + 2 * a.stages;      // accumulator complete
   uint32_t* sm_tmem = reinterpret_cast<uint32_t*>(bars + 2 * a.stages + 1);
-  uint32_t* sm_drop = reinterpret_cast<uint32_t*>((reinterpret_cast<uintptr_t>(sm_tmem) + 4 + 15) & ~static_cast<uintptr_t>(15));
+  uint32_t* sm_drop = sm_tmem + 1 + ((16u - ((smem_u32(sm_tmem) + 4u) & 15u)) & 15u) / 4u;   // 16 B aligned; pointer arithmetic keeps it a shared pointer
                                                 // [8 warps][2][16] dropout words crossing a warp (kron_drop_words16)
 
   const int warp = warp_idx_sync();

@@ -585,7 +585,7 @@ __global__ void __launch_bounds__(kDgThreads, 1) kron_dgrad_tc_kernel(const __gr
   uint64_t* bar_acc_full = bars + 2 * a.stages;  // [2] accumulator tile complete
   uint64_t* bar_acc_empty = bar_acc_full + 2;    // [2] epilogue has read the tile out of TMEM (8 warp arrivals)
   uint32_t* sm_tmem = reinterpret_cast<uint32_t*>(bar_acc_empty + 2);
-  uint32_t* sm_drop = reinterpret_cast<uint32_t*>((reinterpret_cast<uintptr_t>(sm_tmem) + 4 + 15) & ~static_cast<uintptr_t>(15));
+  uint32_t* sm_drop = sm_tmem + 1 + ((16u - ((smem_u32(sm_tmem) + 4u) & 15u)) & 15u) / 4u;   // 16 B aligned; pointer arithmetic keeps it a shared pointer
                                                  // [8 warps][2][16] dropout words crossing a warp (kron_drop_words16)
 
   const int warp = warp_idx_sync();
