@@ -123,6 +123,22 @@ int32_t mml_crd_sort_columns_max(void);
 int     mml_crd_sort_columns(const float* diff, int64_t B, int64_t ld, int64_t col0, int32_t n, int32_t descending,
                              int32_t m, int64_t label0, int64_t* out, int64_t out_ld, void* stream);
 
+/* Full-bank KNN positives of the stage-2 criterion (MIA 2023/stage2_unimodal_student/CL_utils/CRD_criterion_v10.py:69-80,
+ * :108-116): for every anchor b, the num_pos rows j of `bank` with the largest
+ *     sim[b, j] = (row_labels[j] == anchor_labels[b]) ? cos(bank[anchor_rows[b]], bank[j]) : 0
+ * (the reference multiplies sklearn's cosine_similarity by a 0/1 class mask, so rows of other classes score exactly 0),
+ * in descending order: out_idx[B, P] (int64 row numbers), out_sim[B, P] (fp32).  Equal scores resolve to the smaller row.
+ * One TF32 tcgen05 pass over the bank keeps 8 candidates per (anchor, bank slice, column half); every candidate is then
+ * re-scored exactly in fp32, and anchors for which the TF32 error bound cannot prove the result are recomputed by an exact
+ * scan (flags_out[B], optional, reports them; exact_only != 0 forces that scan for every anchor).
+ * P <= mml_crd_knn_max_positives() (8).  The tcgen05 pass needs D % 32 == 0 and D <= 128; other D use the exact scan. */
+int32_t mml_crd_knn_max_positives(void);
+int64_t mml_crd_knn_workspace_bytes(int64_t n_rows, int64_t B, int32_t D);
+int     mml_crd_knn_positives(const float* bank, int64_t n_rows, int32_t D, const int32_t* row_labels,
+                              const int64_t* anchor_rows, const int64_t* anchor_labels, int64_t B, int32_t P,
+                              int32_t exact_only, int64_t* out_idx, float* out_sim, int32_t* flags_out,
+                              void* workspace, size_t workspace_bytes, void* stream);
+
 /* Scores only (ContrastMemory.forward :41-49 [+ :62-63 when Z != NULL]).
  *   Z == NULL : out = exp(dot/T) (raw);  Z != NULL: out = exp(dot/T)/Z.
  *   sums      float[4] or NULL: {0, 0, sum raw side1, sum raw side2}

@@ -12,11 +12,11 @@ The directory name has a hyphen (task-mandated); import it as `multimodal_learni
 from . import _cabi
 from ._cabi import check_device_errors, device_error_flags
 from .crd import (AliasMethod, ContrastLoss, ContrastMemory, CRDLoss, Embed, Normalize)
-from . import crd_loss_v2, crd_select
+from . import crd_knn, crd_loss_v2, crd_select
 from .crd_select import ContrastLoss_v2, ContrastMemory_mono, ContrastMemory_v2, ContrastMemory_v3, ContrastMemory_v4
 from .fusion import BilinearFusion, PolynomialFusion, TrilinearFusion_A, TrilinearFusion_B, init_max_weights, kron_linear
 from .graphed import GraphedTrainStep
 from .kd_loss import DistillKL
 from .sampler import InstanceSampler
 
-__all__ = ["BilinearFusion", "PolynomialFusion", "TrilinearFusion_A", "TrilinearFusion_B", "init_max_weights", "kron_linear", "AliasMethod", "ContrastLoss", "ContrastMemory", "CRDLoss", "Embed", "Normalize", "DistillKL", "GraphedTrainStep", "InstanceSampler", "crd_select", "crd_loss_v2", "check_device_errors", "device_error_flags", "ContrastLoss_v2", "ContrastMemory_v2", "ContrastMemory_v3", "ContrastMemory_v4", "ContrastMemory_mono", "_cabi"]
+__all__ = ["BilinearFusion", "PolynomialFusion", "TrilinearFusion_A", "TrilinearFusion_B", "init_max_weights", "kron_linear", "AliasMethod", "ContrastLoss", "ContrastMemory", "CRDLoss", "Embed", "Normalize", "DistillKL", "GraphedTrainStep", "InstanceSampler", "crd_select", "crd_loss_v2", "crd_knn", "check_device_errors", "device_error_flags", "ContrastLoss_v2", "ContrastMemory_v2", "ContrastMemory_v3", "ContrastMemory_v4", "ContrastMemory_mono", "_cabi"]

@@ -1,0 +1,257 @@
+"""Mirror of the reference's `MIA 2023/stage2_unimodal_student/CL_utils/CRD_criterion_v10.py` (what that tree's
+`train_test_path_multi_distill.py:24,258-262` runs): CRD whose positives are the query's nearest same-class neighbours in
+the FULL memory bank ("neighbors", :69-80 / :108-116) or class centres ("centers", :81-106).
+
+The reference computes `sklearn.cosine_similarity(anchor rows, whole bank)` on the CPU every step, multiplies by a class
+mask and sorts all n columns.  Here the neighbour search is `mml_crd_knn_positives` (one TF32 tcgen05 pass over the bank
+with a fused per-anchor candidate filter, exact fp32 re-score, csrc/crd_knn.cu); the scores, their autograd and the bank
+update are the kernels of `crd.ContrastMemory`.  Same class names, constructor arguments, forward signatures, state_dict
+and side effects."""
+from __future__ import annotations
+
+import math
+import weakref
+
+import numpy as np
+import torch
+from torch import nn
+
+from . import _cabi
+from . import crd as _crd
+from .crd import Normalize
+from .crd_select import Embed  # single Linear + L2 (CRD_criterion_v10.py:316-329)  # noqa: F401
+
+eps = 1e-7
+
+
+def knn_positives(bank, row_labels, anchor_rows, anchor_labels, num_pos, *, exact_only=False, return_flags=False):
+    """-> (neighbors int64 [B, P], similarity fp32 [B, P]) of CRD_criterion_v10.py:71-76 for one bank.
+    row_labels int32 [n] (class of every bank row), anchor_rows int64 [B] (the query's own row), anchor_labels int64 [B]."""
+    if not bank.is_cuda:
+        raise RuntimeError("knn_positives runs on CUDA tensors only")
+    n, D = bank.shape
+    B = anchor_rows.numel()
+    dev = bank.device
+    lib = _cabi.lib()
+    if num_pos > lib.mml_crd_knn_max_positives():
+        raise NotImplementedError(f"num_pos <= {lib.mml_crd_knn_max_positives()} (got {num_pos})")
+    nbytes = lib.mml_crd_knn_workspace_bytes(n, B, D)
+    if nbytes < 0:
+        raise RuntimeError(f"knn_positives: unsupported sizes n={n} B={B} D={D}")
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    out_idx = torch.empty((B, num_pos), dtype=torch.int64, device=dev)
+    out_sim = torch.empty((B, num_pos), dtype=torch.float32, device=dev)
+    flags = torch.empty(B, dtype=torch.int32, device=dev) if return_flags else None
+    _cabi.check(lib.mml_crd_knn_positives(
+        _cabi.dptr(bank, torch.float32), n, D, _cabi.dptr(row_labels, torch.int32), _cabi.dptr(anchor_rows, torch.int64),
+        _cabi.dptr(anchor_labels, torch.int64), B, int(num_pos), int(bool(exact_only)), _cabi.dptr(out_idx), _cabi.dptr(out_sim),
+        _cabi.dptr(flags), _cabi.dptr(ws), ws.numel(), _cabi.cur_stream(dev)), "mml_crd_knn_positives")
+    return (out_idx, out_sim, flags) if return_flags else (out_idx, out_sim)
+
+
+class _CenterBanks:
+    """What `_ScoresFn` reads from a memory module, over the two [n_classes * (num_pos-1), D] centre tables."""
+
+    def __init__(self, mem, c1, c2):
+        self.memory_v1, self.memory_v2, self._T, self.params = c1, c2, mem._T, mem.params
+
+
+class ContrastMemory(_crd.ContrastMemory):
+    """
+    memory buffer that supplies large amount of negative samples.
+    return out_v1, out_v2: [batch size, K+num_pos, 1]                                    (CRD_criterion_v10.py:22-177)
+    """
+
+    def __init__(self, inputSize, outputSize, train_class_idx, K, T=0.07, momentum=0.5):
+        nn.Module.__init__(self)
+        self.nLem = outputSize
+        self.unigrams = torch.ones(self.nLem)
+        self.K = K
+        self.class_idx = train_class_idx
+        self.all_sample_labels = torch.zeros(outputSize)                                  # :34-38
+        for c in range(len(self.class_idx)):
+            self.all_sample_labels[torch.as_tensor(np.asarray(self.class_idx[c]), dtype=torch.long)] = c
+        self.register_buffer('params', torch.tensor([K, T, -1, -1, momentum]))
+        stdv = 1. / math.sqrt(inputSize / 3)
+        self.register_buffer('memory_v1', torch.rand(outputSize, inputSize).mul_(2 * stdv).add_(-stdv))
+        self.register_buffer('memory_v2', torch.rand(outputSize, inputSize).mul_(2 * stdv).add_(-stdv))
+        self._refresh_scalars()
+        self._pending = weakref.WeakSet()
+        self._row_labels = None
+
+    def _apply(self, fn, *args, **kwargs):                  # no AliasMethod in this variant (idx is always supplied)
+        out = nn.Module._apply(self, fn, *args, **kwargs)
+        self._row_labels = None
+        return out
+
+    def _labels_on(self, device):
+        if self._row_labels is None or self._row_labels.device != device:
+            self._row_labels = self.all_sample_labels.to(device=device, dtype=torch.int32)
+        return self._row_labels
+
+    def _class_centers(self, bank, num_pos):
+        """:84-92 -- the mean of every class's rows (num_pos == 2).  k-means centres (num_pos > 2) are sklearn on the host
+        with a random initialisation in the reference and are not rebuilt here."""
+        if num_pos != 2:
+            raise NotImplementedError("pos_extra='centers' with num_pos > 2 runs sklearn KMeans on the host in the reference "
+                                      "(CRD_criterion_v10.py:89-92); only the class-mean case (num_pos == 2) is provided")
+        rows = [torch.as_tensor(np.asarray(c), dtype=torch.long, device=bank.device) for c in self.class_idx]
+        return torch.stack([bank.index_select(0, r).mean(0) for r in rows]).contiguous()
+
+    def forward(self, num_pos, pos_extra, v1, v2, batch_label, y, idx=None):
+        if not (v1.is_cuda and self.memory_v1.is_cuda):
+            raise RuntimeError("ContrastMemory runs on CUDA tensors only (move the module with .cuda()/.to(device))")
+        if idx is None:
+            raise RuntimeError("CRD_criterion_v10.ContrastMemory has no sampler: contrast idx must be supplied (:64)")
+        B = v1.size(0)
+        K = self._K
+        v1, v2, y = _crd._as_f32(v1), _crd._as_f32(v2), _crd._as_i64(y)
+        idx = _crd._as_i64(idx).contiguous().view(B, K + 1)           # same RuntimeError as :65 for a wrong width
+        batch_label = _crd._as_i64(batch_label)
+        dev = v1.device
+        if pos_extra == "neighbors":
+            labels = self._labels_on(dev)
+            anchors = idx[:, 0].contiguous()
+            nbr1, sim1 = knn_positives(self.memory_v1, labels, anchors, batch_label, num_pos)        # :69-76
+            nbr2, sim2 = knn_positives(self.memory_v2, labels, anchors, batch_label, num_pos)        # :108-113
+            # one gather pass over [neighbours of bank 1 | neighbours of bank 2 | the K negatives]; out_v2 reads bank 1 at
+            # columns [0, P) + negatives, out_v1 reads bank 2 at columns [P, 2P) + negatives (:77-79, :114-119)
+            P = num_pos
+            cols = torch.cat((nbr1, nbr2, idx[:, 1:]), 1).contiguous()
+            take1 = torch.cat((torch.arange(P, 2 * P, device=dev), torch.arange(2 * P, 2 * P + K, device=dev)))
+            take2 = torch.cat((torch.arange(0, P, device=dev), torch.arange(2 * P, 2 * P + K, device=dev)))
+            banks = self
+        elif pos_extra == "centers":
+            c1 = self._class_centers(self.memory_v1, num_pos)
+            c2 = self._class_centers(self.memory_v2, num_pos)
+            n_cls = len(self.class_idx)
+            if n_cls != 3:
+                raise RuntimeError("pos_extra='centers' hard-codes 3 classes in the reference (one_hot(..., num_classes=3), :60)")
+            others = torch.tensor([[c for c in range(n_cls) if c != k] for k in range(n_cls)], device=dev)    # :60-61
+            center_cols = torch.cat((batch_label.view(B, 1), others.index_select(0, batch_label)), 1).contiguous()
+            cols = idx
+            banks = None
+        else:
+            raise RuntimeError(f"pos_extra must be 'neighbors' or 'centers'; got {pos_extra!r}")   # reference: NameError later
+
+        def raw_scores(mem, columns):
+            r1, r2, _ = _crd.crd_scores(mem.memory_v1, mem.memory_v2, v1.detach(), v2.detach(), columns, self._T)
+            return r1, r2
+
+        if not self._z_ready:                                                                     # :121-129
+            r1, r2 = raw_scores(self, cols)
+            if pos_extra == "neighbors":
+                r1, r2 = r1.index_select(1, take1), r2.index_select(1, take2)
+            else:
+                q1, q2 = raw_scores(_CenterBanks(self, c1, c2), center_cols)
+                r1 = torch.cat((q1[:, :1], r1, q1[:, 1:]), 1)
+                r2 = torch.cat((q2[:, :1], r2, q2[:, 1:]), 1)
+            self.params[2] = r1.mean() * self.nLem
+            self.params[3] = r2.mean() * self.nLem
+            print("normalization constant Z_v1 is set to {:.1f}".format(self.params[2].item()))
+            print("normalization constant Z_v2 is set to {:.1f}".format(self.params[3].item()))
+            self._z_ready = True
+
+        def scores(mem, columns, track):
+            if torch.is_grad_enabled() and (v1.requires_grad or v2.requires_grad):
+                undo = _crd._UndoLog()
+                if track:
+                    self._pending.add(undo)
+                o1, o2 = _crd._ScoresFn.apply(v1, v2, mem, columns, undo)
+                return o1.squeeze(2), o2.squeeze(2)
+            o1, o2, _ = _crd.crd_scores(mem.memory_v1, mem.memory_v2, v1, v2, columns, self._T, Z=self.params[2:4])
+            return o1, o2
+
+        o1, o2 = scores(self, cols, True)
+        if pos_extra == "neighbors":
+            out_v1, out_v2 = o1.index_select(1, take1), o2.index_select(1, take2)
+        else:
+            q1, q2 = scores(_CenterBanks(self, c1, c2), center_cols, False)
+            out_v1 = torch.cat((q1[:, :1], o1, q1[:, 1:]), 1)      # [own centre | anchor + K negatives | other classes' centres]
+            out_v2 = torch.cat((q2[:, :1], o2, q2[:, 1:]), 1)
+        out_v1, out_v2 = out_v1.unsqueeze(2).contiguous(), out_v2.unsqueeze(2).contiguous()
+        self._update(v1, v2, y)                                                                   # :135-150
+        if pos_extra == "neighbors":
+            return out_v1, out_v2, sim1, sim2
+        return out_v1, out_v2
+
+
+class CRDLoss(nn.Module):
+    """CRD Loss function (CRD_criterion_v10.py:181-232).
+
+    Args: opt.s_dim / t_dim / feat_dim, opt.nce_k, opt.nce_t, opt.nce_m, opt.nce_p (number of positives),
+    opt.pos_extra ("neighbors" | "centers"); n_data = bank rows; train_class_idx = per class, the dataset indices in it."""
+
+    def __init__(self, opt, n_data, train_class_idx):
+        super(CRDLoss, self).__init__()
+        self.embed_s = Embed(opt.s_dim, opt.feat_dim)
+        self.embed_t = Embed(opt.t_dim, opt.feat_dim)
+        self.contrast = ContrastMemory(opt.feat_dim, n_data, train_class_idx, opt.nce_k, opt.nce_t, opt.nce_m)
+        self.num_pos = opt.nce_p
+        self.pos_extra = opt.pos_extra
+        if self.pos_extra == "neighbors":
+            self.criterion_t = ContrastLoss_v2(n_data)
+            self.criterion_s = ContrastLoss_v2(n_data)
+        else:
+            self.criterion_t = ContrastLoss(n_data)
+            self.criterion_s = ContrastLoss(n_data)
+
+    def forward(self, sample_weights, f_s, f_t, batch_label, idx, contrast_idx=None):
+        """-> (loss, per-sample loss [batch_size])"""
+        f_s = self.embed_s(f_s)
+        f_t = self.embed_t(f_t)
+        if self.pos_extra == "neighbors":
+            out_s, out_t, s_similarity, t_similarity = self.contrast(
+                self.num_pos, self.pos_extra, f_s, f_t, batch_label, idx, contrast_idx)
+            s_loss, s_sample_loss = self.criterion_s(sample_weights, out_s, self.num_pos, t_similarity)
+            t_loss, t_sample_loss = self.criterion_t(sample_weights, out_t, self.num_pos, s_similarity)
+        else:
+            out_s, out_t = self.contrast(self.num_pos, self.pos_extra, f_s, f_t, batch_label, idx, contrast_idx)
+            s_loss, s_sample_loss = self.criterion_s(sample_weights, out_s, self.num_pos)
+            t_loss, t_sample_loss = self.criterion_t(sample_weights, out_t, self.num_pos)
+        return s_loss + t_loss, s_sample_loss + t_sample_loss
+
+
+def _log_terms(x, P, n_data):
+    m = x.size(1) - P
+    Pn = 1 / float(n_data)
+    P_pos = x.narrow(1, 0, P)
+    log_D1 = (P_pos / (P_pos + (m * Pn + eps))).log()
+    P_neg = x.narrow(1, P, m)
+    log_D0 = ((m * Pn) / (P_neg + (m * Pn + eps))).log()
+    return log_D1, log_D0
+
+
+class ContrastLoss(nn.Module):
+    """class centres as the extra positives (CRD_criterion_v10.py:235-270)."""
+
+    def __init__(self, n_data):
+        super(ContrastLoss, self).__init__()
+        self.n_data = n_data
+
+    def forward(self, sample_weights, x, num_pos):
+        P = num_pos
+        bsz = x.shape[0]
+        log_D1, log_D0 = _log_terms(x, P, self.n_data)
+        if P > 1:
+            sample_loss = -(log_D1.squeeze() + log_D0.sum(1).view(bsz, 1)).sum(1) / P           # :259
+        else:
+            sample_loss = -(log_D1.squeeze() + log_D0.sum(1).squeeze())                         # :262
+        sample_loss = sample_weights.view(-1) * sample_loss
+        return sample_loss.sum(0) / bsz, sample_loss
+
+
+class ContrastLoss_v2(nn.Module):
+    """KNN neighbours as positives, weighted by their similarity to the query (CRD_criterion_v10.py:274-311)."""
+
+    def __init__(self, n_data):
+        super(ContrastLoss_v2, self).__init__()
+        self.n_data = n_data
+
+    def forward(self, sample_weights, x, num_pos, knn_similarity):
+        P = num_pos
+        bsz = x.shape[0]
+        log_D1, log_D0 = _log_terms(x, P, self.n_data)
+        sample_loss = -((log_D1.squeeze() + log_D0.sum(1).view(bsz, 1)) * knn_similarity).sum(1) / knn_similarity.sum(1)   # :300-301
+        sample_loss = sample_weights.view(-1) * sample_loss
+        return sample_loss.sum(0) / bsz, sample_loss

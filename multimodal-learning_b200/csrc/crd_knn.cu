@@ -1,0 +1,590 @@
+// Full-bank class-masked cosine KNN: the positives of the reference's CRD_criterion_v10 "neighbors" mode
+// (`MIA 2023/stage2_unimodal_student/CL_utils/CRD_criterion_v10.py:69-80, :108-116`):
+//     sim = class_mask[batch_label] * sklearn.cosine_similarity(memory[idx[:, 0]], memory)        # [B, n], on the CPU
+//     neighbors, neighbor_sim = top num_pos of sort(sim, descending)
+// for both banks, every step.  Here: one tcgen05 TF32 GEMM pass over the bank with a fused per-anchor candidate filter,
+// then an exact fp32 re-score of the few candidates -- nothing of size [B, n] is ever stored.
+//
+//   K12a knn_invnorm_kernel   1 / |row| of every bank row                                (one streaming pass, n*D*4 bytes)
+//   K12b knn_query_kernel     the anchors' own rows, L2-normalised -> qn [B, D] (+ label per anchor)
+//   K12c knn_gemm_kernel      S = qn . bank^T by 128 x 128 tiles: qn tile in TENSOR MEMORY (A operand, TF32 round-to-nearest),
+//                             bank rows by TMA (128B swizzle), accumulators double-buffered in TMEM; the epilogue warps
+//                             (thread = anchor, half of the tile's columns) scale by 1/|row|, apply the class mask
+//                             (other classes score exactly 0, as in the reference) and keep the 8 best (score, row) per
+//                             thread in registers.  Grid = anchor tiles x bank slices.
+//   K12d knn_merge_kernel     one warp per anchor: every candidate of every list is re-scored EXACTLY in fp32, the best P by
+//                             (score descending, row ascending) are written, and the anchor is FLAGGED when the TF32 error
+//                             bound cannot prove that no better row was filtered out (P-th exact score <= list minimum + eps)
+//   K12e knn_exact_kernel     flagged anchors only: exact fp32 scan of the whole bank (rare: needs > 8 - P rows of one list
+//                             within eps of the P-th neighbour)
+// Ties (equal scores) resolve to the smaller row index; the reference's CUDA sort leaves them undefined.
+#include "common.cuh"
+#include "kron_tc_common.cuh"
+
+namespace mml {
+namespace {
+
+using namespace tc;
+
+constexpr int kKnnC = 8;                   // candidates kept per (bank slice, column half) list = the largest supported P
+constexpr int kKnnTileN = 128;             // bank rows per accumulator tile
+constexpr int kKnnEpiWarps = 8;
+constexpr int kKnnEpiThreads = kKnnEpiWarps * 32;
+constexpr int kKnnThreads = kKnnEpiThreads + 64;      // + TMA warp + MMA warp
+constexpr uint32_t kKnnBoxBytes = kKnnTileN * 32 * 4; // [128 rows x 32 d] fp32 = 16 KB
+constexpr float kKnnEps = 2.0e-3f;         // >= |TF32 score - exact score|: A rounded (2^-11), B truncated (2^-10), |q| = |r| = 1
+
+__device__ __forceinline__ uint32_t ord_bits(float x) {          // unsigned order == float order
+  const uint32_t u = __float_as_uint(x);
+  return u ^ ((u >> 31) ? 0xFFFFFFFFu : 0x80000000u);
+}
+__device__ __forceinline__ float ord_value(uint32_t o) {
+  return __uint_as_float(o ^ ((o >> 31) ? 0x80000000u : 0xFFFFFFFFu));
+}
+// larger key = better candidate: higher score, then smaller row
+__device__ __forceinline__ unsigned long long knn_key(float s, uint32_t row) {
+  return (static_cast<unsigned long long>(ord_bits(s)) << 32) | (0xFFFFFFFFu - row);
+}
+
+__global__ void knn_invnorm_kernel(const float* __restrict__ bank, int64_t n, int32_t D, float* __restrict__ invn) {
+  // 8 lanes per row, 128-bit streaming loads (the gather kernels' row layout)
+  const int64_t row = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 3;
+  const int sub = threadIdx.x & 7;
+  float acc = 0.f;
+  if (row < n) {
+    const float* p = bank + row * D;
+    for (int c = sub * 4; c < D; c += 32) {
+      const float4 v = ldg_stream_f4(p + c);
+      acc += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+    }
+  }
+  acc += __shfl_xor_sync(kFullMask, acc, 1);
+  acc += __shfl_xor_sync(kFullMask, acc, 2);
+  acc += __shfl_xor_sync(kFullMask, acc, 4);
+  if (row < n && sub == 0) invn[row] = acc > 0.f ? 1.0f / sqrtf(acc) : 0.f;      // sklearn leaves all-zero rows at zero
+}
+
+__global__ void knn_query_kernel(const float* __restrict__ bank, int64_t n, int32_t D, const int64_t* __restrict__ rows,
+                                 const int64_t* __restrict__ labels_in, int64_t B, int64_t Bpad, float* __restrict__ qn,
+                                 int32_t* __restrict__ qlab, uint32_t* err) {
+  const int64_t b = blockIdx.x;
+  const int lane = threadIdx.x;              // 32 threads
+  if (b >= B) {                              // padding rows of the last anchor tile
+    for (int c = lane; c < D; c += 32) qn[b * D + c] = 0.f;
+    if (lane == 0) qlab[b] = -1;
+    return;
+  }
+  int64_t r = rows[b];
+  if (r < 0 || r >= n) {
+    if (lane == 0) flag_device_error(err, MML_DEVERR_CRD_INDEX);
+    r = r < 0 ? 0 : n - 1;
+  }
+  float acc = 0.f;
+  for (int c = lane; c < D; c += 32) {
+    const float v = bank[r * D + c];
+    acc += v * v;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(kFullMask, acc, o);
+  const float norm = sqrtf(acc);
+  for (int c = lane; c < D; c += 32) qn[b * D + c] = norm > 0.f ? bank[r * D + c] / norm : 0.f;
+  if (lane == 0) qlab[b] = static_cast<int32_t>(labels_in[b]);
+}
+
+struct KnnArgs {
+  const float* qn;          // [Bpad][D] normalised queries (zero rows past B)
+  const int32_t* qlab;      // [Bpad]
+  const float* invn;        // [n]
+  const int32_t* labels;    // [n]
+  unsigned long long* part; // [slices * 2][Bpad][kKnnC]
+  int64_t n, Bpad;
+  int32_t D, nbox;          // nbox = D / 32
+  int32_t tiles_total, tiles_per_slice;
+  int32_t stages, tmem_cols;
+  uint32_t idesc;
+};
+
+__global__ void __launch_bounds__(kKnnThreads, 1) knn_gemm_kernel(const __grid_constant__ CUtensorMap tmap_bank, const KnnArgs a) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* sm_b = smem;                                                              // [stages][16 KB]
+  float* sm_invn = reinterpret_cast<float*>(smem + static_cast<size_t>(a.stages) * kKnnBoxBytes);   // [2][128]
+  int32_t* sm_lab = reinterpret_cast<int32_t*>(sm_invn + 2 * kKnnTileN);                           // [2][128]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sm_lab + 2 * kKnnTileN);
+  uint64_t* bar_full = bars;                     // [stages] bank box landed
+  uint64_t* bar_empty = bars + a.stages;         // [stages] MMAs reading the box done
+  uint64_t* bar_acc_full = bars + 2 * a.stages;  // [2] accumulator tile complete
+  uint64_t* bar_acc_empty = bar_acc_full + 2;    // [2] epilogue has read the tile (8 warp arrivals)
+  uint32_t* sm_tmem = reinterpret_cast<uint32_t*>(bar_acc_empty + 2);
+
+  const int warp = warp_idx_sync();
+  const int lane = threadIdx.x & 31;
+  const int64_t b0 = static_cast<int64_t>(blockIdx.x) * kTileM;
+  const int t_begin = blockIdx.y * a.tiles_per_slice;
+  const int t_end = min(a.tiles_total, t_begin + a.tiles_per_slice);
+
+  if (warp == kKnnEpiWarps && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_bank)) : "memory");
+    for (int s = 0; s < a.stages; ++s) {
+      mbar_init(&bar_full[s], 1);
+      mbar_init(&bar_empty[s], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&bar_acc_full[i], 1);
+      mbar_init(&bar_acc_empty[i], kKnnEpiWarps);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == kKnnEpiWarps + 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(sm_tmem)), "r"(a.tmem_cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *sm_tmem;
+  const uint32_t tmem_acc = tmem_base;                   // 2 x 128 accumulator columns
+  const uint32_t tmem_a = tmem_base + 2 * kKnnTileN;     // query tile: D columns
+
+  // ---- A operand: this CTA's 128 normalised queries -> TMEM, once ----
+  if (warp < kKnnEpiWarps) {
+    const int row = threadIdx.x & (kTileM - 1);
+    const int half = threadIdx.x >> 7;
+    const uint32_t lane_base = static_cast<uint32_t>((warp & 3) * 32) << 16;
+    const float* q = a.qn + (b0 + row) * a.D;
+    const int c_lo = half == 0 ? 0 : (a.D / 32 + 1) / 2 * 32;     // warps 0-3: the first half of the 32-column groups
+    const int c_hi = half == 0 ? (a.D / 32 + 1) / 2 * 32 : a.D;
+    for (int c0 = c_lo; c0 < c_hi; c0 += 16) {
+      uint32_t r[16];
+#pragma unroll
+      for (int u = 0; u < 16; u += 4) {
+        const float4 v = *reinterpret_cast<const float4*>(q + c0 + u);
+        r[u + 0] = __float_as_uint(v.x) + 0x1000u;                 // round to nearest onto the TF32 grid
+        r[u + 1] = __float_as_uint(v.y) + 0x1000u;
+        r[u + 2] = __float_as_uint(v.z) + 0x1000u;
+        r[u + 3] = __float_as_uint(v.w) + 0x1000u;
+      }
+      tc_st_32x32b_x16(tmem_a + lane_base + c0, r);
+    }
+    tc_wait_st();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+
+  if (warp == kKnnEpiWarps) {
+    // ===== TMA producer: D/32 boxes of [128 bank rows x 32 d] per tile =====
+    int s = 0;
+    uint32_t ph = 0;
+    for (int t = t_begin; t < t_end; ++t)
+      for (int j = 0; j < a.nbox; ++j) {
+        mbar_wait(&bar_empty[s], ph ^ 1);
+        if (elect_one_sync()) {
+          mbar_arrive_expect_tx(&bar_full[s], kKnnBoxBytes);
+          tma_load_2d(sm_b + static_cast<size_t>(s) * kKnnBoxBytes, &tmap_bank, j * 32, t * kKnnTileN, &bar_full[s]);
+        }
+        __syncwarp();
+        if (++s == a.stages) { s = 0; ph ^= 1; }
+      }
+  } else if (warp == kKnnEpiWarps + 1) {
+    // ===== MMA issuer =====
+    int s = 0;
+    uint32_t ph = 0;
+    const uint32_t b_base = smem_u32(sm_b);
+    for (int t = t_begin; t < t_end; ++t) {
+      const int it = t - t_begin;
+      const int buf = it & 1;
+      mbar_wait(&bar_acc_empty[buf], ((it >> 1) & 1) ^ 1);            // epilogue has drained this accumulator
+      tc_fence_after();
+      for (int j = 0; j < a.nbox; ++j) {
+        mbar_wait(&bar_full[s], ph);
+        tc_fence_after();
+        if (elect_one_sync()) {
+          const uint64_t b_desc = umma_desc_k_sw128(b_base + static_cast<uint32_t>(s) * kKnnBoxBytes);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            tc_mma_tf32_ts(tmem_acc + buf * kKnnTileN, tmem_a + j * 32 + k * 8, b_desc + 2 * k, a.idesc, (j > 0 || k > 0) ? 1u : 0u);
+          tc_commit(&bar_empty[s]);
+          if (j + 1 == a.nbox) tc_commit(&bar_acc_full[buf]);
+        }
+        __syncwarp();
+        if (++s == a.stages) { s = 0; ph ^= 1; }
+      }
+    }
+  } else {
+    // ===== epilogue: thread = (anchor row, 64-column half of every tile) =====
+    const int row = threadIdx.x & (kTileM - 1);
+    const int half = threadIdx.x >> 7;
+    const int tid = threadIdx.x;                          // 0..255
+    const uint32_t lane_base = static_cast<uint32_t>((warp & 3) * 32) << 16;
+    const int32_t mylab = a.qlab[b0 + row];
+    unsigned long long keys[kKnnC];
+#pragma unroll
+    for (int i = 0; i < kKnnC; ++i) keys[i] = 0ull;       // 0 = empty slot: below every real key
+    float thr = -INFINITY;                                // score of the worst kept candidate (-inf while a slot is empty)
+
+    auto insert = [&](float s, uint32_t j) {
+      unsigned long long mk = keys[0];
+      int mp = 0;
+#pragma unroll
+      for (int i = 1; i < kKnnC; ++i)
+        if (keys[i] < mk) { mk = keys[i]; mp = i; }
+      const unsigned long long nk = knn_key(s, j);
+      if (nk > mk) {
+#pragma unroll
+        for (int i = 0; i < kKnnC; ++i)
+          if (i == mp) keys[i] = nk;
+        mk = keys[0];
+#pragma unroll
+        for (int i = 1; i < kKnnC; ++i) mk = keys[i] < mk ? keys[i] : mk;
+        thr = mk == 0ull ? -INFINITY : ord_value(static_cast<uint32_t>(mk >> 32));
+      }
+    };
+
+    // side data of a tile (1/|row| and label of its 128 bank rows): loaded one tile ahead, one value per thread
+    auto load_side = [&](int t) -> uint32_t {
+      if (t >= t_end) return 0u;
+      const int64_t j = static_cast<int64_t>(t) * kKnnTileN + (tid & 127);
+      if (tid < 128) return j < a.n ? __float_as_uint(__ldg(a.invn + j)) : 0u;
+      return j < a.n ? static_cast<uint32_t>(__ldg(a.labels + j)) : 0xFFFFFFFEu;       // -2: no such row
+    };
+    uint32_t side = load_side(t_begin);
+    for (int t = t_begin; t < t_end; ++t) {
+      const int it = t - t_begin;
+      const int buf = it & 1;
+      if (tid < 128) sm_invn[buf * kKnnTileN + tid] = __uint_as_float(side);
+      else sm_lab[buf * kKnnTileN + (tid - 128)] = static_cast<int32_t>(side);
+      side = load_side(t + 1);
+      asm volatile("bar.sync 1, %0;" ::"n"(kKnnEpiThreads) : "memory");
+      mbar_wait(&bar_acc_full[buf], (it >> 1) & 1);
+      tc_fence_after();
+      const uint32_t t_addr = tmem_acc + lane_base + buf * kKnnTileN + half * 64;
+      const float* iv = sm_invn + buf * kKnnTileN + half * 64;
+      const int32_t* lb = sm_lab + buf * kKnnTileN + half * 64;
+      const uint32_t j0 = static_cast<uint32_t>(t) * kKnnTileN + half * 64;
+      const bool whole = static_cast<int64_t>(t + 1) * kKnnTileN <= a.n;      // uniform: only the last tile can hold rows >= n
+      uint32_t accA[16], accB[16];
+#define MML_KNN_CHUNK(Q, ACC, NEXT_LD)                                                                   \
+      {                                                                                                  \
+        tc_wait_ld();                                                                                    \
+        NEXT_LD;                                                                                         \
+        float sc[16];                                                                                    \
+        float m = -INFINITY;                                                                             \
+        _Pragma("unroll") for (int u = 0; u < 16; u += 4) {                                              \
+          const float4 i4 = *reinterpret_cast<const float4*>(iv + (Q) * 16 + u);                         \
+          const int4 l4 = *reinterpret_cast<const int4*>(lb + (Q) * 16 + u);                             \
+          sc[u + 0] = l4.x == mylab ? __uint_as_float(ACC[u + 0]) * i4.x + 0.0f : 0.0f;                  \
+          sc[u + 1] = l4.y == mylab ? __uint_as_float(ACC[u + 1]) * i4.y + 0.0f : 0.0f;                  \
+          sc[u + 2] = l4.z == mylab ? __uint_as_float(ACC[u + 2]) * i4.z + 0.0f : 0.0f;                  \
+          sc[u + 3] = l4.w == mylab ? __uint_as_float(ACC[u + 3]) * i4.w + 0.0f : 0.0f;                  \
+          if (!whole) {                                                                                  \
+            sc[u + 0] = l4.x == -2 ? -INFINITY : sc[u + 0];                                              \
+            sc[u + 1] = l4.y == -2 ? -INFINITY : sc[u + 1];                                              \
+            sc[u + 2] = l4.z == -2 ? -INFINITY : sc[u + 2];                                              \
+            sc[u + 3] = l4.w == -2 ? -INFINITY : sc[u + 3];                                              \
+          }                                                                                              \
+          m = fmaxf(fmaxf(m, fmaxf(sc[u + 0], sc[u + 1])), fmaxf(sc[u + 2], sc[u + 3]));                 \
+        }                                                                                                \
+        if (m > thr) {                                                                                   \
+          _Pragma("unroll") for (int u = 0; u < 16; ++u)                                                 \
+            if (sc[u] > thr) insert(sc[u], j0 + (Q) * 16 + u);                                           \
+        }                                                                                                \
+      }
+      tc_ld_32x32b_x16(t_addr, accA);
+      MML_KNN_CHUNK(0, accA, tc_ld_32x32b_x16(t_addr + 16, accB))
+      MML_KNN_CHUNK(1, accB, tc_ld_32x32b_x16(t_addr + 32, accA))
+      MML_KNN_CHUNK(2, accA, tc_ld_32x32b_x16(t_addr + 48, accB))
+      MML_KNN_CHUNK(3, accB, (void)0)
+#undef MML_KNN_CHUNK
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bar_acc_empty[buf]);
+    }
+    unsigned long long* dst = a.part + ((static_cast<int64_t>(blockIdx.y) * 2 + half) * a.Bpad + (b0 + row)) * kKnnC;
+#pragma unroll
+    for (int i = 0; i < kKnnC; ++i) dst[i] = keys[i];
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == kKnnEpiWarps + 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(a.tmem_cols) : "memory");
+  }
+}
+
+// exact fp32 cosine of query (shared memory, normalised) and bank row j
+__device__ __forceinline__ float knn_exact_score(const float* __restrict__ bank, int32_t D, const float* sm_q, int64_t j, float invn) {
+  const float* p = bank + j * D;
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+  for (int c = 0; c < D; c += 4) {
+    const float4 v = *reinterpret_cast<const float4*>(p + c);
+    const float4 q = *reinterpret_cast<const float4*>(sm_q + c);
+    a0 = fmaf(v.x, q.x, a0);
+    a1 = fmaf(v.y, q.y, a1);
+    a2 = fmaf(v.z, q.z, a2);
+    a3 = fmaf(v.w, q.w, a3);
+  }
+  return ((a0 + a1) + (a2 + a3)) * invn + 0.0f;
+}
+
+constexpr int kMergeWarps = 4;
+
+__global__ void __launch_bounds__(kMergeWarps * 32) knn_merge_kernel(
+    const float* __restrict__ bank, int32_t D, const float* __restrict__ invn, const int32_t* __restrict__ labels,
+    const float* __restrict__ qn, const int32_t* __restrict__ qlab, const unsigned long long* __restrict__ part, int32_t nlists,
+    int64_t B, int64_t Bpad, int32_t P, int64_t* __restrict__ out_idx, float* __restrict__ out_sim, int32_t* __restrict__ flags,
+    int32_t force_flag) {
+  extern __shared__ float sm_qm[];                       // [kMergeWarps][D]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t b = static_cast<int64_t>(blockIdx.x) * kMergeWarps + warp;
+  if (b >= B) return;
+  float* sq = sm_qm + warp * D;
+  for (int c = lane; c < D; c += 32) sq[c] = qn[b * D + c];
+  __syncwarp();
+  const int32_t mylab = qlab[b];
+  unsigned long long best[kKnnC];                        // this lane's exact candidates, unsorted
+#pragma unroll
+  for (int i = 0; i < kKnnC; ++i) best[i] = 0ull;
+  float mmax = -INFINITY;                                // max over this lane's FULL lists of the list's worst TF32 score
+  for (int l = lane; l < nlists; l += 32) {
+    const unsigned long long* src = part + (static_cast<int64_t>(l) * Bpad + b) * kKnnC;
+    float lmin = INFINITY;
+    bool full = true;
+    for (int i = 0; i < kKnnC; ++i) {
+      const unsigned long long k = src[i];
+      if (k == 0ull) { full = false; continue; }
+      const float tf = ord_value(static_cast<uint32_t>(k >> 32));
+      if (tf == -INFINITY) { full = false; continue; }   // a row index past n (last tile): never a candidate
+      lmin = fminf(lmin, tf);
+      const uint32_t j = 0xFFFFFFFFu - static_cast<uint32_t>(k);
+      const float s = labels[j] == mylab ? knn_exact_score(bank, D, sq, j, invn[j]) : 0.0f;
+      const unsigned long long nk = knn_key(s, j);
+      unsigned long long mk = best[0];
+      int mp = 0;
+#pragma unroll
+      for (int q = 1; q < kKnnC; ++q)
+        if (best[q] < mk) { mk = best[q]; mp = q; }
+      if (nk > mk) {
+#pragma unroll
+        for (int q = 0; q < kKnnC; ++q)
+          if (q == mp) best[q] = nk;
+      }
+    }
+    if (full) mmax = fmaxf(mmax, lmin);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mmax = fmaxf(mmax, __shfl_xor_sync(kFullMask, mmax, o));
+  // P rounds of a warp-wide arg-max over the lanes' candidates
+  float vP = -INFINITY;
+  for (int p = 0; p < P; ++p) {
+    unsigned long long mine = best[0];
+#pragma unroll
+    for (int q = 1; q < kKnnC; ++q) mine = best[q] > mine ? best[q] : mine;
+    unsigned long long top = mine;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const unsigned long long other = __shfl_xor_sync(kFullMask, top, o);
+      top = other > top ? other : top;
+    }
+    if (mine == top && top != 0ull) {                    // keys are unique (the row is part of the key): one lane owns it
+#pragma unroll
+      for (int q = 0; q < kKnnC; ++q)
+        if (best[q] == top) best[q] = 0ull;
+    }
+    if (lane == 0) {
+      const bool have = top != 0ull;
+      vP = have ? ord_value(static_cast<uint32_t>(top >> 32)) : -INFINITY;
+      out_idx[b * P + p] = have ? static_cast<int64_t>(0xFFFFFFFFu - static_cast<uint32_t>(top)) : -1;
+      out_sim[b * P + p] = have ? vP : 0.f;
+    }
+  }
+  if (lane == 0) flags[b] = (force_flag || !(vP > mmax + kKnnEps)) ? 1 : 0;   // not provable: re-do this anchor exactly
+}
+
+constexpr int kExactWarps = 8;
+
+__global__ void __launch_bounds__(kExactWarps * 32) knn_exact_kernel(
+    const float* __restrict__ bank, int64_t n, int32_t D, const float* __restrict__ invn, const int32_t* __restrict__ labels,
+    const float* __restrict__ qn, const int32_t* __restrict__ qlab, const int32_t* __restrict__ flags, int32_t P,
+    int64_t* __restrict__ out_idx, float* __restrict__ out_sim) {
+  const int64_t b = blockIdx.x;
+  if (flags[b] == 0) return;
+  extern __shared__ float sm_qe[];                       // [D] query | [kExactWarps][kKnnC] keys
+  unsigned long long* sm_keys = reinterpret_cast<unsigned long long*>(sm_qe + ((D + 3) / 4 * 4));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int c = threadIdx.x; c < D; c += blockDim.x) sm_qe[c] = qn[b * D + c];
+  __syncthreads();
+  const int32_t mylab = qlab[b];
+  unsigned long long best[kKnnC];                        // identical in all lanes of a warp
+#pragma unroll
+  for (int i = 0; i < kKnnC; ++i) best[i] = 0ull;
+  unsigned long long worst = 0ull;
+  // lane l holds columns c = 4 l + 128 k of the query; a row is one coalesced pass of the warp
+  for (int64_t j = warp; j < n; j += kExactWarps) {
+    float s = 0.0f;
+    if (labels[j] == mylab) {
+      float acc = 0.f;
+      for (int c = lane * 4; c < D; c += 128) {
+        const float4 v = ldg_stream_f4(bank + j * D + c);
+        const float4 q = *reinterpret_cast<const float4*>(sm_qe + c);
+        acc = fmaf(v.x, q.x, acc);
+        acc = fmaf(v.y, q.y, acc);
+        acc = fmaf(v.z, q.z, acc);
+        acc = fmaf(v.w, q.w, acc);
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(kFullMask, acc, o);
+      s = acc * invn[j] + 0.0f;
+    }
+    const unsigned long long nk = knn_key(s, static_cast<uint32_t>(j));
+    if (nk > worst) {
+      unsigned long long mk = best[0];
+      int mp = 0;
+#pragma unroll
+      for (int q = 1; q < kKnnC; ++q)
+        if (best[q] < mk) { mk = best[q]; mp = q; }
+#pragma unroll
+      for (int q = 0; q < kKnnC; ++q)
+        if (q == mp) best[q] = nk;
+      worst = best[0];
+#pragma unroll
+      for (int q = 1; q < kKnnC; ++q) worst = best[q] < worst ? best[q] : worst;
+    }
+  }
+  if (lane == 0)
+    for (int i = 0; i < kKnnC; ++i) sm_keys[warp * kKnnC + i] = best[i];
+  __syncthreads();
+  if (warp == 0) {
+    for (int p = 0; p < P; ++p) {
+      unsigned long long top = 0ull;
+      for (int i = lane; i < kExactWarps * kKnnC; i += 32) top = sm_keys[i] > top ? sm_keys[i] : top;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long other = __shfl_xor_sync(kFullMask, top, o);
+        top = other > top ? other : top;
+      }
+      for (int i = lane; i < kExactWarps * kKnnC; i += 32)
+        if (sm_keys[i] == top) sm_keys[i] = 0ull;
+      __syncwarp();
+      if (lane == 0) {
+        const bool have = top != 0ull;
+        out_idx[b * P + p] = have ? static_cast<int64_t>(0xFFFFFFFFu - static_cast<uint32_t>(top)) : -1;
+        out_sim[b * P + p] = have ? ord_value(static_cast<uint32_t>(top >> 32)) : 0.f;
+      }
+    }
+  }
+}
+
+struct KnnPlan {
+  int64_t Bpad;
+  int32_t atiles, tiles_total, slices, tiles_per_slice, nlists, stages, tmem_cols;
+  size_t smem;
+  bool tensor;              // the tcgen05 pass applies (D a multiple of 32, at most 128; n < 2^31)
+  size_t off_invn, off_qn, off_qlab, off_part, off_flags, total;
+};
+
+KnnPlan make_knn_plan(int64_t n, int64_t B, int32_t D) {
+  KnnPlan p{};
+  p.atiles = static_cast<int32_t>((B + kTileM - 1) / kTileM);
+  if (p.atiles < 1) p.atiles = 1;
+  p.Bpad = static_cast<int64_t>(p.atiles) * kTileM;
+  p.tensor = (D % 32 == 0) && D >= 32 && D <= 128 && n < (static_cast<int64_t>(1) << 31) - kKnnTileN;
+  p.tiles_total = static_cast<int32_t>((n + kKnnTileN - 1) / kKnnTileN);
+  int32_t slices = 148 / p.atiles;
+  if (slices < 1) slices = 1;
+  if (slices > p.tiles_total) slices = p.tiles_total;
+  p.tiles_per_slice = (p.tiles_total + slices - 1) / slices;
+  p.slices = (p.tiles_total + p.tiles_per_slice - 1) / p.tiles_per_slice;
+  p.nlists = p.tensor ? p.slices * 2 : 0;
+  p.stages = 8;
+  p.tmem_cols = 512;
+  p.smem = static_cast<size_t>(p.stages) * kKnnBoxBytes + 2 * kKnnTileN * 8 + (2 * p.stages + 4) * 8 + 16 + 1024;
+  size_t off = 0;
+  auto take = [&](size_t bytes) { const size_t o = off; off += (bytes + 255) / 256 * 256; return o; };
+  p.off_invn = take(static_cast<size_t>(n) * sizeof(float));
+  p.off_qn = take(static_cast<size_t>(p.Bpad) * D * sizeof(float));
+  p.off_qlab = take(static_cast<size_t>(p.Bpad) * sizeof(int32_t));
+  p.off_part = take(static_cast<size_t>(p.nlists > 0 ? p.nlists : 1) * p.Bpad * kKnnC * sizeof(unsigned long long));
+  p.off_flags = take(static_cast<size_t>(p.Bpad) * sizeof(int32_t));
+  p.total = off;
+  return p;
+}
+
+}  // namespace
+}  // namespace mml
+
+using namespace mml;
+
+extern "C" int32_t mml_crd_knn_max_positives(void) { return kKnnC; }
+
+extern "C" int64_t mml_crd_knn_workspace_bytes(int64_t n, int64_t B, int32_t D) {
+  if (n < 1 || B < 0 || D < 4 || D % 4 != 0) return -1;
+  return static_cast<int64_t>(make_knn_plan(n, B, D).total);
+}
+
+extern "C" int mml_crd_knn_positives(const float* bank, int64_t n, int32_t D, const int32_t* row_labels, const int64_t* anchor_rows,
+                                     const int64_t* anchor_labels, int64_t B, int32_t P, int32_t exact_only, int64_t* out_idx,
+                                     float* out_sim, int32_t* flags_out, void* workspace, size_t workspace_bytes, void* stream) {
+  MML_REQUIRE(bank && row_labels && anchor_rows && anchor_labels && out_idx && out_sim && workspace, MML_ERR_INVALID_ARG,
+              "crd_knn_positives: null pointer");
+  MML_REQUIRE(n >= 1 && B >= 0 && D >= 4 && D % 4 == 0 && D <= 1024, MML_ERR_INVALID_ARG, "crd_knn_positives: bad sizes");
+  MML_REQUIRE(P >= 1 && P <= kKnnC && P <= n, MML_ERR_UNSUPPORTED, "crd_knn_positives: 1 <= num_pos <= %d supported (got %d)", kKnnC, P);
+  MML_REQUIRE(n < (static_cast<int64_t>(1) << 32) - 1, MML_ERR_UNSUPPORTED, "crd_knn_positives: at most 2^32 - 2 bank rows");
+  MML_REQUIRE(aligned16(bank) && aligned16(workspace), MML_ERR_INVALID_ARG, "crd_knn_positives: bank / workspace must be 16-byte aligned");
+  if (B == 0) return MML_OK;
+  const KnnPlan p = make_knn_plan(n, B, D);
+  MML_REQUIRE(workspace_bytes >= p.total, MML_ERR_INVALID_ARG, "crd_knn_positives: workspace too small (%zu < %zu)", workspace_bytes, p.total);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  uint8_t* ws = static_cast<uint8_t*>(workspace);
+  float* invn = reinterpret_cast<float*>(ws + p.off_invn);
+  float* qn = reinterpret_cast<float*>(ws + p.off_qn);
+  int32_t* qlab = reinterpret_cast<int32_t*>(ws + p.off_qlab);
+  unsigned long long* part = reinterpret_cast<unsigned long long*>(ws + p.off_part);
+  int32_t* flags = flags_out != nullptr ? flags_out : reinterpret_cast<int32_t*>(ws + p.off_flags);
+
+  {
+    const int64_t threads = n * 8;
+    knn_invnorm_kernel<<<static_cast<unsigned>((threads + 255) / 256), 256, 0, st>>>(bank, n, D, invn);
+    const int rc = check_launch("knn_invnorm_kernel");
+    if (rc != MML_OK) return rc;
+  }
+  {
+    knn_query_kernel<<<static_cast<unsigned>(p.Bpad), 32, 0, st>>>(bank, n, D, anchor_rows, anchor_labels, B, p.Bpad, qn, qlab,
+                                                                device_error_word());
+    const int rc = check_launch("knn_query_kernel");
+    if (rc != MML_OK) return rc;
+  }
+  const bool tensor = p.tensor && !exact_only;
+  if (tensor) {
+    CUtensorMap tmap;
+    const int rc0 = get_tensor_map_2d(bank, D, n, 32, kKnnTileN, true, &tmap);
+    if (rc0 != MML_OK) return rc0;
+    KnnArgs a{};
+    a.qn = qn; a.qlab = qlab; a.invn = invn; a.labels = row_labels; a.part = part;
+    a.n = n; a.Bpad = p.Bpad; a.D = D; a.nbox = D / 32;
+    a.tiles_total = p.tiles_total; a.tiles_per_slice = p.tiles_per_slice;
+    a.stages = p.stages; a.tmem_cols = p.tmem_cols;
+    a.idesc = make_idesc_tf32(kTileM, kKnnTileN);
+    MML_CUDA(cudaFuncSetAttribute(knn_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(p.smem)));
+    const dim3 grid(static_cast<unsigned>(p.atiles), static_cast<unsigned>(p.slices));
+    knn_gemm_kernel<<<grid, kKnnThreads, p.smem, st>>>(tmap, a);
+    const int rc = check_launch("knn_gemm_kernel");
+    if (rc != MML_OK) return rc;
+  }
+  {
+    const size_t smem = static_cast<size_t>(kMergeWarps) * D * sizeof(float);
+    knn_merge_kernel<<<static_cast<unsigned>((B + kMergeWarps - 1) / kMergeWarps), kMergeWarps * 32, smem, st>>>(
+        bank, D, invn, row_labels, qn, qlab, part, tensor ? p.nlists : 0, B, p.Bpad, P, out_idx, out_sim, flags, tensor ? 0 : 1);
+    const int rc = check_launch("knn_merge_kernel");
+    if (rc != MML_OK) return rc;
+  }
+  {
+    const size_t smem = static_cast<size_t>((D + 3) / 4 * 4) * sizeof(float) + kExactWarps * kKnnC * sizeof(unsigned long long);
+    knn_exact_kernel<<<static_cast<unsigned>(B), kExactWarps * 32, smem, st>>>(bank, n, D, invn, row_labels, qn, qlab, flags, P,
+                                                                            out_idx, out_sim);
+    const int rc = check_launch("knn_exact_kernel");
+    if (rc != MML_OK) return rc;
+  }
+  return MML_OK;
+}

@@ -279,3 +279,45 @@ def test_crd_reweighted_and_mono_variants_match_reference(golden, name):
         changed = (sd["contrast.memory_v1"] != pre1).any(dim=1).nonzero().flatten().tolist()
         assert sorted(changed) == sorted(g.t(p + "idx").tolist())
         assert (sel_pos[:, 0] == 0).all() and (sel_pos < c["P"]).all()
+
+
+# ---- MIA 2023 stage-2 criterion (CRD_criterion_v10.py: KNN / class-centre positives), oracle/crd_knn_oracle.py ----
+KNN_CASES = ["crdknn_p3_d16", "crdknn_p5_d128", "crdknn_p1_d32", "crdknn_centers_d32"]
+
+
+@pytest.mark.parametrize("name", KNN_CASES)
+def test_crd_knn_variant_matches_reference(golden, name):
+    from oracle import crd_knn_oracle as ko
+    g = golden(name)
+    c = g.cfg
+    sd = g.state_dict("init.")
+    cls = g.np("row_class")
+    class_idx = [np.nonzero(cls == k)[0] for k in range(3)]
+    for s in range(c["steps"]):
+        p = f"step{s}."
+        f_s = g.t(p + "f_s").requires_grad_(True)
+        f_t = g.t(p + "f_t").requires_grad_(True)
+        params = [k for k in sd if k.startswith("embed")]
+        for k in params:
+            sd[k] = sd[k].detach().requires_grad_(True)
+        pre1 = sd["contrast.memory_v1"].clone()
+        loss, sample_loss, res = ko.crd_loss_v10(sd, class_idx, c["P"], c["pos_extra"], g.t(p + "sample_weights"), f_s, f_t,
+                                                 g.t(p + "label"), g.t(p + "idx"), g.t(p + "contrast_idx"), c["n"])
+        loss.backward()
+        width = c["P"] + c["K"] if c["pos_extra"] == "neighbors" else 1 + (c["K"] + 1) + 2
+        assert res[0].shape == (c["B"], width, 1)
+        assert rel_err(res[0], g.t(p + "out_v1")) < FLOAT_TOL and rel_err(res[1], g.t(p + "out_v2")) < FLOAT_TOL
+        if c["pos_extra"] == "neighbors":
+            assert rel_err(res[2], g.t(p + "sim_v1")) < FLOAT_TOL and rel_err(res[3], g.t(p + "sim_v2")) < FLOAT_TOL
+            assert (res[2][:, 0] - 1).abs().max() < 1e-5          # the first neighbour is the query itself (:108)
+        assert rel_err(loss.reshape(-1), g.t(p + "loss")) < FLOAT_TOL
+        assert rel_err(sample_loss, g.t(p + "sample_loss")) < FLOAT_TOL
+        assert rel_err(f_s.grad, g.t(p + "grad_f_s")) < 1e-5
+        assert rel_err(f_t.grad, g.t(p + "grad_f_t")) < 1e-5
+        for k in params:
+            assert rel_err(sd[k].grad, g.t(p + "grad." + k)) < 1e-5, k
+        assert rel_err(sd["contrast.params"], g.t(p + "params")) < FLOAT_TOL
+        for bank in ("memory_v1", "memory_v2"):
+            assert rel_err(sd["contrast." + bank], g.t(p + bank)) < FLOAT_TOL
+        changed = (sd["contrast.memory_v1"] != pre1).any(dim=1).nonzero().flatten().tolist()
+        assert sorted(changed) == sorted(g.t(p + "idx").tolist())
