@@ -18,6 +18,8 @@ Beside it, in the same run and under the same clock sampler:
                   forward+backward; algorithmic flops / CUDA-event time vs the TF32 peak (= measured bf16 peak / 2)
   fused_step      fusion -> CRD, forward + backward + Adam, as ONE CUDA graph: config 4 (TrilinearFusion_A 33^3 -> 96,
                   batch 8192, K 16384, n 1M) and config 1 (BilinearFusion 32x32 -> 64, batch 64), with their CPU baselines
+  knn_positives   full-bank KNN positives of the stage-2 criterion (CRD_criterion_v10): 1024 anchors against 1M x 128 rows,
+                  TF32 tcgen05 pass + exact re-score, vs the TF32 peak; sklearn on the host cores beside it
   strong_scaling  BASELINE config 5 as stated: ONE problem (16M x 128 banks, global batch 8192) on N GPUs
   e2e*            `e2e` = host int64 contrast_idx uploaded every step (the reference's loader contract);
                   `e2e_device_idx` = contrast_idx drawn on the GPU inside the graph (InstanceSampler), `e2e_int32_idx`
@@ -449,6 +451,58 @@ def _time_ms(fn, iters, warmup):
     e1.record()
     torch.cuda.synchronize()
     return e0.elapsed_time(e1) / iters
+
+
+def knn_section(dev, peaks, cpu_anchors):
+    """N4 of SURVEY 8(f): the full-bank KNN positives of `MIA 2023/.../CRD_criterion_v10.py:69-80` at config 2's bank
+    (1M x 128, 1024 anchors, 5 positives, 3 classes): whole call (inverse norms, query prep, TF32 tcgen05 pass with the
+    candidate filter, exact re-score, exact scan of flagged anchors) timed with CUDA events; beside it the reference's
+    own way (sklearn cosine_similarity + sort on the host cores) on a slice of anchors."""
+    from multimodal_learning_b200 import crd_knn
+    n, D, B, P = 1_000_000, 128, 1024, 5
+    gen = torch.Generator(device=dev).manual_seed(0)
+    bank = torch.randn(n, D, device=dev, generator=gen)
+    bank = bank / bank.norm(dim=1, keepdim=True)
+    labels = torch.randint(0, 3, (n,), device=dev, generator=gen, dtype=torch.int32)
+    rows = torch.randperm(n, device=dev, generator=gen)[:B]
+    blab = labels[rows].long()
+    for _ in range(3):
+        idx, sim, flags = crd_knn.knn_positives(bank, labels, rows, blab, P, return_flags=True)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    iters = 20
+    e0.record()
+    for _ in range(iters):
+        crd_knn.knn_positives(bank, labels, rows, blab, P)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / iters
+    tf32_peak = float(peaks["bf16_tflops"]) / 2
+    flops = 2.0 * B * n * D
+    out = {"workload": f"KNN positives over the full bank: {n} x {D} rows, {B} anchors, num_pos {P}, 3 classes",
+           "ms": ms, "bound": "tensor", "achieved": flops / ms / 1e9, "peak": tf32_peak, "unit": "TFLOP/s",
+           "frac": flops / ms / 1e9 / tf32_peak, "flops": flops, "own_kernel_launches": 5,
+           "bank_passes_GBps": 2 * n * D * 4 / ms / 1e6, "flagged_anchors": int(flags.sum()),
+           "note": "time of the whole call (5 launches); flops = 2 B n D of the TF32 pass; the bank is read once for the "
+                   "inverse norms and once by TMA for the GEMM (L2-shared between the 8 anchor tiles)"}
+    if cpu_anchors > 0:
+        try:
+            from sklearn.metrics.pairwise import cosine_similarity
+            torch.set_num_threads(host_cores())
+            hb, hl = bank.cpu(), labels.cpu().long()
+            hr, hlab = rows[:cpu_anchors].cpu(), blab[:cpu_anchors].cpu()
+            t0 = time.perf_counter()
+            mask = (hl.view(1, -1) == hlab.view(-1, 1)).float()
+            sc = mask * torch.tensor(cosine_similarity(hb[hr].numpy(), hb.numpy()))
+            order = torch.sort(sc, descending=True, dim=-1)[1][:, :P]
+            dt = time.perf_counter() - t0
+            out["cpu_baseline"] = {"value": dt * 1e3 * B / cpu_anchors, "unit": "ms per call", "cores": torch.get_num_threads(),
+                                   "kind": "reference", "same_neighbours": bool(torch.equal(order.to(dev), idx[:cpu_anchors])),
+                                   "sample": f"{cpu_anchors} of {B} anchors: sklearn cosine_similarity against all {n} rows, class "
+                                             f"mask, torch.sort (CRD_criterion_v10.py:69-74), scaled x{B // cpu_anchors}"}
+        except Exception as e:                       # noqa: BLE001
+            out["cpu_baseline_error"] = f"{type(e).__name__}: {e}"
+    return out
 
 
 def kron_section(dev, peaks, peak_kind):
@@ -973,6 +1027,12 @@ def run_gpu_arm(args):
                     fused[which] = fused_step_section(dev, which, st, args.warmup)
             except Exception as e:                   # noqa: BLE001
                 errors["fused_step." + which] = f"{type(e).__name__}: {e}"
+    knn = None
+    if world == 1 and not args.no_kron:
+        try:
+            knn = knn_section(dev, peaks, 0 if args.no_cpu else 8)
+        except Exception as e:                       # noqa: BLE001
+            errors["knn_positives"] = f"{type(e).__name__}: {e}"
     if sampler:
         sampler.stop()
 
@@ -1028,6 +1088,8 @@ def run_gpu_arm(args):
                     errors["fused_step." + which + ".cpu_baseline"] = f"{type(e).__name__}: {e}"
     if fused:
         line["fused_step"] = fused
+    if knn is not None:
+        line["knn_positives"] = knn
     if errors:
         line["errors"] = errors
     print(json.dumps(line))

@@ -32,6 +32,7 @@ constexpr int kKnnEpiWarps = 8;
 constexpr int kKnnEpiThreads = kKnnEpiWarps * 32;
 constexpr int kKnnThreads = kKnnEpiThreads + 64;      // + TMA warp + MMA warp
 constexpr uint32_t kKnnBoxBytes = kKnnTileN * 32 * 4; // [128 rows x 32 d] fp32 = 16 KB
+constexpr int kKnnSample = 16;             // the sampling pass visits every 16th bank tile
 constexpr float kKnnEps = 2.0e-3f;         // >= |TF32 score - exact score|: A rounded (2^-11), B truncated (2^-10), |q| = |r| = 1
 
 __device__ __forceinline__ uint32_t ord_bits(float x) {          // unsigned order == float order
@@ -97,6 +98,9 @@ struct KnnArgs {
   const float* invn;        // [n]
   const int32_t* labels;    // [n]
   unsigned long long* part; // [slices * 2][Bpad][kKnnC]
+  float* rej;               // [slices * 2][Bpad] the final threshold of every list: rows it left out score <= this (TF32)
+  const float* thr_init;    // [Bpad] or NULL: a proven lower bound of the anchor's 8-th best score (from the sampling pass)
+  int32_t tile_mul;         // this pass visits bank tiles t * tile_mul (sampling pass: every 16th tile)
   int64_t n, Bpad;
   int32_t D, nbox;          // nbox = D / 32
   int32_t tiles_total, tiles_per_slice;
@@ -108,9 +112,8 @@ __global__ void __launch_bounds__(kKnnThreads, 1) knn_gemm_kernel(const __grid_c
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* sm_b = smem;                                                              // [stages][16 KB]
-  float* sm_invn = reinterpret_cast<float*>(smem + static_cast<size_t>(a.stages) * kKnnBoxBytes);   // [2][128]
-  int32_t* sm_lab = reinterpret_cast<int32_t*>(sm_invn + 2 * kKnnTileN);                           // [2][128]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sm_lab + 2 * kKnnTileN);
+  float* sm_side = reinterpret_cast<float*>(smem + static_cast<size_t>(a.stages) * kKnnBoxBytes);   // [8 warps][2][64 + 64]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sm_side + kKnnEpiWarps * 2 * 128);
   uint64_t* bar_full = bars;                     // [stages] bank box landed
   uint64_t* bar_empty = bars + a.stages;         // [stages] MMAs reading the box done
   uint64_t* bar_acc_full = bars + 2 * a.stages;  // [2] accumulator tile complete
@@ -182,7 +185,7 @@ __global__ void __launch_bounds__(kKnnThreads, 1) knn_gemm_kernel(const __grid_c
         mbar_wait(&bar_empty[s], ph ^ 1);
         if (elect_one_sync()) {
           mbar_arrive_expect_tx(&bar_full[s], kKnnBoxBytes);
-          tma_load_2d(sm_b + static_cast<size_t>(s) * kKnnBoxBytes, &tmap_bank, j * 32, t * kKnnTileN, &bar_full[s]);
+          tma_load_2d(sm_b + static_cast<size_t>(s) * kKnnBoxBytes, &tmap_bank, j * 32, t * a.tile_mul * kKnnTileN, &bar_full[s]);
         }
         __syncwarp();
         if (++s == a.stages) { s = 0; ph ^= 1; }
@@ -216,13 +219,14 @@ __global__ void __launch_bounds__(kKnnThreads, 1) knn_gemm_kernel(const __grid_c
     // ===== epilogue: thread = (anchor row, 64-column half of every tile) =====
     const int row = threadIdx.x & (kTileM - 1);
     const int half = threadIdx.x >> 7;
-    const int tid = threadIdx.x;                          // 0..255
     const uint32_t lane_base = static_cast<uint32_t>((warp & 3) * 32) << 16;
     const int32_t mylab = a.qlab[b0 + row];
     unsigned long long keys[kKnnC];
 #pragma unroll
     for (int i = 0; i < kKnnC; ++i) keys[i] = 0ull;       // 0 = empty slot: below every real key
-    float thr = -INFINITY;                                // score of the worst kept candidate (-inf while a slot is empty)
+    const float floor_thr = a.thr_init != nullptr ? a.thr_init[b0 + row] : -INFINITY;
+    float thr = floor_thr;                                // rows scoring <= thr are left out: the list's worst kept score once it
+                                                          // is full, never below the bound the sampling pass proved
 
     auto insert = [&](float s, uint32_t j) {
       unsigned long long mk = keys[0];
@@ -238,33 +242,43 @@ __global__ void __launch_bounds__(kKnnThreads, 1) knn_gemm_kernel(const __grid_c
         mk = keys[0];
 #pragma unroll
         for (int i = 1; i < kKnnC; ++i) mk = keys[i] < mk ? keys[i] : mk;
-        thr = mk == 0ull ? -INFINITY : ord_value(static_cast<uint32_t>(mk >> 32));
+        thr = mk == 0ull ? floor_thr : fmaxf(floor_thr, ord_value(static_cast<uint32_t>(mk >> 32)));
       }
     };
 
-    // side data of a tile (1/|row| and label of its 128 bank rows): loaded one tile ahead, one value per thread
-    auto load_side = [&](int t) -> uint32_t {
-      if (t >= t_end) return 0u;
-      const int64_t j = static_cast<int64_t>(t) * kKnnTileN + (tid & 127);
-      if (tid < 128) return j < a.n ? __float_as_uint(__ldg(a.invn + j)) : 0u;
-      return j < a.n ? static_cast<uint32_t>(__ldg(a.labels + j)) : 0xFFFFFFFEu;       // -2: no such row
+    // side data of a tile (1/|row| and label of the warp's 64 bank rows): loaded one tile ahead, two + two values per lane,
+    // into a warp-private shared slot -- no CTA-wide barrier couples the epilogue warps
+    float* my_side = sm_side + warp * (2 * 128);
+    auto load_side = [&](int t, uint32_t (&v)[4]) {
+      v[0] = v[1] = 0u;
+      v[2] = v[3] = 0xFFFFFFFEu;                            // -2: no such row
+      if (t >= t_end) return;
+      const int64_t j = static_cast<int64_t>(t) * a.tile_mul * kKnnTileN + half * 64 + lane;
+      if (j < a.n) { v[0] = __float_as_uint(__ldg(a.invn + j)); v[2] = static_cast<uint32_t>(__ldg(a.labels + j)); }
+      if (j + 32 < a.n) { v[1] = __float_as_uint(__ldg(a.invn + j + 32)); v[3] = static_cast<uint32_t>(__ldg(a.labels + j + 32)); }
     };
-    uint32_t side = load_side(t_begin);
+    uint32_t side[4];
+    load_side(t_begin, side);
     for (int t = t_begin; t < t_end; ++t) {
       const int it = t - t_begin;
       const int buf = it & 1;
-      if (tid < 128) sm_invn[buf * kKnnTileN + tid] = __uint_as_float(side);
-      else sm_lab[buf * kKnnTileN + (tid - 128)] = static_cast<int32_t>(side);
-      side = load_side(t + 1);
-      asm volatile("bar.sync 1, %0;" ::"n"(kKnnEpiThreads) : "memory");
+      {
+        uint32_t* d = reinterpret_cast<uint32_t*>(my_side + buf * 128);
+        d[lane] = side[0]; d[lane + 32] = side[1]; d[64 + lane] = side[2]; d[96 + lane] = side[3];
+      }
+      load_side(t + 1, side);
+      __syncwarp();
       mbar_wait(&bar_acc_full[buf], (it >> 1) & 1);
       tc_fence_after();
       const uint32_t t_addr = tmem_acc + lane_base + buf * kKnnTileN + half * 64;
-      const float* iv = sm_invn + buf * kKnnTileN + half * 64;
-      const int32_t* lb = sm_lab + buf * kKnnTileN + half * 64;
-      const uint32_t j0 = static_cast<uint32_t>(t) * kKnnTileN + half * 64;
-      const bool whole = static_cast<int64_t>(t + 1) * kKnnTileN <= a.n;      // uniform: only the last tile can hold rows >= n
+      const float* iv = my_side + buf * 128;
+      const int32_t* lb = reinterpret_cast<const int32_t*>(my_side + buf * 128 + 64);
+      const uint32_t j0 = static_cast<uint32_t>(t) * a.tile_mul * kKnnTileN + half * 64;
+      const bool whole = (static_cast<int64_t>(t) * a.tile_mul + 1) * kKnnTileN <= a.n;      // uniform: only the last tile can hold rows >= n
       uint32_t accA[16], accB[16];
+      // The filter's slow path (a score above the thread's threshold) exists ONCE per accumulator register set and walks
+      // the qualifying elements with a run-time loop: 64 inlined copies of the insertion made the kernel 13.6 K
+      // instructions and instruction-cache bound (r2y: 8.9 ms, "no_inst" stalls everywhere).
 #define MML_KNN_CHUNK(Q, ACC, NEXT_LD)                                                                   \
       {                                                                                                  \
         tc_wait_ld();                                                                                    \
@@ -287,15 +301,23 @@ __global__ void __launch_bounds__(kKnnThreads, 1) knn_gemm_kernel(const __grid_c
           m = fmaxf(fmaxf(m, fmaxf(sc[u + 0], sc[u + 1])), fmaxf(sc[u + 2], sc[u + 3]));                 \
         }                                                                                                \
         if (m > thr) {                                                                                   \
-          _Pragma("unroll") for (int u = 0; u < 16; ++u)                                                 \
-            if (sc[u] > thr) insert(sc[u], j0 + (Q) * 16 + u);                                           \
+          uint32_t cand = 0u;                                                                            \
+          _Pragma("unroll") for (int u = 0; u < 16; ++u) cand |= sc[u] > thr ? (1u << u) : 0u;           \
+          while (cand != 0u) {                                                                           \
+            const int u = __ffs(cand) - 1;                                                               \
+            cand &= cand - 1u;                                                                           \
+            float s = sc[0];                                                                             \
+            _Pragma("unroll") for (int w = 1; w < 16; ++w) s = u == w ? sc[w] : s;                       \
+            if (s > thr) insert(s, j0 + (Q) * 16 + u);                                                   \
+          }                                                                                              \
         }                                                                                                \
       }
       tc_ld_32x32b_x16(t_addr, accA);
-      MML_KNN_CHUNK(0, accA, tc_ld_32x32b_x16(t_addr + 16, accB))
-      MML_KNN_CHUNK(1, accB, tc_ld_32x32b_x16(t_addr + 32, accA))
-      MML_KNN_CHUNK(2, accA, tc_ld_32x32b_x16(t_addr + 48, accB))
-      MML_KNN_CHUNK(3, accB, (void)0)
+#pragma unroll 1
+      for (int q2 = 0; q2 < 2; ++q2) {
+        MML_KNN_CHUNK(2 * q2, accA, tc_ld_32x32b_x16(t_addr + (2 * q2 + 1) * 16, accB))
+        MML_KNN_CHUNK(2 * q2 + 1, accB, if (q2 == 0) tc_ld_32x32b_x16(t_addr + 32, accA))
+      }
 #undef MML_KNN_CHUNK
       tc_fence_before();
       __syncwarp();
@@ -304,6 +326,7 @@ __global__ void __launch_bounds__(kKnnThreads, 1) knn_gemm_kernel(const __grid_c
     unsigned long long* dst = a.part + ((static_cast<int64_t>(blockIdx.y) * 2 + half) * a.Bpad + (b0 + row)) * kKnnC;
 #pragma unroll
     for (int i = 0; i < kKnnC; ++i) dst[i] = keys[i];
+    a.rej[(static_cast<int64_t>(blockIdx.y) * 2 + half) * a.Bpad + (b0 + row)] = thr;
     tc_fence_before();
   }
   __syncthreads();
@@ -328,12 +351,49 @@ __device__ __forceinline__ float knn_exact_score(const float* __restrict__ bank,
   return ((a0 + a1) + (a2 + a3)) * invn + 0.0f;
 }
 
+// Sampling pass -> per-anchor floor of the full pass.  The 8-th best TF32 score among every 16th bank tile is a lower bound of
+// the 8-th best over the whole bank, so a row scoring below (bound - 3 eps) in TF32 cannot be among the anchor's 8 best in
+// exact arithmetic.  Starting every list of the full pass at that floor makes the filter's slow path rare from the first
+// tile on (without it each of the ~36 short lists of an anchor climbs from -inf: r2z, 40 % of the warp-chunks took it).
+__global__ void knn_threshold_kernel(const unsigned long long* __restrict__ part, int32_t nlists, int64_t B, int64_t Bpad,
+                                     float* __restrict__ thr_init) {
+  const int64_t b = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (b >= Bpad) return;
+  if (b >= B) { thr_init[b] = -INFINITY; return; }
+  uint32_t best[kKnnC];                                   // ordered score bits, unsorted; 0 = empty
+#pragma unroll
+  for (int i = 0; i < kKnnC; ++i) best[i] = 0u;
+  for (int l = 0; l < nlists; ++l) {
+    const unsigned long long* src = part + (static_cast<int64_t>(l) * Bpad + b) * kKnnC;
+    for (int i = 0; i < kKnnC; ++i) {
+      const unsigned long long k = src[i];
+      if (k == 0ull) continue;
+      const uint32_t o = static_cast<uint32_t>(k >> 32);
+      uint32_t mk = best[0];
+      int mp = 0;
+#pragma unroll
+      for (int q = 1; q < kKnnC; ++q)
+        if (best[q] < mk) { mk = best[q]; mp = q; }
+      if (o > mk) {
+#pragma unroll
+        for (int q = 0; q < kKnnC; ++q)
+          if (q == mp) best[q] = o;
+      }
+    }
+  }
+  uint32_t mk = best[0];
+#pragma unroll
+  for (int q = 1; q < kKnnC; ++q) mk = best[q] < mk ? best[q] : mk;
+  const float v = mk == 0u ? -INFINITY : ord_value(mk);
+  thr_init[b] = (v == -INFINITY || !(v == v)) ? -INFINITY : v - 3.0f * kKnnEps;
+}
+
 constexpr int kMergeWarps = 4;
 
 __global__ void __launch_bounds__(kMergeWarps * 32) knn_merge_kernel(
     const float* __restrict__ bank, int32_t D, const float* __restrict__ invn, const int32_t* __restrict__ labels,
-    const float* __restrict__ qn, const int32_t* __restrict__ qlab, const unsigned long long* __restrict__ part, int32_t nlists,
-    int64_t B, int64_t Bpad, int32_t P, int64_t* __restrict__ out_idx, float* __restrict__ out_sim, int32_t* __restrict__ flags,
+    const float* __restrict__ qn, const int32_t* __restrict__ qlab, const unsigned long long* __restrict__ part,
+    const float* __restrict__ rej, int32_t nlists, int64_t B, int64_t Bpad, int32_t P, int64_t* __restrict__ out_idx, float* __restrict__ out_sim, int32_t* __restrict__ flags,
     int32_t force_flag) {
   extern __shared__ float sm_qm[];                       // [kMergeWarps][D]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -346,17 +406,13 @@ __global__ void __launch_bounds__(kMergeWarps * 32) knn_merge_kernel(
   unsigned long long best[kKnnC];                        // this lane's exact candidates, unsorted
 #pragma unroll
   for (int i = 0; i < kKnnC; ++i) best[i] = 0ull;
-  float mmax = -INFINITY;                                // max over this lane's FULL lists of the list's worst TF32 score
+  float mmax = -INFINITY;                                // max over this lane's lists of the list's final threshold
   for (int l = lane; l < nlists; l += 32) {
     const unsigned long long* src = part + (static_cast<int64_t>(l) * Bpad + b) * kKnnC;
-    float lmin = INFINITY;
-    bool full = true;
+    mmax = fmaxf(mmax, rej[static_cast<int64_t>(l) * Bpad + b]);      // rows this list left out score <= this (TF32)
     for (int i = 0; i < kKnnC; ++i) {
       const unsigned long long k = src[i];
-      if (k == 0ull) { full = false; continue; }
-      const float tf = ord_value(static_cast<uint32_t>(k >> 32));
-      if (tf == -INFINITY) { full = false; continue; }   // a row index past n (last tile): never a candidate
-      lmin = fminf(lmin, tf);
+      if (k == 0ull) continue;
       const uint32_t j = 0xFFFFFFFFu - static_cast<uint32_t>(k);
       const float s = labels[j] == mylab ? knn_exact_score(bank, D, sq, j, invn[j]) : 0.0f;
       const unsigned long long nk = knn_key(s, j);
@@ -371,7 +427,6 @@ __global__ void __launch_bounds__(kMergeWarps * 32) knn_merge_kernel(
           if (q == mp) best[q] = nk;
       }
     }
-    if (full) mmax = fmaxf(mmax, lmin);
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) mmax = fmaxf(mmax, __shfl_xor_sync(kFullMask, mmax, o));
@@ -479,9 +534,10 @@ __global__ void __launch_bounds__(kExactWarps * 32) knn_exact_kernel(
 struct KnnPlan {
   int64_t Bpad;
   int32_t atiles, tiles_total, slices, tiles_per_slice, nlists, stages, tmem_cols;
+  int32_t tilesA, slicesA, tiles_per_sliceA, nlistsA;      // sampling pass over every kKnnSample-th tile (0 lists: skipped)
   size_t smem;
   bool tensor;              // the tcgen05 pass applies (D a multiple of 32, at most 128; n < 2^31)
-  size_t off_invn, off_qn, off_qlab, off_part, off_flags, total;
+  size_t off_invn, off_qn, off_qlab, off_part, off_rej, off_partA, off_rejA, off_thr, off_flags, total;
 };
 
 KnnPlan make_knn_plan(int64_t n, int64_t B, int32_t D) {
@@ -497,15 +553,30 @@ KnnPlan make_knn_plan(int64_t n, int64_t B, int32_t D) {
   p.tiles_per_slice = (p.tiles_total + slices - 1) / slices;
   p.slices = (p.tiles_total + p.tiles_per_slice - 1) / p.tiles_per_slice;
   p.nlists = p.tensor ? p.slices * 2 : 0;
+  p.tilesA = p.tiles_total >= 16 * kKnnSample ? (p.tiles_total + kKnnSample - 1) / kKnnSample : 0;
+  if (p.tilesA > 0 && p.tensor) {
+    int32_t sa = 148 / p.atiles;
+    if (sa < 1) sa = 1;
+    if (sa > p.tilesA) sa = p.tilesA;
+    p.tiles_per_sliceA = (p.tilesA + sa - 1) / sa;
+    p.slicesA = (p.tilesA + p.tiles_per_sliceA - 1) / p.tiles_per_sliceA;
+    p.nlistsA = p.slicesA * 2;
+  } else {
+    p.tilesA = 0;
+  }
   p.stages = 8;
   p.tmem_cols = 512;
-  p.smem = static_cast<size_t>(p.stages) * kKnnBoxBytes + 2 * kKnnTileN * 8 + (2 * p.stages + 4) * 8 + 16 + 1024;
+  p.smem = static_cast<size_t>(p.stages) * kKnnBoxBytes + kKnnEpiWarps * 2 * 128 * 4 + (2 * p.stages + 4) * 8 + 16 + 1024;
   size_t off = 0;
   auto take = [&](size_t bytes) { const size_t o = off; off += (bytes + 255) / 256 * 256; return o; };
   p.off_invn = take(static_cast<size_t>(n) * sizeof(float));
   p.off_qn = take(static_cast<size_t>(p.Bpad) * D * sizeof(float));
   p.off_qlab = take(static_cast<size_t>(p.Bpad) * sizeof(int32_t));
   p.off_part = take(static_cast<size_t>(p.nlists > 0 ? p.nlists : 1) * p.Bpad * kKnnC * sizeof(unsigned long long));
+  p.off_rej = take(static_cast<size_t>(p.nlists > 0 ? p.nlists : 1) * p.Bpad * sizeof(float));
+  p.off_partA = take(static_cast<size_t>(p.nlistsA > 0 ? p.nlistsA : 1) * p.Bpad * kKnnC * sizeof(unsigned long long));
+  p.off_rejA = take(static_cast<size_t>(p.nlistsA > 0 ? p.nlistsA : 1) * p.Bpad * sizeof(float));
+  p.off_thr = take(static_cast<size_t>(p.Bpad) * sizeof(float));
   p.off_flags = take(static_cast<size_t>(p.Bpad) * sizeof(int32_t));
   p.total = off;
   return p;
@@ -556,26 +627,40 @@ extern "C" int mml_crd_knn_positives(const float* bank, int64_t n, int32_t D, co
     if (rc != MML_OK) return rc;
   }
   const bool tensor = p.tensor && !exact_only;
+  float* rej = reinterpret_cast<float*>(ws + p.off_rej);
   if (tensor) {
     CUtensorMap tmap;
     const int rc0 = get_tensor_map_2d(bank, D, n, 32, kKnnTileN, true, &tmap);
     if (rc0 != MML_OK) return rc0;
     KnnArgs a{};
-    a.qn = qn; a.qlab = qlab; a.invn = invn; a.labels = row_labels; a.part = part;
+    a.qn = qn; a.qlab = qlab; a.invn = invn; a.labels = row_labels;
     a.n = n; a.Bpad = p.Bpad; a.D = D; a.nbox = D / 32;
-    a.tiles_total = p.tiles_total; a.tiles_per_slice = p.tiles_per_slice;
     a.stages = p.stages; a.tmem_cols = p.tmem_cols;
     a.idesc = make_idesc_tf32(kTileM, kKnnTileN);
     MML_CUDA(cudaFuncSetAttribute(knn_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(p.smem)));
-    const dim3 grid(static_cast<unsigned>(p.atiles), static_cast<unsigned>(p.slices));
-    knn_gemm_kernel<<<grid, kKnnThreads, p.smem, st>>>(tmap, a);
+    float* thr_init = nullptr;
+    if (p.nlistsA > 0) {             // sampling pass: every 16th tile -> a proven floor for every anchor's lists
+      unsigned long long* partA = reinterpret_cast<unsigned long long*>(ws + p.off_partA);
+      thr_init = reinterpret_cast<float*>(ws + p.off_thr);
+      a.part = partA; a.rej = reinterpret_cast<float*>(ws + p.off_rejA); a.thr_init = nullptr; a.tile_mul = kKnnSample;
+      a.tiles_total = p.tilesA; a.tiles_per_slice = p.tiles_per_sliceA;
+      knn_gemm_kernel<<<dim3(static_cast<unsigned>(p.atiles), static_cast<unsigned>(p.slicesA)), kKnnThreads, p.smem, st>>>(tmap, a);
+      int rc = check_launch("knn_gemm_kernel (sampling pass)");
+      if (rc != MML_OK) return rc;
+      knn_threshold_kernel<<<static_cast<unsigned>((p.Bpad + 127) / 128), 128, 0, st>>>(partA, p.nlistsA, B, p.Bpad, thr_init);
+      rc = check_launch("knn_threshold_kernel");
+      if (rc != MML_OK) return rc;
+    }
+    a.part = part; a.rej = rej; a.thr_init = thr_init; a.tile_mul = 1;
+    a.tiles_total = p.tiles_total; a.tiles_per_slice = p.tiles_per_slice;
+    knn_gemm_kernel<<<dim3(static_cast<unsigned>(p.atiles), static_cast<unsigned>(p.slices)), kKnnThreads, p.smem, st>>>(tmap, a);
     const int rc = check_launch("knn_gemm_kernel");
     if (rc != MML_OK) return rc;
   }
   {
     const size_t smem = static_cast<size_t>(kMergeWarps) * D * sizeof(float);
     knn_merge_kernel<<<static_cast<unsigned>((B + kMergeWarps - 1) / kMergeWarps), kMergeWarps * 32, smem, st>>>(
-        bank, D, invn, row_labels, qn, qlab, part, tensor ? p.nlists : 0, B, p.Bpad, P, out_idx, out_sim, flags, tensor ? 0 : 1);
+        bank, D, invn, row_labels, qn, qlab, part, rej, tensor ? p.nlists : 0, B, p.Bpad, P, out_idx, out_sim, flags, tensor ? 0 : 1);
     const int rc = check_launch("knn_merge_kernel");
     if (rc != MML_OK) return rc;
   }
