@@ -336,56 +336,57 @@ __global__ void __launch_bounds__(kKnnThreads, 1) knn_gemm_kernel(const __grid_c
   }
 }
 
-// exact fp32 cosine of query (shared memory, normalised) and bank row j
-__device__ __forceinline__ float knn_exact_score(const float* __restrict__ bank, int32_t D, const float* sm_q, int64_t j, float invn) {
-  const float* p = bank + j * D;
-  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-  for (int c = 0; c < D; c += 4) {
-    const float4 v = *reinterpret_cast<const float4*>(p + c);
-    const float4 q = *reinterpret_cast<const float4*>(sm_q + c);
-    a0 = fmaf(v.x, q.x, a0);
-    a1 = fmaf(v.y, q.y, a1);
-    a2 = fmaf(v.z, q.z, a2);
-    a3 = fmaf(v.w, q.w, a3);
-  }
-  return ((a0 + a1) + (a2 + a3)) * invn + 0.0f;
-}
-
 // Sampling pass -> per-anchor floor of the full pass.  The 8-th best TF32 score among every 16th bank tile is a lower bound of
 // the 8-th best over the whole bank, so a row scoring below (bound - 3 eps) in TF32 cannot be among the anchor's 8 best in
 // exact arithmetic.  Starting every list of the full pass at that floor makes the filter's slow path rare from the first
 // tile on (without it each of the ~36 short lists of an anchor climbs from -inf: r2z, 40 % of the warp-chunks took it).
-__global__ void knn_threshold_kernel(const unsigned long long* __restrict__ part, int32_t nlists, int64_t B, int64_t Bpad,
-                                     float* __restrict__ thr_init) {
-  const int64_t b = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(128) knn_threshold_kernel(const unsigned long long* __restrict__ part, int32_t nlists, int64_t B,
+                                                            int64_t Bpad, float* __restrict__ thr_init) {
+  const int lane = threadIdx.x & 31;
+  const int64_t b = static_cast<int64_t>(blockIdx.x) * 4 + (threadIdx.x >> 5);      // one warp per anchor
   if (b >= Bpad) return;
-  if (b >= B) { thr_init[b] = -INFINITY; return; }
-  uint32_t best[kKnnC];                                   // ordered score bits, unsorted; 0 = empty
+  if (b >= B) {
+    if (lane == 0) thr_init[b] = -INFINITY;
+    return;
+  }
+  constexpr int kMaxMine = kKnnC;                         // each lane keeps the 8 best of its share: the union holds the global 8 best
+  unsigned long long mine[kMaxMine];
 #pragma unroll
-  for (int i = 0; i < kKnnC; ++i) best[i] = 0u;
-  for (int l = 0; l < nlists; ++l) {
-    const unsigned long long* src = part + (static_cast<int64_t>(l) * Bpad + b) * kKnnC;
-    for (int i = 0; i < kKnnC; ++i) {
-      const unsigned long long k = src[i];
-      if (k == 0ull) continue;
-      const uint32_t o = static_cast<uint32_t>(k >> 32);
-      uint32_t mk = best[0];
-      int mp = 0;
+  for (int i = 0; i < kMaxMine; ++i) mine[i] = 0ull;
+  const int total = nlists * kKnnC;
+  for (int e = lane; e < total; e += 32) {
+    const unsigned long long k = part[(static_cast<int64_t>(e >> 3) * Bpad + b) * kKnnC + (e & 7)];
+    unsigned long long mk = mine[0];
+    int mp = 0;
 #pragma unroll
-      for (int q = 1; q < kKnnC; ++q)
-        if (best[q] < mk) { mk = best[q]; mp = q; }
-      if (o > mk) {
+    for (int q = 1; q < kMaxMine; ++q)
+      if (mine[q] < mk) { mk = mine[q]; mp = q; }
+    if (k > mk) {
 #pragma unroll
-        for (int q = 0; q < kKnnC; ++q)
-          if (q == mp) best[q] = o;
-      }
+      for (int q = 0; q < kMaxMine; ++q)
+        if (q == mp) mine[q] = k;
     }
   }
-  uint32_t mk = best[0];
+  unsigned long long top = 0ull;
+  for (int r = 0; r < kKnnC; ++r) {                       // the 8-th largest key of the union
+    unsigned long long m = mine[0];
 #pragma unroll
-  for (int q = 1; q < kKnnC; ++q) mk = best[q] < mk ? best[q] : mk;
-  const float v = mk == 0u ? -INFINITY : ord_value(mk);
-  thr_init[b] = (v == -INFINITY || !(v == v)) ? -INFINITY : v - 3.0f * kKnnEps;
+    for (int i = 1; i < kMaxMine; ++i) m = mine[i] > m ? mine[i] : m;
+    top = m;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const unsigned long long other = __shfl_xor_sync(kFullMask, top, o);
+      top = other > top ? other : top;
+    }
+    if (top == 0ull) break;                               // fewer than 8 rows seen: no bound
+#pragma unroll
+    for (int i = 0; i < kMaxMine; ++i)
+      if (mine[i] == top) mine[i] = 0ull;                 // keys are unique: exactly one lane holds it
+  }
+  if (lane == 0) {
+    const float v = top == 0ull ? -INFINITY : ord_value(static_cast<uint32_t>(top >> 32));
+    thr_init[b] = (v == -INFINITY || !(v == v)) ? -INFINITY : v - 3.0f * kKnnEps;
+  }
 }
 
 constexpr int kMergeWarps = 4;
@@ -393,8 +394,8 @@ constexpr int kMergeWarps = 4;
 __global__ void __launch_bounds__(kMergeWarps * 32) knn_merge_kernel(
     const float* __restrict__ bank, int32_t D, const float* __restrict__ invn, const int32_t* __restrict__ labels,
     const float* __restrict__ qn, const int32_t* __restrict__ qlab, const unsigned long long* __restrict__ part,
-    const float* __restrict__ rej, int32_t nlists, int64_t B, int64_t Bpad, int32_t P, int64_t* __restrict__ out_idx, float* __restrict__ out_sim, int32_t* __restrict__ flags,
-    int32_t force_flag) {
+    const float* __restrict__ rej, int32_t nlists, int64_t B, int64_t Bpad, int32_t P, int64_t* __restrict__ out_idx,
+    float* __restrict__ out_sim, int32_t* __restrict__ flags, int32_t force_flag) {
   extern __shared__ float sm_qm[];                       // [kMergeWarps][D]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t b = static_cast<int64_t>(blockIdx.x) * kMergeWarps + warp;
@@ -403,58 +404,316 @@ __global__ void __launch_bounds__(kMergeWarps * 32) knn_merge_kernel(
   for (int c = lane; c < D; c += 32) sq[c] = qn[b * D + c];
   __syncwarp();
   const int32_t mylab = qlab[b];
-  unsigned long long best[kKnnC];                        // this lane's exact candidates, unsorted
+  float mmax = -INFINITY;                                // max over the lists of the list's final threshold
+  for (int l = lane; l < nlists; l += 32) mmax = fmaxf(mmax, rej[static_cast<int64_t>(l) * Bpad + b]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mmax = fmaxf(mmax, __shfl_xor_sync(kFullMask, mmax, o));
+  // Every candidate is re-scored by the WHOLE warp (one coalesced pass over its row, butterfly sum), eight candidates in
+  // flight at a time; the running best-8 is kept identically in all lanes.
+  unsigned long long best[kKnnC];
 #pragma unroll
   for (int i = 0; i < kKnnC; ++i) best[i] = 0ull;
-  float mmax = -INFINITY;                                // max over this lane's lists of the list's final threshold
-  for (int l = lane; l < nlists; l += 32) {
-    const unsigned long long* src = part + (static_cast<int64_t>(l) * Bpad + b) * kKnnC;
-    mmax = fmaxf(mmax, rej[static_cast<int64_t>(l) * Bpad + b]);      // rows this list left out score <= this (TF32)
-    for (int i = 0; i < kKnnC; ++i) {
-      const unsigned long long k = src[i];
-      if (k == 0ull) continue;
-      const uint32_t j = 0xFFFFFFFFu - static_cast<uint32_t>(k);
-      const float s = labels[j] == mylab ? knn_exact_score(bank, D, sq, j, invn[j]) : 0.0f;
-      const unsigned long long nk = knn_key(s, j);
-      unsigned long long mk = best[0];
-      int mp = 0;
+  unsigned long long worst = 0ull;
+  const int total = nlists * kKnnC;
+  for (int base = 0; base < total; base += 32) {
+    const int e = base + lane;
+    const unsigned long long k = e < total ? part[(static_cast<int64_t>(e >> 3) * Bpad + b) * kKnnC + (e & 7)] : 0ull;
+    uint32_t mask = __ballot_sync(kFullMask, k != 0ull);
+    while (mask != 0u) {
+      uint32_t rowj[8];
+      float acc[8], inv[8];
+      int32_t lab[8];
 #pragma unroll
-      for (int q = 1; q < kKnnC; ++q)
-        if (best[q] < mk) { mk = best[q]; mp = q; }
-      if (nk > mk) {
+      for (int g = 0; g < 8; ++g) {
+        acc[g] = 0.f;
+        rowj[g] = 0xFFFFFFFFu;
+        if (mask != 0u) {
+          const int src = __ffs(mask) - 1;
+          mask &= mask - 1u;
+          rowj[g] = 0xFFFFFFFFu - static_cast<uint32_t>(__shfl_sync(kFullMask, static_cast<uint32_t>(k), src));
+        }
+      }
+      // all loads of the round are independent of each other: label, 1/|row| and the row itself, eight candidates at once
 #pragma unroll
-        for (int q = 0; q < kKnnC; ++q)
-          if (q == mp) best[q] = nk;
+      for (int g = 0; g < 8; ++g) {
+        const uint32_t r = rowj[g] == 0xFFFFFFFFu ? 0u : rowj[g];
+        lab[g] = __ldg(labels + r);
+        inv[g] = __ldg(invn + r);
+      }
+      for (int c = lane * 4; c < D; c += 128) {
+        float4 v[8];
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {
+          const uint32_t r = rowj[g] == 0xFFFFFFFFu ? 0u : rowj[g];
+          v[g] = *reinterpret_cast<const float4*>(bank + static_cast<int64_t>(r) * D + c);
+        }
+        const float4 q = *reinterpret_cast<const float4*>(sq + c);
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {
+          acc[g] = fmaf(v[g].x, q.x, acc[g]);
+          acc[g] = fmaf(v[g].y, q.y, acc[g]);
+          acc[g] = fmaf(v[g].z, q.z, acc[g]);
+          acc[g] = fmaf(v[g].w, q.w, acc[g]);
+        }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+        for (int g = 0; g < 8; ++g) acc[g] += __shfl_xor_sync(kFullMask, acc[g], o);
+      }
+#pragma unroll
+      for (int g = 0; g < 8; ++g) {
+        if (rowj[g] == 0xFFFFFFFFu) continue;             // warp-uniform
+        const float sc = lab[g] == mylab ? acc[g] * inv[g] + 0.0f : 0.0f;
+        const unsigned long long nk = knn_key(sc, rowj[g]);
+        if (nk > worst) {
+          unsigned long long mk = best[0];
+          int mp = 0;
+#pragma unroll
+          for (int q = 1; q < kKnnC; ++q)
+            if (best[q] < mk) { mk = best[q]; mp = q; }
+#pragma unroll
+          for (int q = 0; q < kKnnC; ++q)
+            if (q == mp) best[q] = nk;
+          worst = best[0];
+#pragma unroll
+          for (int q = 1; q < kKnnC; ++q) worst = best[q] < worst ? best[q] : worst;
+        }
       }
     }
   }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) mmax = fmaxf(mmax, __shfl_xor_sync(kFullMask, mmax, o));
-  // P rounds of a warp-wide arg-max over the lanes' candidates
+  // the best P, in order
   float vP = -INFINITY;
   for (int p = 0; p < P; ++p) {
-    unsigned long long mine = best[0];
+    unsigned long long top = best[0];
 #pragma unroll
-    for (int q = 1; q < kKnnC; ++q) mine = best[q] > mine ? best[q] : mine;
-    unsigned long long top = mine;
+    for (int q = 1; q < kKnnC; ++q) top = best[q] > top ? best[q] : top;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      const unsigned long long other = __shfl_xor_sync(kFullMask, top, o);
-      top = other > top ? other : top;
-    }
-    if (mine == top && top != 0ull) {                    // keys are unique (the row is part of the key): one lane owns it
-#pragma unroll
-      for (int q = 0; q < kKnnC; ++q)
-        if (best[q] == top) best[q] = 0ull;
-    }
+    for (int q = 0; q < kKnnC; ++q)
+      if (best[q] == top) best[q] = 0ull;
+    const bool have = top != 0ull;
+    vP = have ? ord_value(static_cast<uint32_t>(top >> 32)) : -INFINITY;
     if (lane == 0) {
-      const bool have = top != 0ull;
-      vP = have ? ord_value(static_cast<uint32_t>(top >> 32)) : -INFINITY;
       out_idx[b * P + p] = have ? static_cast<int64_t>(0xFFFFFFFFu - static_cast<uint32_t>(top)) : -1;
       out_sim[b * P + p] = have ? vP : 0.f;
     }
   }
   if (lane == 0) flags[b] = (force_flag || !(vP > mmax + kKnnEps)) ? 1 : 0;   // not provable: re-do this anchor exactly
+}
+
+// ---- exact scan of the flagged anchors, 32 anchors at a time -------------------------------------------------------------
+// knn_compact_kernel lists the flagged anchors; knn_exact_group_kernel gives every lane of a warp ONE of 32 flagged anchors
+// (its normalised query in registers) and streams bank rows through shared memory: a row is read once per warp as broadcast
+// 128-bit loads and costs D FMAs for 32 anchors (the per-anchor scan below reads the whole bank per anchor: 85 ms for 1024
+// flagged anchors over 1M rows; this one is bound by the fp32 FMA rate: ~5 ms).  Grid = (anchor groups, bank slices); groups
+// past the flagged count exit at once.  knn_pick_kernel merges the slices.
+__global__ void __launch_bounds__(1024) knn_compact_kernel(const int32_t* __restrict__ flags, int64_t B, int32_t* __restrict__ list,
+                                                           int32_t* __restrict__ count) {
+  __shared__ int warp_cnt[32];
+  __shared__ int running;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) running = 0;
+  __syncthreads();
+  for (int64_t start = 0; start < B; start += 1024) {
+    const int64_t b = start + tid;
+    const bool f = b < B && flags[b] != 0;
+    const uint32_t bal = __ballot_sync(kFullMask, f);
+    if (lane == 0) warp_cnt[warp] = __popc(bal);
+    __syncthreads();
+    int before = running;
+    for (int w = 0; w < warp; ++w) before += warp_cnt[w];
+    if (f) list[before + __popc(bal & ((1u << lane) - 1u))] = static_cast<int32_t>(b);
+    __syncthreads();
+    if (tid == 0) {
+      int tot = 0;
+      for (int w = 0; w < 32; ++w) tot += warp_cnt[w];
+      running += tot;
+    }
+    __syncthreads();
+  }
+  if (tid == 0) *count = running;
+}
+
+constexpr int kEgWarps = 8;
+constexpr int kEgRows = 64;                 // bank rows per shared-memory tile
+
+template <int kD>
+__global__ void __launch_bounds__(kEgWarps * 32, 1) knn_exact_group_kernel(
+    const float* __restrict__ bank, int64_t n, const float* __restrict__ invn, const int32_t* __restrict__ labels,
+    const float* __restrict__ qn, const int32_t* __restrict__ qlab, const int32_t* __restrict__ list,
+    const int32_t* __restrict__ count, int32_t nslices, int64_t rows_per_slice, int64_t Bpad, unsigned long long* __restrict__ partE) {
+  const int cnt = *count;
+  extern __shared__ __align__(16) float sm_eg[];            // [2][kEgRows][kD] rows | [2][kEgRows] 1/|row| | [2][kEgRows] labels
+  float* sm_rows = sm_eg;
+  float* sm_in = sm_eg + 2 * kEgRows * kD;
+  int32_t* sm_lb = reinterpret_cast<int32_t*>(sm_in + 2 * kEgRows);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  // work items = (group of 32 flagged anchors, bank slice); no flagged anchor -> no item -> the CTA retires at once
+  for (int item = blockIdx.x; item < (cnt + 31) / 32 * nslices; item += gridDim.x) {
+  const int group = item / nslices, slice = item % nslices;
+  const int slot = group * 32 + lane;                       // position in the flagged list
+  const int anchor = slot < cnt ? list[slot] : -1;
+  float q[kD];
+#pragma unroll
+  for (int c = 0; c < kD; c += 4) {
+    const float4 v = anchor >= 0 ? *reinterpret_cast<const float4*>(qn + static_cast<int64_t>(anchor) * kD + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+    q[c] = v.x; q[c + 1] = v.y; q[c + 2] = v.z; q[c + 3] = v.w;
+  }
+  const int32_t mylab = anchor >= 0 ? qlab[anchor] : -3;
+  unsigned long long best[kKnnC];
+#pragma unroll
+  for (int i = 0; i < kKnnC; ++i) best[i] = 0ull;
+  unsigned long long worst = 0ull;
+  const int64_t r_begin = static_cast<int64_t>(slice) * rows_per_slice;
+  const int64_t r_end = r_begin + rows_per_slice < n ? r_begin + rows_per_slice : n;
+  const int ntiles = r_begin < r_end ? static_cast<int>((r_end - r_begin + kEgRows - 1) / kEgRows) : 0;
+  auto issue = [&](int t) {                                 // tile t -> buffer t & 1 (16-byte cp.async, coalesced)
+    if (t < ntiles) {
+      const int64_t r0 = r_begin + static_cast<int64_t>(t) * kEgRows;
+      float* dst = sm_rows + (t & 1) * kEgRows * kD;
+      for (int i = tid; i < kEgRows * kD / 4; i += kEgWarps * 32) {
+        const int64_t r = r0 + (i * 4) / kD;
+        const float* src = bank + (r < r_end ? r : r_end - 1) * kD + (i * 4) % kD;
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst + i * 4)), "l"(src) : "memory");
+      }
+      if (tid < kEgRows) {
+        const int64_t r = r0 + tid;
+        sm_in[(t & 1) * kEgRows + tid] = r < r_end ? __ldg(invn + r) : 0.f;
+        sm_lb[(t & 1) * kEgRows + tid] = r < r_end ? __ldg(labels + r) : -2;
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  issue(0);
+  for (int t = 0; t < ntiles; ++t) {
+    issue(t + 1);
+    asm volatile("cp.async.wait_group 1;" ::: "memory");
+    __syncthreads();
+    const float* tile = sm_rows + (t & 1) * kEgRows * kD;
+    const int64_t r0 = r_begin + static_cast<int64_t>(t) * kEgRows;
+#pragma unroll 1
+    for (int rr = 0; rr < kEgRows / kEgWarps; ++rr) {
+      const int row = warp * (kEgRows / kEgWarps) + rr;
+      const int32_t lab = sm_lb[(t & 1) * kEgRows + row];
+      if (lab == -2) continue;                              // past the slice (uniform)
+      const float* rp = tile + row * kD;
+      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+      for (int c = 0; c < kD; c += 4) {
+        const float4 v = *reinterpret_cast<const float4*>(rp + c);      // broadcast: every lane reads the same row
+        a0 = fmaf(v.x, q[c], a0);
+        a1 = fmaf(v.y, q[c + 1], a1);
+        a2 = fmaf(v.z, q[c + 2], a2);
+        a3 = fmaf(v.w, q[c + 3], a3);
+      }
+      const float sc = lab == mylab ? ((a0 + a1) + (a2 + a3)) * sm_in[(t & 1) * kEgRows + row] + 0.0f : 0.0f;
+      const unsigned long long nk = knn_key(sc, static_cast<uint32_t>(r0 + row));
+      if (nk > worst) {
+        unsigned long long mk = best[0];
+        int mp = 0;
+#pragma unroll
+        for (int i = 1; i < kKnnC; ++i)
+          if (best[i] < mk) { mk = best[i]; mp = i; }
+#pragma unroll
+        for (int i = 0; i < kKnnC; ++i)
+          if (i == mp) best[i] = nk;
+        worst = best[0];
+#pragma unroll
+        for (int i = 1; i < kKnnC; ++i) worst = best[i] < worst ? best[i] : worst;
+      }
+    }
+    __syncthreads();                                        // the buffer is free for tile t + 2
+  }
+  // merge the 8 warps' lists per anchor (shared memory: the tile buffers are idle now), one thread per anchor
+  unsigned long long* sm_k = reinterpret_cast<unsigned long long*>(sm_eg);      // [kEgWarps][32][kKnnC]
+#pragma unroll
+  for (int i = 0; i < kKnnC; ++i) sm_k[(warp * 32 + lane) * kKnnC + i] = best[i];
+  __syncthreads();
+  if (warp == 0 && anchor >= 0) {
+#pragma unroll
+    for (int i = 0; i < kKnnC; ++i) best[i] = 0ull;
+    worst = 0ull;
+    for (int w = 0; w < kEgWarps; ++w)
+      for (int i = 0; i < kKnnC; ++i) {
+        const unsigned long long nk = sm_k[(w * 32 + lane) * kKnnC + i];
+        if (nk > worst) {
+          unsigned long long mk = best[0];
+          int mp = 0;
+#pragma unroll
+          for (int q2 = 1; q2 < kKnnC; ++q2)
+            if (best[q2] < mk) { mk = best[q2]; mp = q2; }
+#pragma unroll
+          for (int q2 = 0; q2 < kKnnC; ++q2)
+            if (q2 == mp) best[q2] = nk;
+          worst = best[0];
+#pragma unroll
+          for (int q2 = 1; q2 < kKnnC; ++q2) worst = best[q2] < worst ? best[q2] : worst;
+        }
+      }
+    unsigned long long* dst = partE + (static_cast<int64_t>(slice) * Bpad + slot) * kKnnC;
+#pragma unroll
+    for (int i = 0; i < kKnnC; ++i) dst[i] = best[i];
+  }
+  __syncthreads();                                          // shared memory is reused by the next item
+  }
+}
+
+// one warp per flagged anchor: the best P of its slices' exact lists
+__global__ void __launch_bounds__(128) knn_pick_kernel(const unsigned long long* __restrict__ partE, int32_t nslices, int64_t Bpad,
+                                                       const int32_t* __restrict__ list, const int32_t* __restrict__ count, int32_t P,
+                                                       int64_t* __restrict__ out_idx, float* __restrict__ out_sim) {
+  const int lane = threadIdx.x & 31;
+  const int slot = blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (slot >= *count) return;
+  const int64_t b = list[slot];
+  unsigned long long mine[kKnnC];
+#pragma unroll
+  for (int i = 0; i < kKnnC; ++i) mine[i] = 0ull;
+  const int total = nslices * kKnnC;
+  for (int e = lane; e < total; e += 32) {
+    const unsigned long long k = partE[(static_cast<int64_t>(e >> 3) * Bpad + slot) * kKnnC + (e & 7)];
+    unsigned long long mk = mine[0];
+    int mp = 0;
+#pragma unroll
+    for (int q = 1; q < kKnnC; ++q)
+      if (mine[q] < mk) { mk = mine[q]; mp = q; }
+    if (k > mk) {
+#pragma unroll
+      for (int q = 0; q < kKnnC; ++q)
+        if (q == mp) mine[q] = k;
+    }
+  }
+  for (int p = 0; p < P; ++p) {
+    unsigned long long top = mine[0];
+#pragma unroll
+    for (int i = 1; i < kKnnC; ++i) top = mine[i] > top ? mine[i] : top;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const unsigned long long other = __shfl_xor_sync(kFullMask, top, o);
+      top = other > top ? other : top;
+    }
+#pragma unroll
+    for (int i = 0; i < kKnnC; ++i)
+      if (mine[i] == top && top != 0ull) mine[i] = 0ull;
+    if (lane == 0) {
+      const bool have = top != 0ull;
+      out_idx[b * P + p] = have ? static_cast<int64_t>(0xFFFFFFFFu - static_cast<uint32_t>(top)) : -1;
+      out_sim[b * P + p] = have ? ord_value(static_cast<uint32_t>(top >> 32)) : 0.f;
+    }
+  }
+}
+
+template <int kD>
+int launch_exact_group(const float* bank, int64_t n, const float* invn, const int32_t* labels, const float* qn, const int32_t* qlab,
+                       const int32_t* list, const int32_t* count, int32_t groups, int32_t slices, int64_t rows_per_slice, int64_t Bpad,
+                       unsigned long long* partE, cudaStream_t st) {
+  const size_t smem = static_cast<size_t>(2) * kEgRows * kD * sizeof(float) + 2 * kEgRows * 8;
+  const size_t need = smem > kEgWarps * 32 * kKnnC * sizeof(unsigned long long) ? smem : kEgWarps * 32 * kKnnC * sizeof(unsigned long long);
+  MML_CUDA(cudaFuncSetAttribute(knn_exact_group_kernel<kD>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(need)));
+  const int64_t items = static_cast<int64_t>(groups) * slices;
+  knn_exact_group_kernel<kD><<<static_cast<unsigned>(items < 296 ? items : 296), kEgWarps * 32, need, st>>>(
+      bank, n, invn, labels, qn, qlab, list, count, slices, rows_per_slice, Bpad, partE);
+  return check_launch("knn_exact_group_kernel");
 }
 
 constexpr int kExactWarps = 8;
@@ -537,7 +796,9 @@ struct KnnPlan {
   int32_t tilesA, slicesA, tiles_per_sliceA, nlistsA;      // sampling pass over every kKnnSample-th tile (0 lists: skipped)
   size_t smem;
   bool tensor;              // the tcgen05 pass applies (D a multiple of 32, at most 128; n < 2^31)
-  size_t off_invn, off_qn, off_qlab, off_part, off_rej, off_partA, off_rejA, off_thr, off_flags, total;
+  int32_t groupsE, slicesE;                               // exact scan of flagged anchors: 32-anchor groups x bank slices
+  int64_t rows_per_sliceE;
+  size_t off_invn, off_qn, off_qlab, off_part, off_rej, off_partA, off_rejA, off_thr, off_flags, off_list, off_count, off_partE, total;
 };
 
 KnnPlan make_knn_plan(int64_t n, int64_t B, int32_t D) {
@@ -578,6 +839,16 @@ KnnPlan make_knn_plan(int64_t n, int64_t B, int32_t D) {
   p.off_rejA = take(static_cast<size_t>(p.nlistsA > 0 ? p.nlistsA : 1) * p.Bpad * sizeof(float));
   p.off_thr = take(static_cast<size_t>(p.Bpad) * sizeof(float));
   p.off_flags = take(static_cast<size_t>(p.Bpad) * sizeof(int32_t));
+  p.groupsE = static_cast<int32_t>(p.Bpad / 32);
+  p.slicesE = 148 * 16 / p.groupsE;
+  if (p.slicesE > 148) p.slicesE = 148;
+  if (p.slicesE < 1) p.slicesE = 1;
+  p.rows_per_sliceE = (n + p.slicesE - 1) / p.slicesE;
+  p.rows_per_sliceE = (p.rows_per_sliceE + kEgRows - 1) / kEgRows * kEgRows;
+  p.slicesE = static_cast<int32_t>((n + p.rows_per_sliceE - 1) / p.rows_per_sliceE);
+  p.off_list = take(static_cast<size_t>(p.Bpad) * sizeof(int32_t));
+  p.off_count = take(sizeof(int32_t));
+  p.off_partE = take(static_cast<size_t>(p.slicesE) * p.Bpad * kKnnC * sizeof(unsigned long long));
   p.total = off;
   return p;
 }
@@ -647,7 +918,7 @@ extern "C" int mml_crd_knn_positives(const float* bank, int64_t n, int32_t D, co
       knn_gemm_kernel<<<dim3(static_cast<unsigned>(p.atiles), static_cast<unsigned>(p.slicesA)), kKnnThreads, p.smem, st>>>(tmap, a);
       int rc = check_launch("knn_gemm_kernel (sampling pass)");
       if (rc != MML_OK) return rc;
-      knn_threshold_kernel<<<static_cast<unsigned>((p.Bpad + 127) / 128), 128, 0, st>>>(partA, p.nlistsA, B, p.Bpad, thr_init);
+      knn_threshold_kernel<<<static_cast<unsigned>((p.Bpad + 3) / 4), 128, 0, st>>>(partA, p.nlistsA, B, p.Bpad, thr_init);
       rc = check_launch("knn_threshold_kernel");
       if (rc != MML_OK) return rc;
     }
@@ -664,7 +935,24 @@ extern "C" int mml_crd_knn_positives(const float* bank, int64_t n, int32_t D, co
     const int rc = check_launch("knn_merge_kernel");
     if (rc != MML_OK) return rc;
   }
-  {
+  if (D == 32 || D == 64 || D == 96 || D == 128) {
+    int32_t* list = reinterpret_cast<int32_t*>(ws + p.off_list);
+    int32_t* count = reinterpret_cast<int32_t*>(ws + p.off_count);
+    unsigned long long* partE = reinterpret_cast<unsigned long long*>(ws + p.off_partE);
+    knn_compact_kernel<<<1, 1024, 0, st>>>(flags, B, list, count);
+    int rc = check_launch("knn_compact_kernel");
+    if (rc != MML_OK) return rc;
+    switch (D) {
+      case 32: rc = launch_exact_group<32>(bank, n, invn, row_labels, qn, qlab, list, count, p.groupsE, p.slicesE, p.rows_per_sliceE, p.Bpad, partE, st); break;
+      case 64: rc = launch_exact_group<64>(bank, n, invn, row_labels, qn, qlab, list, count, p.groupsE, p.slicesE, p.rows_per_sliceE, p.Bpad, partE, st); break;
+      case 96: rc = launch_exact_group<96>(bank, n, invn, row_labels, qn, qlab, list, count, p.groupsE, p.slicesE, p.rows_per_sliceE, p.Bpad, partE, st); break;
+      default: rc = launch_exact_group<128>(bank, n, invn, row_labels, qn, qlab, list, count, p.groupsE, p.slicesE, p.rows_per_sliceE, p.Bpad, partE, st); break;
+    }
+    if (rc != MML_OK) return rc;
+    knn_pick_kernel<<<static_cast<unsigned>((B + 3) / 4), 128, 0, st>>>(partE, p.slicesE, p.Bpad, list, count, P, out_idx, out_sim);
+    rc = check_launch("knn_pick_kernel");
+    if (rc != MML_OK) return rc;
+  } else {                         // other widths: one CTA per flagged anchor
     const size_t smem = static_cast<size_t>((D + 3) / 4 * 4) * sizeof(float) + kExactWarps * kKnnC * sizeof(unsigned long long);
     knn_exact_kernel<<<static_cast<unsigned>(B), kExactWarps * 32, smem, st>>>(bank, n, D, invn, row_labels, qn, qlab, flags, P,
                                                                             out_idx, out_sim);
