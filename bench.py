@@ -481,9 +481,9 @@ def knn_section(dev, peaks, cpu_anchors):
     flops = 2.0 * B * n * D
     out = {"workload": f"KNN positives over the full bank: {n} x {D} rows, {B} anchors, num_pos {P}, 3 classes",
            "ms": ms, "bound": "tensor", "achieved": flops / ms / 1e9, "peak": tf32_peak, "unit": "TFLOP/s",
-           "frac": flops / ms / 1e9 / tf32_peak, "flops": flops, "own_kernel_launches": 5,
+           "frac": flops / ms / 1e9 / tf32_peak, "flops": flops, "own_kernel_launches": 9,
            "bank_passes_GBps": 2 * n * D * 4 / ms / 1e6, "flagged_anchors": int(flags.sum()),
-           "note": "time of the whole call (5 launches); flops = 2 B n D of the TF32 pass; the bank is read once for the "
+           "note": "time of the whole call (9 launches: norms, queries, sampling pass, floor, full pass, re-score, flagged-anchor scan x3); flops = 2 B n D of the TF32 pass; the bank is read once for the "
                    "inverse norms and once by TMA for the GEMM (L2-shared between the 8 anchor tiles)"}
     if cpu_anchors > 0:
         try:
