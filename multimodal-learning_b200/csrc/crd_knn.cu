@@ -28,9 +28,6 @@ using namespace tc;
 
 constexpr int kKnnC = 8;                   // candidates kept per (bank slice, column half) list = the largest supported P
 constexpr int kKnnTileN = 128;             // bank rows per accumulator tile
-constexpr int kKnnEpiWarps = 8;
-constexpr int kKnnEpiThreads = kKnnEpiWarps * 32;
-constexpr int kKnnThreads = kKnnEpiThreads + 64;      // + TMA warp + MMA warp
 constexpr uint32_t kKnnBoxBytes = kKnnTileN * 32 * 4; // [128 rows x 32 d] fp32 = 16 KB
 constexpr int kKnnSample = 16;             // the sampling pass visits every 16th bank tile
 constexpr float kKnnEps = 2.0e-3f;         // >= |TF32 score - exact score|: A rounded (2^-11), B truncated (2^-10), |q| = |r| = 1
@@ -67,11 +64,11 @@ __global__ void knn_invnorm_kernel(const float* __restrict__ bank, int64_t n, in
 
 __global__ void knn_query_kernel(const float* __restrict__ bank, int64_t n, int32_t D, const int64_t* __restrict__ rows,
                                  const int64_t* __restrict__ labels_in, int64_t B, int64_t Bpad, float* __restrict__ qn,
-                                 int32_t* __restrict__ qlab, uint32_t* err) {
+                                 float* __restrict__ qt, int32_t* __restrict__ qlab, uint32_t* err) {
   const int64_t b = blockIdx.x;
   const int lane = threadIdx.x;              // 32 threads
   if (b >= B) {                              // padding rows of the last anchor tile
-    for (int c = lane; c < D; c += 32) qn[b * D + c] = 0.f;
+    for (int c = lane; c < D; c += 32) { qn[b * D + c] = 0.f; qt[b * D + c] = 0.f; }
     if (lane == 0) qlab[b] = -1;
     return;
   }
@@ -88,8 +85,22 @@ __global__ void knn_query_kernel(const float* __restrict__ bank, int64_t n, int3
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(kFullMask, acc, o);
   const float norm = sqrtf(acc);
-  for (int c = lane; c < D; c += 32) qn[b * D + c] = norm > 0.f ? bank[r * D + c] / norm : 0.f;
+  for (int c = lane; c < D; c += 32) {
+    const float v = norm > 0.f ? bank[r * D + c] / norm : 0.f;
+    qn[b * D + c] = v;                                                               // exact: re-scoring
+    qt[b * D + c] = __uint_as_float((__float_as_uint(v) + 0x1000u) & 0xFFFFE000u);   // nearest TF32: the descriptor-fed A operand
+  }
   if (lane == 0) qlab[b] = static_cast<int32_t>(labels_in[b]);
+}
+
+// D[tmem] (+)= A[smem desc] * B[smem desc],  kind::tf32, M = 128, K = 8 (both operands K-major, 128B-swizzled boxes)
+__device__ __forceinline__ void tc_mma_tf32_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
 }
 
 struct KnnArgs {
@@ -108,25 +119,34 @@ struct KnnArgs {
   uint32_t idesc;
 };
 
-__global__ void __launch_bounds__(kKnnThreads, 1) knn_gemm_kernel(const __grid_constant__ CUtensorMap tmap_bank, const KnnArgs a) {
+// kAT = anchor tiles per CTA.  kAT = 1: the query tile is the A operand in TENSOR MEMORY.  kAT = 2: every bank box feeds TWO
+// 128-anchor MMAs (queries in shared memory, both operands by descriptor; all 512 TMEM columns are accumulators), which
+// halves the L2 -> SM stream per flop: one anchor tile per CTA pulls 64 KB per 1418 tensor cycles = 46 B/cycle/SM, above
+// what L2 delivers to every SM at once (r3c: 48 % tensor pipe).  16 epilogue warps instead of 8.
+template <int kAT>
+__global__ void __launch_bounds__((8 * kAT + 2) * 32, 1) knn_gemm_kernel(const __grid_constant__ CUtensorMap tmap_bank,
+                                                                         const __grid_constant__ CUtensorMap tmap_q, const KnnArgs a) {
+  constexpr int EW = 8 * kAT;                    // epilogue warps; warp EW = TMA producer, warp EW + 1 = MMA issuer
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  uint8_t* sm_b = smem;                                                              // [stages][16 KB]
-  float* sm_side = reinterpret_cast<float*>(smem + static_cast<size_t>(a.stages) * kKnnBoxBytes);   // [8 warps][2][64 + 64]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sm_side + kKnnEpiWarps * 2 * 128);
+  uint8_t* sm_a = smem;                                                              // kAT == 2: [2][nbox][16 KB] query boxes
+  uint8_t* sm_b = smem + (kAT == 2 ? static_cast<size_t>(2 * a.nbox) * kKnnBoxBytes : 0);      // [stages][16 KB]
+  float* sm_side = reinterpret_cast<float*>(sm_b + static_cast<size_t>(a.stages) * kKnnBoxBytes);   // [EW warps][2][64 + 64]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sm_side + EW * 2 * 128);
   uint64_t* bar_full = bars;                     // [stages] bank box landed
   uint64_t* bar_empty = bars + a.stages;         // [stages] MMAs reading the box done
-  uint64_t* bar_acc_full = bars + 2 * a.stages;  // [2] accumulator tile complete
-  uint64_t* bar_acc_empty = bar_acc_full + 2;    // [2] epilogue has read the tile (8 warp arrivals)
-  uint32_t* sm_tmem = reinterpret_cast<uint32_t*>(bar_acc_empty + 2);
+  uint64_t* bar_acc_full = bars + 2 * a.stages;  // [2] accumulator tile(s) complete
+  uint64_t* bar_acc_empty = bar_acc_full + 2;    // [2] epilogue has read the tile(s) (EW warp arrivals)
+  uint64_t* bar_a = bar_acc_empty + 2;           // kAT == 2: query boxes landed
+  uint32_t* sm_tmem = reinterpret_cast<uint32_t*>(bar_a + 1);
 
   const int warp = warp_idx_sync();
   const int lane = threadIdx.x & 31;
-  const int64_t b0 = static_cast<int64_t>(blockIdx.x) * kTileM;
+  const int64_t b0 = static_cast<int64_t>(blockIdx.x) * kTileM * kAT;
   const int t_begin = blockIdx.y * a.tiles_per_slice;
   const int t_end = min(a.tiles_total, t_begin + a.tiles_per_slice);
 
-  if (warp == kKnnEpiWarps && lane == 0) {
+  if (warp == EW && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_bank)) : "memory");
     for (int s = 0; s < a.stages; ++s) {
       mbar_init(&bar_full[s], 1);
@@ -134,11 +154,12 @@ __global__ void __launch_bounds__(kKnnThreads, 1) knn_gemm_kernel(const __grid_c
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&bar_acc_full[i], 1);
-      mbar_init(&bar_acc_empty[i], kKnnEpiWarps);
+      mbar_init(&bar_acc_empty[i], EW);
     }
+    mbar_init(bar_a, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == kKnnEpiWarps + 1) {
+  if (warp == EW + 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(sm_tmem)), "r"(a.tmem_cols)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -147,11 +168,11 @@ __global__ void __launch_bounds__(kKnnThreads, 1) knn_gemm_kernel(const __grid_c
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *sm_tmem;
-  const uint32_t tmem_acc = tmem_base;                   // 2 x 128 accumulator columns
-  const uint32_t tmem_a = tmem_base + 2 * kKnnTileN;     // query tile: D columns
+  const uint32_t tmem_acc = tmem_base;                   // [kAT][2] x 128 accumulator columns
+  const uint32_t tmem_a = tmem_base + 2 * kKnnTileN;     // kAT == 1: query tile, D columns
 
-  // ---- A operand: this CTA's 128 normalised queries -> TMEM, once ----
-  if (warp < kKnnEpiWarps) {
+  // ---- kAT == 1: A operand = this CTA's 128 normalised queries -> TMEM, once ----
+  if (kAT == 1 && warp < EW) {
     const int row = threadIdx.x & (kTileM - 1);
     const int half = threadIdx.x >> 7;
     const uint32_t lane_base = static_cast<uint32_t>((warp & 3) * 32) << 16;
@@ -176,8 +197,18 @@ __global__ void __launch_bounds__(kKnnThreads, 1) knn_gemm_kernel(const __grid_c
   __syncthreads();
   tc_fence_after();
 
-  if (warp == kKnnEpiWarps) {
+  if (warp == EW) {
     // ===== TMA producer: D/32 boxes of [128 bank rows x 32 d] per tile =====
+    if (kAT == 2) {
+      if (elect_one_sync()) {
+        mbar_arrive_expect_tx(bar_a, static_cast<uint32_t>(2 * a.nbox) * kKnnBoxBytes);
+        for (int at = 0; at < 2; ++at)
+          for (int j = 0; j < a.nbox; ++j)
+            tma_load_2d(sm_a + static_cast<size_t>(at * a.nbox + j) * kKnnBoxBytes, &tmap_q, j * 32,
+                        static_cast<int32_t>(b0) + at * kTileM, bar_a);
+      }
+      __syncwarp();
+    }
     int s = 0;
     uint32_t ph = 0;
     for (int t = t_begin; t < t_end; ++t)
@@ -190,11 +221,16 @@ __global__ void __launch_bounds__(kKnnThreads, 1) knn_gemm_kernel(const __grid_c
         __syncwarp();
         if (++s == a.stages) { s = 0; ph ^= 1; }
       }
-  } else if (warp == kKnnEpiWarps + 1) {
+  } else if (warp == EW + 1) {
     // ===== MMA issuer =====
     int s = 0;
     uint32_t ph = 0;
     const uint32_t b_base = smem_u32(sm_b);
+    const uint32_t a_base = smem_u32(sm_a);
+    if (kAT == 2) {
+      mbar_wait(bar_a, 0);
+      tc_fence_after();
+    }
     for (int t = t_begin; t < t_end; ++t) {
       const int it = t - t_begin;
       const int buf = it & 1;
@@ -205,9 +241,19 @@ __global__ void __launch_bounds__(kKnnThreads, 1) knn_gemm_kernel(const __grid_c
         tc_fence_after();
         if (elect_one_sync()) {
           const uint64_t b_desc = umma_desc_k_sw128(b_base + static_cast<uint32_t>(s) * kKnnBoxBytes);
+          if (kAT == 1) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k)
-            tc_mma_tf32_ts(tmem_acc + buf * kKnnTileN, tmem_a + j * 32 + k * 8, b_desc + 2 * k, a.idesc, (j > 0 || k > 0) ? 1u : 0u);
+            for (int k = 0; k < 4; ++k)
+              tc_mma_tf32_ts(tmem_acc + buf * kKnnTileN, tmem_a + j * 32 + k * 8, b_desc + 2 * k, a.idesc, (j > 0 || k > 0) ? 1u : 0u);
+          } else {
+#pragma unroll
+            for (int at = 0; at < 2; ++at) {
+              const uint64_t a_desc = umma_desc_k_sw128(a_base + static_cast<uint32_t>(at * a.nbox + j) * kKnnBoxBytes);
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                tc_mma_tf32_ss(tmem_acc + (at * 2 + buf) * kKnnTileN, a_desc + 2 * k, b_desc + 2 * k, a.idesc, (j > 0 || k > 0) ? 1u : 0u);
+            }
+          }
           tc_commit(&bar_empty[s]);
           if (j + 1 == a.nbox) tc_commit(&bar_acc_full[buf]);
         }
@@ -217,8 +263,9 @@ __global__ void __launch_bounds__(kKnnThreads, 1) knn_gemm_kernel(const __grid_c
     }
   } else {
     // ===== epilogue: thread = (anchor row, 64-column half of every tile) =====
-    const int row = threadIdx.x & (kTileM - 1);
-    const int half = threadIdx.x >> 7;
+    const int at = kAT == 2 ? (warp >> 2) & 1 : 0;            // which of the CTA's anchor tiles
+    const int row = at * kTileM + (warp & 3) * 32 + lane;     // anchor within the CTA
+    const int half = kAT == 2 ? warp >> 3 : warp >> 2;
     const uint32_t lane_base = static_cast<uint32_t>((warp & 3) * 32) << 16;
     const int32_t mylab = a.qlab[b0 + row];
     unsigned long long keys[kKnnC];
@@ -270,7 +317,7 @@ __global__ void __launch_bounds__(kKnnThreads, 1) knn_gemm_kernel(const __grid_c
       __syncwarp();
       mbar_wait(&bar_acc_full[buf], (it >> 1) & 1);
       tc_fence_after();
-      const uint32_t t_addr = tmem_acc + lane_base + buf * kKnnTileN + half * 64;
+      const uint32_t t_addr = tmem_acc + lane_base + (at * 2 + buf) * kKnnTileN + half * 64;
       const float* iv = my_side + buf * 128;
       const int32_t* lb = reinterpret_cast<const int32_t*>(my_side + buf * 128 + 64);
       const uint32_t j0 = static_cast<uint32_t>(t) * a.tile_mul * kKnnTileN + half * 64;
@@ -330,7 +377,7 @@ __global__ void __launch_bounds__(kKnnThreads, 1) knn_gemm_kernel(const __grid_c
     tc_fence_before();
   }
   __syncthreads();
-  if (warp == kKnnEpiWarps + 1) {
+  if (warp == EW + 1) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(a.tmem_cols) : "memory");
   }
@@ -792,20 +839,22 @@ __global__ void __launch_bounds__(kExactWarps * 32) knn_exact_kernel(
 
 struct KnnPlan {
   int64_t Bpad;
+  int32_t kat;                                            // anchor tiles per CTA of the GEMM pass (2 when the batch has more than one)
   int32_t atiles, tiles_total, slices, tiles_per_slice, nlists, stages, tmem_cols;
   int32_t tilesA, slicesA, tiles_per_sliceA, nlistsA;      // sampling pass over every kKnnSample-th tile (0 lists: skipped)
   size_t smem;
   bool tensor;              // the tcgen05 pass applies (D a multiple of 32, at most 128; n < 2^31)
   int32_t groupsE, slicesE;                               // exact scan of flagged anchors: 32-anchor groups x bank slices
   int64_t rows_per_sliceE;
-  size_t off_invn, off_qn, off_qlab, off_part, off_rej, off_partA, off_rejA, off_thr, off_flags, off_list, off_count, off_partE, total;
+  size_t off_invn, off_qn, off_qt, off_qlab, off_part, off_rej, off_partA, off_rejA, off_thr, off_flags, off_list, off_count, off_partE, total;
 };
 
 KnnPlan make_knn_plan(int64_t n, int64_t B, int32_t D) {
   KnnPlan p{};
-  p.atiles = static_cast<int32_t>((B + kTileM - 1) / kTileM);
+  p.kat = B > kTileM ? 2 : 1;
+  p.atiles = static_cast<int32_t>((B + kTileM * p.kat - 1) / (kTileM * p.kat));      // CTAs along the anchors
   if (p.atiles < 1) p.atiles = 1;
-  p.Bpad = static_cast<int64_t>(p.atiles) * kTileM;
+  p.Bpad = static_cast<int64_t>(p.atiles) * kTileM * p.kat;
   p.tensor = (D % 32 == 0) && D >= 32 && D <= 128 && n < (static_cast<int64_t>(1) << 31) - kKnnTileN;
   p.tiles_total = static_cast<int32_t>((n + kKnnTileN - 1) / kKnnTileN);
   int32_t slices = 148 / p.atiles;
@@ -825,13 +874,15 @@ KnnPlan make_knn_plan(int64_t n, int64_t B, int32_t D) {
   } else {
     p.tilesA = 0;
   }
-  p.stages = 8;
+  p.stages = p.kat == 2 ? 4 : 8;
   p.tmem_cols = 512;
-  p.smem = static_cast<size_t>(p.stages) * kKnnBoxBytes + kKnnEpiWarps * 2 * 128 * 4 + (2 * p.stages + 4) * 8 + 16 + 1024;
+  p.smem = (p.kat == 2 ? static_cast<size_t>(2 * (D / 32)) * kKnnBoxBytes : 0) + static_cast<size_t>(p.stages) * kKnnBoxBytes +
+           static_cast<size_t>(8 * p.kat) * 2 * 128 * 4 + (2 * p.stages + 5) * 8 + 16 + 1024;
   size_t off = 0;
   auto take = [&](size_t bytes) { const size_t o = off; off += (bytes + 255) / 256 * 256; return o; };
   p.off_invn = take(static_cast<size_t>(n) * sizeof(float));
   p.off_qn = take(static_cast<size_t>(p.Bpad) * D * sizeof(float));
+  p.off_qt = take(static_cast<size_t>(p.Bpad) * D * sizeof(float));
   p.off_qlab = take(static_cast<size_t>(p.Bpad) * sizeof(int32_t));
   p.off_part = take(static_cast<size_t>(p.nlists > 0 ? p.nlists : 1) * p.Bpad * kKnnC * sizeof(unsigned long long));
   p.off_rej = take(static_cast<size_t>(p.nlists > 0 ? p.nlists : 1) * p.Bpad * sizeof(float));
@@ -892,8 +943,8 @@ extern "C" int mml_crd_knn_positives(const float* bank, int64_t n, int32_t D, co
     if (rc != MML_OK) return rc;
   }
   {
-    knn_query_kernel<<<static_cast<unsigned>(p.Bpad), 32, 0, st>>>(bank, n, D, anchor_rows, anchor_labels, B, p.Bpad, qn, qlab,
-                                                                device_error_word());
+    knn_query_kernel<<<static_cast<unsigned>(p.Bpad), 32, 0, st>>>(bank, n, D, anchor_rows, anchor_labels, B, p.Bpad, qn,
+                                                                reinterpret_cast<float*>(ws + p.off_qt), qlab, device_error_word());
     const int rc = check_launch("knn_query_kernel");
     if (rc != MML_OK) return rc;
   }
@@ -908,14 +959,26 @@ extern "C" int mml_crd_knn_positives(const float* bank, int64_t n, int32_t D, co
     a.n = n; a.Bpad = p.Bpad; a.D = D; a.nbox = D / 32;
     a.stages = p.stages; a.tmem_cols = p.tmem_cols;
     a.idesc = make_idesc_tf32(kTileM, kKnnTileN);
-    MML_CUDA(cudaFuncSetAttribute(knn_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(p.smem)));
+    CUtensorMap tmap_q = tmap;
+    if (p.kat == 2) {
+      const int rcq = get_tensor_map_2d(reinterpret_cast<float*>(ws + p.off_qt), D, p.Bpad, 32, kTileM, true, &tmap_q);
+      if (rcq != MML_OK) return rcq;
+      MML_CUDA(cudaFuncSetAttribute(knn_gemm_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(p.smem)));
+    } else {
+      MML_CUDA(cudaFuncSetAttribute(knn_gemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(p.smem)));
+    }
+    auto launch_gemm = [&](int32_t slices) {
+      const dim3 grid(static_cast<unsigned>(p.atiles), static_cast<unsigned>(slices));
+      if (p.kat == 2) knn_gemm_kernel<2><<<grid, (8 * 2 + 2) * 32, p.smem, st>>>(tmap, tmap_q, a);
+      else knn_gemm_kernel<1><<<grid, (8 + 2) * 32, p.smem, st>>>(tmap, tmap_q, a);
+    };
     float* thr_init = nullptr;
     if (p.nlistsA > 0) {             // sampling pass: every 16th tile -> a proven floor for every anchor's lists
       unsigned long long* partA = reinterpret_cast<unsigned long long*>(ws + p.off_partA);
       thr_init = reinterpret_cast<float*>(ws + p.off_thr);
       a.part = partA; a.rej = reinterpret_cast<float*>(ws + p.off_rejA); a.thr_init = nullptr; a.tile_mul = kKnnSample;
       a.tiles_total = p.tilesA; a.tiles_per_slice = p.tiles_per_sliceA;
-      knn_gemm_kernel<<<dim3(static_cast<unsigned>(p.atiles), static_cast<unsigned>(p.slicesA)), kKnnThreads, p.smem, st>>>(tmap, a);
+      launch_gemm(p.slicesA);
       int rc = check_launch("knn_gemm_kernel (sampling pass)");
       if (rc != MML_OK) return rc;
       knn_threshold_kernel<<<static_cast<unsigned>((p.Bpad + 3) / 4), 128, 0, st>>>(partA, p.nlistsA, B, p.Bpad, thr_init);
@@ -924,7 +987,7 @@ extern "C" int mml_crd_knn_positives(const float* bank, int64_t n, int32_t D, co
     }
     a.part = part; a.rej = rej; a.thr_init = thr_init; a.tile_mul = 1;
     a.tiles_total = p.tiles_total; a.tiles_per_slice = p.tiles_per_slice;
-    knn_gemm_kernel<<<dim3(static_cast<unsigned>(p.atiles), static_cast<unsigned>(p.slices)), kKnnThreads, p.smem, st>>>(tmap, a);
+    launch_gemm(p.slices);
     const int rc = check_launch("knn_gemm_kernel");
     if (rc != MML_OK) return rc;
   }
