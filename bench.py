@@ -467,13 +467,13 @@ def knn_section(dev, peaks, cpu_anchors):
     rows = torch.randperm(n, device=dev, generator=gen)[:B]
     blab = labels[rows].long()
     for _ in range(3):
-        idx, sim, flags = crd_knn.knn_positives(bank, labels, rows, blab, P, return_flags=True)
+        idx, sim, flags = crd_knn.knn_positives(bank, labels, rows, blab, P, n_classes=3, return_flags=True)
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     iters = 20
     e0.record()
     for _ in range(iters):
-        crd_knn.knn_positives(bank, labels, rows, blab, P)
+        crd_knn.knn_positives(bank, labels, rows, blab, P, n_classes=3)
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / iters

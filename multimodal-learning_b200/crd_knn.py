@@ -24,9 +24,10 @@ from .crd_select import Embed  # single Linear + L2 (CRD_criterion_v10.py:316-32
 eps = 1e-7
 
 
-def knn_positives(bank, row_labels, anchor_rows, anchor_labels, num_pos, *, exact_only=False, return_flags=False):
+def knn_positives(bank, row_labels, anchor_rows, anchor_labels, num_pos, *, n_classes=0, exact_only=False, return_flags=False):
     """-> (neighbors int64 [B, P], similarity fp32 [B, P]) of CRD_criterion_v10.py:71-76 for one bank.
-    row_labels int32 [n] (class of every bank row), anchor_rows int64 [B] (the query's own row), anchor_labels int64 [B]."""
+    row_labels int32 [n] (class of every bank row), anchor_rows int64 [B] (the query's own row), anchor_labels int64 [B].
+    n_classes in 1..3 promises that every label lies in [0, n_classes) (faster class mask); 0 = arbitrary labels."""
     if not bank.is_cuda:
         raise RuntimeError("knn_positives runs on CUDA tensors only")
     n, D = bank.shape
@@ -43,7 +44,7 @@ def knn_positives(bank, row_labels, anchor_rows, anchor_labels, num_pos, *, exac
     out_sim = torch.empty((B, num_pos), dtype=torch.float32, device=dev)
     flags = torch.empty(B, dtype=torch.int32, device=dev) if return_flags else None
     _cabi.check(lib.mml_crd_knn_positives(
-        _cabi.dptr(bank, torch.float32), n, D, _cabi.dptr(row_labels, torch.int32), _cabi.dptr(anchor_rows, torch.int64),
+        _cabi.dptr(bank, torch.float32), n, D, _cabi.dptr(row_labels, torch.int32), int(n_classes), _cabi.dptr(anchor_rows, torch.int64),
         _cabi.dptr(anchor_labels, torch.int64), B, int(num_pos), int(bool(exact_only)), _cabi.dptr(out_idx), _cabi.dptr(out_sim),
         _cabi.dptr(flags), _cabi.dptr(ws), ws.numel(), _cabi.cur_stream(dev)), "mml_crd_knn_positives")
     return (out_idx, out_sim, flags) if return_flags else (out_idx, out_sim)
@@ -112,8 +113,9 @@ class ContrastMemory(_crd.ContrastMemory):
         if pos_extra == "neighbors":
             labels = self._labels_on(dev)
             anchors = idx[:, 0].contiguous()
-            nbr1, sim1 = knn_positives(self.memory_v1, labels, anchors, batch_label, num_pos)        # :69-76
-            nbr2, sim2 = knn_positives(self.memory_v2, labels, anchors, batch_label, num_pos)        # :108-113
+            ncls = len(self.class_idx) if len(self.class_idx) <= 3 else 0
+            nbr1, sim1 = knn_positives(self.memory_v1, labels, anchors, batch_label, num_pos, n_classes=ncls)    # :69-76
+            nbr2, sim2 = knn_positives(self.memory_v2, labels, anchors, batch_label, num_pos, n_classes=ncls)    # :108-113
             # one gather pass over [neighbours of bank 1 | neighbours of bank 2 | the K negatives]; out_v2 reads bank 1 at
             # columns [0, P) + negatives, out_v1 reads bank 2 at columns [P, 2P) + negatives (:77-79, :114-119)
             P = num_pos

@@ -123,7 +123,10 @@ struct KnnArgs {
 // 128-anchor MMAs (queries in shared memory, both operands by descriptor; all 512 TMEM columns are accumulators), which
 // halves the L2 -> SM stream per flop: one anchor tile per CTA pulls 64 KB per 1418 tensor cycles = 46 B/cycle/SM, above
 // what L2 delivers to every SM at once (r3c: 48 % tensor pipe).  16 epilogue warps instead of 8.
-template <int kAT>
+// kTab: at most 3 classes -> the class mask and 1/|row| become ONE multiplier per (class, bank row), tabulated per tile
+// (cm[c][j] = label[j] == c ? 1/|row j| : 0); a thread reads its anchor's class row: one FFMA per score instead of
+// multiply + compare + select.
+template <int kAT, bool kTab>
 __global__ void __launch_bounds__((8 * kAT + 2) * 32, 1) knn_gemm_kernel(const __grid_constant__ CUtensorMap tmap_bank,
                                                                          const __grid_constant__ CUtensorMap tmap_q, const KnnArgs a) {
   constexpr int EW = 8 * kAT;                    // epilogue warps; warp EW = TMA producer, warp EW + 1 = MMA issuer
@@ -131,8 +134,11 @@ __global__ void __launch_bounds__((8 * kAT + 2) * 32, 1) knn_gemm_kernel(const _
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* sm_a = smem;                                                              // kAT == 2: [2][nbox][16 KB] query boxes
   uint8_t* sm_b = smem + (kAT == 2 ? static_cast<size_t>(2 * a.nbox) * kKnnBoxBytes : 0);      // [stages][16 KB]
-  float* sm_side = reinterpret_cast<float*>(sm_b + static_cast<size_t>(a.stages) * kKnnBoxBytes);   // [EW warps][2][64 + 64]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sm_side + EW * 2 * 128);
+  constexpr int kRowS = 68;                      // class-row stride: 64 + 4 floats, so lanes of different classes hit different banks
+  constexpr int kSide = kTab ? 3 * kRowS + 4 : 128;   // floats per (warp, buffer): 3 skewed class rows, or 64 x 1/|row| + 64 labels
+  float* sm_side = reinterpret_cast<float*>(sm_b + static_cast<size_t>(a.stages) * kKnnBoxBytes);   // [EW warps][2][kSide]
+  float* sm_zero = sm_side + EW * 2 * kSide;     // 64 zeros: the class row of an anchor whose label matches no class
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sm_zero + 64);
   uint64_t* bar_full = bars;                     // [stages] bank box landed
   uint64_t* bar_empty = bars + a.stages;         // [stages] MMAs reading the box done
   uint64_t* bar_acc_full = bars + 2 * a.stages;  // [2] accumulator tile(s) complete
@@ -164,6 +170,7 @@ __global__ void __launch_bounds__((8 * kAT + 2) * 32, 1) knn_gemm_kernel(const _
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
+  if (threadIdx.x < 64) sm_zero[threadIdx.x] = 0.f;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -295,7 +302,7 @@ __global__ void __launch_bounds__((8 * kAT + 2) * 32, 1) knn_gemm_kernel(const _
 
     // side data of a tile (1/|row| and label of the warp's 64 bank rows): loaded one tile ahead, two + two values per lane,
     // into a warp-private shared slot -- no CTA-wide barrier couples the epilogue warps
-    float* my_side = sm_side + warp * (2 * 128);
+    float* my_side = sm_side + warp * (2 * kSide);
     auto load_side = [&](int t, uint32_t (&v)[4]) {
       v[0] = v[1] = 0u;
       v[2] = v[3] = 0xFFFFFFFEu;                            // -2: no such row
@@ -309,8 +316,15 @@ __global__ void __launch_bounds__((8 * kAT + 2) * 32, 1) knn_gemm_kernel(const _
     for (int t = t_begin; t < t_end; ++t) {
       const int it = t - t_begin;
       const int buf = it & 1;
-      {
-        uint32_t* d = reinterpret_cast<uint32_t*>(my_side + buf * 128);
+      if (kTab) {
+        float* d = my_side + buf * kSide;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          d[c * kRowS + lane] = static_cast<int32_t>(side[2]) == c ? __uint_as_float(side[0]) : 0.f;
+          d[c * kRowS + lane + 32] = static_cast<int32_t>(side[3]) == c ? __uint_as_float(side[1]) : 0.f;
+        }
+      } else {
+        uint32_t* d = reinterpret_cast<uint32_t*>(my_side + buf * kSide);
         d[lane] = side[0]; d[lane + 32] = side[1]; d[64 + lane] = side[2]; d[96 + lane] = side[3];
       }
       load_side(t + 1, side);
@@ -318,8 +332,8 @@ __global__ void __launch_bounds__((8 * kAT + 2) * 32, 1) knn_gemm_kernel(const _
       mbar_wait(&bar_acc_full[buf], (it >> 1) & 1);
       tc_fence_after();
       const uint32_t t_addr = tmem_acc + lane_base + (at * 2 + buf) * kKnnTileN + half * 64;
-      const float* iv = my_side + buf * 128;
-      const int32_t* lb = reinterpret_cast<const int32_t*>(my_side + buf * 128 + 64);
+      const float* iv = kTab ? ((mylab >= 0 && mylab < 3) ? my_side + buf * kSide + mylab * kRowS : sm_zero) : my_side + buf * kSide;
+      const int32_t* lb = reinterpret_cast<const int32_t*>(my_side + buf * kSide + 64);      // !kTab only
       const uint32_t j0 = static_cast<uint32_t>(t) * a.tile_mul * kKnnTileN + half * 64;
       const bool whole = (static_cast<int64_t>(t) * a.tile_mul + 1) * kKnnTileN <= a.n;      // uniform: only the last tile can hold rows >= n
       uint32_t accA[16], accB[16];
@@ -334,16 +348,30 @@ __global__ void __launch_bounds__((8 * kAT + 2) * 32, 1) knn_gemm_kernel(const _
         float m = -INFINITY;                                                                             \
         _Pragma("unroll") for (int u = 0; u < 16; u += 4) {                                              \
           const float4 i4 = *reinterpret_cast<const float4*>(iv + (Q) * 16 + u);                         \
-          const int4 l4 = *reinterpret_cast<const int4*>(lb + (Q) * 16 + u);                             \
-          sc[u + 0] = l4.x == mylab ? __uint_as_float(ACC[u + 0]) * i4.x + 0.0f : 0.0f;                  \
-          sc[u + 1] = l4.y == mylab ? __uint_as_float(ACC[u + 1]) * i4.y + 0.0f : 0.0f;                  \
-          sc[u + 2] = l4.z == mylab ? __uint_as_float(ACC[u + 2]) * i4.z + 0.0f : 0.0f;                  \
-          sc[u + 3] = l4.w == mylab ? __uint_as_float(ACC[u + 3]) * i4.w + 0.0f : 0.0f;                  \
-          if (!whole) {                                                                                  \
-            sc[u + 0] = l4.x == -2 ? -INFINITY : sc[u + 0];                                              \
-            sc[u + 1] = l4.y == -2 ? -INFINITY : sc[u + 1];                                              \
-            sc[u + 2] = l4.z == -2 ? -INFINITY : sc[u + 2];                                              \
-            sc[u + 3] = l4.w == -2 ? -INFINITY : sc[u + 3];                                              \
+          if (kTab) {                                                                                    \
+            sc[u + 0] = fmaf(__uint_as_float(ACC[u + 0]), i4.x, 0.0f);                                   \
+            sc[u + 1] = fmaf(__uint_as_float(ACC[u + 1]), i4.y, 0.0f);                                   \
+            sc[u + 2] = fmaf(__uint_as_float(ACC[u + 2]), i4.z, 0.0f);                                   \
+            sc[u + 3] = fmaf(__uint_as_float(ACC[u + 3]), i4.w, 0.0f);                                   \
+            if (!whole) {                                                                                \
+              const int64_t jj = static_cast<int64_t>(j0) + (Q) * 16 + u;                                \
+              sc[u + 0] = jj + 0 < a.n ? sc[u + 0] : -INFINITY;                                          \
+              sc[u + 1] = jj + 1 < a.n ? sc[u + 1] : -INFINITY;                                          \
+              sc[u + 2] = jj + 2 < a.n ? sc[u + 2] : -INFINITY;                                          \
+              sc[u + 3] = jj + 3 < a.n ? sc[u + 3] : -INFINITY;                                          \
+            }                                                                                            \
+          } else {                                                                                       \
+            const int4 l4 = *reinterpret_cast<const int4*>(lb + (Q) * 16 + u);                           \
+            sc[u + 0] = l4.x == mylab ? __uint_as_float(ACC[u + 0]) * i4.x + 0.0f : 0.0f;                \
+            sc[u + 1] = l4.y == mylab ? __uint_as_float(ACC[u + 1]) * i4.y + 0.0f : 0.0f;                \
+            sc[u + 2] = l4.z == mylab ? __uint_as_float(ACC[u + 2]) * i4.z + 0.0f : 0.0f;                \
+            sc[u + 3] = l4.w == mylab ? __uint_as_float(ACC[u + 3]) * i4.w + 0.0f : 0.0f;                \
+            if (!whole) {                                                                                \
+              sc[u + 0] = l4.x == -2 ? -INFINITY : sc[u + 0];                                            \
+              sc[u + 1] = l4.y == -2 ? -INFINITY : sc[u + 1];                                            \
+              sc[u + 2] = l4.z == -2 ? -INFINITY : sc[u + 2];                                            \
+              sc[u + 3] = l4.w == -2 ? -INFINITY : sc[u + 3];                                            \
+            }                                                                                            \
           }                                                                                              \
           m = fmaxf(fmaxf(m, fmaxf(sc[u + 0], sc[u + 1])), fmaxf(sc[u + 2], sc[u + 3]));                 \
         }                                                                                                \
@@ -849,7 +877,7 @@ struct KnnPlan {
   size_t off_invn, off_qn, off_qt, off_qlab, off_part, off_rej, off_partA, off_rejA, off_thr, off_flags, off_list, off_count, off_partE, total;
 };
 
-KnnPlan make_knn_plan(int64_t n, int64_t B, int32_t D) {
+KnnPlan make_knn_plan(int64_t n, int64_t B, int32_t D, int32_t n_classes = 0) {
   KnnPlan p{};
   p.kat = B > kTileM ? 2 : 1;
   p.atiles = static_cast<int32_t>((B + kTileM * p.kat - 1) / (kTileM * p.kat));      // CTAs along the anchors
@@ -877,7 +905,7 @@ KnnPlan make_knn_plan(int64_t n, int64_t B, int32_t D) {
   p.stages = p.kat == 2 ? 4 : 8;
   p.tmem_cols = 512;
   p.smem = (p.kat == 2 ? static_cast<size_t>(2 * (D / 32)) * kKnnBoxBytes : 0) + static_cast<size_t>(p.stages) * kKnnBoxBytes +
-           static_cast<size_t>(8 * p.kat) * 2 * 128 * 4 + (2 * p.stages + 5) * 8 + 16 + 1024;
+           static_cast<size_t>(8 * p.kat) * 2 * ((n_classes >= 1 && n_classes <= 3) ? 208 : 128) * 4 + 256 + (2 * p.stages + 5) * 8 + 16 + 1024;
   size_t off = 0;
   auto take = [&](size_t bytes) { const size_t o = off; off += (bytes + 255) / 256 * 256; return o; };
   p.off_invn = take(static_cast<size_t>(n) * sizeof(float));
@@ -916,8 +944,9 @@ extern "C" int64_t mml_crd_knn_workspace_bytes(int64_t n, int64_t B, int32_t D) 
   return static_cast<int64_t>(make_knn_plan(n, B, D).total);
 }
 
-extern "C" int mml_crd_knn_positives(const float* bank, int64_t n, int32_t D, const int32_t* row_labels, const int64_t* anchor_rows,
-                                     const int64_t* anchor_labels, int64_t B, int32_t P, int32_t exact_only, int64_t* out_idx,
+extern "C" int mml_crd_knn_positives(const float* bank, int64_t n, int32_t D, const int32_t* row_labels, int32_t n_classes,
+                                     const int64_t* anchor_rows, const int64_t* anchor_labels, int64_t B, int32_t P,
+                                     int32_t exact_only, int64_t* out_idx,
                                      float* out_sim, int32_t* flags_out, void* workspace, size_t workspace_bytes, void* stream) {
   MML_REQUIRE(bank && row_labels && anchor_rows && anchor_labels && out_idx && out_sim && workspace, MML_ERR_INVALID_ARG,
               "crd_knn_positives: null pointer");
@@ -926,7 +955,7 @@ extern "C" int mml_crd_knn_positives(const float* bank, int64_t n, int32_t D, co
   MML_REQUIRE(n < (static_cast<int64_t>(1) << 32) - 1, MML_ERR_UNSUPPORTED, "crd_knn_positives: at most 2^32 - 2 bank rows");
   MML_REQUIRE(aligned16(bank) && aligned16(workspace), MML_ERR_INVALID_ARG, "crd_knn_positives: bank / workspace must be 16-byte aligned");
   if (B == 0) return MML_OK;
-  const KnnPlan p = make_knn_plan(n, B, D);
+  const KnnPlan p = make_knn_plan(n, B, D, n_classes);
   MML_REQUIRE(workspace_bytes >= p.total, MML_ERR_INVALID_ARG, "crd_knn_positives: workspace too small (%zu < %zu)", workspace_bytes, p.total);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   uint8_t* ws = static_cast<uint8_t*>(workspace);
@@ -963,14 +992,19 @@ extern "C" int mml_crd_knn_positives(const float* bank, int64_t n, int32_t D, co
     if (p.kat == 2) {
       const int rcq = get_tensor_map_2d(reinterpret_cast<float*>(ws + p.off_qt), D, p.Bpad, 32, kTileM, true, &tmap_q);
       if (rcq != MML_OK) return rcq;
-      MML_CUDA(cudaFuncSetAttribute(knn_gemm_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(p.smem)));
-    } else {
-      MML_CUDA(cudaFuncSetAttribute(knn_gemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(p.smem)));
     }
+    const bool tab = n_classes >= 1 && n_classes <= 3;       // labels in [0, 3): tabulated class multipliers
+    const int smem_i = static_cast<int>(p.smem);
+    if (p.kat == 2 && tab) MML_CUDA(cudaFuncSetAttribute(knn_gemm_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_i));
+    if (p.kat == 2 && !tab) MML_CUDA(cudaFuncSetAttribute(knn_gemm_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_i));
+    if (p.kat == 1 && tab) MML_CUDA(cudaFuncSetAttribute(knn_gemm_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_i));
+    if (p.kat == 1 && !tab) MML_CUDA(cudaFuncSetAttribute(knn_gemm_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_i));
     auto launch_gemm = [&](int32_t slices) {
       const dim3 grid(static_cast<unsigned>(p.atiles), static_cast<unsigned>(slices));
-      if (p.kat == 2) knn_gemm_kernel<2><<<grid, (8 * 2 + 2) * 32, p.smem, st>>>(tmap, tmap_q, a);
-      else knn_gemm_kernel<1><<<grid, (8 + 2) * 32, p.smem, st>>>(tmap, tmap_q, a);
+      if (p.kat == 2 && tab) knn_gemm_kernel<2, true><<<grid, (8 * 2 + 2) * 32, p.smem, st>>>(tmap, tmap_q, a);
+      else if (p.kat == 2) knn_gemm_kernel<2, false><<<grid, (8 * 2 + 2) * 32, p.smem, st>>>(tmap, tmap_q, a);
+      else if (tab) knn_gemm_kernel<1, true><<<grid, (8 + 2) * 32, p.smem, st>>>(tmap, tmap_q, a);
+      else knn_gemm_kernel<1, false><<<grid, (8 + 2) * 32, p.smem, st>>>(tmap, tmap_q, a);
     };
     float* thr_init = nullptr;
     if (p.nlistsA > 0) {             // sampling pass: every 16th tile -> a proven floor for every anchor's lists

@@ -29,12 +29,12 @@ def run(n, D, B, P, iters, cpu_anchors, clustered=False):
     rows = torch.randperm(n, device=dev, generator=gen)[:B]
     blab = labels[rows].long()
     for _ in range(3):
-        idx, sim, flags = crd_knn.knn_positives(bank, labels, rows, blab, P, return_flags=True)
+        idx, sim, flags = crd_knn.knn_positives(bank, labels, rows, blab, P, n_classes=3, return_flags=True)
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(iters):
-        crd_knn.knn_positives(bank, labels, rows, blab, P)
+        crd_knn.knn_positives(bank, labels, rows, blab, P, n_classes=3)
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / iters

@@ -104,9 +104,9 @@ def test_knn_kernel_matches_oracle_bit_for_bit(pkg, ko, n, D, B, P, clustered):
     more_idx, more_sim = ko.knn_neighbors(bank.double(), rows, labels, blab, min(P + 1, n))      # float64: the exact ranking
     want_idx, want_sim = more_idx[:, :P], more_sim[:, :P]
     bd, ld = bank.to(DEV), labels.to(DEV, torch.int32)
-    for exact_only in (False, True):
-        idx, sim, flags = pkg.crd_knn.knn_positives(bd, ld, rows.to(DEV), blab.to(DEV), P, exact_only=exact_only,
-                                                    return_flags=True)
+    for exact_only, ncls in ((False, 3), (False, 0), (True, 0)):        # tabulated class mask / label compares / exact scan
+        idx, sim, flags = pkg.crd_knn.knn_positives(bd, ld, rows.to(DEV), blab.to(DEV), P, n_classes=ncls,
+                                                    exact_only=exact_only, return_flags=True)
         # neighbours whose float64 similarities differ by less than fp32 resolution may swap: compare through the values
         got = ko.masked_cosine(bank.double(), rows, labels, blab).gather(1, idx.cpu())
         assert (got - want_sim).abs().max() < 5e-6, (exact_only, (got - want_sim).abs().max())
@@ -132,7 +132,9 @@ def test_knn_fewer_same_class_rows_than_positives(pkg, ko):
     labels[[17, 250]] = 0
     rows, blab = torch.tensor([17, 250]), torch.tensor([0, 0])
     want_idx, want_sim = ko.knn_neighbors(bank, rows, labels, blab, P)
-    idx, sim = pkg.crd_knn.knn_positives(bank.to(DEV), labels.to(DEV, torch.int32), rows.to(DEV), blab.to(DEV), P)
+    for ncls in (2, 0):
+        idx, sim = pkg.crd_knn.knn_positives(bank.to(DEV), labels.to(DEV, torch.int32), rows.to(DEV), blab.to(DEV), P, n_classes=ncls)
+        assert torch.equal(idx.cpu(), want_idx) and (sim.cpu() - want_sim).abs().max() < 1e-6
     assert torch.equal(idx.cpu(), want_idx) and (sim.cpu() - want_sim).abs().max() < 1e-6
     assert idx[0, 0] == 17 and (sim[:, 2:] == 0).any()
 
@@ -158,7 +160,7 @@ def test_knn_at_config2_scale_sampled_vs_exact(pkg):
     labels = torch.randint(0, 3, (n,), device=DEV, generator=gen, dtype=torch.int32)
     rows = torch.randperm(n, device=DEV, generator=gen)[:B]
     blab = labels[rows].long()
-    idx, sim, flags = pkg.crd_knn.knn_positives(bank, labels, rows, blab, P, return_flags=True)
+    idx, sim, flags = pkg.crd_knn.knn_positives(bank, labels, rows, blab, P, n_classes=3, return_flags=True)
     assert int(flags.sum()) <= 8
     pick = torch.arange(0, B, 37, device=DEV)
     old = torch.backends.cuda.matmul.allow_tf32
