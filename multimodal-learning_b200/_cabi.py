@@ -34,7 +34,8 @@ _SIGNATURES = {
     "mml_crd_sort_columns": (ctypes.c_int, [_P, c_int64, c_int64, c_int64, c_int32, c_int32, c_int32, c_int64, _P, c_int64, _P]),
     "mml_crd_knn_max_positives": (c_int32, []),
     "mml_crd_knn_workspace_bytes": (c_int64, [c_int64, c_int64, c_int32]),
-    "mml_crd_knn_positives": (ctypes.c_int, [_P, c_int64, c_int32, _P, c_int32, _P, _P, c_int64, c_int32, c_int32, _P, _P, _P, _P,
+    "mml_crd_knn_inv_norms": (ctypes.c_int, [_P, c_int64, c_int32, _P, c_int64, _P, _P]),
+    "mml_crd_knn_positives": (ctypes.c_int, [_P, c_int64, c_int32, _P, _P, c_int32, _P, _P, c_int64, c_int32, c_int32, _P, _P, _P, _P,
                                              ctypes.c_size_t, _P]),
     "mml_crd_scores": (ctypes.c_int, [
         _P, _P, c_int64, c_int32, _P, _P, _P, c_int32, _P, c_int64, c_int64,
@@ -102,7 +103,7 @@ def declared_symbols():
     return sorted(_SIGNATURES)
 
 
-def lib() -> ctypes.CDLL:
+def lib():
     """Load (once) and return the C-ABI library; fail loudly if it is not built."""
     global _lib
     if _lib is None:
@@ -117,8 +118,37 @@ def lib() -> ctypes.CDLL:
             fn.argtypes = args
         if handle.mml_abi_version() != ABI_VERSION:
             raise RuntimeError("libmml_b200.so ABI version mismatch")
-        _lib = handle
+        _lib = _DeviceGuardedLib(handle)
     return _lib
+
+
+class _DeviceGuardedLib:
+    """The C ABI works on the CURRENT CUDA device (launches, cudaFuncSetAttribute, tensor maps, the error word).  Every
+    entry point that enqueues work takes the stream `cur_stream(tensor.device)` produced while its arguments are built;
+    that call notes the device, and the entry point then runs with that device current when it is not already (a module
+    on cuda:1 while the process' current device is cuda:0, as the reference's modules allow)."""
+
+    def __init__(self, handle):
+        self._handle = handle
+        self._fns = {}
+
+    def __getattr__(self, name):
+        fn = self._fns.get(name)
+        if fn is None:
+            raw = getattr(self._handle, name)
+
+            def fn(*args, _raw=raw):
+                dev = _pending_device[0]
+                _pending_device[0] = None
+                if dev is not None and dev != torch.cuda.current_device():
+                    with torch.cuda.device(dev):
+                        return _raw(*args)
+                return _raw(*args)
+            self._fns[name] = fn
+        return fn
+
+
+_pending_device = [None]          # device index noted by cur_stream() for the call being assembled
 
 
 def check(rc: int, what: str) -> None:
@@ -146,6 +176,8 @@ def hptr(t: torch.Tensor) -> c_void_p:
 
 
 def cur_stream(device) -> c_void_p:
+    device = torch.device(device)
+    _pending_device[0] = device.index if device.index is not None else torch.cuda.current_device()
     return c_void_p(torch.cuda.current_stream(device).cuda_stream)
 
 

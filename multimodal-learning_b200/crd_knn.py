@@ -24,10 +24,23 @@ from .crd_select import Embed  # single Linear + L2 (CRD_criterion_v10.py:316-32
 eps = 1e-7
 
 
-def knn_positives(bank, row_labels, anchor_rows, anchor_labels, num_pos, *, n_classes=0, exact_only=False, return_flags=False):
+def knn_inv_norms(bank, out=None, rows=None):
+    """1 / |row| of every bank row (rows None) or of the listed rows, written into `out` [n] fp32 (allocated when None)."""
+    n, D = bank.shape
+    if out is None:
+        out = torch.empty(n, dtype=torch.float32, device=bank.device)
+    _cabi.check(_cabi.lib().mml_crd_knn_inv_norms(
+        _cabi.dptr(bank, torch.float32), n, D, _cabi.dptr(rows, torch.int64) if rows is not None else None,
+        0 if rows is None else rows.numel(), _cabi.dptr(out, torch.float32), _cabi.cur_stream(bank.device)), "mml_crd_knn_inv_norms")
+    return out
+
+
+def knn_positives(bank, row_labels, anchor_rows, anchor_labels, num_pos, *, n_classes=0, inv_norms=None, exact_only=False,
+                  return_flags=False):
     """-> (neighbors int64 [B, P], similarity fp32 [B, P]) of CRD_criterion_v10.py:71-76 for one bank.
     row_labels int32 [n] (class of every bank row), anchor_rows int64 [B] (the query's own row), anchor_labels int64 [B].
-    n_classes in 1..3 promises that every label lies in [0, n_classes) (faster class mask); 0 = arbitrary labels."""
+    n_classes in 1..3 promises that every label lies in [0, n_classes) (faster class mask); 0 = arbitrary labels.
+    inv_norms: optional fp32 [n] = 1 / |row| kept up to date by the caller (`knn_inv_norms`); None = computed here."""
     if not bank.is_cuda:
         raise RuntimeError("knn_positives runs on CUDA tensors only")
     n, D = bank.shape
@@ -44,7 +57,8 @@ def knn_positives(bank, row_labels, anchor_rows, anchor_labels, num_pos, *, n_cl
     out_sim = torch.empty((B, num_pos), dtype=torch.float32, device=dev)
     flags = torch.empty(B, dtype=torch.int32, device=dev) if return_flags else None
     _cabi.check(lib.mml_crd_knn_positives(
-        _cabi.dptr(bank, torch.float32), n, D, _cabi.dptr(row_labels, torch.int32), int(n_classes), _cabi.dptr(anchor_rows, torch.int64),
+        _cabi.dptr(bank, torch.float32), n, D, _cabi.dptr(inv_norms, torch.float32) if inv_norms is not None else None,
+        _cabi.dptr(row_labels, torch.int32), int(n_classes), _cabi.dptr(anchor_rows, torch.int64),
         _cabi.dptr(anchor_labels, torch.int64), B, int(num_pos), int(bool(exact_only)), _cabi.dptr(out_idx), _cabi.dptr(out_sim),
         _cabi.dptr(flags), _cabi.dptr(ws), ws.numel(), _cabi.cur_stream(dev)), "mml_crd_knn_positives")
     return (out_idx, out_sim, flags) if return_flags else (out_idx, out_sim)
@@ -79,11 +93,34 @@ class ContrastMemory(_crd.ContrastMemory):
         self._refresh_scalars()
         self._pending = weakref.WeakSet()
         self._row_labels = None
+        self._inv_norms = None           # [2, n] 1/|row| of both banks: full pass once, then only the batch's rows per step
 
     def _apply(self, fn, *args, **kwargs):                  # no AliasMethod in this variant (idx is always supplied)
         out = nn.Module._apply(self, fn, *args, **kwargs)
         self._row_labels = None
+        self._inv_norms = None
         return out
+
+    def _load_from_state_dict(self, *args, **kwargs):
+        super()._load_from_state_dict(*args, **kwargs)
+        self._inv_norms = None
+
+    def invalidate_knn_cache(self):
+        """Call after writing the banks other than through `forward` (the cached row norms would be stale)."""
+        self._inv_norms = None
+
+    def _norms(self):
+        if self._inv_norms is None or self._inv_norms.device != self.memory_v1.device:
+            self._inv_norms = torch.empty((2, self.memory_v1.shape[0]), dtype=torch.float32, device=self.memory_v1.device)
+            knn_inv_norms(self.memory_v1, self._inv_norms[0])
+            knn_inv_norms(self.memory_v2, self._inv_norms[1])
+        return self._inv_norms
+
+    def _update(self, v1, v2, y):
+        super()._update(v1, v2, y)
+        if self._inv_norms is not None:                      # the rows the momentum update rewrote
+            knn_inv_norms(self.memory_v1, self._inv_norms[0], rows=y)
+            knn_inv_norms(self.memory_v2, self._inv_norms[1], rows=y)
 
     def _labels_on(self, device):
         if self._row_labels is None or self._row_labels.device != device:
@@ -114,8 +151,9 @@ class ContrastMemory(_crd.ContrastMemory):
             labels = self._labels_on(dev)
             anchors = idx[:, 0].contiguous()
             ncls = len(self.class_idx) if len(self.class_idx) <= 3 else 0
-            nbr1, sim1 = knn_positives(self.memory_v1, labels, anchors, batch_label, num_pos, n_classes=ncls)    # :69-76
-            nbr2, sim2 = knn_positives(self.memory_v2, labels, anchors, batch_label, num_pos, n_classes=ncls)    # :108-113
+            inv = self._norms()
+            nbr1, sim1 = knn_positives(self.memory_v1, labels, anchors, batch_label, num_pos, n_classes=ncls, inv_norms=inv[0])   # :69-76
+            nbr2, sim2 = knn_positives(self.memory_v2, labels, anchors, batch_label, num_pos, n_classes=ncls, inv_norms=inv[1])   # :108-113
             # one gather pass over [neighbours of bank 1 | neighbours of bank 2 | the K negatives]; out_v2 reads bank 1 at
             # columns [0, P) + negatives, out_v1 reads bank 2 at columns [P, 2P) + negatives (:77-79, :114-119)
             P = num_pos

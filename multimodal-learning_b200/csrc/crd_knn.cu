@@ -44,10 +44,15 @@ __device__ __forceinline__ unsigned long long knn_key(float s, uint32_t row) {
   return (static_cast<unsigned long long>(ord_bits(s)) << 32) | (0xFFFFFFFFu - row);
 }
 
-__global__ void knn_invnorm_kernel(const float* __restrict__ bank, int64_t n, int32_t D, float* __restrict__ invn) {
+// rows == NULL: every row of the bank; else the `count` listed rows (ids outside [0, n) are skipped)
+__global__ void knn_invnorm_kernel(const float* __restrict__ bank, int64_t n, int32_t D, const int64_t* __restrict__ rows,
+                                   int64_t count, float* __restrict__ invn) {
   // 8 lanes per row, 128-bit streaming loads (the gather kernels' row layout)
-  const int64_t row = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 3;
+  const int64_t item = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 3;
   const int sub = threadIdx.x & 7;
+  int64_t row = item;
+  if (rows != nullptr) row = item < count ? rows[item] : -1;
+  if (row < 0 || row >= n) row = n;                      // nothing to do (whole 8-lane group agrees)
   float acc = 0.f;
   if (row < n) {
     const float* p = bank + row * D;
@@ -944,9 +949,21 @@ extern "C" int64_t mml_crd_knn_workspace_bytes(int64_t n, int64_t B, int32_t D) 
   return static_cast<int64_t>(make_knn_plan(n, B, D).total);
 }
 
-extern "C" int mml_crd_knn_positives(const float* bank, int64_t n, int32_t D, const int32_t* row_labels, int32_t n_classes,
-                                     const int64_t* anchor_rows, const int64_t* anchor_labels, int64_t B, int32_t P,
-                                     int32_t exact_only, int64_t* out_idx,
+extern "C" int mml_crd_knn_inv_norms(const float* bank, int64_t n, int32_t D, const int64_t* rows, int64_t count, float* inv_norms,
+                                     void* stream) {
+  MML_REQUIRE(bank && inv_norms, MML_ERR_INVALID_ARG, "crd_knn_inv_norms: null pointer");
+  MML_REQUIRE(n >= 1 && D >= 4 && D % 4 == 0 && count >= 0, MML_ERR_INVALID_ARG, "crd_knn_inv_norms: bad sizes");
+  MML_REQUIRE(aligned16(bank), MML_ERR_INVALID_ARG, "crd_knn_inv_norms: bank must be 16-byte aligned");
+  const int64_t items = rows != nullptr ? count : n;
+  if (items == 0) return MML_OK;
+  knn_invnorm_kernel<<<static_cast<unsigned>((items * 8 + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(bank, n, D, rows, count,
+                                                                                                          inv_norms);
+  return check_launch("knn_invnorm_kernel");
+}
+
+extern "C" int mml_crd_knn_positives(const float* bank, int64_t n, int32_t D, const float* inv_norms, const int32_t* row_labels,
+                                     int32_t n_classes, const int64_t* anchor_rows, const int64_t* anchor_labels, int64_t B,
+                                     int32_t P, int32_t exact_only, int64_t* out_idx,
                                      float* out_sim, int32_t* flags_out, void* workspace, size_t workspace_bytes, void* stream) {
   MML_REQUIRE(bank && row_labels && anchor_rows && anchor_labels && out_idx && out_sim && workspace, MML_ERR_INVALID_ARG,
               "crd_knn_positives: null pointer");
@@ -959,15 +976,16 @@ extern "C" int mml_crd_knn_positives(const float* bank, int64_t n, int32_t D, co
   MML_REQUIRE(workspace_bytes >= p.total, MML_ERR_INVALID_ARG, "crd_knn_positives: workspace too small (%zu < %zu)", workspace_bytes, p.total);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   uint8_t* ws = static_cast<uint8_t*>(workspace);
-  float* invn = reinterpret_cast<float*>(ws + p.off_invn);
+  const float* invn = inv_norms != nullptr ? inv_norms : reinterpret_cast<float*>(ws + p.off_invn);
   float* qn = reinterpret_cast<float*>(ws + p.off_qn);
   int32_t* qlab = reinterpret_cast<int32_t*>(ws + p.off_qlab);
   unsigned long long* part = reinterpret_cast<unsigned long long*>(ws + p.off_part);
   int32_t* flags = flags_out != nullptr ? flags_out : reinterpret_cast<int32_t*>(ws + p.off_flags);
 
-  {
+  if (inv_norms == nullptr) {
     const int64_t threads = n * 8;
-    knn_invnorm_kernel<<<static_cast<unsigned>((threads + 255) / 256), 256, 0, st>>>(bank, n, D, invn);
+    knn_invnorm_kernel<<<static_cast<unsigned>((threads + 255) / 256), 256, 0, st>>>(bank, n, D, nullptr, 0,
+                                                                                     reinterpret_cast<float*>(ws + p.off_invn));
     const int rc = check_launch("knn_invnorm_kernel");
     if (rc != MML_OK) return rc;
   }

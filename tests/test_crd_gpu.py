@@ -490,3 +490,20 @@ def test_out_of_range_ids_are_flagged_not_dereferenced(pkg, golden):
     with pytest.raises(IndexError):
         pkg.check_device_errors()
     assert pkg.device_error_flags() == 0                         # the check cleared the flag
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_modules_work_on_a_device_that_is_not_current(pkg, golden):
+    """The reference's modules run wherever their tensors live; the C ABI acts on the current device, so the ctypes layer
+    switches to the tensors' device for the duration of a call (and back)."""
+    g = golden("crd_d128")
+    c = g.cfg
+    dev1 = torch.device("cuda", 1)
+    assert torch.cuda.current_device() == 0
+    mod = _make_module(pkg, c, g.state_dict("init.")).to(dev1)
+    p = "step0."
+    f_s = g.t(p + "f_s", dev1).requires_grad_(True)
+    loss = mod(f_s, g.t(p + "f_t", dev1), g.t(p + "idx", dev1), g.t(p + "contrast_idx", dev1))
+    loss.backward()
+    assert torch.cuda.current_device() == 0
+    assert rel_err(loss.reshape(-1), g.t(p + "loss")) < 1e-4 and rel_err(f_s.grad, g.t(p + "grad_f_s")) < 1e-4

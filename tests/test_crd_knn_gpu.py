@@ -120,6 +120,14 @@ def test_knn_kernel_matches_oracle_bit_for_bit(pkg, ko, n, D, B, P, clustered):
         else:
             assert int(flags.sum()) <= B // 10
     assert (idx[:, 0].cpu() == rows).all() or clustered                              # the best neighbour is the query itself
+    # caller-kept inverse norms (what the module does between steps): same rows, same similarities
+    inv = pkg.crd_knn.knn_inv_norms(bd)
+    assert rel_err(inv, 1.0 / bank.norm(dim=1)) < 1e-6
+    part = pkg.crd_knn.knn_inv_norms(bd, torch.zeros(n, device=DEV), rows=rows.to(DEV))
+    assert torch.equal(part[rows.to(DEV)], inv[rows.to(DEV)]) and int((part != 0).sum()) == B
+    idx2, sim2 = pkg.crd_knn.knn_positives(bd, ld, rows.to(DEV), blab.to(DEV), P, n_classes=3, inv_norms=inv)
+    idx3, sim3 = pkg.crd_knn.knn_positives(bd, ld, rows.to(DEV), blab.to(DEV), P, n_classes=3)
+    assert torch.equal(idx2, idx3) and torch.equal(sim2, sim3)
 
 
 def test_knn_fewer_same_class_rows_than_positives(pkg, ko):
