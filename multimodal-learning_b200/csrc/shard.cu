@@ -109,6 +109,125 @@ __global__ void __launch_bounds__(kRouteThreads) shard_route_strided_kernel(
   if (lane < world) counts[static_cast<int64_t>(lane) * plane + slot] = run[warp][lane];
 }
 
+// Blocked form of the same routing (identical output, slot by slot): one CTA of 128 threads per slot.
+//   1. the slot's ids are read COALESCED (all of a thread's loads in flight at once) and split into (owner, local id) in
+//      shared memory -- owner by a multiply-high with floor(2^32 / rows_per_rank) and a fix-up, not a division;
+//   2. thread t owns the kIpt consecutive entries t*kIpt.. : the stable position of an id inside its owner's run is
+//      (ids of that owner in earlier threads) + (earlier ids of that owner in this thread) -- per-thread counts in a
+//      shared [owner][thread] table, exclusive-scanned over the threads owner by owner, then used as cursors;
+//   3. ids are placed, in that order, into a shared staging buffer laid out run by run, and
+//   4. written out COALESCED, one run per owner.
+// Measured (scripts/bench_route.py, 1024 x 16385 ids): 105 us at world 2, 116 us at world 8 -- the same as the
+// warp-per-slot kernel above (108 us, serial match_any ranking).  Both are INSTRUCTION-bound, not memory-bound: ncu
+// counts 54 M warp instructions (92 per id) at 49 % issue utilisation against 31 us of HBM time; a first blocked version
+// with per-thread global loads / stores took 179 us, one with register-packed counters 191-241 us.
+template <int kIpt>
+__global__ void __launch_bounds__(kRouteThreads) shard_route_strided_blocked_kernel(
+    const int64_t* __restrict__ idx, int64_t B, int64_t cols, int32_t chunk_cols, int32_t chunks, int64_t rows_per_rank,
+    uint32_t rpr_magic, int32_t world, int32_t* __restrict__ counts, int32_t* __restrict__ out, uint32_t* __restrict__ err) {
+  constexpr int kN = kRouteThreads * kIpt;         // ids per slot
+  __shared__ __align__(16) uint8_t s_own[kN];
+  __shared__ int32_t s_loc[kRouteThreads * (kIpt + 1)];      // row stride kIpt + 1: conflict-free per-thread rows
+  __shared__ int32_t s_out[kN];
+  __shared__ uint16_t s_cnt[32 * kRouteThreads];   // [owner][thread]: counts, then exclusive prefixes (cursors)
+  __shared__ int32_t s_base[33];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int64_t slot = blockIdx.x;                 // = b * chunks + c
+  const int64_t b = slot / chunks;
+  const int c = static_cast<int>(slot % chunks);
+  const int64_t plane = B * chunks;
+  const int64_t k_begin = static_cast<int64_t>(c) * chunk_cols;
+  const int len = static_cast<int>(min(static_cast<int64_t>(chunk_cols), cols - k_begin));
+  const uint32_t rpr = static_cast<uint32_t>(rows_per_rank);
+  const uint64_t n_rows = static_cast<uint64_t>(rows_per_rank) * static_cast<uint64_t>(world);
+  const int64_t* src = idx + b * cols + k_begin;
+  for (int i = tid; i < world * kRouteThreads; i += kRouteThreads) s_cnt[i] = 0;
+  bool bad = false;
+  int64_t raw[kIpt];                               // all of the thread's loads in flight before the first use
+#pragma unroll
+  for (int j = 0; j < kIpt; ++j) {
+    const int i = j * kRouteThreads + tid;
+    raw[j] = __ldg(src + (i < len ? i : len - 1));
+  }
+#pragma unroll
+  for (int j = 0; j < kIpt; ++j) {
+    const int i = j * kRouteThreads + tid;
+    uint8_t o = 255;
+    int32_t l = 0;
+    if (i < len) {
+      const int64_t r64 = raw[j];
+      if (static_cast<uint64_t>(r64) >= n_rows) {
+        bad = true;                                // id outside the bank: flagged and dropped
+      } else {
+        const uint32_t row = static_cast<uint32_t>(r64);
+        uint32_t ow = __umulhi(row, rpr_magic);    // floor(row / rpr) or one less (magic = floor(2^32 / rpr))
+        uint32_t rem = row - ow * rpr;
+        if (rem >= rpr) { ++ow; rem -= rpr; }
+        if (rem >= rpr) { ++ow; rem -= rpr; }
+        o = static_cast<uint8_t>(ow);
+        l = static_cast<int32_t>(rem);
+      }
+    }
+    s_own[i] = o;
+    s_loc[(i / kIpt) * (kIpt + 1) + (i % kIpt)] = l;
+  }
+  if (bad) flag_device_error(err, MML_DEVERR_SHARD_OWNER);
+  __syncthreads();
+  // per-thread counts of its kIpt consecutive entries
+  uint8_t own[kIpt];
+#pragma unroll
+  for (int j = 0; j < kIpt; ++j) own[j] = s_own[tid * kIpt + j];
+#pragma unroll
+  for (int j = 0; j < kIpt; ++j)
+    if (own[j] != 255) s_cnt[own[j] * kRouteThreads + tid] += 1;      // only this thread touches column `tid`
+  __syncthreads();
+  // exclusive scan over the 128 threads, owner by owner: warp w takes owners w, w + 4, ...; a lane scans 4 threads' counts
+  for (int o = warp; o < world; o += kRouteWarps) {
+    uint16_t* row = s_cnt + o * kRouteThreads + lane * 4;
+    const uint32_t c0 = row[0], c1 = row[1], c2 = row[2], c3 = row[3];
+    uint32_t v = c0 + c1 + c2 + c3;
+    const uint32_t mine = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const uint32_t t = __shfl_up_sync(kFullMask, v, d);
+      if (lane >= d) v += t;
+    }
+    const uint32_t ex = v - mine;
+    row[0] = static_cast<uint16_t>(ex);
+    row[1] = static_cast<uint16_t>(ex + c0);
+    row[2] = static_cast<uint16_t>(ex + c0 + c1);
+    row[3] = static_cast<uint16_t>(ex + c0 + c1 + c2);
+    if (lane == 31) s_base[o + 1] = static_cast<int32_t>(v);          // the owner's total, turned into run starts below
+  }
+  __syncthreads();
+  if (tid == 0) {
+    int32_t acc = 0;
+    s_base[0] = 0;
+    for (int o = 0; o < world; ++o) {
+      acc += s_base[o + 1];
+      s_base[o + 1] = acc;
+    }
+  }
+  __syncthreads();
+  // place the ids, in order, into the staging buffer (run by run)
+#pragma unroll
+  for (int j = 0; j < kIpt; ++j) {
+    if (own[j] != 255) {
+      uint16_t* cur = s_cnt + own[j] * kRouteThreads + tid;
+      const int pos = s_base[own[j]] + *cur;
+      *cur += 1;
+      s_out[pos] = s_loc[tid * (kIpt + 1) + j];
+    }
+  }
+  __syncthreads();
+  for (int o = 0; o < world; ++o) {                // coalesced, one run per owner
+    const int r0 = s_base[o], r1 = s_base[o + 1];
+    int32_t* dst = out + (static_cast<int64_t>(o) * plane + slot) * chunk_cols;
+    for (int i = r0 + tid; i < r1; i += kRouteThreads) dst[i - r0] = s_out[i];
+  }
+  if (tid < world) counts[static_cast<int64_t>(tid) * plane + slot] = s_base[tid + 1] - s_base[tid];
+}
+
 int check(const int64_t* idx, int64_t B, int64_t cols, int32_t chunk_cols, int64_t rows_per_rank, int32_t world) {
   MML_REQUIRE(idx && B >= 0 && cols >= 1 && rows_per_rank >= 1, MML_ERR_INVALID_ARG, "shard_route: bad arguments");
   MML_REQUIRE(chunk_cols >= 32 && chunk_cols % 32 == 0, MML_ERR_INVALID_ARG, "shard_route: chunk_cols must be a multiple of 32");
@@ -160,8 +279,23 @@ extern "C" int mml_shard_route_strided(const int64_t* idx, int64_t B, int64_t co
   if (B == 0) return MML_OK;
   const int32_t chunks = static_cast<int32_t>((cols + chunk_cols - 1) / chunk_cols);
   const int64_t warps = B * chunks;
-  shard_route_strided_kernel<<<static_cast<unsigned>((warps + kRouteWarps - 1) / kRouteWarps), kRouteThreads, 0,
-                               static_cast<cudaStream_t>(stream)>>>(idx, B, cols, chunk_cols, chunks, rows_per_rank, world,
-                                                                    counts, ids_out, device_error_word());
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (chunk_cols % kRouteThreads == 0 && chunk_cols / kRouteThreads <= 16 && rows_per_rank >= 2) {
+    const unsigned grid = static_cast<unsigned>(warps);
+    const uint32_t magic = static_cast<uint32_t>((1ull << 32) / static_cast<uint64_t>(rows_per_rank));
+    switch (chunk_cols / kRouteThreads) {
+      case 16: shard_route_strided_blocked_kernel<16><<<grid, kRouteThreads, 0, st>>>(idx, B, cols, chunk_cols, chunks, rows_per_rank, magic, world, counts, ids_out, device_error_word()); break;
+      case 8: shard_route_strided_blocked_kernel<8><<<grid, kRouteThreads, 0, st>>>(idx, B, cols, chunk_cols, chunks, rows_per_rank, magic, world, counts, ids_out, device_error_word()); break;
+      case 4: shard_route_strided_blocked_kernel<4><<<grid, kRouteThreads, 0, st>>>(idx, B, cols, chunk_cols, chunks, rows_per_rank, magic, world, counts, ids_out, device_error_word()); break;
+      case 2: shard_route_strided_blocked_kernel<2><<<grid, kRouteThreads, 0, st>>>(idx, B, cols, chunk_cols, chunks, rows_per_rank, magic, world, counts, ids_out, device_error_word()); break;
+      case 1: shard_route_strided_blocked_kernel<1><<<grid, kRouteThreads, 0, st>>>(idx, B, cols, chunk_cols, chunks, rows_per_rank, magic, world, counts, ids_out, device_error_word()); break;
+      default:
+        shard_route_strided_kernel<<<static_cast<unsigned>((warps + kRouteWarps - 1) / kRouteWarps), kRouteThreads, 0, st>>>(
+            idx, B, cols, chunk_cols, chunks, rows_per_rank, world, counts, ids_out, device_error_word());
+    }
+    return check_launch("shard_route_strided_blocked_kernel");
+  }
+  shard_route_strided_kernel<<<static_cast<unsigned>((warps + kRouteWarps - 1) / kRouteWarps), kRouteThreads, 0, st>>>(
+      idx, B, cols, chunk_cols, chunks, rows_per_rank, world, counts, ids_out, device_error_word());
   return check_launch("shard_route_strided_kernel");
 }
