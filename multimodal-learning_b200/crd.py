@@ -452,9 +452,13 @@ class _L2NormFn(torch.autograd.Function):
         return gx
 
 
+_ALLOW_HOST_NORMALIZE = False      # set by tests/test_sharded_cpu.py only: the gloo choreography test runs the heads on the host
+
+
 class Normalize(nn.Module):
     """normalization layer (no epsilon, as the reference).  power=2 on a CUDA fp32 matrix runs as one fused kernel
-    (forward) / one (backward); any other use keeps the reference's op chain (host-side PyTorch)."""
+    (forward) / one (backward); other powers / ranks keep the reference's op chain on the GPU.  CUDA tensors only, like
+    every module of this package (the gloo CPU tests of the sharded choreography substitute their own backend)."""
 
     def __init__(self, power=2):
         super(Normalize, self).__init__()
@@ -463,5 +467,7 @@ class Normalize(nn.Module):
     def forward(self, x):
         if self.power == 2 and x.is_cuda and x.dtype == torch.float32 and x.dim() == 2:
             return _L2NormFn.apply(x)
+        if not x.is_cuda and not _ALLOW_HOST_NORMALIZE:
+            raise RuntimeError("Normalize runs on CUDA tensors only (no CPU fallback)")
         norm = x.pow(self.power).sum(1, keepdim=True).pow(1. / self.power)
         return x.div(norm)

@@ -87,6 +87,8 @@ def run(rank, world, backend, golden_name, port, result_path):
     else:
         dev = torch.device("cpu")
         dist.init_process_group("gloo", rank=rank, world_size=world)
+        import multimodal_learning_b200.crd as _crd_mod
+        _crd_mod._ALLOW_HOST_NORMALIZE = True      # host-logic test: the Embed heads run on CPU tensors here, nowhere else
     from conftest import Golden, rel_err
     from multimodal_learning_b200.sharded import ShardedCRDLoss
     g = Golden(golden_name)
