@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """compute-sanitizer target: every kernel family once, at small shapes.
 
-    compute-sanitizer --tool memcheck|racecheck|synccheck python scripts/sanitize_target.py [kron|crd|all]"""
+    compute-sanitizer --tool memcheck|racecheck|synccheck python scripts/sanitize_target.py [kron|crd|select|all]"""
 import os
 import sys
 import types
@@ -50,5 +50,47 @@ if what in ("crd", "all"):
     rows = samp(torch.arange(8, device=dev))
     torch.cuda.synchronize()
     print("sampler ok", tuple(rows.shape), flush=True)
+if what in ("select", "all"):
+    # selection variants: relation gaps, per-anchor sort (stage-by-stage and register-blocked), multi-positive loss
+    from multimodal_learning_b200 import _cabi, crd_knn, crd_select
+    for n_cols in (300, 2500):
+        diff = torch.randn(6, n_cols + 10, device=dev)
+        order = crd_select.sort_columns(diff, 5, n_cols, descending=True)
+        ref = torch.sort(diff[:, 5:5 + n_cols], dim=1, descending=True, stable=True)[1]
+        print("sort", n_cols, "ok", bool(torch.equal(order, ref)), flush=True)
+    opt = types.SimpleNamespace(s_dim=24, t_dim=24, feat_dim=64, nce_p=40, nce_p2=5, nce_k=200, nce_k2=64, nce_t=0.07, nce_m=0.5,
+                                select_pos_pairs=True, select_neg_pairs="True", sample_KD="False", select_pos_mode="hard")
+    sel = crd_select.CRDLoss(opt, 700).to(dev)
+    for step in range(2):
+        f_s = torch.randn(8, 24, device=dev, requires_grad=True)
+        idx = torch.randperm(700, device=dev)[:8]
+        cidx = torch.randint(0, 700, (8, 240), device=dev)
+        cidx[:, 0] = idx
+        sel(0.0, f_s, torch.randn(8, 24, device=dev), idx, cidx).backward()
+    torch.cuda.synchronize()
+    print("selection ok", flush=True)
+    # full-bank KNN positives: tensor pass (one and two anchor tiles per CTA, with and without the class table), the
+    # sampling pass (n >= 32768 rows), the exact scans
+    for n, D, B, ncls in ((3000, 128, 20, 3), (40000, 64, 150, 3), (2500, 96, 9, 0), (1500, 48, 7, 0)):
+        bank = torch.randn(n, D, device=dev)
+        labels = torch.randint(0, 3, (n,), device=dev, dtype=torch.int32)
+        rows = torch.randperm(n, device=dev)[:B]
+        for exact in (False, True):
+            nbr, sim, flags = crd_knn.knn_positives(bank, labels, rows, labels[rows].long(), 4, n_classes=ncls, exact_only=exact,
+                                                    return_flags=True)
+        torch.cuda.synchronize()
+        print("knn", n, D, B, "ok", int(flags.sum()), bool((nbr[:, 0] == rows).all()), flush=True)
+    # routing kernels (blocked and warp-per-slot) of the sharded bank, emulated world
+    lib = _cabi.lib()
+    for world, chunk in ((4, 2048), (3, 96)):
+        Bq, cols, rows_per = 5, 4500, 1000
+        cidx = torch.randint(0, rows_per * world, (Bq, cols), device=dev)
+        chunks = (cols + chunk - 1) // chunk
+        counts = torch.zeros(world * Bq * chunks, dtype=torch.int32, device=dev)
+        ids = torch.zeros(world * Bq * chunks * chunk, dtype=torch.int32, device=dev)
+        _cabi.check(lib.mml_shard_route_strided(_cabi.dptr(cidx, torch.int64), Bq, cols, chunk, rows_per, world, _cabi.dptr(counts),
+                                                _cabi.dptr(ids), _cabi.cur_stream(dev)), "route")
+        torch.cuda.synchronize()
+        print("route", world, chunk, "ok", int(counts.sum()) == Bq * cols, flush=True)
 pkg.check_device_errors()
 print("done", flush=True)
