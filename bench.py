@@ -794,6 +794,7 @@ def run_gpu_arm(args):
         step_device(i)
     timer = EventTimer()
     mode = "eager"
+    routing_mode = None
     captured_launches = None
     step_fn = step_device
     if not args.eager:
@@ -806,8 +807,16 @@ def run_gpu_arm(args):
                 crd_mod.KERNEL_TIMER = timer
                 timer.enabled = True
                 mark["l0"] = pkg._cabi.launch_count()
-            gstep = pkg.GraphedTrainStep(lambda a, b, c, d: mod(a, b, c, d), opt_params, g_optim, pool[0], grad_inputs=(0,),
-                                         warmup=3, n_buffers=len(pool), before_capture=before_capture)
+            if world > 1 and len(pool) % 2 == 0 and os.environ.get("MML_PREFETCH_ROUTING", "1") == "1":
+                # the next resident batch's indices are routed under this step's tail (ShardedCRDLoss next_contrast_idx)
+                gstep = pkg.GraphedTrainStep(
+                    lambda a, b, c, d, next_inputs=None: mod(a, b, c, d, next_contrast_idx=next_inputs[3]), opt_params, g_optim,
+                    pool[0], grad_inputs=(0,), warmup=3, n_buffers=len(pool), before_capture=before_capture, pass_next_inputs=True)
+                routing_mode = "prefetched: the next step's indices are routed under this step's tail"
+            else:
+                gstep = pkg.GraphedTrainStep(lambda a, b, c, d: mod(a, b, c, d), opt_params, g_optim, pool[0], grad_inputs=(0,),
+                                             warmup=3, n_buffers=len(pool), before_capture=before_capture)
+                routing_mode = "in step" if world > 1 else None
             timer.enabled = False
             crd_mod.KERNEL_TIMER = None
             captured_launches = (pkg._cabi.launch_count() - mark["l0"]) // len(pool)
@@ -998,8 +1007,12 @@ def run_gpu_arm(args):
         g5 = torch.Generator(device=dev).manual_seed(777 + rank)
         pool5 = [gen_inputs(c5, Bl5, c5["n"], g5, dev) for _ in range(2)]
         with contextlib.redirect_stdout(sys.stderr):
-            gs5 = pkg.GraphedTrainStep(lambda a, b, c, d: mod5(a, b, c, d), p5, o5, pool5[0], grad_inputs=(0,), warmup=3,
-                                       n_buffers=2)
+            if world > 1 and routing_mode is not None and routing_mode.startswith("prefetched"):
+                gs5 = pkg.GraphedTrainStep(lambda a, b, c, d, next_inputs=None: mod5(a, b, c, d, next_contrast_idx=next_inputs[3]),
+                                           p5, o5, pool5[0], grad_inputs=(0,), warmup=3, n_buffers=2, pass_next_inputs=True)
+            else:
+                gs5 = pkg.GraphedTrainStep(lambda a, b, c, d: mod5(a, b, c, d), p5, o5, pool5[0], grad_inputs=(0,), warmup=3,
+                                           n_buffers=2)
         for slot, entry in enumerate(pool5):
             for dst, src in zip(gs5.buffers(slot), entry):
                 dst.detach().copy_(src)
@@ -1069,6 +1082,8 @@ def run_gpu_arm(args):
                 "d2h_bytes_per_step": 4, "note": e2e_note, "eager_ms_per_step": e2e_eager_ms},
         "gpu_launches": launches, "clocks": clocks,
     }
+    if routing_mode is not None:
+        line["config"]["routing"] = routing_mode
     if e2e_device_idx is not None:
         line["e2e_device_idx"] = e2e_device_idx
     if e2e_i32 is not None:

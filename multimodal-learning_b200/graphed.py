@@ -29,6 +29,21 @@ import torch
 _bump = getattr(torch.autograd.graph, "increment_version", None)
 
 
+_END_OF_STEP = []
+
+
+def defer_to_end_of_step(fn):
+    """Run `fn()` after the optimizer step of the GraphedTrainStep that is executing / being captured (modules use it to
+    join side streams they forked for work that may overlap the backward pass: a capture has to see every forked stream
+    rejoin before it ends).  Outside a GraphedTrainStep the callbacks simply run at the next `run_deferred()`."""
+    _END_OF_STEP.append(fn)
+
+
+def run_deferred():
+    while _END_OF_STEP:
+        _END_OF_STEP.pop(0)()
+
+
 class GraphedTrainStep:
     """step = GraphedTrainStep(loss_fn, params, optimizer, example_inputs); loss = step(*inputs)
 
@@ -38,7 +53,11 @@ class GraphedTrainStep:
     stream) can overlap the replay of step i."""
 
     def __init__(self, loss_fn, params, optimizer, example_inputs, grad_inputs=(), warmup=3, n_buffers=1,
-                 before_capture=None):
+                 before_capture=None, pass_next_inputs=False):
+        """pass_next_inputs: call `loss_fn(*inputs, next_inputs=<static inputs of the slot replayed after this one>)` --
+        for losses that can start work on the next batch early (ShardedCRDLoss routes the next contrast_idx under this
+        step's tail).  Only meaningful with `replay()` over pre-filled buffers in round-robin order (an even n_buffers)."""
+        self.pass_next_inputs = bool(pass_next_inputs)
         self.params = [p for p in params]
         self.optimizer = optimizer
         self.loss_fn = loss_fn
@@ -57,8 +76,8 @@ class GraphedTrainStep:
                 for i in grad_inputs:
                     ins[i].requires_grad_(True)
                 self.static_in.append(ins)
-            for _ in range(max(1, warmup)):
-                self._eager(self.static_in[0])
+            for _ in range(max(1, warmup)):      # with pass_next_inputs: the LAST slot, so that slot 0 finds itself prefetched
+                self._eager(self.static_in[-1 if self.pass_next_inputs else 0])
         torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.synchronize(dev)
         if before_capture is not None:
@@ -74,9 +93,10 @@ class GraphedTrainStep:
             # ... and capture on the stream the warm-up ran on: AccumulateGrad nodes that outlive the warm-up keep its
             # stream, and autograd may not make another (let alone the legacy) stream wait on a capturing one
             with torch.cuda.graph(g, pool=pool, stream=side, capture_error_mode="thread_local"):
-                loss = self.loss_fn(*ins)
+                loss = self._loss(ins)
                 loss.backward()
                 self.optimizer.step()
+                run_deferred()
             pool = g.pool()
             self.graphs.append(g)
             self.static_loss.append(loss.detach())
@@ -85,10 +105,17 @@ class GraphedTrainStep:
     def _eager(self, ins):
         for p in self.params:
             p.grad = None
-        loss = self.loss_fn(*ins)
+        loss = self._loss(ins)
         loss.backward()
         self.optimizer.step()
+        run_deferred()
         return loss
+
+    def _loss(self, ins):
+        if not self.pass_next_inputs:
+            return self.loss_fn(*ins)
+        k = next(i for i, s in enumerate(self.static_in) if s is ins)
+        return self.loss_fn(*ins, next_inputs=self.static_in[(k + 1) % len(self.static_in)])
 
     def buffers(self, slot=None):
         """Static input tensors of a slot (default: the one the next call replays) -- copy into them yourself to skip

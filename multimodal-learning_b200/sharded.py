@@ -127,8 +127,9 @@ class CudaBackend:
 class PeerExchange:
     """One symmetric-memory arena per (B_local, cols, D) geometry.  Every rank allocates the same layout; peers'
     arenas are reachable through CUDA peer mappings (`buffer_ptrs`).  Regions:
-      ids  int32 [world][B_l][chunks][chunk]   routed local row ids, block o is read by owner o
-      cnt  int32 [world][B_l][chunks]          entries used in each slot
+      ids  int32 [2][world][B_l][chunks][chunk]   routed local row ids, block o is read by owner o; two buffers, so that the
+                                               next step's indices can be routed while this step's are still being read
+      cnt  int32 [2][world][B_l][chunks]          entries used in each slot
       V    float [2][2][B_g][D]                all-gathered embeddings v1|v2, double-buffered by step parity
       YP   int64 [2][2][B_g]                   all-gathered anchor ids | positive rows, double-buffered
       P    float [2][B_g][D] + tail[16]        this rank's partial dL/dv1|dL/dv2 and its 4 partial sums"""
@@ -144,9 +145,10 @@ class PeerExchange:
         al = lambda n: (n + 255) // 256 * 256
         block = B_local * self.chunks * self.chunk * 4
         cblock = B_local * self.chunks * 4
-        self.off_ids = 0
-        self.off_cnt = al(self.off_ids + self.world * block)
-        self.off_V = al(self.off_cnt + self.world * cblock)
+        self.off_ids = [0, al(self.world * block)]
+        self.off_cnt = [al(self.off_ids[1] + self.world * block), 0]
+        self.off_cnt[1] = al(self.off_cnt[0] + self.world * cblock)
+        self.off_V = al(self.off_cnt[1] + self.world * cblock)
         self.off_YP = al(self.off_V + 2 * 2 * Bg * D * 4)
         self.off_P = al(self.off_YP + 2 * 2 * Bg * 8)
         self.off_tail = self.off_P + 2 * Bg * D * 4
@@ -165,11 +167,14 @@ class PeerExchange:
         bases = [int(p) for p in self.handle.buffer_ptrs]
         P = ctypes.c_void_p
         self.base_ptrs = (P * self.world)(*bases)
-        self.ids_ptrs = (P * self.world)(*[b + self.off_ids + self.rank * block for b in bases])
-        self.cnt_ptrs = (P * self.world)(*[b + self.off_cnt + self.rank * cblock for b in bases])
         view = lambda off, nbytes, dt, shape: self.raw[off:off + nbytes].view(dt).view(shape)
-        self.ids = view(self.off_ids, self.world * block, torch.int32, (-1,))
-        self.counts = view(self.off_cnt, self.world * cblock, torch.int32, (self.world, B_local, self.chunks))
+        self._route_bufs = [
+            ((P * self.world)(*[b + self.off_ids[k] + self.rank * block for b in bases]),
+             (P * self.world)(*[b + self.off_cnt[k] + self.rank * cblock for b in bases]),
+             view(self.off_ids[k], self.world * block, torch.int32, (-1,)),
+             view(self.off_cnt[k], self.world * cblock, torch.int32, (self.world, B_local, self.chunks)))
+            for k in (0, 1)]
+        self.use_route_buffer(0)
         self.V = view(self.off_V, 2 * 2 * Bg * D * 4, torch.float32, (2, 2, Bg, D))
         self.YP = view(self.off_YP, 2 * 2 * Bg * 8, torch.int64, (2, 2, Bg))
         self.P = view(self.off_P, 2 * Bg * D * 4, torch.float32, (2, Bg, D))
@@ -178,6 +183,11 @@ class PeerExchange:
                   if self.grad_pad else None)
         self.step = 0
         self._c = ctypes
+
+    def use_route_buffer(self, k):
+        """Make routing buffer k the one the routing / gather calls of the current step work on."""
+        self.route_buf = k
+        self.ids_ptrs, self.cnt_ptrs, self.ids, self.counts = self._route_bufs[k]
 
     def push(self, v1, v2, idx, pos, buf):
         """all_gather by NVLink stores: my slices land in every rank's V / YP buffers of parity `buf`."""
@@ -334,6 +344,9 @@ class ShardedContrastMemory(nn.Module):
         self._peer = {}                  # (B_local, cols, device) -> PeerExchange
         self._side_stream = None         # routing runs here, under the Embed heads
         self._route_side = None          # set by route_ahead, consumed by _peer_step
+        self._prefetched = None          # (data_ptr, arena, routing buffer, stream) of a prefetched NEXT batch
+        self._routed_ptr = None          # data_ptr of the contrast_idx already routed for the current step
+        self._next_cidx = None           # next batch handed to forward(), routed right after this step's gather
         self.grad_floats = 0             # room for the data-parallel heads' flattened gradient in each arena
         p = torch.tensor([K, T, -1, -1, momentum])
         self._K, self._T, self._momentum = int(p[0].item()), p[1].item(), p[4].item()
@@ -408,6 +421,10 @@ class ShardedContrastMemory(nn.Module):
             return
         dev = cidx.device
         px = self.peer_arena(cidx.shape[0], cols, D, dev)
+        if self._claim_prefetched(px, cidx):
+            return                                  # routed during the previous step (`prefetch_routing`)
+        self._prefetched = None                     # whatever was prefetched is not this batch: its buffer is reused below
+        px.use_route_buffer(1 - px.route_buf)
         if self._side_stream is None:
             self._side_stream = torch.cuda.Stream(dev)
         side = self._side_stream
@@ -416,6 +433,47 @@ class ShardedContrastMemory(nn.Module):
             self.backend.route_strided(cidx, self.rows_per, self.world, px.chunk, px.counts, px.ids)
         cidx.record_stream(side)
         self._route_side = side
+        self._routed_ptr = cidx.data_ptr()
+
+    def _claim_prefetched(self, px, cidx):
+        """True when `cidx` is the tensor whose routing `prefetch_routing` started during the previous step: switch to
+        the buffer it was routed into and make the current stream wait for that routing."""
+        pre = self._prefetched
+        if pre is None or pre[0] != cidx.data_ptr() or pre[1] is not px:
+            return False
+        self._prefetched = None
+        px.use_route_buffer(pre[2])
+        if not torch.cuda.is_current_stream_capturing():      # replayed graphs are ordered by their launches: the routing was
+            torch.cuda.current_stream(cidx.device).wait_stream(pre[3])      # joined at the end of the previous captured step
+        self._routed_ptr = cidx.data_ptr()
+        return True
+
+    def prefetch_routing(self, next_cidx, D):
+        """Route the NEXT step's contrast_idx now, on a side stream, into the routing buffer this step does not use.
+        Called right after this step's gather has been enqueued: the routing kernel then runs under the post-gather
+        barrier (waiting for the slowest rank), the pull-reduce and the Embed heads' backward -- ~300 us of kernels that
+        leave most SMs idle -- instead of in front of the next gather (105 us, `profiles/r2_sharded_timeline_g2.txt`).
+        No peer reads the other buffer before the next step's pre-gather barrier, which this rank reaches only after
+        joining the side stream.  Inside a CUDA-graph capture the join is deferred to the end of the captured step
+        (`graphed.defer_to_end_of_step`)."""
+        cols = self._K + 1
+        if next_cidx is None or next_cidx.dim() != 2 or next_cidx.shape[1] != cols or not next_cidx.is_cuda:
+            return
+        dev = next_cidx.device
+        px = self.peer_arena(next_cidx.shape[0], cols, D, dev)
+        other = 1 - px.route_buf
+        _, _, ids, counts = px._route_bufs[other]
+        if self._side_stream is None:
+            self._side_stream = torch.cuda.Stream(dev)
+        side = self._side_stream
+        cur = torch.cuda.current_stream(dev)
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            self.backend.route_strided(next_cidx, self.rows_per, self.world, px.chunk, counts, ids)
+        next_cidx.record_stream(side)
+        self._prefetched = (next_cidx.data_ptr(), px, other, side)
+        from . import graphed as _graphed
+        _graphed.defer_to_end_of_step(lambda: torch.cuda.current_stream(dev).wait_stream(side))
 
     def _peer_step(self, v1, v2, idx, cidx, n_data):
         """Local embeddings in, loss (global batch) + local dL/dv out.  Exchanges: routed ids / counts are PULLED by
@@ -432,8 +490,11 @@ class ShardedContrastMemory(nn.Module):
         if self._route_side is not None:          # routed ahead of the Embed heads on a side stream (route_ahead): join it
             torch.cuda.current_stream(v1.device).wait_stream(self._route_side)
             self._route_side = None
-        else:
+        elif self._routed_ptr != cidx.data_ptr() and not self._claim_prefetched(px, cidx):
+            self._prefetched = None
+            px.use_route_buffer(1 - px.route_buf)
             be.route_strided(cidx, self.rows_per, self.world, px.chunk, px.counts, px.ids)
+        self._routed_ptr = None
         px.push(v1, v2, idx.contiguous(), cidx[:, 0].contiguous(), buf)
         px.handle.barrier(channel=0)                  # everyone's slots, counts and slices are in place
         V1, V2, Y, pos_rows = px.V[buf, 0], px.V[buf, 1], px.YP[buf, 0], px.YP[buf, 1]
@@ -451,6 +512,9 @@ class ShardedContrastMemory(nn.Module):
             self._z_ready = True
         be.fused_peer(self.memory_v1, self.memory_v2, V1, V2, px, pos_flag, self._T, self.params[2:4], n_data,
                       self._K, Bg, px.P[0], px.P[1], px.tail)
+        if self._next_cidx is not None:               # the caller knows the next batch already: route it under this step's tail
+            nxt, self._next_cidx = self._next_cidx, None
+            self.prefetch_routing(nxt, D)
         px.handle.barrier(channel=1)                  # every rank's partials are complete
         g1 = torch.empty(Bl, D, dtype=torch.float32, device=v1.device)
         g2 = torch.empty(Bl, D, dtype=torch.float32, device=v1.device)
@@ -547,8 +611,13 @@ class ShardedCRDLoss(nn.Module):
         return (torch.func.functional_call(self.embed_s, ps, (f_s,)),
                 torch.func.functional_call(self.embed_t, pt, (f_t,)))
 
-    def forward(self, f_s, f_t, idx, contrast_idx=None):
+    def forward(self, f_s, f_t, idx, contrast_idx=None, next_contrast_idx=None):
+        """next_contrast_idx (extension, peer transport): the contrast_idx of the NEXT call, if the caller already holds it on
+        the device (a prefetching loader does) -- its routing then runs under this step's tail instead of in front of the
+        next gather.  The next call must pass that same tensor as `contrast_idx`."""
         g, mem = self.group, self.contrast
+        from . import graphed as _graphed
+        _graphed.run_deferred()                     # joins left over by a previous step outside a GraphedTrainStep
         if contrast_idx is None:                    # CRD_criterion.py:37-39 on the local anchors
             if mem.multinomial is None:
                 mem.multinomial = AliasMethod(torch.ones(mem.nLem))
@@ -566,6 +635,7 @@ class ShardedCRDLoss(nn.Module):
                     mem.grad_floats = sum(p.numel() for p in self.parameters())
                     px = mem.peer_arena(idx.shape[0], mem._K + 1, self._feat_dim, f_s.device)
                     reducer = px.allreduce_sum
+                mem._next_cidx = next_contrast_idx.contiguous() if next_contrast_idx is not None else None
                 if os.environ.get("MML_ROUTE_AHEAD", "1") == "1":
                     mem.route_ahead(contrast_idx, self._feat_dim)
                 v1, v2 = self._heads(f_s, f_t, reducer)
