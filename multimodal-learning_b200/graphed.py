@@ -68,7 +68,7 @@ class GraphedTrainStep:
             if "capturable" in g and not g["capturable"]:
                 raise RuntimeError("optimizer must be constructed with capturable=True to be replayed from a CUDA graph")
         self.static_in, self.static_loss, self.graphs = [], [], []
-        side = torch.cuda.Stream(dev)
+        side = torch.cuda.Stream(dev, priority=-1)     # the step itself outranks side work its modules fork (e.g. routing of the next batch)
         side.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(side):
             for _ in range(n_buffers):

@@ -33,8 +33,12 @@ def main():
     optim = torch.optim.Adam(params, lr=2e-4, fused=True, capturable=True)
     gen = torch.Generator(device=dev).manual_seed(rank)
     pool = [bench.gen_inputs(cfg, cfg["B"], n, gen, dev) for _ in range(2)]
-    gstep = pkg.GraphedTrainStep(lambda a, b, c, d: mod(a, b, c, d), params, optim, pool[0], grad_inputs=(0,), warmup=3,
-                                 n_buffers=2)
+    if world > 1 and os.environ.get("MML_PREFETCH_ROUTING", "1") == "1":      # as bench.py: next step's indices routed early
+        gstep = pkg.GraphedTrainStep(lambda a, b, c, d, next_inputs=None: mod(a, b, c, d, next_contrast_idx=next_inputs[3]),
+                                     params, optim, pool[0], grad_inputs=(0,), warmup=3, n_buffers=2, pass_next_inputs=True)
+    else:
+        gstep = pkg.GraphedTrainStep(lambda a, b, c, d: mod(a, b, c, d), params, optim, pool[0], grad_inputs=(0,), warmup=3,
+                                     n_buffers=2)
     for slot, entry in enumerate(pool):
         for dst, src in zip(gstep.buffers(slot), entry):
             dst.detach().copy_(src)
