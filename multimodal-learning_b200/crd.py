@@ -21,6 +21,7 @@ What differs from the reference, on purpose:
 from __future__ import annotations
 
 import math
+import os
 import weakref
 
 import torch
@@ -352,6 +353,31 @@ class ContrastMemory(nn.Module):
 # --------------------------------------------------------------------------- #
 # CRDLoss / ContrastLoss / Embed / Normalize
 # --------------------------------------------------------------------------- #
+_HEAD_STREAMS = {}
+
+
+def embed_pair(embed_s, f_s, embed_t, f_t):
+    """The two Embed heads are independent chains of small GEMMs (each leaves most SMs idle): the teacher head runs on a
+    second stream beside the student head.  Autograd replays every backward node on the stream of its forward, so the two
+    backward chains (the longer half: dX, dW, bias reductions per layer) overlap as well -- forward and backward of the heads
+    cost about half the time, with bit-identical results.  Works inside a CUDA-graph capture (fork / join become graph
+    dependencies).  MML_HEADS_STREAMS=0 keeps them in line."""
+    if not (f_s.is_cuda and f_t.is_cuda) or os.environ.get("MML_HEADS_STREAMS", "1") != "1":
+        return embed_s(f_s), embed_t(f_t)
+    dev = f_t.device
+    side = _HEAD_STREAMS.get(dev)
+    if side is None:
+        side = _HEAD_STREAMS[dev] = torch.cuda.Stream(dev, priority=-1)
+    cur = torch.cuda.current_stream(dev)
+    side.wait_stream(cur)
+    with torch.cuda.stream(side):
+        v_t = embed_t(f_t)
+    v_s = embed_s(f_s)
+    cur.wait_stream(side)
+    v_t.record_stream(cur)
+    return v_s, v_t
+
+
 class CRDLoss(nn.Module):
     """CRD Loss function
     includes two symmetric parts:
@@ -381,8 +407,7 @@ class CRDLoss(nn.Module):
         contrast_idx: [batch_size, nce_k + 1] indices (column 0 = positive), or None to sample
         Returns the contrastive loss, shape [1].
         """
-        f_s = self.embed_s(f_s)
-        f_t = self.embed_t(f_t)
+        f_s, f_t = embed_pair(self.embed_s, f_s, self.embed_t, f_t)
         if self.criterion_s.n_data != self.criterion_t.n_data:
             out_s, out_t = self.contrast(f_s, f_t, idx, contrast_idx)
             return self.criterion_s(out_s) + self.criterion_t(out_t)

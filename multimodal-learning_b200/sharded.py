@@ -608,8 +608,8 @@ class ShardedCRDLoss(nn.Module):
         views = {k: v for (k, _), v in zip(named, routed)}
         ps = {k[len("embed_s."):]: v for k, v in views.items() if k.startswith("embed_s.")}
         pt = {k[len("embed_t."):]: v for k, v in views.items() if k.startswith("embed_t.")}
-        return (torch.func.functional_call(self.embed_s, ps, (f_s,)),
-                torch.func.functional_call(self.embed_t, pt, (f_t,)))
+        return _crd.embed_pair(lambda x: torch.func.functional_call(self.embed_s, ps, (x,)), f_s,
+                               lambda x: torch.func.functional_call(self.embed_t, pt, (x,)), f_t)
 
     def forward(self, f_s, f_t, idx, contrast_idx=None, next_contrast_idx=None):
         """next_contrast_idx (extension, peer transport): the contrast_idx of the NEXT call, if the caller already holds it on
