@@ -238,8 +238,7 @@ class CRDLoss(nn.Module):
 
     def forward(self, sample_weights, f_s, f_t, batch_label, idx, contrast_idx=None):
         """-> (loss, per-sample loss [batch_size])"""
-        f_s = self.embed_s(f_s)
-        f_t = self.embed_t(f_t)
+        f_s, f_t = _crd.embed_pair(self.embed_s, f_s, self.embed_t, f_t)      # the two heads on two streams
         if self.pos_extra == "neighbors":
             out_s, out_t, s_similarity, t_similarity = self.contrast(
                 self.num_pos, self.pos_extra, f_s, f_t, batch_label, idx, contrast_idx)

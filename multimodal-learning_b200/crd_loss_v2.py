@@ -6,6 +6,7 @@ from __future__ import annotations
 
 from torch import nn
 
+from . import crd as _crd
 from .crd import Normalize
 from .crd_select import ContrastLoss_v2, ContrastMemory_mono, ContrastMemory_v3, ContrastMemory_v4, Embed, eps  # noqa: F401
 
@@ -31,8 +32,7 @@ class CRDLoss(nn.Module):
 
     def forward(self, epoch, f_s, f_t, idx, contrast_idx=None):
         """f_s / f_t: [batch_size, s_dim / t_dim]; idx: [batch_size]; contrast_idx: [batch_size, nce_p + nce_k] or None."""
-        f_s = self.embed_s(f_s)
-        f_t = self.embed_t(f_t)
+        f_s, f_t = _crd.embed_pair(self.embed_s, f_s, self.embed_t, f_t)      # the two heads on two streams
         out_s, out_t = self.contrast(epoch, f_s, f_t, idx, contrast_idx, self.select_pos_mode)
         s_loss = self.criterion_s(out_s, self.P2)
         t_loss = self.criterion_t(out_t, self.P2)

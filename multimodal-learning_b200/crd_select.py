@@ -407,8 +407,7 @@ class CRDLoss(nn.Module):
         contrast_idx: [batch_size, nce_p + nce_k] (first nce_p columns positives, column 0 the anchor itself) or None
         Returns the contrastive loss: 0-dim (sample_KD "False") or [batch_size] (sample_KD "True").
         """
-        f_s = self.embed_s(f_s)
-        f_t = self.embed_t(f_t)
+        f_s, f_t = _crd.embed_pair(self.embed_s, f_s, self.embed_t, f_t)      # the two heads on two streams
         if self.criterion_s.sample_KD == "False" and self.criterion_s.n_data == self.criterion_t.n_data:
             return self.contrast.fused_nce_loss_v2(epoch, f_s, f_t, idx, contrast_idx, self.criterion_s.n_data,
                                                    self.select_pos_mode)
@@ -446,8 +445,7 @@ class weighted_CRDLoss(nn.Module):
         self.criterion_s = weighted_ContrastLoss(n_data)
 
     def forward(self, f_s, f_t, loss_s, loss_t, idx, contrast_idx=None):
-        f_s = self.embed_s(f_s)
-        f_t = self.embed_t(f_t)
+        f_s, f_t = _crd.embed_pair(self.embed_s, f_s, self.embed_t, f_t)      # the two heads on two streams
         out_s, out_t = self.contrast(f_s, f_t, idx, contrast_idx)
         s_weight = torch.where(loss_s > loss_t, 1.0, 0.0)
         t_weight = torch.where(loss_t > loss_s, 1.0, 0.0)
