@@ -8,6 +8,7 @@ from __future__ import annotations
 
 import ctypes
 import os
+import threading
 from ctypes import c_char_p, c_float, c_int32, c_int64, c_size_t, c_void_p
 
 import torch
@@ -138,8 +139,8 @@ class _DeviceGuardedLib:
             raw = getattr(self._handle, name)
 
             def fn(*args, _raw=raw):
-                dev = _pending_device[0]
-                _pending_device[0] = None
+                dev = getattr(_pending_device, "index", None)
+                _pending_device.index = None
                 if dev is not None and dev != torch.cuda.current_device():
                     with torch.cuda.device(dev):
                         return _raw(*args)
@@ -148,7 +149,7 @@ class _DeviceGuardedLib:
         return fn
 
 
-_pending_device = [None]          # device index noted by cur_stream() for the call being assembled
+_pending_device = threading.local()      # .index: device noted by cur_stream() for the call this thread is assembling
 
 
 def check(rc: int, what: str) -> None:
@@ -177,7 +178,7 @@ def hptr(t: torch.Tensor) -> c_void_p:
 
 def cur_stream(device) -> c_void_p:
     device = torch.device(device)
-    _pending_device[0] = device.index if device.index is not None else torch.cuda.current_device()
+    _pending_device.index = device.index if device.index is not None else torch.cuda.current_device()
     return c_void_p(torch.cuda.current_stream(device).cuda_stream)
 
 
