@@ -160,7 +160,6 @@ class ContrastMemory(_crd.ContrastMemory):
             cols = torch.cat((nbr1, nbr2, idx[:, 1:]), 1).contiguous()
             take1 = torch.cat((torch.arange(P, 2 * P, device=dev), torch.arange(2 * P, 2 * P + K, device=dev)))
             take2 = torch.cat((torch.arange(0, P, device=dev), torch.arange(2 * P, 2 * P + K, device=dev)))
-            banks = self
         elif pos_extra == "centers":
             c1 = self._class_centers(self.memory_v1, num_pos)
             c2 = self._class_centers(self.memory_v2, num_pos)
@@ -170,7 +169,6 @@ class ContrastMemory(_crd.ContrastMemory):
             others = torch.tensor([[c for c in range(n_cls) if c != k] for k in range(n_cls)], device=dev)    # :60-61
             center_cols = torch.cat((batch_label.view(B, 1), others.index_select(0, batch_label)), 1).contiguous()
             cols = idx
-            banks = None
         else:
             raise RuntimeError(f"pos_extra must be 'neighbors' or 'centers'; got {pos_extra!r}")   # reference: NameError later
 
