@@ -18,6 +18,7 @@ What runs where:
 from __future__ import annotations
 
 import math
+import os
 
 import torch
 import torch.nn as nn
@@ -45,6 +46,9 @@ def init_max_weights(module):
 # --------------------------------------------------------------------------- #
 # the Kronecker linear op
 # --------------------------------------------------------------------------- #
+_BRANCH_STREAMS = {}       # device -> side streams of the gated branches
+
+
 class KronLinearState:
     """Per-module cache: chunk table (device) and the packed TF32 copies of the weight, refreshed whenever the dense
     weight's version counter or storage changes.  Writes through `.data` (`init_max_weights`, `p.data.clamp_()`, EMA
@@ -365,6 +369,29 @@ class _GatedKronFusion(nn.Module):
             return getattr(self, f"linear_o{t}")(torch.sigmoid(z) * h)
         return getattr(self, f"linear_o{t}")(own)
 
+    def _branches(self, vecs, gates):
+        """The gated branches (fusion.py:41-54 / :99-121) are independent chains of small kernels: branch 1 stays on the
+        current stream, the others run beside it on side streams (and, by autograd's stream affinity, so do their backward
+        chains).  The Python call order -- hence every dropout's Philox offset and the RNG order of the reference -- is
+        unchanged, the results are bit-identical.  MML_FUSION_STREAMS=0 keeps the branches in line."""
+        dev = vecs[0].device
+        if dev.type != "cuda" or len(gates) < 2 or os.environ.get("MML_FUSION_STREAMS", "1") != "1":
+            return [self._branch(t, vecs, g) for t, g in enumerate(gates, start=1)]
+        sides = _BRANCH_STREAMS.get(dev)
+        if sides is None:
+            sides = _BRANCH_STREAMS[dev] = [torch.cuda.Stream(dev, priority=-1) for _ in range(2)]
+        cur = torch.cuda.current_stream(dev)
+        for s in sides[:len(gates) - 1]:
+            s.wait_stream(cur)                    # the inputs are ready; nothing of branch 1 is queued yet
+        outs = [self._branch(1, vecs, gates[0])]
+        for t in range(2, len(gates) + 1):
+            with torch.cuda.stream(sides[t - 2]):
+                outs.append(self._branch(t, vecs, gates[t - 1]))
+        for s, o in zip(sides, outs[1:]):
+            cur.wait_stream(s)
+            o.record_stream(cur)
+        return outs
+
     def _encode(self, enc, state, factors):
         """Linear(kron) [-> BatchNorm1d -> ReLU] -> Dropout of one Kronecker encoder (fusion.py:29-30 / :94).  In training mode
         the BatchNorm batch statistics come out of the Kronecker kernel's epilogue and one finisher kernel does
@@ -403,9 +430,7 @@ class BilinearFusion(_GatedKronFusion):
 
     def forward(self, vec1, vec2):
         vecs = [self.relu(vec1), self.relu(vec2)]                         # fusion.py:38-39
-        o1 = self._branch(1, vecs, self.gate1)
-        o2 = self._branch(2, vecs, self.gate2)
-        return self._fuse([o1, o2])
+        return self._fuse(self._branches(vecs, (self.gate1, self.gate2)))
 
 
 class PolynomialFusion(_GatedKronFusion):
@@ -427,8 +452,7 @@ class PolynomialFusion(_GatedKronFusion):
 
     def forward(self, vec1, vec2):
         vecs = [self.relu(vec1), self.relu(vec2)]
-        o1 = self._branch(1, vecs, self.gate1)
-        o2 = self._branch(2, vecs, self.gate2)
+        o1, o2 = self._branches(vecs, (self.gate1, self.gate2))
         lin2 = self.encoder2[0]
         out12 = self._encode(self.encoder1, self._kron, [o1, o2])
         if lin2.weight.shape[1] != (out12.shape[1] + 1) ** 2:          # the reference fails in F.linear the same way
@@ -460,10 +484,7 @@ class _TrilinearFusion(_GatedKronFusion):
 
     def forward(self, vec1, vec2, vec3):
         vecs = [vec1, vec2, vec3]
-        o1 = self._branch(1, vecs, self.gate1)
-        o2 = self._branch(2, vecs, self.gate2)
-        o3 = self._branch(3, vecs, self.gate3)
-        return self._fuse([o1, o2, o3])
+        return self._fuse(self._branches(vecs, (self.gate1, self.gate2, self.gate3)))
 
 
 class TrilinearFusion_A(_TrilinearFusion):
