@@ -132,6 +132,8 @@ int     mml_crd_sort_columns(const float* diff, int64_t B, int64_t ld, int64_t c
  * re-scored exactly in fp32, and anchors for which the TF32 error bound cannot prove the result are recomputed by an exact
  * scan (flags_out[B], optional, reports them; exact_only != 0 forces that scan for every anchor).
  * P <= mml_crd_knn_max_positives() (8).  The tcgen05 pass needs D % 32 == 0 and D <= 128; other D use the exact scan.
+ * queries: NULL (the query of anchor b is bank row anchor_rows[b], as in the reference), or explicit query vectors [B, D]
+ * (row-sharded bank: the anchor's own row may live on another rank; anchor_rows is then ignored).
  * inv_norms: NULL, or 1/|row| of every bank row kept by the caller (mml_crd_knn_inv_norms: all rows when rows == NULL, else
  * the listed ones -- e.g. the batch's rows after the momentum update), which saves the pass over the bank that computes them.
  * n_classes: when 1..3 every label must lie in [0, n_classes) and the class mask is tabulated per bank tile (faster);
@@ -141,7 +143,7 @@ int64_t mml_crd_knn_workspace_bytes(int64_t n_rows, int64_t B, int32_t D);
 int     mml_crd_knn_inv_norms(const float* bank, int64_t n_rows, int32_t D, const int64_t* rows, int64_t count,
                               float* inv_norms, void* stream);
 int     mml_crd_knn_positives(const float* bank, int64_t n_rows, int32_t D, const float* inv_norms,
-                              const int32_t* row_labels, int32_t n_classes, const int64_t* anchor_rows, const int64_t* anchor_labels, int64_t B, int32_t P,
+                              const int32_t* row_labels, int32_t n_classes, const int64_t* anchor_rows, const float* queries, const int64_t* anchor_labels, int64_t B, int32_t P,
                               int32_t exact_only, int64_t* out_idx, float* out_sim, int32_t* flags_out,
                               void* workspace, size_t workspace_bytes, void* stream);
 

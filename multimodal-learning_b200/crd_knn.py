@@ -35,16 +35,17 @@ def knn_inv_norms(bank, out=None, rows=None):
     return out
 
 
-def knn_positives(bank, row_labels, anchor_rows, anchor_labels, num_pos, *, n_classes=0, inv_norms=None, exact_only=False,
-                  return_flags=False):
+def knn_positives(bank, row_labels, anchor_rows, anchor_labels, num_pos, *, n_classes=0, inv_norms=None, queries=None,
+                  exact_only=False, return_flags=False):
     """-> (neighbors int64 [B, P], similarity fp32 [B, P]) of CRD_criterion_v10.py:71-76 for one bank.
     row_labels int32 [n] (class of every bank row), anchor_rows int64 [B] (the query's own row), anchor_labels int64 [B].
     n_classes in 1..3 promises that every label lies in [0, n_classes) (faster class mask); 0 = arbitrary labels.
-    inv_norms: optional fp32 [n] = 1 / |row| kept up to date by the caller (`knn_inv_norms`); None = computed here."""
+    inv_norms: optional fp32 [n] = 1 / |row| kept up to date by the caller (`knn_inv_norms`); None = computed here.
+    queries: optional fp32 [B, D] explicit query vectors (then `anchor_rows` may be None): the sharded bank's case."""
     if not bank.is_cuda:
         raise RuntimeError("knn_positives runs on CUDA tensors only")
     n, D = bank.shape
-    B = anchor_rows.numel()
+    B = anchor_rows.numel() if queries is None else queries.shape[0]
     dev = bank.device
     lib = _cabi.lib()
     if num_pos > lib.mml_crd_knn_max_positives():
@@ -58,10 +59,54 @@ def knn_positives(bank, row_labels, anchor_rows, anchor_labels, num_pos, *, n_cl
     flags = torch.empty(B, dtype=torch.int32, device=dev) if return_flags else None
     _cabi.check(lib.mml_crd_knn_positives(
         _cabi.dptr(bank, torch.float32), n, D, _cabi.dptr(inv_norms, torch.float32) if inv_norms is not None else None,
-        _cabi.dptr(row_labels, torch.int32), int(n_classes), _cabi.dptr(anchor_rows, torch.int64),
+        _cabi.dptr(row_labels, torch.int32), int(n_classes), _cabi.dptr(anchor_rows, torch.int64) if anchor_rows is not None else None,
+        _cabi.dptr(queries, torch.float32) if queries is not None else None,
         _cabi.dptr(anchor_labels, torch.int64), B, int(num_pos), int(bool(exact_only)), _cabi.dptr(out_idx), _cabi.dptr(out_sim),
         _cabi.dptr(flags), _cabi.dptr(ws), ws.numel(), _cabi.cur_stream(dev)), "mml_crd_knn_positives")
     return (out_idx, out_sim, flags) if return_flags else (out_idx, out_sim)
+
+
+def sharded_knn_positives(bank_local, row_begin, row_labels_local, anchor_rows, anchor_labels, num_pos, *, group=None,
+                          n_classes=0, inv_norms=None):
+    """`knn_positives` over a ROW-SHARDED bank ("over the sharded bank"): this rank holds rows
+    [row_begin, row_begin + n_local) and `row_labels_local` for them; `anchor_rows` int64 [B_local] are GLOBAL row ids of this
+    rank's anchors (same B_local on every rank), `anchor_labels` their classes.  -> (neighbours as GLOBAL row ids
+    [B_local, P], similarities [B_local, P]), identical to the single-bank result.
+    Exchange: anchors' ids / labels all-gathered (8 B each), their query rows supplied by whichever rank owns them (one
+    all_reduce of [B_global, D]), every rank's exact local top-P per global anchor all-gathered (12 B per candidate), merged
+    by the per-anchor sort kernel (score descending; ties: lower rank = lower rows first, rows ascending inside a rank).
+    Bank rows never cross the wire."""
+    import torch.distributed as dist
+    from .crd_select import sort_columns
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    n_local, D = bank_local.shape
+    dev = bank_local.device
+    Bl = anchor_rows.numel()
+    rows_all = torch.empty(world * Bl, dtype=torch.int64, device=dev)
+    labs_all = torch.empty(world * Bl, dtype=torch.int64, device=dev)
+    dist.all_gather_into_tensor(rows_all, anchor_rows.contiguous(), group=group)
+    dist.all_gather_into_tensor(labs_all, anchor_labels.contiguous(), group=group)
+    mine = (rows_all >= row_begin) & (rows_all < row_begin + n_local)
+    Q = torch.zeros(world * Bl, D, dtype=torch.float32, device=dev)
+    Q[mine] = bank_local.index_select(0, rows_all[mine] - row_begin)
+    dist.all_reduce(Q, group=group)
+    P_loc = min(int(num_pos), n_local)
+    idx, sim = knn_positives(bank_local, row_labels_local, None, labs_all, P_loc, n_classes=n_classes, inv_norms=inv_norms, queries=Q)
+    if P_loc < num_pos:                               # a shard smaller than num_pos: pad with candidates that never win
+        pad = num_pos - P_loc
+        idx = torch.cat((idx, idx.new_full((idx.shape[0], pad), -1)), 1)
+        sim = torch.cat((sim, sim.new_full((sim.shape[0], pad), float("-inf"))), 1)
+    idx = torch.where(idx >= 0, idx + row_begin, idx)
+    P = int(num_pos)
+    all_idx = torch.empty(world, world * Bl, P, dtype=torch.int64, device=dev)
+    all_sim = torch.empty(world, world * Bl, P, dtype=torch.float32, device=dev)
+    dist.all_gather_into_tensor(all_idx, idx.contiguous(), group=group)
+    dist.all_gather_into_tensor(all_sim, sim.contiguous(), group=group)
+    sl = slice(rank * Bl, (rank + 1) * Bl)
+    cs = all_sim[:, sl].permute(1, 0, 2).reshape(Bl, world * P).contiguous()
+    ci = all_idx[:, sl].permute(1, 0, 2).reshape(Bl, world * P).contiguous()
+    order = sort_columns(cs, 0, world * P, descending=True, first=P)
+    return ci.gather(1, order), cs.gather(1, order)
 
 
 class _CenterBanks:

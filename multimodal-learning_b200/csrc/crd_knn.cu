@@ -67,8 +67,10 @@ __global__ void knn_invnorm_kernel(const float* __restrict__ bank, int64_t n, in
   if (row < n && sub == 0) invn[row] = acc > 0.f ? 1.0f / sqrtf(acc) : 0.f;      // sklearn leaves all-zero rows at zero
 }
 
+// queries == NULL: the query of anchor b is row rows[b] of the bank (the reference's case); else queries[b] (the sharded bank:
+// an anchor's own row may live on another rank)
 __global__ void knn_query_kernel(const float* __restrict__ bank, int64_t n, int32_t D, const int64_t* __restrict__ rows,
-                                 const int64_t* __restrict__ labels_in, int64_t B, int64_t Bpad, float* __restrict__ qn,
+                                 const float* __restrict__ queries, const int64_t* __restrict__ labels_in, int64_t B, int64_t Bpad, float* __restrict__ qn,
                                  float* __restrict__ qt, int32_t* __restrict__ qlab, uint32_t* err) {
   const int64_t b = blockIdx.x;
   const int lane = threadIdx.x;              // 32 threads
@@ -77,21 +79,25 @@ __global__ void knn_query_kernel(const float* __restrict__ bank, int64_t n, int3
     if (lane == 0) qlab[b] = -1;
     return;
   }
-  int64_t r = rows[b];
-  if (r < 0 || r >= n) {
-    if (lane == 0) flag_device_error(err, MML_DEVERR_CRD_INDEX);
-    r = r < 0 ? 0 : n - 1;
+  const float* src = queries != nullptr ? queries + b * D : nullptr;
+  if (src == nullptr) {
+    int64_t r = rows[b];
+    if (r < 0 || r >= n) {
+      if (lane == 0) flag_device_error(err, MML_DEVERR_CRD_INDEX);
+      r = r < 0 ? 0 : n - 1;
+    }
+    src = bank + r * D;
   }
   float acc = 0.f;
   for (int c = lane; c < D; c += 32) {
-    const float v = bank[r * D + c];
+    const float v = src[c];
     acc += v * v;
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(kFullMask, acc, o);
   const float norm = sqrtf(acc);
   for (int c = lane; c < D; c += 32) {
-    const float v = norm > 0.f ? bank[r * D + c] / norm : 0.f;
+    const float v = norm > 0.f ? src[c] / norm : 0.f;
     qn[b * D + c] = v;                                                               // exact: re-scoring
     qt[b * D + c] = __uint_as_float((__float_as_uint(v) + 0x1000u) & 0xFFFFE000u);   // nearest TF32: the descriptor-fed A operand
   }
@@ -971,11 +977,12 @@ extern "C" int mml_crd_knn_inv_norms(const float* bank, int64_t n, int32_t D, co
 }
 
 extern "C" int mml_crd_knn_positives(const float* bank, int64_t n, int32_t D, const float* inv_norms, const int32_t* row_labels,
-                                     int32_t n_classes, const int64_t* anchor_rows, const int64_t* anchor_labels, int64_t B,
+                                     int32_t n_classes, const int64_t* anchor_rows, const float* queries,
+                                     const int64_t* anchor_labels, int64_t B,
                                      int32_t P, int32_t exact_only, int64_t* out_idx,
                                      float* out_sim, int32_t* flags_out, void* workspace, size_t workspace_bytes, void* stream) {
-  MML_REQUIRE(bank && row_labels && anchor_rows && anchor_labels && out_idx && out_sim && workspace, MML_ERR_INVALID_ARG,
-              "crd_knn_positives: null pointer");
+  MML_REQUIRE(bank && row_labels && (anchor_rows || queries) && anchor_labels && out_idx && out_sim && workspace,
+              MML_ERR_INVALID_ARG, "crd_knn_positives: null pointer");
   MML_REQUIRE(n >= 1 && B >= 0 && D >= 4 && D % 4 == 0 && D <= 1024, MML_ERR_INVALID_ARG, "crd_knn_positives: bad sizes");
   MML_REQUIRE(P >= 1 && P <= kKnnC && P <= n, MML_ERR_UNSUPPORTED, "crd_knn_positives: 1 <= num_pos <= %d supported (got %d)", kKnnC, P);
   MML_REQUIRE(n < (static_cast<int64_t>(1) << 32) - 1, MML_ERR_UNSUPPORTED, "crd_knn_positives: at most 2^32 - 2 bank rows");
@@ -999,7 +1006,7 @@ extern "C" int mml_crd_knn_positives(const float* bank, int64_t n, int32_t D, co
     if (rc != MML_OK) return rc;
   }
   {
-    knn_query_kernel<<<static_cast<unsigned>(p.Bpad), 32, 0, st>>>(bank, n, D, anchor_rows, anchor_labels, B, p.Bpad, qn,
+    knn_query_kernel<<<static_cast<unsigned>(p.Bpad), 32, 0, st>>>(bank, n, D, anchor_rows, queries, anchor_labels, B, p.Bpad, qn,
                                                                 reinterpret_cast<float*>(ws + p.off_qt), qlab, device_error_word());
     const int rc = check_launch("knn_query_kernel");
     if (rc != MML_OK) return rc;

@@ -128,6 +128,9 @@ def test_knn_kernel_matches_oracle_bit_for_bit(pkg, ko, n, D, B, P, clustered):
     idx2, sim2 = pkg.crd_knn.knn_positives(bd, ld, rows.to(DEV), blab.to(DEV), P, n_classes=3, inv_norms=inv)
     idx3, sim3 = pkg.crd_knn.knn_positives(bd, ld, rows.to(DEV), blab.to(DEV), P, n_classes=3)
     assert torch.equal(idx2, idx3) and torch.equal(sim2, sim3)
+    # explicit query vectors (the sharded bank's case) == the bank's own rows
+    idx4, sim4 = pkg.crd_knn.knn_positives(bd, ld, None, blab.to(DEV), P, n_classes=3, queries=bd[rows.to(DEV)].contiguous())
+    assert torch.equal(idx4, idx3) and torch.equal(sim4, sim3)
 
 
 def test_knn_fewer_same_class_rows_than_positives(pkg, ko):

@@ -41,3 +41,17 @@ def test_sharded_step_replayed_from_cuda_graph_equals_eager(tmp_path):
                         str(out)], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
     assert out.read_text().startswith("ok")
+
+
+def test_sharded_knn_positives_equal_single_bank(tmp_path):
+    """N4 over the sharded bank: per-shard exact top-P + candidate exchange == `knn_positives` over the whole bank."""
+    import torch
+    world = min(torch.cuda.device_count(), 4)
+    if world < 2:
+        pytest.skip("needs >= 2 GPUs")
+    out = tmp_path / "res.txt"
+    port = 29800 + os.getpid() % 90
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "_sharded_knn_worker.py"), str(world), str(port), str(out)],
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+    assert out.read_text().startswith("ok")
