@@ -147,6 +147,27 @@ int     mml_crd_knn_positives(const float* bank, int64_t n_rows, int32_t D, cons
                               int32_t exact_only, int64_t* out_idx, float* out_sim, int32_t* flags_out,
                               void* workspace, size_t workspace_bytes, void* stream);
 
+/* Per-class k-means centres of a bank (MIA 2023/stage2_unimodal_student/CL_utils/CRD_criterion_v10.py:84-92, :122-129: the
+ * reference copies every class's rows to the host and runs sklearn KMeans(n_clusters = num_pos - 1) on them, every forward).
+ * `rows` (device, int64) lists the bank rows class after class; class_offsets (HOST, int64 [n_classes + 1], class_offsets[0]
+ * == 0) delimits the classes; centres (device, fp32 [n_classes, k, D]) holds the current centres and is updated in place.
+ * The call enqueues `iterations` Lloyd iterations (sklearn's `_kmeans_single_lloyd`): every listed row goes to the centre of
+ * its class that minimises |c|^2 - 2 x.c (lowest index on ties), each centre becomes the mean of its rows (an empty cluster
+ * keeps its centre), and a class whose summed squared centre shift is <= tol[c] sets done[c] = 1 -- further iterations leave a
+ * finished class untouched, so iterations may be enqueued in batches and `done` read between batches (tol / done may be NULL:
+ * no stopping rule).  update == 0: assignment pass only -- centres stay, and the outputs below describe them.
+ * Outputs of the last pass, each optional: inertia [n_classes, k] (sum of squared distances of a centre's rows to it, before
+ * the update), counts [n_classes, k] (int64 rows per centre), row_dist [class_offsets[n_classes]] (squared distance of every
+ * listed row to its nearest centre -- the D^2 weights of a k-means++ initialisation).
+ * Sums are accumulated in a fixed order: the result is bit-reproducible.  D in {32, 64, 128, 256, 512}, k <=
+ * mml_crd_kmeans_max_clusters() (8), n_classes <= 32.  A row index outside [0, n_rows) raises MML_DEVERR_CRD_INDEX. */
+int32_t mml_crd_kmeans_max_clusters(void);
+int64_t mml_crd_kmeans_workspace_bytes(int32_t n_classes, int32_t k, int32_t D);
+int     mml_crd_kmeans_lloyd(const float* bank, int64_t n_rows, int32_t D, const int64_t* rows, const int64_t* class_offsets,
+                             int32_t n_classes, int32_t k, float* centres, const float* tol, int32_t iterations,
+                             int32_t update, int32_t* done, float* inertia, int64_t* counts, float* row_dist,
+                             void* workspace, size_t workspace_bytes, void* stream);
+
 /* Scores only (ContrastMemory.forward :41-49 [+ :62-63 when Z != NULL]).
  *   Z == NULL : out = exp(dot/T) (raw);  Z != NULL: out = exp(dot/T)/Z.
  *   sums      float[4] or NULL: {0, 0, sum raw side1, sum raw side2}

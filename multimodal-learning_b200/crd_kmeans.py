@@ -1,0 +1,112 @@
+"""Per-class k-means centres of a memory bank, on the device (csrc/crd_kmeans.cu, K13).
+
+The reference's pos_extra == "centers" with num_pos > 2 (`MIA 2023/stage2_unimodal_student/CL_utils/CRD_criterion_v10.py:84-92`
+for bank 1, `:122-129` for bank 2) copies every class's bank rows to the host and fits
+`sklearn.cluster.KMeans(n_clusters=num_pos - 1)` on them -- in every forward, with sklearn's randomly seeded k-means++
+initialisation, so the reference's own centres differ from run to run.  `class_kmeans` is the same estimator with its defaults
+(k-means++ initialisation by D^2 sampling, Lloyd iterations, `max_iter=300`, `tol=1e-4` scaled by the mean feature variance,
+one initialisation) as passes over the bank in HBM; given the same initial centres it reproduces sklearn's centres (the oracle
+and `tests/golden/crdkmeans_*` pin that), and its random draws come from a torch generator, so it is reproducible under a seed.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import _cabi
+
+
+class ClassRows:
+    """The bank rows of every class, class after class, on the bank's device (+ the class boundaries on the host)."""
+
+    def __init__(self, class_idx, device):
+        lists = [torch.as_tensor(np.asarray(c), dtype=torch.long).reshape(-1) for c in class_idx]
+        if not lists or any(r.numel() == 0 for r in lists):
+            raise RuntimeError("every class needs at least one row")
+        self.sizes = [int(r.numel()) for r in lists]
+        self.offsets = torch.tensor([0] + list(np.cumsum(self.sizes)), dtype=torch.int64)      # host
+        self.rows = torch.cat(lists).to(device)
+        self.n_classes = len(lists)
+        self.device = self.rows.device
+
+
+def lloyd(bank, cls: ClassRows, centres, *, iterations=1, update=True, tol=None, done=None, inertia=None, counts=None,
+          row_dist=None, workspace=None):
+    """`mml_crd_kmeans_lloyd`: `iterations` Lloyd iterations over the listed rows, centres [C, k, D] updated in place."""
+    if not bank.is_cuda:
+        raise RuntimeError("class k-means runs on CUDA tensors only")
+    n, D = bank.shape
+    C, k, Dc = centres.shape
+    if C != cls.n_classes or Dc != D:
+        raise RuntimeError(f"centres must be [{cls.n_classes}, k, {D}]; got {tuple(centres.shape)}")
+    lib = _cabi.lib()
+    if k > lib.mml_crd_kmeans_max_clusters():
+        raise NotImplementedError(f"at most {lib.mml_crd_kmeans_max_clusters()} centres per class (got {k})")
+    nbytes = lib.mml_crd_kmeans_workspace_bytes(C, k, D)
+    if nbytes <= 0:
+        raise NotImplementedError(f"class k-means: unsupported sizes classes={C} k={k} D={D}")
+    if workspace is None or workspace.numel() < nbytes:
+        workspace = torch.empty(nbytes, dtype=torch.uint8, device=bank.device)
+    _cabi.check(lib.mml_crd_kmeans_lloyd(
+        _cabi.dptr(bank, torch.float32), n, D, _cabi.dptr(cls.rows, torch.int64), _cabi.hptr(cls.offsets), C, k,
+        _cabi.dptr(centres, torch.float32), _cabi.dptr(tol, torch.float32), int(iterations), int(bool(update)),
+        _cabi.dptr(done, torch.int32), _cabi.dptr(inertia, torch.float32), _cabi.dptr(counts, torch.int64),
+        _cabi.dptr(row_dist, torch.float32), _cabi.dptr(workspace), workspace.numel(), _cabi.cur_stream(bank.device)),
+        "mml_crd_kmeans_lloyd")
+    return workspace
+
+
+def class_variance_tolerance(bank, cls: ClassRows, tol=1e-4, workspace=None):
+    """sklearn's `_tolerance` per class: tol * mean over features of the variance of the class's rows -> fp32 [C]."""
+    C, D = cls.n_classes, bank.shape[1]
+    mean = torch.zeros((C, 1, D), dtype=torch.float32, device=bank.device)
+    inertia = torch.empty((C, 1), dtype=torch.float32, device=bank.device)
+    ws = lloyd(bank, cls, mean, update=True, workspace=workspace)                 # one centre at 0 -> the class mean
+    lloyd(bank, cls, mean, update=False, inertia=inertia, workspace=ws)           # sum |x - mean|^2
+    sizes = torch.tensor(cls.sizes, dtype=torch.float32, device=bank.device)
+    return (inertia[:, 0] / (sizes * D) * tol).contiguous()
+
+
+def kmeans_plus_plus(bank, cls: ClassRows, k, generator=None, workspace=None):
+    """k-means++ initial centres [C, k, D]: the first centre of a class is one of its rows drawn uniformly, every further
+    one a row drawn with probability proportional to its squared distance to the nearest centre chosen so far."""
+    dev = bank.device
+    C, D = cls.n_classes, bank.shape[1]
+    first = [cls.rows[int(cls.offsets[c]) + torch.randint(cls.sizes[c], (1,), generator=generator, device=dev)] for c in range(C)]
+    centres = bank.index_select(0, torch.cat(first)).view(C, 1, D).repeat(1, k, 1).contiguous()   # duplicates do not change a min
+    if k == 1:
+        return centres
+    row_dist = torch.empty(cls.rows.numel(), dtype=torch.float32, device=dev)
+    for j in range(1, k):
+        workspace = lloyd(bank, cls, centres, update=False, row_dist=row_dist, workspace=workspace)
+        for c in range(C):
+            lo, hi = int(cls.offsets[c]), int(cls.offsets[c + 1])
+            cum = row_dist[lo:hi].double().cumsum(0)
+            u = torch.rand(1, generator=generator, device=dev, dtype=torch.float64) * cum[-1]
+            pick = torch.searchsorted(cum, u, right=True).clamp_(max=hi - lo - 1)
+            centres[c, j] = bank[cls.rows[lo + pick]].view(D)
+    return centres
+
+
+def class_kmeans(bank, cls: ClassRows, k, *, init=None, generator=None, max_iter=300, tol=1e-4, check_every=8, return_info=False):
+    """-> centres fp32 [C, k, D] (`KMeans(n_clusters=k).fit(rows of class c).cluster_centers_` for every class c).
+    init: optional initial centres [C, k, D] (else k-means++ from `generator`).  The `done` flags are read back every
+    `check_every` iterations -- the only host synchronisation."""
+    bank = bank.detach()
+    dev = bank.device
+    C = cls.n_classes
+    with torch.no_grad():
+        tol_c = class_variance_tolerance(bank, cls, tol)
+        centres = kmeans_plus_plus(bank, cls, k, generator) if init is None else init.to(device=dev, dtype=torch.float32).clone().contiguous()
+        done = torch.zeros(C, dtype=torch.int32, device=dev)
+        ws = None
+        iters = 0
+        while iters < max_iter:
+            step = min(check_every, max_iter - iters)
+            ws = lloyd(bank, cls, centres, iterations=step, tol=tol_c, done=done, workspace=ws)
+            iters += step
+            if bool(done.all()):
+                break
+    if return_info:
+        return centres, {"done": done, "tol": tol_c, "iterations_enqueued": iters}
+    return centres

@@ -18,6 +18,7 @@ from torch import nn
 
 from . import _cabi
 from . import crd as _crd
+from . import crd_kmeans as _kmeans
 from .crd import Normalize
 from .crd_select import Embed  # single Linear + L2 (CRD_criterion_v10.py:316-329)  # noqa: F401
 
@@ -139,11 +140,15 @@ class ContrastMemory(_crd.ContrastMemory):
         self._pending = weakref.WeakSet()
         self._row_labels = None
         self._inv_norms = None           # [2, n] 1/|row| of both banks: full pass once, then only the batch's rows per step
+        self._class_rows_dev = None      # crd_kmeans.ClassRows of `class_idx` on the banks' device ("centers")
+        self.kmeans_generator = None     # torch.Generator of the k-means++ draws (None = the device's default generator)
+        self.kmeans_init = None          # optional [2, n_classes, num_pos - 1, D]: fixed initial centres for banks 1 / 2
 
     def _apply(self, fn, *args, **kwargs):                  # no AliasMethod in this variant (idx is always supplied)
         out = nn.Module._apply(self, fn, *args, **kwargs)
         self._row_labels = None
         self._inv_norms = None
+        self._class_rows_dev = None
         return out
 
     def _load_from_state_dict(self, *args, **kwargs):
@@ -172,14 +177,22 @@ class ContrastMemory(_crd.ContrastMemory):
             self._row_labels = self.all_sample_labels.to(device=device, dtype=torch.int32)
         return self._row_labels
 
-    def _class_centers(self, bank, num_pos):
-        """:84-92 -- the mean of every class's rows (num_pos == 2).  k-means centres (num_pos > 2) are sklearn on the host
-        with a random initialisation in the reference and are not rebuilt here."""
-        if num_pos != 2:
-            raise NotImplementedError("pos_extra='centers' with num_pos > 2 runs sklearn KMeans on the host in the reference "
-                                      "(CRD_criterion_v10.py:89-92); only the class-mean case (num_pos == 2) is provided")
-        rows = [torch.as_tensor(np.asarray(c), dtype=torch.long, device=bank.device) for c in self.class_idx]
-        return torch.stack([bank.index_select(0, r).mean(0) for r in rows]).contiguous()
+    def _class_rows(self, device):
+        if self._class_rows_dev is None or self._class_rows_dev.device != device:
+            self._class_rows_dev = _kmeans.ClassRows(self.class_idx, device)
+        return self._class_rows_dev
+
+    def _class_centers(self, bank, num_pos, which=0):
+        """:84-92 -- [n_classes * (num_pos - 1), D]: the mean of every class's rows (num_pos == 2), or the num_pos - 1 k-means
+        centres of every class (num_pos > 2; sklearn KMeans on the host in the reference, `crd_kmeans.class_kmeans` here,
+        drawing its k-means++ initialisation from `self.kmeans_generator`, or started from `self.kmeans_init[which]`)."""
+        cls = self._class_rows(bank.device)
+        if num_pos == 2:
+            return torch.stack([bank.index_select(0, cls.rows[int(cls.offsets[c]):int(cls.offsets[c + 1])]).mean(0)
+                                for c in range(cls.n_classes)]).contiguous()
+        init = self.kmeans_init[which] if self.kmeans_init is not None else None
+        centres = _kmeans.class_kmeans(bank, cls, num_pos - 1, init=init, generator=self.kmeans_generator)
+        return centres.view(cls.n_classes * (num_pos - 1), bank.shape[1])
 
     def forward(self, num_pos, pos_extra, v1, v2, batch_label, y, idx=None):
         if not (v1.is_cuda and self.memory_v1.is_cuda):
@@ -206,13 +219,16 @@ class ContrastMemory(_crd.ContrastMemory):
             take1 = torch.cat((torch.arange(P, 2 * P, device=dev), torch.arange(2 * P, 2 * P + K, device=dev)))
             take2 = torch.cat((torch.arange(0, P, device=dev), torch.arange(2 * P, 2 * P + K, device=dev)))
         elif pos_extra == "centers":
-            c1 = self._class_centers(self.memory_v1, num_pos)
-            c2 = self._class_centers(self.memory_v2, num_pos)
+            c1 = self._class_centers(self.memory_v1, num_pos, 0)
+            c2 = self._class_centers(self.memory_v2, num_pos, 1)
             n_cls = len(self.class_idx)
             if n_cls != 3:
                 raise RuntimeError("pos_extra='centers' hard-codes 3 classes in the reference (one_hot(..., num_classes=3), :60)")
-            others = torch.tensor([[c for c in range(n_cls) if c != k] for k in range(n_cls)], device=dev)    # :60-61
-            center_cols = torch.cat((batch_label.view(B, 1), others.index_select(0, batch_label)), 1).contiguous()
+            # rows of the centre tables read per sample: [own class's num_pos-1 centres | the other two classes'] (:60-61, :94-99)
+            Q = num_pos - 1
+            order = torch.tensor([[k] + [c for c in range(n_cls) if c != k] for k in range(n_cls)], device=dev)
+            table = (order.view(n_cls, n_cls, 1) * Q + torch.arange(Q, device=dev)).view(n_cls, n_cls * Q)
+            center_cols = table.index_select(0, batch_label).contiguous()
             cols = idx
         else:
             raise RuntimeError(f"pos_extra must be 'neighbors' or 'centers'; got {pos_extra!r}")   # reference: NameError later
@@ -227,8 +243,8 @@ class ContrastMemory(_crd.ContrastMemory):
                 r1, r2 = r1.index_select(1, take1), r2.index_select(1, take2)
             else:
                 q1, q2 = raw_scores(_CenterBanks(self, c1, c2), center_cols)
-                r1 = torch.cat((q1[:, :1], r1, q1[:, 1:]), 1)
-                r2 = torch.cat((q2[:, :1], r2, q2[:, 1:]), 1)
+                r1 = torch.cat((q1[:, :Q], r1, q1[:, Q:]), 1)
+                r2 = torch.cat((q2[:, :Q], r2, q2[:, Q:]), 1)
             self.params[2] = r1.mean() * self.nLem
             self.params[3] = r2.mean() * self.nLem
             print("normalization constant Z_v1 is set to {:.1f}".format(self.params[2].item()))
@@ -250,8 +266,8 @@ class ContrastMemory(_crd.ContrastMemory):
             out_v1, out_v2 = o1.index_select(1, take1), o2.index_select(1, take2)
         else:
             q1, q2 = scores(_CenterBanks(self, c1, c2), center_cols, False)
-            out_v1 = torch.cat((q1[:, :1], o1, q1[:, 1:]), 1)      # [own centre | anchor + K negatives | other classes' centres]
-            out_v2 = torch.cat((q2[:, :1], o2, q2[:, 1:]), 1)
+            out_v1 = torch.cat((q1[:, :Q], o1, q1[:, Q:]), 1)      # [own centres | anchor + K negatives | other classes' centres]
+            out_v2 = torch.cat((q2[:, :Q], o2, q2[:, Q:]), 1)
         out_v1, out_v2 = out_v1.unsqueeze(2).contiguous(), out_v2.unsqueeze(2).contiguous()
         self._update(v1, v2, y)                                                                   # :135-150
         if pos_extra == "neighbors":

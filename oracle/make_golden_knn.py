@@ -32,8 +32,30 @@ def _import_reference():
         sys.path.remove(root)
 
 
+class _RecordingKMeans:
+    """Stands in for `KMeans` inside the reference module (CRD_criterion_v10.py:89-92): draws the k-means++ initial centres
+    itself (seeded), runs the real sklearn estimator from them, and keeps (init, centres) of every fit in call order."""
+    log = []
+    rng = np.random.RandomState(0)
+
+    def __init__(self, n_clusters):
+        self.k = n_clusters
+
+    def fit(self, X):
+        from sklearn.cluster import KMeans, kmeans_plusplus
+        init, _ = kmeans_plusplus(X, self.k, random_state=_RecordingKMeans.rng)
+        est = KMeans(n_clusters=self.k, init=init.copy(), n_init=1).fit(X)
+        self.cluster_centers_ = est.cluster_centers_
+        _RecordingKMeans.log.append((init.astype(np.float32), est.cluster_centers_.astype(np.float32), est.n_iter_))
+        return self
+
+
 def gen(mod_v10, name, *, pos_extra, B, s_dim, t_dim, D, P, K, n, steps=2, seed=2023):
     torch.manual_seed(seed)
+    record = pos_extra == "centers" and P > 2
+    if record:
+        mod_v10.KMeans = _RecordingKMeans
+        _RecordingKMeans.rng = np.random.RandomState(seed)
     rng = np.random.default_rng(seed)
     cls = rng.integers(0, 3, size=n)
     class_idx = [np.nonzero(cls == c)[0] for c in range(3)]
@@ -53,6 +75,7 @@ def gen(mod_v10, name, *, pos_extra, B, s_dim, t_dim, D, P, K, n, steps=2, seed=
         cidx[:, 0] = idx
         w = torch.rand(B) + 0.5
         mod.zero_grad()
+        _RecordingKMeans.log.clear()
         with contextlib.redirect_stdout(io.StringIO()), _cuda_is_identity():
             loss, sample_loss = mod(w, f_s, f_t, label, idx, cidx)
         loss.backward()
@@ -65,6 +88,12 @@ def gen(mod_v10, name, *, pos_extra, B, s_dim, t_dim, D, P, K, n, steps=2, seed=
                        p + "memory_v1": mod.contrast.memory_v1.clone(), p + "memory_v2": mod.contrast.memory_v2.clone()})
         if pos_extra == "neighbors":
             arrays[p + "sim_v1"], arrays[p + "sim_v2"] = captured["out"][2], captured["out"][3]
+        if record:                                           # fits in call order: bank 1 classes 0..2, then bank 2 classes 0..2
+            log = _RecordingKMeans.log
+            assert len(log) == 6
+            arrays[p + "kmeans_init"] = torch.from_numpy(np.stack([e[0] for e in log]).reshape(2, 3, P - 1, D))
+            arrays[p + "kmeans_centres"] = torch.from_numpy(np.stack([e[1] for e in log]).reshape(2, 3, P - 1, D))
+            arrays[p + "kmeans_iters"] = torch.tensor([e[2] for e in log])
         for k, v in mod.named_parameters():
             arrays[p + "grad." + k] = v.grad.clone()
     _save(name, dict(pos_extra=pos_extra, B=B, s_dim=s_dim, t_dim=t_dim, D=D, P=P, K=K, n=n, steps=steps, T=0.07, momentum=0.5),
@@ -78,6 +107,8 @@ def main():
     gen(m, "crdknn_p5_d128", pos_extra="neighbors", B=8, s_dim=24, t_dim=20, D=128, P=5, K=40, n=300, steps=3)
     gen(m, "crdknn_p1_d32", pos_extra="neighbors", B=5, s_dim=10, t_dim=12, D=32, P=1, K=20, n=140)
     gen(m, "crdknn_centers_d32", pos_extra="centers", B=6, s_dim=10, t_dim=12, D=32, P=2, K=20, n=150)
+    gen(m, "crdknn_kmeans_p4_d32", pos_extra="centers", B=6, s_dim=10, t_dim=12, D=32, P=4, K=20, n=600)
+    gen(m, "crdknn_kmeans_p3_d128", pos_extra="centers", B=8, s_dim=16, t_dim=12, D=128, P=3, K=30, n=480)
 
 
 if __name__ == "__main__":

@@ -92,5 +92,20 @@ if what in ("select", "all"):
                                                 _cabi.dptr(ids), _cabi.cur_stream(dev)), "route")
         torch.cuda.synchronize()
         print("route", world, chunk, "ok", int(counts.sum()) == Bq * cols, flush=True)
+if what in ("kmeans", "all"):
+    # per-class k-means centres: every feature width (CTA sizes 256 / 128 / 64), ragged classes, the stop flags
+    from multimodal_learning_b200 import crd_kmeans
+    for D, k, sizes in ((32, 8, (300, 17, 1000)), (128, 3, (1000, 777, 1)), (256, 4, (900, 31, 650)), (512, 2, (260, 100, 7))):
+        n = sum(sizes)
+        bank = torch.randn(n, D, device=dev)
+        perm = torch.randperm(n).numpy()
+        class_idx, at = [], 0
+        for m in sizes:
+            class_idx.append(perm[at:at + m])
+            at += m
+        cls = crd_kmeans.ClassRows(class_idx, dev)
+        centres, info = crd_kmeans.class_kmeans(bank, cls, k, max_iter=24, return_info=True)
+        torch.cuda.synchronize()
+        print("kmeans", D, k, "ok", bool(torch.isfinite(centres).all()), info["done"].tolist(), flush=True)
 pkg.check_device_errors()
 print("done", flush=True)

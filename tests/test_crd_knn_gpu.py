@@ -17,7 +17,7 @@ from conftest import rel_err
 pytestmark = pytest.mark.gpu
 TOL = 1e-4
 DEV = "cuda:0"
-CASES = ["crdknn_p3_d16", "crdknn_p5_d128", "crdknn_p1_d32", "crdknn_centers_d32"]
+CASES = ["crdknn_p3_d16", "crdknn_p5_d128", "crdknn_p1_d32", "crdknn_centers_d32", "crdknn_kmeans_p4_d32", "crdknn_kmeans_p3_d128"]
 
 
 @pytest.fixture(scope="module")
@@ -55,6 +55,8 @@ def test_crd_knn_module_matches_reference_golden(pkg, golden, name, capsys):
         f_t = g.t(p + "f_t", DEV).requires_grad_(True)
         pre1 = mod.contrast.memory_v1.clone()
         mod.zero_grad()
+        if c["pos_extra"] == "centers" and c["P"] > 2:      # the reference's k-means starts at random: same start as recorded
+            mod.contrast.kmeans_init = g.t(p + "kmeans_init", DEV)
         loss, sample_loss = mod(g.t(p + "sample_weights", DEV), f_s, f_t, g.t(p + "label", DEV), g.t(p + "idx", DEV),
                                 g.t(p + "contrast_idx", DEV))
         loss.backward()

@@ -282,7 +282,8 @@ def test_crd_reweighted_and_mono_variants_match_reference(golden, name):
 
 
 # ---- MIA 2023 stage-2 criterion (CRD_criterion_v10.py: KNN / class-centre positives), oracle/crd_knn_oracle.py ----
-KNN_CASES = ["crdknn_p3_d16", "crdknn_p5_d128", "crdknn_p1_d32", "crdknn_centers_d32"]
+KNN_CASES = ["crdknn_p3_d16", "crdknn_p5_d128", "crdknn_p1_d32", "crdknn_centers_d32", "crdknn_kmeans_p4_d32",
+             "crdknn_kmeans_p3_d128"]
 
 
 @pytest.mark.parametrize("name", KNN_CASES)
@@ -301,10 +302,19 @@ def test_crd_knn_variant_matches_reference(golden, name):
         for k in params:
             sd[k] = sd[k].detach().requires_grad_(True)
         pre1 = sd["contrast.memory_v1"].clone()
+        kmeans = c["pos_extra"] == "centers" and c["P"] > 2
+        if kmeans:                                          # the k-means restatement against sklearn's fits inside the reference
+            for b, bank in enumerate(("memory_v1", "memory_v2")):
+                for k in range(3):
+                    X = sd["contrast." + bank][torch.as_tensor(class_idx[k])].numpy()
+                    got, iters = ko.kmeans_lloyd(X, g.np(p + "kmeans_init")[b, k])
+                    assert iters == int(g.np(p + "kmeans_iters")[3 * b + k])
+                    assert np.abs(got - g.np(p + "kmeans_centres")[b, k]).max() < 2e-6
         loss, sample_loss, res = ko.crd_loss_v10(sd, class_idx, c["P"], c["pos_extra"], g.t(p + "sample_weights"), f_s, f_t,
-                                                 g.t(p + "label"), g.t(p + "idx"), g.t(p + "contrast_idx"), c["n"])
+                                                 g.t(p + "label"), g.t(p + "idx"), g.t(p + "contrast_idx"), c["n"],
+                                                 kmeans_init=g.t(p + "kmeans_init") if kmeans else None)
         loss.backward()
-        width = c["P"] + c["K"] if c["pos_extra"] == "neighbors" else 1 + (c["K"] + 1) + 2
+        width = c["P"] + c["K"] if c["pos_extra"] == "neighbors" else (c["P"] - 1) + (c["K"] + 1) + 2 * (c["P"] - 1)
         assert res[0].shape == (c["B"], width, 1)
         assert rel_err(res[0], g.t(p + "out_v1")) < FLOAT_TOL and rel_err(res[1], g.t(p + "out_v2")) < FLOAT_TOL
         if c["pos_extra"] == "neighbors":
