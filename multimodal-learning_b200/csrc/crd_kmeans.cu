@@ -8,7 +8,8 @@
 //   kmeans_assign_kernel  one pass over the listed bank rows (HBM-bound: every row is read exactly once).  A CTA belongs to one
 //                         class and holds that class's k centres in shared memory.  Eight lanes share a row (D/8 values each,
 //                         128-byte coalesced segments) and every group keeps kR rows in flight, so a centre chunk read from
-//                         shared memory is used 4 * kR times.  Scores are sklearn's E-step form |c|^2 - 2 x.c (lowest index wins
+//                         shared memory is used 4 * kR times; the next iteration's rows (and the row numbers of the one after)
+//                         are already in flight while this one is scored.  Scores are sklearn's E-step form |c|^2 - 2 x.c (lowest index wins
 //                         ties).  Every lane owns a private shared-memory accumulator per centre for its D/8 values: no atomics,
 //                         a fixed row -> lane mapping, fixed-order reductions afterwards -> bit-reproducible sums.
 //   kmeans_update_kernel  one CTA per centre adds the per-CTA partial sums in a fixed order, writes the new centre (an empty
@@ -48,11 +49,27 @@ struct KmArgs {
   int32_t D, k, C, update;
 };
 
-template <int kV, int kR>
-__global__ void __launch_bounds__(256) kmeans_assign_kernel(const KmArgs a) {
+// Rows in flight per 8-lane group and CTA size.  kV = D / 32 float4 per lane and row; kK = centres per class rounded up to
+// 2 / 4 / 8 (compile-time trip counts; the padding centres score +inf and are never chosen).  The lane-private accumulators
+// are kK * kV float4 per thread, which bounds the CTA size.
+template <int kV>
+struct KmRows {
+  static constexpr int value = kV <= 2 ? 4 : (kV == 4 ? 2 : 1);
+};
+__host__ __device__ constexpr int km_threads(int kV, int kK) {
+  int t = 512;
+  while (t > 64 && t * kK * kV * 16 > 180 * 1024) t /= 2;
+  return t;
+}
+
+template <int kV, int kK>
+__global__ void __launch_bounds__(km_threads(kV, kK)) kmeans_assign_kernel(const KmArgs a) {
   extern __shared__ float4 km_smem[];
   constexpr int D = 32 * kV;
-  const int threads = static_cast<int>(blockDim.x);
+  constexpr int kR = KmRows<kV>::value;
+  constexpr int kRowsIter = 4 * kR;
+  constexpr int threads = km_threads(kV, kK);
+  constexpr int nwarps = threads / 32;
   const int tid = static_cast<int>(threadIdx.x);
   const int warp = tid >> 5, lane = tid & 31, g = lane >> 3, l8 = lane & 7;
   const int cta = static_cast<int>(blockIdx.x);
@@ -62,14 +79,15 @@ __global__ void __launch_bounds__(256) kmeans_assign_kernel(const KmArgs a) {
   while (c + 1 < a.C && cta >= a.cta_begin[c + 1]) ++c;
   if (a.done != nullptr && a.done[c] != 0) return;
 
-  float4* sm_centre = km_smem;                                   // [k][kV * 8]
-  float* sm_cnorm = reinterpret_cast<float*>(sm_centre + kKmMaxK * kV * 8);   // [8]
-  float4* sm_acc = sm_centre + kKmMaxK * kV * 8 + 2;             // [k * kV][threads], lane-private
+  float4* sm_centre = km_smem;                                    // [kK][kV * 8]
+  float* sm_cnorm = reinterpret_cast<float*>(sm_centre + kK * kV * 8);   // [8]
+  float4* sm_acc = sm_centre + kK * kV * 8 + 2;                   // [kK * kV][threads], lane-private
   const float4* centre_g = reinterpret_cast<const float4*>(a.centres + static_cast<int64_t>(c) * k * D);
-  for (int i = tid; i < k * kV * 8; i += threads) sm_centre[i] = centre_g[i];
-  for (int i = 0; i < k * kV; ++i) sm_acc[i * threads + tid] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int i = tid; i < kK * kV * 8; i += threads) sm_centre[i] = i < k * kV * 8 ? centre_g[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+  for (int i = 0; i < kK * kV; ++i) sm_acc[i * threads + tid] = make_float4(0.f, 0.f, 0.f, 0.f);
   __syncthreads();
-  for (int j = warp; j < k; j += threads >> 5) {                  // |c_j|^2, a warp per centre
+  for (int j = warp; j < kK; j += nwarps) {                       // |c_j|^2, a warp per centre
     float s = 0.f;
     for (int i = lane; i < kV * 8; i += 32) {
       const float4 v = sm_centre[j * kV * 8 + i];
@@ -77,62 +95,80 @@ __global__ void __launch_bounds__(256) kmeans_assign_kernel(const KmArgs a) {
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(kFullMask, s, o);
-    if (lane == 0) sm_cnorm[j] = s;
+    if (lane == 0) sm_cnorm[j] = j < k ? s : __int_as_float(0x7f800000);
   }
   __syncthreads();
-  float cn[kKmMaxK];
+  float cn[kK];
 #pragma unroll
-  for (int j = 0; j < kKmMaxK; ++j) cn[j] = j < k ? sm_cnorm[j] : 0.f;
+  for (int j = 0; j < kK; ++j) cn[j] = sm_cnorm[j];
 
   // this CTA's contiguous slice of the class's row list, in whole warp-iterations of 4 * kR rows
   const int64_t m0 = a.row_begin[c], m1 = a.row_begin[c + 1];
   const int nctas = a.cta_begin[c + 1] - a.cta_begin[c];
-  constexpr int kRowsIter = 4 * kR;
   const int64_t iters = (m1 - m0 + kRowsIter - 1) / kRowsIter;
   const int64_t per = (iters + nctas - 1) / nctas;
   const int64_t it0 = per * (cta - a.cta_begin[c]);
   const int64_t it1 = it0 + per < iters ? it0 + per : iters;
-  const int nwarps = threads >> 5;
 
-  int32_t cnt[kKmMaxK];
-  float inr[kKmMaxK];
+  int32_t cnt[kK];
+  float inr[kK];
 #pragma unroll
-  for (int j = 0; j < kKmMaxK; ++j) cnt[j] = 0, inr[j] = 0.f;
+  for (int j = 0; j < kK; ++j) cnt[j] = 0, inr[j] = 0.f;
 
-  for (int64_t it = it0 + warp; it < it1; it += nwarps) {
+  // two-deep software pipeline: row numbers two iterations ahead, rows one iteration ahead
+  auto row_ids = [&](int64_t it, int64_t (&rid)[kR]) {
     const int64_t p0 = m0 + it * kRowsIter + g * kR;
-    float4 x[kR][kV];
-    bool valid[kR];
+#pragma unroll
+    for (int t = 0; t < kR; ++t) rid[t] = a.rows[p0 + t < m1 ? p0 + t : m0];
+  };
+  auto fetch = [&](const int64_t (&rid)[kR], float4 (&dst)[kR][kV]) {
 #pragma unroll
     for (int t = 0; t < kR; ++t) {
-      valid[t] = p0 + t < m1;
-      int64_t rid = a.rows[valid[t] ? p0 + t : m0];
-      if (rid < 0 || rid >= a.n) {                                // a bad row index: flag it, read row 0
+      int64_t r = rid[t];
+      if (r < 0 || r >= a.n) {                                    // a bad row number: flag it, read row 0
         flag_device_error(a.err, MML_DEVERR_CRD_INDEX);
-        rid = 0;
+        r = 0;
       }
-      const float* src = a.bank + rid * D + l8 * 4;
+      const float* src = a.bank + r * D + l8 * 4;
 #pragma unroll
-      for (int i = 0; i < kV; ++i) x[t][i] = ldg_stream_f4(src + i * 32);
+      for (int i = 0; i < kV; ++i) dst[t][i] = ldg_stream_f4(src + i * 32);
     }
-    float acc[kR][kKmMaxK], xx[kR];
+  };
+  int64_t rid[kR];
+  float4 xn[kR][kV];
+  int64_t it = it0 + warp;
+  if (it < it1) {
+    row_ids(it, rid);
+    fetch(rid, xn);
+    if (it + nwarps < it1) row_ids(it + nwarps, rid);
+  }
+  for (; it < it1; it += nwarps) {
+    float4 x[kR][kV];
+#pragma unroll
+    for (int t = 0; t < kR; ++t)
+#pragma unroll
+      for (int i = 0; i < kV; ++i) x[t][i] = xn[t][i];
+    if (it + nwarps < it1) {
+      fetch(rid, xn);
+      if (it + 2 * nwarps < it1) row_ids(it + 2 * nwarps, rid);
+    }
+    const int64_t p0 = m0 + it * kRowsIter + g * kR;
+    float acc[kR][kK], xx[kR];
 #pragma unroll
     for (int t = 0; t < kR; ++t) {
       xx[t] = 0.f;
 #pragma unroll
       for (int i = 0; i < kV; ++i) xx[t] = dot4(x[t][i], x[t][i], xx[t]);
 #pragma unroll
-      for (int j = 0; j < kKmMaxK; ++j) acc[t][j] = 0.f;
+      for (int j = 0; j < kK; ++j) acc[t][j] = 0.f;
     }
 #pragma unroll
-    for (int j = 0; j < kKmMaxK; ++j) {
-      if (j < k) {
+    for (int j = 0; j < kK; ++j) {
 #pragma unroll
-        for (int i = 0; i < kV; ++i) {
-          const float4 c4 = sm_centre[(j * kV + i) * 8 + l8];
+      for (int i = 0; i < kV; ++i) {
+        const float4 c4 = sm_centre[(j * kV + i) * 8 + l8];
 #pragma unroll
-          for (int t = 0; t < kR; ++t) acc[t][j] = dot4(x[t][i], c4, acc[t][j]);
-        }
+        for (int t = 0; t < kR; ++t) acc[t][j] = dot4(x[t][i], c4, acc[t][j]);
       }
     }
 #pragma unroll
@@ -141,8 +177,7 @@ __global__ void __launch_bounds__(256) kmeans_assign_kernel(const KmArgs a) {
       for (int t = 0; t < kR; ++t) {
         xx[t] += __shfl_xor_sync(kFullMask, xx[t], o);
 #pragma unroll
-        for (int j = 0; j < kKmMaxK; ++j)
-          if (j < k) acc[t][j] += __shfl_xor_sync(kFullMask, acc[t][j], o);
+        for (int j = 0; j < kK; ++j) acc[t][j] += __shfl_xor_sync(kFullMask, acc[t][j], o);
       }
     }
 #pragma unroll
@@ -150,18 +185,15 @@ __global__ void __launch_bounds__(256) kmeans_assign_kernel(const KmArgs a) {
       int best = 0;
       float bv = fmaf(-2.f, acc[t][0], cn[0]);
 #pragma unroll
-      for (int j = 1; j < kKmMaxK; ++j) {
+      for (int j = 1; j < kK; ++j) {
         const float v = fmaf(-2.f, acc[t][j], cn[j]);
-        if (j < k && v < bv) bv = v, best = j;
+        if (v < bv) bv = v, best = j;
       }
-      if (valid[t]) {
+      if (p0 + t < m1) {
         const float d = fmaxf(xx[t] + bv, 0.f);
-        if (l8 == 0) {
-          if (a.row_dist != nullptr) a.row_dist[p0 + t] = d;
+        if (l8 == 0 && a.row_dist != nullptr) a.row_dist[p0 + t] = d;
 #pragma unroll
-          for (int j = 0; j < kKmMaxK; ++j)
-            if (j == best) cnt[j] += 1, inr[j] += d;
-        }
+        for (int j = 0; j < kK; ++j) cnt[j] += j == best ? 1 : 0, inr[j] += j == best ? d : 0.f;
         float4* slot = sm_acc + best * kV * threads + tid;
 #pragma unroll
         for (int i = 0; i < kV; ++i) {
@@ -179,58 +211,76 @@ __global__ void __launch_bounds__(256) kmeans_assign_kernel(const KmArgs a) {
   for (int o = tid; o < k * kV * 8; o += threads) {
     const int ji = o >> 3, e8 = o & 7;
     float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int w = 0; w < nwarps; ++w)
-#pragma unroll
-      for (int gg = 0; gg < 4; ++gg) {
-        const float4 v = sm_acc[ji * threads + w * 32 + gg * 8 + e8];
-        s.x += v.x, s.y += v.y, s.z += v.z, s.w += v.w;
-      }
+#pragma unroll 4
+    for (int w = 0; w < nwarps * 4; ++w) {
+      const float4 v = sm_acc[ji * threads + w * 8 + e8];
+      s.x += v.x, s.y += v.y, s.z += v.z, s.w += v.w;
+    }
     out[o] = s;
   }
   __syncthreads();
   // counts and inertia: the group leaders' registers through the (now free) accumulator space
-  int32_t* sm_cnt = reinterpret_cast<int32_t*>(sm_acc);           // [k][threads / 8]
-  float* sm_inr = reinterpret_cast<float*>(sm_acc) + kKmMaxK * (threads >> 3);
+  constexpr int groups = threads / 8;
+  int32_t* sm_cnt = reinterpret_cast<int32_t*>(sm_acc);           // [kK][groups]
+  float* sm_inr = reinterpret_cast<float*>(sm_acc) + kK * groups;
   if (l8 == 0) {
 #pragma unroll
-    for (int j = 0; j < kKmMaxK; ++j)
-      if (j < k) sm_cnt[j * (threads >> 3) + (tid >> 3)] = cnt[j], sm_inr[j * (threads >> 3) + (tid >> 3)] = inr[j];
+    for (int j = 0; j < kK; ++j) sm_cnt[j * groups + (tid >> 3)] = cnt[j], sm_inr[j * groups + (tid >> 3)] = inr[j];
   }
   __syncthreads();
-  if (tid < k) {
+  for (int j = warp; j < k; j += nwarps) {                        // a warp per centre
     int32_t n_j = 0;
     float in_j = 0.f;
-    for (int q = 0; q < (threads >> 3); ++q) n_j += sm_cnt[tid * (threads >> 3) + q], in_j += sm_inr[tid * (threads >> 3) + q];
-    a.part_count[cta * k + tid] = n_j;
-    a.part_inertia[cta * k + tid] = in_j;
+    for (int q = lane; q < groups; q += 32) n_j += sm_cnt[j * groups + q], in_j += sm_inr[j * groups + q];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) n_j += __shfl_xor_sync(kFullMask, n_j, o), in_j += __shfl_xor_sync(kFullMask, in_j, o);
+    if (lane == 0) a.part_count[cta * k + j] = n_j, a.part_inertia[cta * k + j] = in_j;
   }
 }
 
-// One CTA per (class, centre), D / 4 threads.
-__global__ void kmeans_update_kernel(const KmArgs a) {
+// One CTA of 256 threads per (class, centre): D / 4 element lanes x 256 / (D / 4) slices of the class's CTAs.
+__global__ void __launch_bounds__(256) kmeans_update_kernel(const KmArgs a) {
   const int c = static_cast<int>(blockIdx.x) / a.k, j = static_cast<int>(blockIdx.x) % a.k;
-  const int tid = static_cast<int>(threadIdx.x);
+  const int tid = static_cast<int>(threadIdx.x), warp = tid >> 5, lane = tid & 31;
   const int D = a.D, k = a.k;
   if (a.done != nullptr && a.done[c] != 0) return;
-  __shared__ float sm_red[32];
-  __shared__ int64_t sm_count;
+  __shared__ float4 sm_slice[256];
+  __shared__ float sm_red[8];
+  __shared__ int32_t sm_cnt[8];
+  __shared__ double sm_inr[8];
   const int b0 = a.cta_begin[c], b1 = a.cta_begin[c + 1];
+  {                                                               // rows and inertia of this centre (the grid has <= 256 CTAs)
+    int32_t n_t = 0;
+    double in_t = 0.0;
+    if (b0 + tid < b1) n_t = a.part_count[(b0 + tid) * k + j], in_t = static_cast<double>(a.part_inertia[(b0 + tid) * k + j]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) n_t += __shfl_xor_sync(kFullMask, n_t, o), in_t += __shfl_xor_sync(kFullMask, in_t, o);
+    if (lane == 0) sm_cnt[warp] = n_t, sm_inr[warp] = in_t;
+  }
+  __syncthreads();
+  int64_t n_j = 0;
+  double in_j = 0.0;
+#pragma unroll
+  for (int w = 0; w < 8; ++w) n_j += sm_cnt[w], in_j += sm_inr[w];
   if (tid == 0) {
-    int64_t n_j = 0;
-    double in_j = 0.0;
-    for (int b = b0; b < b1; ++b) n_j += a.part_count[b * k + j], in_j += static_cast<double>(a.part_inertia[b * k + j]);
-    sm_count = n_j;
     if (a.counts != nullptr) a.counts[c * k + j] = n_j;
     if (a.inertia != nullptr) a.inertia[c * k + j] = static_cast<float>(in_j);
   }
-  __syncthreads();
   if (a.update == 0) return;
-  const int64_t n_j = sm_count;
+  const int lanes = D / 4, slices = 256 / lanes;                  // D in 32..512 -> 8..128 lanes, 32..2 slices
+  const int e = tid % lanes, sl = tid / lanes;
+  float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
+  for (int b = b0 + sl; b < b1; b += slices) {
+    const float4 v = *reinterpret_cast<const float4*>(a.part_sum + (static_cast<int64_t>(b) * k + j) * D + e * 4);
+    s.x += v.x, s.y += v.y, s.z += v.z, s.w += v.w;
+  }
+  sm_slice[tid] = s;
+  __syncthreads();
   float d2 = 0.f;
-  if (tid * 4 < D) {
-    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int b = b0; b < b1; ++b) {
-      const float4 v = *reinterpret_cast<const float4*>(a.part_sum + (static_cast<int64_t>(b) * k + j) * D + tid * 4);
+  if (tid < lanes) {
+    for (int q = 1; q < slices; ++q) {
+      const float4 v = sm_slice[q * lanes + tid];
       s.x += v.x, s.y += v.y, s.z += v.z, s.w += v.w;
     }
     float4* dst = reinterpret_cast<float4*>(a.centres + (static_cast<int64_t>(c) * k + j) * D + tid * 4);
@@ -246,11 +296,12 @@ __global__ void kmeans_update_kernel(const KmArgs a) {
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) d2 += __shfl_xor_sync(kFullMask, d2, o);
-  if ((tid & 31) == 0) sm_red[tid >> 5] = d2;
+  if (lane == 0) sm_red[warp] = d2;
   __syncthreads();
   if (tid == 0) {
     float tot = 0.f;
-    for (int w = 0; w < (static_cast<int>(blockDim.x) + 31) / 32; ++w) tot += sm_red[w];
+#pragma unroll
+    for (int w = 0; w < 8; ++w) tot += sm_red[w];
     a.shift[c * k + j] = tot;
     __threadfence();
     if (atomicAdd(a.arrive + c, 1) == k - 1) {                    // the class's last centre: stop rule of _kmeans_single_lloyd
@@ -284,14 +335,29 @@ KmPlan make_km_plan(int32_t C, int32_t k, int32_t D) {
   return p;
 }
 
-template <int kV, int kR>
-int launch_assign(const KmArgs& a, int grid, int threads, cudaStream_t st) {
-  const size_t smem = sizeof(float4) * (kKmMaxK * kV * 8 + 2 + static_cast<size_t>(a.k) * kV * threads);
+template <int kV, int kK>
+int launch_assign(const KmArgs& a, int grid, cudaStream_t st) {
+  constexpr int threads = km_threads(kV, kK);
+  constexpr size_t smem = sizeof(float4) * (kK * kV * 8 + 2 + static_cast<size_t>(kK) * kV * threads);
   if (smem > 48 * 1024)                                           // per device and per call: the attribute is device state
-    MML_CUDA(cudaFuncSetAttribute(kmeans_assign_kernel<kV, kR>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-  kmeans_assign_kernel<kV, kR><<<grid, threads, smem, st>>>(a);
+    MML_CUDA(cudaFuncSetAttribute(kmeans_assign_kernel<kV, kK>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  kmeans_assign_kernel<kV, kK><<<grid, threads, smem, st>>>(a);
   return check_launch("kmeans_assign_kernel");
 }
+
+template <int kV>
+int launch_assign_k(const KmArgs& a, int grid, cudaStream_t st) {
+  if (a.k <= 2) return launch_assign<kV, 2>(a, grid, st);
+  if (a.k <= 4) return launch_assign<kV, 4>(a, grid, st);
+  return launch_assign<kV, 8>(a, grid, st);
+}
+
+int km_threads_for(int kV, int k) {
+  const int kK = k <= 2 ? 2 : (k <= 4 ? 4 : 8);
+  return km_threads(kV, kK);
+}
+
+int km_rows_iter(int kV) { return 4 * (kV <= 2 ? 4 : (kV == 4 ? 2 : 1)); }
 
 }  // namespace
 }  // namespace mml
@@ -325,9 +391,8 @@ extern "C" int mml_crd_kmeans_lloyd(const float* bank, int64_t n, int32_t D, con
     MML_REQUIRE(class_offsets[c + 1] > class_offsets[c], MML_ERR_INVALID_ARG, "crd_kmeans_lloyd: class %d has no rows", c);
   if (iterations == 0) return MML_OK;
 
-  // rows in flight per 8-lane group and CTA size by feature width (the lane-private accumulators are k * D / 2 bytes per thread)
-  const int threads = D <= 128 ? 256 : (D == 256 ? 128 : 64);
-  const int rows_iter = 4 * (D <= 128 ? 4 : (D == 256 ? 2 : 1));
+  const int threads = km_threads_for(D / 32, k);
+  const int rows_iter = km_rows_iter(D / 32);
   KmArgs a{};
   a.bank = bank, a.rows = rows, a.centres = centres, a.tol = tol, a.done = done, a.inertia = inertia, a.counts = counts;
   a.row_dist = row_dist;
@@ -363,14 +428,14 @@ extern "C" int mml_crd_kmeans_lloyd(const float* bank, int64_t n, int32_t D, con
   for (int it = 0; it < iterations; ++it) {
     int rc;
     switch (D) {
-      case 32: rc = launch_assign<1, 4>(a, grid, threads, st); break;
-      case 64: rc = launch_assign<2, 4>(a, grid, threads, st); break;
-      case 128: rc = launch_assign<4, 4>(a, grid, threads, st); break;
-      case 256: rc = launch_assign<8, 2>(a, grid, threads, st); break;
-      default: rc = launch_assign<16, 1>(a, grid, threads, st); break;
+      case 32: rc = launch_assign_k<1>(a, grid, st); break;
+      case 64: rc = launch_assign_k<2>(a, grid, st); break;
+      case 128: rc = launch_assign_k<4>(a, grid, st); break;
+      case 256: rc = launch_assign_k<8>(a, grid, st); break;
+      default: rc = launch_assign_k<16>(a, grid, st); break;
     }
     if (rc != MML_OK) return rc;
-    kmeans_update_kernel<<<n_classes * k, D / 4 < 32 ? 32 : D / 4, 0, st>>>(a);
+    kmeans_update_kernel<<<n_classes * k, 256, 0, st>>>(a);
     rc = check_launch("kmeans_update_kernel");
     if (rc != MML_OK) return rc;
   }
