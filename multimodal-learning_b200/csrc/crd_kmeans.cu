@@ -52,9 +52,9 @@ struct KmArgs {
 // Rows in flight per 8-lane group and CTA size.  kV = D / 32 float4 per lane and row; kK = centres per class rounded up to
 // 2 / 4 / 8 (compile-time trip counts; the padding centres score +inf and are never chosen).  The lane-private accumulators
 // are kK * kV float4 per thread, which bounds the CTA size.
-template <int kV>
-struct KmRows {
-  static constexpr int value = kV <= 2 ? 4 : (kV == 4 ? 2 : 1);
+template <int kV, int kK>
+struct KmRows {      // kV == 4 with 8 centres runs 256-thread CTAs: registers for 4 rows, and twice the reuse of a centre chunk
+  static constexpr int value = kV <= 2 ? 4 : (kV == 4 ? (kK == 8 ? 4 : 2) : 1);
 };
 __host__ __device__ constexpr int km_threads(int kV, int kK) {
   int t = 512;
@@ -66,7 +66,7 @@ template <int kV, int kK>
 __global__ void __launch_bounds__(km_threads(kV, kK)) kmeans_assign_kernel(const KmArgs a) {
   extern __shared__ float4 km_smem[];
   constexpr int D = 32 * kV;
-  constexpr int kR = KmRows<kV>::value;
+  constexpr int kR = KmRows<kV, kK>::value;
   constexpr int kRowsIter = 4 * kR;
   constexpr int threads = km_threads(kV, kK);
   constexpr int nwarps = threads / 32;
@@ -357,7 +357,7 @@ int km_threads_for(int kV, int k) {
   return km_threads(kV, kK);
 }
 
-int km_rows_iter(int kV) { return 4 * (kV <= 2 ? 4 : (kV == 4 ? 2 : 1)); }
+int km_rows_iter(int kV, int k) { return 4 * (kV <= 2 ? 4 : (kV == 4 ? (k > 4 ? 4 : 2) : 1)); }
 
 }  // namespace
 }  // namespace mml
@@ -392,7 +392,7 @@ extern "C" int mml_crd_kmeans_lloyd(const float* bank, int64_t n, int32_t D, con
   if (iterations == 0) return MML_OK;
 
   const int threads = km_threads_for(D / 32, k);
-  const int rows_iter = km_rows_iter(D / 32);
+  const int rows_iter = km_rows_iter(D / 32, k);
   KmArgs a{};
   a.bank = bank, a.rows = rows, a.centres = centres, a.tol = tol, a.done = done, a.inertia = inertia, a.counts = counts;
   a.row_dist = row_dist;
