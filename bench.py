@@ -20,6 +20,8 @@ Beside it, in the same run and under the same clock sampler:
                   batch 8192, K 16384, n 1M) and config 1 (BilinearFusion 32x32 -> 64, batch 64), with their CPU baselines
   knn_positives   full-bank KNN positives of the stage-2 criterion (CRD_criterion_v10): 1024 anchors against 1M x 128 rows,
                   TF32 tcgen05 pass + exact re-score, vs the TF32 peak; sklearn on the host cores beside it
+  kmeans_centres  per-class k-means centres of the same criterion (pos_extra "centers", num_pos > 2): one Lloyd iteration over
+                  a 1M x 128 bank vs the HBM copy peak, the whole fit, sklearn KMeans on the host for one class beside it
   strong_scaling  BASELINE config 5 as stated: ONE problem (16M x 128 banks, global batch 8192) on N GPUs
   e2e*            `e2e` = host int64 contrast_idx uploaded every step (the reference's loader contract);
                   `e2e_device_idx` = contrast_idx drawn on the GPU inside the graph (InstanceSampler), `e2e_int32_idx`
@@ -507,6 +509,63 @@ def knn_section(dev, peaks, cpu_anchors):
                                    "kind": "reference", "same_neighbours": bool(torch.equal(order.to(dev), idx[:cpu_anchors])),
                                    "sample": f"{cpu_anchors} of {B} anchors: sklearn cosine_similarity against all {n} rows, class "
                                              f"mask, torch.sort (CRD_criterion_v10.py:69-74), scaled x{B // cpu_anchors}"}
+        except Exception as e:                       # noqa: BLE001
+            out["cpu_baseline_error"] = f"{type(e).__name__}: {e}"
+    return out
+
+
+def kmeans_section(dev, peaks, cpu):
+    """N4, pos_extra == "centers" with num_pos > 2 (`MIA 2023/.../CRD_criterion_v10.py:84-92`): per-class k-means centres of
+    a 1M x 128 bank, 3 classes, 3 centres each.  One Lloyd iteration (assign pass over the bank + update) timed with CUDA
+    events against the measured HBM copy peak, the whole fit (tolerance, k-means++ start, iterations until every class
+    stops) by wall clock; beside it the reference's own way for ONE class (rows copied to the host, sklearn KMeans)."""
+    from multimodal_learning_b200 import crd_kmeans as km
+    n, D, k = 1 << 20, 128, 3
+    gen = torch.Generator(device=dev).manual_seed(0)
+    modes = torch.randn(24, D, device=dev, generator=gen)
+    bank = torch.nn.functional.normalize(modes[torch.randint(0, 24, (n,), device=dev, generator=gen)]
+                                         + 0.5 * torch.randn(n, D, device=dev, generator=gen), dim=1).contiguous()
+    labels = torch.randint(0, 3, (n,), device=dev, generator=gen)
+    class_idx = [torch.nonzero(labels == c).flatten().cpu().numpy() for c in range(3)]
+    cls = km.ClassRows(class_idx, dev)
+    gen.manual_seed(1)
+    centres = km.kmeans_plus_plus(bank, cls, k, gen)
+    ws = km.lloyd(bank, cls, centres, iterations=3)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 20
+    e0.record()
+    km.lloyd(bank, cls, centres, iterations=reps, workspace=ws)
+    e1.record()
+    torch.cuda.synchronize()
+    it_ms = e0.elapsed_time(e1) / reps
+    gen.manual_seed(1)
+    km.class_kmeans(bank, cls, k, generator=gen)
+    gen.manual_seed(1)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    fit, info = km.class_kmeans(bank, cls, k, generator=gen, return_info=True)
+    torch.cuda.synchronize()
+    fit_ms = (time.perf_counter() - t0) * 1e3
+    nbytes = n * (4 * D + 8)
+    peak = float(peaks["hbm_gbs"])
+    out = {"workload": f"per-class k-means centres: {n} x {D} bank, 3 classes, {k} centres per class",
+           "lloyd_iteration_ms": it_ms, "fit_ms": fit_ms, "iterations_enqueued": info["iterations_enqueued"],
+           "converged": bool(info["done"].all()), "bound": "hbm", "achieved": nbytes / it_ms / 1e6, "peak": peak, "unit": "GB/s",
+           "frac": nbytes / it_ms / 1e6 / peak, "bytes": nbytes, "own_kernel_launches": 2,
+           "note": "one iteration = kmeans_assign_kernel (every listed row read once: 4 D + 8 bytes) + kmeans_update_kernel; "
+                   "the assign pass is bound by shared-memory wavefronts, see profiles/r2_kmeans_ncu.txt"}
+    if cpu:
+        try:
+            from sklearn.cluster import KMeans
+            t0 = time.perf_counter()
+            X = bank.index_select(0, cls.rows[:cls.sizes[0]]).cpu().numpy()
+            est = KMeans(n_clusters=k).fit(X)
+            dt = time.perf_counter() - t0
+            out["cpu_baseline"] = {"value": dt * 1e3 * 3, "unit": "ms per bank", "cores": host_cores(), "kind": "reference",
+                                   "iterations": int(est.n_iter_),
+                                   "sample": f"class 0 only ({X.shape[0]} rows): index_select -> .cpu().numpy() -> sklearn KMeans(n_clusters={k}).fit "
+                                             "(CRD_criterion_v10.py:86-92), scaled x3 classes"}
         except Exception as e:                       # noqa: BLE001
             out["cpu_baseline_error"] = f"{type(e).__name__}: {e}"
     return out
@@ -1053,6 +1112,12 @@ def run_gpu_arm(args):
             knn = knn_section(dev, peaks, 0 if args.no_cpu else 8)
         except Exception as e:                       # noqa: BLE001
             errors["knn_positives"] = f"{type(e).__name__}: {e}"
+    kmeans = None
+    if world == 1 and not args.no_kron:
+        try:
+            kmeans = kmeans_section(dev, peaks, not args.no_cpu)
+        except Exception as e:                       # noqa: BLE001
+            errors["kmeans_centres"] = f"{type(e).__name__}: {e}"
     if sampler:
         sampler.stop()
 
@@ -1112,6 +1177,8 @@ def run_gpu_arm(args):
         line["fused_step"] = fused
     if knn is not None:
         line["knn_positives"] = knn
+    if kmeans is not None:
+        line["kmeans_centres"] = kmeans
     if errors:
         line["errors"] = errors
     print(json.dumps(line))

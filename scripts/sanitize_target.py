@@ -95,7 +95,7 @@ if what in ("select", "all"):
 if what in ("kmeans", "all"):
     # per-class k-means centres: every feature width (CTA sizes 256 / 128 / 64), ragged classes, the stop flags
     from multimodal_learning_b200 import crd_kmeans
-    for D, k, sizes in ((32, 8, (300, 17, 1000)), (128, 3, (1000, 777, 1)), (256, 4, (900, 31, 650)), (512, 2, (260, 100, 7))):
+    for D, k, sizes in ((32, 8, (300, 17, 1000)), (128, 3, (1000, 777, 1)), (128, 7, (2000, 900, 1500)), (64, 5, (700, 300, 90)), (256, 4, (900, 31, 650)), (512, 2, (260, 100, 7))):
         n = sum(sizes)
         bank = torch.randn(n, D, device=dev)
         perm = torch.randperm(n).numpy()
