@@ -188,6 +188,10 @@ class ContrastMemory(_crd.ContrastMemory):
         drawing its k-means++ initialisation from `self.kmeans_generator`, or started from `self.kmeans_init[which]`)."""
         cls = self._class_rows(bank.device)
         if num_pos == 2:
+            if bank.shape[1] in (32, 64, 128, 256, 512):     # one pass over the bank: a single centre at 0 moves to the class mean
+                mean = torch.zeros((cls.n_classes, 1, bank.shape[1]), dtype=torch.float32, device=bank.device)
+                _kmeans.lloyd(bank.detach(), cls, mean)
+                return mean.view(cls.n_classes, bank.shape[1])
             return torch.stack([bank.index_select(0, cls.rows[int(cls.offsets[c]):int(cls.offsets[c + 1])]).mean(0)
                                 for c in range(cls.n_classes)]).contiguous()
         init = self.kmeans_init[which] if self.kmeans_init is not None else None
