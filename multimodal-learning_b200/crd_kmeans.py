@@ -95,6 +95,8 @@ def class_kmeans(bank, cls: ClassRows, k, *, init=None, generator=None, max_iter
     bank = bank.detach()
     dev = bank.device
     C = cls.n_classes
+    if init is not None and tuple(init.shape) != (C, k, bank.shape[1]):
+        raise RuntimeError(f"init must be [{C}, {k}, {bank.shape[1]}]; got {tuple(init.shape)}")
     with torch.no_grad():
         tol_c = class_variance_tolerance(bank, cls, tol)
         centres = kmeans_plus_plus(bank, cls, k, generator) if init is None else init.to(device=dev, dtype=torch.float32).clone().contiguous()
