@@ -171,29 +171,64 @@ __global__ void __launch_bounds__(km_threads(kV, kK)) kmeans_assign_kernel(const
         for (int t = 0; t < kR; ++t) acc[t][j] = dot4(x[t][i], c4, acc[t][j]);
       }
     }
+    // Sum over the group's 8 lanes.  A plain butterfly would move every value three times; instead the first level(s) hand
+    // half of the ROWS to each half of the group (a lane sends the partial sums of the rows it gives up and keeps the
+    // others), so afterwards lanes [t * 8 / kR, (t + 1) * 8 / kR) own row t: kR = 2: 5 + 2 * 5 shuffles instead of 30.
+    float w[kK + 1];
+    int my_t = 0;
+    if constexpr (kR == 4) {
+      const bool h2 = (l8 & 4) != 0, h1 = (l8 & 2) != 0;
+      float u[2][kK + 1];
 #pragma unroll
-    for (int o = 1; o < 8; o <<= 1) {
+      for (int s2 = 0; s2 < 2; ++s2) {
 #pragma unroll
-      for (int t = 0; t < kR; ++t) {
-        xx[t] += __shfl_xor_sync(kFullMask, xx[t], o);
-#pragma unroll
-        for (int j = 0; j < kK; ++j) acc[t][j] += __shfl_xor_sync(kFullMask, acc[t][j], o);
+        for (int j = 0; j < kK; ++j)
+          u[s2][j] = (h2 ? acc[2 + s2][j] : acc[s2][j]) + __shfl_xor_sync(kFullMask, h2 ? acc[s2][j] : acc[2 + s2][j], 4);
+        u[s2][kK] = (h2 ? xx[2 + s2] : xx[s2]) + __shfl_xor_sync(kFullMask, h2 ? xx[s2] : xx[2 + s2], 4);
       }
+#pragma unroll
+      for (int j = 0; j <= kK; ++j) w[j] = (h1 ? u[1][j] : u[0][j]) + __shfl_xor_sync(kFullMask, h1 ? u[0][j] : u[1][j], 2);
+#pragma unroll
+      for (int j = 0; j <= kK; ++j) w[j] += __shfl_xor_sync(kFullMask, w[j], 1);
+      my_t = (h2 ? 2 : 0) + (h1 ? 1 : 0);
+    } else if constexpr (kR == 2) {
+      const bool h2 = (l8 & 4) != 0;
+#pragma unroll
+      for (int j = 0; j < kK; ++j) w[j] = (h2 ? acc[1][j] : acc[0][j]) + __shfl_xor_sync(kFullMask, h2 ? acc[0][j] : acc[1][j], 4);
+      w[kK] = (h2 ? xx[1] : xx[0]) + __shfl_xor_sync(kFullMask, h2 ? xx[0] : xx[1], 4);
+#pragma unroll
+      for (int o = 2; o > 0; o >>= 1)
+#pragma unroll
+        for (int j = 0; j <= kK; ++j) w[j] += __shfl_xor_sync(kFullMask, w[j], o);
+      my_t = h2 ? 1 : 0;
+    } else {
+#pragma unroll
+      for (int j = 0; j < kK; ++j) w[j] = acc[0][j];
+      w[kK] = xx[0];
+#pragma unroll
+      for (int o = 4; o > 0; o >>= 1)
+#pragma unroll
+        for (int j = 0; j <= kK; ++j) w[j] += __shfl_xor_sync(kFullMask, w[j], o);
     }
+    // the nearest centre of the row this lane owns ...
+    int best_m = 0;
+    float bv = fmaf(-2.f, w[0], cn[0]);
+#pragma unroll
+    for (int j = 1; j < kK; ++j) {
+      const float v = fmaf(-2.f, w[j], cn[j]);
+      if (v < bv) bv = v, best_m = j;
+    }
+    if (p0 + my_t < m1) {
+      const float d = fmaxf(w[kK] + bv, 0.f);
+      if ((l8 & (8 / kR - 1)) == 0 && a.row_dist != nullptr) a.row_dist[p0 + my_t] = d;
+#pragma unroll
+      for (int j = 0; j < kK; ++j) cnt[j] += j == best_m ? 1 : 0, inr[j] += j == best_m ? d : 0.f;
+    }
+    // ... and every lane adds its D / 8 values of each of the group's rows to that row's centre
 #pragma unroll
     for (int t = 0; t < kR; ++t) {
-      int best = 0;
-      float bv = fmaf(-2.f, acc[t][0], cn[0]);
-#pragma unroll
-      for (int j = 1; j < kK; ++j) {
-        const float v = fmaf(-2.f, acc[t][j], cn[j]);
-        if (v < bv) bv = v, best = j;
-      }
+      const int best = kR == 1 ? best_m : __shfl_sync(kFullMask, best_m, (lane & 24) | (t * (8 / kR)));
       if (p0 + t < m1) {
-        const float d = fmaxf(xx[t] + bv, 0.f);
-        if (l8 == 0 && a.row_dist != nullptr) a.row_dist[p0 + t] = d;
-#pragma unroll
-        for (int j = 0; j < kK; ++j) cnt[j] += j == best ? 1 : 0, inr[j] += j == best ? d : 0.f;
         float4* slot = sm_acc + best * kV * threads + tid;
 #pragma unroll
         for (int i = 0; i < kV; ++i) {
@@ -203,6 +238,15 @@ __global__ void __launch_bounds__(km_threads(kV, kK)) kmeans_assign_kernel(const
         }
       }
     }
+  }
+  // counts / inertia were kept by the lanes that own a row: fold the owners of a group into its lane 0 (fixed order)
+  if constexpr (kR >= 2) {
+#pragma unroll
+    for (int j = 0; j < kK; ++j) cnt[j] += __shfl_xor_sync(kFullMask, cnt[j], 4), inr[j] += __shfl_xor_sync(kFullMask, inr[j], 4);
+  }
+  if constexpr (kR == 4) {
+#pragma unroll
+    for (int j = 0; j < kK; ++j) cnt[j] += __shfl_xor_sync(kFullMask, cnt[j], 2), inr[j] += __shfl_xor_sync(kFullMask, inr[j], 2);
   }
   __syncthreads();
 
