@@ -5,7 +5,7 @@
 //                        KMeans(n_clusters = num_pos - 1).fit(feature).cluster_centers_
 // by Lloyd iterations on the device.  One iteration is two launches:
 //
-//   kmeans_assign_kernel  one pass over the listed bank rows (HBM-bound: every row is read exactly once).  A CTA belongs to one
+//   kmeans_assign_kernel  one pass over the listed bank rows (every row is read exactly once: 4 D + 8 bytes per row).  A CTA belongs to one
 //                         class and holds that class's k centres in shared memory.  Eight lanes share a row (D/8 values each,
 //                         128-byte coalesced segments) and every group keeps kR rows in flight, so a centre chunk read from
 //                         shared memory is used 4 * kR times; the next iteration's rows (and the row numbers of the one after)
