@@ -150,7 +150,7 @@ int     mml_crd_knn_positives(const float* bank, int64_t n_rows, int32_t D, cons
 /* Per-class k-means centres of a bank (MIA 2023/stage2_unimodal_student/CL_utils/CRD_criterion_v10.py:84-92, :122-129: the
  * reference copies every class's rows to the host and runs sklearn KMeans(n_clusters = num_pos - 1) on them, every forward).
  * `rows` (device, int64) lists the bank rows class after class; class_offsets (HOST, int64 [n_classes + 1], class_offsets[0]
- * == 0) delimits the classes; centres (device, fp32 [n_classes, k, D]) holds the current centres and is updated in place.
+ * == 0, non-decreasing: a class may have no rows in this list when the bank is sharded) delimits the classes; centres (device, fp32 [n_classes, k, D]) holds the current centres and is updated in place.
  * The call enqueues `iterations` Lloyd iterations (sklearn's `_kmeans_single_lloyd`): every listed row goes to the centre of
  * its class that minimises |c|^2 - 2 x.c (lowest index on ties), each centre becomes the mean of its rows (an empty cluster
  * keeps its centre), and a class whose summed squared centre shift is <= tol[c] sets done[c] = 1 -- further iterations leave a
@@ -158,14 +158,15 @@ int     mml_crd_knn_positives(const float* bank, int64_t n_rows, int32_t D, cons
  * no stopping rule).  update == 0: assignment pass only -- centres stay, and the outputs below describe them.
  * Outputs of the last pass, each optional: inertia [n_classes, k] (sum of squared distances of a centre's rows to it, before
  * the update), counts [n_classes, k] (int64 rows per centre), row_dist [class_offsets[n_classes]] (squared distance of every
- * listed row to its nearest centre -- the D^2 weights of a k-means++ initialisation).
+ * listed row to its nearest centre -- the D^2 weights of a k-means++ initialisation), sums [n_classes, k, D] (the rows of
+ * every centre added up: with counts, what ranks that each hold a shard of the rows all-reduce before they divide).
  * Sums are accumulated in a fixed order: the result is bit-reproducible.  D in {32, 64, 128, 256, 512}, k <=
  * mml_crd_kmeans_max_clusters() (8), n_classes <= 32.  A row index outside [0, n_rows) raises MML_DEVERR_CRD_INDEX. */
 int32_t mml_crd_kmeans_max_clusters(void);
 int64_t mml_crd_kmeans_workspace_bytes(int32_t n_classes, int32_t k, int32_t D);
 int     mml_crd_kmeans_lloyd(const float* bank, int64_t n_rows, int32_t D, const int64_t* rows, const int64_t* class_offsets,
                              int32_t n_classes, int32_t k, float* centres, const float* tol, int32_t iterations,
-                             int32_t update, int32_t* done, float* inertia, int64_t* counts, float* row_dist,
+                             int32_t update, int32_t* done, float* inertia, int64_t* counts, float* sums, float* row_dist,
                              void* workspace, size_t workspace_bytes, void* stream);
 
 /* Scores only (ContrastMemory.forward :41-49 [+ :62-63 when Z != NULL]).

@@ -35,7 +35,7 @@ _SIGNATURES = {
     "mml_crd_sort_columns": (ctypes.c_int, [_P, c_int64, c_int64, c_int64, c_int32, c_int32, c_int32, c_int64, _P, c_int64, _P]),
     "mml_crd_kmeans_max_clusters": (c_int32, []),
     "mml_crd_kmeans_workspace_bytes": (c_int64, [c_int32, c_int32, c_int32]),
-    "mml_crd_kmeans_lloyd": (ctypes.c_int, [_P, c_int64, c_int32, _P, _P, c_int32, c_int32, _P, _P, c_int32, c_int32, _P, _P, _P, _P,
+    "mml_crd_kmeans_lloyd": (ctypes.c_int, [_P, c_int64, c_int32, _P, _P, c_int32, c_int32, _P, _P, c_int32, c_int32, _P, _P, _P, _P, _P,
                                             _P, ctypes.c_size_t, _P]),
     "mml_crd_knn_max_positives": (c_int32, []),
     "mml_crd_knn_workspace_bytes": (c_int64, [c_int64, c_int64, c_int32]),

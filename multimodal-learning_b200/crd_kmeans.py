@@ -19,9 +19,9 @@ from . import _cabi
 class ClassRows:
     """The bank rows of every class, class after class, on the bank's device (+ the class boundaries on the host)."""
 
-    def __init__(self, class_idx, device):
+    def __init__(self, class_idx, device, allow_empty=False):
         lists = [torch.as_tensor(np.asarray(c), dtype=torch.long).reshape(-1) for c in class_idx]
-        if not lists or any(r.numel() == 0 for r in lists):
+        if not lists or (not allow_empty and any(r.numel() == 0 for r in lists)) or sum(r.numel() for r in lists) == 0:
             raise RuntimeError("every class needs at least one row")
         self.sizes = [int(r.numel()) for r in lists]
         self.offsets = torch.tensor([0] + list(np.cumsum(self.sizes)), dtype=torch.int64)      # host
@@ -31,7 +31,7 @@ class ClassRows:
 
 
 def lloyd(bank, cls: ClassRows, centres, *, iterations=1, update=True, tol=None, done=None, inertia=None, counts=None,
-          row_dist=None, workspace=None):
+          sums=None, row_dist=None, workspace=None):
     """`mml_crd_kmeans_lloyd`: `iterations` Lloyd iterations over the listed rows, centres [C, k, D] updated in place."""
     if not bank.is_cuda:
         raise RuntimeError("class k-means runs on CUDA tensors only")
@@ -51,7 +51,7 @@ def lloyd(bank, cls: ClassRows, centres, *, iterations=1, update=True, tol=None,
         _cabi.dptr(bank, torch.float32), n, D, _cabi.dptr(cls.rows, torch.int64), _cabi.hptr(cls.offsets), C, k,
         _cabi.dptr(centres, torch.float32), _cabi.dptr(tol, torch.float32), int(iterations), int(bool(update)),
         _cabi.dptr(done, torch.int32), _cabi.dptr(inertia, torch.float32), _cabi.dptr(counts, torch.int64),
-        _cabi.dptr(row_dist, torch.float32), _cabi.dptr(workspace), workspace.numel(), _cabi.cur_stream(bank.device)),
+        _cabi.dptr(sums, torch.float32), _cabi.dptr(row_dist, torch.float32), _cabi.dptr(workspace), workspace.numel(), _cabi.cur_stream(bank.device)),
         "mml_crd_kmeans_lloyd")
     return workspace
 
@@ -108,6 +108,94 @@ def class_kmeans(bank, cls: ClassRows, k, *, init=None, generator=None, max_iter
             ws = lloyd(bank, cls, centres, iterations=step, tol=tol_c, done=done, workspace=ws)
             iters += step
             if bool(done.all()):
+                break
+    if return_info:
+        return centres, {"done": done, "tol": tol_c, "iterations_enqueued": iters}
+    return centres
+
+
+def sharded_class_kmeans(bank_local, cls_local: ClassRows, k, *, group=None, init=None, generator=None, max_iter=300, tol=1e-4,
+                         check_every=8, return_info=False):
+    """`class_kmeans` over a bank whose rows are sharded across the ranks of `group`: `bank_local` is this rank's shard and
+    `cls_local` lists ITS rows by class with local row numbers (`ClassRows(..., allow_empty=True)`: a class may be absent from
+    a shard).  Bank rows never cross the wire: every Lloyd iteration each rank runs the assign pass over its shard, the ranks
+    all-reduce the per-centre sums and counts ([C, k, D + 1] doubles) and apply the same update and stop rule; the k-means++
+    draws are made by rank 0, the rank that owns the drawn row supplies it.  Returns the same centres on every rank."""
+    import torch.distributed as dist
+    bank = bank_local.detach()
+    dev = bank.device
+    C, D = cls_local.n_classes, bank.shape[1]
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    src = dist.get_global_rank(group, 0) if group is not None else 0
+    cls = cls_local
+    with torch.no_grad():
+        sizes = torch.tensor(cls.sizes, dtype=torch.float64, device=dev)
+        dist.all_reduce(sizes, group=group)
+        if bool((sizes < 1).any()):
+            raise RuntimeError("every class needs at least one row on some rank")
+        # sklearn's tolerance: class mean, then the summed squared distance to it, both reduced over the shards
+        mean = torch.zeros((C, 1, D), dtype=torch.float32, device=dev)
+        sums1 = torch.empty((C, 1, D), dtype=torch.float32, device=dev)
+        ws = lloyd(bank, cls, mean, update=False, sums=sums1)
+        tot = sums1.double()
+        dist.all_reduce(tot, group=group)
+        mean = (tot / sizes.view(C, 1, 1)).float().contiguous()
+        inertia = torch.empty((C, 1), dtype=torch.float32, device=dev)
+        ws = lloyd(bank, cls, mean, update=False, inertia=inertia, workspace=ws)
+        spread = inertia[:, 0].double()
+        dist.all_reduce(spread, group=group)
+        tol_c = (spread / (sizes * D) * tol).float().contiguous()
+
+        def draw(weights):
+            """One row per class, drawn with probability proportional to `weights` (per listed local row) over ALL shards."""
+            cums = [weights[int(cls.offsets[c]):int(cls.offsets[c + 1])].double().cumsum(0) for c in range(C)]
+            local = torch.stack([cm[-1] if cm.numel() else torch.zeros((), dtype=torch.float64, device=dev) for cm in cums])
+            totals = torch.empty((world, C), dtype=torch.float64, device=dev)
+            dist.all_gather_into_tensor(totals, local.contiguous(), group=group)
+            u = torch.rand(C, generator=generator, device=dev, dtype=torch.float64)
+            dist.broadcast(u, src=src, group=group)
+            upto = totals.cumsum(0)                                       # [world, C]
+            target = u * upto[-1]
+            rows = torch.zeros((C, D), dtype=torch.float32, device=dev)
+            for c in range(C):
+                owner = torch.searchsorted(upto[:, c].contiguous(), target[c:c + 1], right=True).clamp_(max=world - 1)
+                if cums[c].numel() == 0:
+                    continue
+                before = upto[rank - 1, c] if rank > 0 else torch.zeros((), dtype=torch.float64, device=dev)
+                pick = torch.searchsorted(cums[c], (target[c:c + 1] - before).clamp_(min=0), right=True).clamp_(max=cums[c].numel() - 1)
+                row = bank[cls.rows[int(cls.offsets[c]) + pick]].view(D)
+                rows[c] = torch.where(owner == rank, row, torch.zeros_like(row))
+            dist.all_reduce(rows, group=group)
+            return rows
+
+        if init is None:
+            n_listed = cls.rows.numel()
+            centres = draw(torch.ones(n_listed, dtype=torch.float32, device=dev)).view(C, 1, D).repeat(1, k, 1).contiguous()
+            row_dist = torch.empty(n_listed, dtype=torch.float32, device=dev)
+            for j in range(1, k):
+                ws = lloyd(bank, cls, centres, update=False, row_dist=row_dist, workspace=ws)
+                centres[:, j] = draw(row_dist)
+        else:
+            if tuple(init.shape) != (C, k, D):
+                raise RuntimeError(f"init must be [{C}, {k}, {D}]; got {tuple(init.shape)}")
+            centres = init.to(device=dev, dtype=torch.float32).clone().contiguous()
+
+        done = torch.zeros(C, dtype=torch.int32, device=dev)
+        sums = torch.zeros((C, k, D), dtype=torch.float32, device=dev)
+        counts = torch.zeros((C, k), dtype=torch.int64, device=dev)
+        iters = 0
+        while iters < max_iter:
+            ws = lloyd(bank, cls, centres, update=False, done=done, sums=sums, counts=counts, workspace=ws)
+            buf = torch.cat((sums.double(), counts.double().unsqueeze(2)), 2).contiguous()
+            dist.all_reduce(buf, group=group)
+            n_j = buf[:, :, D:]
+            new = torch.where(n_j > 0, buf[:, :, :D] / n_j.clamp(min=1), centres.double()).float()      # an empty cluster keeps its centre
+            shift = ((new - centres) ** 2).sum((1, 2))
+            frozen = done.bool()
+            centres = torch.where(frozen.view(C, 1, 1), centres, new).contiguous()
+            done = (frozen | (shift <= tol_c)).int()
+            iters += 1
+            if iters % check_every == 0 and bool(done.all()):
                 break
     if return_info:
         return centres, {"done": done, "tol": tol_c, "iterations_enqueued": iters}

@@ -36,6 +36,7 @@ struct KmArgs {
   int32_t* done;                     // [C] or null
   float* inertia;                    // [C, k] or null
   int64_t* counts;                   // [C, k] or null
+  float* sums;                       // [C, k, D] or null: the rows of every centre, summed (for a reduction across shards)
   float* row_dist;                   // [m] or null
   float* part_sum;                   // [grid, k, D]
   float* part_inertia;               // [grid, k]
@@ -310,7 +311,7 @@ __global__ void __launch_bounds__(256) kmeans_update_kernel(const KmArgs a) {
     if (a.counts != nullptr) a.counts[c * k + j] = n_j;
     if (a.inertia != nullptr) a.inertia[c * k + j] = static_cast<float>(in_j);
   }
-  if (a.update == 0) return;
+  if (a.update == 0 && a.sums == nullptr) return;
   const int lanes = D / 4, slices = 256 / lanes;                  // D in 32..512 -> 8..128 lanes, 32..2 slices
   const int e = tid % lanes, sl = tid / lanes;
   float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -327,17 +328,21 @@ __global__ void __launch_bounds__(256) kmeans_update_kernel(const KmArgs a) {
       const float4 v = sm_slice[q * lanes + tid];
       s.x += v.x, s.y += v.y, s.z += v.z, s.w += v.w;
     }
-    float4* dst = reinterpret_cast<float4*>(a.centres + (static_cast<int64_t>(c) * k + j) * D + tid * 4);
-    const float4 old = *dst;
-    float4 nw = old;
-    if (n_j > 0) {                                                // an empty cluster keeps its centre
-      const float inv = 1.f / static_cast<float>(n_j);
-      nw = make_float4(s.x * inv, s.y * inv, s.z * inv, s.w * inv);
+    if (a.sums != nullptr) *reinterpret_cast<float4*>(a.sums + (static_cast<int64_t>(c) * k + j) * D + tid * 4) = s;
+    if (a.update != 0) {
+      float4* dst = reinterpret_cast<float4*>(a.centres + (static_cast<int64_t>(c) * k + j) * D + tid * 4);
+      const float4 old = *dst;
+      float4 nw = old;
+      if (n_j > 0) {                                              // an empty cluster keeps its centre
+        const float inv = 1.f / static_cast<float>(n_j);
+        nw = make_float4(s.x * inv, s.y * inv, s.z * inv, s.w * inv);
+      }
+      const float ex = nw.x - old.x, ey = nw.y - old.y, ez = nw.z - old.z, ew = nw.w - old.w;
+      d2 = ex * ex + ey * ey + ez * ez + ew * ew;
+      *dst = nw;
     }
-    const float ex = nw.x - old.x, ey = nw.y - old.y, ez = nw.z - old.z, ew = nw.w - old.w;
-    d2 = ex * ex + ey * ey + ez * ez + ew * ew;
-    *dst = nw;
   }
+  if (a.update == 0) return;
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) d2 += __shfl_xor_sync(kFullMask, d2, o);
   if (lane == 0) sm_red[warp] = d2;
@@ -417,7 +422,7 @@ extern "C" int64_t mml_crd_kmeans_workspace_bytes(int32_t n_classes, int32_t k, 
 
 extern "C" int mml_crd_kmeans_lloyd(const float* bank, int64_t n, int32_t D, const int64_t* rows, const int64_t* class_offsets,
                                     int32_t n_classes, int32_t k, float* centres, const float* tol, int32_t iterations, int32_t update,
-                                    int32_t* done, float* inertia, int64_t* counts, float* row_dist, void* workspace,
+                                    int32_t* done, float* inertia, int64_t* counts, float* sums, float* row_dist, void* workspace,
                                     size_t workspace_bytes, void* stream) {
   MML_REQUIRE(bank && rows && class_offsets && centres && workspace, MML_ERR_INVALID_ARG, "crd_kmeans_lloyd: null pointer");
   MML_REQUIRE(n >= 1 && iterations >= 0, MML_ERR_INVALID_ARG, "crd_kmeans_lloyd: bad sizes");
@@ -426,19 +431,20 @@ extern "C" int mml_crd_kmeans_lloyd(const float* bank, int64_t n, int32_t D, con
   MML_REQUIRE(k >= 1 && k <= kKmMaxK, MML_ERR_UNSUPPORTED, "crd_kmeans_lloyd: 1 <= clusters per class <= %d (got %d)", kKmMaxK, k);
   MML_REQUIRE(n_classes >= 1 && n_classes <= kKmMaxClasses, MML_ERR_UNSUPPORTED, "crd_kmeans_lloyd: 1 <= classes <= %d (got %d)",
               kKmMaxClasses, n_classes);
-  MML_REQUIRE(aligned16(bank) && aligned16(centres) && aligned16(workspace), MML_ERR_INVALID_ARG,
-              "crd_kmeans_lloyd: bank / centres / workspace must be 16-byte aligned");
+  MML_REQUIRE(aligned16(bank) && aligned16(centres) && aligned16(workspace) && aligned16(sums), MML_ERR_INVALID_ARG,
+              "crd_kmeans_lloyd: bank / centres / sums / workspace must be 16-byte aligned");
   const KmPlan p = make_km_plan(n_classes, k, D);
   MML_REQUIRE(workspace_bytes >= p.total, MML_ERR_WORKSPACE, "crd_kmeans_lloyd: workspace too small (%zu < %zu)", workspace_bytes, p.total);
   MML_REQUIRE(class_offsets[0] == 0, MML_ERR_INVALID_ARG, "crd_kmeans_lloyd: class_offsets[0] must be 0");
-  for (int c = 0; c < n_classes; ++c)
-    MML_REQUIRE(class_offsets[c + 1] > class_offsets[c], MML_ERR_INVALID_ARG, "crd_kmeans_lloyd: class %d has no rows", c);
+  for (int c = 0; c < n_classes; ++c)      // a class may be empty HERE (its rows live on other shards), the list as a whole may not
+    MML_REQUIRE(class_offsets[c + 1] >= class_offsets[c], MML_ERR_INVALID_ARG, "crd_kmeans_lloyd: class_offsets must not decrease (class %d)", c);
+  MML_REQUIRE(class_offsets[n_classes] >= 1, MML_ERR_INVALID_ARG, "crd_kmeans_lloyd: no rows listed");
   if (iterations == 0) return MML_OK;
 
   const int threads = km_threads_for(D / 32, k);
   const int rows_iter = km_rows_iter(D / 32, k);
   KmArgs a{};
-  a.bank = bank, a.rows = rows, a.centres = centres, a.tol = tol, a.done = done, a.inertia = inertia, a.counts = counts;
+  a.bank = bank, a.rows = rows, a.centres = centres, a.tol = tol, a.done = done, a.inertia = inertia, a.counts = counts, a.sums = sums;
   a.row_dist = row_dist;
   uint8_t* ws = static_cast<uint8_t*>(workspace);
   a.part_sum = reinterpret_cast<float*>(ws + p.off_sum);

@@ -44,7 +44,7 @@ def _bank(n, D, sizes, seed, clustered=0):
 
 
 def _numpy_step(X, class_idx, centres):
-    new, counts, inertia, dist = centres.copy(), [], [], []
+    new, counts, inertia, dist, sums = centres.copy(), [], [], [], np.zeros(centres.shape)
     for c, rows in enumerate(class_idx):
         x = X[rows].astype(np.float64)
         cen = centres[c].astype(np.float64)
@@ -57,7 +57,8 @@ def _numpy_step(X, class_idx, centres):
         for j in range(cen.shape[0]):
             if (lab == j).any():
                 new[c, j] = x[lab == j].mean(0)
-    return new, np.stack(counts), np.stack(inertia), np.concatenate(dist)
+                sums[c, j] = x[lab == j].sum(0)
+    return new, np.stack(counts), np.stack(inertia), np.concatenate(dist), sums
 
 
 @pytest.mark.parametrize("name", ["crdknn_kmeans_p4_d32", "crdknn_kmeans_p3_d128"])
@@ -83,7 +84,7 @@ def test_one_lloyd_iteration_matches_numpy(km, D, k, sizes):
     X, class_idx = _bank(n, D, sizes, seed=D + k, clustered=k)
     rng = np.random.default_rng(1)
     init = np.stack([X[rng.choice(r, k, replace=len(r) < k)] for r in class_idx])
-    want, counts, inertia, dist = _numpy_step(X, class_idx, init)
+    want, counts, inertia, dist, sums = _numpy_step(X, class_idx, init)
     cls = km.ClassRows(class_idx, DEV)
     bank = torch.from_numpy(X).to(DEV)
     centres = torch.from_numpy(init).to(DEV).contiguous()
@@ -96,11 +97,13 @@ def test_one_lloyd_iteration_matches_numpy(km, D, k, sizes):
     assert np.abs(centres.cpu().numpy() - want).max() < 1e-5
     assert np.abs(got_d.cpu().numpy() - dist).max() < 1e-4 * max(1.0, dist.max())
     assert np.abs(got_in.cpu().numpy() - inertia).max() < 1e-4 * max(1.0, inertia.max())
-    # assignment-only pass: centres stay, outputs describe them
-    before = centres.clone()
-    km.lloyd(bank, cls, centres, update=False, counts=got_n)
-    assert torch.equal(before, centres)
-    assert int(got_n.sum()) == sum(sizes)
+    # assignment-only pass: centres stay, outputs describe them (same start again: the sums that shards would all-reduce)
+    centres = torch.from_numpy(init).to(DEV).contiguous()
+    got_s = torch.empty((C, k, D), device=DEV)
+    km.lloyd(bank, cls, centres, update=False, counts=got_n, sums=got_s)
+    assert torch.equal(torch.from_numpy(init).to(DEV), centres)
+    assert np.array_equal(got_n.cpu().numpy(), counts)
+    assert np.abs(got_s.cpu().numpy() - sums).max() < 1e-5 * max(1.0, np.abs(sums).max())
 
 
 def test_kmeans_is_bit_reproducible_and_a_fixed_point(km):

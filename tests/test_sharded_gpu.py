@@ -55,3 +55,17 @@ def test_sharded_knn_positives_equal_single_bank(tmp_path):
                        capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
     assert out.read_text().startswith("ok")
+
+
+def test_sharded_class_kmeans_equals_single_bank(tmp_path):
+    """N4 "centers" over the sharded bank: per-shard assign pass + all-reduced sums == `class_kmeans` over the whole bank."""
+    import torch
+    world = min(torch.cuda.device_count(), 4)
+    if world < 2:
+        pytest.skip("needs >= 2 GPUs")
+    out = tmp_path / "res.txt"
+    port = 29700 + os.getpid() % 90
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "_sharded_kmeans_worker.py"), str(world), str(port), str(out)],
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+    assert out.read_text().startswith("ok")
