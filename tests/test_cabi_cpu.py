@@ -50,6 +50,27 @@ def test_kernels_refuse_cpu_tensors():
         am.draw(8)                       # no CPU fallback
 
 
+def test_class_rows_host_logic_and_kmeans_refuses_cpu_tensors():
+    """The class row lists of the k-means centres (crd_kmeans.ClassRows) and the limits the C ABI reports, without a GPU."""
+    km = pkg.crd_kmeans
+    cls = km.ClassRows([[4, 1, 9], np.array([0, 2]), torch.tensor([3])], "cpu")
+    assert cls.n_classes == 3 and cls.sizes == [3, 2, 1]
+    assert cls.offsets.tolist() == [0, 3, 5, 6] and cls.offsets.dtype == torch.int64
+    assert cls.rows.tolist() == [4, 1, 9, 0, 2, 3]
+    with pytest.raises(RuntimeError):
+        km.ClassRows([[0, 1], []], "cpu")                                 # a class without rows
+    shard = km.ClassRows([[0, 1], []], "cpu", allow_empty=True)         # ... unless it lives on another shard
+    assert shard.sizes == [2, 0] and shard.offsets.tolist() == [0, 2, 2]
+    with pytest.raises(RuntimeError):
+        km.ClassRows([[], []], "cpu", allow_empty=True)
+    lib = _cabi.lib()
+    assert lib.mml_crd_kmeans_max_clusters() == 8
+    assert lib.mml_crd_kmeans_workspace_bytes(3, 3, 128) > 0
+    assert lib.mml_crd_kmeans_workspace_bytes(3, 9, 128) == 0 and lib.mml_crd_kmeans_workspace_bytes(33, 3, 128) == 0
+    with pytest.raises(RuntimeError, match="CUDA tensors only"):
+        km.lloyd(torch.zeros(6, 32), cls, torch.zeros(3, 2, 32))         # no CPU fallback
+
+
 def test_alias_build_host_bit_exact(golden):
     g = golden("alias")
     for c in g.cfg["cases"]:
