@@ -109,6 +109,7 @@ def main():
     gen(m, "crdknn_centers_d32", pos_extra="centers", B=6, s_dim=10, t_dim=12, D=32, P=2, K=20, n=150)
     gen(m, "crdknn_kmeans_p4_d32", pos_extra="centers", B=6, s_dim=10, t_dim=12, D=32, P=4, K=20, n=600)
     gen(m, "crdknn_kmeans_p3_d128", pos_extra="centers", B=8, s_dim=16, t_dim=12, D=128, P=3, K=30, n=480)
+    gen(m, "crdknn_kmeans_p6_d64", pos_extra="centers", B=6, s_dim=12, t_dim=10, D=64, P=6, K=20, n=450)
 
 
 if __name__ == "__main__":

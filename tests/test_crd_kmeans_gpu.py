@@ -61,7 +61,7 @@ def _numpy_step(X, class_idx, centres):
     return new, np.stack(counts), np.stack(inertia), np.concatenate(dist), sums
 
 
-@pytest.mark.parametrize("name", ["crdknn_kmeans_p4_d32", "crdknn_kmeans_p3_d128"])
+@pytest.mark.parametrize("name", ["crdknn_kmeans_p4_d32", "crdknn_kmeans_p3_d128", "crdknn_kmeans_p6_d64"])
 def test_kmeans_from_recorded_start_lands_on_sklearn_centres(km, golden, name):
     g = golden(name)
     c = g.cfg

@@ -17,7 +17,8 @@ from conftest import rel_err
 pytestmark = pytest.mark.gpu
 TOL = 1e-4
 DEV = "cuda:0"
-CASES = ["crdknn_p3_d16", "crdknn_p5_d128", "crdknn_p1_d32", "crdknn_centers_d32", "crdknn_kmeans_p4_d32", "crdknn_kmeans_p3_d128"]
+CASES = ["crdknn_p3_d16", "crdknn_p5_d128", "crdknn_p1_d32", "crdknn_centers_d32", "crdknn_kmeans_p4_d32", "crdknn_kmeans_p3_d128",
+         "crdknn_kmeans_p6_d64"]
 
 
 @pytest.fixture(scope="module")

@@ -283,7 +283,7 @@ def test_crd_reweighted_and_mono_variants_match_reference(golden, name):
 
 # ---- MIA 2023 stage-2 criterion (CRD_criterion_v10.py: KNN / class-centre positives), oracle/crd_knn_oracle.py ----
 KNN_CASES = ["crdknn_p3_d16", "crdknn_p5_d128", "crdknn_p1_d32", "crdknn_centers_d32", "crdknn_kmeans_p4_d32",
-             "crdknn_kmeans_p3_d128"]
+             "crdknn_kmeans_p3_d128", "crdknn_kmeans_p6_d64"]
 
 
 @pytest.mark.parametrize("name", KNN_CASES)
